@@ -1,0 +1,175 @@
+"""ctypes mirror of include/bidinet_b200.h's POD structs plus the reference's defaults.
+
+The default values restate the four reference ``LayerDesc`` constructors
+(sdr/PredictiveRSDR.h:32-41, sdr/IPredictiveRSDR.h:35-45,
+neo/PredictiveHierarchy.h:34-44, neo/Agent.h:49-64) and the public hyper-parameter
+members of the hierarchy objects (sdr/IPredictiveRSDR.h:101-105, neo/Agent.h:137-144).
+``_columnGamma`` / ``_columnGammaLambda`` are never initialised by the reference
+(neo/Agent.h:25-26,130-131); this build defaults them to 0.99 / 0.95 explicitly.
+"""
+import ctypes as C
+
+KWINNERS, ITERATIVE, NEO_HIERARCHY, NEO_AGENT = 0, 1, 2, 3
+VARIANT_NAMES = {KWINNERS: "kwinners", ITERATIVE: "iterative",
+                 NEO_HIERARCHY: "neo_hierarchy", NEO_AGENT: "neo_agent"}
+COLUMN_ACTIONS = 3
+
+ARRAY_NAMES = [
+    "VIS_INPUT", "VIS_RECON",
+    "HID_THRESHOLD", "HID_STATE", "HID_STATE_PREV", "HID_ACTIVATION", "HID_RECON",
+    "HID_SPIKE", "HID_SPIKE_PREV",
+    "FF_W", "REC_W", "LAT_W", "FF_TRACE", "REC_TRACE",
+    "P_STATE", "P_STATE_PREV", "P_ACTIVATION", "P_ACTIVATION_PREV", "P_BASELINE",
+    "FB_W", "PRED_W",
+    "COL_INPUT", "COL_RECON_ERR", "COL_FF_W", "COL_LAT_W",
+    "COL_THRESHOLD", "COL_ACTIVATION", "COL_SPIKE", "COL_SPIKE_PREV", "COL_STATE",
+    "COL_Q_W", "COL_Q_TRACE", "COL_ACT_STATE", "COL_ACT_EXPL", "COL_ACT_W", "COL_ACT_TRACE",
+    "COL_PREV_VALUE", "PREDICTION",
+]
+ARRAY = {n: i for i, n in enumerate(ARRAY_NAMES)}
+# arrays that hold a per-unit connection list (bidi_conn_counts is defined for them)
+LIST_ARRAYS = ("FF_W", "REC_W", "LAT_W", "FB_W", "PRED_W", "COL_INPUT")
+
+
+class LayerDesc(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int),
+        ("r_ff", C.c_int), ("r_rec", C.c_int), ("r_lat", C.c_int), ("r_pred", C.c_int), ("r_fb", C.c_int),
+        ("learn_ff", C.c_float), ("learn_rec", C.c_float), ("learn_lat", C.c_float),
+        ("learn_threshold", C.c_float),
+        ("learn_fb", C.c_float), ("learn_pred", C.c_float),
+        ("sparsity", C.c_float),
+        ("avg_surprise_decay", C.c_float), ("attention_factor", C.c_float),
+        ("iter_settle", C.c_int), ("iter_measure", C.c_int),
+        ("leak", C.c_float), ("lambda_", C.c_float),
+        ("weight_decay", C.c_float), ("max_weight_delta", C.c_float),
+        ("baseline_decay", C.c_float), ("sensitivity", C.c_float),
+        ("col_cells", C.c_int), ("col_iter", C.c_int),
+        ("col_sparsity", C.c_float), ("col_leak", C.c_float),
+        ("col_gamma", C.c_float), ("col_gamma_lambda", C.c_float),
+        ("col_alpha_ff", C.c_float), ("col_alpha_lat", C.c_float), ("col_alpha_threshold", C.c_float),
+        ("col_alpha_q", C.c_float), ("col_alpha_action", C.c_float),
+        ("col_expl_stddev", C.c_float), ("col_expl_break", C.c_float),
+    ]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int),
+        ("in_width", C.c_int), ("in_height", C.c_int),
+        ("r_infb", C.c_int), ("n_layers", C.c_int),
+        ("learn_infb", C.c_float),
+        ("col_cells", C.c_int), ("col_iter", C.c_int),
+        ("col_sparsity", C.c_float), ("col_leak", C.c_float),
+        ("col_gamma", C.c_float), ("col_gamma_lambda", C.c_float),
+        ("col_alpha_ff", C.c_float), ("col_alpha_lat", C.c_float), ("col_alpha_threshold", C.c_float),
+        ("col_alpha_q", C.c_float), ("col_alpha_action", C.c_float),
+        ("col_expl_stddev", C.c_float), ("col_expl_break", C.c_float),
+        ("init_min_w", C.c_float), ("init_max_w", C.c_float),
+        ("init_min_inh", C.c_float), ("init_max_inh", C.c_float), ("init_threshold", C.c_float),
+    ]
+
+
+_COLUMN_DEFAULTS = dict(
+    col_cells=16, col_iter=7, col_sparsity=0.125, col_leak=0.1,
+    col_gamma=0.99, col_gamma_lambda=0.95,
+    col_alpha_ff=0.01, col_alpha_lat=0.05, col_alpha_threshold=0.01,
+    col_alpha_q=0.01, col_alpha_action=0.1,
+    col_expl_stddev=0.05, col_expl_break=0.01)
+
+_LAYER_DEFAULTS = {
+    KWINNERS: dict(
+        width=16, height=16, r_ff=8, r_rec=4, r_lat=3, r_pred=4, r_fb=8,
+        learn_ff=0.02, learn_rec=0.02, learn_lat=0.2, learn_threshold=0.12,
+        learn_fb=0.05, learn_pred=0.05,
+        avg_surprise_decay=0.01, attention_factor=4.0, sparsity=0.01),
+    ITERATIVE: dict(
+        width=16, height=16, r_ff=3, r_rec=3, r_lat=3, r_pred=3, r_fb=3,
+        learn_ff=0.01, learn_rec=0.01, learn_lat=0.2, learn_fb=0.05, learn_pred=0.05,
+        iter_settle=30, iter_measure=5, leak=0.3, lambda_=0.95,
+        weight_decay=0.0, max_weight_delta=0.5, sparsity=0.2, learn_threshold=0.02,
+        baseline_decay=0.01, sensitivity=8.0),
+    NEO_HIERARCHY: dict(
+        width=16, height=16, r_ff=4, r_rec=4, r_lat=4, r_pred=4, r_fb=4,
+        learn_ff=0.01, learn_rec=0.01, learn_lat=0.05, learn_fb=0.1, learn_pred=0.03,
+        iter_settle=30, iter_measure=0, leak=0.1, lambda_=0.95,
+        weight_decay=0.0, max_weight_delta=0.5, sparsity=0.02, learn_threshold=0.01,
+        baseline_decay=0.01, sensitivity=6.0),
+}
+_LAYER_DEFAULTS[NEO_AGENT] = dict(_LAYER_DEFAULTS[NEO_HIERARCHY], **_COLUMN_DEFAULTS)
+
+_LEARN_INFB = {KWINNERS: 0.0, ITERATIVE: 0.05, NEO_HIERARCHY: 0.1, NEO_AGENT: 0.1}
+
+
+def layer_desc(variant, **overrides):
+    """A LayerDesc holding the reference defaults of ``variant``, then ``overrides``."""
+    d = LayerDesc()
+    vals = dict(_LAYER_DEFAULTS[variant])
+    for k, v in overrides.items():
+        vals["lambda_" if k == "lambda" else k] = v
+    for k, v in vals.items():
+        if not hasattr(d, k):
+            raise AttributeError("LayerDesc has no field %r" % k)
+        setattr(d, k, v)
+    return d
+
+
+def make_config(variant, in_width, in_height, layers, r_infb=0,
+                init=(-0.01, 0.01, 0.01, 0.05, 0.1), **overrides):
+    """(Config, LayerDesc array) for ``variant``.
+
+    ``layers`` is a list of dicts of LayerDesc overrides (at least width/height) or
+    LayerDesc objects.  ``init`` = (minW, maxW, minInh, maxInh, threshold), the
+    createRandom arguments (RunnerMain.cpp:154, Experiment_Prediction.cpp:126).
+    """
+    descs = (LayerDesc * len(layers))()
+    for i, l in enumerate(layers):
+        descs[i] = l if isinstance(l, LayerDesc) else layer_desc(variant, **l)
+    cfg = Config()
+    cfg.variant = variant
+    cfg.in_width, cfg.in_height = in_width, in_height
+    cfg.r_infb = r_infb
+    cfg.n_layers = len(layers)
+    cfg.learn_infb = _LEARN_INFB[variant]
+    for k, v in _COLUMN_DEFAULTS.items():
+        setattr(cfg, k, v)
+    (cfg.init_min_w, cfg.init_max_w, cfg.init_min_inh, cfg.init_max_inh,
+     cfg.init_threshold) = init
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("Config has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg, descs
+
+
+# ---- the BASELINE.json configurations (SURVEY section 8 shorthand) -------------
+def config_c1(variant=KWINNERS):
+    """C1: input 16x16, layers 16^2 -> 8^2 -> 4^2, class defaults."""
+    layers = [dict(width=16, height=16), dict(width=8, height=8), dict(width=4, height=4)]
+    return make_config(variant, 16, 16, layers, r_infb=0 if variant == KWINNERS else 16)
+
+
+def config_experiment_prediction():
+    """Experiment_Prediction.cpp:113-126: input 2x2, 16^2 -> 12^2 -> 8^2, inFB 16, threshold 0."""
+    layers = [dict(width=16, height=16), dict(width=12, height=12), dict(width=8, height=8)]
+    return make_config(ITERATIVE, 2, 2, layers, r_infb=16, init=(-0.01, 0.01, 0.01, 0.05, 0.0))
+
+
+def config_c2():
+    """C2/C3: neo::Agent of RunnerMain.cpp:141-154: input 8x8, layers 8^2 -> 4^2, inFB 8."""
+    layers = [dict(width=8, height=8), dict(width=4, height=4)]
+    return make_config(NEO_AGENT, 8, 8, layers, r_infb=8)
+
+
+def config_c4(variant=KWINNERS):
+    """C4: input 128x128, layers 96^2..16^2, every radius 6, inFB 6."""
+    r = dict(r_ff=6, r_rec=6, r_lat=6, r_pred=6, r_fb=6)
+    layers = [dict(width=w, height=w, **r) for w in (96, 64, 48, 32, 24, 16)]
+    return make_config(variant, 128, 128, layers, r_infb=0 if variant == KWINNERS else 6)
+
+
+def config_c5(size=1024, variant=KWINNERS):
+    """C5: one same-size layer (size x size over size x size), every radius 6."""
+    r = dict(r_ff=6, r_rec=6, r_lat=6, r_pred=6, r_fb=6)
+    return make_config(variant, size, size, [dict(width=size, height=size, **r)],
+                       r_infb=0 if variant == KWINNERS else 6)

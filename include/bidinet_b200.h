@@ -1,0 +1,219 @@
+/*
+ * bidinet_b200.h -- C ABI of the B200-native BIDInet hierarchy-update engine.
+ *
+ * The reference (222464/BIDInet) has no FFI layer: its experiment mains call
+ * plain C++ value classes (sdr::PredictiveRSDR, sdr::IPredictiveRSDR,
+ * neo::PredictiveHierarchy, neo::Agent).  This header is the boundary a
+ * drop-in facade for those classes binds to (see include/bidinet/*.h and
+ * INTEGRATION.md).  Every entry point cites the reference interface it
+ * replaces; paths are relative to BIDInet/source/ of the reference.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary
+ *   - every call returns 0 on success, a negative BIDI_E* code otherwise;
+ *     bidi_last_error() gives the message (no exceptions cross the ABI)
+ *   - one engine = one device + one CUDA stream; calls on one engine must be
+ *     serialised by the caller (the reference is single threaded as well)
+ *   - "arrays" are the reference's per-layer state vectors, serialised in the
+ *     REFERENCE order: unit index = x + y*width, connection lists clipped to
+ *     the grid and concatenated unit after unit, inside a unit dx outer / dy
+ *     inner (sdr/RSDR.cpp:48-62).  The engine converts to and from its own
+ *     HBM layout.
+ */
+#ifndef BIDINET_B200_H
+#define BIDINET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BIDI_MAX_LAYERS 16
+#define BIDI_COLUMN_ACTIONS 3 /* neo/Agent.h:9-11 _attention,_learnPrediction,_signal */
+
+/* Which reference hierarchy the engine reproduces. */
+enum bidi_variant {
+  BIDI_KWINNERS = 0,      /* sdr::PredictiveRSDR    sdr/PredictiveRSDR.cpp:100-194 */
+  BIDI_ITERATIVE = 1,     /* sdr::IPredictiveRSDR   sdr/IPredictiveRSDR.cpp:138-240 */
+  BIDI_NEO_HIERARCHY = 2, /* neo::PredictiveHierarchy neo/PredictiveHierarchy.cpp:137-245 */
+  BIDI_NEO_AGENT = 3      /* neo::Agent             neo/Agent.cpp:141-284 */
+};
+
+enum bidi_status {
+  BIDI_OK = 0,
+  BIDI_EINVAL = -1,  /* bad argument / unsupported configuration */
+  BIDI_ECUDA = -2,   /* CUDA runtime error (message has the CUDA string) */
+  BIDI_ENOMEM = -3,
+  BIDI_ENODEV = -4   /* no usable CUDA device: there is NO CPU fallback */
+};
+
+/*
+ * One layer of the hierarchy.  Union of the fields of the four reference
+ * LayerDesc structs (sdr/PredictiveRSDR.h:14-42, sdr/IPredictiveRSDR.h:14-46,
+ * neo/PredictiveHierarchy.h:14-45, neo/Agent.h:19-65); a variant ignores the
+ * fields its reference class does not have.
+ */
+typedef struct bidi_layer_desc {
+  int width, height;
+  int r_ff, r_rec, r_lat, r_pred, r_fb; /* receptive, recurrent, lateral, predictive, feedback radii */
+  float learn_ff, learn_rec, learn_lat;
+  float learn_threshold;                /* _learnThreshold / _sdrLearnThreshold */
+  float learn_fb, learn_pred;
+  float sparsity;                       /* _sparsity / _sdrSparsity */
+  /* k-winners (sdr/PredictiveRSDR.h:27-30) */
+  float avg_surprise_decay, attention_factor;
+  /* iterative coders */
+  int iter_settle;                      /* _sdrIterSettle, or _sdrIter for the neo classes */
+  int iter_measure;                     /* _sdrIterMeasure (ITERATIVE only) */
+  float leak;                           /* _sdrLeak */
+  float lambda;                         /* _sdrLambda (trace decay, neo classes) */
+  float weight_decay, max_weight_delta; /* _sdrWeightDecay, _sdrMaxWeightDelta */
+  float baseline_decay, sensitivity;    /* _sdrBaselineDecay, _sdrSensitivity */
+  /* per-node columns (neo/Agent.h:22-31) */
+  int col_cells, col_iter;
+  float col_sparsity, col_leak, col_gamma, col_gamma_lambda;
+  float col_alpha_ff, col_alpha_lat, col_alpha_threshold, col_alpha_q, col_alpha_action;
+  float col_expl_stddev, col_expl_break;
+} bidi_layer_desc;
+
+typedef struct bidi_config {
+  int variant; /* enum bidi_variant */
+  int in_width, in_height;
+  int r_infb;        /* inputFeedBackRadius (not KWINNERS) */
+  int n_layers;
+  float learn_infb;  /* _learnInputFeedBack  sdr/IPredictiveRSDR.h:101 */
+  /* columns of the input prediction nodes (public members, neo/Agent.h:125-135) */
+  int col_cells, col_iter;
+  float col_sparsity, col_leak, col_gamma, col_gamma_lambda;
+  float col_alpha_ff, col_alpha_lat, col_alpha_threshold, col_alpha_q, col_alpha_action;
+  float col_expl_stddev, col_expl_break;
+  /* createRandom arguments (sdr/IPredictiveRSDR.h:107) */
+  float init_min_w, init_max_w, init_min_inh, init_max_inh, init_threshold;
+} bidi_config;
+
+/*
+ * State arrays.  `layer` is 0..n_layers-1; for the P_*, FB_W and COL_* arrays
+ * layer == n_layers addresses the INPUT prediction nodes
+ * (sdr/IPredictiveRSDR.h:68-81) and their columns.  Arrays a variant does not
+ * have report length 0.
+ */
+enum bidi_array {
+  /* sparse coder of the layer (sdr/RSDR.h:15-41, sdr/IRSDR.h:21-49) */
+  BIDI_VIS_INPUT = 0, BIDI_VIS_RECON,
+  BIDI_HID_THRESHOLD, BIDI_HID_STATE, BIDI_HID_STATE_PREV, BIDI_HID_ACTIVATION, BIDI_HID_RECON,
+  BIDI_HID_SPIKE, BIDI_HID_SPIKE_PREV,
+  BIDI_FF_W, BIDI_REC_W, BIDI_LAT_W, BIDI_FF_TRACE, BIDI_REC_TRACE,
+  /* prediction nodes (sdr/PredictiveRSDR.h:44-61) */
+  BIDI_P_STATE, BIDI_P_STATE_PREV, BIDI_P_ACTIVATION, BIDI_P_ACTIVATION_PREV,
+  BIDI_P_BASELINE, /* _averageSurprise (KWINNERS) or _baseline */
+  BIDI_FB_W, BIDI_PRED_W,
+  /* columns (neo/Column.h:9-58); concatenated node after node */
+  BIDI_COL_INPUT, BIDI_COL_RECON_ERR,             /* [sum nIn] */
+  BIDI_COL_FF_W,                                  /* [node][cell][input] */
+  BIDI_COL_LAT_W,                                 /* [node][cell][cell] */
+  BIDI_COL_THRESHOLD, BIDI_COL_ACTIVATION, BIDI_COL_SPIKE, BIDI_COL_SPIKE_PREV, BIDI_COL_STATE, /* [node][cell] */
+  BIDI_COL_Q_W, BIDI_COL_Q_TRACE,                 /* [node][cell] */
+  BIDI_COL_ACT_STATE, BIDI_COL_ACT_EXPL,          /* [node][action] */
+  BIDI_COL_ACT_W, BIDI_COL_ACT_TRACE,             /* [node][action][cell] */
+  BIDI_COL_PREV_VALUE,                            /* [node] */
+  /* sdr::PredictiveRSDR::_prediction (sdr/PredictiveRSDR.h:77), layer 0 only */
+  BIDI_PREDICTION,
+  BIDI_ARRAY_COUNT
+};
+
+typedef struct bidi_engine bidi_engine;
+
+/* Message of the last failed call; h may be NULL for a failed bidi_create. */
+const char* bidi_last_error(const bidi_engine* h);
+
+/*
+ * Allocate an engine for n_agents independent hierarchies of identical shape on
+ * CUDA device `device` (state zero-initialised as the reference's constructors
+ * do, thresholds = cfg->init_threshold).  Replaces the allocation half of
+ * createRandom (sdr/PredictiveRSDR.cpp:8, sdr/IPredictiveRSDR.cpp:8,
+ * neo/PredictiveHierarchy.cpp:8, neo/Agent.cpp:7).  Fails with BIDI_ENODEV when
+ * no CUDA device is usable.
+ */
+int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_agents, int device,
+                bidi_engine** out);
+void bidi_destroy(bidi_engine* h);
+
+/*
+ * Random half of createRandom: agent a (first <= a < first+count) gets exactly
+ * the weights std::mt19937(seed_base + a) produces in the reference's draw
+ * order (sdr/RSDR.cpp:48-116, sdr/PredictiveRSDR.cpp:38-91,
+ * neo/Column.cpp:22-43).
+ */
+int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base);
+
+/* Shape queries. */
+int bidi_num_agents(const bidi_engine* h);
+int bidi_num_inputs(const bidi_engine* h);          /* in_width*in_height */
+long long bidi_array_len(const bidi_engine* h, int which, int layer); /* <0 on error */
+/*
+ * Per-unit list lengths of a connection-list array (FF_W, REC_W, LAT_W, FB_W,
+ * PRED_W: the clipped window sizes; COL_INPUT: nIn per node).  `counts` has one
+ * entry per unit of the layer.  What the reference exposes through
+ * getHiddenNode(i)._feedForwardConnections.size() (sdr/RSDR.h:116).
+ */
+int bidi_conn_counts(const bidi_engine* h, int which, int layer, int* counts, int n_units);
+
+/* Serialised-state access in reference order. */
+int bidi_set_array(bidi_engine* h, int agent, int which, int layer, const float* src, long long len);
+int bidi_get_array(bidi_engine* h, int agent, int which, int layer, float* dst, long long len);
+
+/*
+ * setInput(index, value) for every input of every agent at once
+ * (sdr/PredictiveRSDR.h:84, sdr/IPredictiveRSDR.h:111, neo/Agent.h:150):
+ * in[agent][index], host memory; copied host->device on the engine's stream.
+ */
+int bidi_set_inputs(bidi_engine* h, const float* in);
+int bidi_set_input(bidi_engine* h, int agent, int index, float value);
+
+/*
+ * simStep (sdr/PredictiveRSDR.h:82, sdr/IPredictiveRSDR.h:109, neo/Agent.h:148)
+ * for all agents: one pass bottom-up coding -> top-down prediction -> learning.
+ *   rewards  [n_agents] host, NEO_AGENT only (NULL = 0)
+ *   noise_u, noise_v  [n_agents][n_columns][3] host, NEO_AGENT only: the values
+ *            the reference draws per column visit (neo/Column.cpp:126-131):
+ *            u = dist01(gen); v = u < breakChance ? dist01(gen) : pertDist(gen).
+ *            Column visit order = layers top -> bottom, nodes ascending, then the
+ *            input nodes (neo/Agent.cpp:155-156,212).  NULL = the engine draws
+ *            from its own counter-based per-column generator.
+ *   learn    the reference's `learn` flag.
+ * Asynchronous: returns after enqueueing on the engine's stream.
+ */
+int bidi_step(bidi_engine* h, const float* rewards, const float* noise_u, const float* noise_v,
+              int learn);
+int bidi_num_columns(const bidi_engine* h);
+
+/*
+ * getPrediction(index) for every input of every agent (sdr/PredictiveRSDR.h:92,
+ * sdr/IPredictiveRSDR.h:119, neo/Agent.h:158): out[agent][index], host memory.
+ * Synchronises the engine's stream.
+ */
+int bidi_get_predictions(bidi_engine* h, float* out);
+/* Column::getAction(a) (neo/Column.h:85) of every column: out[agent][column][3]. */
+int bidi_get_column_actions(bidi_engine* h, float* out);
+
+int bidi_sync(bidi_engine* h);
+
+/*
+ * Device-resident stepping for throughput runs: frames[T][agent][index] is
+ * uploaded once; bidi_step_frame(t) is bidi_set_inputs(frame t % T) + bidi_step
+ * without any host<->device traffic.
+ */
+int bidi_load_frames(bidi_engine* h, const float* frames, int n_frames);
+int bidi_step_frame(bidi_engine* h, int t, const float* rewards_dev_or_null, int learn);
+
+/* Timing helpers on the engine's stream (CUDA events), for bench.py. */
+int bidi_timer_start(bidi_engine* h);
+int bidi_timer_stop_ms(bidi_engine* h, float* ms);
+/* Number of kernel launches (graph kernel nodes included) issued so far. */
+long long bidi_launch_count(const bidi_engine* h);
+/* Bytes of device memory held by the engine. */
+long long bidi_device_bytes(const bidi_engine* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BIDINET_B200_H */

@@ -1,0 +1,395 @@
+// oracle/ref_harness.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// Headless C wrapper around the UNMODIFIED reference classes, compiled from the
+// sources where they lie under /root/reference (see oracle/Makefile) into
+// oracle/_ref/libbidiref.so.  It gives the tests and bench.py's reference arm
+//   - creation from a fixed seed (the mains seed from time(), RunnerMain.cpp:36)
+//   - setInput / simStep / getPrediction exactly as the mains call them
+//   - a dump of every state array in the serialised order include/bidinet_b200.h
+//     defines, so the CUDA engine and the C restatement (oracle/bidi_oracle.c)
+//     can be started from, and compared with, an identical state.
+// Nothing here is copied from the reference; it only calls it.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <random>
+#include <vector>
+#include <iostream>
+
+// The coders' node vectors, neo::Column internals and _inputPredictionNodes are
+// private (sdr/RSDR.h:43-52, neo/Column.h:8-58, neo/Agent.h:116-120); access
+// specifiers do not change layout, so this TU may see them as public.
+#define private public
+#include <sdr/PredictiveRSDR.h>
+#include <sdr/IPredictiveRSDR.h>
+#include <neo/PredictiveHierarchy.h>
+#include <neo/Agent.h>
+#undef private
+
+#include "bidinet_b200.h"
+
+namespace {
+
+struct Ref {
+  bidi_config cfg;
+  std::vector<bidi_layer_desc> ld;
+  std::mt19937 gen;
+  sdr::PredictiveRSDR kw;
+  sdr::IPredictiveRSDR it;
+  neo::PredictiveHierarchy nh;
+  neo::Agent ag;
+};
+
+template <class D> void fill_common(D& d, const bidi_layer_desc& s) {
+  d._width = s.width; d._height = s.height;
+  d._receptiveRadius = s.r_ff; d._recurrentRadius = s.r_rec; d._lateralRadius = s.r_lat;
+  d._predictiveRadius = s.r_pred; d._feedBackRadius = s.r_fb;
+  d._learnFeedForward = s.learn_ff; d._learnRecurrent = s.learn_rec; d._learnLateral = s.learn_lat;
+  d._learnFeedBack = s.learn_fb; d._learnPrediction = s.learn_pred;
+}
+template <class D> void fill_neo(D& d, const bidi_layer_desc& s) {
+  fill_common(d, s);
+  d._sdrIter = s.iter_settle; d._sdrLeak = s.leak; d._sdrLambda = s.lambda;
+  d._sdrWeightDecay = s.weight_decay; d._sdrMaxWeightDelta = s.max_weight_delta;
+  d._sdrSparsity = s.sparsity; d._sdrLearnThreshold = s.learn_threshold;
+  d._sdrBaselineDecay = s.baseline_decay; d._sdrSensitivity = s.sensitivity;
+}
+
+// ---- generic element visitors (serialised order of include/bidinet_b200.h) ----
+template <class Coder, class F> bool visit_coder(Coder& c, int which, F&& f) {
+  switch (which) {
+    case BIDI_VIS_INPUT: for (auto& v : c._visible) f(v._input); return true;
+    case BIDI_VIS_RECON: for (auto& v : c._visible) f(v._reconstruction); return true;
+    case BIDI_HID_THRESHOLD: for (auto& h : c._hidden) f(h._threshold); return true;
+    case BIDI_HID_STATE: for (auto& h : c._hidden) f(h._state); return true;
+    case BIDI_HID_STATE_PREV: for (auto& h : c._hidden) f(h._statePrev); return true;
+    case BIDI_HID_ACTIVATION: for (auto& h : c._hidden) f(h._activation); return true;
+    case BIDI_HID_RECON: for (auto& h : c._hidden) f(h._reconstruction); return true;
+    case BIDI_FF_W: for (auto& h : c._hidden) for (auto& k : h._feedForwardConnections) f(k._weight); return true;
+    case BIDI_REC_W: for (auto& h : c._hidden) for (auto& k : h._recurrentConnections) f(k._weight); return true;
+    default: return false;
+  }
+}
+template <class Coder, class F> bool visit_icoder(Coder& c, int which, bool traces, F&& f) {
+  if (visit_coder(c, which, f)) return true;
+  switch (which) {
+    case BIDI_HID_SPIKE: for (auto& h : c._hidden) f(h._spike); return true;
+    case BIDI_HID_SPIKE_PREV: for (auto& h : c._hidden) f(h._spikePrev); return true;
+    case BIDI_LAT_W: for (auto& h : c._hidden) for (auto& k : h._lateralConnections) f(k._weight); return true;
+    case BIDI_FF_TRACE: if (!traces) return false;
+      for (auto& h : c._hidden) for (auto& k : h._feedForwardConnections) f(k._trace); return true;
+    case BIDI_REC_TRACE: if (!traces) return false;
+      for (auto& h : c._hidden) for (auto& k : h._recurrentConnections) f(k._trace); return true;
+    default: return false;
+  }
+}
+template <class Nodes, class F> bool visit_pnodes(Nodes& nodes, int which, F&& f) {
+  switch (which) {
+    case BIDI_P_STATE: for (auto& p : nodes) f(p._state); return true;
+    case BIDI_P_STATE_PREV: for (auto& p : nodes) f(p._statePrev); return true;
+    case BIDI_P_ACTIVATION: for (auto& p : nodes) f(p._activation); return true;
+    case BIDI_P_ACTIVATION_PREV: for (auto& p : nodes) f(p._activationPrev); return true;
+    case BIDI_FB_W: for (auto& p : nodes) for (auto& k : p._feedBackConnections) f(k._weight); return true;
+    default: return false;
+  }
+}
+template <class Nodes, class F> bool visit_pred_w(Nodes& nodes, F&& f) {
+  for (auto& p : nodes) for (auto& k : p._predictiveConnections) f(k._weight);
+  return true;
+}
+template <class Nodes, class F> bool visit_columns(Nodes& nodes, int which, F&& f) {
+  switch (which) {
+    case BIDI_COL_INPUT: for (auto& p : nodes) for (auto& v : p._column._inputs) f(v); return true;
+    case BIDI_COL_RECON_ERR: for (auto& p : nodes) for (auto& v : p._column._reconstructionError) f(v); return true;
+    case BIDI_COL_FF_W: for (auto& p : nodes) for (auto& c : p._column._cells) for (auto& k : c._feedForwardConnections) f(k._weight); return true;
+    case BIDI_COL_LAT_W: for (auto& p : nodes) for (auto& c : p._column._cells) for (auto& k : c._lateralConnections) f(k._weight); return true;
+    case BIDI_COL_THRESHOLD: for (auto& p : nodes) for (auto& c : p._column._cells) f(c._threshold); return true;
+    case BIDI_COL_ACTIVATION: for (auto& p : nodes) for (auto& c : p._column._cells) f(c._activation); return true;
+    case BIDI_COL_SPIKE: for (auto& p : nodes) for (auto& c : p._column._cells) f(c._spike); return true;
+    case BIDI_COL_SPIKE_PREV: for (auto& p : nodes) for (auto& c : p._column._cells) f(c._spikePrev); return true;
+    case BIDI_COL_STATE: for (auto& p : nodes) for (auto& c : p._column._cells) f(c._state); return true;
+    case BIDI_COL_Q_W: for (auto& p : nodes) for (auto& k : p._column._qConnections) f(k._weight); return true;
+    case BIDI_COL_Q_TRACE: for (auto& p : nodes) for (auto& k : p._column._qConnections) f(k._trace); return true;
+    case BIDI_COL_ACT_STATE: for (auto& p : nodes) for (auto& a : p._column._actions) f(a._state); return true;
+    case BIDI_COL_ACT_EXPL: for (auto& p : nodes) for (auto& a : p._column._actions) f(a._exploratoryState); return true;
+    case BIDI_COL_ACT_W: for (auto& p : nodes) for (auto& a : p._column._actions) for (auto& k : a._connections) f(k._weight); return true;
+    case BIDI_COL_ACT_TRACE: for (auto& p : nodes) for (auto& a : p._column._actions) for (auto& k : a._connections) f(k._trace); return true;
+    case BIDI_COL_PREV_VALUE: for (auto& p : nodes) f(p._column._prevValue); return true;
+    default: return false;
+  }
+}
+
+template <class F> bool visit(Ref& r, int which, int layer, F&& f) {
+  const int L = r.cfg.n_layers;
+  if (layer < 0 || layer > L) return false;
+  switch (r.cfg.variant) {
+    case BIDI_KWINNERS: {
+      if (which == BIDI_PREDICTION) {
+        if (layer != 0) return false;
+        for (auto& v : r.kw._prediction) f(v);
+        return true;
+      }
+      if (layer >= L) return false;
+      auto& ly = const_cast<sdr::PredictiveRSDR::Layer&>(r.kw.getLayers()[layer]);
+      if (visit_coder(ly._sdr, which, f)) return true;
+      if (which == BIDI_P_BASELINE) { for (auto& p : ly._predictionNodes) f(p._averageSurprise); return true; }
+      if (which == BIDI_PRED_W) return visit_pred_w(ly._predictionNodes, f);
+      return visit_pnodes(ly._predictionNodes, which, f);
+    }
+    case BIDI_ITERATIVE: {
+      if (layer == L) return visit_pnodes(r.it._inputPredictionNodes, which, f);
+      auto& ly = const_cast<sdr::IPredictiveRSDR::Layer&>(r.it.getLayers()[layer]);
+      if (visit_icoder(ly._sdr, which, false, f)) return true;
+      if (which == BIDI_P_BASELINE) { for (auto& p : ly._predictionNodes) f(p._baseline); return true; }
+      if (which == BIDI_PRED_W) return visit_pred_w(ly._predictionNodes, f);
+      return visit_pnodes(ly._predictionNodes, which, f);
+    }
+    case BIDI_NEO_HIERARCHY: {
+      if (layer == L) return visit_pnodes(r.nh._inputPredictionNodes, which, f);
+      auto& ly = const_cast<neo::PredictiveHierarchy::Layer&>(r.nh.getLayers()[layer]);
+      if (visit_icoder(ly._sdr, which, true, f)) return true;
+      if (which == BIDI_P_BASELINE) { for (auto& p : ly._predictionNodes) f(p._baseline); return true; }
+      if (which == BIDI_PRED_W) return visit_pred_w(ly._predictionNodes, f);
+      return visit_pnodes(ly._predictionNodes, which, f);
+    }
+    case BIDI_NEO_AGENT: {
+      if (layer == L) {
+        if (visit_pnodes(r.ag._inputPredictionNodes, which, f)) return true;
+        return visit_columns(r.ag._inputPredictionNodes, which, f);
+      }
+      auto& ly = const_cast<neo::Agent::Layer&>(r.ag.getLayers()[layer]);
+      if (visit_icoder(ly._sdr, which, true, f)) return true;
+      if (which == BIDI_P_BASELINE) { for (auto& p : ly._predictionNodes) f(p._baseline); return true; }
+      if (which == BIDI_PRED_W) return visit_pred_w(ly._predictionNodes, f);
+      if (visit_pnodes(ly._predictionNodes, which, f)) return true;
+      return visit_columns(ly._predictionNodes, which, f);
+    }
+  }
+  return false;
+}
+
+// neo::Column leaves Cell::_activation/_spike/_state and Action::_error
+// uninitialised until the first simStep overwrites them (neo/Column.h:31-33);
+// zero them so a dump taken before the first step is defined.
+template <class Nodes> void zero_column_scratch(Nodes& nodes) {
+  for (auto& p : nodes) {
+    for (auto& c : p._column._cells) { c._activation = 0.0f; c._spike = 0.0f; c._state = 0.0f; }
+    for (auto& a : p._column._actions) a._error = 0.0f;
+  }
+}
+
+} // namespace
+
+extern "C" {
+
+void* ref_create(const bidi_config* cfg, const bidi_layer_desc* layers, unsigned seed) {
+  Ref* r = new Ref();
+  r->cfg = *cfg;
+  r->ld.assign(layers, layers + cfg->n_layers);
+  r->gen.seed(seed);
+  const int L = cfg->n_layers;
+  switch (cfg->variant) {
+    case BIDI_KWINNERS: {
+      std::vector<sdr::PredictiveRSDR::LayerDesc> d(L);
+      for (int l = 0; l < L; l++) {
+        fill_common(d[l], layers[l]);
+        d[l]._learnThreshold = layers[l].learn_threshold;
+        d[l]._averageSurpriseDecay = layers[l].avg_surprise_decay;
+        d[l]._attentionFactor = layers[l].attention_factor;
+        d[l]._sparsity = layers[l].sparsity;
+      }
+      r->kw.createRandom(cfg->in_width, cfg->in_height, d, cfg->init_min_w, cfg->init_max_w,
+                         cfg->init_threshold, r->gen);
+      break;
+    }
+    case BIDI_ITERATIVE: {
+      std::vector<sdr::IPredictiveRSDR::LayerDesc> d(L);
+      for (int l = 0; l < L; l++) {
+        fill_common(d[l], layers[l]);
+        d[l]._sdrIterSettle = layers[l].iter_settle; d[l]._sdrIterMeasure = layers[l].iter_measure;
+        d[l]._sdrLeak = layers[l].leak; d[l]._sdrLambda = layers[l].lambda;
+        d[l]._sdrWeightDecay = layers[l].weight_decay; d[l]._sdrMaxWeightDelta = layers[l].max_weight_delta;
+        d[l]._sdrSparsity = layers[l].sparsity; d[l]._sdrLearnThreshold = layers[l].learn_threshold;
+        d[l]._sdrBaselineDecay = layers[l].baseline_decay; d[l]._sdrSensitivity = layers[l].sensitivity;
+      }
+      r->it._learnInputFeedBack = cfg->learn_infb;
+      r->it.createRandom(cfg->in_width, cfg->in_height, cfg->r_infb, d, cfg->init_min_w, cfg->init_max_w,
+                         cfg->init_min_inh, cfg->init_max_inh, cfg->init_threshold, r->gen);
+      break;
+    }
+    case BIDI_NEO_HIERARCHY: {
+      std::vector<neo::PredictiveHierarchy::LayerDesc> d(L);
+      for (int l = 0; l < L; l++) fill_neo(d[l], layers[l]);
+      r->nh._learnInputFeedBack = cfg->learn_infb;
+      r->nh.createRandom(cfg->in_width, cfg->in_height, cfg->r_infb, d, cfg->init_min_w, cfg->init_max_w,
+                         cfg->init_min_inh, cfg->init_max_inh, cfg->init_threshold, r->gen);
+      break;
+    }
+    case BIDI_NEO_AGENT: {
+      std::vector<neo::Agent::LayerDesc> d(L);
+      for (int l = 0; l < L; l++) {
+        fill_neo(d[l], layers[l]);
+        const bidi_layer_desc& s = layers[l];
+        d[l]._cellsPerColumn = s.col_cells; d[l]._columnSparsity = s.col_sparsity; d[l]._columnIter = s.col_iter;
+        d[l]._columnLeak = s.col_leak; d[l]._columnGamma = s.col_gamma; d[l]._columnGammaLambda = s.col_gamma_lambda;
+        d[l]._columnFeedForwardAlpha = s.col_alpha_ff; d[l]._columnLateralAlpha = s.col_alpha_lat;
+        d[l]._columnThresholdAlpha = s.col_alpha_threshold; d[l]._columnQAlpha = s.col_alpha_q;
+        d[l]._columnActionAlpha = s.col_alpha_action; d[l]._columnExplorationStdDev = s.col_expl_stddev;
+        d[l]._columnExplorationBreakChance = s.col_expl_break;
+      }
+      neo::Agent& a = r->ag;
+      a._cellsPerColumn = cfg->col_cells; a._columnSparsity = cfg->col_sparsity; a._columnIter = cfg->col_iter;
+      a._columnLeak = cfg->col_leak; a._columnGamma = cfg->col_gamma; a._columnGammaLambda = cfg->col_gamma_lambda;
+      a._columnFeedForwardAlpha = cfg->col_alpha_ff; a._columnLateralAlpha = cfg->col_alpha_lat;
+      a._columnThresholdAlpha = cfg->col_alpha_threshold; a._columnQAlpha = cfg->col_alpha_q;
+      a._columnActionAlpha = cfg->col_alpha_action; a._columnExplorationStdDev = cfg->col_expl_stddev;
+      a._columnExplorationBreakChance = cfg->col_expl_break;
+      a._learnInputFeedBack = cfg->learn_infb;
+      a.createRandom(cfg->in_width, cfg->in_height, cfg->r_infb, d, cfg->init_min_w, cfg->init_max_w,
+                     cfg->init_min_inh, cfg->init_max_inh, cfg->init_threshold, r->gen);
+      for (auto& ly : a._layers) zero_column_scratch(ly._predictionNodes);
+      zero_column_scratch(a._inputPredictionNodes);
+      break;
+    }
+    default: delete r; return nullptr;
+  }
+  return r;
+}
+
+void ref_destroy(void* h) { delete static_cast<Ref*>(h); }
+
+long long ref_array_len(void* h, int which, int layer) {
+  long long n = 0;
+  if (!visit(*static_cast<Ref*>(h), which, layer, [&](float&) { n++; })) return 0;
+  return n;
+}
+int ref_get_array(void* h, int which, int layer, float* dst) {
+  return visit(*static_cast<Ref*>(h), which, layer, [&](float& v) { *dst++ = v; }) ? 0 : -1;
+}
+int ref_set_array(void* h, int which, int layer, const float* src) {
+  return visit(*static_cast<Ref*>(h), which, layer, [&](float& v) { v = *src++; }) ? 0 : -1;
+}
+
+void ref_set_input(void* h, int i, float v) {
+  Ref& r = *static_cast<Ref*>(h);
+  switch (r.cfg.variant) {
+    case BIDI_KWINNERS: r.kw.setInput(i, v); break;
+    case BIDI_ITERATIVE: r.it.setInput(i, v); break;
+    case BIDI_NEO_HIERARCHY: r.nh.setInput(i, v); break;
+    case BIDI_NEO_AGENT: r.ag.setInput(i, v); break;
+  }
+}
+void ref_set_inputs(void* h, const float* in, int n) {
+  for (int i = 0; i < n; i++) ref_set_input(h, i, in[i]);
+}
+float ref_get_prediction(void* h, int i) {
+  Ref& r = *static_cast<Ref*>(h);
+  switch (r.cfg.variant) {
+    case BIDI_KWINNERS: return r.kw.getPrediction(i);
+    case BIDI_ITERATIVE: return r.it.getPrediction(i);
+    case BIDI_NEO_HIERARCHY: return r.nh.getPrediction(i);
+    case BIDI_NEO_AGENT: return r.ag.getPrediction(i);
+  }
+  return 0.0f;
+}
+void ref_get_predictions(void* h, float* out, int n) {
+  for (int i = 0; i < n; i++) out[i] = ref_get_prediction(h, i);
+}
+
+void ref_step(void* h, float reward, int learn) {
+  Ref& r = *static_cast<Ref*>(h);
+  switch (r.cfg.variant) {
+    case BIDI_KWINNERS: r.kw.simStep(learn != 0); break;
+    case BIDI_ITERATIVE: r.it.simStep(r.gen, learn != 0); break;
+    case BIDI_NEO_HIERARCHY: r.nh.simStep(r.gen, learn != 0); break;
+    case BIDI_NEO_AGENT: r.ag.simStep(reward, r.gen, learn != 0); break;
+  }
+}
+
+// n steps back to back on one frame sequence frames[t % n_frames][n_in]; returns
+// nothing -- used by the timing legs so the Python call overhead stays outside.
+void ref_run(void* h, const float* frames, int n_frames, int n_in, const float* rewards, int steps, int learn) {
+  for (int t = 0; t < steps; t++) {
+    ref_set_inputs(h, frames + (size_t)(t % n_frames) * n_in, n_in);
+    ref_step(h, rewards ? rewards[t % n_frames] : 0.0f, learn);
+  }
+}
+
+int ref_num_columns(void* h) {
+  Ref& r = *static_cast<Ref*>(h);
+  if (r.cfg.variant != BIDI_NEO_AGENT) return 0;
+  int n = (int)r.ag._inputPredictionNodes.size();
+  for (auto& ly : r.ag._layers) n += (int)ly._predictionNodes.size();
+  return n;
+}
+
+// The exploration draws the NEXT simStep will make (neo/Column.cpp:126-131), in
+// column visit order (neo/Agent.cpp:155-156,212), obtained by replaying a COPY of
+// the generator.  The draws do not depend on the network state, so the copy
+// yields exactly what Column::simStep will see.  u,v: [n_columns][3].
+int ref_peek_noise(void* h, float* u, float* v) {
+  Ref& r = *static_cast<Ref*>(h);
+  if (r.cfg.variant != BIDI_NEO_AGENT) return -1;
+  std::mt19937 g = r.gen;
+  const int L = r.cfg.n_layers;
+  size_t k = 0;
+  auto visit_col = [&](float stddev, float brk) {
+    std::uniform_real_distribution<float> dist01(0.0f, 1.0f);
+    std::normal_distribution<float> pertDist(0.0f, stddev);
+    for (int a = 0; a < BIDI_COLUMN_ACTIONS; a++, k++) {
+      u[k] = dist01(g);
+      v[k] = (u[k] < brk) ? dist01(g) : pertDist(g);
+    }
+  };
+  for (int l = L - 1; l >= 0; l--)
+    for (size_t pi = 0; pi < r.ag._layers[l]._predictionNodes.size(); pi++)
+      visit_col(r.ld[l].col_expl_stddev, r.ld[l].col_expl_break);
+  for (size_t pi = 0; pi < r.ag._inputPredictionNodes.size(); pi++)
+    visit_col(r.cfg.col_expl_stddev, r.cfg.col_expl_break);
+  return 0;
+}
+
+// Per-unit list lengths, as bidi_conn_counts.
+int ref_conn_counts(void* h, int which, int layer, int* counts) {
+  Ref& r = *static_cast<Ref*>(h);
+  const int L = r.cfg.n_layers;
+  int k = 0;
+#define COUNT_CODER(C)                                                                              \
+  if (which == BIDI_FF_W) { for (auto& n : (C)._hidden) counts[k++] = (int)n._feedForwardConnections.size(); return 0; } \
+  if (which == BIDI_REC_W) { for (auto& n : (C)._hidden) counts[k++] = (int)n._recurrentConnections.size(); return 0; }  \
+  if (which == BIDI_LAT_W) { for (auto& n : (C)._hidden) counts[k++] = (int)n._lateralConnections.size(); return 0; }
+#define COUNT_NODES(N)                                                                              \
+  if (which == BIDI_FB_W) { for (auto& p : (N)) counts[k++] = (int)p._feedBackConnections.size(); return 0; }
+#define COUNT_PRED(N)                                                                               \
+  if (which == BIDI_PRED_W) { for (auto& p : (N)) counts[k++] = (int)p._predictiveConnections.size(); return 0; }
+  switch (r.cfg.variant) {
+    case BIDI_KWINNERS:
+      if (layer >= L) return -1;
+      COUNT_CODER(const_cast<sdr::RSDR&>(r.kw._layers[layer]._sdr))
+      COUNT_NODES(r.kw._layers[layer]._predictionNodes) COUNT_PRED(r.kw._layers[layer]._predictionNodes)
+      break;
+    case BIDI_ITERATIVE:
+      if (layer == L) { COUNT_NODES(r.it._inputPredictionNodes) break; }
+      COUNT_CODER(r.it._layers[layer]._sdr)
+      COUNT_NODES(r.it._layers[layer]._predictionNodes) COUNT_PRED(r.it._layers[layer]._predictionNodes)
+      break;
+    case BIDI_NEO_HIERARCHY:
+      if (layer == L) { COUNT_NODES(r.nh._inputPredictionNodes) break; }
+      COUNT_CODER(r.nh._layers[layer]._sdr)
+      COUNT_NODES(r.nh._layers[layer]._predictionNodes) COUNT_PRED(r.nh._layers[layer]._predictionNodes)
+      break;
+    case BIDI_NEO_AGENT:
+      if (layer == L) {
+        COUNT_NODES(r.ag._inputPredictionNodes)
+        if (which == BIDI_COL_INPUT) { for (auto& p : r.ag._inputPredictionNodes) counts[k++] = p._column.getNumStates(); return 0; }
+        break;
+      }
+      COUNT_CODER(r.ag._layers[layer]._sdr)
+      COUNT_NODES(r.ag._layers[layer]._predictionNodes) COUNT_PRED(r.ag._layers[layer]._predictionNodes)
+      if (which == BIDI_COL_INPUT) { for (auto& p : r.ag._layers[layer]._predictionNodes) counts[k++] = p._column.getNumStates(); return 0; }
+      break;
+  }
+  return -1;
+}
+
+} // extern "C"
