@@ -1,0 +1,8 @@
+"""bidinet_b200: B200-native engine for BIDInet's per-timestep hierarchy update.
+
+The product is the CUDA library behind include/bidinet_b200.h; this package holds
+its sources (csrc/), the build recipe and a thin ctypes binding used by the tests
+and bench.py.
+"""
+from . import config  # noqa: F401
+from .engine import ABI, BidiError, Engine, load_library  # noqa: F401

@@ -1,0 +1,899 @@
+// bidi_engine.cu -- host side of the engine and the extern "C" boundary
+// (include/bidinet_b200.h).  Builds the geometry tables and the HBM layout
+// (bidi_types.h), converts between the reference's serialised state and the slot
+// planes, and records one simStep as a CUDA graph of the kernels in
+// bidi_kernels.cuh.  There is no CPU compute path: without a CUDA device
+// bidi_create fails with BIDI_ENODEV.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "bidi_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct WinHost {
+  WinDev d;
+  std::vector<int> cx, cy, gxlo, gxhi, gylo, gyhi;
+};
+
+struct ColumnsHost {
+  std::vector<int> in_off;
+};
+
+struct LayerHost {
+  WinHost ff, rec, lat, fb, pred;
+  ColumnsHost col;
+};
+
+} // namespace
+
+struct bidi_engine {
+  bidi_config cfg;
+  std::vector<bidi_layer_desc> ld;
+  int device = 0, A = 0, L = 0, n_in = 0, ncol = 0, max_units = 0;
+  std::vector<LayerDev> layers;    // host copy, device pointers inside
+  std::vector<LayerHost> hl;
+  long long stride = 0;            // floats per agent blob
+  EngineDev P;                     // kernel argument
+  // device memory
+  float* d_blob = nullptr; float* d_in0 = nullptr; float* d_pred = nullptr;
+  float* d_rewards = nullptr; float* d_noise_u = nullptr; float* d_noise_v = nullptr; float* d_col_actions = nullptr;
+  float* d_frames = nullptr; float* d_frame_rewards = nullptr; int n_frames = 0;
+  int* d_tables = nullptr; LayerDev* d_layers = nullptr;
+  long long device_bytes = 0;
+  // pinned staging
+  float* h_in = nullptr; float* h_pred = nullptr; float* h_rewards = nullptr; float* h_noise = nullptr; float* h_actions = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // one graph per value of the learn flag
+  cudaGraphExec_t graphs[2] = {nullptr, nullptr};
+  int graph_kernels[2] = {0, 0};
+  long long launches = 0;
+  unsigned long long step_index = 0, noise_seed = 0x5DEECE66DULL;
+  // host mirror of ONE agent's blob for set/get_array
+  std::vector<float> mirror; int mirror_agent = -1; bool mirror_dirty = false;
+  std::string err;
+};
+
+namespace {
+
+int fail(bidi_engine* h, int code, const std::string& msg) {
+  g_last_error = msg;
+  if (h) h->err = msg;
+  return code;
+}
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, BIDI_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+
+// ------------------------------------------------------------------ geometry
+// Window centres exactly as the reference computes them (sdr/RSDR.cpp:33-41):
+// fp32 ratio, fp32 product, std::round (half away from zero), truncation to int.
+void build_win(WinHost& w, int uw, int uh, int tw, int th, int r, bool identity, bool excl) {
+  WinDev& d = w.d;
+  memset(&d, 0, sizeof(d));
+  d.uw = uw; d.uh = uh; d.tw = tw; d.th = th; d.r = r; d.excl = excl ? 1 : 0; d.U = uw * uh;
+  d.w_off = -1; d.tr_off = -1;
+  w.cx.assign(uw, 0); w.cy.assign(uh, 0);
+  const float rx = static_cast<float>(tw) / static_cast<float>(uw);
+  const float ry = static_cast<float>(th) / static_cast<float>(uh);
+  for (int x = 0; x < uw; x++) w.cx[x] = identity ? x : static_cast<int>(std::round(x * rx));
+  for (int y = 0; y < uh; y++) w.cy[y] = identity ? y : static_cast<int>(std::round(y * ry));
+  w.gxlo.assign(tw, 0); w.gxhi.assign(tw, -1); w.gylo.assign(th, 0); w.gyhi.assign(th, -1);
+  if (r < 0) { d.dxn = d.dyn = d.nslots = 0; return; }
+  const int span = 2 * r + 1;
+  d.absx = span >= tw; d.absy = span >= th;
+  d.dxn = d.absx ? tw : span; d.dyn = d.absy ? th : span;
+  d.nslots = d.dxn * d.dyn;
+  auto ranges = [r](const std::vector<int>& c, int tn, std::vector<int>& lo, std::vector<int>& hi) {
+    for (int t = 0; t < tn; t++) {
+      int l = (int)c.size(), hgh = -1;
+      for (int u = 0; u < (int)c.size(); u++)
+        if (std::abs(c[u] - t) <= r) { l = std::min(l, u); hgh = std::max(hgh, u); }
+      lo[t] = l; hi[t] = hgh;
+    }
+  };
+  ranges(w.cx, tw, w.gxlo, w.gxhi);
+  ranges(w.cy, th, w.gylo, w.gyhi);
+}
+
+// Host twin of bidi::for_each_conn: f(slot, target) in the reference's list order.
+template <class F> void for_each_conn_host(const WinHost& w, int ux, int uy, F&& f) {
+  const WinDev& d = w.d;
+  if (d.r < 0) return;
+  const int cx = w.cx[ux], cy = w.cy[uy];
+  for (int sx = 0; sx < d.dxn; sx++) {
+    const int tx = d.absx ? sx : cx - d.r + sx;
+    if (tx < 0 || tx >= d.tw || std::abs(tx - cx) > d.r) continue;
+    for (int sy = 0; sy < d.dyn; sy++) {
+      const int ty = d.absy ? sy : cy - d.r + sy;
+      if (ty < 0 || ty >= d.th || std::abs(ty - cy) > d.r) continue;
+      if (d.excl && tx == cx && ty == cy) continue;
+      f(sx * d.dyn + sy, tx + ty * d.tw);
+    }
+  }
+}
+long long conn_total(const WinHost& w) {
+  long long n = 0;
+  for (int uy = 0; uy < w.d.uh; uy++)
+    for (int ux = 0; ux < w.d.uw; ux++) for_each_conn_host(w, ux, uy, [&](int, int) { n++; });
+  return n;
+}
+
+struct Allocator {
+  long long top = 0;
+  long long take(long long n) { long long o = top; top += (n + 31) / 32 * 32; return o; }
+};
+
+bool is_iter(int v) { return v != BIDI_KWINNERS; }
+bool is_traced(int v) { return v == BIDI_NEO_HIERARCHY || v == BIDI_NEO_AGENT; }
+
+// ------------------------------------------------------------------ array table
+// How a serialised array (include/bidinet_b200.h enum bidi_array) maps to storage.
+struct ArrayRef {
+  enum Kind { NONE, PLANE, LIST, DENSE_IN, DENSE_PRED } kind = NONE;
+  long long off = 0, len = 0;   // PLANE: blob offset and length
+  const WinHost* win = nullptr; // LIST
+  bool trace = false;
+};
+
+ArrayRef find_array(const bidi_engine* h, int which, int layer) {
+  ArrayRef r;
+  const int L = h->L, V = h->cfg.variant;
+  if (layer < 0 || layer > L) return r;
+  auto plane = [&](long long off, long long len) { r.kind = ArrayRef::PLANE; r.off = off; r.len = len; return r; };
+  auto list = [&](const WinHost& w, bool tr) {
+    if (w.d.r < 0 || (tr ? w.d.tr_off : w.d.w_off) < 0) return r;
+    r.kind = ArrayRef::LIST; r.win = &w; r.trace = tr; r.len = conn_total(w); return r;
+  };
+  if (which == BIDI_PREDICTION) {
+    if (V != BIDI_KWINNERS || layer != 0) return r;
+    r.kind = ArrayRef::DENSE_PRED; r.len = h->n_in; return r;
+  }
+  const LayerDev& D = h->layers[layer];
+  const LayerHost& H = h->hl[layer];
+  if (which <= BIDI_REC_TRACE) {
+    if (layer >= L) return r;
+    switch (which) {
+      case BIDI_VIS_INPUT:
+        if (layer == 0) { r.kind = ArrayRef::DENSE_IN; r.len = h->n_in; return r; }
+        return plane(D.vis_input, D.nv);
+      case BIDI_VIS_RECON: return plane(D.vis_recon, D.nv);
+      case BIDI_HID_THRESHOLD: return plane(D.thr, D.nh);
+      case BIDI_HID_STATE: return plane(D.state, D.nh);
+      case BIDI_HID_STATE_PREV: return plane(D.state_prev, D.nh);
+      case BIDI_HID_ACTIVATION: return plane(D.act, D.nh);
+      case BIDI_HID_RECON: return plane(D.recon, D.nh);
+      case BIDI_HID_SPIKE: return is_iter(V) ? plane(D.spike, D.nh) : r;
+      case BIDI_HID_SPIKE_PREV: return is_iter(V) ? plane(D.spike_prev, D.nh) : r;
+      case BIDI_FF_W: return list(H.ff, false);
+      case BIDI_REC_W: return list(H.rec, false);
+      case BIDI_LAT_W: return is_iter(V) ? list(H.lat, false) : r;
+      case BIDI_FF_TRACE: return is_traced(V) ? list(H.ff, true) : r;
+      case BIDI_REC_TRACE: return is_traced(V) ? list(H.rec, true) : r;
+    }
+    return r;
+  }
+  if (layer == L && V == BIDI_KWINNERS) return r;
+  switch (which) {
+    case BIDI_P_STATE:
+      if (layer == L) { r.kind = ArrayRef::DENSE_PRED; r.len = h->n_in; return r; }
+      return plane(D.p_state, D.pn);
+    case BIDI_P_STATE_PREV: return plane(D.p_state_prev, D.pn);
+    case BIDI_P_ACTIVATION: return plane(D.p_act, D.pn);
+    case BIDI_P_ACTIVATION_PREV: return plane(D.p_act_prev, D.pn);
+    case BIDI_P_BASELINE: return layer == L ? r : plane(D.p_baseline, D.pn);
+    case BIDI_FB_W: return list(H.fb, false);
+    case BIDI_PRED_W: return layer == L ? r : list(H.pred, false);
+  }
+  if (V != BIDI_NEO_AGENT) return r;
+  const ColumnsDev& C = D.col;
+  const long long tot = C.tot_in, nc = (long long)C.n * C.cells;
+  switch (which) {
+    case BIDI_COL_INPUT: return plane(C.inputs, tot);
+    case BIDI_COL_RECON_ERR: return plane(C.recon_err, tot);
+    case BIDI_COL_FF_W: return plane(C.ff_w, tot * C.cells);
+    case BIDI_COL_LAT_W: return plane(C.lat_w, nc * C.cells);
+    case BIDI_COL_THRESHOLD: return plane(C.thr, nc);
+    case BIDI_COL_ACTIVATION: return plane(C.act, nc);
+    case BIDI_COL_SPIKE: return plane(C.spike, nc);
+    case BIDI_COL_SPIKE_PREV: return plane(C.spike_prev, nc);
+    case BIDI_COL_STATE: return plane(C.state, nc);
+    case BIDI_COL_Q_W: return plane(C.q_w, nc);
+    case BIDI_COL_Q_TRACE: return plane(C.q_tr, nc);
+    case BIDI_COL_ACT_STATE: return plane(C.a_state, (long long)C.n * 3);
+    case BIDI_COL_ACT_EXPL: return plane(C.a_expl, (long long)C.n * 3);
+    case BIDI_COL_ACT_W: return plane(C.a_w, nc * 3);
+    case BIDI_COL_ACT_TRACE: return plane(C.a_tr, nc * 3);
+    case BIDI_COL_PREV_VALUE: return plane(C.prev_value, C.n);
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------ mirror
+int mirror_flush(bidi_engine* h) {
+  if (h->mirror_agent >= 0 && h->mirror_dirty) {
+    CU(cudaMemcpyAsync(h->d_blob + (long long)h->mirror_agent * h->stride, h->mirror.data(),
+                       sizeof(float) * h->stride, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->mirror_dirty = false;
+  }
+  return BIDI_OK;
+}
+int mirror_load(bidi_engine* h, int agent) {
+  if (h->mirror_agent == agent) return BIDI_OK;
+  int rc = mirror_flush(h);
+  if (rc) return rc;
+  h->mirror.resize((size_t)h->stride);
+  CU(cudaMemcpyAsync(h->mirror.data(), h->d_blob + (long long)agent * h->stride, sizeof(float) * h->stride,
+                     cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->mirror_agent = agent;
+  h->mirror_dirty = false;
+  return BIDI_OK;
+}
+// device state is about to change: the mirror must be written back and dropped
+int mirror_release(bidi_engine* h) {
+  int rc = mirror_flush(h);
+  h->mirror_agent = -1;
+  return rc;
+}
+
+// Serialised list <-> slot planes inside a host blob image.
+template <class F> void walk_list(const WinHost& w, bool trace, float* blob, F&& f) {
+  float* base = blob + (trace ? w.d.tr_off : w.d.w_off);
+  const long long U = w.d.U;
+  for (int uy = 0; uy < w.d.uh; uy++)
+    for (int ux = 0; ux < w.d.uw; ux++) {
+      const long long u = ux + (long long)uy * w.d.uw;
+      for_each_conn_host(w, ux, uy, [&](int s, int) { f(base[(long long)s * U + u]); });
+    }
+}
+
+// ------------------------------------------------------------------ launches
+inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+constexpr int kBlock = 128;
+
+struct Recorder {
+  bidi_engine* h;
+  int kernels = 0;
+  template <class K, class... Args> void launch(K kernel, long long threads, Args... args) {
+    kernel<<<grid_for(threads, kBlock), kBlock, 0, h->stream>>>(h->P, args...);
+    kernels++;
+  }
+};
+
+void record_columns(Recorder& R, int l) {
+  bidi_engine* h = R.h;
+  const ColumnsDev& C = h->layers[l].col;
+  const long long warps = (long long)h->A * C.n;
+  const size_t smem = sizeof(float) * BIDI_COL_WARPS * (2 * (size_t)C.max_in + 96);
+  bidi::k_columns<<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, l);
+  R.kernels++;
+}
+
+// One simStep as a sequence of kernel launches on h->stream (captured into a graph).
+void record_step(Recorder& R, bool learn) {
+  bidi_engine* h = R.h;
+  const int L = h->L, V = h->cfg.variant;
+  const long long A = h->A;
+  auto& ly = h->layers;
+  if (V == BIDI_KWINNERS) {
+    // sdr/PredictiveRSDR.cpp:102-112
+    for (int l = 0; l < L; l++) {
+      R.launch(bidi::k_kw_activate, A * ly[l].nh, l);
+      R.launch(bidi::k_kw_inhibit, A * ly[l].nh, l, ly[l].act, ly[l].state, l < L - 1 ? ly[l + 1].vis_input : -1LL);
+      R.launch(bidi::k_reconstruct, A * (ly[l].nv + ly[l].nh), l, ly[l].state, 0, 0.0f, 0);
+    }
+    // :115-171
+    for (int l = L - 1; l >= 0; l--) {
+      R.launch(bidi::k_predict, A * ly[l].pn, l, (int)learn);
+      R.launch(bidi::k_kw_inhibit, A * ly[l].nh, l, ly[l].p_act, ly[l].p_state, -1LL);
+    }
+    // :173-185
+    if (learn) for (int l = 0; l < L; l++) R.launch(bidi::k_kw_learn, A * ly[l].nh, l);
+    R.launch(bidi::k_step_end, A * h->max_units, h->max_units);
+    // :188-193
+    R.launch(bidi::k_kw_predict_input, A * h->n_in);
+    return;
+  }
+  for (int l = 0; l < L; l++) {
+    const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
+    if (V == BIDI_ITERATIVE) { // sdr/IRSDR.cpp:125-216
+      const int settle = ly[l].iter_settle, measure = ly[l].iter_measure;
+      for (int it = 0; it < settle; it++) {
+        R.launch(bidi::k_ic_sweep, nh, l, (int)(it == 0), 0, 0.0f);
+        R.launch(bidi::k_reconstruct, nvh, l, ly[l].spike, 0, 0.0f, 1);
+      }
+      const float inv = 1.0f / measure;
+      for (int it = 0; it < measure; it++) {
+        R.launch(bidi::k_ic_sweep, nh, l, (int)(settle == 0 && it == 0), 1, inv);
+        R.launch(bidi::k_reconstruct, nvh, l, ly[l].spike, 0, 0.0f, 1);
+      }
+      R.launch(bidi::k_reconstruct, nvh, l, ly[l].state, 0, 0.0f, 0);
+      if (l < L - 1) R.launch(bidi::k_ic_finish, nh, l, 0, 0.0f);
+    } else { // neo/SparseCoder.cpp:116-176
+      const int iter = ly[l].iter_settle;
+      float counter = 0.0f;
+      for (int it = 0; it < iter; it++) {
+        R.launch(bidi::k_ic_sweep, nh, l, (int)(it == 0), 2, 0.0f);
+        counter += 1.0f;
+        R.launch(bidi::k_reconstruct, nvh, l, ly[l].state, 1, 1.0f / counter, 1);
+      }
+      R.launch(bidi::k_ic_finish, nh, l, 1, 1.0f / counter);
+    }
+  }
+  for (int l = L - 1; l >= 0; l--) {
+    if (V == BIDI_NEO_AGENT) record_columns(R, l);
+    R.launch(bidi::k_predict, A * ly[l].pn, l, (int)learn);
+  }
+  if (V == BIDI_NEO_AGENT) record_columns(R, L);
+  R.launch(bidi::k_predict_input, A * h->n_in, (int)learn);
+  if (learn)
+    for (int l = 0; l < L; l++) {
+      if (V == BIDI_ITERATIVE) R.launch(bidi::k_ic_learn, A * ly[l].nh, l);
+      else R.launch(bidi::k_neo_learn, A * ly[l].nh, l);
+    }
+  R.launch(bidi::k_step_end, A * h->max_units, h->max_units);
+}
+
+int ensure_graph(bidi_engine* h, bool learn) {
+  cudaGraphExec_t& exec = h->graphs[learn];
+  if (exec) return BIDI_OK;
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  Recorder R{h};
+  record_step(R, learn);
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  if (e != cudaSuccess) return fail(h, BIDI_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, BIDI_ECUDA, std::string("kernel launch during capture: ") + cudaGetErrorString(e));
+  CU(cudaGraphInstantiate(&exec, graph, 0));
+  CU(cudaGraphDestroy(graph));
+  h->graph_kernels[learn] = R.kernels;
+  return BIDI_OK;
+}
+
+int run_step(bidi_engine* h, bool learn, bool device_noise) {
+  int rc = mirror_release(h);
+  if (rc) return rc;
+  if (h->cfg.variant == BIDI_NEO_AGENT && device_noise) {
+    // the step counter changes every call, so this launch stays outside the graph
+    bidi::k_noise<<<grid_for((long long)h->A * h->ncol, kBlock), kBlock, 0, h->stream>>>(
+        h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index);
+    h->launches++;
+  }
+  rc = ensure_graph(h, learn);
+  if (rc) return rc;
+  CU(cudaGraphLaunch(h->graphs[learn], h->stream));
+  h->launches += h->graph_kernels[learn];
+  h->step_index++;
+  return BIDI_OK;
+}
+
+void fill_columns_params(ColumnsDev& C, int cells, int iter, float sparsity, float leak, float gamma, float gl,
+                         float aff, float alat, float athr, float aq, float aact, float std, float brk) {
+  C.cells = cells; C.iter = iter; C.sparsity = sparsity; C.leak = leak; C.gamma = gamma; C.gamma_lambda = gl;
+  C.a_ff = aff; C.a_lat = alat; C.a_thr = athr; C.a_q = aq; C.a_act = aact; C.expl_std = std; C.expl_break = brk;
+}
+
+} // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+const char* bidi_last_error(const bidi_engine* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+void bidi_destroy(bidi_engine* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& g : h->graphs) if (g) cudaGraphExecDestroy(g);
+  cudaFree(h->d_blob); cudaFree(h->d_in0); cudaFree(h->d_pred); cudaFree(h->d_rewards); cudaFree(h->d_noise_u);
+  cudaFree(h->d_noise_v); cudaFree(h->d_col_actions); cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
+  cudaFree(h->d_tables); cudaFree(h->d_layers);
+  cudaFreeHost(h->h_in); cudaFreeHost(h->h_pred); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_noise); cudaFreeHost(h->h_actions);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_agents, int device, bidi_engine** out) {
+  bidi_engine* h = nullptr;
+  if (!cfg || !layers || !out) return fail(h, BIDI_EINVAL, "bidi_create: null argument");
+  *out = nullptr;
+  if (cfg->variant < BIDI_KWINNERS || cfg->variant > BIDI_NEO_AGENT) return fail(h, BIDI_EINVAL, "bidi_create: unknown variant");
+  if (cfg->n_layers < 1 || cfg->n_layers > BIDI_MAX_LAYERS) return fail(h, BIDI_EINVAL, "bidi_create: n_layers out of range");
+  if (n_agents < 1 || cfg->in_width < 1 || cfg->in_height < 1) return fail(h, BIDI_EINVAL, "bidi_create: bad sizes");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(h, BIDI_ENODEV, "bidi_create: no usable CUDA device (this engine has no CPU path)");
+  }
+  const int V = cfg->variant, L = cfg->n_layers;
+  for (int l = 0; l < L; l++) {
+    const bidi_layer_desc& d = layers[l];
+    if (d.width < 1 || d.height < 1 || d.r_ff < 0 || d.r_lat < 0 || d.r_pred < 0 || d.r_rec < -1 || (l < L - 1 && d.r_fb < 0))
+      return fail(h, BIDI_EINVAL, "bidi_create: bad layer descriptor");
+    if (V == BIDI_ITERATIVE && d.iter_settle + d.iter_measure < 1) return fail(h, BIDI_EINVAL, "bidi_create: no coder iterations");
+    if ((V == BIDI_NEO_HIERARCHY || V == BIDI_NEO_AGENT) && d.iter_settle < 1) return fail(h, BIDI_EINVAL, "bidi_create: no coder iterations");
+    if (V == BIDI_NEO_AGENT && (d.col_cells < 1 || d.col_cells > 32 || d.col_iter < 1))
+      return fail(h, BIDI_EINVAL, "bidi_create: columns need 1..32 cells and >= 1 iteration");
+  }
+  if (V != BIDI_KWINNERS && cfg->r_infb < 0) return fail(h, BIDI_EINVAL, "bidi_create: bad input feedback radius");
+  if (V == BIDI_NEO_AGENT && (cfg->col_cells < 1 || cfg->col_cells > 32 || cfg->col_iter < 1))
+    return fail(h, BIDI_EINVAL, "bidi_create: columns need 1..32 cells and >= 1 iteration");
+
+  h = new bidi_engine();
+  h->cfg = *cfg; h->ld.assign(layers, layers + L);
+  h->device = device; h->A = n_agents; h->L = L; h->n_in = cfg->in_width * cfg->in_height;
+  h->layers.assign(L + 1, LayerDev());
+  h->hl.resize(L + 1);
+  for (auto& d : h->layers) memset(&d, 0, sizeof(LayerDev));
+
+  // ---- geometry and blob layout
+  Allocator al;
+  int vw = cfg->in_width, vh = cfg->in_height;
+  h->max_units = h->n_in;
+  for (int l = 0; l <= L; l++) {
+    LayerDev& D = h->layers[l];
+    LayerHost& H = h->hl[l];
+    if (l < L) {
+      const bidi_layer_desc& d = layers[l];
+      D.vw = vw; D.vh = vh; D.hw = d.width; D.hh = d.height; D.nv = vw * vh; D.nh = d.width * d.height;
+      h->max_units = std::max(h->max_units, D.nh);
+      D.vis_input = l == 0 ? -1 : al.take(D.nv);
+      D.vis_recon = al.take(D.nv);
+      D.thr = al.take(D.nh); D.state = al.take(D.nh); D.state_prev = al.take(D.nh); D.act = al.take(D.nh);
+      D.recon = al.take(D.nh); D.spike = al.take(D.nh); D.spike_prev = al.take(D.nh);
+      build_win(H.ff, D.hw, D.hh, vw, vh, d.r_ff, false, false);
+      build_win(H.rec, D.hw, D.hh, D.hw, D.hh, d.r_rec, true, true);
+      build_win(H.lat, D.hw, D.hh, D.hw, D.hh, d.r_lat, true, true);
+      H.ff.d.w_off = al.take((long long)H.ff.d.nslots * D.nh);
+      if (d.r_rec >= 0) H.rec.d.w_off = al.take((long long)H.rec.d.nslots * D.nh);
+      if (is_iter(V)) H.lat.d.w_off = al.take((long long)H.lat.d.nslots * D.nh);
+      if (is_traced(V)) {
+        H.ff.d.tr_off = al.take((long long)H.ff.d.nslots * D.nh);
+        if (d.r_rec >= 0) H.rec.d.tr_off = al.take((long long)H.rec.d.nslots * D.nh);
+      }
+      D.pn = D.nh;
+      D.p_state = al.take(D.pn);
+      if (l < L - 1) build_win(H.fb, D.hw, D.hh, layers[l + 1].width, layers[l + 1].height, d.r_fb, false, false);
+      else build_win(H.fb, D.hw, D.hh, 1, 1, -1, true, false);
+      build_win(H.pred, D.hw, D.hh, D.hw, D.hh, d.r_pred, true, false);
+      if (l < L - 1) H.fb.d.w_off = al.take((long long)H.fb.d.nslots * D.pn);
+      H.pred.d.w_off = al.take((long long)H.pred.d.nslots * D.pn);
+      D.learn_ff = d.learn_ff; D.learn_rec = d.learn_rec; D.learn_lat = d.learn_lat; D.learn_threshold = d.learn_threshold;
+      D.learn_fb = d.learn_fb; D.learn_pred = d.learn_pred; D.sparsity = d.sparsity;
+      D.avg_surprise_decay = d.avg_surprise_decay; D.attention_factor = d.attention_factor;
+      D.iter_settle = d.iter_settle; D.iter_measure = d.iter_measure; D.leak = d.leak; D.lambda = d.lambda;
+      D.weight_decay = d.weight_decay; D.max_weight_delta = d.max_weight_delta;
+      D.baseline_decay = d.baseline_decay; D.sensitivity = d.sensitivity;
+      vw = d.width; vh = d.height;
+    } else {
+      if (V == BIDI_KWINNERS) continue;
+      D.pn = h->n_in;
+      D.p_state = -1;
+      D.hw = cfg->in_width; D.hh = cfg->in_height;
+      build_win(H.fb, cfg->in_width, cfg->in_height, layers[0].width, layers[0].height, cfg->r_infb, false, false);
+      build_win(H.pred, cfg->in_width, cfg->in_height, 1, 1, -1, true, false);
+      build_win(H.ff, 1, 1, 1, 1, -1, true, false); build_win(H.rec, 1, 1, 1, 1, -1, true, false); build_win(H.lat, 1, 1, 1, 1, -1, true, false);
+      H.fb.d.w_off = al.take((long long)H.fb.d.nslots * D.pn);
+      D.learn_fb = cfg->learn_infb;
+    }
+    D.p_state_prev = al.take(D.pn); D.p_act = al.take(D.pn); D.p_act_prev = al.take(D.pn);
+    D.p_baseline = al.take(D.pn); D.p_mod = al.take(D.pn);
+    if (V == BIDI_NEO_AGENT) {
+      ColumnsDev& C = D.col;
+      C.n = D.pn;
+      if (l < L) {
+        const bidi_layer_desc& d = layers[l];
+        fill_columns_params(C, d.col_cells, d.col_iter, d.col_sparsity, d.col_leak, d.col_gamma, d.col_gamma_lambda, d.col_alpha_ff,
+                            d.col_alpha_lat, d.col_alpha_threshold, d.col_alpha_q, d.col_alpha_action, d.col_expl_stddev, d.col_expl_break);
+      } else {
+        fill_columns_params(C, cfg->col_cells, cfg->col_iter, cfg->col_sparsity, cfg->col_leak, cfg->col_gamma, cfg->col_gamma_lambda,
+                            cfg->col_alpha_ff, cfg->col_alpha_lat, cfg->col_alpha_threshold, cfg->col_alpha_q, cfg->col_alpha_action,
+                            cfg->col_expl_stddev, cfg->col_expl_break);
+      }
+      // nIn = |pred| + 2|fb|  (neo/Agent.cpp:90,137)
+      H.col.in_off.assign(C.n + 1, 0);
+      C.max_in = 0;
+      for (int i = 0; i < C.n; i++) {
+        const int ux = i % H.fb.d.uw, uy = i / H.fb.d.uw;
+        int nfb = 0, npr = 0;
+        for_each_conn_host(H.fb, ux, uy, [&](int, int) { nfb++; });
+        for_each_conn_host(H.pred, ux, uy, [&](int, int) { npr++; });
+        const int nin = npr + 2 * nfb;
+        H.col.in_off[i + 1] = H.col.in_off[i] + nin;
+        C.max_in = std::max(C.max_in, nin);
+      }
+      C.tot_in = H.col.in_off[C.n];
+      const long long nc = (long long)C.n * C.cells;
+      C.inputs = al.take(C.tot_in); C.recon_err = al.take(C.tot_in);
+      C.ff_w = al.take((long long)C.tot_in * C.cells); C.lat_w = al.take(nc * C.cells);
+      C.thr = al.take(nc); C.act = al.take(nc); C.spike = al.take(nc); C.spike_prev = al.take(nc); C.state = al.take(nc);
+      C.q_w = al.take(nc); C.q_tr = al.take(nc); C.a_state = al.take(C.n * 3LL); C.a_expl = al.take(C.n * 3LL);
+      C.a_w = al.take(nc * 3); C.a_tr = al.take(nc * 3); C.prev_value = al.take(C.n);
+    }
+  }
+  h->stride = al.top;
+  if (V == BIDI_NEO_AGENT) { // visit order: layers top -> bottom, then the input nodes
+    int base = 0;
+    for (int l = L - 1; l >= 0; l--) { h->layers[l].col.noise_base = base; base += h->layers[l].col.n; }
+    h->layers[L].col.noise_base = base; base += h->layers[L].col.n;
+    h->ncol = base;
+  }
+
+  // ---- device memory
+  if (cudaSetDevice(device) != cudaSuccess) { bidi_destroy(h); return fail(nullptr, BIDI_ENODEV, "bidi_create: cudaSetDevice failed"); }
+  auto bail = [&](int code, const std::string& msg) { bidi_destroy(h); h = nullptr; return fail(nullptr, code, msg); };
+#define CU_CREATE(call)                                                                            \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return bail(e_ == cudaErrorMemoryAllocation ? BIDI_ENOMEM : BIDI_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+  CU_CREATE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU_CREATE(cudaEventCreate(&h->ev0));
+  CU_CREATE(cudaEventCreate(&h->ev1));
+  const size_t A = (size_t)n_agents, nin = (size_t)h->n_in, nn = std::max<size_t>(1, (size_t)h->ncol * 3);
+  CU_CREATE(cudaMalloc(&h->d_blob, sizeof(float) * A * (size_t)h->stride));
+  CU_CREATE(cudaMemsetAsync(h->d_blob, 0, sizeof(float) * A * (size_t)h->stride, h->stream));
+  CU_CREATE(cudaMalloc(&h->d_in0, sizeof(float) * A * nin));
+  CU_CREATE(cudaMalloc(&h->d_pred, sizeof(float) * A * nin));
+  CU_CREATE(cudaMalloc(&h->d_rewards, sizeof(float) * A));
+  CU_CREATE(cudaMalloc(&h->d_noise_u, sizeof(float) * A * nn));
+  CU_CREATE(cudaMalloc(&h->d_noise_v, sizeof(float) * A * nn));
+  CU_CREATE(cudaMalloc(&h->d_col_actions, sizeof(float) * A * nn));
+  CU_CREATE(cudaMemsetAsync(h->d_in0, 0, sizeof(float) * A * nin, h->stream));
+  CU_CREATE(cudaMemsetAsync(h->d_pred, 0, sizeof(float) * A * nin, h->stream));
+  CU_CREATE(cudaMemsetAsync(h->d_rewards, 0, sizeof(float) * A, h->stream));
+  CU_CREATE(cudaMemsetAsync(h->d_noise_u, 0, sizeof(float) * A * nn, h->stream));
+  CU_CREATE(cudaMemsetAsync(h->d_noise_v, 0, sizeof(float) * A * nn, h->stream));
+  CU_CREATE(cudaMemsetAsync(h->d_col_actions, 0, sizeof(float) * A * nn, h->stream));
+  h->device_bytes = (long long)sizeof(float) * (long long)(A * (size_t)h->stride + 2 * A * nin + A + 3 * A * nn);
+  CU_CREATE(cudaMallocHost(&h->h_in, sizeof(float) * A * nin));
+  CU_CREATE(cudaMallocHost(&h->h_pred, sizeof(float) * A * nin));
+  CU_CREATE(cudaMallocHost(&h->h_rewards, sizeof(float) * A));
+  CU_CREATE(cudaMallocHost(&h->h_noise, sizeof(float) * 2 * A * nn));
+  CU_CREATE(cudaMallocHost(&h->h_actions, sizeof(float) * A * nn));
+
+  // ---- integer tables: one device pool, pointers patched into the WinDev copies
+  std::vector<int> pool;
+  struct Patch { const int** dst; size_t off; };
+  std::vector<Patch> patches;
+  auto push = [&](const std::vector<int>& v, const int** dst) {
+    patches.push_back({dst, pool.size()});
+    pool.insert(pool.end(), v.begin(), v.end());
+    if (v.empty()) pool.push_back(0);
+  };
+  for (int l = 0; l <= L; l++) {
+    LayerHost& H = h->hl[l];
+    for (WinHost* w : {&H.ff, &H.rec, &H.lat, &H.fb, &H.pred}) {
+      push(w->cx, &w->d.cx); push(w->cy, &w->d.cy);
+      push(w->gxlo, &w->d.gx_lo); push(w->gxhi, &w->d.gx_hi); push(w->gylo, &w->d.gy_lo); push(w->gyhi, &w->d.gy_hi);
+    }
+    if (V == BIDI_NEO_AGENT) push(H.col.in_off, &h->layers[l].col.in_off);
+  }
+  CU_CREATE(cudaMalloc(&h->d_tables, sizeof(int) * pool.size()));
+  CU_CREATE(cudaMemcpyAsync(h->d_tables, pool.data(), sizeof(int) * pool.size(), cudaMemcpyHostToDevice, h->stream));
+  for (auto& p : patches) *p.dst = h->d_tables + p.off;
+  for (int l = 0; l <= L; l++) {
+    LayerDev& D = h->layers[l];
+    LayerHost& H = h->hl[l];
+    D.ff = H.ff.d; D.rec = H.rec.d; D.lat = H.lat.d; D.fb = H.fb.d; D.pred = H.pred.d;
+  }
+  CU_CREATE(cudaMalloc(&h->d_layers, sizeof(LayerDev) * (L + 1)));
+  CU_CREATE(cudaMemcpyAsync(h->d_layers, h->layers.data(), sizeof(LayerDev) * (L + 1), cudaMemcpyHostToDevice, h->stream));
+  h->device_bytes += (long long)(sizeof(int) * pool.size() + sizeof(LayerDev) * (L + 1));
+
+  EngineDev& P = h->P;
+  P.variant = V; P.L = L; P.A = n_agents; P.n_in = h->n_in;
+  P.blob = h->d_blob; P.stride = h->stride; P.in0 = h->d_in0; P.pred_out = h->d_pred;
+  P.rewards = h->d_rewards; P.noise_u = h->d_noise_u; P.noise_v = h->d_noise_v; P.col_actions = h->d_col_actions;
+  P.ncol = h->ncol; P.layers = h->d_layers;
+  CU_CREATE(cudaStreamSynchronize(h->stream));
+
+  // thresholds start at init_threshold (sdr/RSDR.cpp:43, neo/Column.cpp:27); everything else at 0
+  {
+    std::vector<float> img((size_t)h->stride, 0.0f);
+    for (int l = 0; l <= L; l++) {
+      const LayerDev& D = h->layers[l];
+      if (l < L) for (int i = 0; i < D.nh; i++) img[D.thr + i] = cfg->init_threshold;
+      if (V == BIDI_NEO_AGENT) for (long long i = 0; i < (long long)D.col.n * D.col.cells; i++) img[D.col.thr + i] = cfg->init_threshold;
+    }
+    for (int a = 0; a < n_agents; a++)
+      CU_CREATE(cudaMemcpyAsync(h->d_blob + (long long)a * h->stride, img.data(), sizeof(float) * h->stride, cudaMemcpyHostToDevice, h->stream));
+    CU_CREATE(cudaStreamSynchronize(h->stream));
+  }
+  // the column kernel may need more than the default 48 KB of dynamic shared memory
+  if (V == BIDI_NEO_AGENT) {
+    int max_in = 0;
+    for (auto& D : h->layers) max_in = std::max(max_in, D.col.max_in);
+    const size_t smem = sizeof(float) * BIDI_COL_WARPS * (2 * (size_t)max_in + 96);
+    if (smem > 200 * 1024) return bail(BIDI_EINVAL, "bidi_create: column input count too large for shared memory");
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  *out = h;
+  return BIDI_OK;
+}
+
+int bidi_num_agents(const bidi_engine* h) { return h ? h->A : 0; }
+int bidi_num_inputs(const bidi_engine* h) { return h ? h->n_in : 0; }
+int bidi_num_columns(const bidi_engine* h) { return h ? h->ncol : 0; }
+long long bidi_launch_count(const bidi_engine* h) { return h ? h->launches : 0; }
+long long bidi_device_bytes(const bidi_engine* h) { return h ? h->device_bytes : 0; }
+
+long long bidi_array_len(const bidi_engine* h, int which, int layer) {
+  if (!h) return -1;
+  return find_array(h, which, layer).len;
+}
+
+int bidi_conn_counts(const bidi_engine* h, int which, int layer, int* counts, int n_units) {
+  bidi_engine* hm = const_cast<bidi_engine*>(h);
+  if (!h || !counts || layer < 0 || layer > h->L) return fail(hm, BIDI_EINVAL, "bidi_conn_counts: bad argument");
+  const LayerHost& H = h->hl[layer];
+  const WinHost* w = nullptr;
+  switch (which) {
+    case BIDI_FF_W: w = &H.ff; break;
+    case BIDI_REC_W: w = &H.rec; break;
+    case BIDI_LAT_W: w = &H.lat; break;
+    case BIDI_FB_W: w = &H.fb; break;
+    case BIDI_PRED_W: w = &H.pred; break;
+    case BIDI_COL_INPUT:
+      if (h->cfg.variant != BIDI_NEO_AGENT || n_units != h->layers[layer].col.n) return fail(hm, BIDI_EINVAL, "bidi_conn_counts: bad column query");
+      for (int i = 0; i < n_units; i++) counts[i] = H.col.in_off[i + 1] - H.col.in_off[i];
+      return BIDI_OK;
+    default: return fail(hm, BIDI_EINVAL, "bidi_conn_counts: not a list array");
+  }
+  if (n_units != w->d.U || w->cx.empty()) return fail(hm, BIDI_EINVAL, "bidi_conn_counts: unit count mismatch");
+  for (int i = 0; i < n_units; i++) {
+    int n = 0;
+    for_each_conn_host(*w, i % w->d.uw, i / w->d.uw, [&](int, int) { n++; });
+    counts[i] = n;
+  }
+  return BIDI_OK;
+}
+
+int bidi_sync(bidi_engine* h) {
+  if (!h) return fail(h, BIDI_EINVAL, "null engine");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return BIDI_OK;
+}
+
+int bidi_set_array(bidi_engine* h, int agent, int which, int layer, const float* src, long long len) {
+  if (!h || !src || agent < 0 || agent >= h->A) return fail(h, BIDI_EINVAL, "bidi_set_array: bad argument");
+  CU(cudaSetDevice(h->device));
+  const ArrayRef r = find_array(h, which, layer);
+  if (r.kind == ArrayRef::NONE || r.len != len) return fail(h, BIDI_EINVAL, "bidi_set_array: no such array or length mismatch");
+  if (r.kind == ArrayRef::DENSE_IN || r.kind == ArrayRef::DENSE_PRED) {
+    float* dst = (r.kind == ArrayRef::DENSE_IN ? h->d_in0 : h->d_pred) + (long long)agent * h->n_in;
+    CU(cudaMemcpyAsync(dst, src, sizeof(float) * len, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BIDI_OK;
+  }
+  int rc = mirror_load(h, agent);
+  if (rc) return rc;
+  if (r.kind == ArrayRef::PLANE) memcpy(h->mirror.data() + r.off, src, sizeof(float) * len);
+  else walk_list(*r.win, r.trace, h->mirror.data(), [&](float& v) { v = *src++; });
+  h->mirror_dirty = true;
+  return BIDI_OK;
+}
+
+int bidi_get_array(bidi_engine* h, int agent, int which, int layer, float* dst, long long len) {
+  if (!h || !dst || agent < 0 || agent >= h->A) return fail(h, BIDI_EINVAL, "bidi_get_array: bad argument");
+  CU(cudaSetDevice(h->device));
+  const ArrayRef r = find_array(h, which, layer);
+  if (r.kind == ArrayRef::NONE || r.len != len) return fail(h, BIDI_EINVAL, "bidi_get_array: no such array or length mismatch");
+  if (r.kind == ArrayRef::DENSE_IN || r.kind == ArrayRef::DENSE_PRED) {
+    const float* s = (r.kind == ArrayRef::DENSE_IN ? h->d_in0 : h->d_pred) + (long long)agent * h->n_in;
+    CU(cudaMemcpyAsync(dst, s, sizeof(float) * len, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return BIDI_OK;
+  }
+  int rc = mirror_load(h, agent);
+  if (rc) return rc;
+  if (r.kind == ArrayRef::PLANE) memcpy(dst, h->mirror.data() + r.off, sizeof(float) * len);
+  else walk_list(*r.win, r.trace, h->mirror.data(), [&](float& v) { *dst++ = v; });
+  return BIDI_OK;
+}
+
+// The reference's createRandom draw order, replayed with the same
+// standard-library engine and distribution the reference uses.
+int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
+  if (!h || first < 0 || count < 0 || first + count > h->A) return fail(h, BIDI_EINVAL, "bidi_init_random: bad agent range");
+  CU(cudaSetDevice(h->device));
+  int rc = mirror_release(h);
+  if (rc) return rc;
+  const int L = h->L, V = h->cfg.variant;
+  const bidi_config& g = h->cfg;
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int nthreads = (int)std::min<unsigned>(hw, (unsigned)std::max(1, count));
+  std::vector<std::vector<float>> images(nthreads);
+  std::vector<std::string> errors(nthreads);
+  auto fill_agent = [&](std::vector<float>& img, unsigned seed) {
+    std::mt19937 gen(seed);
+    std::uniform_real_distribution<float> weightDist(g.init_min_w, g.init_max_w);
+    std::uniform_real_distribution<float> inhibitionDist(g.init_min_inh, g.init_max_inh);
+    std::fill(img.begin(), img.end(), 0.0f);
+    auto draw_list = [&](const WinHost& w, long long u, int ux, int uy, std::uniform_real_distribution<float>& dist) {
+      if (w.d.w_off < 0) return;
+      float* base = img.data() + w.d.w_off;
+      for_each_conn_host(w, ux, uy, [&](int s, int) { base[(long long)s * w.d.U + u] = dist(gen); });
+    };
+    auto draw_column = [&](const ColumnsDev& C, const ColumnsHost& CH, int node) { // neo/Column.cpp:22-43
+      const int in0 = CH.in_off[node], nin = CH.in_off[node + 1] - in0;
+      float* ff = img.data() + C.ff_w + (long long)C.cells * in0;
+      for (int i = 0; i < C.cells; i++) {
+        img[C.thr + (long long)node * C.cells + i] = g.init_threshold;
+        for (int j = 0; j < nin; j++) ff[(long long)i * nin + j] = weightDist(gen);
+        for (int j = 0; j < C.cells; j++) img[C.lat_w + ((long long)node * C.cells + i) * C.cells + j] = inhibitionDist(gen);
+        img[C.q_w + (long long)node * C.cells + i] = weightDist(gen);
+      }
+      for (int a = 0; a < 3; a++)
+        for (int k = 0; k < C.cells; k++) img[C.a_w + ((long long)node * 3 + a) * C.cells + k] = weightDist(gen);
+    };
+    for (int l = 0; l <= L; l++) {
+      if (l == L && V == BIDI_KWINNERS) break;
+      const LayerDev& D = h->layers[l];
+      const LayerHost& H = h->hl[l];
+      if (l < L) {
+        for (int i = 0; i < D.nh; i++) {
+          const int ux = i % D.hw, uy = i / D.hw;
+          img[D.thr + i] = g.init_threshold;
+          draw_list(H.ff, i, ux, uy, weightDist);
+          draw_list(H.rec, i, ux, uy, weightDist);
+          if (is_iter(V)) draw_list(H.lat, i, ux, uy, inhibitionDist);
+        }
+      }
+      for (int i = 0; i < D.pn; i++) {
+        const int ux = i % H.fb.d.uw, uy = i / H.fb.d.uw;
+        (void)weightDist(gen); // the node's bias: drawn, never used (sdr/PredictiveRSDR.cpp:39)
+        draw_list(H.fb, i, ux, uy, weightDist);
+        if (l < L) draw_list(H.pred, i, ux, uy, weightDist);
+        if (V == BIDI_NEO_AGENT) draw_column(D.col, H.col, i);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  std::vector<cudaError_t> cuerr(nthreads, cudaSuccess);
+  for (int t = 0; t < nthreads; t++)
+    pool.emplace_back([&, t]() {
+      cudaSetDevice(h->device);
+      images[t].resize((size_t)h->stride);
+      for (int a = first + t; a < first + count; a += nthreads) {
+        fill_agent(images[t], seed_base + (unsigned)a);
+        cudaError_t e = cudaMemcpy(h->d_blob + (long long)a * h->stride, images[t].data(), sizeof(float) * h->stride, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cuerr[t] = e; return; }
+      }
+    });
+  for (auto& t : pool) t.join();
+  for (auto e : cuerr) if (e != cudaSuccess) return fail(h, BIDI_ECUDA, std::string("bidi_init_random upload: ") + cudaGetErrorString(e));
+  return BIDI_OK;
+}
+
+int bidi_set_inputs(bidi_engine* h, const float* in) {
+  if (!h || !in) return fail(h, BIDI_EINVAL, "bidi_set_inputs: null argument");
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = sizeof(float) * (size_t)h->A * h->n_in;
+  CU(cudaStreamSynchronize(h->stream)); // the staging buffer may still be in flight
+  memcpy(h->h_in, in, bytes);
+  CU(cudaMemcpyAsync(h->d_in0, h->h_in, bytes, cudaMemcpyHostToDevice, h->stream));
+  return BIDI_OK;
+}
+
+int bidi_set_input(bidi_engine* h, int agent, int index, float value) {
+  if (!h || agent < 0 || agent >= h->A || index < 0 || index >= h->n_in) return fail(h, BIDI_EINVAL, "bidi_set_input: out of range");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->d_in0 + (long long)agent * h->n_in + index, &value, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BIDI_OK;
+}
+
+int bidi_step(bidi_engine* h, const float* rewards, const float* noise_u, const float* noise_v, int learn) {
+  if (!h) return fail(h, BIDI_EINVAL, "null engine");
+  if ((noise_u == nullptr) != (noise_v == nullptr)) return fail(h, BIDI_EINVAL, "bidi_step: noise_u and noise_v go together");
+  CU(cudaSetDevice(h->device));
+  const bool agent = h->cfg.variant == BIDI_NEO_AGENT;
+  if (agent) {
+    CU(cudaStreamSynchronize(h->stream));
+    if (rewards) memcpy(h->h_rewards, rewards, sizeof(float) * h->A);
+    else memset(h->h_rewards, 0, sizeof(float) * h->A);
+    CU(cudaMemcpyAsync(h->d_rewards, h->h_rewards, sizeof(float) * h->A, cudaMemcpyHostToDevice, h->stream));
+    if (noise_u) {
+      const size_t n = (size_t)h->A * h->ncol * 3;
+      memcpy(h->h_noise, noise_u, sizeof(float) * n);
+      memcpy(h->h_noise + n, noise_v, sizeof(float) * n);
+      CU(cudaMemcpyAsync(h->d_noise_u, h->h_noise, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpyAsync(h->d_noise_v, h->h_noise + n, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  return run_step(h, learn != 0, agent && noise_u == nullptr);
+}
+
+int bidi_get_predictions(bidi_engine* h, float* out) {
+  if (!h || !out) return fail(h, BIDI_EINVAL, "bidi_get_predictions: null argument");
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = sizeof(float) * (size_t)h->A * h->n_in;
+  CU(cudaMemcpyAsync(h->h_pred, h->d_pred, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  memcpy(out, h->h_pred, bytes);
+  return BIDI_OK;
+}
+
+int bidi_get_column_actions(bidi_engine* h, float* out) {
+  if (!h || !out || h->ncol == 0) return fail(h, BIDI_EINVAL, "bidi_get_column_actions: no columns");
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = sizeof(float) * (size_t)h->A * h->ncol * 3;
+  CU(cudaMemcpyAsync(h->h_actions, h->d_col_actions, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  memcpy(out, h->h_actions, bytes);
+  return BIDI_OK;
+}
+
+int bidi_load_frames(bidi_engine* h, const float* frames, const float* rewards, int n_frames) {
+  if (!h || !frames || n_frames < 1) return fail(h, BIDI_EINVAL, "bidi_load_frames: bad argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
+  h->d_frames = nullptr; h->d_frame_rewards = nullptr; h->n_frames = 0;
+  const size_t n = (size_t)n_frames * h->A * h->n_in;
+  CU(cudaMalloc(&h->d_frames, sizeof(float) * n));
+  CU(cudaMemcpy(h->d_frames, frames, sizeof(float) * n, cudaMemcpyHostToDevice));
+  if (rewards) {
+    CU(cudaMalloc(&h->d_frame_rewards, sizeof(float) * (size_t)n_frames * h->A));
+    CU(cudaMemcpy(h->d_frame_rewards, rewards, sizeof(float) * (size_t)n_frames * h->A, cudaMemcpyHostToDevice));
+  }
+  h->n_frames = n_frames;
+  return BIDI_OK;
+}
+
+int bidi_step_frame(bidi_engine* h, int t, int learn) {
+  if (!h || h->n_frames < 1 || t < 0) return fail(h, BIDI_EINVAL, "bidi_step_frame: no frames loaded");
+  CU(cudaSetDevice(h->device));
+  const int f = t % h->n_frames;
+  const size_t n = (size_t)h->A * h->n_in;
+  CU(cudaMemcpyAsync(h->d_in0, h->d_frames + (size_t)f * n, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->d_frame_rewards)
+    CU(cudaMemcpyAsync(h->d_rewards, h->d_frame_rewards + (size_t)f * h->A, sizeof(float) * h->A, cudaMemcpyDeviceToDevice, h->stream));
+  return run_step(h, learn != 0, h->cfg.variant == BIDI_NEO_AGENT);
+}
+
+int bidi_timer_start(bidi_engine* h) {
+  if (!h) return fail(h, BIDI_EINVAL, "null engine");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->ev0, h->stream));
+  return BIDI_OK;
+}
+int bidi_timer_stop_ms(bidi_engine* h, float* ms) {
+  if (!h || !ms) return fail(h, BIDI_EINVAL, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaEventSynchronize(h->ev1));
+  CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return BIDI_OK;
+}
+
+/* sizeof the two POD structs, so a binding can check its mirror of the header */
+int bidi_abi_sizes(int* config_bytes, int* layer_desc_bytes) {
+  if (config_bytes) *config_bytes = (int)sizeof(bidi_config);
+  if (layer_desc_bytes) *layer_desc_bytes = (int)sizeof(bidi_layer_desc);
+  return BIDI_OK;
+}
+
+} // extern "C"

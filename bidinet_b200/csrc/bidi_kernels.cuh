@@ -1,0 +1,584 @@
+// bidi_kernels.cuh -- sm_100a kernels of the per-timestep hierarchy update.
+//
+// Mapping: one thread per (agent, unit); adjacent threads own adjacent units, so a
+// warp reads one slot plane w[slot][unit..unit+31] as a single coalesced request
+// and walks the slots in the reference's list order.  All floating point is
+// written as plain a*b+c and compiled with -fmad=false: the reference's x86-64
+// build has no FMA, and spikes / k-winner ranks are discontinuous in the last ulp
+// (SURVEY section 7 "hard parts").
+#pragma once
+#include <cuda_runtime.h>
+#include "bidi_types.h"
+#include "bidi_math.h"
+
+namespace bidi {
+
+// ------------------------------------------------------------------ addressing
+__device__ __forceinline__ float* blob_of(const EngineDev& P, int a) { return P.blob + (long long)a * P.stride; }
+__device__ __forceinline__ float* vis_input_of(const EngineDev& P, const LayerDev& L, int l, int a) {
+  return l == 0 ? P.in0 + (long long)a * P.n_in : blob_of(P, a) + L.vis_input;
+}
+// prediction-node state of node layer l (l == P.L: the input nodes, dense output array)
+__device__ __forceinline__ float* p_state_of(const EngineDev& P, const LayerDev& L, int l, int a) {
+  return l == P.L ? P.pred_out + (long long)a * P.n_in : blob_of(P, a) + L.p_state;
+}
+
+// Valid slot box of unit (ux,uy): the window clipped to the target grid
+// (sdr/RSDR.cpp:53: vx >= 0 && vx < visibleWidth && ...).  Slots outside
+// [sx0,sx1]x[sy0,sy1] correspond to connections the reference never creates.
+struct SlotBox { int cx, cy, sx0, sx1, sy0, sy1; };
+__device__ __forceinline__ SlotBox slot_box(const WinDev& w, int ux, int uy) {
+  SlotBox b;
+  b.cx = w.cx[ux]; b.cy = w.cy[uy];
+  if (w.absx) { b.sx0 = max(0, b.cx - w.r); b.sx1 = min(w.tw - 1, b.cx + w.r); }
+  else { b.sx0 = max(0, w.r - b.cx); b.sx1 = min(w.dxn - 1, w.tw - 1 - b.cx + w.r); }
+  if (w.absy) { b.sy0 = max(0, b.cy - w.r); b.sy1 = min(w.th - 1, b.cy + w.r); }
+  else { b.sy0 = max(0, w.r - b.cy); b.sy1 = min(w.dyn - 1, w.th - 1 - b.cy + w.r); }
+  return b;
+}
+__device__ __forceinline__ int slot_tx(const WinDev& w, const SlotBox& b, int sx) { return w.absx ? sx : b.cx - w.r + sx; }
+__device__ __forceinline__ int slot_ty(const WinDev& w, const SlotBox& b, int sy) { return w.absy ? sy : b.cy - w.r + sy; }
+// number of list entries of the unit (clipped window, minus the excluded centre)
+__device__ __forceinline__ int slot_count(const WinDev& w, const SlotBox& b) {
+  if (w.r < 0) return 0;
+  int n = max(0, b.sx1 - b.sx0 + 1) * max(0, b.sy1 - b.sy0 + 1);
+  return (w.excl && n > 0) ? n - 1 : n;
+}
+
+// f(slot, target) for every connection of the unit, in the reference's list order.
+// The loops run over the whole slot box so that a warp stays converged on one
+// slot plane at a time; `valid` masks slots the unit does not own.
+template <class F>
+__device__ __forceinline__ void for_each_conn(const WinDev& w, int ux, int uy, F&& f) {
+  if (w.r < 0) return;
+  const SlotBox b = slot_box(w, ux, uy);
+  for (int sx = 0; sx < w.dxn; sx++) {
+    const bool okx = sx >= b.sx0 && sx <= b.sx1;
+    const int tx = slot_tx(w, b, sx);
+    for (int sy = 0; sy < w.dyn; sy++) {
+      const int ty = slot_ty(w, b, sy);
+      bool ok = okx && sy >= b.sy0 && sy <= b.sy1;
+      if (w.excl && tx == b.cx && ty == b.cy) ok = false;
+      if (ok) f(sx * w.dyn + sy, tx + ty * w.tw);
+    }
+  }
+}
+
+// Gather form of the reference's scatter reconstruction (sdr/RSDR.cpp:175-187):
+// sum over the units whose window contains target (tx,ty) of w[unit->target]*drive,
+// visited in ascending unit index = the order the scatter adds them.  A zero drive
+// contributes +-0 to a sum that starts at +0, so skipping it is exact.
+__device__ __forceinline__ float gather_recon(const WinDev& w, const float* __restrict__ wp,
+                                              const float* __restrict__ drive, int tx, int ty, bool scaled, float mult) {
+  float sum = 0.0f;
+  if (w.r < 0) return sum;
+  const int y0 = w.gy_lo[ty], y1 = w.gy_hi[ty], x0 = w.gx_lo[tx], x1 = w.gx_hi[tx];
+  for (int uy = y0; uy <= y1; uy++) {
+    const int cy = w.cy[uy];
+    const int sy = w.absy ? ty : ty - cy + w.r;
+    for (int ux = x0; ux <= x1; ux++) {
+      const int cx = w.cx[ux];
+      if (w.excl && cx == tx && cy == ty) continue;
+      const int u = ux + uy * w.uw;
+      const float d = drive[u];
+      if (d != 0.0f) {
+        const int sx = w.absx ? tx : tx - cx + w.r;
+        const float wv = wp[(long long)(sx * w.dyn + sy) * w.U + u];
+        sum += scaled ? wv * d * mult : wv * d;
+      }
+    }
+  }
+  return sum;
+}
+
+#define BIDI_THREAD_AGENT_UNIT(N)                                        \
+  const long long gid_ = (long long)blockIdx.x * blockDim.x + threadIdx.x; \
+  if (gid_ >= (long long)P.A * (N)) return;                              \
+  const int a = (int)(gid_ / (N));                                        \
+  const int i = (int)(gid_ % (N));
+
+// ------------------------------------------------------------------ k-winners coder
+// sdr/RSDR.cpp:123-133: a = -theta + sum_ff x*w + sum_rec sPrev*w
+__global__ void k_kw_activate(EngineDev P, int l) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.nh)
+  float* B = blob_of(P, a);
+  const float* x = vis_input_of(P, L, l, a);
+  const float* sprev = B + L.state_prev;
+  const float* wff = B + L.ff.w_off;
+  const float* wrec = B + L.rec.w_off;
+  const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
+  float sum = -B[L.thr + i];
+  for_each_conn(L.ff, ux, uy, [&](int s, int t) { sum += x[t] * wff[(long long)s * U + i]; });
+  for_each_conn(L.rec, ux, uy, [&](int s, int t) { sum += sprev[t] * wrec[(long long)s * U + i]; });
+  B[L.act + i] = sum;
+}
+
+// sdr/RSDR.cpp:135-145 and :148-163: rank among the lateral neighbours.  `src`
+// and `dst` are blob offsets; dst_next (>=0) also receives the state as the next
+// layer's visible input (sdr/PredictiveRSDR.cpp:108-111).
+__global__ void k_kw_inhibit(EngineDev P, int l, long long src, long long dst, long long dst_next) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.nh)
+  float* B = blob_of(P, a);
+  const float* act = B + src;
+  const int ux = i % L.hw, uy = i / L.hw;
+  const float mine = act[i];
+  int n = 0, cnt = 0;
+  for_each_conn(L.lat, ux, uy, [&](int, int t) { n++; cnt += act[t] >= mine ? 1 : 0; });
+  const float num_active = L.sparsity * (float)n;
+  const float s = (float)cnt < num_active ? 1.0f : 0.0f;
+  B[dst + i] = s;
+  if (dst_next >= 0) B[dst_next + i] = s;
+}
+
+// Reconstruction of the visible layer and of the previous hidden state from a
+// per-unit drive (state or spike): sdr/RSDR.cpp:165-194, sdr/IRSDR.cpp:218-254,
+// neo/SparseCoder.cpp:242-259 (scaled: drive*multiplier).  Threads [0,nv) own a
+// visible cell, [nv,nv+nh) a hidden unit.  copy_spike: also spikePrev = spike
+// (sdr/IRSDR.cpp:170-171), race-free here because this kernel never reads spikePrev.
+__global__ void k_reconstruct(EngineDev P, int l, long long drive_off, int scaled, float mult, int copy_spike) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.nv + L.nh)
+  float* B = blob_of(P, a);
+  const float* drive = B + drive_off;
+  if (i < L.nv) {
+    B[L.vis_recon + i] = gather_recon(L.ff, B + L.ff.w_off, drive, i % L.vw, i / L.vw, scaled != 0, mult);
+  } else {
+    const int h = i - L.nv;
+    B[L.recon + h] = gather_recon(L.rec, B + L.rec.w_off, drive, h % L.hw, h / L.hw, scaled != 0, mult);
+    if (copy_spike) B[L.spike_prev + h] = B[L.spike + h];
+  }
+}
+
+// sdr/RSDR.cpp:196-212 applied to layer 0's predicted states -> _prediction
+// (sdr/PredictiveRSDR.cpp:188-193)
+__global__ void k_kw_predict_input(EngineDev P) {
+  const LayerDev& L = P.layers[0];
+  BIDI_THREAD_AGENT_UNIT(L.nv)
+  float* B = blob_of(P, a);
+  P.pred_out[(long long)a * P.n_in + i] = gather_recon(L.ff, B + L.ff.w_off, B + L.p_state, i % L.vw, i / L.vw, false, 0.0f);
+}
+
+// sdr/RSDR.cpp:241-266: winners only; theta for every unit
+__global__ void k_kw_learn(EngineDev P, int l) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.nh)
+  float* B = blob_of(P, a);
+  const float* x = vis_input_of(P, L, l, a);
+  const float* vrec = B + L.vis_recon;
+  const float* sprev = B + L.state_prev;
+  const float* hrec = B + L.recon;
+  float* wff = B + L.ff.w_off;
+  float* wrec = B + L.rec.w_off;
+  const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
+  const float learn = B[L.state + i];
+  if (learn > 0.0f) {
+    const float att = B[L.p_mod + i];
+    const float kf = L.learn_ff * att * learn, kr = L.learn_rec * att * learn;
+    for_each_conn(L.ff, ux, uy, [&](int s, int t) { wff[(long long)s * U + i] += kf * (x[t] - vrec[t]); });
+    for_each_conn(L.rec, ux, uy, [&](int s, int t) { wrec[(long long)s * U + i] += kr * (sprev[t] - hrec[t]); });
+  }
+  B[L.thr + i] += L.learn_threshold * (learn - L.sparsity);
+}
+
+// ------------------------------------------------------------------ iterative coders
+// One leaky-integrate-and-fire sweep: sdr/IRSDR.cpp:138-168 / :177-209 /
+// neo/SparseCoder.cpp:129-158.  first: activation and state start from 0
+// (sdr/IRSDR.cpp:131-135).  acc: 0 = settle (no state change), 1 = state +=
+// scale*spike (measure; scale = 1/measureIter), 2 = state += spike (neo).
+__global__ void k_ic_sweep(EngineDev P, int l, int first, int acc, float scale) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.nh)
+  float* B = blob_of(P, a);
+  const float* x = vis_input_of(P, L, l, a);
+  const float* vrec = B + L.vis_recon;
+  const float* sprev = B + L.state_prev;
+  const float* hrec = B + L.recon;
+  const float* spk_prev = B + L.spike_prev;
+  const float* wff = B + L.ff.w_off;
+  const float* wrec = B + L.rec.w_off;
+  const float* wlat = B + L.lat.w_off;
+  const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
+  float excitation = 0.0f;
+  for_each_conn(L.ff, ux, uy, [&](int s, int t) { excitation += (x[t] - vrec[t]) * wff[(long long)s * U + i]; });
+  for_each_conn(L.rec, ux, uy, [&](int s, int t) { excitation += (sprev[t] - hrec[t]) * wrec[(long long)s * U + i]; });
+  float inhibition = 0.0f;
+  for_each_conn(L.lat, ux, uy, [&](int s, int t) { inhibition += spk_prev[t] * wlat[(long long)s * U + i]; });
+  float act = first ? 0.0f : B[L.act + i];
+  float st = first ? 0.0f : B[L.state + i];
+  act = (1.0f - L.leak) * act + excitation - inhibition;
+  float spike;
+  if (act > B[L.thr + i]) { act = 0.0f; spike = 1.0f; } else spike = 0.0f;
+  if (acc == 1) st += scale * spike;
+  else if (acc == 2) st += spike;
+  B[L.act + i] = act;
+  B[L.spike + i] = spike;
+  B[L.state + i] = st;
+}
+
+// End of the up pass of one layer: neo: state *= 1/counter (neo/SparseCoder.cpp:171-175);
+// then the next layer's input = state (x the column's _attention action for
+// neo::Agent, neo/Agent.cpp:147-151).
+__global__ void k_ic_finish(EngineDev P, int l, int scale_state, float mult) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.nh)
+  float* B = blob_of(P, a);
+  float st = B[L.state + i];
+  if (scale_state) { st *= mult; B[L.state + i] = st; }
+  if (l < P.L - 1) {
+    const LayerDev& N = P.layers[l + 1];
+    if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + i * 3 + 0];
+    B[N.vis_input + i] = st;
+  }
+}
+
+// lateral anti-Hebbian + threshold homeostasis: sdr/IRSDR.cpp:313-317
+__device__ __forceinline__ void ic_learn_tail(const LayerDev& L, float* B, int i, int ux, int uy) {
+  const float* state = B + L.state;
+  float* wlat = B + L.lat.w_off;
+  const float si = state[i], sp2 = L.sparsity * L.sparsity;
+  const int U = L.nh;
+  for_each_conn(L.lat, ux, uy, [&](int s, int t) {
+    const long long k = (long long)s * U + i;
+    wlat[k] = bidi_max(0.0f, wlat[k] + L.learn_lat * (si * state[t] - sp2));
+  });
+  B[L.thr + i] = bidi_max(0.0f, B[L.thr + i] + (si - L.sparsity) * L.learn_threshold);
+}
+
+// sdr/IRSDR.cpp:287-319 (Hebbian, clamped delta)
+__global__ void k_ic_learn(EngineDev P, int l) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.nh)
+  float* B = blob_of(P, a);
+  const float* x = vis_input_of(P, L, l, a);
+  const float* vrec = B + L.vis_recon;
+  const float* sprev = B + L.state_prev;
+  const float* hrec = B + L.recon;
+  float* wff = B + L.ff.w_off;
+  float* wrec = B + L.rec.w_off;
+  const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
+  const float learn = B[L.state + i], maxd = L.max_weight_delta, decay = L.weight_decay;
+  for_each_conn(L.ff, ux, uy, [&](int s, int t) {
+    const long long k = (long long)s * U + i;
+    const float delta = L.learn_ff * learn * (x[t] - vrec[t]) - decay * wff[k];
+    wff[k] += bidi_min(maxd, bidi_max(-maxd, delta));
+  });
+  for_each_conn(L.rec, ux, uy, [&](int s, int t) {
+    const long long k = (long long)s * U + i;
+    const float delta = L.learn_rec * learn * (sprev[t] - hrec[t]) - decay * wrec[k];
+    wrec[k] += bidi_min(maxd, bidi_max(-maxd, delta));
+  });
+  ic_learn_tail(L, B, i, ux, uy);
+}
+
+// neo/Agent.cpp:252-265 (reward from the prediction error) followed by
+// neo/SparseCoder.cpp:326-361 (reward-modulated update through eligibility traces)
+__global__ void k_neo_learn(EngineDev P, int l) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.nh)
+  float* B = blob_of(P, a);
+  const float* x = vis_input_of(P, L, l, a);
+  const float* vrec = B + L.vis_recon;
+  const float* sprev = B + L.state_prev;
+  const float* hrec = B + L.recon;
+  float* wff = B + L.ff.w_off; float* tff = B + L.ff.tr_off;
+  float* wrec = B + L.rec.w_off; float* trec = B + L.rec.tr_off;
+  const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
+  const float learn = B[L.state + i], maxd = L.max_weight_delta, decay = L.weight_decay;
+  const float err = learn - B[L.p_state_prev + i];
+  const float error2 = err * err;
+  const float base = B[L.p_baseline + i];
+  const float reward = bidi_sigmoid(L.sensitivity * (error2 - base));
+  B[L.p_baseline + i] = (1.0f - L.baseline_decay) * base + L.baseline_decay * error2;
+  for_each_conn(L.ff, ux, uy, [&](int s, int t) {
+    const long long k = (long long)s * U + i;
+    const float tr = tff[k];
+    const float delta = L.learn_ff * reward * tr - decay * wff[k];
+    wff[k] += bidi_min(maxd, bidi_max(-maxd, delta));
+    tff[k] = L.lambda * tr + learn * (x[t] - vrec[t]);
+  });
+  for_each_conn(L.rec, ux, uy, [&](int s, int t) {
+    const long long k = (long long)s * U + i;
+    const float tr = trec[k];
+    const float delta = L.learn_rec * reward * tr - decay * wrec[k];
+    wrec[k] += bidi_min(maxd, bidi_max(-maxd, delta));
+    trec[k] = L.lambda * tr + learn * (sprev[t] - hrec[t]);
+  });
+  ic_learn_tail(L, B, i, ux, uy);
+}
+
+// ------------------------------------------------------------------ prediction nodes
+// Down pass of node layer l < L: sdr/PredictiveRSDR.cpp:122-160,
+// sdr/IPredictiveRSDR.cpp:156-194, neo/PredictiveHierarchy.cpp:151-181,
+// neo/Agent.cpp:177-208.  The delta rule runs BEFORE the activation that uses the
+// weights.
+__global__ void k_predict(EngineDev P, int l, int learn) {
+  const LayerDev& L = P.layers[l];
+  BIDI_THREAD_AGENT_UNIT(L.pn)
+  float* B = blob_of(P, a);
+  const bool top = l == P.L - 1;
+  const LayerDev& Up = P.layers[top ? l : l + 1];
+  const float* up_state = B + Up.p_state;
+  const float* up_prev = B + Up.p_state_prev;
+  const float* state = B + L.state;
+  const float* sprev = B + L.state_prev;
+  float* wfb = B + L.fb.w_off;
+  float* wpr = B + L.pred.w_off;
+  const int ux = i % L.hw, uy = i / L.hw, U = L.pn;
+  if (learn) {
+    float err = state[i] - B[L.p_state_prev + i];
+    if (P.variant == BIDI_KWINNERS) {
+      const float surprise = err * err, avg = B[L.p_baseline + i];
+      B[L.p_mod + i] = bidi_sigmoid(L.attention_factor * (surprise - avg));
+      B[L.p_baseline + i] = (1.0f - L.avg_surprise_decay) * avg + L.avg_surprise_decay * surprise;
+    } else if (P.variant == BIDI_ITERATIVE) {
+      const float error2 = err * err, base = B[L.p_baseline + i];
+      B[L.p_baseline + i] = (1.0f - L.baseline_decay) * base + L.baseline_decay * error2;
+    } else if (P.variant == BIDI_NEO_AGENT) {
+      err = B[L.col.a_expl + i * 3 + 1] * err; // _learnPrediction gate, neo/Agent.cpp:181
+    }
+    const float kfb = L.learn_fb * err, kpr = L.learn_pred * err;
+    if (!top) for_each_conn(L.fb, ux, uy, [&](int s, int t) { wfb[(long long)s * U + i] += kfb * up_prev[t]; });
+    for_each_conn(L.pred, ux, uy, [&](int s, int t) { wpr[(long long)s * U + i] += kpr * sprev[t]; });
+  }
+  float activation = 0.0f;
+  if (!top) for_each_conn(L.fb, ux, uy, [&](int s, int t) { activation += wfb[(long long)s * U + i] * up_state[t]; });
+  for_each_conn(L.pred, ux, uy, [&](int s, int t) { activation += wpr[(long long)s * U + i] * state[t]; });
+  B[L.p_act + i] = activation;
+  if (P.variant != BIDI_KWINNERS) B[L.p_state + i] = bidi_clamp01(activation);
+}
+
+// Input prediction nodes: sdr/IPredictiveRSDR.cpp:198-218, neo/Agent.cpp:232-246
+__global__ void k_predict_input(EngineDev P, int learn) {
+  const LayerDev& L = P.layers[P.L];
+  BIDI_THREAD_AGENT_UNIT(L.pn)
+  float* B = blob_of(P, a);
+  const LayerDev& L0 = P.layers[0];
+  const float* p0 = B + L0.p_state;
+  const float* p0_prev = B + L0.p_state_prev;
+  float* wfb = B + L.fb.w_off;
+  const int ux = i % L.fb.uw, uy = i / L.fb.uw, U = L.pn;
+  if (learn) {
+    float err = P.in0[(long long)a * P.n_in + i] - B[L.p_state_prev + i];
+    if (P.variant == BIDI_NEO_AGENT) err = B[L.col.a_expl + i * 3 + 1] * err;
+    const float k = L.learn_fb * err; // learn_fb of the input layer = _learnInputFeedBack
+    for_each_conn(L.fb, ux, uy, [&](int s, int t) { wfb[(long long)s * U + i] += k * p0_prev[t]; });
+  }
+  float activation = 0.0f;
+  for_each_conn(L.fb, ux, uy, [&](int s, int t) { activation += wfb[(long long)s * U + i] * p0[t]; });
+  B[L.p_act + i] = activation;
+  P.pred_out[(long long)a * P.n_in + i] = activation;
+}
+
+// stepEnd of every layer + the *_Prev copies: sdr/PredictiveRSDR.cpp:177-184,
+// sdr/IPredictiveRSDR.cpp:224-239
+__global__ void k_step_end(EngineDev P, int max_units) {
+  BIDI_THREAD_AGENT_UNIT(max_units)
+  float* B = blob_of(P, a);
+  const int nl = P.variant == BIDI_KWINNERS ? P.L : P.L + 1;
+  for (int l = 0; l < nl; l++) {
+    const LayerDev& L = P.layers[l];
+    if (l < P.L && i < L.nh) B[L.state_prev + i] = B[L.state + i];
+    if (i < L.pn) {
+      B[L.p_state_prev + i] = p_state_of(P, L, l, a)[i];
+      B[L.p_act_prev + i] = B[L.p_act + i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ neo::Column
+// Exploration noise when the caller supplies none: a counter-based generator keyed
+// by (seed, step, agent, column, action); u uniform, v uniform or N(0,std).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(unsigned long long h) { return (float)(h >> 40) * (1.0f / 16777216.0f); }
+
+__global__ void k_noise(EngineDev P, float* u, float* v, unsigned long long seed, unsigned long long step) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)P.A * P.ncol;
+  if (gid >= n) return;
+  const int c = (int)(gid % P.ncol);
+  float std = 0.0f, brk = 0.0f;
+  for (int l = 0; l <= P.L; l++) {
+    const ColumnsDev& C = P.layers[l].col;
+    if (c >= C.noise_base && c < C.noise_base + C.n) { std = C.expl_std; brk = C.expl_break; }
+  }
+  for (int k = 0; k < 3; k++) {
+    unsigned long long h = mix64(seed ^ mix64(step * 0x100000001B3ULL + (unsigned long long)gid * 3 + k));
+    const float uu = u01(h);
+    h = mix64(h);
+    float vv;
+    if (uu < brk) vv = u01(h);
+    else {
+      const float r1 = fmaxf(u01(h), 5.9604645e-8f), r2 = u01(mix64(h));
+      vv = sqrtf(-2.0f * logf(r1)) * cospif(2.0f * r2) * std;
+    }
+    u[gid * 3 + k] = uu;
+    v[gid * 3 + k] = vv;
+  }
+}
+
+// One warp per column: lanes [0,cells) own a cell for the integrate-and-fire sweep
+// (sequential over the inputs, the reference's order), all lanes share the
+// reconstruction and the element-wise weight updates.  neo/Column.cpp:46-169; the
+// inputs are gathered first as neo/Agent.cpp:159-169 / :217-220 do.
+#define BIDI_COL_WARPS 8
+__global__ void __launch_bounds__(BIDI_COL_WARPS * 32) k_columns(EngineDev P, int l) {
+  extern __shared__ float smem[];
+  const LayerDev& L = P.layers[l];
+  const ColumnsDev& C = L.col;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long cid = (long long)blockIdx.x * BIDI_COL_WARPS + warp;
+  if (cid >= (long long)P.A * C.n) return;
+  const int a = (int)(cid / C.n), node = (int)(cid % C.n);
+  float* B = blob_of(P, a);
+  const int cells = C.cells;
+  const int in0 = C.in_off[node], nin = C.in_off[node + 1] - in0;
+  // per-warp shared scratch
+  float* s_in = smem + (size_t)warp * (2 * C.max_in + 3 * 32);
+  float* s_err = s_in + C.max_in;
+  float* s_spike = s_err + C.max_in;
+  float* s_sprev = s_spike + 32;
+  float* s_state = s_sprev + 32;
+
+  // ---- gather the column's inputs
+  const bool input_layer = l == P.L;
+  const LayerDev& Up = P.layers[input_layer ? 0 : (l == P.L - 1 ? l : l + 1)];
+  const int ux = node % L.fb.uw, uy = node / L.fb.uw;
+  int nfb = 0;
+  if (L.fb.r >= 0 && (input_layer || l < P.L - 1)) {
+    const SlotBox b = slot_box(L.fb, ux, uy);
+    const int ny = b.sy1 - b.sy0 + 1;
+    nfb = slot_count(L.fb, b);
+    const float* up_sig = B + Up.col.a_expl;
+    const float* up_state = B + Up.p_state;
+    for (int k = lane; k < nfb; k += 32) {
+      const int sx = b.sx0 + k / ny, sy = b.sy0 + k % ny;
+      const int t = slot_tx(L.fb, b, sx) + slot_ty(L.fb, b, sy) * L.fb.tw;
+      s_in[2 * k] = up_sig[t * 3 + 2];   // _signal
+      s_in[2 * k + 1] = up_state[t];
+    }
+  }
+  if (!input_layer) {
+    const SlotBox b = slot_box(L.pred, ux, uy);
+    const int ny = b.sy1 - b.sy0 + 1;
+    const int npr = slot_count(L.pred, b);
+    const float* state = B + L.state;
+    for (int k = lane; k < npr; k += 32) {
+      const int sx = b.sx0 + k / ny, sy = b.sy0 + k % ny;
+      s_in[2 * nfb + k] = state[slot_tx(L.pred, b, sx) + slot_ty(L.pred, b, sy) * L.pred.tw];
+    }
+  }
+  float* g_in = B + C.inputs + in0;
+  float* g_err = B + C.recon_err + in0;
+  float* ff = B + C.ff_w + (long long)cells * in0;
+  float* lat = B + C.lat_w + (long long)node * cells * cells;
+  const int cb = node * cells;
+  __syncwarp();
+  for (int j = lane; j < nin; j += 32) { g_in[j] = s_in[j]; s_err[j] = g_err[j]; }
+  if (lane < 32) { s_sprev[lane] = lane < cells ? B[C.spike_prev + cb + lane] : 0.0f; s_state[lane] = 0.0f; s_spike[lane] = 0.0f; }
+  __syncwarp();
+
+  // ---- iterate
+  float act = 0.0f, st = 0.0f;
+  const float thr = lane < cells ? B[C.thr + cb + lane] : 0.0f;
+  float counter = 0.0f;
+  for (int it = 0; it < C.iter; it++) {
+    float spike = 0.0f;
+    if (lane < cells) {
+      float excitation = 0.0f;
+      const float* w = ff + (long long)lane * nin;
+      for (int j = 0; j < nin; j++) excitation += w[j] * s_err[j];
+      float inhibition = 0.0f;
+      const float* wl = lat + lane * cells;
+      for (int j = 0; j < cells; j++) inhibition += wl[j] * s_sprev[j];
+      float activation = (1.0f - C.leak) * act + excitation - inhibition;
+      if (activation > thr) { activation = 0.0f; spike = 1.0f; }
+      st += spike;
+      act = activation;
+    }
+    __syncwarp();
+    if (lane < cells) { s_spike[lane] = spike; s_sprev[lane] = spike; }
+    __syncwarp();
+    counter += 1.0f;
+    const float multiplier = 1.0f / counter;
+    for (int j = lane; j < nin; j += 32) {
+      float recon = 0.0f;
+      for (int k = 0; k < cells; k++) {
+        const float sp = s_spike[k];
+        if (sp != 0.0f) recon += sp * multiplier * ff[(long long)k * nin + j];
+      }
+      s_err[j] = s_in[j] - recon;
+    }
+    __syncwarp();
+  }
+  const float mult = 1.0f / counter;
+  st *= mult;
+  if (lane < cells) s_state[lane] = st;
+  __syncwarp();
+
+  // ---- value and actions (sequential over the cells, neo/Column.cpp:111-123)
+  const float* qw = B + C.q_w + cb;
+  float q = 0.0f;
+  for (int k = 0; k < cells; k++) q += qw[k] * s_state[k];
+  float a_state = 0.0f, a_expl = 0.0f;
+  if (lane < 3) {
+    const float* aw = B + C.a_w + ((long long)node * 3 + lane) * cells;
+    float sum = 0.0f;
+    for (int k = 0; k < cells; k++) sum += aw[k] * s_state[k];
+    a_state = bidi_sigmoid(sum);
+    const long long nk = ((long long)a * P.ncol + C.noise_base + node) * 3 + lane;
+    const float u = P.noise_u[nk], v = P.noise_v[nk];
+    a_expl = u < C.expl_break ? v : bidi_clamp01(a_state + v);
+    B[C.a_state + node * 3 + lane] = a_state;
+    B[C.a_expl + node * 3 + lane] = a_expl;
+    P.col_actions[nk] = a_expl;
+  }
+  const float prev_value = B[C.prev_value + node];
+  const float td = P.rewards[a] + C.gamma * q - prev_value;
+  const float q_alpha_td = C.a_q * td, act_alpha_td = C.a_act * td;
+  // ---- learning
+  if (lane < cells) {
+    float* qwm = B + C.q_w + cb;
+    float* qtr = B + C.q_tr + cb;
+    const float tr = qtr[lane];
+    qwm[lane] += q_alpha_td * tr;
+    qtr[lane] = tr * C.gamma_lambda + st;
+  }
+  for (int act_i = 0; act_i < 3; act_i++) {
+    const float as = __shfl_sync(0xffffffffu, a_state, act_i), ae = __shfl_sync(0xffffffffu, a_expl, act_i);
+    if (lane < cells) {
+      float* aw = B + C.a_w + ((long long)node * 3 + act_i) * cells;
+      float* at = B + C.a_tr + ((long long)node * 3 + act_i) * cells;
+      const float tr = at[lane];
+      aw[lane] += act_alpha_td * tr;
+      at[lane] = tr * C.gamma_lambda + (ae - as) * st;
+    }
+  }
+  const float sp2 = C.sparsity * C.sparsity;
+  for (int e = lane; e < cells * nin; e += 32) {
+    const int ci = e / nin, j = e - ci * nin;
+    const float sc = s_state[ci];
+    if (sc > 0.0f) ff[e] += C.a_ff * sc * s_err[j];
+  }
+  for (int e = lane; e < cells * cells; e += 32) {
+    const int ci = e / cells, j = e - ci * cells;
+    lat[e] = bidi_max(0.0f, lat[e] + C.a_lat * (s_state[ci] * s_state[j] - sp2));
+  }
+  for (int j = lane; j < nin; j += 32) g_err[j] = s_err[j];
+  if (lane < cells) {
+    B[C.thr + cb + lane] = thr + C.a_thr * (st - C.sparsity);
+    B[C.act + cb + lane] = act;
+    B[C.spike + cb + lane] = s_spike[lane];
+    B[C.spike_prev + cb + lane] = s_sprev[lane];
+    B[C.state + cb + lane] = st;
+  }
+  if (lane == 0) B[C.prev_value + node] = q;
+}
+
+} // namespace bidi

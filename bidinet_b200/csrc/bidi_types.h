@@ -1,0 +1,93 @@
+// bidi_types.h -- plain structs shared by the host engine and the CUDA kernels.
+//
+// HBM layout.  Every agent owns one contiguous "blob" of
+// floats; agent a's blob starts at blob + a*stride.  Inside a blob:
+//   * per-unit state arrays are dense planes [unit], unit = x + y*width
+//     (the reference's node order, sdr/RSDR.cpp:36-38)
+//   * a connection family (feed-forward, recurrent, lateral, feedback,
+//     predictive) is a stack of "slot planes" w[slot][unit]: slot (sx,sy) is a
+//     position inside the receptive window, so the weights one warp of adjacent
+//     units needs for a slot are adjacent in memory, and walking the slots
+//     sx-outer / sy-inner visits a unit's weights in exactly the reference's
+//     dx-outer / dy-inner list order (sdr/RSDR.cpp:48-62).  Slots that fall off
+//     the target grid hold 0 and are never read.
+//   * the per-node columns of neo::Agent keep the reference's dense
+//     [node][cell][input] order (neo/Column.cpp:22-43), one contiguous run per
+//     column.
+// Layer-0 inputs and the input-space predictions live OUTSIDE the blobs in dense
+// [agent][index] arrays so that setInput/getPrediction traffic is one contiguous
+// host<->device copy.
+#ifndef BIDI_TYPES_H
+#define BIDI_TYPES_H
+
+#include "bidinet_b200.h"
+
+#define BIDI_MAX_NODE_LAYERS (BIDI_MAX_LAYERS + 1)
+
+// One connection family: units of a uw x uh grid look at a window of radius r
+// around a centre in a tw x th target grid.
+struct WinDev {
+  int uw, uh, tw, th;
+  int r;             // -1: family absent
+  int dxn, dyn;      // slot box: dxn = min(2r+1, tw), dyn = min(2r+1, th)
+  int absx, absy;    // slot coordinate = absolute target coordinate (window spans the grid)
+  int excl;          // centre excluded (recurrent, lateral)
+  int nslots;        // dxn*dyn
+  int U;             // uw*uh
+  const int* cx;     // [uw] window centre per unit column, round_f32(ux * tw/uw)  (sdr/RSDR.cpp:40)
+  const int* cy;     // [uh]
+  // reverse map for gather-form reconstruction: target column tx is inside the
+  // windows of unit columns gx_lo[tx]..gx_hi[tx] (cx is monotone, so it is a range)
+  const int* gx_lo; const int* gx_hi;  // [tw]
+  const int* gy_lo; const int* gy_hi;  // [th]
+  long long w_off;   // float offset of w[slot][unit] inside the agent blob, -1 if none
+  long long tr_off;  // eligibility traces, same shape, -1 if none
+};
+
+struct ColumnsDev {
+  int n, cells, tot_in;     // nodes, cells per column, sum of nIn
+  int max_in;               // largest nIn
+  const int* in_off;        // [n+1] prefix sums of nIn (same for every agent)
+  long long inputs, recon_err, ff_w, lat_w, thr, act, spike, spike_prev, state;
+  long long q_w, q_tr, a_state, a_expl, a_w, a_tr, prev_value;
+  int noise_base;           // first column index of this layer in the visit order (x3 for the noise arrays)
+  // neo/Column.cpp:46 simStep arguments
+  float sparsity, gamma, leak, a_ff, a_lat, a_thr, a_q, a_act, gamma_lambda, expl_std, expl_break;
+  int iter;
+};
+
+// One layer: the sparse coder (visible -> hidden) and its prediction nodes.
+// Index n_layers holds only the input prediction nodes (pn_*, fb, col).
+struct LayerDev {
+  int vw, vh, hw, hh, nv, nh;
+  // coder unit planes (offsets into the blob)
+  long long vis_input, vis_recon;   // vis_input is -1 for layer 0 (dense input array)
+  long long thr, state, state_prev, act, recon, spike, spike_prev;
+  WinDev ff, rec, lat;
+  // prediction nodes
+  int pn;                           // number of prediction nodes (nh, or n_in for the input nodes)
+  long long p_state, p_state_prev, p_act, p_act_prev, p_baseline, p_mod; // p_mod: attention / reward scratch
+  WinDev fb, pred;
+  ColumnsDev col;
+  // hyper-parameters (bidi_layer_desc)
+  float learn_ff, learn_rec, learn_lat, learn_threshold, learn_fb, learn_pred, sparsity;
+  float avg_surprise_decay, attention_factor;
+  int iter_settle, iter_measure;
+  float leak, lambda, weight_decay, max_weight_delta, baseline_decay, sensitivity;
+};
+
+struct EngineDev {
+  int variant, L, A, n_in;
+  float* blob;            // [A][stride]
+  long long stride;       // floats per agent
+  float* in0;             // [A][n_in] layer-0 visible input
+  float* pred_out;        // [A][n_in] getPrediction values
+  const float* rewards;   // [A]
+  const float* noise_u;   // [A][ncol*3]
+  const float* noise_v;
+  float* col_actions;     // [A][ncol*3] exploratory actions in visit order (getAction)
+  int ncol;
+  const LayerDev* layers; // device array [L+1]
+};
+
+#endif

@@ -1,0 +1,207 @@
+"""ctypes binding of the C ABI (include/bidinet_b200.h).
+
+``Engine`` is the Python-side mirror of what the reference's experiment mains do
+with a hierarchy object: create it from a layer-descriptor list, then per step
+``set_inputs`` / ``step`` / ``get_predictions`` (RunnerMain.cpp:139-154,239-249,
+Experiment_Prediction.cpp:124-148).  All compute happens in the CUDA library; if it
+is missing or no GPU is usable this module raises -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB_PATH
+from .config import ARRAY, ARRAY_NAMES, Config, LayerDesc
+
+_FP = C.POINTER(C.c_float)
+_IP = C.POINTER(C.c_int)
+
+# every symbol include/bidinet_b200.h declares: (restype, argtypes)
+ABI = {
+    "bidi_last_error": (C.c_char_p, [C.c_void_p]),
+    "bidi_create": (C.c_int, [C.POINTER(Config), C.POINTER(LayerDesc), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "bidi_destroy": (None, [C.c_void_p]),
+    "bidi_init_random": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint]),
+    "bidi_num_agents": (C.c_int, [C.c_void_p]),
+    "bidi_num_inputs": (C.c_int, [C.c_void_p]),
+    "bidi_num_columns": (C.c_int, [C.c_void_p]),
+    "bidi_array_len": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int]),
+    "bidi_conn_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _IP, C.c_int]),
+    "bidi_set_array": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _FP, C.c_longlong]),
+    "bidi_get_array": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _FP, C.c_longlong]),
+    "bidi_set_inputs": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_set_input": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float]),
+    "bidi_step": (C.c_int, [C.c_void_p, _FP, _FP, _FP, C.c_int]),
+    "bidi_get_predictions": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_get_column_actions": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_sync": (C.c_int, [C.c_void_p]),
+    "bidi_load_frames": (C.c_int, [C.c_void_p, _FP, _FP, C.c_int]),
+    "bidi_step_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bidi_timer_start": (C.c_int, [C.c_void_p]),
+    "bidi_timer_stop_ms": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_launch_count": (C.c_longlong, [C.c_void_p]),
+    "bidi_device_bytes": (C.c_longlong, [C.c_void_p]),
+    "bidi_abi_sizes": (C.c_int, [_IP, _IP]),
+}
+
+_lib = None
+
+
+class BidiError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BidiError("%s is missing: run __graft_entry__.build() (no CPU fallback exists)" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in ABI.items():
+            f = getattr(lib, name)
+            f.restype, f.argtypes = res, args
+        cb, lb = C.c_int(), C.c_int()
+        lib.bidi_abi_sizes(C.byref(cb), C.byref(lb))
+        if cb.value != C.sizeof(Config) or lb.value != C.sizeof(LayerDesc):
+            raise BidiError("config.py structs do not match include/bidinet_b200.h")
+        _lib = lib
+    return _lib
+
+
+def _fptr(a):
+    return a.ctypes.data_as(_FP)
+
+
+class Engine:
+    """n_agents independent hierarchies of one shape on one CUDA device."""
+
+    def __init__(self, cfg, layers, n_agents=1, device=0, seed=None):
+        self.lib = load_library()
+        self.cfg, self.layers = cfg, layers
+        self.n_layers = cfg.n_layers
+        self.n_agents = n_agents
+        self.n_in = cfg.in_width * cfg.in_height
+        h = C.c_void_p()
+        rc = self.lib.bidi_create(C.byref(cfg), layers, n_agents, device, C.byref(h))
+        if rc != 0:
+            raise BidiError("bidi_create failed (%d): %s" % (rc, self.lib.bidi_last_error(None).decode()))
+        self.h = h
+        self.n_columns = self.lib.bidi_num_columns(self.h)
+        if seed is not None:
+            self.init_random(seed)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise BidiError("%s failed (%d): %s" % (what, rc, self.lib.bidi_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bidi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- createRandom
+    def init_random(self, seed_base, first=0, count=None):
+        """agent a gets the weights std::mt19937(seed_base + a) yields in the reference's draw order."""
+        count = self.n_agents - first if count is None else count
+        self._check(self.lib.bidi_init_random(self.h, first, count, seed_base), "bidi_init_random")
+
+    # ---- serialised state
+    def array_len(self, which, layer):
+        return int(self.lib.bidi_array_len(self.h, ARRAY[which] if isinstance(which, str) else which, layer))
+
+    def get_array(self, which, layer, agent=0):
+        w = ARRAY[which] if isinstance(which, str) else which
+        n = self.array_len(w, layer)
+        out = np.zeros(n, dtype=np.float32)
+        if n:
+            self._check(self.lib.bidi_get_array(self.h, agent, w, layer, _fptr(out), n), "bidi_get_array")
+        return out
+
+    def set_array(self, which, layer, values, agent=0):
+        w = ARRAY[which] if isinstance(which, str) else which
+        a = np.ascontiguousarray(values, dtype=np.float32)
+        self._check(self.lib.bidi_set_array(self.h, agent, w, layer, _fptr(a), a.size), "bidi_set_array")
+
+    def conn_counts(self, which, layer, n_units):
+        out = np.zeros(n_units, dtype=np.int32)
+        self._check(self.lib.bidi_conn_counts(self.h, ARRAY[which], layer, out.ctypes.data_as(_IP), n_units),
+                    "bidi_conn_counts")
+        return out
+
+    def state(self, agent=0):
+        out = {}
+        for name in ARRAY_NAMES:
+            for layer in range(self.n_layers + 1):
+                if self.array_len(name, layer) > 0:
+                    out[(name, layer)] = self.get_array(name, layer, agent)
+        return out
+
+    def load_state(self, state, agent=0):
+        for (name, layer), a in state.items():
+            self.set_array(name, layer, a, agent)
+
+    # ---- per step
+    def set_inputs(self, x):
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        assert a.size == self.n_agents * self.n_in, (a.size, self.n_agents, self.n_in)
+        self._check(self.lib.bidi_set_inputs(self.h, _fptr(a)), "bidi_set_inputs")
+
+    def set_input(self, agent, index, value):
+        self._check(self.lib.bidi_set_input(self.h, agent, index, value), "bidi_set_input")
+
+    def step(self, rewards=None, noise=None, learn=True):
+        r = None if rewards is None else np.ascontiguousarray(rewards, dtype=np.float32).reshape(self.n_agents)
+        u = v = None
+        if noise is not None:
+            u = np.ascontiguousarray(noise[0], dtype=np.float32)
+            v = np.ascontiguousarray(noise[1], dtype=np.float32)
+            assert u.size == v.size == self.n_agents * self.n_columns * 3
+        self._check(self.lib.bidi_step(self.h, None if r is None else _fptr(r), None if u is None else _fptr(u),
+                                       None if v is None else _fptr(v), int(bool(learn))), "bidi_step")
+
+    def get_predictions(self):
+        out = np.zeros((self.n_agents, self.n_in), dtype=np.float32)
+        self._check(self.lib.bidi_get_predictions(self.h, _fptr(out)), "bidi_get_predictions")
+        return out
+
+    def get_column_actions(self):
+        out = np.zeros((self.n_agents, self.n_columns, 3), dtype=np.float32)
+        self._check(self.lib.bidi_get_column_actions(self.h, _fptr(out)), "bidi_get_column_actions")
+        return out
+
+    def sync(self):
+        self._check(self.lib.bidi_sync(self.h), "bidi_sync")
+
+    # ---- device-resident stepping and timing (bench.py)
+    def load_frames(self, frames, rewards=None):
+        f = np.ascontiguousarray(frames, dtype=np.float32).reshape(-1, self.n_agents, self.n_in)
+        r = None if rewards is None else np.ascontiguousarray(rewards, dtype=np.float32).reshape(f.shape[0], self.n_agents)
+        self._check(self.lib.bidi_load_frames(self.h, _fptr(f), None if r is None else _fptr(r), f.shape[0]),
+                    "bidi_load_frames")
+
+    def step_frame(self, t, learn=True):
+        self._check(self.lib.bidi_step_frame(self.h, int(t), int(bool(learn))), "bidi_step_frame")
+
+    def timer_start(self):
+        self._check(self.lib.bidi_timer_start(self.h), "bidi_timer_start")
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        self._check(self.lib.bidi_timer_stop_ms(self.h, C.byref(ms)), "bidi_timer_stop_ms")
+        return ms.value
+
+    @property
+    def launch_count(self):
+        return int(self.lib.bidi_launch_count(self.h))
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.bidi_device_bytes(self.h))

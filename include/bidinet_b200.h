@@ -4,7 +4,7 @@
  * The reference (222464/BIDInet) has no FFI layer: its experiment mains call
  * plain C++ value classes (sdr::PredictiveRSDR, sdr::IPredictiveRSDR,
  * neo::PredictiveHierarchy, neo::Agent).  This header is the boundary a
- * drop-in facade for those classes binds to (see include/bidinet/*.h and
+ * drop-in facade for those classes binds to (see the headers under include/bidinet/ and
  * INTEGRATION.md).  Every entry point cites the reference interface it
  * replaces; paths are relative to BIDInet/source/ of the reference.
  *
@@ -198,12 +198,13 @@ int bidi_get_column_actions(bidi_engine* h, float* out);
 int bidi_sync(bidi_engine* h);
 
 /*
- * Device-resident stepping for throughput runs: frames[T][agent][index] is
- * uploaded once; bidi_step_frame(t) is bidi_set_inputs(frame t % T) + bidi_step
- * without any host<->device traffic.
+ * Device-resident stepping for throughput runs: frames[T][agent][index] (and
+ * optionally rewards[T][agent]) are uploaded once; bidi_step_frame(t) is
+ * bidi_set_inputs(frame t % T) + bidi_step without any host<->device traffic
+ * (exploration noise from the engine's own generator).
  */
-int bidi_load_frames(bidi_engine* h, const float* frames, int n_frames);
-int bidi_step_frame(bidi_engine* h, int t, const float* rewards_dev_or_null, int learn);
+int bidi_load_frames(bidi_engine* h, const float* frames, const float* rewards, int n_frames);
+int bidi_step_frame(bidi_engine* h, int t, int learn);
 
 /* Timing helpers on the engine's stream (CUDA events), for bench.py. */
 int bidi_timer_start(bidi_engine* h);
@@ -212,6 +213,8 @@ int bidi_timer_stop_ms(bidi_engine* h, float* ms);
 long long bidi_launch_count(const bidi_engine* h);
 /* Bytes of device memory held by the engine. */
 long long bidi_device_bytes(const bidi_engine* h);
+/* sizeof(bidi_config), sizeof(bidi_layer_desc): lets a binding check its mirror. */
+int bidi_abi_sizes(int* config_bytes, int* layer_desc_bytes);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,43 @@
+"""The C restatement (oracle/bidi_oracle.c) against the UNMODIFIED reference compiled
+from /root/reference (oracle/_ref/libbidiref.so): every state array bit-identical
+after creation and after every step, for all four hierarchies.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import OracleHierarchy, RefHierarchy, have_ref
+
+from util import diff_states, small_cases
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libbidiref.so not built (needs /root/reference)")
+
+
+@pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
+def test_oracle_matches_reference(case):
+    name, cfg, ld, frame, reward = case
+    ref, orc = RefHierarchy(cfg, ld, 1234), OracleHierarchy(cfg, ld, 1234)
+    assert diff_states(ref.state(), orc.state()) == []
+    for t in range(12):
+        x = frame(t)
+        ref.set_inputs(x)
+        orc.set_inputs(x)
+        if ref.num_columns():
+            ur, vr = ref.peek_noise()
+            uo, vo = orc.peek_noise()
+            assert np.array_equal(ur, uo) and np.array_equal(vr, vo)
+        learn = t != 7  # one no-learn step in the middle
+        ref.step(reward(t), learn)
+        orc.step(reward(t), learn)
+        assert diff_states(ref.state(), orc.state()) == [], "step %d" % t
+        assert np.array_equal(ref.get_predictions(), orc.get_predictions())
+
+
+def test_conn_counts_match_reference():
+    for name, cfg, ld, _, _ in small_cases():
+        ref, orc = RefHierarchy(cfg, ld, 7), OracleHierarchy(cfg, ld, 7)
+        for layer in range(cfg.n_layers + 1):
+            for which in ("FF_W", "REC_W", "LAT_W", "FB_W", "PRED_W", "COL_INPUT"):
+                n = 4096
+                a, b = ref.conn_counts(which, layer, n), orc.conn_counts(which, layer, n)
+                assert (a is None) == (b is None), (name, which, layer)
+                if a is not None:
+                    assert np.array_equal(a, b), (name, which, layer)

@@ -1,0 +1,99 @@
+"""CUDA engine (through the C ABI) against the oracle on the same seeded inputs.
+
+Bar: every state array -- activations, spikes, k-winner sets, predictions, weights,
+traces, column state -- EQUAL (np.array_equal, i.e. bit-exact up to the sign of
+zero) after every step.  The kernels keep the reference's fp32 operation order and
+are built without FMA contraction, and bidi_math.h restates the C library's expf,
+so no tolerance is needed."""
+import numpy as np
+import pytest
+
+from bidinet_b200 import Engine
+from bidinet_b200 import config as cf
+from oracle.pyoracle import OracleHierarchy
+
+from util import diff_states, small_cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
+def test_upload_download_roundtrip(case):
+    """bidi_set_array / bidi_get_array: serialised reference order <-> slot planes."""
+    name, cfg, ld, _, _ = case
+    orc = OracleHierarchy(cfg, ld, 99)
+    eng = Engine(cfg, ld, n_agents=2)
+    st = orc.state()
+    rng = np.random.RandomState(1)
+    st = {k: rng.randn(*v.shape).astype(np.float32) for k, v in st.items()}
+    eng.load_state(st, agent=1)
+    assert diff_states(st, eng.state(agent=1)) == []
+    zero = eng.state(agent=0)  # the other agent is untouched
+    assert all(not np.any(v) or k[0] in ("HID_THRESHOLD", "COL_THRESHOLD") for k, v in zero.items())
+
+
+@pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
+def test_init_random_matches_oracle(case):
+    """bidi_init_random replays createRandom's std::mt19937 draw order."""
+    name, cfg, ld, _, _ = case
+    eng = Engine(cfg, ld, n_agents=3, seed=1234)
+    for a in (0, 2):
+        orc = OracleHierarchy(cfg, ld, 1234 + a)
+        assert diff_states(orc.state(), eng.state(agent=a)) == [], "agent %d" % a
+
+
+@pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
+def test_free_running_parity(case):
+    """N steps from an identical state, no re-synchronisation: exact after every step."""
+    name, cfg, ld, frame, reward = case
+    orc = OracleHierarchy(cfg, ld, 1234)
+    eng = Engine(cfg, ld, n_agents=1)
+    eng.load_state(orc.state())
+    steps = 25
+    for t in range(steps):
+        x = frame(t)
+        orc.set_inputs(x)
+        eng.set_inputs(x)
+        noise = orc.peek_noise() if orc.num_columns() else None
+        learn = t != 9
+        orc.step(reward(t), learn)
+        eng.step(rewards=[reward(t)], noise=noise, learn=learn)
+        bad = diff_states(orc.state(), eng.state())
+        assert bad == [], "step %d: %s" % (t, bad[:6])
+        assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0])
+
+
+def test_batched_agents_are_independent():
+    """Agents in one engine evolve exactly like separate single-agent runs."""
+    cfg, ld = cf.config_c2()
+    A = 5
+    eng = Engine(cfg, ld, n_agents=A, seed=1234)
+    orcs = [OracleHierarchy(cfg, ld, 1234 + a) for a in range(A)]
+    rng = np.random.RandomState(3)
+    for t in range(6):
+        x = rng.rand(A, 64).astype(np.float32)
+        r = rng.randn(A).astype(np.float32)
+        nz = [o.peek_noise() for o in orcs]
+        for a, o in enumerate(orcs):
+            o.set_inputs(x[a])
+            o.step(float(r[a]))
+        eng.set_inputs(x)
+        eng.step(rewards=r, noise=(np.stack([n[0] for n in nz]), np.stack([n[1] for n in nz])))
+        pred = eng.get_predictions()
+        for a, o in enumerate(orcs):
+            assert np.array_equal(o.get_predictions(), pred[a]), (t, a)
+    for a in (0, A - 1):
+        assert diff_states(orcs[a].state(), eng.state(agent=a)) == []
+
+
+def test_device_noise_mode_runs_and_explores():
+    """noise=None: the engine's own generator; actions stay in [0,1] and differ between agents."""
+    cfg, ld = cf.config_c2()
+    eng = Engine(cfg, ld, n_agents=4, seed=1)
+    x = np.random.RandomState(0).rand(4, 64).astype(np.float32)
+    for t in range(3):
+        eng.set_inputs(x)
+        eng.step(rewards=np.zeros(4, np.float32))
+    act = eng.get_column_actions()
+    assert np.all(act >= 0) and np.all(act <= 1) and np.isfinite(eng.get_predictions()).all()
+    assert not np.array_equal(act[0], act[1])
