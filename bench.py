@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of BIDInet's per-timestep hierarchy update on B200.
+
+Workload (BASELINE.json configs[1]/[2], SURVEY section 8 "C3"): the neo::Agent
+hierarchy RunnerMain.cpp:141-154 builds (input 8x8, layers 8x8 -> 4x4, input feedback
+radius 8, 144 columns), --agents-per-gpu independent agents per GPU, learning on,
+driven by the headless RunnerMain loop (sine state vector + the four
+clock inputs of RunnerMain.cpp:235-236 + the ten fed-back actions of :241-242,
+reward = mean(action) - 0.5).  One "step" = one simStep of every agent.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
+  python bench.py --impl reference [--gpus N] --steps K --warmup W   the reference's CPU code
+
+Our arm prints one JSON line with
+  value        agent-steps/s, inputs resident in HBM (frames preloaded, action
+               feedback and reward computed on the device), CUDA-event timed
+  e2e          the same metric through the C ABI with HOST buffers: per step
+               bidi_set_inputs (H2D) + bidi_step (H2D rewards) + bidi_get_predictions
+               (D2H), the host doing the action feedback like RunnerMain does
+  roofline     the dominant kernel's algorithmic bytes / its CUDA-event duration,
+               against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline the reference's own CPU code (oracle/_ref) on this host's cores, on a
+               bounded sample of the same workload
+Multi-GPU (torchrun, one rank per GPU): agents are sharded over ranks, no data-path
+collective; time = max over ranks; scaling = weak (agents per GPU fixed).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_STATE, N_CLOCK, INPUT_COUNT, N_ACTION = 15, 4, 20, 10  # RunnerMain.cpp:115-116
+FB_IDX = np.arange(INPUT_COUNT, INPUT_COUNT + N_ACTION, dtype=np.int32)
+
+
+def base_frames(n_frames, agents, first_agent, n_in=64, t0=0):
+    """Open-loop part of the RunnerMain input: [T][A][n_in]."""
+    t = (t0 + np.arange(n_frames, dtype=np.float32))[:, None, None]
+    a = (first_agent + np.arange(agents, dtype=np.float32))[None, :, None]
+    f = np.zeros((n_frames, agents, n_in), dtype=np.float32)
+    i = np.arange(N_STATE, dtype=np.float32)[None, None, :]
+    f[:, :, :N_STATE] = 0.5 + 0.5 * np.sin(0.05 * t * (1.0 + i) + 0.1 * a)
+    c = np.arange(N_CLOCK, dtype=np.float32)[None, None, :]
+    f[:, :, N_STATE:N_STATE + N_CLOCK] = np.sin(t / 60.0 * 2.0 * c * 2.0 * 3.141596) * 0.5 + 0.5
+    return f
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smmax.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes_per_agent_step(eng, rho_c=1.0):
+    """SURVEY 8d, NEO_AGENT: every persistent float read once (4 B), plus 4 B more for
+    every float the learning rules write back: coder w+trace, lateral, thresholds,
+    prediction weights, column lateral/q/action w+trace/threshold, and rho_c x the
+    column feed-forward weights (rho_c = fraction of cells with state > 0; the survey
+    measured ~1)."""
+    L = eng.n_layers
+    read = write = 0
+    for l in range(L + 1):
+        for name in ("FF_W", "REC_W", "LAT_W", "FF_TRACE", "REC_TRACE", "FB_W", "PRED_W", "HID_THRESHOLD",
+                     "COL_LAT_W", "COL_Q_W", "COL_Q_TRACE", "COL_ACT_W", "COL_ACT_TRACE", "COL_THRESHOLD"):
+            n = eng.array_len(name, l)
+            read += n
+            write += n
+        n = eng.array_len("COL_FF_W", l)
+        read += n
+        write += int(rho_c * n)
+    return 4 * (read + write)
+
+
+def column_bytes_per_agent_step(eng, rho_c=1.0):
+    """The share of algorithmic_bytes_per_agent_step the column kernel moves."""
+    tot = 0
+    for l in range(eng.n_layers + 1):
+        for name in ("COL_LAT_W", "COL_Q_W", "COL_Q_TRACE", "COL_ACT_W", "COL_ACT_TRACE", "COL_THRESHOLD"):
+            tot += 2 * eng.array_len(name, l)
+        tot += int((1 + rho_c) * eng.array_len("COL_FF_W", l))
+    return 4 * tot
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(cfg, ld, cores, steps_per_thread, warmup=10):
+    """agent-steps/s of the reference's CPU code: `cores` threads, one agent each, the
+    headless RunnerMain loop (ref_run_runner releases the GIL: it is one C call)."""
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.have_ref() else "port"
+    cls = pyoracle.RefHierarchy if kind == "reference" else pyoracle.OracleHierarchy
+    hs = [cls(cfg, ld, 1234 + a) for a in range(cores)]
+    frames = [base_frames(64, 1, a)[:, 0, :] for a in range(cores)]
+    for h, f in zip(hs, frames):
+        h.run_runner(f, warmup, FB_IDX, FB_IDX)
+
+    def work(k):
+        hs[k].run_runner(frames[k], steps_per_thread, FB_IDX, FB_IDX)
+
+    def timed():
+        th = [threading.Thread(target=work, args=(k,)) for k in range(cores)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0
+    return kind, hs, timed
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores."""
+    if rank != 0:
+        return
+    from bidinet_b200 import config as cf
+    cfg, ld = cf.config_c2()
+    cores = host_cores()
+    inner = args.ref_inner_steps
+    kind, hs, timed = cpu_reference_rate(cfg, ld, cores, inner)
+    for _ in range(args.warmup):
+        timed()
+    dts = [timed() for _ in range(args.steps)]
+    total = sum(dts)
+    value = cores * inner * args.steps / total
+    sample = "%d threads x 1 agent x %d simSteps per bench step" % (cores, inner)
+    print(json.dumps({
+        "impl": "reference", "metric": "agent_steps_per_s", "value": value, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: neo::Agent RunnerMain hierarchy (in 8x8, 8x8->4x4, 144 columns), headless runner loop",
+                   "agents": cores, "learn": True},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--agents-per-gpu", type=int, default=4096)
+    ap.add_argument("--ref-inner-steps", type=int, default=20)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=1500)
+    ap.add_argument("--profile-kernel", default="columns")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    from bidinet_b200 import Engine
+    from bidinet_b200 import config as cf
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    A, K, W = args.agents_per_gpu, args.steps, max(3, args.warmup)
+    cfg, ld = cf.config_c2()
+    eng = Engine(cfg, ld, n_agents=A, device=local_rank)
+    eng.init_random(1234 + rank * A)  # global agent g <- std::mt19937(1234 + g)
+    n_in = eng.n_in
+    T = min(W + K, 64)
+    frames = base_frames(T, A, rank * A, n_in)
+    eng.load_frames(frames)
+    eng.set_feedback(FB_IDX, FB_IDX, 0.5, 0.5, 0.05, True)
+
+    # ---- value: device-resident inputs, CUDA events on the engine's stream
+    t = 0
+    for _ in range(W):
+        eng.step_frame(t)
+        t += 1
+    eng.sync()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launch_count
+    eng.timer_start()
+    for _ in range(K):
+        eng.step_frame(t)
+        t += 1
+    ms = eng.timer_stop_ms()
+    eng.sync()
+    barrier()
+    launches = eng.launch_count - launches0
+    ms = max_over_ranks(ms)
+    value = world * A * K / (ms * 1e-3)
+
+    # ---- e2e: host buffers through the C ABI, host<->device copies inside the timed region
+    rng = np.random.RandomState(rank)
+    pred = eng.get_predictions()
+    x = np.empty((A, n_in), dtype=np.float32)
+    rewards = np.zeros(A, dtype=np.float32)
+
+    def host_step(tt):
+        nonlocal pred
+        np.copyto(x, frames[tt % T])
+        act = pred[:, FB_IDX] * 0.5 + 0.5
+        np.clip(act + rng.normal(0.0, 0.05, act.shape).astype(np.float32), 0.0, 1.0, out=x[:, FB_IDX])
+        np.subtract(np.clip(act, 0.0, 1.0).mean(axis=1), 0.5, out=rewards)
+        eng.set_inputs(x)
+        eng.step(rewards=rewards)
+        pred = eng.get_predictions()
+
+    for _ in range(W):
+        host_step(t)
+        t += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        host_step(t)
+        t += 1
+    eng.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * A * K / e2e_s
+    if rank == 0:
+        clk = clocks.stop()
+
+    # ---- roofline: the dominant kernel's own duration, CUDA events inside the step graph
+    kern = args.profile_kernel
+    eng.profile_select(kern)
+    for _ in range(3):
+        eng.step_frame(t)
+        t += 1
+    eng.profile_collect()
+    k_ms0, k_n0 = eng.profile_collect()
+    for _ in range(K):
+        eng.step_frame(t)
+        t += 1
+        eng.profile_collect()
+    k_ms, k_n = eng.profile_collect()
+    k_ms, k_n = k_ms - k_ms0, k_n - k_n0
+    eng.profile_select("")
+    step_bytes = algorithmic_bytes_per_agent_step(eng)
+    kern_bytes_step = column_bytes_per_agent_step(eng) if kern == "columns" else step_bytes
+    launches_per_step = max(1, k_n // max(1, K))
+    avg_launch_s = (k_ms * 1e-3) / max(1, k_n)
+    bytes_per_launch = kern_bytes_step * A / launches_per_step
+    achieved = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
+    peak, peak_src = hbm_peak()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        kind, hs, timed = cpu_reference_rate(cfg, ld, cores, args.cpu_baseline_steps)
+        dt = timed()
+        cpu = {"value": cores * args.cpu_baseline_steps / dt, "unit": "agent-steps/s", "cores": cores, "kind": kind,
+               "sample": "%d threads x 1 agent x %d simSteps of the same runner loop (%.1f s)" % (cores, args.cpu_baseline_steps, dt)}
+
+    out = {
+        "metric": "agent_steps_per_s", "value": value, "unit": "agent-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: neo::Agent RunnerMain hierarchy (in 8x8, 8x8->4x4, 144 columns), headless runner loop",
+                   "agents_per_gpu": A, "agents": world * A, "learn": True, "parallelism": "agents sharded over ranks, no collective",
+                   "l2": "per-step working set %.1f GB per GPU exceeds the 126 MB L2" % (eng.device_bytes / 1e9),
+                   "exploration_noise": "engine counter-based generator", "state_bytes_per_gpu": eng.device_bytes},
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,
+                "h2d_bytes_per_step": int(A * n_in * 4 + A * 4), "d2h_bytes_per_step": int(A * n_in * 4)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": bytes_per_launch, "avg_launch_ms": 1e3 * avg_launch_s,
+                     "launches_per_step": int(launches_per_step),
+                     "whole_step": {"algorithmic_bytes_per_agent_step": step_bytes,
+                                    "achieved": step_bytes * A / (ms / K * 1e-3) / 1e9,
+                                    "frac": step_bytes * A / (ms / K * 1e-3) / 1e9 / peak}},
+        "clocks": clk,
+    }
+    if cpu:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

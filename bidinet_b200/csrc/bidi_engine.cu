@@ -60,6 +60,11 @@ struct bidi_engine {
   int graph_kernels[2] = {0, 0};
   long long launches = 0;
   unsigned long long step_index = 0, noise_seed = 0x5DEECE66DULL;
+  // feedback taps (bidi_set_feedback)
+  int fb_n = 0; int* d_fb_src = nullptr; int* d_fb_dst = nullptr; float fb_scale = 0, fb_bias = 0, fb_std = 0; int fb_reward = 0;
+  // kernel profiling (bidi_profile_select): external events around the launches of one kernel
+  std::string profile_name; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profile_events;
+  double profile_ms = 0; long long profile_launches = 0;
   // host mirror of ONE agent's blob for set/get_array
   std::vector<float> mirror; int mirror_agent = -1; bool mirror_dirty = false;
   std::string err;
@@ -270,8 +275,22 @@ constexpr int kBlock = 128;
 struct Recorder {
   bidi_engine* h;
   int kernels = 0;
-  template <class K, class... Args> void launch(K kernel, long long threads, Args... args) {
+  // bracket a launch with external event records when its kernel is the one being profiled
+  bool profiled(const char* name) const { return !h->profile_name.empty() && h->profile_name == name; }
+  void before(const char* name) {
+    if (!profiled(name)) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    h->profile_events.push_back({a, b});
+    cudaEventRecordWithFlags(a, h->stream, cudaEventRecordExternal);
+  }
+  void after(const char* name) {
+    if (profiled(name)) cudaEventRecordWithFlags(h->profile_events.back().second, h->stream, cudaEventRecordExternal);
+  }
+  template <class K, class... Args> void launch(const char* name, K kernel, long long threads, Args... args) {
+    before(name);
     kernel<<<grid_for(threads, kBlock), kBlock, 0, h->stream>>>(h->P, args...);
+    after(name);
     kernels++;
   }
 };
@@ -281,7 +300,9 @@ void record_columns(Recorder& R, int l) {
   const ColumnsDev& C = h->layers[l].col;
   const long long warps = (long long)h->A * C.n;
   const size_t smem = sizeof(float) * BIDI_COL_WARPS * (2 * (size_t)C.max_in + 96);
+  R.before("columns");
   bidi::k_columns<<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, l);
+  R.after("columns");
   R.kernels++;
 }
 
@@ -294,20 +315,20 @@ void record_step(Recorder& R, bool learn) {
   if (V == BIDI_KWINNERS) {
     // sdr/PredictiveRSDR.cpp:102-112
     for (int l = 0; l < L; l++) {
-      R.launch(bidi::k_kw_activate, A * ly[l].nh, l);
-      R.launch(bidi::k_kw_inhibit, A * ly[l].nh, l, ly[l].act, ly[l].state, l < L - 1 ? ly[l + 1].vis_input : -1LL);
-      R.launch(bidi::k_reconstruct, A * (ly[l].nv + ly[l].nh), l, ly[l].state, 0, 0.0f, 0);
+      R.launch("kw_activate", bidi::k_kw_activate, A * ly[l].nh, l);
+      R.launch("kw_inhibit", bidi::k_kw_inhibit, A * ly[l].nh, l, ly[l].act, ly[l].state, l < L - 1 ? ly[l + 1].vis_input : -1LL);
+      R.launch("reconstruct", bidi::k_reconstruct, A * (ly[l].nv + ly[l].nh), l, ly[l].state, 0, 0.0f, 0);
     }
     // :115-171
     for (int l = L - 1; l >= 0; l--) {
-      R.launch(bidi::k_predict, A * ly[l].pn, l, (int)learn);
-      R.launch(bidi::k_kw_inhibit, A * ly[l].nh, l, ly[l].p_act, ly[l].p_state, -1LL);
+      R.launch("predict", bidi::k_predict, A * ly[l].pn, l, (int)learn);
+      R.launch("kw_inhibit", bidi::k_kw_inhibit, A * ly[l].nh, l, ly[l].p_act, ly[l].p_state, -1LL);
     }
     // :173-185
-    if (learn) for (int l = 0; l < L; l++) R.launch(bidi::k_kw_learn, A * ly[l].nh, l);
-    R.launch(bidi::k_step_end, A * h->max_units, h->max_units);
+    if (learn) for (int l = 0; l < L; l++) R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, l);
+    R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
     // :188-193
-    R.launch(bidi::k_kw_predict_input, A * h->n_in);
+    R.launch("kw_predict_input", bidi::k_kw_predict_input, A * h->n_in);
     return;
   }
   for (int l = 0; l < L; l++) {
@@ -315,39 +336,39 @@ void record_step(Recorder& R, bool learn) {
     if (V == BIDI_ITERATIVE) { // sdr/IRSDR.cpp:125-216
       const int settle = ly[l].iter_settle, measure = ly[l].iter_measure;
       for (int it = 0; it < settle; it++) {
-        R.launch(bidi::k_ic_sweep, nh, l, (int)(it == 0), 0, 0.0f);
-        R.launch(bidi::k_reconstruct, nvh, l, ly[l].spike, 0, 0.0f, 1);
+        R.launch("ic_sweep", bidi::k_ic_sweep, nh, l, (int)(it == 0), 0, 0.0f);
+        R.launch("reconstruct", bidi::k_reconstruct, nvh, l, ly[l].spike, 0, 0.0f, 1);
       }
       const float inv = 1.0f / measure;
       for (int it = 0; it < measure; it++) {
-        R.launch(bidi::k_ic_sweep, nh, l, (int)(settle == 0 && it == 0), 1, inv);
-        R.launch(bidi::k_reconstruct, nvh, l, ly[l].spike, 0, 0.0f, 1);
+        R.launch("ic_sweep", bidi::k_ic_sweep, nh, l, (int)(settle == 0 && it == 0), 1, inv);
+        R.launch("reconstruct", bidi::k_reconstruct, nvh, l, ly[l].spike, 0, 0.0f, 1);
       }
-      R.launch(bidi::k_reconstruct, nvh, l, ly[l].state, 0, 0.0f, 0);
-      if (l < L - 1) R.launch(bidi::k_ic_finish, nh, l, 0, 0.0f);
+      R.launch("reconstruct", bidi::k_reconstruct, nvh, l, ly[l].state, 0, 0.0f, 0);
+      if (l < L - 1) R.launch("ic_finish", bidi::k_ic_finish, nh, l, 0, 0.0f);
     } else { // neo/SparseCoder.cpp:116-176
       const int iter = ly[l].iter_settle;
       float counter = 0.0f;
       for (int it = 0; it < iter; it++) {
-        R.launch(bidi::k_ic_sweep, nh, l, (int)(it == 0), 2, 0.0f);
+        R.launch("ic_sweep", bidi::k_ic_sweep, nh, l, (int)(it == 0), 2, 0.0f);
         counter += 1.0f;
-        R.launch(bidi::k_reconstruct, nvh, l, ly[l].state, 1, 1.0f / counter, 1);
+        R.launch("reconstruct", bidi::k_reconstruct, nvh, l, ly[l].state, 1, 1.0f / counter, 1);
       }
-      R.launch(bidi::k_ic_finish, nh, l, 1, 1.0f / counter);
+      R.launch("ic_finish", bidi::k_ic_finish, nh, l, 1, 1.0f / counter);
     }
   }
   for (int l = L - 1; l >= 0; l--) {
     if (V == BIDI_NEO_AGENT) record_columns(R, l);
-    R.launch(bidi::k_predict, A * ly[l].pn, l, (int)learn);
+    R.launch("predict", bidi::k_predict, A * ly[l].pn, l, (int)learn);
   }
   if (V == BIDI_NEO_AGENT) record_columns(R, L);
-  R.launch(bidi::k_predict_input, A * h->n_in, (int)learn);
+  R.launch("predict_input", bidi::k_predict_input, A * h->n_in, (int)learn);
   if (learn)
     for (int l = 0; l < L; l++) {
-      if (V == BIDI_ITERATIVE) R.launch(bidi::k_ic_learn, A * ly[l].nh, l);
-      else R.launch(bidi::k_neo_learn, A * ly[l].nh, l);
+      if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, l);
+      else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, l);
     }
-  R.launch(bidi::k_step_end, A * h->max_units, h->max_units);
+  R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
 }
 
 int ensure_graph(bidi_engine* h, bool learn) {
@@ -404,7 +425,8 @@ void bidi_destroy(bidi_engine* h) {
   for (auto& g : h->graphs) if (g) cudaGraphExecDestroy(g);
   cudaFree(h->d_blob); cudaFree(h->d_in0); cudaFree(h->d_pred); cudaFree(h->d_rewards); cudaFree(h->d_noise_u);
   cudaFree(h->d_noise_v); cudaFree(h->d_col_actions); cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
-  cudaFree(h->d_tables); cudaFree(h->d_layers);
+  cudaFree(h->d_tables); cudaFree(h->d_layers); cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
+  for (auto& e : h->profile_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_pred); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_noise); cudaFreeHost(h->h_actions);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -871,7 +893,58 @@ int bidi_step_frame(bidi_engine* h, int t, int learn) {
   CU(cudaMemcpyAsync(h->d_in0, h->d_frames + (size_t)f * n, sizeof(float) * n, cudaMemcpyDeviceToDevice, h->stream));
   if (h->d_frame_rewards)
     CU(cudaMemcpyAsync(h->d_rewards, h->d_frame_rewards + (size_t)f * h->A, sizeof(float) * h->A, cudaMemcpyDeviceToDevice, h->stream));
+  if (h->fb_n > 0) {
+    bidi::k_feedback<<<grid_for(h->A, kBlock), kBlock, 0, h->stream>>>(h->P, h->fb_n, h->d_fb_src, h->d_fb_dst, h->fb_scale, h->fb_bias,
+                                                                      h->fb_std, h->noise_seed ^ 0xFEEDULL, h->step_index,
+                                                                      h->fb_reward ? h->d_rewards : nullptr);
+    h->launches++;
+  }
   return run_step(h, learn != 0, h->cfg.variant == BIDI_NEO_AGENT);
+}
+
+int bidi_set_feedback(bidi_engine* h, int n, const int* src, const int* dst, float scale, float bias, float noise_std,
+                      int reward_from_actions) {
+  if (!h || n < 0 || (n > 0 && (!src || !dst))) return fail(h, BIDI_EINVAL, "bidi_set_feedback: bad argument");
+  for (int k = 0; k < n; k++)
+    if (src[k] < 0 || src[k] >= h->n_in || dst[k] < 0 || dst[k] >= h->n_in) return fail(h, BIDI_EINVAL, "bidi_set_feedback: index out of range");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
+  h->d_fb_src = h->d_fb_dst = nullptr; h->fb_n = 0;
+  if (n > 0) {
+    CU(cudaMalloc(&h->d_fb_src, sizeof(int) * n));
+    CU(cudaMalloc(&h->d_fb_dst, sizeof(int) * n));
+    CU(cudaMemcpy(h->d_fb_src, src, sizeof(int) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->d_fb_dst, dst, sizeof(int) * n, cudaMemcpyHostToDevice));
+  }
+  h->fb_n = n; h->fb_scale = scale; h->fb_bias = bias; h->fb_std = noise_std; h->fb_reward = reward_from_actions;
+  return BIDI_OK;
+}
+
+int bidi_profile_select(bidi_engine* h, const char* kernel_name) {
+  if (!h) return fail(h, BIDI_EINVAL, "null engine");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  for (auto& e : h->profile_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  h->profile_events.clear();
+  h->profile_name = kernel_name ? kernel_name : "";
+  h->profile_ms = 0; h->profile_launches = 0;
+  return BIDI_OK;
+}
+
+int bidi_profile_collect(bidi_engine* h, double* total_ms, long long* launches) {
+  if (!h) return fail(h, BIDI_EINVAL, "null engine");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  for (auto& e : h->profile_events) {
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) { h->profile_ms += ms; h->profile_launches++; }
+    else cudaGetLastError(); // the pair belongs to the graph of the other learn flag: not recorded yet
+  }
+  if (total_ms) *total_ms = h->profile_ms;
+  if (launches) *launches = h->profile_launches;
+  return BIDI_OK;
 }
 
 int bidi_timer_start(bidi_engine* h) {

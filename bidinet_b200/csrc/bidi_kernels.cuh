@@ -423,6 +423,27 @@ __global__ void k_noise(EngineDev P, float* u, float* v, unsigned long long seed
   }
 }
 
+// The caller's side of the RunnerMain loop, for device-resident runs: input[dst] =
+// clamp01(prediction[src]*scale + bias + N(0,std)) (RunnerMain.cpp:241-242) and,
+// if asked, reward = mean(clamp01(prediction[src]*scale + bias)) - 0.5, the
+// headless stand-in for the Box2D body velocity.
+__global__ void k_feedback(EngineDev P, int n, const int* __restrict__ src, const int* __restrict__ dst, float scale,
+                           float bias, float std, unsigned long long seed, unsigned long long step, float* rewards) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= P.A) return;
+  const float* pred = P.pred_out + (long long)a * P.n_in;
+  float* in = P.in0 + (long long)a * P.n_in;
+  float sum = 0.0f;
+  for (int k = 0; k < n; k++) {
+    const float act = pred[src[k]] * scale + bias;
+    sum += bidi_clamp01(act);
+    unsigned long long h = mix64(seed ^ mix64(step * 0x9E3779B1ULL + (unsigned long long)a * n + k));
+    const float r1 = fmaxf(u01(h), 5.9604645e-8f), r2 = u01(mix64(h));
+    in[dst[k]] = bidi_clamp01(act + sqrtf(-2.0f * logf(r1)) * cospif(2.0f * r2) * std);
+  }
+  if (rewards) rewards[a] = sum / (float)n - 0.5f;
+}
+
 // One warp per column: lanes [0,cells) own a cell for the integrate-and-fire sweep
 // (sequential over the inputs, the reference's order), all lanes share the
 // reconstruction and the element-wise weight updates.  neo/Column.cpp:46-169; the

@@ -38,6 +38,9 @@ ABI = {
     "bidi_sync": (C.c_int, [C.c_void_p]),
     "bidi_load_frames": (C.c_int, [C.c_void_p, _FP, _FP, C.c_int]),
     "bidi_step_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bidi_set_feedback": (C.c_int, [C.c_void_p, C.c_int, _IP, _IP, C.c_float, C.c_float, C.c_float, C.c_int]),
+    "bidi_profile_select": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "bidi_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "bidi_timer_start": (C.c_int, [C.c_void_p]),
     "bidi_timer_stop_ms": (C.c_int, [C.c_void_p, _FP]),
     "bidi_launch_count": (C.c_longlong, [C.c_void_p]),
@@ -189,6 +192,22 @@ class Engine:
 
     def step_frame(self, t, learn=True):
         self._check(self.lib.bidi_step_frame(self.h, int(t), int(bool(learn))), "bidi_step_frame")
+
+    def set_feedback(self, src, dst, scale=0.5, bias=0.5, noise_std=0.05, reward_from_actions=True):
+        s = np.ascontiguousarray(src, dtype=np.int32)
+        d = np.ascontiguousarray(dst, dtype=np.int32)
+        assert s.size == d.size
+        self._check(self.lib.bidi_set_feedback(self.h, s.size, s.ctypes.data_as(_IP), d.ctypes.data_as(_IP), scale, bias,
+                                               noise_std, int(bool(reward_from_actions))), "bidi_set_feedback")
+
+    def profile_select(self, kernel_name):
+        self._check(self.lib.bidi_profile_select(self.h, kernel_name.encode() if kernel_name else None),
+                    "bidi_profile_select")
+
+    def profile_collect(self):
+        ms, n = C.c_double(), C.c_longlong()
+        self._check(self.lib.bidi_profile_collect(self.h, C.byref(ms), C.byref(n)), "bidi_profile_collect")
+        return ms.value, n.value
 
     def timer_start(self):
         self._check(self.lib.bidi_timer_start(self.h), "bidi_timer_start")

@@ -206,6 +206,25 @@ int bidi_sync(bidi_engine* h);
 int bidi_load_frames(bidi_engine* h, const float* frames, const float* rewards, int n_frames);
 int bidi_step_frame(bidi_engine* h, int t, int learn);
 
+/*
+ * The caller's half of the RunnerMain loop for device-resident runs
+ * (RunnerMain.cpp:241-249): before every bidi_step_frame, for each tap k,
+ * input[dst[k]] = clamp01(prediction[src[k]]*scale + bias + N(0,noise_std)); with
+ * reward_from_actions the step's reward is mean_k clamp01(prediction[src[k]]*scale
+ * + bias) - 0.5, the headless stand-in for the Box2D body velocity.  n = 0 disables.
+ */
+int bidi_set_feedback(bidi_engine* h, int n, const int* src, const int* dst, float scale, float bias,
+                      float noise_std, int reward_from_actions);
+
+/*
+ * Kernel-level timing inside the step graph: the launches of the named kernel
+ * ("columns", "ic_sweep", "reconstruct", "predict", ...) are bracketed by CUDA
+ * events on the engine's stream.  bidi_profile_collect, called after a step,
+ * adds that step's launches to the running totals (it synchronises).
+ */
+int bidi_profile_select(bidi_engine* h, const char* kernel_name);
+int bidi_profile_collect(bidi_engine* h, double* total_ms, long long* launches);
+
 /* Timing helpers on the engine's stream (CUDA events), for bench.py. */
 int bidi_timer_start(bidi_engine* h);
 int bidi_timer_stop_ms(bidi_engine* h, float* ms);

@@ -921,3 +921,20 @@ void orc_run(void* h, const float* frames, int n_frames, int n_in, const float* 
     orc_step(h, rewards ? rewards[t % n_frames] : 0.0f, learn);
   }
 }
+
+/* RunnerMain.cpp:235-251, headless; same loop as ref_run_runner in ref_harness.cpp. */
+void orc_run_runner(void* h, const float* frames, int n_frames, int n_in, int steps, int n_fb, const int* src,
+                    const int* dst, int learn) {
+  oracle* o = (oracle*)h;
+  for (int t = 0; t < steps; t++) {
+    orc_set_inputs(h, frames + (size_t)(t % n_frames) * n_in, n_in);
+    normal_state ns = { 0, 0.0f };
+    float sum = 0.0f;
+    for (int k = 0; k < n_fb; k++) {
+      const float a = orc_get_prediction(h, src[k]) * 0.5f + 0.5f;
+      sum += clamp01(a);
+      orc_set_input(h, dst[k], clamp01(a + normal_real(&o->gen, &ns, 0.0f, 0.05f)));
+    }
+    orc_step(h, n_fb ? sum / (float)n_fb - 0.5f : 0.0f, learn);
+  }
+}

@@ -28,6 +28,8 @@ void orc_step(void* h, float reward, int learn);
 /* simStep with the exploration noise supplied (the generator is not advanced) */
 void orc_step_noise(void* h, float reward, const float* u, const float* v, int learn);
 void orc_run(void* h, const float* frames, int n_frames, int n_in, const float* rewards, int steps, int learn);
+void orc_run_runner(void* h, const float* frames, int n_frames, int n_in, int steps, int n_fb, const int* src,
+                    const int* dst, int learn);
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,7 @@ def _bind(lib, p):
         "peek_noise": (C.c_int, [C.c_void_p, _FP, _FP]),
         "step": (None, [C.c_void_p, C.c_float, C.c_int]),
         "run": (None, [C.c_void_p, _FP, C.c_int, C.c_int, _FP, C.c_int, C.c_int]),
+        "run_runner": (None, [C.c_void_p, _FP, C.c_int, C.c_int, C.c_int, C.c_int, _IP, _IP, C.c_int]),
     }
     for name, (res, args) in sig.items():
         f = getattr(lib, p + name)
@@ -165,6 +166,15 @@ class _Hierarchy:
         assert rw is None or rw.size == fr.shape[0]
         self._f("run")(self.h, _fptr(fr), fr.shape[0], self.n_in, None if rw is None else _fptr(rw),
                        int(steps), int(bool(learn)))
+
+
+    def run_runner(self, frames, steps, src, dst, learn=True):
+        """The headless RunnerMain loop (closed action feedback) for `steps` steps."""
+        fr = np.ascontiguousarray(frames, dtype=np.float32).reshape(-1, self.n_in)
+        s = np.ascontiguousarray(src, dtype=np.int32)
+        d = np.ascontiguousarray(dst, dtype=np.int32)
+        self._f("run_runner")(self.h, _fptr(fr), fr.shape[0], self.n_in, int(steps), s.size,
+                              s.ctypes.data_as(_IP), d.ctypes.data_as(_IP), int(bool(learn)))
 
 
 class RefHierarchy(_Hierarchy):

@@ -315,6 +315,28 @@ void ref_run(void* h, const float* frames, int n_frames, int n_in, const float* 
   }
 }
 
+// The RunnerMain loop, headless (RunnerMain.cpp:235-251): per step the open-loop
+// part of the input comes from frames[t % n_frames]; inputs dst[k] are the fed-back
+// actions clamp01(getPrediction(src[k])*0.5+0.5+N(0,0.05)) with the noise drawn
+// from the agent's generator through a per-step normal_distribution, as the main
+// does; reward = mean_k clamp01(getPrediction(src[k])*0.5+0.5) - 0.5 stands in for
+// the Box2D body velocity.
+void ref_run_runner(void* h, const float* frames, int n_frames, int n_in, int steps, int n_fb, const int* src,
+                    const int* dst, int learn) {
+  Ref& r = *static_cast<Ref*>(h);
+  for (int t = 0; t < steps; t++) {
+    ref_set_inputs(h, frames + (size_t)(t % n_frames) * n_in, n_in);
+    std::normal_distribution<float> noiseDist(0.0f, 0.05f);
+    float sum = 0.0f;
+    for (int k = 0; k < n_fb; k++) {
+      const float a = ref_get_prediction(h, src[k]) * 0.5f + 0.5f;
+      sum += std::min(1.0f, std::max(0.0f, a));
+      ref_set_input(h, dst[k], std::min(1.0f, std::max(0.0f, a + noiseDist(r.gen))));
+    }
+    ref_step(h, n_fb ? sum / n_fb - 0.5f : 0.0f, learn);
+  }
+}
+
 int ref_num_columns(void* h) {
   Ref& r = *static_cast<Ref*>(h);
   if (r.cfg.variant != BIDI_NEO_AGENT) return 0;
