@@ -27,8 +27,31 @@ struct WinHost {
 };
 
 struct ColumnsHost {
-  std::vector<int> in_off;
+  std::vector<int> in_off, rec_off, stride;
 };
+
+// Pointers to the sections of one column record inside a host blob image
+// (layout: bidi_types.h, ColumnsDev).
+struct ColRec {
+  float *W, *latT, *thr, *q_w, *q_tr, *a_w, *a_tr, *sprev, *err, *scal;
+  int S, Cq, nin;
+};
+ColRec col_rec(const ColumnsDev& C, const ColumnsHost& H, float* blob, int node) {
+  ColRec r;
+  r.S = H.stride[node]; r.Cq = C.cq; r.nin = H.in_off[node + 1] - H.in_off[node];
+  r.W = blob + C.rec_base + H.rec_off[node];
+  r.latT = r.W + (long long)C.cells * r.S;
+  r.thr = r.latT + C.cells * C.cq;
+  r.q_w = r.thr + C.cq; r.q_tr = r.q_w + C.cq; r.a_w = r.q_tr + C.cq; r.a_tr = r.a_w + 3 * C.cq;
+  r.sprev = r.a_tr + 3 * C.cq; r.err = r.sprev + C.cq; r.scal = r.err + r.S;
+  return r;
+}
+// row stride of a column's weights: nIn rounded up to a multiple of 4 with stride/4 odd
+int column_stride(int nin) {
+  int s = std::max(4, (nin + 3) / 4 * 4);
+  if (((s / 4) & 1) == 0) s += 4;
+  return s;
+}
 
 struct LayerHost {
   WinHost ff, rec, lat, fb, pred;
@@ -149,10 +172,11 @@ bool is_traced(int v) { return v == BIDI_NEO_HIERARCHY || v == BIDI_NEO_AGENT; }
 // ------------------------------------------------------------------ array table
 // How a serialised array (include/bidinet_b200.h enum bidi_array) maps to storage.
 struct ArrayRef {
-  enum Kind { NONE, PLANE, LIST, DENSE_IN, DENSE_PRED } kind = NONE;
+  enum Kind { NONE, PLANE, LIST, DENSE_IN, DENSE_PRED, COLUMN } kind = NONE;
   long long off = 0, len = 0;   // PLANE: blob offset and length
   const WinHost* win = nullptr; // LIST
   bool trace = false;
+  int which = 0, layer = 0;     // COLUMN: a field of the column records
 };
 
 ArrayRef find_array(const bidi_engine* h, int which, int layer) {
@@ -160,6 +184,7 @@ ArrayRef find_array(const bidi_engine* h, int which, int layer) {
   const int L = h->L, V = h->cfg.variant;
   if (layer < 0 || layer > L) return r;
   auto plane = [&](long long off, long long len) { r.kind = ArrayRef::PLANE; r.off = off; r.len = len; return r; };
+  auto column = [&](long long len) { r.kind = ArrayRef::COLUMN; r.which = which; r.layer = layer; r.len = len; return r; };
   auto list = [&](const WinHost& w, bool tr) {
     if (w.d.r < 0 || (tr ? w.d.tr_off : w.d.w_off) < 0) return r;
     r.kind = ArrayRef::LIST; r.win = &w; r.trace = tr; r.len = conn_total(w); return r;
@@ -209,21 +234,17 @@ ArrayRef find_array(const bidi_engine* h, int which, int layer) {
   const long long tot = C.tot_in, nc = (long long)C.n * C.cells;
   switch (which) {
     case BIDI_COL_INPUT: return plane(C.inputs, tot);
-    case BIDI_COL_RECON_ERR: return plane(C.recon_err, tot);
-    case BIDI_COL_FF_W: return plane(C.ff_w, tot * C.cells);
-    case BIDI_COL_LAT_W: return plane(C.lat_w, nc * C.cells);
-    case BIDI_COL_THRESHOLD: return plane(C.thr, nc);
     case BIDI_COL_ACTIVATION: return plane(C.act, nc);
     case BIDI_COL_SPIKE: return plane(C.spike, nc);
-    case BIDI_COL_SPIKE_PREV: return plane(C.spike_prev, nc);
     case BIDI_COL_STATE: return plane(C.state, nc);
-    case BIDI_COL_Q_W: return plane(C.q_w, nc);
-    case BIDI_COL_Q_TRACE: return plane(C.q_tr, nc);
     case BIDI_COL_ACT_STATE: return plane(C.a_state, (long long)C.n * 3);
     case BIDI_COL_ACT_EXPL: return plane(C.a_expl, (long long)C.n * 3);
-    case BIDI_COL_ACT_W: return plane(C.a_w, nc * 3);
-    case BIDI_COL_ACT_TRACE: return plane(C.a_tr, nc * 3);
-    case BIDI_COL_PREV_VALUE: return plane(C.prev_value, C.n);
+    case BIDI_COL_RECON_ERR: return column(tot);
+    case BIDI_COL_FF_W: return column(tot * C.cells);
+    case BIDI_COL_LAT_W: return column(nc * C.cells);
+    case BIDI_COL_THRESHOLD: case BIDI_COL_SPIKE_PREV: case BIDI_COL_Q_W: case BIDI_COL_Q_TRACE: return column(nc);
+    case BIDI_COL_ACT_W: case BIDI_COL_ACT_TRACE: return column(nc * 3);
+    case BIDI_COL_PREV_VALUE: return column(C.n);
   }
   return r;
 }
@@ -268,6 +289,27 @@ template <class F> void walk_list(const WinHost& w, bool trace, float* blob, F&&
     }
 }
 
+// A record-resident column array in the reference's order ([node][cell][input] ...).
+template <class F> void walk_column(const bidi_engine* h, int which, int layer, float* blob, F&& f) {
+  const ColumnsDev& C = h->layers[layer].col;
+  const ColumnsHost& H = h->hl[layer].col;
+  for (int node = 0; node < C.n; node++) {
+    const ColRec r = col_rec(C, H, blob, node);
+    switch (which) {
+      case BIDI_COL_RECON_ERR: for (int j = 0; j < r.nin; j++) f(r.err[j]); break;
+      case BIDI_COL_FF_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < r.nin; j++) f(r.W[(long long)i * r.S + j]); break;
+      case BIDI_COL_LAT_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < C.cells; j++) f(r.latT[j * r.Cq + i]); break;
+      case BIDI_COL_THRESHOLD: for (int i = 0; i < C.cells; i++) f(r.thr[i]); break;
+      case BIDI_COL_SPIKE_PREV: for (int i = 0; i < C.cells; i++) f(r.sprev[i]); break;
+      case BIDI_COL_Q_W: for (int i = 0; i < C.cells; i++) f(r.q_w[i]); break;
+      case BIDI_COL_Q_TRACE: for (int i = 0; i < C.cells; i++) f(r.q_tr[i]); break;
+      case BIDI_COL_ACT_W: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_w[a * r.Cq + i]); break;
+      case BIDI_COL_ACT_TRACE: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_tr[a * r.Cq + i]); break;
+      case BIDI_COL_PREV_VALUE: f(r.scal[0]); break;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ launches
 inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
 constexpr int kBlock = 128;
@@ -295,13 +337,19 @@ struct Recorder {
   }
 };
 
+size_t columns_smem_bytes(const ColumnsDev& C) {
+  const int cpw = C.cells <= 16 ? 2 : 1;
+  return sizeof(float) * BIDI_COL_WARPS * cpw * (size_t)bidi::column_slab_floats(C.max_rec, C.max_s) + 8 * BIDI_COL_WARPS;
+}
 void record_columns(Recorder& R, int l) {
   bidi_engine* h = R.h;
   const ColumnsDev& C = h->layers[l].col;
-  const long long warps = (long long)h->A * C.n;
-  const size_t smem = sizeof(float) * BIDI_COL_WARPS * (2 * (size_t)C.max_in + 96);
+  const int cpw = C.cells <= 16 ? 2 : 1;
+  const long long warps = (long long)h->A * ((C.n + cpw - 1) / cpw);
+  const size_t smem = columns_smem_bytes(C);
   R.before("columns");
-  bidi::k_columns<<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, l);
+  if (cpw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, l);
+  else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, l);
   R.after("columns");
   R.kernels++;
 }
@@ -533,23 +581,29 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       }
       // nIn = |pred| + 2|fb|  (neo/Agent.cpp:90,137)
       H.col.in_off.assign(C.n + 1, 0);
-      C.max_in = 0;
+      H.col.rec_off.assign(C.n + 1, 0);
+      H.col.stride.assign(C.n, 0);
+      C.cq = (C.cells + 3) / 4 * 4;
+      C.max_in = C.max_s = C.max_rec = 0;
       for (int i = 0; i < C.n; i++) {
         const int ux = i % H.fb.d.uw, uy = i / H.fb.d.uw;
         int nfb = 0, npr = 0;
         for_each_conn_host(H.fb, ux, uy, [&](int, int) { nfb++; });
         for_each_conn_host(H.pred, ux, uy, [&](int, int) { npr++; });
         const int nin = npr + 2 * nfb;
+        const int S = column_stride(nin);
+        const int rec = C.cells * S + C.cells * C.cq + 10 * C.cq + S + 4;
         H.col.in_off[i + 1] = H.col.in_off[i] + nin;
-        C.max_in = std::max(C.max_in, nin);
+        H.col.rec_off[i + 1] = H.col.rec_off[i] + rec;
+        H.col.stride[i] = S;
+        C.max_in = std::max(C.max_in, nin); C.max_s = std::max(C.max_s, S); C.max_rec = std::max(C.max_rec, rec);
       }
       C.tot_in = H.col.in_off[C.n];
       const long long nc = (long long)C.n * C.cells;
-      C.inputs = al.take(C.tot_in); C.recon_err = al.take(C.tot_in);
-      C.ff_w = al.take((long long)C.tot_in * C.cells); C.lat_w = al.take(nc * C.cells);
-      C.thr = al.take(nc); C.act = al.take(nc); C.spike = al.take(nc); C.spike_prev = al.take(nc); C.state = al.take(nc);
-      C.q_w = al.take(nc); C.q_tr = al.take(nc); C.a_state = al.take(C.n * 3LL); C.a_expl = al.take(C.n * 3LL);
-      C.a_w = al.take(nc * 3); C.a_tr = al.take(nc * 3); C.prev_value = al.take(C.n);
+      C.rec_base = al.take(H.col.rec_off[C.n]);
+      C.inputs = al.take(C.tot_in);
+      C.act = al.take(nc); C.spike = al.take(nc); C.state = al.take(nc);
+      C.a_state = al.take(C.n * 3LL); C.a_expl = al.take(C.n * 3LL);
     }
   }
   h->stride = al.top;
@@ -609,7 +663,11 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       push(w->cx, &w->d.cx); push(w->cy, &w->d.cy);
       push(w->gxlo, &w->d.gx_lo); push(w->gxhi, &w->d.gx_hi); push(w->gylo, &w->d.gy_lo); push(w->gyhi, &w->d.gy_hi);
     }
-    if (V == BIDI_NEO_AGENT) push(H.col.in_off, &h->layers[l].col.in_off);
+    if (V == BIDI_NEO_AGENT) {
+      push(H.col.in_off, &h->layers[l].col.in_off);
+      push(H.col.rec_off, &h->layers[l].col.rec_off);
+      push(H.col.stride, &h->layers[l].col.stride);
+    }
   }
   CU_CREATE(cudaMalloc(&h->d_tables, sizeof(int) * pool.size()));
   CU_CREATE(cudaMemcpyAsync(h->d_tables, pool.data(), sizeof(int) * pool.size(), cudaMemcpyHostToDevice, h->stream));
@@ -636,7 +694,11 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     for (int l = 0; l <= L; l++) {
       const LayerDev& D = h->layers[l];
       if (l < L) for (int i = 0; i < D.nh; i++) img[D.thr + i] = cfg->init_threshold;
-      if (V == BIDI_NEO_AGENT) for (long long i = 0; i < (long long)D.col.n * D.col.cells; i++) img[D.col.thr + i] = cfg->init_threshold;
+      if (V == BIDI_NEO_AGENT)
+        for (int node = 0; node < D.col.n; node++) {
+          const ColRec r = col_rec(D.col, h->hl[l].col, img.data(), node);
+          for (int i = 0; i < D.col.cells; i++) r.thr[i] = cfg->init_threshold;
+        }
     }
     for (int a = 0; a < n_agents; a++)
       CU_CREATE(cudaMemcpyAsync(h->d_blob + (long long)a * h->stride, img.data(), sizeof(float) * h->stride, cudaMemcpyHostToDevice, h->stream));
@@ -644,11 +706,11 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   }
   // the column kernel may need more than the default 48 KB of dynamic shared memory
   if (V == BIDI_NEO_AGENT) {
-    int max_in = 0;
-    for (auto& D : h->layers) max_in = std::max(max_in, D.col.max_in);
-    const size_t smem = sizeof(float) * BIDI_COL_WARPS * (2 * (size_t)max_in + 96);
-    if (smem > 200 * 1024) return bail(BIDI_EINVAL, "bidi_create: column input count too large for shared memory");
-    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = 0;
+    for (auto& D : h->layers) if (D.col.n > 0) smem = std::max(smem, columns_smem_bytes(D.col));
+    if (smem > 227 * 1024) return bail(BIDI_EINVAL, "bidi_create: a column record does not fit in shared memory");
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   *out = h;
   return BIDI_OK;
@@ -712,6 +774,7 @@ int bidi_set_array(bidi_engine* h, int agent, int which, int layer, const float*
   int rc = mirror_load(h, agent);
   if (rc) return rc;
   if (r.kind == ArrayRef::PLANE) memcpy(h->mirror.data() + r.off, src, sizeof(float) * len);
+  else if (r.kind == ArrayRef::COLUMN) walk_column(h, r.which, r.layer, h->mirror.data(), [&](float& v) { v = *src++; });
   else walk_list(*r.win, r.trace, h->mirror.data(), [&](float& v) { v = *src++; });
   h->mirror_dirty = true;
   return BIDI_OK;
@@ -731,6 +794,7 @@ int bidi_get_array(bidi_engine* h, int agent, int which, int layer, float* dst, 
   int rc = mirror_load(h, agent);
   if (rc) return rc;
   if (r.kind == ArrayRef::PLANE) memcpy(dst, h->mirror.data() + r.off, sizeof(float) * len);
+  else if (r.kind == ArrayRef::COLUMN) walk_column(h, r.which, r.layer, h->mirror.data(), [&](float& v) { *dst++ = v; });
   else walk_list(*r.win, r.trace, h->mirror.data(), [&](float& v) { *dst++ = v; });
   return BIDI_OK;
 }
@@ -759,16 +823,15 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
       for_each_conn_host(w, ux, uy, [&](int s, int) { base[(long long)s * w.d.U + u] = dist(gen); });
     };
     auto draw_column = [&](const ColumnsDev& C, const ColumnsHost& CH, int node) { // neo/Column.cpp:22-43
-      const int in0 = CH.in_off[node], nin = CH.in_off[node + 1] - in0;
-      float* ff = img.data() + C.ff_w + (long long)C.cells * in0;
+      const ColRec r = col_rec(C, CH, img.data(), node);
       for (int i = 0; i < C.cells; i++) {
-        img[C.thr + (long long)node * C.cells + i] = g.init_threshold;
-        for (int j = 0; j < nin; j++) ff[(long long)i * nin + j] = weightDist(gen);
-        for (int j = 0; j < C.cells; j++) img[C.lat_w + ((long long)node * C.cells + i) * C.cells + j] = inhibitionDist(gen);
-        img[C.q_w + (long long)node * C.cells + i] = weightDist(gen);
+        r.thr[i] = g.init_threshold;
+        for (int j = 0; j < r.nin; j++) r.W[(long long)i * r.S + j] = weightDist(gen);
+        for (int j = 0; j < C.cells; j++) r.latT[j * r.Cq + i] = inhibitionDist(gen);
+        r.q_w[i] = weightDist(gen);
       }
       for (int a = 0; a < 3; a++)
-        for (int k = 0; k < C.cells; k++) img[C.a_w + ((long long)node * 3 + a) * C.cells + k] = weightDist(gen);
+        for (int k = 0; k < C.cells; k++) r.a_w[a * r.Cq + k] = weightDist(gen);
     };
     for (int l = 0; l <= L; l++) {
       if (l == L && V == BIDI_KWINNERS) break;

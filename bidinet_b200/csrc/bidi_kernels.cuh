@@ -444,162 +444,6 @@ __global__ void k_feedback(EngineDev P, int n, const int* __restrict__ src, cons
   if (rewards) rewards[a] = sum / (float)n - 0.5f;
 }
 
-// One warp per column: lanes [0,cells) own a cell for the integrate-and-fire sweep
-// (sequential over the inputs, the reference's order), all lanes share the
-// reconstruction and the element-wise weight updates.  neo/Column.cpp:46-169; the
-// inputs are gathered first as neo/Agent.cpp:159-169 / :217-220 do.
-#define BIDI_COL_WARPS 8
-__global__ void __launch_bounds__(BIDI_COL_WARPS * 32) k_columns(EngineDev P, int l) {
-  extern __shared__ float smem[];
-  const LayerDev& L = P.layers[l];
-  const ColumnsDev& C = L.col;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long cid = (long long)blockIdx.x * BIDI_COL_WARPS + warp;
-  if (cid >= (long long)P.A * C.n) return;
-  const int a = (int)(cid / C.n), node = (int)(cid % C.n);
-  float* B = blob_of(P, a);
-  const int cells = C.cells;
-  const int in0 = C.in_off[node], nin = C.in_off[node + 1] - in0;
-  // per-warp shared scratch
-  float* s_in = smem + (size_t)warp * (2 * C.max_in + 3 * 32);
-  float* s_err = s_in + C.max_in;
-  float* s_spike = s_err + C.max_in;
-  float* s_sprev = s_spike + 32;
-  float* s_state = s_sprev + 32;
-
-  // ---- gather the column's inputs
-  const bool input_layer = l == P.L;
-  const LayerDev& Up = P.layers[input_layer ? 0 : (l == P.L - 1 ? l : l + 1)];
-  const int ux = node % L.fb.uw, uy = node / L.fb.uw;
-  int nfb = 0;
-  if (L.fb.r >= 0 && (input_layer || l < P.L - 1)) {
-    const SlotBox b = slot_box(L.fb, ux, uy);
-    const int ny = b.sy1 - b.sy0 + 1;
-    nfb = slot_count(L.fb, b);
-    const float* up_sig = B + Up.col.a_expl;
-    const float* up_state = B + Up.p_state;
-    for (int k = lane; k < nfb; k += 32) {
-      const int sx = b.sx0 + k / ny, sy = b.sy0 + k % ny;
-      const int t = slot_tx(L.fb, b, sx) + slot_ty(L.fb, b, sy) * L.fb.tw;
-      s_in[2 * k] = up_sig[t * 3 + 2];   // _signal
-      s_in[2 * k + 1] = up_state[t];
-    }
-  }
-  if (!input_layer) {
-    const SlotBox b = slot_box(L.pred, ux, uy);
-    const int ny = b.sy1 - b.sy0 + 1;
-    const int npr = slot_count(L.pred, b);
-    const float* state = B + L.state;
-    for (int k = lane; k < npr; k += 32) {
-      const int sx = b.sx0 + k / ny, sy = b.sy0 + k % ny;
-      s_in[2 * nfb + k] = state[slot_tx(L.pred, b, sx) + slot_ty(L.pred, b, sy) * L.pred.tw];
-    }
-  }
-  float* g_in = B + C.inputs + in0;
-  float* g_err = B + C.recon_err + in0;
-  float* ff = B + C.ff_w + (long long)cells * in0;
-  float* lat = B + C.lat_w + (long long)node * cells * cells;
-  const int cb = node * cells;
-  __syncwarp();
-  for (int j = lane; j < nin; j += 32) { g_in[j] = s_in[j]; s_err[j] = g_err[j]; }
-  if (lane < 32) { s_sprev[lane] = lane < cells ? B[C.spike_prev + cb + lane] : 0.0f; s_state[lane] = 0.0f; s_spike[lane] = 0.0f; }
-  __syncwarp();
-
-  // ---- iterate
-  float act = 0.0f, st = 0.0f;
-  const float thr = lane < cells ? B[C.thr + cb + lane] : 0.0f;
-  float counter = 0.0f;
-  for (int it = 0; it < C.iter; it++) {
-    float spike = 0.0f;
-    if (lane < cells) {
-      float excitation = 0.0f;
-      const float* w = ff + (long long)lane * nin;
-      for (int j = 0; j < nin; j++) excitation += w[j] * s_err[j];
-      float inhibition = 0.0f;
-      const float* wl = lat + lane * cells;
-      for (int j = 0; j < cells; j++) inhibition += wl[j] * s_sprev[j];
-      float activation = (1.0f - C.leak) * act + excitation - inhibition;
-      if (activation > thr) { activation = 0.0f; spike = 1.0f; }
-      st += spike;
-      act = activation;
-    }
-    __syncwarp();
-    if (lane < cells) { s_spike[lane] = spike; s_sprev[lane] = spike; }
-    __syncwarp();
-    counter += 1.0f;
-    const float multiplier = 1.0f / counter;
-    for (int j = lane; j < nin; j += 32) {
-      float recon = 0.0f;
-      for (int k = 0; k < cells; k++) {
-        const float sp = s_spike[k];
-        if (sp != 0.0f) recon += sp * multiplier * ff[(long long)k * nin + j];
-      }
-      s_err[j] = s_in[j] - recon;
-    }
-    __syncwarp();
-  }
-  const float mult = 1.0f / counter;
-  st *= mult;
-  if (lane < cells) s_state[lane] = st;
-  __syncwarp();
-
-  // ---- value and actions (sequential over the cells, neo/Column.cpp:111-123)
-  const float* qw = B + C.q_w + cb;
-  float q = 0.0f;
-  for (int k = 0; k < cells; k++) q += qw[k] * s_state[k];
-  float a_state = 0.0f, a_expl = 0.0f;
-  if (lane < 3) {
-    const float* aw = B + C.a_w + ((long long)node * 3 + lane) * cells;
-    float sum = 0.0f;
-    for (int k = 0; k < cells; k++) sum += aw[k] * s_state[k];
-    a_state = bidi_sigmoid(sum);
-    const long long nk = ((long long)a * P.ncol + C.noise_base + node) * 3 + lane;
-    const float u = P.noise_u[nk], v = P.noise_v[nk];
-    a_expl = u < C.expl_break ? v : bidi_clamp01(a_state + v);
-    B[C.a_state + node * 3 + lane] = a_state;
-    B[C.a_expl + node * 3 + lane] = a_expl;
-    P.col_actions[nk] = a_expl;
-  }
-  const float prev_value = B[C.prev_value + node];
-  const float td = P.rewards[a] + C.gamma * q - prev_value;
-  const float q_alpha_td = C.a_q * td, act_alpha_td = C.a_act * td;
-  // ---- learning
-  if (lane < cells) {
-    float* qwm = B + C.q_w + cb;
-    float* qtr = B + C.q_tr + cb;
-    const float tr = qtr[lane];
-    qwm[lane] += q_alpha_td * tr;
-    qtr[lane] = tr * C.gamma_lambda + st;
-  }
-  for (int act_i = 0; act_i < 3; act_i++) {
-    const float as = __shfl_sync(0xffffffffu, a_state, act_i), ae = __shfl_sync(0xffffffffu, a_expl, act_i);
-    if (lane < cells) {
-      float* aw = B + C.a_w + ((long long)node * 3 + act_i) * cells;
-      float* at = B + C.a_tr + ((long long)node * 3 + act_i) * cells;
-      const float tr = at[lane];
-      aw[lane] += act_alpha_td * tr;
-      at[lane] = tr * C.gamma_lambda + (ae - as) * st;
-    }
-  }
-  const float sp2 = C.sparsity * C.sparsity;
-  for (int e = lane; e < cells * nin; e += 32) {
-    const int ci = e / nin, j = e - ci * nin;
-    const float sc = s_state[ci];
-    if (sc > 0.0f) ff[e] += C.a_ff * sc * s_err[j];
-  }
-  for (int e = lane; e < cells * cells; e += 32) {
-    const int ci = e / cells, j = e - ci * cells;
-    lat[e] = bidi_max(0.0f, lat[e] + C.a_lat * (s_state[ci] * s_state[j] - sp2));
-  }
-  for (int j = lane; j < nin; j += 32) g_err[j] = s_err[j];
-  if (lane < cells) {
-    B[C.thr + cb + lane] = thr + C.a_thr * (st - C.sparsity);
-    B[C.act + cb + lane] = act;
-    B[C.spike + cb + lane] = s_spike[lane];
-    B[C.spike_prev + cb + lane] = s_sprev[lane];
-    B[C.state + cb + lane] = st;
-  }
-  if (lane == 0) B[C.prev_value + node] = q;
-}
-
 } // namespace bidi
+
+#include "bidi_columns.cuh"

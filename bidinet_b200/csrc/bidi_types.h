@@ -44,12 +44,28 @@ struct WinDev {
   long long tr_off;  // eligibility traces, same shape, -1 if none
 };
 
+// The columns (neo::Column) of one node layer.  Everything a column reads AND
+// writes each step lives in one contiguous, 16-byte aligned "record" so that one
+// TMA bulk copy brings it into shared memory and one takes it back:
+//   W[cells][S]      feed-forward weights, row stride S = nIn padded to a multiple
+//                    of 4 with S/4 odd (conflict-free 128-bit shared loads when
+//                    lane i walks row i); pad entries are 0
+//   latT[cells][Cq]  lateral weights TRANSPOSED (latT[k][i] = lat[i][k]), Cq = cells
+//                    rounded up to 4
+//   10 vectors [Cq]  threshold, q w, q trace, 3 action w, 3 action traces, spikePrev
+//   err[S]           _reconstructionError
+//   scal[4]          prevValue, pad
+// Write-only per-step outputs (inputs, activation, spike, state, action states) stay
+// in plain planes.
 struct ColumnsDev {
-  int n, cells, tot_in;     // nodes, cells per column, sum of nIn
+  int n, cells, cq, tot_in; // nodes, cells per column, cells rounded up to 4, sum of nIn
   int max_in;               // largest nIn
+  int max_s, max_rec;       // largest padded stride / record length (floats)
   const int* in_off;        // [n+1] prefix sums of nIn (same for every agent)
-  long long inputs, recon_err, ff_w, lat_w, thr, act, spike, spike_prev, state;
-  long long q_w, q_tr, a_state, a_expl, a_w, a_tr, prev_value;
+  const int* rec_off;       // [n+1] record offsets (floats) relative to rec_base
+  const int* stride;        // [n] S
+  long long rec_base;       // blob offset of the first record
+  long long inputs, act, spike, state, a_state, a_expl; // planes
   int noise_base;           // first column index of this layer in the visit order (x3 for the noise arrays)
   // neo/Column.cpp:46 simStep arguments
   float sparsity, gamma, leak, a_ff, a_lat, a_thr, a_q, a_act, gamma_lambda, expl_std, expl_break;
