@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "bidi_kernels.cuh"
+#include "bidi_coder.cuh"
 
 namespace {
 
@@ -67,6 +68,8 @@ struct bidi_engine {
   std::vector<LayerDev> layers;    // host copy, device pointers inside
   std::vector<LayerHost> hl;
   long long stride = 0;            // floats per agent blob
+  std::vector<int> coder_cta;      // per layer: the fused one-CTA-per-agent coder kernel applies
+  bool force_phase_kernels = false;
   EngineDev P;                     // kernel argument
   // device memory
   float* d_blob = nullptr; float* d_in0 = nullptr; float* d_pred = nullptr;
@@ -381,6 +384,16 @@ void record_step(Recorder& R, bool learn) {
   }
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
+    if (h->coder_cta[l] && !h->force_phase_kernels) { // whole up pass of the layer in one launch
+      const int threads = std::min(512, std::max(64, (ly[l].nv + ly[l].nh + 31) / 32 * 32));
+      const size_t smem = sizeof(float) * (size_t)bidi::coder_cta_smem_floats(ly[l]);
+      R.before("coder");
+      if (V == BIDI_ITERATIVE) bidi::k_coder_cta<0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, l);
+      else bidi::k_coder_cta<1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, l);
+      R.after("coder");
+      R.kernels++;
+      continue;
+    }
     if (V == BIDI_ITERATIVE) { // sdr/IRSDR.cpp:125-216
       const int settle = ly[l].iter_settle, measure = ly[l].iter_measure;
       for (int it = 0; it < settle; it++) {
@@ -704,6 +717,19 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       CU_CREATE(cudaMemcpyAsync(h->d_blob + (long long)a * h->stride, img.data(), sizeof(float) * h->stride, cudaMemcpyHostToDevice, h->stream));
     CU_CREATE(cudaStreamSynchronize(h->stream));
   }
+  // layers whose planes fit in shared memory use the fused coder kernel
+  h->coder_cta.assign(L, 0);
+  if (V != BIDI_KWINNERS) {
+    size_t smem = 0;
+    for (int l = 0; l < L; l++) {
+      const size_t need = sizeof(float) * (size_t)bidi::coder_cta_smem_floats(h->layers[l]);
+      if (need <= 200 * 1024) { h->coder_cta[l] = 1; smem = std::max(smem, need); }
+    }
+    if (smem > 0) {
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_cta<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_cta<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+  }
   // the column kernel may need more than the default 48 KB of dynamic shared memory
   if (V == BIDI_NEO_AGENT) {
     size_t smem = 0;
@@ -981,6 +1007,17 @@ int bidi_set_feedback(bidi_engine* h, int n, const int* src, const int* dst, flo
     CU(cudaMemcpy(h->d_fb_dst, dst, sizeof(int) * n, cudaMemcpyHostToDevice));
   }
   h->fb_n = n; h->fb_scale = scale; h->fb_bias = bias; h->fb_std = noise_std; h->fb_reward = reward_from_actions;
+  return BIDI_OK;
+}
+
+/* 1: always run the per-phase kernels, even where the fused coder kernel applies (tests compare both paths) */
+int bidi_set_option(bidi_engine* h, const char* name, int value) {
+  if (!h || !name) return fail(h, BIDI_EINVAL, "bidi_set_option: null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (std::string(name) == "force_phase_kernels") h->force_phase_kernels = value != 0;
+  else return fail(h, BIDI_EINVAL, "bidi_set_option: unknown option");
+  for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   return BIDI_OK;
 }
 

@@ -225,6 +225,13 @@ int bidi_set_feedback(bidi_engine* h, int n, const int* src, const int* dst, flo
 int bidi_profile_select(bidi_engine* h, const char* kernel_name);
 int bidi_profile_collect(bidi_engine* h, double* total_ms, long long* launches);
 
+/*
+ * Engine options.  "force_phase_kernels" = 1: run one kernel per phase even where
+ * the fused per-agent coder kernel applies (both paths give identical results; the
+ * tests compare them).
+ */
+int bidi_set_option(bidi_engine* h, const char* name, int value);
+
 /* Timing helpers on the engine's stream (CUDA events), for bench.py. */
 int bidi_timer_start(bidi_engine* h);
 int bidi_timer_stop_ms(bidi_engine* h, float* ms);

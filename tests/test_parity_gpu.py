@@ -42,12 +42,16 @@ def test_init_random_matches_oracle(case):
         assert diff_states(orc.state(), eng.state(agent=a)) == [], "agent %d" % a
 
 
+@pytest.mark.parametrize("phase_kernels", [False, True], ids=["fused", "per_phase"])
 @pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
-def test_free_running_parity(case):
-    """N steps from an identical state, no re-synchronisation: exact after every step."""
+def test_free_running_parity(case, phase_kernels):
+    """N steps from an identical state, no re-synchronisation: exact after every step.
+    Both engine paths are held to it: the fused per-agent coder kernel (default where
+    the layer fits in shared memory) and the one-kernel-per-phase path (large layers)."""
     name, cfg, ld, frame, reward = case
     orc = OracleHierarchy(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1)
+    eng.set_option("force_phase_kernels", phase_kernels)
     eng.load_state(orc.state())
     steps = 25
     for t in range(steps):
