@@ -28,9 +28,8 @@ __host__ __device__ inline long long coder_cta_smem_floats(const LayerDev& L) {
 }
 
 template <int NEO>
-__global__ void __launch_bounds__(512) k_coder_cta(EngineDev P, int l) {
+__global__ void __launch_bounds__(512) k_coder_cta(EngineDev P, LayerDev L, int l, long long next_vis_input) {
   extern __shared__ __align__(16) float sm[];
-  const LayerDev& L = P.layers[l];
   const int a = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
   float* B = blob_of(P, a);
   const int nv = L.nv, nh = L.nh, hw = L.hw, hh = L.hh;
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(512) k_coder_cta(EngineDev P, int l) {
     for (int j = tid; j < nv; j += T) B[L.vis_recon + j] = vrec[j];
     for (int j = tid; j < nh; j += T) B[L.recon + j] = hrec[j];
   }
-  const bool has_next = l < P.L - 1;
+  const bool has_next = next_vis_input >= 0;
   for (int i = tid; i < nh; i += T) {
     float st = state[i];
     if (NEO) st *= mult;  // neo/SparseCoder.cpp:171-175
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(512) k_coder_cta(EngineDev P, int l) {
     B[L.spike_prev + i] = spike[i];
     if (has_next) {  // next layer's input (neo/Agent.cpp:147-151)
       if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + i * 3 + 0];
-      B[P.layers[l + 1].vis_input + i] = st;
+      B[next_vis_input + i] = st;
     }
   }
 }

@@ -61,10 +61,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __host__ __device__ inline int column_slab_floats(int max_rec, int max_s) { return max_rec + max_s; }
 
 template <int LPC>
-__global__ void __launch_bounds__(BIDI_COL_WARPS * 32) k_columns(EngineDev P, int l) {
+__global__ void __launch_bounds__(BIDI_COL_WARPS * 32) k_columns(EngineDev P, LayerDev L, int l, long long up_a_expl, long long up_p_state) {
   extern __shared__ __align__(128) float smem[];
   constexpr int CPW = 32 / LPC;  // columns per warp
-  const LayerDev& L = P.layers[l];
   const ColumnsDev& C = L.col;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane / LPC, r = lane % LPC, lane0 = sub * LPC;
@@ -111,15 +110,14 @@ __global__ void __launch_bounds__(BIDI_COL_WARPS * 32) k_columns(EngineDev P, in
   // ---- gather the column's inputs while the copy is in flight (neo/Agent.cpp:159-169, :217-220)
   const bool input_layer = l == P.L;
   if (active) {
-    const LayerDev& Up = P.layers[input_layer ? 0 : (l == P.L - 1 ? l : l + 1)];
     const int ux = node % L.fb.uw, uy = node / L.fb.uw;
     int nfb = 0;
     if (L.fb.r >= 0 && (input_layer || l < P.L - 1)) {
       const SlotBox b = slot_box(L.fb, ux, uy);
       const int ny = b.sy1 - b.sy0 + 1;
       nfb = slot_count(L.fb, b);
-      const float* up_sig = B + Up.col.a_expl;
-      const float* up_state = B + Up.p_state;
+      const float* up_sig = B + up_a_expl;
+      const float* up_state = B + up_p_state;
       for (int k = r; k < nfb; k += LPC) {
         const int sx = b.sx0 + k / ny, sy = b.sy0 + k % ny;
         const int t = slot_tx(L.fb, b, sx) + slot_ty(L.fb, b, sy) * L.fb.tw;

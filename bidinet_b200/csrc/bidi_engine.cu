@@ -351,8 +351,10 @@ void record_columns(Recorder& R, int l) {
   const long long warps = (long long)h->A * ((C.n + cpw - 1) / cpw);
   const size_t smem = columns_smem_bytes(C);
   R.before("columns");
-  if (cpw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, l);
-  else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, l);
+  const int L = h->L;
+  const LayerDev& Up = h->layers[l == L ? 0 : (l == L - 1 ? l : l + 1)];
+  if (cpw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l, Up.col.a_expl, Up.p_state);
+  else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l, Up.col.a_expl, Up.p_state);
   R.after("columns");
   R.kernels++;
 }
@@ -366,20 +368,20 @@ void record_step(Recorder& R, bool learn) {
   if (V == BIDI_KWINNERS) {
     // sdr/PredictiveRSDR.cpp:102-112
     for (int l = 0; l < L; l++) {
-      R.launch("kw_activate", bidi::k_kw_activate, A * ly[l].nh, l);
-      R.launch("kw_inhibit", bidi::k_kw_inhibit, A * ly[l].nh, l, ly[l].act, ly[l].state, l < L - 1 ? ly[l + 1].vis_input : -1LL);
-      R.launch("reconstruct", bidi::k_reconstruct, A * (ly[l].nv + ly[l].nh), l, ly[l].state, 0, 0.0f, 0);
+      R.launch("kw_activate", bidi::k_kw_activate, A * ly[l].nh, ly[l], l);
+      R.launch("kw_inhibit", bidi::k_kw_inhibit, A * ly[l].nh, ly[l], l, ly[l].act, ly[l].state, l < L - 1 ? ly[l + 1].vis_input : -1LL);
+      R.launch("reconstruct", bidi::k_reconstruct, A * (ly[l].nv + ly[l].nh), ly[l], l, ly[l].state, 0, 0.0f, 0);
     }
     // :115-171
     for (int l = L - 1; l >= 0; l--) {
-      R.launch("predict", bidi::k_predict, A * ly[l].pn, l, (int)learn);
-      R.launch("kw_inhibit", bidi::k_kw_inhibit, A * ly[l].nh, l, ly[l].p_act, ly[l].p_state, -1LL);
+      R.launch("predict", bidi::k_predict, A * ly[l].pn, ly[l], l, (int)learn, ly[l < L - 1 ? l + 1 : l].p_state, ly[l < L - 1 ? l + 1 : l].p_state_prev);
+      R.launch("kw_inhibit", bidi::k_kw_inhibit, A * ly[l].nh, ly[l], l, ly[l].p_act, ly[l].p_state, -1LL);
     }
     // :173-185
-    if (learn) for (int l = 0; l < L; l++) R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, l);
+    if (learn) for (int l = 0; l < L; l++) R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, ly[l], l);
     R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
     // :188-193
-    R.launch("kw_predict_input", bidi::k_kw_predict_input, A * h->n_in);
+    R.launch("kw_predict_input", bidi::k_kw_predict_input, A * h->n_in, ly[0]);
     return;
   }
   for (int l = 0; l < L; l++) {
@@ -388,8 +390,8 @@ void record_step(Recorder& R, bool learn) {
       const int threads = std::min(512, std::max(64, (ly[l].nv + ly[l].nh + 31) / 32 * 32));
       const size_t smem = sizeof(float) * (size_t)bidi::coder_cta_smem_floats(ly[l]);
       R.before("coder");
-      if (V == BIDI_ITERATIVE) bidi::k_coder_cta<0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, l);
-      else bidi::k_coder_cta<1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, l);
+      if (V == BIDI_ITERATIVE) bidi::k_coder_cta<0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, l < L - 1 ? ly[l + 1].vis_input : -1LL);
+      else bidi::k_coder_cta<1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, l < L - 1 ? ly[l + 1].vis_input : -1LL);
       R.after("coder");
       R.kernels++;
       continue;
@@ -397,37 +399,37 @@ void record_step(Recorder& R, bool learn) {
     if (V == BIDI_ITERATIVE) { // sdr/IRSDR.cpp:125-216
       const int settle = ly[l].iter_settle, measure = ly[l].iter_measure;
       for (int it = 0; it < settle; it++) {
-        R.launch("ic_sweep", bidi::k_ic_sweep, nh, l, (int)(it == 0), 0, 0.0f);
-        R.launch("reconstruct", bidi::k_reconstruct, nvh, l, ly[l].spike, 0, 0.0f, 1);
+        R.launch("ic_sweep", bidi::k_ic_sweep, nh, ly[l], l, (int)(it == 0), 0, 0.0f);
+        R.launch("reconstruct", bidi::k_reconstruct, nvh, ly[l], l, ly[l].spike, 0, 0.0f, 1);
       }
       const float inv = 1.0f / measure;
       for (int it = 0; it < measure; it++) {
-        R.launch("ic_sweep", bidi::k_ic_sweep, nh, l, (int)(settle == 0 && it == 0), 1, inv);
-        R.launch("reconstruct", bidi::k_reconstruct, nvh, l, ly[l].spike, 0, 0.0f, 1);
+        R.launch("ic_sweep", bidi::k_ic_sweep, nh, ly[l], l, (int)(settle == 0 && it == 0), 1, inv);
+        R.launch("reconstruct", bidi::k_reconstruct, nvh, ly[l], l, ly[l].spike, 0, 0.0f, 1);
       }
-      R.launch("reconstruct", bidi::k_reconstruct, nvh, l, ly[l].state, 0, 0.0f, 0);
-      if (l < L - 1) R.launch("ic_finish", bidi::k_ic_finish, nh, l, 0, 0.0f);
+      R.launch("reconstruct", bidi::k_reconstruct, nvh, ly[l], l, ly[l].state, 0, 0.0f, 0);
+      if (l < L - 1) R.launch("ic_finish", bidi::k_ic_finish, nh, ly[l], l, 0, 0.0f, ly[l + 1].vis_input);
     } else { // neo/SparseCoder.cpp:116-176
       const int iter = ly[l].iter_settle;
       float counter = 0.0f;
       for (int it = 0; it < iter; it++) {
-        R.launch("ic_sweep", bidi::k_ic_sweep, nh, l, (int)(it == 0), 2, 0.0f);
+        R.launch("ic_sweep", bidi::k_ic_sweep, nh, ly[l], l, (int)(it == 0), 2, 0.0f);
         counter += 1.0f;
-        R.launch("reconstruct", bidi::k_reconstruct, nvh, l, ly[l].state, 1, 1.0f / counter, 1);
+        R.launch("reconstruct", bidi::k_reconstruct, nvh, ly[l], l, ly[l].state, 1, 1.0f / counter, 1);
       }
-      R.launch("ic_finish", bidi::k_ic_finish, nh, l, 1, 1.0f / counter);
+      R.launch("ic_finish", bidi::k_ic_finish, nh, ly[l], l, 1, 1.0f / counter, l < L - 1 ? ly[l + 1].vis_input : -1LL);
     }
   }
   for (int l = L - 1; l >= 0; l--) {
     if (V == BIDI_NEO_AGENT) record_columns(R, l);
-    R.launch("predict", bidi::k_predict, A * ly[l].pn, l, (int)learn);
+    R.launch("predict", bidi::k_predict, A * ly[l].pn, ly[l], l, (int)learn, ly[l < L - 1 ? l + 1 : l].p_state, ly[l < L - 1 ? l + 1 : l].p_state_prev);
   }
   if (V == BIDI_NEO_AGENT) record_columns(R, L);
-  R.launch("predict_input", bidi::k_predict_input, A * h->n_in, (int)learn);
+  R.launch("predict_input", bidi::k_predict_input, A * h->n_in, ly[L], (int)learn, ly[0].p_state, ly[0].p_state_prev);
   if (learn)
     for (int l = 0; l < L; l++) {
-      if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, l);
-      else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, l);
+      if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
+      else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
     }
   R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
 }

@@ -99,8 +99,7 @@ __device__ __forceinline__ float gather_recon(const WinDev& w, const float* __re
 
 // ------------------------------------------------------------------ k-winners coder
 // sdr/RSDR.cpp:123-133: a = -theta + sum_ff x*w + sum_rec sPrev*w
-__global__ void k_kw_activate(EngineDev P, int l) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_kw_activate(EngineDev P, LayerDev L, int l) {
   BIDI_THREAD_AGENT_UNIT(L.nh)
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
@@ -117,8 +116,7 @@ __global__ void k_kw_activate(EngineDev P, int l) {
 // sdr/RSDR.cpp:135-145 and :148-163: rank among the lateral neighbours.  `src`
 // and `dst` are blob offsets; dst_next (>=0) also receives the state as the next
 // layer's visible input (sdr/PredictiveRSDR.cpp:108-111).
-__global__ void k_kw_inhibit(EngineDev P, int l, long long src, long long dst, long long dst_next) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_kw_inhibit(EngineDev P, LayerDev L, int l, long long src, long long dst, long long dst_next) {
   BIDI_THREAD_AGENT_UNIT(L.nh)
   float* B = blob_of(P, a);
   const float* act = B + src;
@@ -137,8 +135,7 @@ __global__ void k_kw_inhibit(EngineDev P, int l, long long src, long long dst, l
 // neo/SparseCoder.cpp:242-259 (scaled: drive*multiplier).  Threads [0,nv) own a
 // visible cell, [nv,nv+nh) a hidden unit.  copy_spike: also spikePrev = spike
 // (sdr/IRSDR.cpp:170-171), race-free here because this kernel never reads spikePrev.
-__global__ void k_reconstruct(EngineDev P, int l, long long drive_off, int scaled, float mult, int copy_spike) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_reconstruct(EngineDev P, LayerDev L, int l, long long drive_off, int scaled, float mult, int copy_spike) {
   BIDI_THREAD_AGENT_UNIT(L.nv + L.nh)
   float* B = blob_of(P, a);
   const float* drive = B + drive_off;
@@ -153,16 +150,14 @@ __global__ void k_reconstruct(EngineDev P, int l, long long drive_off, int scale
 
 // sdr/RSDR.cpp:196-212 applied to layer 0's predicted states -> _prediction
 // (sdr/PredictiveRSDR.cpp:188-193)
-__global__ void k_kw_predict_input(EngineDev P) {
-  const LayerDev& L = P.layers[0];
+__global__ void k_kw_predict_input(EngineDev P, LayerDev L) {
   BIDI_THREAD_AGENT_UNIT(L.nv)
   float* B = blob_of(P, a);
   P.pred_out[(long long)a * P.n_in + i] = gather_recon(L.ff, B + L.ff.w_off, B + L.p_state, i % L.vw, i / L.vw, false, 0.0f);
 }
 
 // sdr/RSDR.cpp:241-266: winners only; theta for every unit
-__global__ void k_kw_learn(EngineDev P, int l) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_kw_learn(EngineDev P, LayerDev L, int l) {
   BIDI_THREAD_AGENT_UNIT(L.nh)
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
@@ -187,8 +182,7 @@ __global__ void k_kw_learn(EngineDev P, int l) {
 // neo/SparseCoder.cpp:129-158.  first: activation and state start from 0
 // (sdr/IRSDR.cpp:131-135).  acc: 0 = settle (no state change), 1 = state +=
 // scale*spike (measure; scale = 1/measureIter), 2 = state += spike (neo).
-__global__ void k_ic_sweep(EngineDev P, int l, int first, int acc, float scale) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale) {
   BIDI_THREAD_AGENT_UNIT(L.nh)
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
@@ -220,16 +214,14 @@ __global__ void k_ic_sweep(EngineDev P, int l, int first, int acc, float scale) 
 // End of the up pass of one layer: neo: state *= 1/counter (neo/SparseCoder.cpp:171-175);
 // then the next layer's input = state (x the column's _attention action for
 // neo::Agent, neo/Agent.cpp:147-151).
-__global__ void k_ic_finish(EngineDev P, int l, int scale_state, float mult) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_ic_finish(EngineDev P, LayerDev L, int l, int scale_state, float mult, long long next_vis_input) {
   BIDI_THREAD_AGENT_UNIT(L.nh)
   float* B = blob_of(P, a);
   float st = B[L.state + i];
   if (scale_state) { st *= mult; B[L.state + i] = st; }
-  if (l < P.L - 1) {
-    const LayerDev& N = P.layers[l + 1];
+  if (next_vis_input >= 0) {
     if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + i * 3 + 0];
-    B[N.vis_input + i] = st;
+    B[next_vis_input + i] = st;
   }
 }
 
@@ -247,8 +239,7 @@ __device__ __forceinline__ void ic_learn_tail(const LayerDev& L, float* B, int i
 }
 
 // sdr/IRSDR.cpp:287-319 (Hebbian, clamped delta)
-__global__ void k_ic_learn(EngineDev P, int l) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_ic_learn(EngineDev P, LayerDev L, int l) {
   BIDI_THREAD_AGENT_UNIT(L.nh)
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
@@ -274,8 +265,7 @@ __global__ void k_ic_learn(EngineDev P, int l) {
 
 // neo/Agent.cpp:252-265 (reward from the prediction error) followed by
 // neo/SparseCoder.cpp:326-361 (reward-modulated update through eligibility traces)
-__global__ void k_neo_learn(EngineDev P, int l) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_neo_learn(EngineDev P, LayerDev L, int l) {
   BIDI_THREAD_AGENT_UNIT(L.nh)
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
@@ -313,14 +303,12 @@ __global__ void k_neo_learn(EngineDev P, int l) {
 // sdr/IPredictiveRSDR.cpp:156-194, neo/PredictiveHierarchy.cpp:151-181,
 // neo/Agent.cpp:177-208.  The delta rule runs BEFORE the activation that uses the
 // weights.
-__global__ void k_predict(EngineDev P, int l, int learn) {
-  const LayerDev& L = P.layers[l];
+__global__ void k_predict(EngineDev P, LayerDev L, int l, int learn, long long up_p_state, long long up_p_state_prev) {
   BIDI_THREAD_AGENT_UNIT(L.pn)
   float* B = blob_of(P, a);
   const bool top = l == P.L - 1;
-  const LayerDev& Up = P.layers[top ? l : l + 1];
-  const float* up_state = B + Up.p_state;
-  const float* up_prev = B + Up.p_state_prev;
+  const float* up_state = B + up_p_state;
+  const float* up_prev = B + up_p_state_prev;
   const float* state = B + L.state;
   const float* sprev = B + L.state_prev;
   float* wfb = B + L.fb.w_off;
@@ -350,13 +338,11 @@ __global__ void k_predict(EngineDev P, int l, int learn) {
 }
 
 // Input prediction nodes: sdr/IPredictiveRSDR.cpp:198-218, neo/Agent.cpp:232-246
-__global__ void k_predict_input(EngineDev P, int learn) {
-  const LayerDev& L = P.layers[P.L];
+__global__ void k_predict_input(EngineDev P, LayerDev L, int learn, long long p0_state, long long p0_state_prev) {
   BIDI_THREAD_AGENT_UNIT(L.pn)
   float* B = blob_of(P, a);
-  const LayerDev& L0 = P.layers[0];
-  const float* p0 = B + L0.p_state;
-  const float* p0_prev = B + L0.p_state_prev;
+  const float* p0 = B + p0_state;
+  const float* p0_prev = B + p0_state_prev;
   float* wfb = B + L.fb.w_off;
   const int ux = i % L.fb.uw, uy = i / L.fb.uw, U = L.pn;
   if (learn) {
