@@ -388,7 +388,7 @@ void record_step(Recorder& R, bool learn) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
     if (h->coder_cta[l] && !h->force_phase_kernels) { // whole up pass of the layer in one launch
       const int threads = std::min(512, std::max(64, (ly[l].nv + ly[l].nh + 31) / 32 * 32));
-      const size_t smem = sizeof(float) * (size_t)bidi::coder_cta_smem_floats(ly[l]);
+      const size_t smem = sizeof(float) * (size_t)bidi::coder_cta_shape(ly[l]).floats;
       R.before("coder");
       if (V == BIDI_ITERATIVE) bidi::k_coder_cta<0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, l < L - 1 ? ly[l + 1].vis_input : -1LL);
       else bidi::k_coder_cta<1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, l < L - 1 ? ly[l + 1].vis_input : -1LL);
@@ -724,7 +724,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   if (V != BIDI_KWINNERS) {
     size_t smem = 0;
     for (int l = 0; l < L; l++) {
-      const size_t need = sizeof(float) * (size_t)bidi::coder_cta_smem_floats(h->layers[l]);
+      const size_t need = sizeof(float) * (size_t)bidi::coder_cta_shape(h->layers[l]).floats;
       if (need <= 200 * 1024) { h->coder_cta[l] = 1; smem = std::max(smem, need); }
     }
     if (smem > 0) {
