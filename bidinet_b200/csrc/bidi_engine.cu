@@ -28,29 +28,32 @@ struct WinHost {
 };
 
 struct ColumnsHost {
-  std::vector<int> in_off, rec_off, stride;
+  std::vector<int> in_off, rec_off, stride, in_src;
 };
 
-// Pointers to the sections of one column record inside a host blob image
-// (layout: bidi_types.h, ColumnsDev).
+// Pointers to the sections of one column inside a host blob image.  Columns are
+// stored in PAIRS (nodes 2p, 2p+1) with every element interleaved [..][2]
+// (layout: bidi_types.h, ColumnsDev), so element k of a section is ptr[2*k].
 struct ColRec {
   float *W, *latT, *thr, *q_w, *q_tr, *a_w, *a_tr, *sprev, *err, *scal;
   int S, Cq, nin;
 };
 ColRec col_rec(const ColumnsDev& C, const ColumnsHost& H, float* blob, int node) {
   ColRec r;
-  r.S = H.stride[node]; r.Cq = C.cq; r.nin = H.in_off[node + 1] - H.in_off[node];
-  r.W = blob + C.rec_base + H.rec_off[node];
-  r.latT = r.W + (long long)C.cells * r.S;
-  r.thr = r.latT + C.cells * C.cq;
-  r.q_w = r.thr + C.cq; r.q_tr = r.q_w + C.cq; r.a_w = r.q_tr + C.cq; r.a_tr = r.a_w + 3 * C.cq;
-  r.sprev = r.a_tr + 3 * C.cq; r.err = r.sprev + C.cq; r.scal = r.err + r.S;
+  const int pair = node >> 1, half = node & 1;
+  r.S = H.stride[pair]; r.Cq = C.cq; r.nin = H.in_off[node + 1] - H.in_off[node];
+  r.W = blob + C.rec_base + H.rec_off[pair] + half;
+  r.latT = r.W + 2LL * C.cells * r.S;
+  r.thr = r.latT + 2 * C.cells * C.cq;
+  r.q_w = r.thr + 2 * C.cq; r.q_tr = r.q_w + 2 * C.cq; r.a_w = r.q_tr + 2 * C.cq; r.a_tr = r.a_w + 6 * C.cq;
+  r.sprev = r.a_tr + 6 * C.cq; r.err = r.sprev + 2 * C.cq; r.scal = r.err + 2 * r.S;
   return r;
 }
-// row stride of a column's weights: nIn rounded up to a multiple of 4 with stride/4 odd
-int column_stride(int nin) {
-  int s = std::max(4, (nin + 3) / 4 * 4);
-  if (((s / 4) & 1) == 0) s += 4;
+// common row stride of a column pair: >= nIn of both, even, with stride/2 odd so that
+// lane i's 128-bit shared-memory loads of row i (2*stride floats apart) never conflict
+int column_pair_stride(int nin) {
+  int s = std::max(2, (nin + 1) / 2 * 2);
+  if (((s / 2) & 1) == 0) s += 2;
   return s;
 }
 
@@ -299,15 +302,15 @@ template <class F> void walk_column(const bidi_engine* h, int which, int layer, 
   for (int node = 0; node < C.n; node++) {
     const ColRec r = col_rec(C, H, blob, node);
     switch (which) {
-      case BIDI_COL_RECON_ERR: for (int j = 0; j < r.nin; j++) f(r.err[j]); break;
-      case BIDI_COL_FF_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < r.nin; j++) f(r.W[(long long)i * r.S + j]); break;
-      case BIDI_COL_LAT_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < C.cells; j++) f(r.latT[j * r.Cq + i]); break;
-      case BIDI_COL_THRESHOLD: for (int i = 0; i < C.cells; i++) f(r.thr[i]); break;
-      case BIDI_COL_SPIKE_PREV: for (int i = 0; i < C.cells; i++) f(r.sprev[i]); break;
-      case BIDI_COL_Q_W: for (int i = 0; i < C.cells; i++) f(r.q_w[i]); break;
-      case BIDI_COL_Q_TRACE: for (int i = 0; i < C.cells; i++) f(r.q_tr[i]); break;
-      case BIDI_COL_ACT_W: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_w[a * r.Cq + i]); break;
-      case BIDI_COL_ACT_TRACE: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_tr[a * r.Cq + i]); break;
+      case BIDI_COL_RECON_ERR: for (int j = 0; j < r.nin; j++) f(r.err[2 * j]); break;
+      case BIDI_COL_FF_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < r.nin; j++) f(r.W[2 * ((long long)i * r.S + j)]); break;
+      case BIDI_COL_LAT_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < C.cells; j++) f(r.latT[2 * (j * r.Cq + i)]); break;
+      case BIDI_COL_THRESHOLD: for (int i = 0; i < C.cells; i++) f(r.thr[2 * i]); break;
+      case BIDI_COL_SPIKE_PREV: for (int i = 0; i < C.cells; i++) f(r.sprev[2 * i]); break;
+      case BIDI_COL_Q_W: for (int i = 0; i < C.cells; i++) f(r.q_w[2 * i]); break;
+      case BIDI_COL_Q_TRACE: for (int i = 0; i < C.cells; i++) f(r.q_tr[2 * i]); break;
+      case BIDI_COL_ACT_W: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_w[2 * (a * r.Cq + i)]); break;
+      case BIDI_COL_ACT_TRACE: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_tr[2 * (a * r.Cq + i)]); break;
       case BIDI_COL_PREV_VALUE: f(r.scal[0]); break;
     }
   }
@@ -340,21 +343,31 @@ struct Recorder {
   }
 };
 
+// One column pair per warp: shared memory, not warps, limits how many pairs an SM holds
+// (the pair record is ~18-22 KB), so giving every pair a whole warp doubles the warps
+// that hide each other's latency at no shared-memory cost; lanes 16..31 idle only
+// during the 16-cell sweep and share the reconstruction and learning loops.
+int columns_pairs_per_warp(const ColumnsDev& C) {
+#ifdef BIDI_COL_PPW2
+  return C.cells <= 16 ? 2 : 1;
+#else
+  return 1;
+#endif
+}
 size_t columns_smem_bytes(const ColumnsDev& C) {
-  const int cpw = C.cells <= 16 ? 2 : 1;
-  return sizeof(float) * BIDI_COL_WARPS * cpw * (size_t)bidi::column_slab_floats(C.max_rec, C.max_s) + 8 * BIDI_COL_WARPS;
+  const int ppw = columns_pairs_per_warp(C);
+  return sizeof(float) * BIDI_COL_WARPS * ppw * (size_t)bidi::column_slab_floats(C) + 8 * BIDI_COL_WARPS;
 }
 void record_columns(Recorder& R, int l) {
   bidi_engine* h = R.h;
   const ColumnsDev& C = h->layers[l].col;
-  const int cpw = C.cells <= 16 ? 2 : 1;
-  const long long warps = (long long)h->A * ((C.n + cpw - 1) / cpw);
+  const int ppw = columns_pairs_per_warp(C);
+  const int n_pairs = (C.n + 1) / 2;
+  const long long warps = (long long)h->A * ((n_pairs + ppw - 1) / ppw);
   const size_t smem = columns_smem_bytes(C);
   R.before("columns");
-  const int L = h->L;
-  const LayerDev& Up = h->layers[l == L ? 0 : (l == L - 1 ? l : l + 1)];
-  if (cpw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l, Up.col.a_expl, Up.p_state);
-  else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l, Up.col.a_expl, Up.p_state);
+  if (ppw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   R.after("columns");
   R.kernels++;
 }
@@ -596,8 +609,9 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       }
       // nIn = |pred| + 2|fb|  (neo/Agent.cpp:90,137)
       H.col.in_off.assign(C.n + 1, 0);
-      H.col.rec_off.assign(C.n + 1, 0);
-      H.col.stride.assign(C.n, 0);
+      const int n_pairs = (C.n + 1) / 2;
+      H.col.rec_off.assign(n_pairs + 1, 0);
+      H.col.stride.assign(n_pairs, 0);
       C.cq = (C.cells + 3) / 4 * 4;
       C.max_in = C.max_s = C.max_rec = 0;
       for (int i = 0; i < C.n; i++) {
@@ -606,22 +620,49 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
         for_each_conn_host(H.fb, ux, uy, [&](int, int) { nfb++; });
         for_each_conn_host(H.pred, ux, uy, [&](int, int) { npr++; });
         const int nin = npr + 2 * nfb;
-        const int S = column_stride(nin);
-        const int rec = C.cells * S + C.cells * C.cq + 10 * C.cq + S + 4;
         H.col.in_off[i + 1] = H.col.in_off[i] + nin;
-        H.col.rec_off[i + 1] = H.col.rec_off[i] + rec;
-        H.col.stride[i] = S;
-        C.max_in = std::max(C.max_in, nin); C.max_s = std::max(C.max_s, S); C.max_rec = std::max(C.max_rec, rec);
+        C.max_in = std::max(C.max_in, nin);
+      }
+      for (int p = 0; p < n_pairs; p++) {
+        const int na = H.col.in_off[2 * p + 1] - H.col.in_off[2 * p];
+        const int nb = 2 * p + 1 < C.n ? H.col.in_off[2 * p + 2] - H.col.in_off[2 * p + 1] : 0;
+        const int S = column_pair_stride(std::max(na, nb));
+        const int rec = 2 * (C.cells * S + C.cells * C.cq + 10 * C.cq + S + 4);
+        H.col.rec_off[p + 1] = H.col.rec_off[p] + rec;
+        H.col.stride[p] = S;
+        C.max_s = std::max(C.max_s, S); C.max_rec = std::max(C.max_rec, rec);
       }
       C.tot_in = H.col.in_off[C.n];
       const long long nc = (long long)C.n * C.cells;
-      C.rec_base = al.take(H.col.rec_off[C.n]);
+      C.rec_base = al.take(H.col.rec_off[n_pairs]);
       C.inputs = al.take(C.tot_in);
       C.act = al.take(nc); C.spike = al.take(nc); C.state = al.take(nc);
       C.a_state = al.take(C.n * 3LL); C.a_expl = al.take(C.n * 3LL);
     }
   }
   h->stride = al.top;
+  if (V == BIDI_NEO_AGENT) {
+    if (h->stride >= (1LL << 31)) { delete h; return fail(nullptr, BIDI_EINVAL, "bidi_create: agent state too large for 32-bit gather offsets"); }
+    // where every column input comes from: per feedback connection the upper column's
+    // _signal action and the upper node's state, then the coder state per predictive
+    // connection (neo/Agent.cpp:159-169; input nodes: :217-220)
+    for (int l = 0; l <= L; l++) {
+      LayerHost& H = h->hl[l];
+      const LayerDev& D = h->layers[l];
+      const bool input_layer = l == L;
+      const LayerDev& Up = h->layers[input_layer ? 0 : (l == L - 1 ? l : l + 1)];
+      H.col.in_src.clear();
+      for (int i = 0; i < D.col.n; i++) {
+        const int ux = i % H.fb.d.uw, uy = i / H.fb.d.uw;
+        if (input_layer || l < L - 1)
+          for_each_conn_host(H.fb, ux, uy, [&](int, int t) {
+            H.col.in_src.push_back((int)(Up.col.a_expl + t * 3 + 2));
+            H.col.in_src.push_back((int)(Up.p_state + t));
+          });
+        if (!input_layer) for_each_conn_host(H.pred, ux, uy, [&](int, int t) { H.col.in_src.push_back((int)(D.state + t)); });
+      }
+    }
+  }
   if (V == BIDI_NEO_AGENT) { // visit order: layers top -> bottom, then the input nodes
     int base = 0;
     for (int l = L - 1; l >= 0; l--) { h->layers[l].col.noise_base = base; base += h->layers[l].col.n; }
@@ -682,6 +723,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       push(H.col.in_off, &h->layers[l].col.in_off);
       push(H.col.rec_off, &h->layers[l].col.rec_off);
       push(H.col.stride, &h->layers[l].col.stride);
+      push(H.col.in_src, &h->layers[l].col.in_src);
     }
   }
   CU_CREATE(cudaMalloc(&h->d_tables, sizeof(int) * pool.size()));
@@ -701,6 +743,10 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   P.blob = h->d_blob; P.stride = h->stride; P.in0 = h->d_in0; P.pred_out = h->d_pred;
   P.rewards = h->d_rewards; P.noise_u = h->d_noise_u; P.noise_v = h->d_noise_v; P.col_actions = h->d_col_actions;
   P.ncol = h->ncol; P.layers = h->d_layers;
+  {  // constants the packed-pair arithmetic must not see at compile time (bidi_columns.cuh)
+    const float one[2] = {1.0f, 1.0f}, negzero[2] = {-0.0f, -0.0f}, negone[2] = {-1.0f, -1.0f};
+    memcpy(&P.k_one2, one, 8); memcpy(&P.k_negzero2, negzero, 8); memcpy(&P.k_negone2, negone, 8);
+  }
   CU_CREATE(cudaStreamSynchronize(h->stream));
 
   // thresholds start at init_threshold (sdr/RSDR.cpp:43, neo/Column.cpp:27); everything else at 0
@@ -712,7 +758,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       if (V == BIDI_NEO_AGENT)
         for (int node = 0; node < D.col.n; node++) {
           const ColRec r = col_rec(D.col, h->hl[l].col, img.data(), node);
-          for (int i = 0; i < D.col.cells; i++) r.thr[i] = cfg->init_threshold;
+          for (int i = 0; i < D.col.cells; i++) r.thr[2 * i] = cfg->init_threshold;
         }
     }
     for (int a = 0; a < n_agents; a++)
@@ -853,13 +899,13 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
     auto draw_column = [&](const ColumnsDev& C, const ColumnsHost& CH, int node) { // neo/Column.cpp:22-43
       const ColRec r = col_rec(C, CH, img.data(), node);
       for (int i = 0; i < C.cells; i++) {
-        r.thr[i] = g.init_threshold;
-        for (int j = 0; j < r.nin; j++) r.W[(long long)i * r.S + j] = weightDist(gen);
-        for (int j = 0; j < C.cells; j++) r.latT[j * r.Cq + i] = inhibitionDist(gen);
-        r.q_w[i] = weightDist(gen);
+        r.thr[2 * i] = g.init_threshold;
+        for (int j = 0; j < r.nin; j++) r.W[2 * ((long long)i * r.S + j)] = weightDist(gen);
+        for (int j = 0; j < C.cells; j++) r.latT[2 * (j * r.Cq + i)] = inhibitionDist(gen);
+        r.q_w[2 * i] = weightDist(gen);
       }
       for (int a = 0; a < 3; a++)
-        for (int k = 0; k < C.cells; k++) r.a_w[a * r.Cq + k] = weightDist(gen);
+        for (int k = 0; k < C.cells; k++) r.a_w[2 * (a * r.Cq + k)] = weightDist(gen);
     };
     for (int l = 0; l <= L; l++) {
       if (l == L && V == BIDI_KWINNERS) break;
@@ -1063,6 +1109,14 @@ int bidi_timer_stop_ms(bidi_engine* h, float* ms) {
   CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
   return BIDI_OK;
 }
+
+#ifdef BIDI_COL_TIMING
+int bidi_debug_col_timing(unsigned long long* out16, int reset) {
+  if (out16) cudaMemcpyFromSymbol(out16, bidi::g_col_timing, sizeof(unsigned long long) * 16);
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(bidi::g_col_timing, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 /* sizeof the two POD structs, so a binding can check its mirror of the header */
 int bidi_abi_sizes(int* config_bytes, int* layer_desc_bytes) {

@@ -44,26 +44,31 @@ struct WinDev {
   long long tr_off;  // eligibility traces, same shape, -1 if none
 };
 
-// The columns (neo::Column) of one node layer.  Everything a column reads AND
-// writes each step lives in one contiguous, 16-byte aligned "record" so that one
-// TMA bulk copy brings it into shared memory and one takes it back:
-//   W[cells][S]      feed-forward weights, row stride S = nIn padded to a multiple
-//                    of 4 with S/4 odd (conflict-free 128-bit shared loads when
-//                    lane i walks row i); pad entries are 0
-//   latT[cells][Cq]  lateral weights TRANSPOSED (latT[k][i] = lat[i][k]), Cq = cells
-//                    rounded up to 4
-//   10 vectors [Cq]  threshold, q w, q trace, 3 action w, 3 action traces, spikePrev
-//   err[S]           _reconstructionError
-//   scal[4]          prevValue, pad
+// The columns (neo::Column) of one node layer.  Columns are stored in PAIRS (nodes
+// 2p and 2p+1): everything the two columns read AND write each step lives in one
+// contiguous, 16-byte aligned "pair record" with every element interleaved [..][2]
+// (x = column 2p, y = column 2p+1), so that one TMA bulk copy brings the pair into
+// shared memory, one takes it back, and a lane works on both columns at once with
+// packed f32x2 arithmetic:
+//   W2[cells][S][2]     feed-forward weights, common row stride S >= both nIn, S even
+//                       with S/2 odd (conflict-free 128-bit shared loads when lane i
+//                       walks row i); pad entries are 0
+//   latT2[cells][Cq][2] lateral weights TRANSPOSED (latT[k][i] = lat[i][k]), Cq = cells
+//                       rounded up to 4
+//   10 vectors [Cq][2]  threshold, q w, q trace, 3 action w, 3 action traces, spikePrev
+//   err2[S][2]          _reconstructionError
+//   scal2[4][2]         prevValue, pad
+// A layer with an odd number of nodes ends with a phantom column of zeros.
 // Write-only per-step outputs (inputs, activation, spike, state, action states) stay
 // in plain planes.
 struct ColumnsDev {
   int n, cells, cq, tot_in; // nodes, cells per column, cells rounded up to 4, sum of nIn
   int max_in;               // largest nIn
-  int max_s, max_rec;       // largest padded stride / record length (floats)
+  int max_s, max_rec;       // largest pair stride / pair record length (floats)
   const int* in_off;        // [n+1] prefix sums of nIn (same for every agent)
-  const int* rec_off;       // [n+1] record offsets (floats) relative to rec_base
-  const int* stride;        // [n] S
+  const int* in_src;        // [tot_in] blob offset each column input is gathered from (neo/Agent.cpp:159-169)
+  const int* rec_off;       // [n_pairs+1] pair record offsets (floats) relative to rec_base
+  const int* stride;        // [n_pairs] S
   long long rec_base;       // blob offset of the first record
   long long inputs, act, spike, state, a_state, a_expl; // planes
   int noise_base;           // first column index of this layer in the visit order (x3 for the noise arrays)
@@ -104,6 +109,9 @@ struct EngineDev {
   float* col_actions;     // [A][ncol*3] exploratory actions in visit order (getAction)
   int ncol;
   const LayerDev* layers; // device array [L+1]
+  // {1,1}, {-0,-0}, {-1,-1} as packed f32x2 bit patterns.  Passed at run time so that
+  // ptxas cannot fold fma(a,b,-0) / fma(a,1,c) back into a fused multiply-add.
+  unsigned long long k_one2, k_negzero2, k_negone2;
 };
 
 #endif
