@@ -17,6 +17,7 @@
 
 #include "bidi_kernels.cuh"
 #include "bidi_coder.cuh"
+#include "bidi_tiles.cuh"
 
 namespace {
 
@@ -72,6 +73,7 @@ struct bidi_engine {
   std::vector<LayerHost> hl;
   long long stride = 0;            // floats per agent blob
   std::vector<int> coder_cta;      // per layer: the fused one-CTA-per-agent coder kernel applies
+  std::vector<int> tiled;          // per node layer: few threads, use the cooperative tile kernels (bidi_tiles.cuh)
   bool force_phase_kernels = false;
   EngineDev P;                     // kernel argument
   // device memory
@@ -142,6 +144,10 @@ void build_win(WinHost& w, int uw, int uh, int tw, int th, int r, bool identity,
   };
   ranges(w.cx, tw, w.gxlo, w.gxhi);
   ranges(w.cy, th, w.gylo, w.gyhi);
+  int mx = 0, my = 0;
+  for (int t = 0; t < tw; t++) mx = std::max(mx, w.gxhi[t] - w.gxlo[t] + 1);
+  for (int t = 0; t < th; t++) my = std::max(my, w.gyhi[t] - w.gylo[t] + 1);
+  d.max_cand = mx * my;
 }
 
 // Host twin of bidi::for_each_conn: f(slot, target) in the reference's list order.
@@ -337,7 +343,14 @@ struct Recorder {
   }
   template <class K, class... Args> void launch(const char* name, K kernel, long long threads, Args... args) {
     before(name);
-    kernel<<<grid_for(threads, kBlock), kBlock, 0, h->stream>>>(h->P, args...);
+    // few threads (one large single agent): one warp per block, so the warps spread over
+    // all SMs and each gets a whole SM's load/store path to hide its latency with
+#ifdef BIDI_SMALL_BLOCKS
+    const int block = threads < 148LL * 2 * kBlock ? 32 : kBlock;
+#else
+    const int block = kBlock;
+#endif
+    kernel<<<grid_for(threads, block), block, 0, h->stream>>>(h->P, args...);
     after(name);
     kernels++;
   }
@@ -354,6 +367,17 @@ int columns_pairs_per_warp(const ColumnsDev& C) {
   return 1;
 #endif
 }
+template <class K, class... Args>
+void launch_tile(Recorder& R, const char* name, K kernel, long long tiles, size_t smem, Args... args) {
+  R.before(name);
+  kernel<<<(unsigned)tiles, TILE_U * TILE_G, smem, R.h->stream>>>(R.h->P, args...);
+  R.after(name);
+  R.kernels++;
+}
+inline long long tiles_of(long long agents, int units) { return agents * ((units + TILE_U - 1) / TILE_U); }
+inline size_t tile_bytes(int slots) { return sizeof(float) * TILE_U * (size_t)std::max(1, slots); }
+inline int nslots_of(const WinDev& w) { return w.r < 0 ? 0 : w.nslots; }
+
 size_t columns_smem_bytes(const ColumnsDev& C) {
   const int ppw = columns_pairs_per_warp(C);
   return sizeof(float) * BIDI_COL_WARPS * ppw * (size_t)bidi::column_slab_floats(C) + 8 * BIDI_COL_WARPS;
@@ -381,20 +405,44 @@ void record_step(Recorder& R, bool learn) {
   if (V == BIDI_KWINNERS) {
     // sdr/PredictiveRSDR.cpp:102-112
     for (int l = 0; l < L; l++) {
-      R.launch("kw_activate", bidi::k_kw_activate, A * ly[l].nh, ly[l], l);
-      R.launch("kw_inhibit", bidi::k_kw_inhibit, A * ly[l].nh, ly[l], l, ly[l].act, ly[l].state, l < L - 1 ? ly[l + 1].vis_input : -1LL);
-      R.launch("reconstruct", bidi::k_reconstruct, A * (ly[l].nv + ly[l].nh), ly[l], l, ly[l].state, 0, 0.0f, 0);
+      const LayerDev& Y = ly[l];
+      const long long nxt = l < L - 1 ? ly[l + 1].vis_input : -1LL;
+      if (h->tiled[l]) {
+        launch_tile(R, "kw_activate", bidi::k_t_kw_activate, tiles_of(A, Y.nh), tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec)), Y, l);
+        launch_tile(R, "kw_inhibit", bidi::k_t_kw_inhibit, tiles_of(A, Y.nh), 0, Y, l, Y.act, Y.state, nxt);
+        launch_tile(R, "reconstruct", bidi::k_t_reconstruct, tiles_of(A, Y.nv) + tiles_of(A, Y.nh),
+                    tile_bytes(std::max(Y.ff.max_cand, Y.rec.max_cand)), Y, l, Y.state, 0, 0.0f, 0, 0);
+      } else {
+        R.launch("kw_activate", bidi::k_kw_activate, A * Y.nh, Y, l);
+        R.launch("kw_inhibit", bidi::k_kw_inhibit, A * Y.nh, Y, l, Y.act, Y.state, nxt);
+        R.launch("reconstruct", bidi::k_reconstruct, A * (Y.nv + Y.nh), Y, l, Y.state, 0, 0.0f, 0);
+      }
     }
     // :115-171
     for (int l = L - 1; l >= 0; l--) {
-      R.launch("predict", bidi::k_predict, A * ly[l].pn, ly[l], l, (int)learn, ly[l < L - 1 ? l + 1 : l].p_state, ly[l < L - 1 ? l + 1 : l].p_state_prev);
-      R.launch("kw_inhibit", bidi::k_kw_inhibit, A * ly[l].nh, ly[l], l, ly[l].p_act, ly[l].p_state, -1LL);
+      const LayerDev& Y = ly[l];
+      const LayerDev& Up = ly[l < L - 1 ? l + 1 : l];
+      if (h->tiled[l]) {
+        launch_tile(R, "predict", bidi::k_t_predict, tiles_of(A, Y.pn), tile_bytes(nslots_of(Y.fb) + nslots_of(Y.pred)), Y, l, (int)learn,
+                    Up.p_state, Up.p_state_prev);
+        launch_tile(R, "kw_inhibit", bidi::k_t_kw_inhibit, tiles_of(A, Y.nh), 0, Y, l, Y.p_act, Y.p_state, -1LL);
+      } else {
+        R.launch("predict", bidi::k_predict, A * Y.pn, Y, l, (int)learn, Up.p_state, Up.p_state_prev);
+        R.launch("kw_inhibit", bidi::k_kw_inhibit, A * Y.nh, Y, l, Y.p_act, Y.p_state, -1LL);
+      }
     }
     // :173-185
-    if (learn) for (int l = 0; l < L; l++) R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, ly[l], l);
+    if (learn)
+      for (int l = 0; l < L; l++) {
+        if (h->tiled[l]) launch_tile(R, "kw_learn", bidi::k_t_kw_learn, tiles_of(A, ly[l].nh), 0, ly[l], l);
+        else R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, ly[l], l);
+      }
     R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
     // :188-193
-    R.launch("kw_predict_input", bidi::k_kw_predict_input, A * h->n_in, ly[0]);
+    if (h->tiled[0])
+      launch_tile(R, "kw_predict_input", bidi::k_t_reconstruct, tiles_of(A, ly[0].nv), tile_bytes(ly[0].ff.max_cand), ly[0], 0, ly[0].p_state, 0,
+                  0.0f, 0, 1);
+    else R.launch("kw_predict_input", bidi::k_kw_predict_input, A * h->n_in, ly[0]);
     return;
   }
   for (int l = 0; l < L; l++) {
@@ -409,39 +457,55 @@ void record_step(Recorder& R, bool learn) {
       R.kernels++;
       continue;
     }
+    const LayerDev& Y = ly[l];
+    const bool tl = h->tiled[l] != 0;
+    const size_t sm_sweep = tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec) + nslots_of(Y.lat));
+    const size_t sm_rec = tile_bytes(std::max(Y.ff.max_cand, Y.rec.max_cand));
+    const long long t_sweep = tiles_of(A, Y.nh), t_rec = tiles_of(A, Y.nv) + tiles_of(A, Y.nh);
+    auto sweep = [&](int first, int acc, float scale) {
+      if (tl) launch_tile(R, "ic_sweep", bidi::k_t_ic_sweep, t_sweep, sm_sweep, Y, l, first, acc, scale);
+      else R.launch("ic_sweep", bidi::k_ic_sweep, nh, Y, l, first, acc, scale);
+    };
+    auto recon = [&](long long drive, int scaled, float mult, int copy_spike) {
+      if (tl) launch_tile(R, "reconstruct", bidi::k_t_reconstruct, t_rec, sm_rec, Y, l, drive, scaled, mult, copy_spike, 0);
+      else R.launch("reconstruct", bidi::k_reconstruct, nvh, Y, l, drive, scaled, mult, copy_spike);
+    };
     if (V == BIDI_ITERATIVE) { // sdr/IRSDR.cpp:125-216
-      const int settle = ly[l].iter_settle, measure = ly[l].iter_measure;
-      for (int it = 0; it < settle; it++) {
-        R.launch("ic_sweep", bidi::k_ic_sweep, nh, ly[l], l, (int)(it == 0), 0, 0.0f);
-        R.launch("reconstruct", bidi::k_reconstruct, nvh, ly[l], l, ly[l].spike, 0, 0.0f, 1);
-      }
+      const int settle = Y.iter_settle, measure = Y.iter_measure;
+      for (int it = 0; it < settle; it++) { sweep((int)(it == 0), 0, 0.0f); recon(Y.spike, 0, 0.0f, 1); }
       const float inv = 1.0f / measure;
-      for (int it = 0; it < measure; it++) {
-        R.launch("ic_sweep", bidi::k_ic_sweep, nh, ly[l], l, (int)(settle == 0 && it == 0), 1, inv);
-        R.launch("reconstruct", bidi::k_reconstruct, nvh, ly[l], l, ly[l].spike, 0, 0.0f, 1);
-      }
-      R.launch("reconstruct", bidi::k_reconstruct, nvh, ly[l], l, ly[l].state, 0, 0.0f, 0);
-      if (l < L - 1) R.launch("ic_finish", bidi::k_ic_finish, nh, ly[l], l, 0, 0.0f, ly[l + 1].vis_input);
+      for (int it = 0; it < measure; it++) { sweep((int)(settle == 0 && it == 0), 1, inv); recon(Y.spike, 0, 0.0f, 1); }
+      recon(Y.state, 0, 0.0f, 0);
+      if (l < L - 1) R.launch("ic_finish", bidi::k_ic_finish, nh, Y, l, 0, 0.0f, ly[l + 1].vis_input);
     } else { // neo/SparseCoder.cpp:116-176
-      const int iter = ly[l].iter_settle;
+      const int iter = Y.iter_settle;
       float counter = 0.0f;
       for (int it = 0; it < iter; it++) {
-        R.launch("ic_sweep", bidi::k_ic_sweep, nh, ly[l], l, (int)(it == 0), 2, 0.0f);
+        sweep((int)(it == 0), 2, 0.0f);
         counter += 1.0f;
-        R.launch("reconstruct", bidi::k_reconstruct, nvh, ly[l], l, ly[l].state, 1, 1.0f / counter, 1);
+        recon(Y.state, 1, 1.0f / counter, 1);
       }
-      R.launch("ic_finish", bidi::k_ic_finish, nh, ly[l], l, 1, 1.0f / counter, l < L - 1 ? ly[l + 1].vis_input : -1LL);
+      R.launch("ic_finish", bidi::k_ic_finish, nh, Y, l, 1, 1.0f / counter, l < L - 1 ? ly[l + 1].vis_input : -1LL);
     }
   }
   for (int l = L - 1; l >= 0; l--) {
+    const LayerDev& Y = ly[l];
+    const LayerDev& Up = ly[l < L - 1 ? l + 1 : l];
     if (V == BIDI_NEO_AGENT) record_columns(R, l);
-    R.launch("predict", bidi::k_predict, A * ly[l].pn, ly[l], l, (int)learn, ly[l < L - 1 ? l + 1 : l].p_state, ly[l < L - 1 ? l + 1 : l].p_state_prev);
+    if (h->tiled[l] && V != BIDI_NEO_AGENT)
+      launch_tile(R, "predict", bidi::k_t_predict, tiles_of(A, Y.pn), tile_bytes(nslots_of(Y.fb) + nslots_of(Y.pred)), Y, l, (int)learn, Up.p_state,
+                  Up.p_state_prev);
+    else R.launch("predict", bidi::k_predict, A * Y.pn, Y, l, (int)learn, Up.p_state, Up.p_state_prev);
   }
   if (V == BIDI_NEO_AGENT) record_columns(R, L);
-  R.launch("predict_input", bidi::k_predict_input, A * h->n_in, ly[L], (int)learn, ly[0].p_state, ly[0].p_state_prev);
+  if (h->tiled[L] && V != BIDI_NEO_AGENT)
+    launch_tile(R, "predict_input", bidi::k_t_predict, tiles_of(A, ly[L].pn), tile_bytes(nslots_of(ly[L].fb)), ly[L], L, (int)learn, ly[0].p_state,
+                ly[0].p_state_prev);
+  else R.launch("predict_input", bidi::k_predict_input, A * h->n_in, ly[L], (int)learn, ly[0].p_state, ly[0].p_state_prev);
   if (learn)
     for (int l = 0; l < L; l++) {
-      if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
+      if (h->tiled[l]) launch_tile(R, "ic_learn", bidi::k_t_ic_learn, tiles_of(A, ly[l].nh), 0, ly[l], l, (int)(V != BIDI_ITERATIVE));
+      else if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
       else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
     }
   R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
@@ -778,6 +842,28 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_cta<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
   }
+  // node layers with few (agent, unit) threads use the cooperative tile kernels
+  h->tiled.assign(L + 1, 0);
+  {
+    size_t sm = 0;
+    for (int l = 0; l <= L; l++) {
+      if (l == L && V == BIDI_KWINNERS) break;
+      const LayerDev& Y = h->layers[l];
+      const int units = l < L ? std::max(Y.nh, Y.nv) : Y.pn;
+      size_t need = tile_bytes(nslots_of(Y.fb) + nslots_of(Y.pred));
+      if (l < L) {
+        need = std::max(need, tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec) + nslots_of(Y.lat)));
+        need = std::max(need, tile_bytes(std::max(Y.ff.max_cand, Y.rec.max_cand)));
+      }
+      if ((long long)n_agents * units <= 32768 && need <= 200 * 1024) { h->tiled[l] = 1; sm = std::max(sm, need); }
+    }
+    if (sm > 0) {
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_t_kw_activate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_t_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_t_ic_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_t_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+  }
   // the column kernel may need more than the default 48 KB of dynamic shared memory
   if (V == BIDI_NEO_AGENT) {
     size_t smem = 0;
@@ -1064,6 +1150,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   if (std::string(name) == "force_phase_kernels") h->force_phase_kernels = value != 0;
+  else if (std::string(name) == "tile_kernels") { if (!value) std::fill(h->tiled.begin(), h->tiled.end(), 0); }
   else return fail(h, BIDI_EINVAL, "bidi_set_option: unknown option");
   for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   return BIDI_OK;

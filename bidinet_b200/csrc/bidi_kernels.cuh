@@ -64,6 +64,52 @@ __device__ __forceinline__ void for_each_conn(const WinDev& w, int ux, int uy, F
   }
 }
 
+// sum += src(target) * w[slot][unit] over the WHOLE slot box, in the reference's list
+// order, with no per-slot test: the slot planes hold 0 wherever the unit has no
+// connection (off-grid, outside the radius, excluded centre), the target index is
+// clamped into the grid, and (+-0) added to the running sum leaves it unchanged.  The
+// loop body is then a bare load-load-multiply-add the compiler can unroll and batch,
+// which is what keeps a single large agent (C4) from being bound by load latency.
+template <class Src>
+__device__ __forceinline__ float dot_conn(const WinDev& w, int ux, int uy, const float* __restrict__ plane, long long U, int i,
+                                          float sum, Src&& src) {
+  if (w.r < 0) return sum;
+  const int cx = w.cx[ux], cy = w.cy[uy];
+  const float* wp = plane + i;
+#ifdef BIDI_DOT_BATCH
+  // slots in list order (sx outer, sy inner), B at a time: all 2B loads of a batch are
+  // issued before the first add, so one memory round trip serves B connections
+  constexpr int B = 16;
+  int sx = 0, sy = 0;
+  for (int s0 = 0; s0 < w.nslots; s0 += B) {
+    float wv[B], xv[B];
+#pragma unroll
+    for (int k = 0; k < B; k++) {
+      const bool in = s0 + k < w.nslots;
+      const int tx = w.absx ? sx : min(max(cx - w.r + sx, 0), w.tw - 1);
+      const int ty = w.absy ? sy : min(max(cy - w.r + sy, 0), w.th - 1);
+      wv[k] = in ? wp[(long long)(s0 + k) * U] : 0.0f;
+      xv[k] = in ? src(tx + ty * w.tw) : 0.0f;
+      if (++sy == w.dyn) { sy = 0; sx++; }
+    }
+#pragma unroll
+    for (int k = 0; k < B; k++)
+      if (s0 + k < w.nslots) sum += xv[k] * wv[k];
+  }
+#else
+  for (int sx = 0; sx < w.dxn; sx++) {
+    const int tx = w.absx ? sx : min(max(cx - w.r + sx, 0), w.tw - 1);
+#pragma unroll 8
+    for (int sy = 0; sy < w.dyn; sy++) {
+      const int ty = w.absy ? sy : min(max(cy - w.r + sy, 0), w.th - 1);
+      sum += src(tx + ty * w.tw) * wp[0];
+      wp += U;
+    }
+  }
+#endif
+  return sum;
+}
+
 // Gather form of the reference's scatter reconstruction (sdr/RSDR.cpp:175-187):
 // sum over the units whose window contains target (tx,ty) of w[unit->target]*drive,
 // visited in ascending unit index = the order the scatter adds them.  A zero drive
@@ -108,8 +154,8 @@ __global__ void k_kw_activate(EngineDev P, LayerDev L, int l) {
   const float* wrec = B + L.rec.w_off;
   const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
   float sum = -B[L.thr + i];
-  for_each_conn(L.ff, ux, uy, [&](int s, int t) { sum += x[t] * wff[(long long)s * U + i]; });
-  for_each_conn(L.rec, ux, uy, [&](int s, int t) { sum += sprev[t] * wrec[(long long)s * U + i]; });
+  sum = dot_conn(L.ff, ux, uy, wff, U, i, sum, [&](int t) { return x[t]; });
+  sum = dot_conn(L.rec, ux, uy, wrec, U, i, sum, [&](int t) { return sprev[t]; });
   B[L.act + i] = sum;
 }
 
@@ -195,10 +241,10 @@ __global__ void k_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, f
   const float* wlat = B + L.lat.w_off;
   const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
   float excitation = 0.0f;
-  for_each_conn(L.ff, ux, uy, [&](int s, int t) { excitation += (x[t] - vrec[t]) * wff[(long long)s * U + i]; });
-  for_each_conn(L.rec, ux, uy, [&](int s, int t) { excitation += (sprev[t] - hrec[t]) * wrec[(long long)s * U + i]; });
+  excitation = dot_conn(L.ff, ux, uy, wff, U, i, excitation, [&](int t) { return x[t] - vrec[t]; });
+  excitation = dot_conn(L.rec, ux, uy, wrec, U, i, excitation, [&](int t) { return sprev[t] - hrec[t]; });
   float inhibition = 0.0f;
-  for_each_conn(L.lat, ux, uy, [&](int s, int t) { inhibition += spk_prev[t] * wlat[(long long)s * U + i]; });
+  inhibition = dot_conn(L.lat, ux, uy, wlat, U, i, inhibition, [&](int t) { return spk_prev[t]; });
   float act = first ? 0.0f : B[L.act + i];
   float st = first ? 0.0f : B[L.state + i];
   act = (1.0f - L.leak) * act + excitation - inhibition;
@@ -331,8 +377,8 @@ __global__ void k_predict(EngineDev P, LayerDev L, int l, int learn, long long u
     for_each_conn(L.pred, ux, uy, [&](int s, int t) { wpr[(long long)s * U + i] += kpr * sprev[t]; });
   }
   float activation = 0.0f;
-  if (!top) for_each_conn(L.fb, ux, uy, [&](int s, int t) { activation += wfb[(long long)s * U + i] * up_state[t]; });
-  for_each_conn(L.pred, ux, uy, [&](int s, int t) { activation += wpr[(long long)s * U + i] * state[t]; });
+  if (!top) activation = dot_conn(L.fb, ux, uy, wfb, U, i, activation, [&](int t) { return up_state[t]; });
+  activation = dot_conn(L.pred, ux, uy, wpr, U, i, activation, [&](int t) { return state[t]; });
   B[L.p_act + i] = activation;
   if (P.variant != BIDI_KWINNERS) B[L.p_state + i] = bidi_clamp01(activation);
 }
@@ -352,7 +398,7 @@ __global__ void k_predict_input(EngineDev P, LayerDev L, int learn, long long p0
     for_each_conn(L.fb, ux, uy, [&](int s, int t) { wfb[(long long)s * U + i] += k * p0_prev[t]; });
   }
   float activation = 0.0f;
-  for_each_conn(L.fb, ux, uy, [&](int s, int t) { activation += wfb[(long long)s * U + i] * p0[t]; });
+  activation = dot_conn(L.fb, ux, uy, wfb, U, i, activation, [&](int t) { return p0[t]; });
   B[L.p_act + i] = activation;
   P.pred_out[(long long)a * P.n_in + i] = activation;
 }

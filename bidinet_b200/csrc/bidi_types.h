@@ -34,6 +34,7 @@ struct WinDev {
   int excl;          // centre excluded (recurrent, lateral)
   int nslots;        // dxn*dyn
   int U;             // uw*uh
+  int max_cand;      // largest number of units whose window can contain one target (gather form)
   const int* cx;     // [uw] window centre per unit column, round_f32(ux * tw/uw)  (sdr/RSDR.cpp:40)
   const int* cy;     // [uh]
   // reverse map for gather-form reconstruction: target column tx is inside the

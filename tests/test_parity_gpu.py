@@ -42,16 +42,21 @@ def test_init_random_matches_oracle(case):
         assert diff_states(orc.state(), eng.state(agent=a)) == [], "agent %d" % a
 
 
-@pytest.mark.parametrize("phase_kernels", [False, True], ids=["fused", "per_phase"])
+@pytest.mark.parametrize("path", ["default", "per_phase_tiles", "per_phase_threads"])
 @pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
-def test_free_running_parity(case, phase_kernels):
+def test_free_running_parity(case, path):
     """N steps from an identical state, no re-synchronisation: exact after every step.
-    Both engine paths are held to it: the fused per-agent coder kernel (default where
-    the layer fits in shared memory) and the one-kernel-per-phase path (large layers)."""
+    Every engine path is held to it: the default (fused per-agent coder kernel where the
+    layer fits in shared memory, cooperative tile kernels for small launches), one
+    kernel per phase with the tile kernels (large single agents), and one kernel per
+    phase with one thread per unit (large agent batches, very large layers)."""
     name, cfg, ld, frame, reward = case
     orc = OracleHierarchy(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1)
-    eng.set_option("force_phase_kernels", phase_kernels)
+    if path != "default":
+        eng.set_option("force_phase_kernels", True)
+    if path == "per_phase_threads":
+        eng.set_option("tile_kernels", False)
     eng.load_state(orc.state())
     steps = 25
     for t in range(steps):
