@@ -39,20 +39,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_STATE, N_CLOCK, INPUT_COUNT, N_ACTION = 15, 4, 20, 10  # RunnerMain.cpp:115-116
-FB_IDX = np.arange(INPUT_COUNT, INPUT_COUNT + N_ACTION, dtype=np.int32)
-
-
-def base_frames(n_frames, agents, first_agent, n_in=64, t0=0):
-    """Open-loop part of the RunnerMain input: [T][A][n_in]."""
-    t = (t0 + np.arange(n_frames, dtype=np.float32))[:, None, None]
-    a = (first_agent + np.arange(agents, dtype=np.float32))[None, :, None]
-    f = np.zeros((n_frames, agents, n_in), dtype=np.float32)
-    i = np.arange(N_STATE, dtype=np.float32)[None, None, :]
-    f[:, :, :N_STATE] = 0.5 + 0.5 * np.sin(0.05 * t * (1.0 + i) + 0.1 * a)
-    c = np.arange(N_CLOCK, dtype=np.float32)[None, None, :]
-    f[:, :, N_STATE:N_STATE + N_CLOCK] = np.sin(t / 60.0 * 2.0 * c * 2.0 * 3.141596) * 0.5 + 0.5
-    return f
+from bidinet_b200.sharding import (FB_IDX, base_frames, max_over_ranks as _max_over_ranks, rank_info,  # noqa: E402
+                                   seed_base_for, whole_job_rate)
 
 
 class ClockSampler:
@@ -214,9 +202,7 @@ def main():
     ap.add_argument("--profile-kernel", default="columns")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local_rank = rank_info()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -239,16 +225,12 @@ def main():
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return _max_over_ranks(x, dist, "cuda")
 
     A, K, W = args.agents_per_gpu, args.steps, max(3, args.warmup)
     cfg, ld = cf.config_c2()
     eng = Engine(cfg, ld, n_agents=A, device=local_rank)
-    eng.init_random(1234 + rank * A)  # global agent g <- std::mt19937(1234 + g)
+    eng.init_random(seed_base_for(rank, A))  # global agent g <- std::mt19937(1234 + g)
     n_in = eng.n_in
     T = min(W + K, 64)
     frames = base_frames(T, A, rank * A, n_in)
@@ -275,7 +257,7 @@ def main():
     barrier()
     launches = eng.launch_count - launches0
     ms = max_over_ranks(ms)
-    value = world * A * K / (ms * 1e-3)
+    value = whole_job_rate(A, world, K, ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI, host<->device copies inside the timed region
     rng = np.random.RandomState(rank)
@@ -304,7 +286,7 @@ def main():
     eng.sync()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = world * A * K / e2e_s
+    e2e_value = whole_job_rate(A, world, K, e2e_s)
     if rank == 0:
         clk = clocks.stop()
 
