@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -98,6 +99,15 @@ struct bidi_engine {
   double profile_ms = 0; long long profile_launches = 0;
   // host mirror of ONE agent's blob for set/get_array
   std::vector<float> mirror; int mirror_agent = -1; bool mirror_dirty = false;
+  // spatial strip split of one oversized layer (bidi_strip.inl)
+  int strip_part = 0, strip_n = 1;
+  int strip_span[BIDI_SPAN_COUNT][2] = {};
+  struct StripXfer { int point, peer; long long off, count; };
+  std::vector<StripXfer> strip_send, strip_recv;   // per exchange point, peer: rows of one plane
+  std::vector<bidi_engine*> strip_peers;           // same-process transport, indexed by part
+  void* nccl_comm = nullptr;                       // one-process-per-GPU transport
+  cudaEvent_t strip_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t strip_done = nullptr;
   std::string err;
 };
 
@@ -528,9 +538,12 @@ int ensure_graph(bidi_engine* h, bool learn) {
   return BIDI_OK;
 }
 
+int strip_step_nccl(bidi_engine* h, bool learn);
+
 int run_step(bidi_engine* h, bool learn, bool device_noise) {
   int rc = mirror_release(h);
   if (rc) return rc;
+  if (h->strip_n > 1) return strip_step_nccl(h, learn);
   if (h->cfg.variant == BIDI_NEO_AGENT && device_noise) {
     // the step counter changes every call, so this launch stays outside the graph
     bidi::k_noise<<<grid_for((long long)h->A * h->ncol, kBlock), kBlock, 0, h->stream>>>(
@@ -551,6 +564,8 @@ void fill_columns_params(ColumnsDev& C, int cells, int iter, float sparsity, flo
   C.a_ff = aff; C.a_lat = alat; C.a_thr = athr; C.a_q = aq; C.a_act = aact; C.expl_std = std; C.expl_break = brk;
 }
 
+void strip_release(bidi_engine* h);
+
 } // namespace
 
 // =================================================================== C ABI
@@ -570,6 +585,7 @@ void bidi_destroy(bidi_engine* h) {
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_pred); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_noise); cudaFreeHost(h->h_actions);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  strip_release(h);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -617,6 +633,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     if (l < L) {
       const bidi_layer_desc& d = layers[l];
       D.vw = vw; D.vh = vh; D.hw = d.width; D.hh = d.height; D.nv = vw * vh; D.nh = d.width * d.height;
+      D.row0 = 0; D.row1 = D.hh; D.vrow0 = 0; D.vrow1 = D.vh;
       h->max_units = std::max(h->max_units, D.nh);
       D.vis_input = l == 0 ? -1 : al.take(D.nv);
       D.vis_recon = al.take(D.nv);
@@ -650,7 +667,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       if (V == BIDI_KWINNERS) continue;
       D.pn = h->n_in;
       D.p_state = -1;
-      D.hw = cfg->in_width; D.hh = cfg->in_height;
+      D.hw = cfg->in_width; D.hh = cfg->in_height; D.row0 = 0; D.row1 = D.hh;
       build_win(H.fb, cfg->in_width, cfg->in_height, layers[0].width, layers[0].height, cfg->r_infb, false, false);
       build_win(H.pred, cfg->in_width, cfg->in_height, 1, 1, -1, true, false);
       build_win(H.ff, 1, 1, 1, 1, -1, true, false); build_win(H.rec, 1, 1, 1, 1, -1, true, false); build_win(H.lat, 1, 1, 1, 1, -1, true, false);
@@ -1213,3 +1230,5 @@ int bidi_abi_sizes(int* config_bytes, int* layer_desc_bytes) {
 }
 
 } // extern "C"
+
+#include "bidi_strip.inl"

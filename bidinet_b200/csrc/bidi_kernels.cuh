@@ -137,16 +137,24 @@ __device__ __forceinline__ float gather_recon(const WinDev& w, const float* __re
   return sum;
 }
 
+// one thread per (agent, hidden unit of the launch's row strip)
+#define BIDI_THREAD_AGENT_HIDDEN                                            \
+  const long long gid_ = (long long)blockIdx.x * blockDim.x + threadIdx.x; \
+  const int n_ = (L.row1 - L.row0) * L.hw;                                  \
+  if (gid_ >= (long long)P.A * n_) return;                                  \
+  const int a = (int)(gid_ / n_);                                           \
+  const int i = L.row0 * L.hw + (int)(gid_ % n_);
+
 #define BIDI_THREAD_AGENT_UNIT(N)                                        \
   const long long gid_ = (long long)blockIdx.x * blockDim.x + threadIdx.x; \
   if (gid_ >= (long long)P.A * (N)) return;                              \
   const int a = (int)(gid_ / (N));                                        \
-  const int i = (int)(gid_ % (N));
+  int i = (int)(gid_ % (N));
 
 // ------------------------------------------------------------------ k-winners coder
 // sdr/RSDR.cpp:123-133: a = -theta + sum_ff x*w + sum_rec sPrev*w
 __global__ void k_kw_activate(EngineDev P, LayerDev L, int l) {
-  BIDI_THREAD_AGENT_UNIT(L.nh)
+  BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
   const float* sprev = B + L.state_prev;
@@ -163,7 +171,7 @@ __global__ void k_kw_activate(EngineDev P, LayerDev L, int l) {
 // and `dst` are blob offsets; dst_next (>=0) also receives the state as the next
 // layer's visible input (sdr/PredictiveRSDR.cpp:108-111).
 __global__ void k_kw_inhibit(EngineDev P, LayerDev L, int l, long long src, long long dst, long long dst_next) {
-  BIDI_THREAD_AGENT_UNIT(L.nh)
+  BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   const float* act = B + src;
   const int ux = i % L.hw, uy = i / L.hw;
@@ -182,13 +190,15 @@ __global__ void k_kw_inhibit(EngineDev P, LayerDev L, int l, long long src, long
 // visible cell, [nv,nv+nh) a hidden unit.  copy_spike: also spikePrev = spike
 // (sdr/IRSDR.cpp:170-171), race-free here because this kernel never reads spikePrev.
 __global__ void k_reconstruct(EngineDev P, LayerDev L, int l, long long drive_off, int scaled, float mult, int copy_spike) {
-  BIDI_THREAD_AGENT_UNIT(L.nv + L.nh)
+  const int nvs = (L.vrow1 - L.vrow0) * L.vw, nhs = (L.row1 - L.row0) * L.hw;
+  BIDI_THREAD_AGENT_UNIT(nvs + nhs)
   float* B = blob_of(P, a);
   const float* drive = B + drive_off;
-  if (i < L.nv) {
-    B[L.vis_recon + i] = gather_recon(L.ff, B + L.ff.w_off, drive, i % L.vw, i / L.vw, scaled != 0, mult);
+  if (i < nvs) {
+    const int v = L.vrow0 * L.vw + i;
+    B[L.vis_recon + v] = gather_recon(L.ff, B + L.ff.w_off, drive, v % L.vw, v / L.vw, scaled != 0, mult);
   } else {
-    const int h = i - L.nv;
+    const int h = L.row0 * L.hw + (i - nvs);
     B[L.recon + h] = gather_recon(L.rec, B + L.rec.w_off, drive, h % L.hw, h / L.hw, scaled != 0, mult);
     if (copy_spike) B[L.spike_prev + h] = B[L.spike + h];
   }
@@ -197,14 +207,16 @@ __global__ void k_reconstruct(EngineDev P, LayerDev L, int l, long long drive_of
 // sdr/RSDR.cpp:196-212 applied to layer 0's predicted states -> _prediction
 // (sdr/PredictiveRSDR.cpp:188-193)
 __global__ void k_kw_predict_input(EngineDev P, LayerDev L) {
-  BIDI_THREAD_AGENT_UNIT(L.nv)
+  const int nvs = (L.vrow1 - L.vrow0) * L.vw;
+  BIDI_THREAD_AGENT_UNIT(nvs)
+  i += L.vrow0 * L.vw;
   float* B = blob_of(P, a);
   P.pred_out[(long long)a * P.n_in + i] = gather_recon(L.ff, B + L.ff.w_off, B + L.p_state, i % L.vw, i / L.vw, false, 0.0f);
 }
 
 // sdr/RSDR.cpp:241-266: winners only; theta for every unit
 __global__ void k_kw_learn(EngineDev P, LayerDev L, int l) {
-  BIDI_THREAD_AGENT_UNIT(L.nh)
+  BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
   const float* vrec = B + L.vis_recon;
@@ -229,7 +241,7 @@ __global__ void k_kw_learn(EngineDev P, LayerDev L, int l) {
 // (sdr/IRSDR.cpp:131-135).  acc: 0 = settle (no state change), 1 = state +=
 // scale*spike (measure; scale = 1/measureIter), 2 = state += spike (neo).
 __global__ void k_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale) {
-  BIDI_THREAD_AGENT_UNIT(L.nh)
+  BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
   const float* vrec = B + L.vis_recon;
@@ -261,7 +273,7 @@ __global__ void k_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, f
 // then the next layer's input = state (x the column's _attention action for
 // neo::Agent, neo/Agent.cpp:147-151).
 __global__ void k_ic_finish(EngineDev P, LayerDev L, int l, int scale_state, float mult, long long next_vis_input) {
-  BIDI_THREAD_AGENT_UNIT(L.nh)
+  BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   float st = B[L.state + i];
   if (scale_state) { st *= mult; B[L.state + i] = st; }
@@ -286,7 +298,7 @@ __device__ __forceinline__ void ic_learn_tail(const LayerDev& L, float* B, int i
 
 // sdr/IRSDR.cpp:287-319 (Hebbian, clamped delta)
 __global__ void k_ic_learn(EngineDev P, LayerDev L, int l) {
-  BIDI_THREAD_AGENT_UNIT(L.nh)
+  BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
   const float* vrec = B + L.vis_recon;
@@ -312,7 +324,7 @@ __global__ void k_ic_learn(EngineDev P, LayerDev L, int l) {
 // neo/Agent.cpp:252-265 (reward from the prediction error) followed by
 // neo/SparseCoder.cpp:326-361 (reward-modulated update through eligibility traces)
 __global__ void k_neo_learn(EngineDev P, LayerDev L, int l) {
-  BIDI_THREAD_AGENT_UNIT(L.nh)
+  BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
   const float* vrec = B + L.vis_recon;
@@ -350,7 +362,7 @@ __global__ void k_neo_learn(EngineDev P, LayerDev L, int l) {
 // neo/Agent.cpp:177-208.  The delta rule runs BEFORE the activation that uses the
 // weights.
 __global__ void k_predict(EngineDev P, LayerDev L, int l, int learn, long long up_p_state, long long up_p_state_prev) {
-  BIDI_THREAD_AGENT_UNIT(L.pn)
+  BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   const bool top = l == P.L - 1;
   const float* up_state = B + up_p_state;
@@ -416,6 +428,22 @@ __global__ void k_step_end(EngineDev P, int max_units) {
       B[L.p_state_prev + i] = p_state_of(P, L, l, a)[i];
       B[L.p_act_prev + i] = B[L.p_act + i];
     }
+  }
+}
+
+// The same for one row strip of a split layer (bidi_strip.inl): the winners are kept on
+// hidden rows [s0,s1) (owned rows plus the halo later phases read), the prediction
+// nodes only on the owned rows [L.row0,L.row1).
+__global__ void k_strip_step_end(EngineDev P, LayerDev L, int s0, int s1) {
+  const int n = (s1 - s0) * L.hw;
+  BIDI_THREAD_AGENT_UNIT(n)
+  i += s0 * L.hw;
+  float* B = blob_of(P, a);
+  B[L.state_prev + i] = B[L.state + i];
+  const int row = i / L.hw;
+  if (row >= L.row0 && row < L.row1) {
+    B[L.p_state_prev + i] = B[L.p_state + i];
+    B[L.p_act_prev + i] = B[L.p_act + i];
   }
 }
 

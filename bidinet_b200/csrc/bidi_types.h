@@ -82,6 +82,9 @@ struct ColumnsDev {
 // Index n_layers holds only the input prediction nodes (pn_*, fb, col).
 struct LayerDev {
   int vw, vh, hw, hh, nv, nh;
+  // Row strip a launch works on (hidden rows [row0,row1), visible rows [vrow0,vrow1)).
+  // The whole grid except when one oversized layer is split across GPUs (bidi_strip_*).
+  int row0, row1, vrow0, vrow1;
   // coder unit planes (offsets into the blob)
   long long vis_input, vis_recon;   // vis_input is -1 for layer 0 (dense input array)
   long long thr, state, state_prev, act, recon, spike, spike_prev;

@@ -47,7 +47,16 @@ ABI = {
     "bidi_launch_count": (C.c_longlong, [C.c_void_p]),
     "bidi_device_bytes": (C.c_longlong, [C.c_void_p]),
     "bidi_abi_sizes": (C.c_int, [_IP, _IP]),
+    "bidi_strip_plan": (C.c_int, [C.POINTER(Config), C.POINTER(LayerDesc), C.c_int, C.c_int, _IP]),
+    "bidi_strip_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bidi_strip_link_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "bidi_strip_step_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "bidi_strip_step_frame_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
+    "bidi_strip_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "bidi_strip_link_nccl": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bidi_strip_halo_floats": (C.c_longlong, [C.c_void_p]),
 }
+SPAN_NAMES = ["OWN_HID", "OWN_VIS", "EXT_HID", "STATE", "ACT", "VIS_RECON", "HID_RECON", "PRED_STATE"]
 
 _lib = None
 
@@ -221,6 +230,20 @@ class Engine:
         self._check(self.lib.bidi_timer_stop_ms(self.h, C.byref(ms)), "bidi_timer_stop_ms")
         return ms.value
 
+    # ---- spatial split of one oversized layer (include/bidinet_b200.h, bidi_strip_*)
+    def strip_configure(self, part, n_parts):
+        self._check(self.lib.bidi_strip_configure(self.h, part, n_parts), "bidi_strip_configure")
+        self.strip_part, self.strip_n = part, n_parts
+        self.spans = strip_plan(self.cfg, self.layers, part, n_parts)
+
+    def strip_link_nccl(self, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.bidi_strip_link_nccl(self.h, buf), "bidi_strip_link_nccl")
+
+    @property
+    def strip_halo_floats(self):
+        return int(self.lib.bidi_strip_halo_floats(self.h))
+
     @property
     def launch_count(self):
         return int(self.lib.bidi_launch_count(self.h))
@@ -228,3 +251,121 @@ class Engine:
     @property
     def device_bytes(self):
         return int(self.lib.bidi_device_bytes(self.h))
+
+
+def strip_plan(cfg, layers, part, n_parts):
+    """{span name: (lo, hi)} row intervals of one part of a split layer (pure geometry, no GPU)."""
+    lib = load_library()
+    out = (C.c_int * (2 * len(SPAN_NAMES)))()
+    rc = lib.bidi_strip_plan(C.byref(cfg), layers, part, n_parts, out)
+    if rc != 0:
+        raise BidiError("bidi_strip_plan failed (%d): %s" % (rc, lib.bidi_last_error(None).decode()))
+    return {n: (out[2 * i], out[2 * i + 1]) for i, n in enumerate(SPAN_NAMES)}
+
+
+def nccl_unique_id():
+    """128 bytes for bidi_strip_link_nccl; call on one rank and ship them to the others."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.bidi_strip_nccl_unique_id(buf)
+    if rc != 0:
+        raise BidiError("bidi_strip_nccl_unique_id failed (%d): %s" % (rc, lib.bidi_last_error(None).decode()))
+    return buf.raw
+
+
+class StripGroup:
+    """One oversized single-layer k-winners hierarchy split into row strips over several
+    engines of THIS process (devices[p] hosts part p; the same device may repeat).  The
+    parts exchange halo rows by peer copies; results equal the unsplit engine's bit for
+    bit.  State arrays come back assembled from the rows each part owns."""
+
+    def __init__(self, cfg, layers, devices, n_agents=1, seed=None):
+        self.cfg, self.layers = cfg, layers
+        n = len(devices)
+        self.parts = [Engine(cfg, layers, n_agents=n_agents, device=d) for d in devices]
+        for p, e in enumerate(self.parts):
+            e.strip_configure(p, n)
+        self.lib = self.parts[0].lib
+        self._handles = (C.c_void_p * n)(*[e.h for e in self.parts])
+        rc = self.lib.bidi_strip_link_local(self._handles, n)
+        if rc != 0:
+            raise BidiError("bidi_strip_link_local failed (%d): %s" % (rc, self.lib.bidi_last_error(self.parts[0].h).decode()))
+        self.n_in, self.n_agents = self.parts[0].n_in, n_agents
+        if seed is not None:
+            for e in self.parts:
+                e.init_random(seed)
+
+    def close(self):
+        for e in self.parts:
+            e.close()
+
+    def load_state(self, state, agent=0):
+        for e in self.parts:
+            e.load_state(state, agent)
+
+    def set_inputs(self, x):
+        for e in self.parts:
+            e.set_inputs(x)
+
+    def load_frames(self, frames):
+        for e in self.parts:
+            e.load_frames(frames)
+
+    def step(self, learn=True):
+        rc = self.lib.bidi_strip_step_local(self._handles, len(self.parts), int(bool(learn)))
+        if rc != 0:
+            raise BidiError("bidi_strip_step_local failed (%d): %s" % (rc, self.lib.bidi_last_error(self.parts[0].h).decode()))
+
+    def step_frame(self, t, learn=True):
+        rc = self.lib.bidi_strip_step_frame_local(self._handles, len(self.parts), int(t), int(bool(learn)))
+        if rc != 0:
+            raise BidiError("bidi_strip_step_frame_local failed (%d): %s" % (rc, self.lib.bidi_last_error(self.parts[0].h).decode()))
+
+    def sync(self):
+        for e in self.parts:
+            e.sync()
+
+    def get_predictions(self):
+        return assemble_rows([e.get_predictions() for e in self.parts], [e.spans["OWN_VIS"] for e in self.parts],
+                             self.cfg.in_width)
+
+    def state(self, agent=0):
+        return assemble_state(self.parts, agent)
+
+
+def assemble_rows(arrays, spans, width):
+    """Whole-grid plane [..., H*W] from per-part copies: rows [lo,hi) come from the part that owns them."""
+    out = np.array(arrays[0], copy=True)
+    for a, (lo, hi) in zip(arrays, spans):
+        out[..., lo * width:hi * width] = a[..., lo * width:hi * width]
+    return out
+
+
+_VISIBLE_PLANES = ("VIS_RECON", "PREDICTION")
+_REPLICATED = ("VIS_INPUT",)
+
+
+def assemble_state(parts, agent=0):
+    """The serialised state of a split layer: every array taken from the part that owns the rows
+    (unit planes) or the units (connection lists, which are concatenated unit after unit)."""
+    cfg, ld = parts[0].cfg, parts[0].layers
+    vw, hw = cfg.in_width, ld[0].width
+    states = [e.state(agent) for e in parts]
+    out = {}
+    for key in states[0]:
+        name, layer = key
+        if name in _REPLICATED:
+            out[key] = states[0][key]
+        elif name in _VISIBLE_PLANES:
+            out[key] = assemble_rows([s[key] for s in states], [e.spans["OWN_VIS"] for e in parts], vw)
+        elif name in ("FF_W", "REC_W", "PRED_W", "LAT_W", "FB_W"):
+            counts = parts[0].conn_counts(name, layer, ld[0].width * ld[0].height)
+            offs = np.concatenate([[0], np.cumsum(counts)])
+            res = np.array(states[0][key], copy=True)
+            for s, e in zip(states, parts):
+                lo, hi = e.spans["OWN_HID"]
+                res[offs[lo * hw]:offs[hi * hw]] = s[key][offs[lo * hw]:offs[hi * hw]]
+            out[key] = res
+        else:
+            out[key] = assemble_rows([s[key] for s in states], [e.spans["OWN_HID"] for e in parts], hw)
+    return out

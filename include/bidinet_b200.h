@@ -232,6 +232,52 @@ int bidi_profile_collect(bidi_engine* h, double* total_ms, long long* launches);
  */
 int bidi_set_option(bidi_engine* h, const char* name, int value);
 
+/*
+ * Spatial split of ONE oversized layer over several GPUs (BASELINE config 5;
+ * the reference cannot even index such a layer: its connection indices are unsigned
+ * short, sdr/RSDR.h:10).  A single-layer BIDI_KWINNERS hierarchy is cut into n_parts
+ * horizontal row strips; part p owns hidden rows [p*H/n, (p+1)*H/n) and the matching
+ * visible rows.  Weights never move: a unit's weights live on the part that owns the
+ * unit (plus identical, redundantly updated copies of the few halo rows whose weights
+ * the gather-form reconstruction of the owned rows reads).  Per step the parts exchange
+ * halo rows of five unit-state planes (activations before the k-winner rank, winners,
+ * reconstructions, prediction activations, predicted winners); results are bit-identical
+ * to the unsplit engine.
+ *
+ * Every part is a full bidi_engine created with the SAME config on its own device and
+ * given the same inputs (bidi_set_inputs / bidi_load_frames take the whole frame).
+ * bidi_strip_configure must precede bidi_init_random / bidi_set_array.  Two transports:
+ *   - same process (one host thread drives all parts, any mix of devices, peer copies
+ *     over NVLink): bidi_strip_link_local, then bidi_strip_step_local per step;
+ *   - one process per GPU (torchrun): bidi_strip_nccl_unique_id on rank 0, ship the
+ *     128 bytes to every rank, bidi_strip_link_nccl, then plain bidi_step /
+ *     bidi_step_frame; halos go through ncclSend/ncclRecv on the engine's stream.
+ * bidi_get_predictions / bidi_get_array return whole-grid arrays of which only the rows
+ * the part owns are meaningful (bidi_strip_plan tells which).
+ */
+enum bidi_strip_span { /* row intervals [lo,hi) of part p, see bidi_strip_plan */
+  BIDI_SPAN_OWN_HID = 0,  /* hidden rows the part owns */
+  BIDI_SPAN_OWN_VIS,      /* visible (input) rows the part owns */
+  BIDI_SPAN_EXT_HID,      /* hidden rows whose weights it holds and updates (owned + halo) */
+  BIDI_SPAN_STATE,        /* hidden rows on which it keeps the winners (state) valid */
+  BIDI_SPAN_ACT,          /* hidden rows of activations it needs for the k-winner rank */
+  BIDI_SPAN_VIS_RECON,    /* visible rows of the reconstruction its learning rule reads */
+  BIDI_SPAN_HID_RECON,    /* hidden rows of the recurrent reconstruction it reads */
+  BIDI_SPAN_PRED_STATE,   /* hidden rows of predicted winners the input prediction reads */
+  BIDI_SPAN_COUNT
+};
+/* Pure geometry, no device needed: spans[BIDI_SPAN_COUNT][2] of part `part` of `n_parts`. */
+int bidi_strip_plan(const bidi_config* cfg, const bidi_layer_desc* layers, int part, int n_parts, int* spans);
+int bidi_strip_configure(bidi_engine* h, int part, int n_parts);
+int bidi_strip_link_local(bidi_engine** parts, int n_parts);
+int bidi_strip_step_local(bidi_engine** parts, int n_parts, int learn);
+/* frames variant of the above: every part steps on frame t of its loaded frames */
+int bidi_strip_step_frame_local(bidi_engine** parts, int n_parts, int t, int learn);
+int bidi_strip_nccl_unique_id(void* id128);
+int bidi_strip_link_nccl(bidi_engine* h, const void* id128);
+/* floats this part sends per step over the transport (all exchange points, learn on) */
+long long bidi_strip_halo_floats(const bidi_engine* h);
+
 /* Timing helpers on the engine's stream (CUDA events), for bench.py. */
 int bidi_timer_start(bidi_engine* h);
 int bidi_timer_stop_ms(bidi_engine* h, float* ms);

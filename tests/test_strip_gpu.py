@@ -1,0 +1,140 @@
+"""One layer split into row strips over several engines against the
+oracle stepping the WHOLE layer: every state array assembled from the parts' owned rows
+must be equal (np.array_equal) after every step, learning on.  The same-process transport
+runs on one GPU (several parts on the same device); the NCCL transport needs two."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from bidinet_b200 import Engine, StripGroup, assemble_rows, assemble_state, nccl_unique_id
+from bidinet_b200 import config as cf
+from oracle.pyoracle import OracleHierarchy
+
+from util import diff_states
+
+pytestmark = pytest.mark.gpu
+
+GEOMS = [  # (in_w, in_h, hid_w, hid_h, r_ff, r_rec, r_lat, r_pred, sparsity)
+    (24, 24, 24, 24, 3, 3, 3, 3, 0.15),      # C5 in miniature: same-size map, equal radii
+    (17, 29, 11, 23, 3, 2, 2, 3, 0.3),       # ragged, non-integer ratios
+    (9, 40, 12, 16, 2, -1, 1, 4, 0.3),       # no recurrent family, wide predictive window
+]
+
+
+def _cfg(g):
+    iw, ih, hw, hh, rff, rrec, rlat, rpred, sp = g
+    return cf.make_config(cf.KWINNERS, iw, ih, [dict(width=hw, height=hh, r_ff=rff, r_rec=rrec, r_lat=rlat, r_pred=rpred,
+                                                     sparsity=sp, learn_ff=0.1, learn_rec=0.1)])
+
+
+def _frames(g, n=8, seed=0):
+    rng = np.random.RandomState(seed)
+    return (rng.rand(n, g[0] * g[1]) < 0.3).astype(np.float32)
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 4])
+@pytest.mark.parametrize("g", GEOMS, ids=lambda g: "%dx%d_to_%dx%d" % g[:4])
+def test_local_strips_match_the_whole_layer(g, n_parts):
+    cfg, ld = _cfg(g)
+    orc = OracleHierarchy(cfg, ld, 1234)
+    grp = StripGroup(cfg, ld, devices=[0] * n_parts)
+    grp.load_state(orc.state())
+    frames = _frames(g)
+    winners = 0
+    for t in range(12):
+        x = frames[t % len(frames)]
+        learn = t != 5
+        orc.set_inputs(x)
+        orc.step(0.0, learn)
+        grp.set_inputs(x)
+        grp.step(learn)
+        so = orc.state()
+        bad = diff_states(so, grp.state())
+        assert bad == [], "step %d: %s" % (t, bad[:6])
+        assert np.array_equal(orc.get_predictions(), grp.get_predictions()[0])
+        winners += int(so[("HID_STATE", 0)].sum())
+    assert winners > 0  # the learning rule had winners to work on
+    assert all(e.strip_halo_floats > 0 for e in grp.parts)
+    grp.close()
+
+
+def test_strips_init_random_like_the_whole_layer():
+    g = GEOMS[1]
+    cfg, ld = _cfg(g)
+    orc = OracleHierarchy(cfg, ld, 77)
+    grp = StripGroup(cfg, ld, devices=[0, 0, 0], seed=77)
+    assert diff_states(orc.state(), grp.state()) == []
+    grp.close()
+
+
+def test_unlinked_part_refuses_to_step():
+    import bidinet_b200
+    cfg, ld = _cfg(GEOMS[0])
+    e = Engine(cfg, ld)
+    e.strip_configure(0, 2)
+    with pytest.raises(bidinet_b200.BidiError, match="one part of a split layer"):
+        e.step()
+    e.close()
+
+
+# ---- NCCL transport: one process per GPU
+def _nccl_worker(rank, world, uid, g, steps, q):
+    try:
+        cfg, ld = _cfg(g)
+        e = Engine(cfg, ld, device=rank)
+        e.strip_configure(rank, world)
+        e.strip_link_nccl(uid)
+        orc = OracleHierarchy(cfg, ld, 1234)   # only to produce the identical initial state
+        e.load_state(orc.state())
+        frames = _frames(g)
+        for t in range(steps):
+            e.set_inputs(frames[t % len(frames)])
+            e.step()
+        e.sync()
+        q.put((rank, e.spans, {k: v for k, v in e.state().items()}, e.get_predictions()))
+        e.close()
+    except Exception as ex:  # surface the failure in the parent
+        q.put((rank, None, repr(ex), None))
+
+
+def test_nccl_strips_match_the_whole_layer():
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g, world, steps = GEOMS[0], 2, 6
+    uid = nccl_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, uid, g, steps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    for r, spans, st, pred in got:
+        assert spans is not None, st
+    cfg, ld = _cfg(g)
+    orc = OracleHierarchy(cfg, ld, 1234)
+    frames = _frames(g)
+    for t in range(steps):
+        orc.set_inputs(frames[t % len(frames)])
+        orc.step(0.0)
+
+    class Part:  # what assemble_state needs from an engine
+        def __init__(self, spans, st):
+            self.cfg, self.layers, self.spans, self._st = cfg, ld, spans, st
+
+        def state(self, agent=0):
+            return self._st
+
+    probe = Engine(cfg, ld)
+    parts = [Part(s, st) for _, s, st, _ in got]
+    for p in parts:
+        p.conn_counts = probe.conn_counts
+    assert diff_states(orc.state(), assemble_state(parts)) == []
+    pred = assemble_rows([p for _, _, _, p in got], [s["OWN_VIS"] for _, s, _, _ in got], cfg.in_width)
+    assert np.array_equal(orc.get_predictions(), pred[0])
+    probe.close()
