@@ -190,6 +190,119 @@ def run_reference(args, rank, world):
     }))
 
 
+def c5_frames(size, n_frames=8, density=0.05, seed=7):
+    """sparse random binary frames (density 5 %, seed 7), period 8."""
+    rng = np.random.RandomState(seed)
+    return (rng.rand(n_frames, size * size) < density).astype(np.float32)
+
+
+def c5_bytes_per_step(eng, rho=0.0):
+    """SURVEY 8d, KWINNERS: 4 B per ff/rec/pred weight read once + 4*rho*(ff+rec) written back by
+    the winners-only learning rule; rho is negligible at sparsity 0.01 (the prediction delta rule
+    only touches units whose prediction was wrong)."""
+    n_ff, n_rec, n_pred = (eng.array_len(k, 0) for k in ("FF_W", "REC_W", "PRED_W"))
+    return 4 * (n_ff + n_rec + n_pred) + int(4 * rho * (n_ff + n_rec))
+
+
+def run_c5(args, rank, world, local_rank):
+    """--workload c5: ONE k-winners layer size x size over a size x size input, every radius 6
+    (BASELINE config 5), cut into `world` row strips, one per GPU, halos over NCCL send/recv.
+    Strong scaling: the layer is fixed, each GPU streams 1/world of the weights."""
+    import torch
+    import torch.distributed as dist
+    from bidinet_b200 import Engine, nccl_unique_id
+    from bidinet_b200 import config as cf
+
+    size, K, W = args.c5_size, args.steps, max(3, args.warmup)
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg, ld = cf.config_c5(size)
+    eng = Engine(cfg, ld, n_agents=1, device=local_rank)
+    if world > 1:
+        eng.strip_configure(rank, world)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        eng.strip_link_nccl(bytes(uid.cpu().numpy().tobytes()))
+    eng.init_random(1234)
+    frames = c5_frames(size)
+    T = len(frames)
+    eng.load_frames(frames[:, None, :])
+    t = 0
+    for _ in range(W):
+        eng.step_frame(t)
+        t += 1
+    eng.sync()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launch_count
+    eng.timer_start()
+    for _ in range(K):
+        eng.step_frame(t)
+        t += 1
+    ms = eng.timer_stop_ms()
+    eng.sync()
+    barrier()
+    launches = eng.launch_count - launches0
+    ms = _max_over_ranks(ms, dist if world > 1 else None, "cuda")
+    value = K / (ms * 1e-3)
+
+    # e2e: the whole frame goes to every part from host memory, the owned prediction rows come back
+    for _ in range(W):
+        eng.set_inputs(frames[t % T])
+        eng.step()
+        eng.get_predictions()
+        t += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        eng.set_inputs(frames[t % T])
+        eng.step()
+        pred = eng.get_predictions()
+        t += 1
+    eng.sync()
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, dist if world > 1 else None, "cuda")
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    step_bytes = c5_bytes_per_step(eng)
+    halo = eng.strip_halo_floats * 4 if world > 1 else 0
+    dev_bytes = eng.device_bytes
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak, peak_src = hbm_peak()
+    per_gpu = step_bytes / world
+    achieved = per_gpu / (ms / K * 1e-3) / 1e9
+    n_units = size * size
+    print(json.dumps({
+        "metric": "agent_steps_per_s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C5: one k-winners layer %dx%d over a %dx%d input, every radius 6, 1 agent" % (size, size, size, size),
+                   "units": n_units, "unit_updates_per_s": value * n_units, "learn": True,
+                   "parallelism": "%d row strips, one per GPU, halo rows over NCCL send/recv" % world if world > 1 else "one GPU, unsplit",
+                   "halo_bytes_sent_per_gpu_step": halo, "l2": "weights streamed per step: %.0f MB per GPU" % (per_gpu / 1e6),
+                   "state_bytes_per_gpu": dev_bytes},
+        "e2e": {"value": K / e2e_s, "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,
+                "h2d_bytes_per_step": int(4 * n_units), "d2h_bytes_per_step": int(4 * n_units)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "whole step (6 phase kernels + halo exchanges)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": per_gpu, "avg_launch_ms": ms / K, "launches_per_step": 1},
+        "clocks": clk,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,10 +314,15 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=1500)
     ap.add_argument("--profile-kernel", default="columns")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"])
+    ap.add_argument("--c5-size", type=int, default=1024)
     args = ap.parse_args()
     rank, world, local_rank = rank_info()
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "c5":
+        run_c5(args, rank, world, local_rank)
         return
 
     import torch

@@ -385,8 +385,12 @@ __global__ void k_predict(EngineDev P, LayerDev L, int l, int learn, long long u
       err = B[L.col.a_expl + i * 3 + 1] * err; // _learnPrediction gate, neo/Agent.cpp:181
     }
     const float kfb = L.learn_fb * err, kpr = L.learn_pred * err;
-    if (!top) for_each_conn(L.fb, ux, uy, [&](int s, int t) { wfb[(long long)s * U + i] += kfb * up_prev[t]; });
-    for_each_conn(L.pred, ux, uy, [&](int s, int t) { wpr[(long long)s * U + i] += kpr * sprev[t]; });
+    // w += k*src: a zero error or a zero source adds (+-0), which leaves w as it was, so
+    // those weights are neither read nor written (binary, sparse states: almost all of them)
+    if (err != 0.0f) {
+      if (!top) for_each_conn(L.fb, ux, uy, [&](int s, int t) { const float v = up_prev[t]; if (v != 0.0f) wfb[(long long)s * U + i] += kfb * v; });
+      for_each_conn(L.pred, ux, uy, [&](int s, int t) { const float v = sprev[t]; if (v != 0.0f) wpr[(long long)s * U + i] += kpr * v; });
+    }
   }
   float activation = 0.0f;
   if (!top) activation = dot_conn(L.fb, ux, uy, wfb, U, i, activation, [&](int t) { return up_state[t]; });
