@@ -1,0 +1,237 @@
+// bidi_columns16.cuh -- neo::Column::simStep (neo/Column.cpp:46-169) specialised for the
+// reference's default of 16 cells per column (neo/Agent.h:22), on the PLANAR pair record
+// (bidi_types.h, ColumnsDev).
+//
+// One warp owns one column pair and every lane is busy in every phase:
+//   lane = (column c = lane / 16, cell or input slot i = lane % 16).
+//   * sweep: lane (c, i) walks row i of column c's weights sequentially -- the
+//     reference's summation order -- four inputs per 128-bit shared-memory load; the
+//     products are packed (FFMA2), the running sum is one scalar FADD chain per lane.
+//     Rows are S = 4 (mod 8) floats apart, so the eight rows a quarter warp reads at once
+//     fall in distinct banks.
+//   * reconstruction and the element-wise weight update: lane (c, i) owns the input
+//     PAIRS i, i+16, ... of column c (64-bit accesses, packed arithmetic), looping only
+//     over its own column's spiking cells in ascending order.
+// The kernel is bound by instruction issue, not by HBM (profiles/r1_columns_notes.md), so
+// what matters is the number of warp instructions per pair: the cell count is a compile
+// time constant, and nothing is computed for a column that did not spike.
+//
+// Rounding rules are those of bidi_columns.cuh: no fused multiply-add anywhere.
+#pragma once
+#include "bidi_columns.cuh"
+
+namespace bidi {
+
+__device__ __forceinline__ float lo32(u64 v) { float x, y; upk(v, x, y); return x; }
+__device__ __forceinline__ float hi32(u64 v) { float x, y; upk(v, x, y); return y; }
+
+__global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l) {
+  extern __shared__ __align__(128) float smem[];
+  constexpr int CC = 16;
+  const ColumnsDev& C = L.col;
+  const Pair F{P.k_one2, P.k_negzero2, P.k_negone2};
+  const int lane = threadIdx.x, c = lane >> 4, i = lane & 15;
+  const int n_pairs = (C.n + 1) >> 1;
+  const long long task = blockIdx.x;
+  const int a = (int)(task / n_pairs), pair = (int)(task % n_pairs);
+  const int node = 2 * pair + c;
+  const bool has = node < C.n;
+  float* B = blob_of(P, a);
+
+  const int S = C.stride[pair];
+  const int R = C.rec_off[pair + 1] - C.rec_off[pair];
+  const int blk = R >> 1;
+  float* rec = smem;
+  float* in_s = smem + C.max_rec + c * C.max_s;          // gathered inputs of column c, [S], pad 0
+  float* st_s = smem + C.max_rec + 2 * C.max_s + c * CC;  // final cell states of column c
+  float* kf_s = st_s + 2 * CC;                            // feed-forward learning factors of column c
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C.max_rec + 2 * C.max_s + 4 * CC);
+  float* g_rec = B + C.rec_base + C.rec_off[pair];
+
+  // ---- the record starts on its way in (one TMA bulk copy)
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  if (lane == 0) {
+    mbar_expect_tx(bar, (uint32_t)R * 4u);
+    tma_load_1d(rec, g_rec, (uint32_t)R * 4u, bar);
+  }
+  // sections of column c's block
+  float* W = rec + c * blk;          // [16][S]
+  float* latT = W + CC * S;          // [16][16], latT[k][i] = lat[i][k]
+  float* v_thr = latT + CC * CC;
+  float* v_qw = v_thr + CC; float* v_qtr = v_qw + CC;
+  float* v_aw = v_qtr + CC;          // [3][16]
+  float* v_atr = v_aw + 3 * CC;
+  float* v_sprev = v_atr + 3 * CC;
+  float* err = v_sprev + CC;         // [S]
+  float* scal = err + S;             // [4]
+
+  // ---- gather column c's inputs while the copy is in flight (neo/Agent.cpp:159-169, :217-220)
+  const float reward = P.rewards[a];
+  float nz_u = 0.0f, nz_v = 0.0f;
+  const long long nk = ((long long)a * P.ncol + C.noise_base + node) * 3 + i;
+  if (has && i < 3) { nz_u = P.noise_u[nk]; nz_v = P.noise_v[nk]; }
+  {
+    const int in0 = has ? C.in_off[node] : 0;
+    const int nin = has ? C.in_off[node + 1] - in0 : 0;
+    const int* src = C.in_src + in0;
+    float* g_in = B + C.inputs + in0;
+    constexpr int GT = 9;  // 144 inputs per trip
+    for (int j0 = 0; j0 < S; j0 += 16 * GT) {
+      float gv[GT];
+#pragma unroll
+      for (int t = 0; t < GT; t++) { const int j = j0 + i + 16 * t; gv[t] = j < nin ? B[src[j]] : 0.0f; }
+#pragma unroll
+      for (int t = 0; t < GT; t++) {
+        const int j = j0 + i + 16 * t;
+        if (j < S) in_s[j] = gv[t];
+        if (j < nin) g_in[j] = gv[t];
+      }
+    }
+  }
+  __syncwarp();
+  mbar_wait(bar, 0);
+
+  // ---- iterate (neo/Column.cpp:58-103)
+  const float thr = v_thr[i];
+  float sp = v_sprev[i];
+  unsigned m = (__ballot_sync(0xffffffffu, sp != 0.0f) >> (16 * c)) & 0xffffu;  // column c's spiking cells
+  float act = 0.0f, st = 0.0f, counter = 0.0f, mult = 0.0f;
+  const float oml = 1.0f - C.leak;
+  const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(W + i * S);
+  const ulonglong2* e4 = reinterpret_cast<const ulonglong2*>(err);
+  const int n4 = S >> 2, n2 = S >> 1;
+  const u64* in2 = reinterpret_cast<const u64*>(in_s);
+  u64* err2 = reinterpret_cast<u64*>(err);
+  constexpr int NP = 5;  // input pairs per lane per trip: 16*5*2 = 160 inputs
+  for (int it = 0; it < C.iter; it++) {
+    // excitation += w * err, sequentially over the inputs
+    float exc = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < n4; j++) {
+      const ulonglong2 w = w4[j], e = e4[j];
+      const u64 p01 = F.mul(w.x, e.x), p23 = F.mul(w.y, e.y);
+      exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+    }
+    // inhibition += lat * spikePrev over the cells that spiked (the others add +-0)
+    float inh = 0.0f;
+    for (unsigned mm = m; mm; mm &= mm - 1) inh += latT[(__ffs(mm) - 1) * CC + i];
+    float av = oml * act + exc - inh;
+    if (av > thr) { av = 0.0f; sp = 1.0f; } else sp = 0.0f;
+    st += sp;
+    act = av;
+    m = (__ballot_sync(0xffffffffu, sp != 0.0f) >> (16 * c)) & 0xffffu;  // also orders the err reads above
+    counter += 1.0f;
+    mult = 1.0f / counter;
+    // reconstruction from the spiking cells, ascending cell index (neo/Column.cpp:93-102):
+    // recon += (spike*multiplier) * w ; error = input - recon
+    const u64 mult2 = pk(mult, mult);
+    for (int p0 = 0; p0 < n2; p0 += 16 * NP) {
+      float rx[NP], ry[NP];
+#pragma unroll
+      for (int t = 0; t < NP; t++) { rx[t] = 0.0f; ry[t] = 0.0f; }
+      for (unsigned mm = m; mm; mm &= mm - 1) {
+        const u64* row = reinterpret_cast<const u64*>(W + (__ffs(mm) - 1) * S) + p0 + i;
+#pragma unroll
+        for (int t = 0; t < NP; t++)
+          if (p0 + i + 16 * t < n2) {
+            const u64 pr = F.mul(mult2, row[16 * t]);
+            rx[t] += lo32(pr); ry[t] += hi32(pr);
+          }
+      }
+#pragma unroll
+      for (int t = 0; t < NP; t++) {
+        const int p = p0 + i + 16 * t;
+        if (p < n2) err2[p] = F.sub2(in2[p], pk(rx[t], ry[t]));
+      }
+    }
+    __syncwarp();
+  }
+  st *= mult;
+  st_s[i] = st;
+  __syncwarp();
+
+  // ---- value and actions, sequential over the cells (neo/Column.cpp:111-123):
+  // lanes 0..2 of each half accumulate one action each, lane 3 the value
+  float accum = 0.0f;
+  if (i < 4) {
+    const float* wv = i < 3 ? v_aw + i * CC : v_qw;
+#pragma unroll
+    for (int k = 0; k < CC; k++) accum += wv[k] * st_s[k];
+  }
+  const float q = __shfl_sync(0xffffffffu, accum, 16 * c + 3);
+  float as = 0.0f, ae = 0.0f;
+  if (i < 3) {
+    as = bidi_sigmoid(accum);
+    ae = nz_u < C.expl_break ? nz_v : bidi_clamp01(as + nz_v);
+    if (has) {
+      B[C.a_state + node * 3 + i] = as;
+      B[C.a_expl + node * 3 + i] = ae;
+      P.col_actions[nk] = ae;
+    }
+  }
+  // tdError = reward + gamma*q - prevValue
+  const float td = reward + C.gamma * q - scal[0];
+  const float q_alpha_td = C.a_q * td, act_alpha_td = C.a_act * td;
+  const float gl = C.gamma_lambda;
+
+  // ---- learning (neo/Column.cpp:139-166), all inside the shared-memory record
+  {
+    const float tr = v_qtr[i];
+    v_qw[i] = v_qw[i] + q_alpha_td * tr;
+    v_qtr[i] = tr * gl + st;
+  }
+#pragma unroll
+  for (int ai = 0; ai < 3; ai++) {
+    const float as_i = __shfl_sync(0xffffffffu, as, 16 * c + ai), ae_i = __shfl_sync(0xffffffffu, ae, 16 * c + ai);
+    const float tr = v_atr[ai * CC + i];
+    v_aw[ai * CC + i] = v_aw[ai * CC + i] + act_alpha_td * tr;
+    v_atr[ai * CC + i] = tr * gl + (ae_i - as_i) * st;
+  }
+  // feed-forward: w[r][j] += (alpha*state_r)*err_j for the cells with state_r > 0
+  kf_s[i] = C.a_ff * st;
+  __syncwarp();
+  const unsigned live = (__ballot_sync(0xffffffffu, st > 0.0f) >> (16 * c)) & 0xffffu;
+  for (int p0 = 0; p0 < n2; p0 += 16 * NP) {
+    u64 e2[NP];
+#pragma unroll
+    for (int t = 0; t < NP; t++) { const int p = p0 + i + 16 * t; e2[t] = p < n2 ? err2[p] : 0ull; }
+    for (unsigned mm = live; mm; mm &= mm - 1) {
+      const int r = __ffs(mm) - 1;
+      const float kf = kf_s[r];
+      const u64 k2 = pk(kf, kf);
+      u64* row = reinterpret_cast<u64*>(W + r * S) + p0 + i;
+#pragma unroll
+      for (int t = 0; t < NP; t++)
+        if (p0 + i + 16 * t < n2) row[16 * t] = F.add2(F.mul(k2, e2[t]), row[16 * t]);
+    }
+  }
+  // lateral: lat[i][r] = max(0, lat[i][r] + alpha*(state_i*state_r - sparsity^2)), every (i, r)
+  {
+    const float sp2 = C.sparsity * C.sparsity;
+#pragma unroll
+    for (int r = 0; r < CC; r++) {
+      float* p = latT + r * CC + i;
+      *p = bidi_max(0.0f, *p + C.a_lat * (st * st_s[r] - sp2));
+    }
+  }
+  // threshold += alpha*(state - sparsity)
+  v_thr[i] = thr + C.a_thr * (st - C.sparsity);
+  v_sprev[i] = sp;
+  if (has) {
+    const int cb = node * CC + i;
+    B[C.act + cb] = act; B[C.spike + cb] = sp; B[C.state + cb] = st;
+  }
+  __syncwarp();  // every lane has read prevValue
+  if (i == 0) scal[0] = q;
+
+  // ---- record back to HBM (one TMA bulk copy)
+  fence_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_1d(g_rec, rec, (uint32_t)R * 4u);
+    tma_store_commit_and_wait();
+  }
+}
+
+} // namespace bidi

@@ -39,21 +39,33 @@ struct ColumnsHost {
 struct ColRec {
   float *W, *latT, *thr, *q_w, *q_tr, *a_w, *a_tr, *sprev, *err, *scal;
   int S, Cq, nin;
+  int es;  // element stride: 2 in the pair-interleaved layout, 1 in the planar one
 };
 ColRec col_rec(const ColumnsDev& C, const ColumnsHost& H, float* blob, int node) {
   ColRec r;
   const int pair = node >> 1, half = node & 1;
   r.S = H.stride[pair]; r.Cq = C.cq; r.nin = H.in_off[node + 1] - H.in_off[node];
-  r.W = blob + C.rec_base + H.rec_off[pair] + half;
-  r.latT = r.W + 2LL * C.cells * r.S;
-  r.thr = r.latT + 2 * C.cells * C.cq;
-  r.q_w = r.thr + 2 * C.cq; r.q_tr = r.q_w + 2 * C.cq; r.a_w = r.q_tr + 2 * C.cq; r.a_tr = r.a_w + 6 * C.cq;
-  r.sprev = r.a_tr + 6 * C.cq; r.err = r.sprev + 2 * C.cq; r.scal = r.err + 2 * r.S;
+  const int block = C.cells * r.S + C.cells * C.cq + 10 * C.cq + r.S + 4;  // floats of ONE column
+  r.es = C.planar ? 1 : 2;
+  // planar: column 2p's block, then column 2p+1's; interleaved: element k of a section is ptr[2*k]
+  r.W = blob + C.rec_base + H.rec_off[pair] + (C.planar ? half * block : half);
+  const int e = r.es;
+  r.latT = r.W + (long long)e * C.cells * r.S;
+  r.thr = r.latT + e * C.cells * C.cq;
+  r.q_w = r.thr + e * C.cq; r.q_tr = r.q_w + e * C.cq; r.a_w = r.q_tr + e * C.cq; r.a_tr = r.a_w + 3 * e * C.cq;
+  r.sprev = r.a_tr + 3 * e * C.cq; r.err = r.sprev + e * C.cq; r.scal = r.err + e * r.S;
   return r;
 }
-// common row stride of a column pair: >= nIn of both, even, with stride/2 odd so that
-// lane i's 128-bit shared-memory loads of row i (2*stride floats apart) never conflict
-int column_pair_stride(int nin) {
+// common row stride of a column pair, >= nIn of both.
+// interleaved layout: even, with stride/2 odd so that lane i's 128-bit shared-memory loads of
+// row i (2*stride floats apart) never conflict.  planar layout: stride = 4 (mod 8), so that
+// the 128-bit loads of rows 0..7 (one per lane of a quarter warp) fall in distinct banks.
+int column_pair_stride(int nin, bool planar) {
+  if (planar) {
+    int s = std::max(4, (nin + 3) / 4 * 4);
+    if ((s & 7) != 4) s += 4;
+    return s;
+  }
   int s = std::max(2, (nin + 1) / 2 * 2);
   if (((s / 2) & 1) == 0) s += 2;
   return s;
@@ -318,15 +330,15 @@ template <class F> void walk_column(const bidi_engine* h, int which, int layer, 
   for (int node = 0; node < C.n; node++) {
     const ColRec r = col_rec(C, H, blob, node);
     switch (which) {
-      case BIDI_COL_RECON_ERR: for (int j = 0; j < r.nin; j++) f(r.err[2 * j]); break;
-      case BIDI_COL_FF_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < r.nin; j++) f(r.W[2 * ((long long)i * r.S + j)]); break;
-      case BIDI_COL_LAT_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < C.cells; j++) f(r.latT[2 * (j * r.Cq + i)]); break;
-      case BIDI_COL_THRESHOLD: for (int i = 0; i < C.cells; i++) f(r.thr[2 * i]); break;
-      case BIDI_COL_SPIKE_PREV: for (int i = 0; i < C.cells; i++) f(r.sprev[2 * i]); break;
-      case BIDI_COL_Q_W: for (int i = 0; i < C.cells; i++) f(r.q_w[2 * i]); break;
-      case BIDI_COL_Q_TRACE: for (int i = 0; i < C.cells; i++) f(r.q_tr[2 * i]); break;
-      case BIDI_COL_ACT_W: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_w[2 * (a * r.Cq + i)]); break;
-      case BIDI_COL_ACT_TRACE: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_tr[2 * (a * r.Cq + i)]); break;
+      case BIDI_COL_RECON_ERR: for (int j = 0; j < r.nin; j++) f(r.err[r.es * j]); break;
+      case BIDI_COL_FF_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < r.nin; j++) f(r.W[r.es * ((long long)i * r.S + j)]); break;
+      case BIDI_COL_LAT_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < C.cells; j++) f(r.latT[r.es * (j * r.Cq + i)]); break;
+      case BIDI_COL_THRESHOLD: for (int i = 0; i < C.cells; i++) f(r.thr[r.es * i]); break;
+      case BIDI_COL_SPIKE_PREV: for (int i = 0; i < C.cells; i++) f(r.sprev[r.es * i]); break;
+      case BIDI_COL_Q_W: for (int i = 0; i < C.cells; i++) f(r.q_w[r.es * i]); break;
+      case BIDI_COL_Q_TRACE: for (int i = 0; i < C.cells; i++) f(r.q_tr[r.es * i]); break;
+      case BIDI_COL_ACT_W: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_w[r.es * (a * r.Cq + i)]); break;
+      case BIDI_COL_ACT_TRACE: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_tr[r.es * (a * r.Cq + i)]); break;
       case BIDI_COL_PREV_VALUE: f(r.scal[0]); break;
     }
   }
@@ -400,7 +412,8 @@ void record_columns(Recorder& R, int l) {
   const long long warps = (long long)h->A * ((n_pairs + ppw - 1) / ppw);
   const size_t smem = columns_smem_bytes(C);
   R.before("columns");
-  if (ppw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  if (C.planar) bidi::k_columns16<<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  else if (ppw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   R.after("columns");
   R.kernels++;
@@ -694,6 +707,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       H.col.rec_off.assign(n_pairs + 1, 0);
       H.col.stride.assign(n_pairs, 0);
       C.cq = (C.cells + 3) / 4 * 4;
+      C.planar = C.cells == 16 ? 1 : 0;  // the reference's default size runs the specialised kernel (bidi_columns16.cuh)
       C.max_in = C.max_s = C.max_rec = 0;
       for (int i = 0; i < C.n; i++) {
         const int ux = i % H.fb.d.uw, uy = i / H.fb.d.uw;
@@ -707,7 +721,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       for (int p = 0; p < n_pairs; p++) {
         const int na = H.col.in_off[2 * p + 1] - H.col.in_off[2 * p];
         const int nb = 2 * p + 1 < C.n ? H.col.in_off[2 * p + 2] - H.col.in_off[2 * p + 1] : 0;
-        const int S = column_pair_stride(std::max(na, nb));
+        const int S = column_pair_stride(std::max(na, nb), C.planar != 0);
         const int rec = 2 * (C.cells * S + C.cells * C.cq + 10 * C.cq + S + 4);
         H.col.rec_off[p + 1] = H.col.rec_off[p] + rec;
         H.col.stride[p] = S;
@@ -839,7 +853,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       if (V == BIDI_NEO_AGENT)
         for (int node = 0; node < D.col.n; node++) {
           const ColRec r = col_rec(D.col, h->hl[l].col, img.data(), node);
-          for (int i = 0; i < D.col.cells; i++) r.thr[2 * i] = cfg->init_threshold;
+          for (int i = 0; i < D.col.cells; i++) r.thr[r.es * i] = cfg->init_threshold;
         }
     }
     for (int a = 0; a < n_agents; a++)
@@ -888,6 +902,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     if (smem > 227 * 1024) return bail(BIDI_EINVAL, "bidi_create: a column record does not fit in shared memory");
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   *out = h;
   return BIDI_OK;
@@ -1002,13 +1017,13 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
     auto draw_column = [&](const ColumnsDev& C, const ColumnsHost& CH, int node) { // neo/Column.cpp:22-43
       const ColRec r = col_rec(C, CH, img.data(), node);
       for (int i = 0; i < C.cells; i++) {
-        r.thr[2 * i] = g.init_threshold;
-        for (int j = 0; j < r.nin; j++) r.W[2 * ((long long)i * r.S + j)] = weightDist(gen);
-        for (int j = 0; j < C.cells; j++) r.latT[2 * (j * r.Cq + i)] = inhibitionDist(gen);
-        r.q_w[2 * i] = weightDist(gen);
+        r.thr[r.es * i] = g.init_threshold;
+        for (int j = 0; j < r.nin; j++) r.W[r.es * ((long long)i * r.S + j)] = weightDist(gen);
+        for (int j = 0; j < C.cells; j++) r.latT[r.es * (j * r.Cq + i)] = inhibitionDist(gen);
+        r.q_w[r.es * i] = weightDist(gen);
       }
       for (int a = 0; a < 3; a++)
-        for (int k = 0; k < C.cells; k++) r.a_w[2 * (a * r.Cq + k)] = weightDist(gen);
+        for (int k = 0; k < C.cells; k++) r.a_w[r.es * (a * r.Cq + k)] = weightDist(gen);
     };
     for (int l = 0; l <= L; l++) {
       if (l == L && V == BIDI_KWINNERS) break;

@@ -511,3 +511,4 @@ __global__ void k_feedback(EngineDev P, int n, const int* __restrict__ src, cons
 } // namespace bidi
 
 #include "bidi_columns.cuh"
+#include "bidi_columns16.cuh"

@@ -60,11 +60,16 @@ struct WinDev {
 //   err2[S][2]          _reconstructionError
 //   scal2[4][2]         prevValue, pad
 // A layer with an odd number of nodes ends with a phantom column of zeros.
+// Columns of 16 cells (the reference's default, neo/Agent.h:22) use the PLANAR variant of
+// the record instead: column 2p's block followed by column 2p+1's, each block holding the
+// same sections in the same order without the [2] interleave, W rows S floats apart with
+// S = 4 (mod 8).  bidi_columns16.cuh works on it with lane = (column, cell).
 // Write-only per-step outputs (inputs, activation, spike, state, action states) stay
 // in plain planes.
 struct ColumnsDev {
   int n, cells, cq, tot_in; // nodes, cells per column, cells rounded up to 4, sum of nIn
   int max_in;               // largest nIn
+  int planar;               // record layout: 0 pair-interleaved (k_columns), 1 planar (k_columns16)
   int max_s, max_rec;       // largest pair stride / pair record length (floats)
   const int* in_off;        // [n+1] prefix sums of nIn (same for every agent)
   const int* in_src;        // [tot_in] blob offset each column input is gathered from (neo/Agent.cpp:159-169)
