@@ -18,6 +18,7 @@
 
 #include "bidi_kernels.cuh"
 #include "bidi_coder.cuh"
+#include "bidi_coder_dense.cuh"
 #include "bidi_tiles.cuh"
 
 namespace {
@@ -87,7 +88,7 @@ struct bidi_engine {
   long long stride = 0;            // floats per agent blob
   std::vector<int> coder_cta;      // per layer: the fused one-CTA-per-agent coder kernel applies
   std::vector<int> tiled;          // per node layer: few threads, use the cooperative tile kernels (bidi_tiles.cuh)
-  bool force_phase_kernels = false;
+  bool force_phase_kernels = false, no_dense_coder = false;
   EngineDev P;                     // kernel argument
   // device memory
   float* d_blob = nullptr; float* d_in0 = nullptr; float* d_pred = nullptr;
@@ -471,11 +472,19 @@ void record_step(Recorder& R, bool learn) {
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
     if (h->coder_cta[l] && !h->force_phase_kernels) { // whole up pass of the layer in one launch
-      const int threads = std::min(512, std::max(64, (ly[l].nv + ly[l].nh + 31) / 32 * 32));
-      const size_t smem = sizeof(float) * (size_t)bidi::coder_cta_shape(ly[l]).floats;
+      const long long nxt = l < L - 1 ? ly[l + 1].vis_input : -1LL;
       R.before("coder");
-      if (V == BIDI_ITERATIVE) bidi::k_coder_cta<0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, l < L - 1 ? ly[l + 1].vis_input : -1LL);
-      else bidi::k_coder_cta<1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, l < L - 1 ? ly[l + 1].vis_input : -1LL);
+      if (h->coder_cta[l] == 2) {  // windows span the grid: dense rows (bidi_coder_dense.cuh)
+        const int threads = bidi::coder_dense_threads(ly[l]);
+        const size_t smem = sizeof(float) * (size_t)bidi::coder_dense_shape(ly[l]).floats;
+        if (V == BIDI_ITERATIVE) bidi::k_coder_dense<0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+        else bidi::k_coder_dense<1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+      } else {
+        const int threads = std::min(512, std::max(64, (ly[l].nv + ly[l].nh + 31) / 32 * 32));
+        const size_t smem = sizeof(float) * (size_t)bidi::coder_cta_shape(ly[l]).floats;
+        if (V == BIDI_ITERATIVE) bidi::k_coder_cta<0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+        else bidi::k_coder_cta<1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+      }
       R.after("coder");
       R.kernels++;
       continue;
@@ -863,14 +872,20 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   // layers whose planes fit in shared memory use the fused coder kernel
   h->coder_cta.assign(L, 0);
   if (V != BIDI_KWINNERS) {
-    size_t smem = 0;
+    size_t smem = 0, smem_dense = 0;
     for (int l = 0; l < L; l++) {
       const size_t need = sizeof(float) * (size_t)bidi::coder_cta_shape(h->layers[l]).floats;
-      if (need <= 200 * 1024) { h->coder_cta[l] = 1; smem = std::max(smem, need); }
+      const size_t need_dense = sizeof(float) * (size_t)bidi::coder_dense_shape(h->layers[l]).floats;
+      if (bidi::coder_dense_applies(h->layers[l]) && need_dense <= 200 * 1024 && !h->no_dense_coder) { h->coder_cta[l] = 2; smem_dense = std::max(smem_dense, need_dense); }
+      else if (need <= 200 * 1024) { h->coder_cta[l] = 1; smem = std::max(smem, need); }
     }
     if (smem > 0) {
       CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_cta<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_cta<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (smem_dense > 0) {
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
     }
   }
   // node layers with few (agent, unit) threads use the cooperative tile kernels
@@ -1183,6 +1198,20 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   CU(cudaStreamSynchronize(h->stream));
   if (std::string(name) == "force_phase_kernels") h->force_phase_kernels = value != 0;
   else if (std::string(name) == "tile_kernels") { if (!value) std::fill(h->tiled.begin(), h->tiled.end(), 0); }
+  else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
+    if (!value) {
+      size_t smem = 0;
+      for (int l = 0; l < h->L; l++) {
+        const size_t need = sizeof(float) * (size_t)bidi::coder_cta_shape(h->layers[l]).floats;
+        if (h->coder_cta[l] == 2) h->coder_cta[l] = need <= 200 * 1024 ? 1 : 0;
+        if (h->coder_cta[l] == 1) smem = std::max(smem, need);
+      }
+      if (smem > 0) {
+        CU(cudaFuncSetAttribute(bidi::k_coder_cta<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(bidi::k_coder_cta<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      }
+    }
+  }
   else return fail(h, BIDI_EINVAL, "bidi_set_option: unknown option");
   for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   return BIDI_OK;

@@ -42,18 +42,22 @@ def test_init_random_matches_oracle(case):
         assert diff_states(orc.state(), eng.state(agent=a)) == [], "agent %d" % a
 
 
-@pytest.mark.parametrize("path", ["default", "per_phase_tiles", "per_phase_threads"])
+@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads"])
 @pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
 def test_free_running_parity(case, path):
     """N steps from an identical state, no re-synchronisation: exact after every step.
     Every engine path is held to it: the default (fused per-agent coder kernel where the
-    layer fits in shared memory, cooperative tile kernels for small launches), one
+    layer fits in shared memory -- its dense-row form where the windows span the grid --
+    and cooperative tile kernels for small launches), the general fused coder kernel
+    everywhere, one
     kernel per phase with the tile kernels (large single agents), and one kernel per
     phase with one thread per unit (large agent batches, very large layers)."""
     name, cfg, ld, frame, reward = case
     orc = OracleHierarchy(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1)
-    if path != "default":
+    if path == "fused_general":
+        eng.set_option("dense_coder", False)
+    elif path != "default":
         eng.set_option("force_phase_kernels", True)
     if path == "per_phase_threads":
         eng.set_option("tile_kernels", False)
