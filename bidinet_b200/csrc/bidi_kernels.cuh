@@ -64,6 +64,39 @@ __device__ __forceinline__ void for_each_conn(const WinDev& w, int ux, int uy, F
   }
 }
 
+// Element-wise learning rules over EVERY slot of the box, NB slots at a time: all of a
+// batch's loads (load(slot, clamped target) -> V) are issued before the first store
+// (store(slot, V, valid)), so one memory round trip serves NB connections instead of one.
+// Loads are unconditional (the target index is clamped into the grid); only the stores are
+// predicated, which keeps the slots a unit does not own at 0.
+template <int NB, class V, class LoadF, class StoreF>
+__device__ __forceinline__ void for_each_slot_batched(const WinDev& w, int ux, int uy, LoadF&& load, StoreF&& store) {
+  if (w.r < 0) return;
+  const SlotBox b = slot_box(w, ux, uy);
+  for (int sx = 0; sx < w.dxn; sx++) {
+    const bool okx = sx >= b.sx0 && sx <= b.sx1;
+    const int txr = slot_tx(w, b, sx), tx = min(max(txr, 0), w.tw - 1);
+    for (int sy0 = 0; sy0 < w.dyn; sy0 += NB) {
+      V v[NB];
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int sy = min(sy0 + q, w.dyn - 1);
+        const int ty = min(max(slot_ty(w, b, sy), 0), w.th - 1);
+        v[q] = load(sx * w.dyn + sy, tx + ty * w.tw);
+      }
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int sy = sy0 + q, tyr = slot_ty(w, b, sy);
+        bool ok = okx && sy < w.dyn && sy >= b.sy0 && sy <= b.sy1;
+        if (w.excl && txr == b.cx && tyr == b.cy) ok = false;
+        if (ok) store(sx * w.dyn + sy, v[q]);
+      }
+    }
+  }
+}
+struct WE { float w, e; };
+struct WTE { float w, tr, e; };
+
 // sum += src(target) * w[slot][unit] over the WHOLE slot box, in the reference's list
 // order, with no per-slot test: the slot planes hold 0 wherever the unit has no
 // connection (off-grid, outside the radius, excluded centre), the target index is
@@ -285,14 +318,13 @@ __global__ void k_ic_finish(EngineDev P, LayerDev L, int l, int scale_state, flo
 
 // lateral anti-Hebbian + threshold homeostasis: sdr/IRSDR.cpp:313-317
 __device__ __forceinline__ void ic_learn_tail(const LayerDev& L, float* B, int i, int ux, int uy) {
-  const float* state = B + L.state;
-  float* wlat = B + L.lat.w_off;
+  const float* __restrict__ state = B + L.state;
+  float* __restrict__ wlat = B + L.lat.w_off;
   const float si = state[i], sp2 = L.sparsity * L.sparsity;
   const int U = L.nh;
-  for_each_conn(L.lat, ux, uy, [&](int s, int t) {
-    const long long k = (long long)s * U + i;
-    wlat[k] = bidi_max(0.0f, wlat[k] + L.learn_lat * (si * state[t] - sp2));
-  });
+  for_each_slot_batched<8, WE>(L.lat, ux, uy,
+      [&](int s, int t) { return WE{wlat[(long long)s * U + i], state[t]}; },
+      [&](int s, const WE& v) { wlat[(long long)s * U + i] = bidi_max(0.0f, v.w + L.learn_lat * (si * v.e - sp2)); });
   B[L.thr + i] = bidi_max(0.0f, B[L.thr + i] + (si - L.sparsity) * L.learn_threshold);
 }
 
@@ -300,24 +332,26 @@ __device__ __forceinline__ void ic_learn_tail(const LayerDev& L, float* B, int i
 __global__ void k_ic_learn(EngineDev P, LayerDev L, int l) {
   BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
-  const float* x = vis_input_of(P, L, l, a);
-  const float* vrec = B + L.vis_recon;
-  const float* sprev = B + L.state_prev;
-  const float* hrec = B + L.recon;
-  float* wff = B + L.ff.w_off;
-  float* wrec = B + L.rec.w_off;
+  const float* __restrict__ x = vis_input_of(P, L, l, a);
+  const float* __restrict__ vrec = B + L.vis_recon;
+  const float* __restrict__ sprev = B + L.state_prev;
+  const float* __restrict__ hrec = B + L.recon;
+  float* __restrict__ wff = B + L.ff.w_off;
+  float* __restrict__ wrec = B + L.rec.w_off;
   const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
   const float learn = B[L.state + i], maxd = L.max_weight_delta, decay = L.weight_decay;
-  for_each_conn(L.ff, ux, uy, [&](int s, int t) {
-    const long long k = (long long)s * U + i;
-    const float delta = L.learn_ff * learn * (x[t] - vrec[t]) - decay * wff[k];
-    wff[k] += bidi_min(maxd, bidi_max(-maxd, delta));
-  });
-  for_each_conn(L.rec, ux, uy, [&](int s, int t) {
-    const long long k = (long long)s * U + i;
-    const float delta = L.learn_rec * learn * (sprev[t] - hrec[t]) - decay * wrec[k];
-    wrec[k] += bidi_min(maxd, bidi_max(-maxd, delta));
-  });
+  for_each_slot_batched<8, WE>(L.ff, ux, uy,
+      [&](int s, int t) { return WE{wff[(long long)s * U + i], x[t] - vrec[t]}; },
+      [&](int s, const WE& v) {
+        const float delta = L.learn_ff * learn * v.e - decay * v.w;
+        wff[(long long)s * U + i] = v.w + bidi_min(maxd, bidi_max(-maxd, delta));
+      });
+  for_each_slot_batched<8, WE>(L.rec, ux, uy,
+      [&](int s, int t) { return WE{wrec[(long long)s * U + i], sprev[t] - hrec[t]}; },
+      [&](int s, const WE& v) {
+        const float delta = L.learn_rec * learn * v.e - decay * v.w;
+        wrec[(long long)s * U + i] = v.w + bidi_min(maxd, bidi_max(-maxd, delta));
+      });
   ic_learn_tail(L, B, i, ux, uy);
 }
 
@@ -326,12 +360,12 @@ __global__ void k_ic_learn(EngineDev P, LayerDev L, int l) {
 __global__ void k_neo_learn(EngineDev P, LayerDev L, int l) {
   BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
-  const float* x = vis_input_of(P, L, l, a);
-  const float* vrec = B + L.vis_recon;
-  const float* sprev = B + L.state_prev;
-  const float* hrec = B + L.recon;
-  float* wff = B + L.ff.w_off; float* tff = B + L.ff.tr_off;
-  float* wrec = B + L.rec.w_off; float* trec = B + L.rec.tr_off;
+  const float* __restrict__ x = vis_input_of(P, L, l, a);
+  const float* __restrict__ vrec = B + L.vis_recon;
+  const float* __restrict__ sprev = B + L.state_prev;
+  const float* __restrict__ hrec = B + L.recon;
+  float* __restrict__ wff = B + L.ff.w_off; float* __restrict__ tff = B + L.ff.tr_off;
+  float* __restrict__ wrec = B + L.rec.w_off; float* __restrict__ trec = B + L.rec.tr_off;
   const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
   const float learn = B[L.state + i], maxd = L.max_weight_delta, decay = L.weight_decay;
   const float err = learn - B[L.p_state_prev + i];
@@ -339,20 +373,22 @@ __global__ void k_neo_learn(EngineDev P, LayerDev L, int l) {
   const float base = B[L.p_baseline + i];
   const float reward = bidi_sigmoid(L.sensitivity * (error2 - base));
   B[L.p_baseline + i] = (1.0f - L.baseline_decay) * base + L.baseline_decay * error2;
-  for_each_conn(L.ff, ux, uy, [&](int s, int t) {
-    const long long k = (long long)s * U + i;
-    const float tr = tff[k];
-    const float delta = L.learn_ff * reward * tr - decay * wff[k];
-    wff[k] += bidi_min(maxd, bidi_max(-maxd, delta));
-    tff[k] = L.lambda * tr + learn * (x[t] - vrec[t]);
-  });
-  for_each_conn(L.rec, ux, uy, [&](int s, int t) {
-    const long long k = (long long)s * U + i;
-    const float tr = trec[k];
-    const float delta = L.learn_rec * reward * tr - decay * wrec[k];
-    wrec[k] += bidi_min(maxd, bidi_max(-maxd, delta));
-    trec[k] = L.lambda * tr + learn * (sprev[t] - hrec[t]);
-  });
+  for_each_slot_batched<8, WTE>(L.ff, ux, uy,
+      [&](int s, int t) { const long long k = (long long)s * U + i; return WTE{wff[k], tff[k], x[t] - vrec[t]}; },
+      [&](int s, const WTE& v) {
+        const long long k = (long long)s * U + i;
+        const float delta = L.learn_ff * reward * v.tr - decay * v.w;
+        wff[k] = v.w + bidi_min(maxd, bidi_max(-maxd, delta));
+        tff[k] = L.lambda * v.tr + learn * v.e;
+      });
+  for_each_slot_batched<8, WTE>(L.rec, ux, uy,
+      [&](int s, int t) { const long long k = (long long)s * U + i; return WTE{wrec[k], trec[k], sprev[t] - hrec[t]}; },
+      [&](int s, const WTE& v) {
+        const long long k = (long long)s * U + i;
+        const float delta = L.learn_rec * reward * v.tr - decay * v.w;
+        wrec[k] = v.w + bidi_min(maxd, bidi_max(-maxd, delta));
+        trec[k] = L.lambda * v.tr + learn * v.e;
+      });
   ic_learn_tail(L, B, i, ux, uy);
 }
 
