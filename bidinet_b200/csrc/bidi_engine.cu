@@ -20,6 +20,7 @@
 #include "bidi_coder.cuh"
 #include "bidi_coder_dense.cuh"
 #include "bidi_tiles.cuh"
+#include "bidi_grid.cuh"
 
 namespace {
 
@@ -89,6 +90,10 @@ struct bidi_engine {
   std::vector<int> coder_cta;      // per layer: the fused one-CTA-per-agent coder kernel applies
   std::vector<int> tiled;          // per node layer: few threads, use the cooperative tile kernels (bidi_tiles.cuh)
   bool force_phase_kernels = false, no_dense_coder = false;
+  // per layer: the 2-D tile kernels of bidi_grid.cuh apply (large k-winners layers); shared-memory floats they stage
+  struct GridSizes { int on, ff, rec, lat, fb, pred, gather; };
+  std::vector<GridSizes> gridk;
+  int grid_mode = 1;               // 0 off, 1 layers at least 16 units wide that are not tiled, 2 every layer
   EngineDev P;                     // kernel argument
   // device memory
   float* d_blob = nullptr; float* d_in0 = nullptr; float* d_pred = nullptr;
@@ -420,6 +425,43 @@ void record_columns(Recorder& R, int l) {
   R.kernels++;
 }
 
+template <class K, class... Args>
+void launch_grid(Recorder& R, const char* name, K kernel, long long blocks, size_t smem_floats, Args... args) {
+  if (blocks <= 0) return;
+  R.before(name);
+  kernel<<<(unsigned)blocks, GRID_TX * GRID_TY, sizeof(float) * smem_floats, R.h->stream>>>(R.h->P, args...);
+  R.after(name);
+  R.kernels++;
+}
+// which layers run the 2-D tile kernels, and how much shared memory they stage
+int select_grid_kernels(bidi_engine* h) {
+  h->gridk.assign(h->L, bidi_engine::GridSizes{0, 0, 0, 0, 0, 0, 0});
+  if (h->cfg.variant != BIDI_KWINNERS || h->grid_mode == 0) return BIDI_OK;
+  size_t most = 0;
+  for (int l = 0; l < h->L; l++) {
+    const LayerHost& H = h->hl[l];
+    bidi_engine::GridSizes g;
+    g.ff = bidi::grid_box_floats(H.ff.d, H.ff.cx.data(), H.ff.cy.data());
+    g.rec = bidi::grid_box_floats(H.rec.d, H.rec.cx.data(), H.rec.cy.data());
+    g.lat = bidi::grid_box_floats(H.lat.d, H.lat.cx.data(), H.lat.cy.data());
+    g.fb = bidi::grid_box_floats(H.fb.d, H.fb.cx.data(), H.fb.cy.data());
+    g.pred = bidi::grid_box_floats(H.pred.d, H.pred.cx.data(), H.pred.cy.data());
+    g.gather = std::max(bidi::grid_gather_floats(H.ff.d, H.ff.gxlo.data(), H.ff.gxhi.data(), H.ff.gylo.data(), H.ff.gyhi.data()),
+                        bidi::grid_gather_floats(H.rec.d, H.rec.gxlo.data(), H.rec.gxhi.data(), H.rec.gylo.data(), H.rec.gyhi.data()));
+    const size_t need = sizeof(float) * (size_t)std::max({g.ff + g.rec, g.lat, g.fb + g.pred, g.gather});
+    g.on = need <= 160 * 1024 && (h->grid_mode == 2 || (!h->tiled[l] && h->layers[l].hw >= 16)) ? 1 : 0;
+    if (g.on) most = std::max(most, need);
+    h->gridk[l] = g;
+  }
+  if (most > 48 * 1024) {
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_activate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_inhibit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+    CU(cudaFuncSetAttribute(bidi::k_g_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+  }
+  return BIDI_OK;
+}
+
 // One simStep as a sequence of kernel launches on h->stream (captured into a graph).
 void record_step(Recorder& R, bool learn) {
   bidi_engine* h = R.h;
@@ -431,7 +473,13 @@ void record_step(Recorder& R, bool learn) {
     for (int l = 0; l < L; l++) {
       const LayerDev& Y = ly[l];
       const long long nxt = l < L - 1 ? ly[l + 1].vis_input : -1LL;
-      if (h->tiled[l]) {
+      if (h->gridk[l].on) {
+        const auto& G = h->gridk[l];
+        const long long th = A * bidi::grid_tiles(Y.hw, Y.hh), tv = A * bidi::grid_tiles(Y.vw, Y.vh);
+        launch_grid(R, "kw_activate", bidi::k_g_kw_activate, th, G.ff + G.rec, Y, l, G.ff);
+        launch_grid(R, "kw_inhibit", bidi::k_g_kw_inhibit, th, G.lat, Y, l, Y.act, Y.state, nxt);
+        launch_grid(R, "reconstruct", bidi::k_g_reconstruct, tv + th, G.gather, Y, l, Y.state, 1, 0);
+      } else if (h->tiled[l]) {
         launch_tile(R, "kw_activate", bidi::k_t_kw_activate, tiles_of(A, Y.nh), tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec)), Y, l);
         launch_tile(R, "kw_inhibit", bidi::k_t_kw_inhibit, tiles_of(A, Y.nh), 0, Y, l, Y.act, Y.state, nxt);
         launch_tile(R, "reconstruct", bidi::k_t_reconstruct, tiles_of(A, Y.nv) + tiles_of(A, Y.nh),
@@ -446,7 +494,12 @@ void record_step(Recorder& R, bool learn) {
     for (int l = L - 1; l >= 0; l--) {
       const LayerDev& Y = ly[l];
       const LayerDev& Up = ly[l < L - 1 ? l + 1 : l];
-      if (h->tiled[l]) {
+      if (h->gridk[l].on) {
+        const auto& G = h->gridk[l];
+        const long long th = A * bidi::grid_tiles(Y.hw, Y.hh);
+        launch_grid(R, "predict", bidi::k_g_kw_predict, th, G.fb + G.pred, Y, l, (int)learn, Up.p_state, Up.p_state_prev, G.fb);
+        launch_grid(R, "kw_inhibit", bidi::k_g_kw_inhibit, th, G.lat, Y, l, Y.p_act, Y.p_state, -1LL);
+      } else if (h->tiled[l]) {
         launch_tile(R, "predict", bidi::k_t_predict, tiles_of(A, Y.pn), tile_bytes(nslots_of(Y.fb) + nslots_of(Y.pred)), Y, l, (int)learn,
                     Up.p_state, Up.p_state_prev);
         launch_tile(R, "kw_inhibit", bidi::k_t_kw_inhibit, tiles_of(A, Y.nh), 0, Y, l, Y.p_act, Y.p_state, -1LL);
@@ -458,12 +511,14 @@ void record_step(Recorder& R, bool learn) {
     // :173-185
     if (learn)
       for (int l = 0; l < L; l++) {
-        if (h->tiled[l]) launch_tile(R, "kw_learn", bidi::k_t_kw_learn, tiles_of(A, ly[l].nh), 0, ly[l], l);
+        if (h->gridk[l].on) launch_grid(R, "kw_learn", bidi::k_g_kw_learn, A * bidi::grid_tiles(ly[l].hw, ly[l].hh), 0, ly[l], l);
+        else if (h->tiled[l]) launch_tile(R, "kw_learn", bidi::k_t_kw_learn, tiles_of(A, ly[l].nh), 0, ly[l], l);
         else R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, ly[l], l);
       }
     R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
     // :188-193
-    if (h->tiled[0])
+    if (h->gridk[0].on) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1);
+    else if (h->tiled[0])
       launch_tile(R, "kw_predict_input", bidi::k_t_reconstruct, tiles_of(A, ly[0].nv), tile_bytes(ly[0].ff.max_cand), ly[0], 0, ly[0].p_state, 0,
                   0.0f, 0, 1);
     else R.launch("kw_predict_input", bidi::k_kw_predict_input, A * h->n_in, ly[0]);
@@ -910,6 +965,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       CU_CREATE(cudaFuncSetAttribute(bidi::k_t_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     }
   }
+  if (select_grid_kernels(h) != BIDI_OK) return bail(BIDI_ECUDA, g_last_error);
   // the column kernel may need more than the default 48 KB of dynamic shared memory
   if (V == BIDI_NEO_AGENT) {
     size_t smem = 0;
@@ -1197,7 +1253,15 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   if (std::string(name) == "force_phase_kernels") h->force_phase_kernels = value != 0;
-  else if (std::string(name) == "tile_kernels") { if (!value) std::fill(h->tiled.begin(), h->tiled.end(), 0); }
+  else if (std::string(name) == "tile_kernels") {
+    if (!value) std::fill(h->tiled.begin(), h->tiled.end(), 0);
+    int rc = select_grid_kernels(h);
+    if (rc) return rc;
+  } else if (std::string(name) == "grid_kernels") {  // 0 off, 1 default (wide, untiled k-winners layers), 2 every k-winners layer
+    h->grid_mode = value;
+    int rc = select_grid_kernels(h);
+    if (rc) return rc;
+  }
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
       size_t smem = 0;

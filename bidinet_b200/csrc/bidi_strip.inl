@@ -157,21 +157,45 @@ void strip_phase(bidi_engine* h, int phase, bool learn) {
   };
   rows(BIDI_SPAN_OWN_HID);
   const long long nh = A * (Y.row1 - Y.row0) * Y.hw, nv = A * (Y.vrow1 - Y.vrow0) * Y.vw;
+  const auto& G = h->gridk[0];
+  const long long th = A * bidi::grid_tiles(Y.hw, Y.row1 - Y.row0), tv = A * bidi::grid_tiles(Y.vw, Y.vrow1 - Y.vrow0);
+  auto grid = [&](auto kernel, long long blocks, int smem_floats, auto... args) {
+    if (blocks <= 0) return;
+    kernel<<<(unsigned)blocks, GRID_TX * GRID_TY, sizeof(float) * (size_t)smem_floats, h->stream>>>(h->P, args...);
+    h->launches++;
+  };
   switch (phase) {
-    case 0: strip_launch(h, bidi::k_kw_activate, nh, Y, 0); break;
-    case 1: strip_launch(h, bidi::k_kw_inhibit, nh, Y, 0, Y.act, Y.state, -1LL); break;
-    case 2: strip_launch(h, bidi::k_reconstruct, nv + nh, Y, 0, Y.state, 0, 0.0f, 0); break;
-    case 3: strip_launch(h, bidi::k_predict, nh, Y, 0, (int)learn, Y.p_state, Y.p_state_prev); break;
-    case 4: strip_launch(h, bidi::k_kw_inhibit, nh, Y, 0, Y.p_act, Y.p_state, -1LL); break;
+    case 0:
+      if (G.on) grid(bidi::k_g_kw_activate, th, G.ff + G.rec, Y, 0, G.ff);
+      else strip_launch(h, bidi::k_kw_activate, nh, Y, 0);
+      break;
+    case 1:
+      if (G.on) grid(bidi::k_g_kw_inhibit, th, G.lat, Y, 0, Y.act, Y.state, -1LL);
+      else strip_launch(h, bidi::k_kw_inhibit, nh, Y, 0, Y.act, Y.state, -1LL);
+      break;
+    case 2:
+      if (G.on) grid(bidi::k_g_reconstruct, tv + th, G.gather, Y, 0, Y.state, 1, 0);
+      else strip_launch(h, bidi::k_reconstruct, nv + nh, Y, 0, Y.state, 0, 0.0f, 0);
+      break;
+    case 3:
+      if (G.on) grid(bidi::k_g_kw_predict, th, G.fb + G.pred, Y, 0, (int)learn, Y.p_state, Y.p_state_prev, G.fb);
+      else strip_launch(h, bidi::k_predict, nh, Y, 0, (int)learn, Y.p_state, Y.p_state_prev);
+      break;
+    case 4:
+      if (G.on) grid(bidi::k_g_kw_inhibit, th, G.lat, Y, 0, Y.p_act, Y.p_state, -1LL);
+      else strip_launch(h, bidi::k_kw_inhibit, nh, Y, 0, Y.p_act, Y.p_state, -1LL);
+      break;
     case 5: {
       if (learn) {
         rows(BIDI_SPAN_EXT_HID);  // owned rows + the halo rows whose weights this part mirrors
-        strip_launch(h, bidi::k_kw_learn, A * (Y.row1 - Y.row0) * Y.hw, Y, 0);
+        if (G.on) grid(bidi::k_g_kw_learn, A * bidi::grid_tiles(Y.hw, Y.row1 - Y.row0), 0, Y, 0);
+        else strip_launch(h, bidi::k_kw_learn, A * (Y.row1 - Y.row0) * Y.hw, Y, 0);
         rows(BIDI_SPAN_OWN_HID);
       }
       const int s0 = span(BIDI_SPAN_STATE, 0), s1 = span(BIDI_SPAN_STATE, 1);
       strip_launch(h, bidi::k_strip_step_end, A * (s1 - s0) * Y.hw, Y, s0, s1);
-      strip_launch(h, bidi::k_kw_predict_input, nv, Y);
+      if (G.on) grid(bidi::k_g_reconstruct, tv, G.gather, Y, 0, Y.p_state, 0, 1);
+      else strip_launch(h, bidi::k_kw_predict_input, nv, Y);
       break;
     }
   }
@@ -331,6 +355,10 @@ int bidi_strip_configure(bidi_engine* h, int part, int n_parts) {
   h->strip_part = part; h->strip_n = n_parts;
   if (n_parts == 1) return BIDI_OK;
   std::fill(h->tiled.begin(), h->tiled.end(), 0);
+  {
+    int rc2 = select_grid_kernels(h);
+    if (rc2) return rc2;
+  }
   strip_build_plan(h);
   for (auto& e : h->strip_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CU(cudaEventCreateWithFlags(&h->strip_done, cudaEventDisableTiming));

@@ -42,7 +42,7 @@ def test_init_random_matches_oracle(case):
         assert diff_states(orc.state(), eng.state(agent=a)) == [], "agent %d" % a
 
 
-@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads"])
+@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
 @pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
 def test_free_running_parity(case, path):
     """N steps from an identical state, no re-synchronisation: exact after every step.
@@ -50,8 +50,9 @@ def test_free_running_parity(case, path):
     layer fits in shared memory -- its dense-row form where the windows span the grid --
     and cooperative tile kernels for small launches), the general fused coder kernel
     everywhere, one
-    kernel per phase with the tile kernels (large single agents), and one kernel per
-    phase with one thread per unit (large agent batches, very large layers)."""
+    kernel per phase with the tile kernels (large single agents), one kernel per
+    phase with one thread per unit (large agent batches), and the 2-D grid-tile kernels
+    (very large k-winners layers)."""
     name, cfg, ld, frame, reward = case
     orc = OracleHierarchy(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1)
@@ -61,6 +62,11 @@ def test_free_running_parity(case, path):
         eng.set_option("force_phase_kernels", True)
     if path == "per_phase_threads":
         eng.set_option("tile_kernels", False)
+        eng.set_option("grid_kernels", 0)
+    if path == "per_phase_grid":  # the 2-D tile kernels for large k-winners layers, forced onto every layer
+        if cfg.variant != cf.KWINNERS:
+            pytest.skip("k-winners only")
+        eng.set_option("grid_kernels", 2)
     eng.load_state(orc.state())
     steps = 25
     for t in range(steps):

@@ -34,12 +34,15 @@ def _frames(g, n=8, seed=0):
     return (rng.rand(n, g[0] * g[1]) < 0.3).astype(np.float32)
 
 
+@pytest.mark.parametrize("kernels", ["grid", "threads"])
 @pytest.mark.parametrize("n_parts", [2, 3, 4])
 @pytest.mark.parametrize("g", GEOMS, ids=lambda g: "%dx%d_to_%dx%d" % g[:4])
-def test_local_strips_match_the_whole_layer(g, n_parts):
+def test_local_strips_match_the_whole_layer(g, n_parts, kernels):
     cfg, ld = _cfg(g)
     orc = OracleHierarchy(cfg, ld, 1234)
     grp = StripGroup(cfg, ld, devices=[0] * n_parts)
+    for e in grp.parts:  # both kernel families under the split: 2-D tiles (large layers) and one thread per unit
+        e.set_option("grid_kernels", 2 if kernels == "grid" else 0)
     grp.load_state(orc.state())
     frames = _frames(g)
     winners = 0
