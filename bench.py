@@ -227,11 +227,17 @@ def run_c5(args, rank, world, local_rank):
     eng = Engine(cfg, ld, n_agents=1, device=local_rank)
     if world > 1:
         eng.strip_configure(rank, world)
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        eng.strip_link_nccl(bytes(uid.cpu().numpy().tobytes()))
+        if args.c5_transport == "nccl":
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            eng.strip_link_nccl(bytes(uid.cpu().numpy().tobytes()))
+        else:  # peer memory: gather every part's CUDA IPC handles
+            mine = torch.frombuffer(bytearray(eng.strip_ipc_export()), dtype=torch.uint8).cuda()
+            allh = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)]
+            dist.all_gather(allh, mine)
+            eng.strip_link_ipc([bytes(t.cpu().numpy().tobytes()) for t in allh])
     eng.init_random(1234)
     frames = c5_frames(size)
     T = len(frames)
@@ -290,7 +296,8 @@ def run_c5(args, rank, world, local_rank):
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C5: one k-winners layer %dx%d over a %dx%d input, every radius 6, 1 agent" % (size, size, size, size),
                    "units": n_units, "unit_updates_per_s": value * n_units, "learn": True,
-                   "parallelism": "%d row strips, one per GPU, halo rows over NCCL send/recv" % world if world > 1 else "one GPU, unsplit",
+                   "parallelism": ("%d row strips, one per GPU, halo rows %s" % (world, "pushed into peer memory over NVLink by one kernel per exchange point"
+                                   if args.c5_transport == "ipc" else "over NCCL send/recv")) if world > 1 else "one GPU, unsplit",
                    "halo_bytes_sent_per_gpu_step": halo, "l2": "weights streamed per step: %.0f MB per GPU" % (per_gpu / 1e6),
                    "state_bytes_per_gpu": dev_bytes},
         "e2e": {"value": K / e2e_s, "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,
@@ -316,6 +323,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"])
     ap.add_argument("--c5-size", type=int, default=1024)
+    ap.add_argument("--c5-transport", default="ipc", choices=["ipc", "nccl"])
     args = ap.parse_args()
     rank, world, local_rank = rank_info()
     if args.impl == "reference":

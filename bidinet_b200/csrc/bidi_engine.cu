@@ -124,6 +124,14 @@ struct bidi_engine {
   std::vector<StripXfer> strip_send, strip_recv;   // per exchange point, peer: rows of one plane
   std::vector<bidi_engine*> strip_peers;           // same-process transport, indexed by part
   void* nccl_comm = nullptr;                       // one-process-per-GPU transport
+  // peer-memory transport (bidi_strip_link_ipc): device tables for k_strip_push
+  bool ipc_linked = false;
+  std::vector<void*> ipc_opened;                   // peer mappings to close
+  unsigned* d_flags = nullptr; unsigned* d_epoch = nullptr;
+  float** d_peer_blob = nullptr; unsigned** d_peer_flags = nullptr;
+  bidi::StripXferDev* d_sends = nullptr; int* d_notify = nullptr; int* d_await = nullptr;
+  struct PushArgs { int send0, n_sends, notify0, n_notify, await0, n_await; } push[5] = {};
+  bool strip_use_graph = true;                     // record the split step (NCCL exchanges included) into a CUDA graph
   cudaEvent_t strip_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t strip_done = nullptr;
   std::string err;
@@ -448,7 +456,7 @@ int select_grid_kernels(bidi_engine* h) {
     g.pred = bidi::grid_box_floats(H.pred.d, H.pred.cx.data(), H.pred.cy.data());
     g.gather = std::max(bidi::grid_gather_floats(H.ff.d, H.ff.gxlo.data(), H.ff.gxhi.data(), H.ff.gylo.data(), H.ff.gyhi.data()),
                         bidi::grid_gather_floats(H.rec.d, H.rec.gxlo.data(), H.rec.gxhi.data(), H.rec.gylo.data(), H.rec.gyhi.data()));
-    const size_t need = sizeof(float) * (size_t)std::max({g.ff + g.rec, g.lat, g.fb + g.pred, g.gather});
+    const size_t need = sizeof(float) * (size_t)std::max({g.ff + g.rec, g.lat, g.fb + g.pred, 3 * g.gather});
     g.on = need <= 160 * 1024 && (h->grid_mode == 2 || (!h->tiled[l] && h->layers[l].hw >= 16)) ? 1 : 0;
     if (g.on) most = std::max(most, need);
     h->gridk[l] = g;
@@ -478,7 +486,7 @@ void record_step(Recorder& R, bool learn) {
         const long long th = A * bidi::grid_tiles(Y.hw, Y.hh), tv = A * bidi::grid_tiles(Y.vw, Y.vh);
         launch_grid(R, "kw_activate", bidi::k_g_kw_activate, th, G.ff + G.rec, Y, l, G.ff);
         launch_grid(R, "kw_inhibit", bidi::k_g_kw_inhibit, th, G.lat, Y, l, Y.act, Y.state, nxt);
-        launch_grid(R, "reconstruct", bidi::k_g_reconstruct, tv + th, G.gather, Y, l, Y.state, 1, 0);
+        launch_grid(R, "reconstruct", bidi::k_g_reconstruct, tv + th, 3 * G.gather, Y, l, Y.state, 1, 0, G.gather);
       } else if (h->tiled[l]) {
         launch_tile(R, "kw_activate", bidi::k_t_kw_activate, tiles_of(A, Y.nh), tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec)), Y, l);
         launch_tile(R, "kw_inhibit", bidi::k_t_kw_inhibit, tiles_of(A, Y.nh), 0, Y, l, Y.act, Y.state, nxt);
@@ -517,7 +525,7 @@ void record_step(Recorder& R, bool learn) {
       }
     R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
     // :188-193
-    if (h->gridk[0].on) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1);
+    if (h->gridk[0].on) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather);
     else if (h->tiled[0])
       launch_tile(R, "kw_predict_input", bidi::k_t_reconstruct, tiles_of(A, ly[0].nv), tile_bytes(ly[0].ff.max_cand), ly[0], 0, ly[0].p_state, 0,
                   0.0f, 0, 1);
@@ -1262,6 +1270,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     int rc = select_grid_kernels(h);
     if (rc) return rc;
   }
+  else if (std::string(name) == "strip_graph") h->strip_use_graph = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
       size_t smem = 0;

@@ -58,20 +58,44 @@ __device__ __forceinline__ void stage_box(float* __restrict__ sm, const Box& b, 
     sm[k] = (gx >= 0 && gx < tw && gy >= 0 && gy < th) ? src(gx + gy * tw) : 0.0f;
   }
 }
-// sum += sm(target) * w[slot][unit] over the whole slot box, list order
+// sum += sm(target) * w[slot][unit] over the whole slot box, list order.  DYN = the
+// window's height when it is one of the usual 2r+1 (the inner loop is then fully unrolled:
+// all DYN weight loads of a window column are in flight together), 0 = any height.
+template <int DYN>
+__device__ __forceinline__ float box_dot_n(const WinDev& w, const Box& b, const float* __restrict__ s0, const float* __restrict__ wp,
+                                           long long U, float sum) {
+  const int dyn = DYN ? DYN : w.dyn;
+  for (int sx = 0; sx < w.dxn; sx++) {
+    const float* sp = s0 + sx;
+    if (DYN) {
+      float wv[DYN ? DYN : 1], xv[DYN ? DYN : 1];
+#pragma unroll
+      for (int sy = 0; sy < DYN; sy++) { wv[sy] = wp[(long long)sy * U]; xv[sy] = sp[sy * b.w]; }
+#pragma unroll
+      for (int sy = 0; sy < DYN; sy++) sum += xv[sy] * wv[sy];
+      wp += (long long)DYN * U;
+    } else {
+#pragma unroll 4
+      for (int sy = 0; sy < dyn; sy++) {
+        sum += sp[sy * b.w] * wp[0];
+        wp += U;
+      }
+    }
+  }
+  return sum;
+}
 __device__ __forceinline__ float box_dot(const WinDev& w, const Box& b, const float* __restrict__ sm, int ux, int uy,
                                          const float* __restrict__ wp, long long U, float sum) {
   if (w.r < 0) return sum;
   const float* s0 = sm + (w.absx ? 0 : w.cx[ux] - w.r - b.x0) + (w.absy ? 0 : w.cy[uy] - w.r - b.y0) * b.w;
-  for (int sx = 0; sx < w.dxn; sx++) {
-    const float* sp = s0 + sx;
-#pragma unroll 8
-    for (int sy = 0; sy < w.dyn; sy++) {
-      sum += sp[sy * b.w] * wp[0];
-      wp += U;
-    }
+  switch (w.dyn) {
+    case 5: return box_dot_n<5>(w, b, s0, wp, U, sum);
+    case 7: return box_dot_n<7>(w, b, s0, wp, U, sum);
+    case 9: return box_dot_n<9>(w, b, s0, wp, U, sum);
+    case 13: return box_dot_n<13>(w, b, s0, wp, U, sum);
+    case 17: return box_dot_n<17>(w, b, s0, wp, U, sum);
+    default: return box_dot_n<0>(w, b, s0, wp, U, sum);
   }
-  return sum;
 }
 // largest window box of any tile, in floats (host: shared memory to reserve)
 inline int grid_box_floats(const WinDev& w, const int* cx, const int* cy) {
@@ -115,10 +139,19 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_inhibit(EngineDev P, 
   const SlotBox sb = slot_box(w, T.ux, T.uy);
   const float mine = sm[(T.ux - b.x0) + (T.uy - b.y0) * b.w];
   int cnt = 0;
+  const int ny = sb.sy1 - sb.sy0 + 1;
   for (int sx = sb.sx0; sx <= sb.sx1; sx++) {
     const float* sp = sm + (slot_tx(w, sb, sx) - b.x0) + (slot_ty(w, sb, sb.sy0) - b.y0) * b.w;
+    if (ny == 13) {  // an interior unit of a radius-6 layer: the whole column at once
+#pragma unroll
+      for (int q = 0; q < 13; q++) cnt += sp[q * b.w] >= mine ? 1 : 0;
+    } else if (ny == 7) {
+#pragma unroll
+      for (int q = 0; q < 7; q++) cnt += sp[q * b.w] >= mine ? 1 : 0;
+    } else {
 #pragma unroll 4
-    for (int sy = sb.sy0; sy <= sb.sy1; sy++) { cnt += *sp >= mine ? 1 : 0; sp += b.w; }
+      for (int q = 0; q < ny; q++) cnt += sp[q * b.w] >= mine ? 1 : 0;
+    }
   }
   cnt -= 1;  // the loop counted the unit itself (mine >= mine); the lateral list excludes the centre
   const float s = (float)cnt < L.sparsity * (float)slot_count(w, sb) ? 1.0f : 0.0f;
@@ -129,7 +162,8 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_inhibit(EngineDev P, 
 // ---- gather-form reconstruction (sdr/RSDR.cpp:165-212): tiles [0,vt) of an agent own
 // visible cells (feed-forward family), the rest hidden units (recurrent family);
 // to_pred: the visible result is the input-space prediction (sdr/PredictiveRSDR.cpp:188-193).
-__global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_reconstruct(EngineDev P, LayerDev L, int l, long long drive_off, int hidden_too, int to_pred) {
+__global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_reconstruct(EngineDev P, LayerDev L, int l, long long drive_off, int hidden_too, int to_pred,
+                                                                      int cap) {
   extern __shared__ float sm[];
   const int vt = grid_tiles(L.vw, L.vrow1 - L.vrow0), ht = hidden_too ? grid_tiles(L.hw, L.row1 - L.row0) : 0;
   const int a = blockIdx.x / (vt + ht), tile = blockIdx.x % (vt + ht);
@@ -148,26 +182,50 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_reconstruct(EngineDev P,
   int bx0 = w.uw, bx1 = -1, by0 = w.uh, by1 = -1;
   for (int t = T.ux0; t <= tx1; t++) { bx0 = min(bx0, w.gx_lo[t]); bx1 = max(bx1, w.gx_hi[t]); }
   for (int t = T.uy0; t <= ty1; t++) { by0 = min(by0, w.gy_lo[t]); by1 = max(by1, w.gy_hi[t]); }
-  const int bw = max(0, bx1 - bx0 + 1), bh = max(0, by1 - by0 + 1);
-  for (int k = threadIdx.x; k < bw * bh; k += GRID_TX * GRID_TY) { const int by = k / bw; sm[k] = drive[(bx0 + k - by * bw) + (by0 + by) * w.uw]; }
+  const int bw = max(0, bx1 - bx0 + 1), bh = max(0, by1 - by0 + 1), nb = bw * bh;
+  // The drive is sparse (k-winners: ~1 % of the units), so instead of every cell walking
+  // its (2r+1)^2 candidates the CTA compacts the non-zero units of the box into a list,
+  // in ascending unit index -- the order the reference's scatter adds them -- and every cell
+  // walks the list.  Warp g compacts the g-th eighth of the box; a scan over the eight
+  // counts gives each warp its place.
+  int* l_unit = reinterpret_cast<int*>(sm);   // [nb] unit index
+  int* l_ctr = l_unit + cap;                  // [nb] window centre, cx | cy << 16
+  float* l_d = sm + 2 * cap;                  // [nb] drive
+  __shared__ int s_cnt[GRID_TY + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = ((nb + GRID_TY - 1) / GRID_TY + 31) / 32 * 32, k0 = warp * chunk, k1 = min(nb, k0 + chunk);
+  int mine = 0;
+  for (int k = k0 + lane; k < k0 + chunk; k += 32) {
+    float d = 0.0f;
+    if (k < k1) { const int by = k / bw; d = drive[(bx0 + k - by * bw) + (by0 + by) * w.uw]; }
+    mine += __popc(__ballot_sync(0xffffffffu, d != 0.0f));
+  }
+  if (lane == 0) s_cnt[warp + 1] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) { s_cnt[0] = 0; for (int g = 0; g < GRID_TY; g++) s_cnt[g + 1] += s_cnt[g]; }
+  __syncthreads();
+  int pos = s_cnt[warp];
+  for (int k = k0 + lane; k < k0 + chunk; k += 32) {
+    float d = 0.0f;
+    int ux = 0, uy = 0;
+    if (k < k1) { const int by = k / bw; ux = bx0 + k - by * bw; uy = by0 + by; d = drive[ux + uy * w.uw]; }
+    const unsigned m = __ballot_sync(0xffffffffu, d != 0.0f);
+    if (d != 0.0f) {
+      const int q = pos + __popc(m & ((1u << lane) - 1u));
+      l_unit[q] = ux + uy * w.uw; l_ctr[q] = w.cx[ux] | (w.cy[uy] << 16); l_d[q] = d;
+    }
+    pos += __popc(m);
+  }
   __syncthreads();
   if (!T.ok) return;
-  const int tx = T.ux, ty = T.uy;
+  const int tx = T.ux, ty = T.uy, n = s_cnt[GRID_TY], r = w.r;
   const float* wp = B + w.w_off;
   float sum = 0.0f;
-  const int y0 = w.gy_lo[ty], y1 = w.gy_hi[ty], x0 = w.gx_lo[tx], x1 = w.gx_hi[tx];
-  for (int uy = y0; uy <= y1; uy++) {
-    const int cy = w.cy[uy];
-    const int sy = w.absy ? ty : ty - cy + w.r;
-    const float* dp = sm + (uy - by0) * bw - bx0;
-    for (int ux = x0; ux <= x1; ux++) {
-      const float d = dp[ux];
-      if (d != 0.0f) {
-        const int cx = w.cx[ux];
-        if (w.excl && cx == tx && cy == ty) continue;
-        const int sx = w.absx ? tx : tx - cx + w.r;
-        sum += wp[(long long)(sx * w.dyn + sy) * w.U + ux + uy * w.uw] * d;
-      }
+  for (int k = 0; k < n; k++) {
+    const int c = l_ctr[k], dx = tx - (c & 0xffff), dy = ty - (c >> 16);
+    if (dx >= -r && dx <= r && dy >= -r && dy <= r && !(w.excl && (dx | dy) == 0)) {
+      const int sx = w.absx ? tx : dx + r, sy = w.absy ? ty : dy + r;
+      sum += wp[(long long)(sx * w.dyn + sy) * w.U + l_unit[k]] * l_d[k];
     }
   }
   out[T.unit] = sum;
@@ -209,19 +267,43 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_predict(EngineDev P, 
   if (!top) stage_box(sm, bf, L.fb.tw, L.fb.th, [&](int t) { return up_state[t]; });
   stage_box(sm_pred, bp, L.pred.tw, L.pred.th, [&](int t) { return state[t]; });
   __syncthreads();
-  if (!T.ok) return;
   const int i = T.unit;
-  if (learn) {
+  float kfb = 0.0f, kpr = 0.0f;
+  bool wrong = false;
+  if (learn && T.ok) {
     const float err = state[i] - B[L.p_state_prev + i];
     const float surprise = err * err, avg = B[L.p_baseline + i];
     B[L.p_mod + i] = bidi_sigmoid(L.attention_factor * (surprise - avg));
     B[L.p_baseline + i] = (1.0f - L.avg_surprise_decay) * avg + L.avg_surprise_decay * surprise;
-    const float kfb = L.learn_fb * err, kpr = L.learn_pred * err;
-    if (err != 0.0f) {
-      if (!top) for_each_conn(L.fb, T.ux, T.uy, [&](int s, int t) { const float v = up_prev[t]; if (v != 0.0f) wfb[(long long)s * U + i] += kfb * v; });
-      for_each_conn(L.pred, T.ux, T.uy, [&](int s, int t) { const float v = sprev[t]; if (v != 0.0f) wpr[(long long)s * U + i] += kpr * v; });
+    kfb = L.learn_fb * err; kpr = L.learn_pred * err;
+    wrong = err != 0.0f;
+  }
+  // delta rule: w += k*source for the few units whose prediction was wrong (a zero error or
+  // a zero source adds +-0).  The rule is element-wise, so the 32 lanes of the warp share the
+  // connections of each such unit instead of one lane walking all (2r+1)^2 of them.
+  for (unsigned todo = __ballot_sync(0xffffffffu, wrong); todo; todo &= todo - 1) {
+    const int src = __ffs(todo) - 1, lane = threadIdx.x & 31;
+    const int ux = T.ux0 + src, uy = T.uy, unit = ux + uy * L.hw;
+    const float kfb_w = __shfl_sync(0xffffffffu, kfb, src), kpr_w = __shfl_sync(0xffffffffu, kpr, src);
+    for (int fam = top ? 1 : 0; fam < 2; fam++) {
+      const WinDev& w = fam ? L.pred : L.fb;
+      if (w.r < 0) continue;
+      float* wq = (fam ? wpr : wfb) + unit;
+      const float* from = fam ? sprev : up_prev;
+      const float k = fam ? kpr_w : kfb_w;
+      const SlotBox sb = slot_box(w, ux, uy);
+      for (int sl = lane; sl < w.nslots; sl += 32) {
+        const int sx = sl / w.dyn, sy = sl - sx * w.dyn;
+        const int tx = slot_tx(w, sb, sx), ty = slot_ty(w, sb, sy);
+        if (sx >= sb.sx0 && sx <= sb.sx1 && sy >= sb.sy0 && sy <= sb.sy1 && !(w.excl && tx == sb.cx && ty == sb.cy)) {
+          const float v = from[tx + ty * w.tw];
+          if (v != 0.0f) wq[(long long)sl * U] += k * v;
+        }
+      }
     }
   }
+  __syncwarp();
+  if (!T.ok) return;
   float activation = 0.0f;
   if (!top) activation = box_dot(L.fb, bf, sm, T.ux, T.uy, wfb + i, U, activation);
   activation = box_dot(L.pred, bp, sm_pred, T.ux, T.uy, wpr + i, U, activation);

@@ -474,8 +474,9 @@ __global__ void k_step_end(EngineDev P, int max_units) {
 // The same for one row strip of a split layer (bidi_strip.inl): the winners are kept on
 // hidden rows [s0,s1) (owned rows plus the halo later phases read), the prediction
 // nodes only on the owned rows [L.row0,L.row1).
-__global__ void k_strip_step_end(EngineDev P, LayerDev L, int s0, int s1) {
+__global__ void k_strip_step_end(EngineDev P, LayerDev L, int s0, int s1, unsigned* epoch) {
   const int n = (s1 - s0) * L.hw;
+  if (epoch && blockIdx.x == 0 && threadIdx.x == 0) *epoch += 1u;  // the step's exchanges (k_strip_push) are behind us
   BIDI_THREAD_AGENT_UNIT(n)
   i += s0 * L.hw;
   float* B = blob_of(P, a);
@@ -485,6 +486,48 @@ __global__ void k_strip_step_end(EngineDev P, LayerDev L, int s0, int s1) {
     B[L.p_state_prev + i] = B[L.p_state + i];
     B[L.p_act_prev + i] = B[L.p_act + i];
   }
+}
+
+// Halo exchange of a split layer over peer-mapped memory (NVLink): ONE small kernel per
+// exchange point pushes the rows the neighbours need straight into their blobs (plain
+// coalesced stores to peer memory), publishes an epoch number in each neighbour's flag
+// word, and waits for the neighbours' flags -- transfer, signal and wait in one launch,
+// no library call, capturable in the step's CUDA graph.  One CTA: the halos are a few
+// rows (r x width x 4 B = 24.6 kB per direction for C5).
+struct StripXferDev { int peer; int pad; long long off, count; };
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(1024) k_strip_push(EngineDev P, const StripXferDev* __restrict__ sends, int n_sends, float* const* __restrict__ peer_blob,
+                                                     unsigned* const* __restrict__ peer_flags, unsigned* my_flags, const unsigned* epoch_ctr, int point,
+                                                     int me, int n_parts, const int* __restrict__ notify, int n_notify, const int* __restrict__ await, int n_await) {
+  const unsigned epoch = *epoch_ctr * 8u + (unsigned)point + 1u;
+  for (int k = 0; k < n_sends; k++) {
+    const StripXferDev x = sends[k];
+    for (int a = 0; a < P.A; a++) {
+      const float* src = P.blob + (long long)a * P.stride + x.off;
+      float* dst = peer_blob[x.peer] + (long long)a * P.stride + x.off;
+      if (((x.off | x.count | P.stride) & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (long long j = threadIdx.x; j < (x.count >> 2); j += blockDim.x) d4[j] = s4[j];
+      } else {
+        for (long long j = threadIdx.x; j < x.count; j += blockDim.x) dst[j] = src[j];
+      }
+    }
+  }
+  __threadfence_system();  // this thread's stores to peer memory are ordered before the flag
+  __syncthreads();
+  if ((int)threadIdx.x < n_notify) st_release_sys(peer_flags[notify[threadIdx.x]] + point * n_parts + me, epoch);
+  if ((int)threadIdx.x < n_await) {
+    const unsigned* f = my_flags + point * n_parts + await[threadIdx.x];
+    while ((int)(ld_acquire_sys(f) - epoch) < 0) {}
+  }
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------ neo::Column

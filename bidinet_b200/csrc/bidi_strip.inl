@@ -133,6 +133,13 @@ void strip_release(bidi_engine* h) {
     if (NcclApi* nc = nccl_api(why)) nc->CommDestroy(h->nccl_comm);
     h->nccl_comm = nullptr;
   }
+  for (void* p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+  h->ipc_opened.clear();
+  h->ipc_linked = false;
+  cudaFree(h->d_flags); cudaFree(h->d_epoch); cudaFree(h->d_peer_blob); cudaFree(h->d_peer_flags);
+  cudaFree(h->d_sends); cudaFree(h->d_notify); cudaFree(h->d_await);
+  h->d_flags = h->d_epoch = nullptr; h->d_peer_blob = nullptr; h->d_peer_flags = nullptr;
+  h->d_sends = nullptr; h->d_notify = h->d_await = nullptr;
   for (auto& e : h->strip_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
   if (h->strip_done) { cudaEventDestroy(h->strip_done); h->strip_done = nullptr; }
   for (bidi_engine* p : h->strip_peers)  // the other parts must not follow a dangling pointer
@@ -174,7 +181,7 @@ void strip_phase(bidi_engine* h, int phase, bool learn) {
       else strip_launch(h, bidi::k_kw_inhibit, nh, Y, 0, Y.act, Y.state, -1LL);
       break;
     case 2:
-      if (G.on) grid(bidi::k_g_reconstruct, tv + th, G.gather, Y, 0, Y.state, 1, 0);
+      if (G.on) grid(bidi::k_g_reconstruct, tv + th, 3 * G.gather, Y, 0, Y.state, 1, 0, G.gather);
       else strip_launch(h, bidi::k_reconstruct, nv + nh, Y, 0, Y.state, 0, 0.0f, 0);
       break;
     case 3:
@@ -193,8 +200,8 @@ void strip_phase(bidi_engine* h, int phase, bool learn) {
         rows(BIDI_SPAN_OWN_HID);
       }
       const int s0 = span(BIDI_SPAN_STATE, 0), s1 = span(BIDI_SPAN_STATE, 1);
-      strip_launch(h, bidi::k_strip_step_end, A * (s1 - s0) * Y.hw, Y, s0, s1);
-      if (G.on) grid(bidi::k_g_reconstruct, tv, G.gather, Y, 0, Y.p_state, 0, 1);
+      strip_launch(h, bidi::k_strip_step_end, A * (s1 - s0) * Y.hw, Y, s0, s1, h->ipc_linked ? h->d_epoch : nullptr);
+      if (G.on) grid(bidi::k_g_reconstruct, tv, 3 * G.gather, Y, 0, Y.p_state, 0, 1, G.gather);
       else strip_launch(h, bidi::k_kw_predict_input, nv, Y);
       break;
     }
@@ -271,15 +278,62 @@ int strip_exchange_nccl(bidi_engine* h, int point) {
   return BIDI_OK;
 }
 
-int strip_step_nccl(bidi_engine* h, bool learn) {
-  if (!h->nccl_comm) return fail(h, BIDI_EINVAL, "this engine is one part of a split layer: link it (bidi_strip_link_nccl) or step all parts with bidi_strip_step_local");
+void strip_exchange_push(bidi_engine* h, int point) {
+  const auto& a = h->push[point];
+  if (a.n_sends == 0 && a.n_await == 0) return;
+  bidi::k_strip_push<<<1, 1024, 0, h->stream>>>(h->P, h->d_sends + a.send0, a.n_sends, h->d_peer_blob, h->d_peer_flags, h->d_flags, h->d_epoch, point,
+                                                h->strip_part, h->strip_n, h->d_notify + a.notify0, a.n_notify, h->d_await + a.await0, a.n_await);
+  h->launches++;
+}
+
+int strip_record_nccl(bidi_engine* h, bool learn) {
   for (int phase = 0; phase < kStripPhases; phase++) {
     strip_phase(h, phase, learn);
     if (phase < kStripPhases - 1 && strip_point_used(phase, learn)) {
-      int rc = strip_exchange_nccl(h, phase);
-      if (rc) return rc;
+      if (h->ipc_linked) strip_exchange_push(h, phase);
+      else {
+        int rc = strip_exchange_nccl(h, phase);
+        if (rc) return rc;
+      }
     }
   }
+  return BIDI_OK;
+}
+
+// The whole step -- six compute phases and five grouped send/recv exchanges -- is recorded
+// once into a CUDA graph per value of `learn` (NCCL operations can be captured), so a step
+// costs one graph launch instead of ~15 separate submissions.
+int strip_step_nccl(bidi_engine* h, bool learn) {
+  if (!h->nccl_comm && !h->ipc_linked)
+    return fail(h, BIDI_EINVAL, "this engine is one part of a split layer: link it (bidi_strip_link_ipc / bidi_strip_link_nccl) or step all parts with bidi_strip_step_local");
+  if (h->strip_use_graph) {
+    cudaGraphExec_t& exec = h->graphs[learn];
+    if (!exec) {
+      const long long before = h->launches;
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = strip_record_nccl(h, learn);
+      cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+      h->graph_kernels[learn] = (int)(h->launches - before);
+      h->launches = before;
+      if (rc == BIDI_OK && e == cudaSuccess && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+      } else {  // capture not possible with this NCCL: submit the launches one by one from now on
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        exec = nullptr;
+        h->strip_use_graph = false;
+      }
+    }
+    if (exec) {
+      CU(cudaGraphLaunch(exec, h->stream));
+      h->launches += h->graph_kernels[learn];
+      h->step_index++;
+      return BIDI_OK;
+    }
+  }
+  int rc = strip_record_nccl(h, learn);
+  if (rc) return rc;
   CU(cudaGetLastError());
   h->step_index++;
   return BIDI_OK;
@@ -418,6 +472,78 @@ int bidi_strip_link_nccl(bidi_engine* h, const void* id128) {
   NcclUid id;
   memcpy(&id, id128, sizeof(id));
   NC(nc->CommInitRank(&h->nccl_comm, h->strip_n, id, h->strip_part));
+  return BIDI_OK;
+}
+
+// Peer-memory transport.  Export: the CUDA IPC handles of this part's blob and flag words.
+int bidi_strip_ipc_export(bidi_engine* h, void* handle128) {
+  if (!h || !handle128 || h->strip_n < 2) return fail(h, BIDI_EINVAL, "bidi_strip_ipc_export: configure the part first (bidi_strip_configure, n_parts >= 2)");
+  static_assert(2 * sizeof(cudaIpcMemHandle_t) <= 128, "two IPC handles fit the 128-byte record");
+  CU(cudaSetDevice(h->device));
+  if (!h->d_flags) {
+    CU(cudaMalloc(&h->d_flags, sizeof(unsigned) * 5 * h->strip_n));
+    CU(cudaMemset(h->d_flags, 0, sizeof(unsigned) * 5 * h->strip_n));
+    CU(cudaMalloc(&h->d_epoch, sizeof(unsigned)));
+    CU(cudaMemset(h->d_epoch, 0, sizeof(unsigned)));
+  }
+  cudaIpcMemHandle_t hb, hf;
+  CU(cudaIpcGetMemHandle(&hb, h->d_blob));
+  CU(cudaIpcGetMemHandle(&hf, h->d_flags));
+  memset(handle128, 0, 128);
+  memcpy(handle128, &hb, sizeof(hb));
+  memcpy(static_cast<char*>(handle128) + 64, &hf, sizeof(hf));
+  return BIDI_OK;
+}
+
+// Link: handles[n_parts][128] as exported by every part (this part's own record is ignored).
+int bidi_strip_link_ipc(bidi_engine* h, const void* handles) {
+  if (!h || !handles || h->strip_n < 2 || !h->d_flags) return fail(h, BIDI_EINVAL, "bidi_strip_link_ipc: export this part's handles first (bidi_strip_ipc_export)");
+  CU(cudaSetDevice(h->device));
+  const int n = h->strip_n, me = h->strip_part;
+  std::vector<float*> blobs(n, nullptr);
+  std::vector<unsigned*> flags(n, nullptr);
+  blobs[me] = h->d_blob; flags[me] = h->d_flags;
+  std::vector<char> need(n, 0);
+  for (const auto& x : h->strip_send) need[x.peer] = 1;
+  for (const auto& x : h->strip_recv) need[x.peer] = 1;
+  for (int q = 0; q < n; q++) {
+    if (q == me || !need[q]) continue;
+    cudaIpcMemHandle_t hb, hf;
+    memcpy(&hb, static_cast<const char*>(handles) + 128 * q, sizeof(hb));
+    memcpy(&hf, static_cast<const char*>(handles) + 128 * q + 64, sizeof(hf));
+    void *pb = nullptr, *pf = nullptr;
+    CU(cudaIpcOpenMemHandle(&pb, hb, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(pb);
+    CU(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened.push_back(pf);
+    blobs[q] = static_cast<float*>(pb); flags[q] = static_cast<unsigned*>(pf);
+  }
+  // per exchange point: the rows to push, whom to notify, whom to wait for
+  std::vector<bidi::StripXferDev> sends;
+  std::vector<int> notify, await;
+  for (int point = 0; point < 5; point++) {
+    auto& a = h->push[point];
+    a.send0 = (int)sends.size(); a.notify0 = (int)notify.size(); a.await0 = (int)await.size();
+    std::vector<char> to(n, 0), from(n, 0);
+    for (const auto& x : h->strip_send) if (x.point == point) { sends.push_back({x.peer, 0, x.off, x.count}); to[x.peer] = 1; }
+    for (const auto& x : h->strip_recv) if (x.point == point) from[x.peer] = 1;
+    for (int q = 0; q < n; q++) { if (to[q]) notify.push_back(q); if (from[q]) await.push_back(q); }
+    a.n_sends = (int)sends.size() - a.send0; a.n_notify = (int)notify.size() - a.notify0; a.n_await = (int)await.size() - a.await0;
+    if (a.n_notify > 1024 || a.n_await > 1024) return fail(h, BIDI_EINVAL, "bidi_strip_link_ipc: too many neighbours");
+  }
+  auto upload = [&](auto** dst, const auto& v) -> cudaError_t {
+    using T = typename std::remove_reference<decltype(v)>::type::value_type;
+    cudaError_t e = cudaMalloc(dst, sizeof(T) * std::max<size_t>(1, v.size()));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+  };
+  CU(upload(&h->d_peer_blob, blobs));
+  CU(upload(&h->d_peer_flags, flags));
+  CU(upload(&h->d_sends, sends));
+  CU(upload(&h->d_notify, notify));
+  CU(upload(&h->d_await, await));
+  for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  h->ipc_linked = true;
   return BIDI_OK;
 }
 

@@ -52,6 +52,8 @@ ABI = {
     "bidi_strip_link_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "bidi_strip_step_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int]),
     "bidi_strip_step_frame_local": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]),
+    "bidi_strip_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bidi_strip_link_ipc": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bidi_strip_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "bidi_strip_link_nccl": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bidi_strip_halo_floats": (C.c_longlong, [C.c_void_p]),
@@ -239,6 +241,19 @@ class Engine:
     def strip_link_nccl(self, unique_id):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._check(self.lib.bidi_strip_link_nccl(self.h, buf), "bidi_strip_link_nccl")
+
+    def strip_ipc_export(self):
+        """128 bytes (CUDA IPC handles of this part's state and flag words) for strip_link_ipc."""
+        buf = C.create_string_buffer(128)
+        self._check(self.lib.bidi_strip_ipc_export(self.h, buf), "bidi_strip_ipc_export")
+        return buf.raw
+
+    def strip_link_ipc(self, handles):
+        """handles: the 128-byte records of ALL parts, in part order."""
+        raw = b"".join(bytes(x) for x in handles)
+        assert len(raw) == 128 * self.strip_n
+        buf = C.create_string_buffer(raw, len(raw))
+        self._check(self.lib.bidi_strip_link_ipc(self.h, buf), "bidi_strip_link_ipc")
 
     @property
     def strip_halo_floats(self):

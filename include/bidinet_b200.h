@@ -249,9 +249,14 @@ int bidi_set_option(bidi_engine* h, const char* name, int value);
  * bidi_strip_configure must precede bidi_init_random / bidi_set_array.  Two transports:
  *   - same process (one host thread drives all parts, any mix of devices, peer copies
  *     over NVLink): bidi_strip_link_local, then bidi_strip_step_local per step;
- *   - one process per GPU (torchrun): bidi_strip_nccl_unique_id on rank 0, ship the
- *     128 bytes to every rank, bidi_strip_link_nccl, then plain bidi_step /
- *     bidi_step_frame; halos go through ncclSend/ncclRecv on the engine's stream.
+ *   - one process per GPU (torchrun), peer memory: every rank calls bidi_strip_ipc_export,
+ *     the 128-byte records are gathered to all ranks (any host channel), then
+ *     bidi_strip_link_ipc and plain bidi_step / bidi_step_frame.  One small kernel per
+ *     exchange point stores the halo rows straight into the neighbours' memory over
+ *     NVLink, raises a flag there and waits for theirs; the whole step is one CUDA graph;
+ *   - one process per GPU, NCCL: bidi_strip_nccl_unique_id on rank 0, ship the 128 bytes
+ *     to every rank, bidi_strip_link_nccl; halos go through ncclSend/ncclRecv on the
+ *     engine's stream (also inside the step's graph).
  * bidi_get_predictions / bidi_get_array return whole-grid arrays of which only the rows
  * the part owns are meaningful (bidi_strip_plan tells which).
  */
@@ -273,6 +278,8 @@ int bidi_strip_link_local(bidi_engine** parts, int n_parts);
 int bidi_strip_step_local(bidi_engine** parts, int n_parts, int learn);
 /* frames variant of the above: every part steps on frame t of its loaded frames */
 int bidi_strip_step_frame_local(bidi_engine** parts, int n_parts, int t, int learn);
+int bidi_strip_ipc_export(bidi_engine* h, void* handle128);
+int bidi_strip_link_ipc(bidi_engine* h, const void* handles /* [n_parts][128] */);
 int bidi_strip_nccl_unique_id(void* id128);
 int bidi_strip_link_nccl(bidi_engine* h, const void* id128);
 /* floats this part sends per step over the transport (all exchange points, learn on) */

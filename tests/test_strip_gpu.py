@@ -82,13 +82,18 @@ def test_unlinked_part_refuses_to_step():
     e.close()
 
 
-# ---- NCCL transport: one process per GPU
-def _nccl_worker(rank, world, uid, g, steps, q):
+# ---- NCCL and peer-memory transports: one process per GPU
+def _nccl_worker(rank, world, uid, g, steps, q, pipes=None):
     try:
         cfg, ld = _cfg(g)
         e = Engine(cfg, ld, device=rank)
         e.strip_configure(rank, world)
-        e.strip_link_nccl(uid)
+        if uid is not None:
+            e.strip_link_nccl(uid)
+        else:  # CUDA IPC: every part exports its handles, all parts get all of them
+            to_parent, from_parent = pipes
+            to_parent.put((rank, e.strip_ipc_export()))
+            e.strip_link_ipc(from_parent.get(timeout=300))
         orc = OracleHierarchy(cfg, ld, 1234)   # only to produce the identical initial state
         e.load_state(orc.state())
         frames = _frames(g)
@@ -102,18 +107,28 @@ def _nccl_worker(rank, world, uid, g, steps, q):
         q.put((rank, None, repr(ex), None))
 
 
-def test_nccl_strips_match_the_whole_layer():
+@pytest.mark.parametrize("transport", ["nccl", "ipc"])
+def test_multi_process_strips_match_the_whole_layer(transport):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     g, world, steps = GEOMS[0], 2, 6
-    uid = nccl_unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, world, uid, g, steps, q)) for r in range(world)]
-    for p in procs:
-        p.start()
+    if transport == "nccl":
+        uid = nccl_unique_id()
+        procs = [ctx.Process(target=_nccl_worker, args=(r, world, uid, g, steps, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+    else:
+        up, down = ctx.Queue(), [ctx.Queue() for _ in range(world)]
+        procs = [ctx.Process(target=_nccl_worker, args=(r, world, None, g, steps, q, (up, down[r]))) for r in range(world)]
+        for p in procs:
+            p.start()
+        handles = dict(up.get(timeout=600) for _ in procs)
+        for d in down:
+            d.put([handles[r] for r in range(world)])
     got = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
     for p in procs:
         p.join(timeout=60)
