@@ -21,6 +21,7 @@
 #include "bidi_coder_dense.cuh"
 #include "bidi_tiles.cuh"
 #include "bidi_grid.cuh"
+#include "bidi_coop.cuh"
 
 namespace {
 
@@ -131,6 +132,9 @@ struct bidi_engine {
   float** d_peer_blob = nullptr; unsigned** d_peer_flags = nullptr;
   bidi::StripXferDev* d_sends = nullptr; int* d_notify = nullptr; int* d_await = nullptr;
   struct PushArgs { int send0, n_sends, notify0, n_notify, await0, n_await; } push[5] = {};
+  // whole step as one cooperative launch (bidi_coop.cuh): the program per value of `learn`
+  int coop_mode = 0;                               // option "coop_step": 1 = use it when every layer runs the tile kernels (measured no faster than the graph: off by default)
+  bidi::CoopOp* d_coop_ops[2] = {nullptr, nullptr}; int coop_n[2] = {0, 0}; int coop_grid = 0; size_t coop_smem = 0;
   bool strip_use_graph = true;                     // record the split step (NCCL exchanges included) into a CUDA graph
   cudaEvent_t strip_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t strip_done = nullptr;
@@ -365,6 +369,43 @@ constexpr int kBlock = 128;
 struct Recorder {
   bidi_engine* h;
   int kernels = 0;
+  // collect mode: the launches become the program of the cooperative step kernel instead
+  std::vector<bidi::CoopOp>* collect = nullptr;
+  bool collect_ok = true;
+  size_t collect_smem = 0;
+  int collect_blocks = 0;
+  struct Pack {
+    bidi::CoopOp op;
+    void put(int v) { if (op.ni < 5) iv[op.ni++] = v; }
+    void put(float v) { if (op.nf < 2) op.f[op.nf++] = v; }
+    void put(long long v) { if (op.na < 3) op.a[op.na++] = v; }
+    void put(const LayerDev&) { has_layer = true; }
+    int iv[5] = {0, 0, 0, 0, 0};
+    bool has_layer = false;
+  };
+  template <class... Args> void add_op(const void* kernel, long long blocks, size_t smem, Args... args) {
+    static const std::pair<const void*, int> table[] = {
+        {(const void*)bidi::k_t_kw_activate, bidi::OP_KW_ACTIVATE}, {(const void*)bidi::k_t_kw_inhibit, bidi::OP_KW_INHIBIT},
+        {(const void*)bidi::k_t_reconstruct, bidi::OP_RECONSTRUCT}, {(const void*)bidi::k_t_kw_learn, bidi::OP_KW_LEARN},
+        {(const void*)bidi::k_t_ic_sweep, bidi::OP_IC_SWEEP},       {(const void*)bidi::k_t_ic_learn, bidi::OP_IC_LEARN},
+        {(const void*)bidi::k_t_predict, bidi::OP_PREDICT},         {(const void*)bidi::k_ic_finish, bidi::OP_IC_FINISH},
+        {(const void*)bidi::k_step_end, bidi::OP_STEP_END}};
+    int code = 0;
+    for (const auto& e : table) if (e.first == kernel) code = e.second;
+    if (!code) { collect_ok = false; return; }
+    Pack p;
+    memset(&p.op, 0, sizeof(p.op));
+    (p.put(args), ...);
+    p.op.code = code; p.op.blocks = (int)blocks;
+    // the first int after a layer descriptor is the layer index; the other ints follow
+    const int skip = p.has_layer ? 1 : 0;
+    p.op.l = p.has_layer ? p.iv[0] : 0;
+    for (int k = skip; k < p.op.ni; k++) p.op.i[k - skip] = p.iv[k];
+    p.op.ni -= skip;
+    collect->push_back(p.op);
+    collect_smem = std::max(collect_smem, smem);
+    collect_blocks = std::max(collect_blocks, (int)blocks);
+  }
   // bracket a launch with external event records when its kernel is the one being profiled
   bool profiled(const char* name) const { return !h->profile_name.empty() && h->profile_name == name; }
   void before(const char* name) {
@@ -378,14 +419,9 @@ struct Recorder {
     if (profiled(name)) cudaEventRecordWithFlags(h->profile_events.back().second, h->stream, cudaEventRecordExternal);
   }
   template <class K, class... Args> void launch(const char* name, K kernel, long long threads, Args... args) {
+    if (collect) { add_op((const void*)kernel, grid_for(threads, TILE_U * TILE_G), 0, args...); return; }
     before(name);
-    // few threads (one large single agent): one warp per block, so the warps spread over
-    // all SMs and each gets a whole SM's load/store path to hide its latency with
-#ifdef BIDI_SMALL_BLOCKS
-    const int block = threads < 148LL * 2 * kBlock ? 32 : kBlock;
-#else
     const int block = kBlock;
-#endif
     kernel<<<grid_for(threads, block), block, 0, h->stream>>>(h->P, args...);
     after(name);
     kernels++;
@@ -405,6 +441,7 @@ int columns_pairs_per_warp(const ColumnsDev& C) {
 }
 template <class K, class... Args>
 void launch_tile(Recorder& R, const char* name, K kernel, long long tiles, size_t smem, Args... args) {
+  if (R.collect) { R.add_op((const void*)kernel, tiles, smem, args...); return; }
   R.before(name);
   kernel<<<(unsigned)tiles, TILE_U * TILE_G, smem, R.h->stream>>>(R.h->P, args...);
   R.after(name);
@@ -436,6 +473,7 @@ void record_columns(Recorder& R, int l) {
 template <class K, class... Args>
 void launch_grid(Recorder& R, const char* name, K kernel, long long blocks, size_t smem_floats, Args... args) {
   if (blocks <= 0) return;
+  if (R.collect) { R.collect_ok = false; return; }
   R.before(name);
   kernel<<<(unsigned)blocks, GRID_TX * GRID_TY, sizeof(float) * smem_floats, R.h->stream>>>(R.h->P, args...);
   R.after(name);
@@ -481,7 +519,7 @@ void record_step(Recorder& R, bool learn) {
     for (int l = 0; l < L; l++) {
       const LayerDev& Y = ly[l];
       const long long nxt = l < L - 1 ? ly[l + 1].vis_input : -1LL;
-      if (h->gridk[l].on) {
+      if (h->gridk[l].on && !R.collect) {
         const auto& G = h->gridk[l];
         const long long th = A * bidi::grid_tiles(Y.hw, Y.hh), tv = A * bidi::grid_tiles(Y.vw, Y.vh);
         launch_grid(R, "kw_activate", bidi::k_g_kw_activate, th, G.ff + G.rec, Y, l, G.ff);
@@ -502,7 +540,7 @@ void record_step(Recorder& R, bool learn) {
     for (int l = L - 1; l >= 0; l--) {
       const LayerDev& Y = ly[l];
       const LayerDev& Up = ly[l < L - 1 ? l + 1 : l];
-      if (h->gridk[l].on) {
+      if (h->gridk[l].on && !R.collect) {
         const auto& G = h->gridk[l];
         const long long th = A * bidi::grid_tiles(Y.hw, Y.hh);
         launch_grid(R, "predict", bidi::k_g_kw_predict, th, G.fb + G.pred, Y, l, (int)learn, Up.p_state, Up.p_state_prev, G.fb);
@@ -519,13 +557,13 @@ void record_step(Recorder& R, bool learn) {
     // :173-185
     if (learn)
       for (int l = 0; l < L; l++) {
-        if (h->gridk[l].on) launch_grid(R, "kw_learn", bidi::k_g_kw_learn, A * bidi::grid_tiles(ly[l].hw, ly[l].hh), 0, ly[l], l);
+        if (h->gridk[l].on && !R.collect) launch_grid(R, "kw_learn", bidi::k_g_kw_learn, A * bidi::grid_tiles(ly[l].hw, ly[l].hh), 0, ly[l], l);
         else if (h->tiled[l]) launch_tile(R, "kw_learn", bidi::k_t_kw_learn, tiles_of(A, ly[l].nh), 0, ly[l], l);
         else R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, ly[l], l);
       }
     R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
     // :188-193
-    if (h->gridk[0].on) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather);
+    if (h->gridk[0].on && !R.collect) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather);
     else if (h->tiled[0])
       launch_tile(R, "kw_predict_input", bidi::k_t_reconstruct, tiles_of(A, ly[0].nv), tile_bytes(ly[0].ff.max_cand), ly[0], 0, ly[0].p_state, 0,
                   0.0f, 0, 1);
@@ -534,7 +572,7 @@ void record_step(Recorder& R, bool learn) {
   }
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
-    if (h->coder_cta[l] && !h->force_phase_kernels) { // whole up pass of the layer in one launch
+    if (h->coder_cta[l] && !h->force_phase_kernels && !R.collect) { // whole up pass of the layer in one launch
       const long long nxt = l < L - 1 ? ly[l + 1].vis_input : -1LL;
       R.before("coder");
       if (h->coder_cta[l] == 2) {  // windows span the grid: dense rows (bidi_coder_dense.cuh)
@@ -625,10 +663,57 @@ int ensure_graph(bidi_engine* h, bool learn) {
 
 int strip_step_nccl(bidi_engine* h, bool learn);
 
+struct Recorder;
+void record_step(Recorder& R, bool learn);
+// every layer on the tile kernels, no columns, not a strip of a split layer
+bool coop_eligible(const bidi_engine* h) {
+  if (h->coop_mode == 0 || h->cfg.variant == BIDI_NEO_AGENT || h->strip_n > 1 || !h->profile_name.empty()) return false;
+  const int n = h->cfg.variant == BIDI_KWINNERS ? h->L : h->L + 1;
+  for (int l = 0; l < n; l++) if (!h->tiled[l]) return false;
+  return true;
+}
+void coop_release(bidi_engine* h) {
+  for (int k = 0; k < 2; k++) { cudaFree(h->d_coop_ops[k]); h->d_coop_ops[k] = nullptr; h->coop_n[k] = 0; }
+}
+// 1: the program for `learn` is ready; 0: this engine cannot run the step cooperatively
+int ensure_coop(bidi_engine* h, bool learn) {
+  if (h->d_coop_ops[learn]) return 1;
+  int coop = 0;
+  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device) != cudaSuccess || !coop) { h->coop_mode = 0; return 0; }
+  std::vector<bidi::CoopOp> ops;
+  Recorder R{h};
+  R.collect = &ops;
+  record_step(R, learn);
+  if (!R.collect_ok || ops.empty()) { h->coop_mode = 0; return 0; }
+  const size_t smem = std::max(h->coop_smem, R.collect_smem);
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(bidi::k_step_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError(); h->coop_mode = 0; return 0;
+  }
+  int per_sm = 0, sms = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bidi::k_step_coop, TILE_U * TILE_G, smem);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+  if (per_sm < 1 || sms < 1) { h->coop_mode = 0; return 0; }
+  h->coop_smem = smem;
+  h->coop_grid = std::max(1, std::min(per_sm * sms, std::max(R.collect_blocks, h->coop_grid)));
+  if (cudaMalloc(&h->d_coop_ops[learn], sizeof(bidi::CoopOp) * ops.size()) != cudaSuccess) { cudaGetLastError(); h->coop_mode = 0; return 0; }
+  cudaMemcpy(h->d_coop_ops[learn], ops.data(), sizeof(bidi::CoopOp) * ops.size(), cudaMemcpyHostToDevice);
+  h->coop_n[learn] = (int)ops.size();
+  return 1;
+}
+
 int run_step(bidi_engine* h, bool learn, bool device_noise) {
   int rc = mirror_release(h);
   if (rc) return rc;
   if (h->strip_n > 1) return strip_step_nccl(h, learn);
+  if (coop_eligible(h) && ensure_coop(h, learn)) {
+    const bidi::CoopOp* ops = h->d_coop_ops[learn];
+    int n = h->coop_n[learn];
+    void* args[] = {&h->P, &ops, &n};
+    CU(cudaLaunchCooperativeKernel((const void*)bidi::k_step_coop, dim3(h->coop_grid), dim3(TILE_U * TILE_G), args, h->coop_smem, h->stream));
+    h->launches += 1;
+    h->step_index++;
+    return BIDI_OK;
+  }
   if (h->cfg.variant == BIDI_NEO_AGENT && device_noise) {
     // the step counter changes every call, so this launch stays outside the graph
     bidi::k_noise<<<grid_for((long long)h->A * h->ncol, kBlock), kBlock, 0, h->stream>>>(
@@ -671,6 +756,7 @@ void bidi_destroy(bidi_engine* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   strip_release(h);
+  coop_release(h);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1271,6 +1357,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     if (rc) return rc;
   }
   else if (std::string(name) == "strip_graph") h->strip_use_graph = value != 0;
+  else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
       size_t smem = 0;
@@ -1287,6 +1374,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   }
   else return fail(h, BIDI_EINVAL, "bidi_set_option: unknown option");
   for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  coop_release(h);
   return BIDI_OK;
 }
 

@@ -305,8 +305,11 @@ __global__ void k_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, f
 // End of the up pass of one layer: neo: state *= 1/counter (neo/SparseCoder.cpp:171-175);
 // then the next layer's input = state (x the column's _attention action for
 // neo::Agent, neo/Agent.cpp:147-151).
-__global__ void k_ic_finish(EngineDev P, LayerDev L, int l, int scale_state, float mult, long long next_vis_input) {
-  BIDI_THREAD_AGENT_HIDDEN
+__device__ __forceinline__ void d_ic_finish(const EngineDev& P, const LayerDev& L, int l, int scale_state, float mult, long long next_vis_input, long long gid_) {
+  const int n_ = (L.row1 - L.row0) * L.hw;
+  if (gid_ >= (long long)P.A * n_) return;
+  const int a = (int)(gid_ / n_);
+  const int i = L.row0 * L.hw + (int)(gid_ % n_);
   float* B = blob_of(P, a);
   float st = B[L.state + i];
   if (scale_state) { st *= mult; B[L.state + i] = st; }
@@ -314,6 +317,9 @@ __global__ void k_ic_finish(EngineDev P, LayerDev L, int l, int scale_state, flo
     if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + i * 3 + 0];
     B[next_vis_input + i] = st;
   }
+}
+__global__ void k_ic_finish(EngineDev P, LayerDev L, int l, int scale_state, float mult, long long next_vis_input) {
+  d_ic_finish(P, L, l, scale_state, mult, next_vis_input, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // lateral anti-Hebbian + threshold homeostasis: sdr/IRSDR.cpp:313-317
@@ -457,8 +463,10 @@ __global__ void k_predict_input(EngineDev P, LayerDev L, int learn, long long p0
 
 // stepEnd of every layer + the *_Prev copies: sdr/PredictiveRSDR.cpp:177-184,
 // sdr/IPredictiveRSDR.cpp:224-239
-__global__ void k_step_end(EngineDev P, int max_units) {
-  BIDI_THREAD_AGENT_UNIT(max_units)
+__device__ __forceinline__ void d_step_end(const EngineDev& P, int max_units, long long gid_) {
+  if (gid_ >= (long long)P.A * max_units) return;
+  const int a = (int)(gid_ / max_units);
+  const int i = (int)(gid_ % max_units);
   float* B = blob_of(P, a);
   const int nl = P.variant == BIDI_KWINNERS ? P.L : P.L + 1;
   for (int l = 0; l < nl; l++) {
@@ -470,6 +478,7 @@ __global__ void k_step_end(EngineDev P, int max_units) {
     }
   }
 }
+__global__ void k_step_end(EngineDev P, int max_units) { d_step_end(P, max_units, (long long)blockIdx.x * blockDim.x + threadIdx.x); }
 
 // The same for one row strip of a split layer (bidi_strip.inl): the winners are kept on
 // hidden rows [s0,s1) (owned rows plus the halo later phases read), the prediction

@@ -19,11 +19,11 @@ namespace bidi {
 #define TILE_G 8
 
 struct TileId { int a, u0, ul, g, unit; bool ok; };
-__device__ __forceinline__ TileId tile_id(int n_units) {
+__device__ __forceinline__ TileId tile_id(int n_units, int bid) {
   TileId t;
   const int tiles = (n_units + TILE_U - 1) / TILE_U;
-  t.a = blockIdx.x / tiles;
-  t.u0 = (blockIdx.x % tiles) * TILE_U;
+  t.a = bid / tiles;
+  t.u0 = (bid % tiles) * TILE_U;
   t.ul = threadIdx.x & 31;
   t.g = threadIdx.x >> 5;
   t.unit = t.u0 + t.ul;
@@ -81,9 +81,9 @@ __device__ __forceinline__ float tile_sum(const float* __restrict__ Pbuf, int ba
 }
 
 // ---- sdr/RSDR.cpp:123-133
-__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_activate(EngineDev P, LayerDev L, int l) {
+__device__ __forceinline__ void t_kw_activate(const EngineDev& P, const LayerDev& L, int l, int bid) {
   extern __shared__ float Pbuf[];
-  const TileId T = tile_id(L.nh);
+  const TileId T = tile_id(L.nh, bid);
   float* B = blob_of(P, T.a);
   const float* x = vis_input_of(P, L, l, T.a);
   const float* sprev = B + L.state_prev;
@@ -95,9 +95,9 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_activate(EngineDev P, L
 }
 
 // ---- sdr/RSDR.cpp:135-163
-__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_inhibit(EngineDev P, LayerDev L, int l, long long src, long long dst, long long dst_next) {
+__device__ __forceinline__ void t_kw_inhibit(const EngineDev& P, const LayerDev& L, int l, long long src, long long dst, long long dst_next, int bid) {
   __shared__ int s_n[TILE_G][TILE_U], s_c[TILE_G][TILE_U];
-  const TileId T = tile_id(L.nh);
+  const TileId T = tile_id(L.nh, bid);
   float* B = blob_of(P, T.a);
   const float* act = B + src;
   const float mine = T.ok ? act[T.unit] : 0.0f;
@@ -117,11 +117,10 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_inhibit(EngineDev P, La
 // ---- reconstruction (gather): sdr/RSDR.cpp:165-212, sdr/IRSDR.cpp:218-254, neo/SparseCoder.cpp:242-259
 // mode 0: tiles [0,tv) reconstruct the visible layer, the rest the hidden one; mode 1:
 // _prediction = reconstructFeedForward(layer-0 predicted states) (sdr/PredictiveRSDR.cpp:188-193)
-__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_reconstruct(EngineDev P, LayerDev L, int l, long long drive_off, int scaled, float mult,
-                                                                    int copy_spike, int mode) {
+__device__ __forceinline__ void t_reconstruct(const EngineDev& P, const LayerDev& L, int l, long long drive_off, int scaled, float mult, int copy_spike, int mode, int bid) {
   extern __shared__ float Pbuf[];
   const int tv = (L.nv + TILE_U - 1) / TILE_U, th = mode ? 0 : (L.nh + TILE_U - 1) / TILE_U;
-  const int a = blockIdx.x / (tv + th), tile = blockIdx.x % (tv + th);
+  const int a = bid / (tv + th), tile = bid % (tv + th);
   const bool vis = tile < tv;
   const int ul = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int n_targets = vis ? L.nv : L.nh, target = (vis ? tile : tile - tv) * TILE_U + ul;
@@ -162,8 +161,8 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_reconstruct(EngineDev P, L
 }
 
 // ---- sdr/RSDR.cpp:241-266 (winners only)
-__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_learn(EngineDev P, LayerDev L, int l) {
-  const TileId T = tile_id(L.nh);
+__device__ __forceinline__ void t_kw_learn(const EngineDev& P, const LayerDev& L, int l, int bid) {
+  const TileId T = tile_id(L.nh, bid);
   float* B = blob_of(P, T.a);
   if (!T.ok) return;
   const float* x = vis_input_of(P, L, l, T.a);
@@ -184,9 +183,9 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_learn(EngineDev P, Laye
 }
 
 // ---- one sweep of the iterative coders, per phase: sdr/IRSDR.cpp:138-168
-__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale) {
+__device__ __forceinline__ void t_ic_sweep(const EngineDev& P, const LayerDev& L, int l, int first, int acc, float scale, int bid) {
   extern __shared__ float Pbuf[];
-  const TileId T = tile_id(L.nh);
+  const TileId T = tile_id(L.nh, bid);
   float* B = blob_of(P, T.a);
   const float* x = vis_input_of(P, L, l, T.a);
   const float* vrec = B + L.vis_recon;
@@ -217,8 +216,8 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_sweep(EngineDev P, Laye
 
 // ---- coder learning of the iterative variants: sdr/IRSDR.cpp:287-319, neo/SparseCoder.cpp:326-361
 // (+ the reward of neo/Agent.cpp:252-265).  traced = 0: Hebbian; 1: eligibility traces.
-__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_learn(EngineDev P, LayerDev L, int l, int traced) {
-  const TileId T = tile_id(L.nh);
+__device__ __forceinline__ void t_ic_learn(const EngineDev& P, const LayerDev& L, int l, int traced, int bid) {
+  const TileId T = tile_id(L.nh, bid);
   float* B = blob_of(P, T.a);
   const float* x = vis_input_of(P, L, l, T.a);
   const float* vrec = B + L.vis_recon;
@@ -277,10 +276,9 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_learn(EngineDev P, Laye
 
 // ---- down pass of node layer l (all variants but neo::Agent, whose columns come first):
 // sdr/PredictiveRSDR.cpp:122-160, sdr/IPredictiveRSDR.cpp:156-194.  l == P.L: the input nodes.
-__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_predict(EngineDev P, LayerDev L, int l, int learn, long long up_p_state,
-                                                                long long up_p_state_prev) {
+__device__ __forceinline__ void t_predict(const EngineDev& P, const LayerDev& L, int l, int learn, long long up_p_state, long long up_p_state_prev, int bid) {
   extern __shared__ float Pbuf[];
-  const TileId T = tile_id(L.pn);
+  const TileId T = tile_id(L.pn, bid);
   float* B = blob_of(P, T.a);
   const bool input_layer = l == P.L, top = l == P.L - 1;
   const float* up_state = B + up_p_state;
@@ -325,5 +323,14 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_predict(EngineDev P, Layer
     else if (P.variant != BIDI_KWINNERS) B[L.p_state + i] = bidi_clamp01(activation);
   }
 }
+
+// ---- kernel wrappers: one CTA per tile
+__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_activate(EngineDev P, LayerDev L, int l) { t_kw_activate(P, L, l, (int)blockIdx.x); }
+__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_inhibit(EngineDev P, LayerDev L, int l, long long src, long long dst, long long dst_next) { t_kw_inhibit(P, L, l, src, dst, dst_next, (int)blockIdx.x); }
+__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_reconstruct(EngineDev P, LayerDev L, int l, long long drive_off, int scaled, float mult, int copy_spike, int mode) { t_reconstruct(P, L, l, drive_off, scaled, mult, copy_spike, mode, (int)blockIdx.x); }
+__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_learn(EngineDev P, LayerDev L, int l) { t_kw_learn(P, L, l, (int)blockIdx.x); }
+__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale) { t_ic_sweep(P, L, l, first, acc, scale, (int)blockIdx.x); }
+__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_learn(EngineDev P, LayerDev L, int l, int traced) { t_ic_learn(P, L, l, traced, (int)blockIdx.x); }
+__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_predict(EngineDev P, LayerDev L, int l, int learn, long long up_p_state, long long up_p_state_prev) { t_predict(P, L, l, learn, up_p_state, up_p_state_prev, (int)blockIdx.x); }
 
 } // namespace bidi

@@ -42,23 +42,27 @@ def test_init_random_matches_oracle(case):
         assert diff_states(orc.state(), eng.state(agent=a)) == [], "agent %d" % a
 
 
-@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
+@pytest.mark.parametrize("path", ["default", "coop", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
 @pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
 def test_free_running_parity(case, path):
     """N steps from an identical state, no re-synchronisation: exact after every step.
-    Every engine path is held to it: the default (fused per-agent coder kernel where the
+    Every engine path is held to it: the default (a CUDA graph; fused per-agent coder kernel where the
     layer fits in shared memory -- its dense-row form where the windows span the grid --
     and cooperative tile kernels for small launches), the general fused coder kernel
-    everywhere, one
+    everywhere, the whole step as ONE cooperative launch that interprets the phase list, one
     kernel per phase with the tile kernels (large single agents), one kernel per
     phase with one thread per unit (large agent batches), and the 2-D grid-tile kernels
     (very large k-winners layers)."""
     name, cfg, ld, frame, reward = case
     orc = OracleHierarchy(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1)
+    if path == "coop":  # the whole step as one cooperative launch interpreting the phase list
+        if cfg.variant == cf.NEO_AGENT:
+            pytest.skip("no columns in the cooperative step")
+        eng.set_option("coop_step", True)
     if path == "fused_general":
         eng.set_option("dense_coder", False)
-    elif path != "default":
+    elif path not in ("default", "coop"):
         eng.set_option("force_phase_kernels", True)
     if path == "per_phase_threads":
         eng.set_option("tile_kernels", False)

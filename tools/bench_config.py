@@ -32,6 +32,9 @@ def run(name, cfg, ld, frame, gpu_steps, cpu_steps, parity_steps):
     cls = RefHierarchy if have_ref() else OracleHierarchy
     ref = cls(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1, seed=1234)
+    for kv in filter(None, os.environ.get("BIDI_OPTS", "").split(",")):  # e.g. BIDI_OPTS=grid_kernels=2
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     # exact parity of the first steps at full size (the engine replays createRandom itself)
     ok = True
     for t in range(parity_steps):
@@ -66,7 +69,8 @@ def run(name, cfg, ld, frame, gpu_steps, cpu_steps, parity_steps):
     out = {"config": name, "variant": cf.VARIANT_NAMES[cfg.variant], "gpu_ms_per_step": gpu_ms, "e2e_ms_per_step": e2e_ms,
            "cpu_ms_per_step_1core": cpu_ms, "cpu_kind": "reference" if have_ref() else "port",
            "speedup_resident": cpu_ms / gpu_ms, "speedup_e2e": cpu_ms / e2e_ms, "launches_per_step": launches,
-           "parity_exact_first_steps": bool(ok), "parity_steps": parity_steps, "device_MB": eng.device_bytes / 1e6}
+           "parity_exact_first_steps": bool(ok), "parity_steps": parity_steps, "device_MB": eng.device_bytes / 1e6,
+           "options": os.environ.get("BIDI_OPTS", "")}
     print(json.dumps(out), flush=True)
     eng.close()
 
