@@ -157,6 +157,22 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
       const bool measuring = !NEO && it >= L.iter_settle;
       float sp = 0.0f, av = 0.0f, stv = 0.0f;
       if (i < nh) {
+        // the lateral weights of the first few spiking neighbours are fetched from HBM/L2 now,
+        // so that their latency hides behind the excitation sums (an absent entry adds +0)
+        constexpr int LATQ = 8;
+        const int r = L.lat.r, ux = i % hw, uy = i / hw;
+        float lw[LATQ];
+#pragma unroll
+        for (int e = 0; e < LATQ; e++) {
+          lw[e] = 0.0f;
+          if (e < n_spk) {
+            const int cc = lat_list[e], tx = cc & 0xffff, ty = cc >> 16, dx = tx - ux, dy = ty - uy;
+            if (dx >= -r && dx <= r && dy >= -r && dy <= r && (dx | dy) != 0) {
+              const int sx = L.lat.absx ? tx : dx + r, sy = L.lat.absy ? ty : dy + r;
+              lw[e] = wlat[(long long)(sx * L.lat.dyn + sy) * nh + i];
+            }
+          }
+        }
         float excitation = 0.0f;
         const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wff + i * S.Sf);
 #pragma unroll 4
@@ -175,8 +191,9 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
           }
         }
         float inhibition = 0.0f;
-        const int r = L.lat.r, ux = i % hw, uy = i / hw;
-        for (int e = 0; e < n_spk; e++) {
+#pragma unroll
+        for (int e = 0; e < LATQ; e++) inhibition += lw[e];
+        for (int e = LATQ; e < n_spk; e++) {
           const int cc = lat_list[e], tx = cc & 0xffff, ty = cc >> 16, dx = tx - ux, dy = ty - uy;
           if (dx >= -r && dx <= r && dy >= -r && dy <= r && (dx | dy) != 0) {
             const int sx = L.lat.absx ? tx : dx + r, sy = L.lat.absy ? ty : dy + r;
