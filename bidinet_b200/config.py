@@ -9,9 +9,10 @@ members of the hierarchy objects (sdr/IPredictiveRSDR.h:101-105, neo/Agent.h:137
 """
 import ctypes as C
 
-KWINNERS, ITERATIVE, NEO_HIERARCHY, NEO_AGENT = 0, 1, 2, 3
+KWINNERS, ITERATIVE, NEO_HIERARCHY, NEO_AGENT, QPRSDR = 0, 1, 2, 3, 4
+MAX_ACTIONS = 64
 VARIANT_NAMES = {KWINNERS: "kwinners", ITERATIVE: "iterative",
-                 NEO_HIERARCHY: "neo_hierarchy", NEO_AGENT: "neo_agent"}
+                 NEO_HIERARCHY: "neo_hierarchy", NEO_AGENT: "neo_agent", QPRSDR: "qprsdr"}
 COLUMN_ACTIONS = 3
 
 ARRAY_NAMES = [
@@ -25,10 +26,12 @@ ARRAY_NAMES = [
     "COL_THRESHOLD", "COL_ACTIVATION", "COL_SPIKE", "COL_SPIKE_PREV", "COL_STATE",
     "COL_Q_W", "COL_Q_TRACE", "COL_ACT_STATE", "COL_ACT_EXPL", "COL_ACT_W", "COL_ACT_TRACE",
     "COL_PREV_VALUE", "PREDICTION",
+    "Q_STATE", "Q_ERROR", "Q_BIAS_W", "Q_BIAS_TRACE", "Q_FF_W", "Q_FF_TRACE",
+    "QCONN_W", "QCONN_TRACE", "ACT_PREDICTED", "ACT_DERIVE", "ACT_EXPL", "ACT_ERROR", "Q_PREV_VALUE",
 ]
 ARRAY = {n: i for i, n in enumerate(ARRAY_NAMES)}
 # arrays that hold a per-unit connection list (bidi_conn_counts is defined for them)
-LIST_ARRAYS = ("FF_W", "REC_W", "LAT_W", "FB_W", "PRED_W", "COL_INPUT")
+LIST_ARRAYS = ("FF_W", "REC_W", "LAT_W", "FB_W", "PRED_W", "COL_INPUT", "Q_FF_W")
 
 
 class LayerDesc(C.Structure):
@@ -67,6 +70,10 @@ class Config(C.Structure):
         ("col_expl_stddev", C.c_float), ("col_expl_break", C.c_float),
         ("init_min_w", C.c_float), ("init_max_w", C.c_float),
         ("init_min_inh", C.c_float), ("init_max_inh", C.c_float), ("init_threshold", C.c_float),
+        ("q_alpha", C.c_float), ("q_action_alpha", C.c_float), ("q_derive_alpha", C.c_float),
+        ("q_expl_break", C.c_float), ("q_expl_stddev", C.c_float), ("q_gamma", C.c_float), ("q_gamma_lambda", C.c_float),
+        ("q_derive_iterations", C.c_int), ("q_n_actions", C.c_int),
+        ("q_action_idx", C.c_int * MAX_ACTIONS), ("q_anti_idx", C.c_int * MAX_ACTIONS),
     ]
 
 
@@ -97,8 +104,12 @@ _LAYER_DEFAULTS = {
         baseline_decay=0.01, sensitivity=6.0),
 }
 _LAYER_DEFAULTS[NEO_AGENT] = dict(_LAYER_DEFAULTS[NEO_HIERARCHY], **_COLUMN_DEFAULTS)
+_LAYER_DEFAULTS[QPRSDR] = _LAYER_DEFAULTS[ITERATIVE]  # sdr::QPRSDR owns an sdr::IPredictiveRSDR
 
-_LEARN_INFB = {KWINNERS: 0.0, ITERATIVE: 0.05, NEO_HIERARCHY: 0.1, NEO_AGENT: 0.1}
+_LEARN_INFB = {KWINNERS: 0.0, ITERATIVE: 0.05, NEO_HIERARCHY: 0.1, NEO_AGENT: 0.1, QPRSDR: 0.05}
+# sdr/QPRSDR.h:96-106
+_Q_DEFAULTS = dict(q_alpha=0.01, q_action_alpha=0.1, q_derive_iterations=32, q_derive_alpha=0.05,
+                   q_expl_break=0.01, q_expl_stddev=0.05, q_gamma=0.99, q_gamma_lambda=0.98)
 
 
 def layer_desc(variant, **overrides):
@@ -115,7 +126,7 @@ def layer_desc(variant, **overrides):
 
 
 def make_config(variant, in_width, in_height, layers, r_infb=0,
-                init=(-0.01, 0.01, 0.01, 0.05, 0.1), **overrides):
+                init=(-0.01, 0.01, 0.01, 0.05, 0.1), actions=(), anti_actions=(), **overrides):
     """(Config, LayerDesc array) for ``variant``.
 
     ``layers`` is a list of dicts of LayerDesc overrides (at least width/height) or
@@ -133,6 +144,12 @@ def make_config(variant, in_width, in_height, layers, r_infb=0,
     cfg.learn_infb = _LEARN_INFB[variant]
     for k, v in _COLUMN_DEFAULTS.items():
         setattr(cfg, k, v)
+    for k, v in _Q_DEFAULTS.items():
+        setattr(cfg, k, v)
+    assert len(actions) == len(anti_actions) <= MAX_ACTIONS
+    cfg.q_n_actions = len(actions)
+    for k, (a, b) in enumerate(zip(actions, anti_actions)):
+        cfg.q_action_idx[k], cfg.q_anti_idx[k] = a, b
     (cfg.init_min_w, cfg.init_max_w, cfg.init_min_inh, cfg.init_max_inh,
      cfg.init_threshold) = init
     for k, v in overrides.items():
@@ -153,6 +170,13 @@ def config_experiment_prediction():
     """Experiment_Prediction.cpp:113-126: input 2x2, 16^2 -> 12^2 -> 8^2, inFB 16, threshold 0."""
     layers = [dict(width=16, height=16), dict(width=12, height=12), dict(width=8, height=8)]
     return make_config(ITERATIVE, 2, 2, layers, r_infb=16, init=(-0.01, 0.01, 0.01, 0.05, 0.0))
+
+
+def config_q_small():
+    """A small sdr::QPRSDR: input 8x8 (cells 40..47 actions, 48..55 their complements), layers 8^2 -> 4^2."""
+    layers = [dict(width=8, height=8), dict(width=4, height=4)]
+    return make_config(QPRSDR, 8, 8, layers, r_infb=4, actions=list(range(40, 48)), anti_actions=list(range(48, 56)),
+                       init=(-0.3, 0.3, 0.01, 0.05, 0.0))  # lively from the first steps: non-zero Q values, errors and traces
 
 
 def config_c2():

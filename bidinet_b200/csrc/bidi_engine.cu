@@ -22,6 +22,7 @@
 #include "bidi_tiles.cuh"
 #include "bidi_grid.cuh"
 #include "bidi_coop.cuh"
+#include "bidi_qnet.cuh"
 
 namespace {
 
@@ -132,6 +133,12 @@ struct bidi_engine {
   float** d_peer_blob = nullptr; unsigned** d_peer_flags = nullptr;
   bidi::StripXferDev* d_sends = nullptr; int* d_notify = nullptr; int* d_await = nullptr;
   struct PushArgs { int send0, n_sends, notify0, n_notify, await0, n_await; } push[5] = {};
+  // sdr::QPRSDR: the engine runs the ITERATIVE hierarchy (cfg.variant is normalised to it) plus the Q network
+  bool qnet = false;
+  int q_half = 0, q_top = 0, n_noise = 0;           // n_noise: floats per agent in noise_u / noise_v
+  std::vector<std::vector<char>> q_keep;            // per layer: [slot][unit] the reference keeps the connection
+  std::vector<int> q_act_index, q_a_input;
+  float* d_qmask = nullptr; int* d_qtables = nullptr;
   // whole step as one cooperative launch (bidi_coop.cuh): the program per value of `learn`
   int coop_mode = 0;                               // option "coop_step": 1 = use it when every layer runs the tile kernels (measured no faster than the graph: off by default)
   bidi::CoopOp* d_coop_ops[2] = {nullptr, nullptr}; int coop_n[2] = {0, 0}; int coop_grid = 0; size_t coop_smem = 0;
@@ -224,7 +231,7 @@ bool is_traced(int v) { return v == BIDI_NEO_HIERARCHY || v == BIDI_NEO_AGENT; }
 // ------------------------------------------------------------------ array table
 // How a serialised array (include/bidinet_b200.h enum bidi_array) maps to storage.
 struct ArrayRef {
-  enum Kind { NONE, PLANE, LIST, DENSE_IN, DENSE_PRED, COLUMN } kind = NONE;
+  enum Kind { NONE, PLANE, LIST, DENSE_IN, DENSE_PRED, COLUMN, QLIST } kind = NONE;
   long long off = 0, len = 0;   // PLANE: blob offset and length
   const WinHost* win = nullptr; // LIST
   bool trace = false;
@@ -280,6 +287,34 @@ ArrayRef find_array(const bidi_engine* h, int which, int layer) {
     case BIDI_P_BASELINE: return layer == L ? r : plane(D.p_baseline, D.pn);
     case BIDI_FB_W: return list(H.fb, false);
     case BIDI_PRED_W: return layer == L ? r : list(H.pred, false);
+  }
+  if (h->qnet && which >= BIDI_Q_STATE) {
+    if (layer < L) {
+      switch (which) {
+        case BIDI_Q_STATE: return plane(D.q_state, D.nh);
+        case BIDI_Q_ERROR: return plane(D.q_err, D.nh);
+        case BIDI_Q_BIAS_W: return plane(D.q_bias_w, D.nh);
+        case BIDI_Q_BIAS_TRACE: return plane(D.q_bias_tr, D.nh);
+        case BIDI_Q_FF_W: case BIDI_Q_FF_TRACE: {
+          r.kind = ArrayRef::QLIST; r.win = &H.ff; r.trace = which == BIDI_Q_FF_TRACE; r.layer = layer;
+          long long n = 0;
+          for (char c : h->q_keep[layer]) n += c;
+          r.len = n;
+          return r;
+        }
+      }
+    }
+    if (layer != 0) return r;
+    switch (which) {
+      case BIDI_QCONN_W: return plane(h->P.q_qc_w, h->q_top);
+      case BIDI_QCONN_TRACE: return plane(h->P.q_qc_tr, h->q_top);
+      case BIDI_ACT_PREDICTED: return plane(h->P.q_act, 2 * h->q_half);
+      case BIDI_ACT_DERIVE: return plane(h->P.q_act + 2 * h->q_half, 2 * h->q_half);
+      case BIDI_ACT_EXPL: return plane(h->P.q_act + 4 * h->q_half, 2 * h->q_half);
+      case BIDI_ACT_ERROR: return plane(h->P.q_act + 6 * h->q_half, 2 * h->q_half);
+      case BIDI_Q_PREV_VALUE: return plane(h->P.q_prev, 1);
+    }
+    return r;
   }
   if (V != BIDI_NEO_AGENT) return r;
   const ColumnsDev& C = D.col;
@@ -338,6 +373,20 @@ template <class F> void walk_list(const WinHost& w, bool trace, float* blob, F&&
     for (int ux = 0; ux < w.d.uw; ux++) {
       const long long u = ux + (long long)uy * w.d.uw;
       for_each_conn_host(w, ux, uy, [&](int s, int) { f(base[(long long)s * U + u]); });
+    }
+}
+
+// The Q network's kept connections (sdr/QPRSDR.cpp:72-81) <-> its slot planes.
+template <class F> void walk_qlist(const bidi_engine* h, int layer, bool trace, float* blob, F&& f) {
+  const WinHost& w = h->hl[layer].ff;
+  const LayerDev& D = h->layers[layer];
+  float* base = blob + (trace ? D.q_tr_off : D.q_w_off);
+  const std::vector<char>& keep = h->q_keep[layer];
+  const long long U = w.d.U;
+  for (int uy = 0; uy < w.d.uh; uy++)
+    for (int ux = 0; ux < w.d.uw; ux++) {
+      const long long u = ux + (long long)uy * w.d.uw;
+      for_each_conn_host(w, ux, uy, [&](int s, int) { if (keep[(size_t)s * U + u]) f(base[(long long)s * U + u]); });
     }
 }
 
@@ -642,6 +691,13 @@ void record_step(Recorder& R, bool learn) {
       else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
     }
   R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
+  if (h->qnet) {  // sdr/QPRSDR.cpp:102-341, after _prsdr.simStep
+    if (R.collect) { R.collect_ok = false; return; }
+    R.before("qnet");
+    bidi::k_qnet<<<(unsigned)A, 256, 0, h->stream>>>(h->P, (int)learn);
+    R.after("qnet");
+    R.kernels++;
+  }
 }
 
 int ensure_graph(bidi_engine* h, bool learn) {
@@ -714,6 +770,10 @@ int run_step(bidi_engine* h, bool learn, bool device_noise) {
     h->step_index++;
     return BIDI_OK;
   }
+  if (h->qnet && device_noise) {
+    bidi::k_noise_q<<<grid_for((long long)h->A * h->q_half, kBlock), kBlock, 0, h->stream>>>(h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index);
+    h->launches++;
+  }
   if (h->cfg.variant == BIDI_NEO_AGENT && device_noise) {
     // the step counter changes every call, so this launch stays outside the graph
     bidi::k_noise<<<grid_for((long long)h->A * h->ncol, kBlock), kBlock, 0, h->stream>>>(
@@ -751,6 +811,7 @@ void bidi_destroy(bidi_engine* h) {
   cudaFree(h->d_blob); cudaFree(h->d_in0); cudaFree(h->d_pred); cudaFree(h->d_rewards); cudaFree(h->d_noise_u);
   cudaFree(h->d_noise_v); cudaFree(h->d_col_actions); cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
   cudaFree(h->d_tables); cudaFree(h->d_layers); cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
+  cudaFree(h->d_qmask); cudaFree(h->d_qtables);
   for (auto& e : h->profile_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_pred); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_noise); cudaFreeHost(h->h_actions);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -765,7 +826,16 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   bidi_engine* h = nullptr;
   if (!cfg || !layers || !out) return fail(h, BIDI_EINVAL, "bidi_create: null argument");
   *out = nullptr;
-  if (cfg->variant < BIDI_KWINNERS || cfg->variant > BIDI_NEO_AGENT) return fail(h, BIDI_EINVAL, "bidi_create: unknown variant");
+  if (cfg->variant < BIDI_KWINNERS || cfg->variant > BIDI_QPRSDR) return fail(h, BIDI_EINVAL, "bidi_create: unknown variant");
+  const bool qnet = cfg->variant == BIDI_QPRSDR;
+  if (qnet) {
+    if (cfg->q_n_actions < 1 || cfg->q_n_actions > BIDI_MAX_ACTIONS || cfg->q_derive_iterations < 0)
+      return fail(h, BIDI_EINVAL, "bidi_create: a QPRSDR needs 1..BIDI_MAX_ACTIONS actions");
+    for (int k = 0; k < cfg->q_n_actions; k++)
+      if (cfg->q_action_idx[k] < 0 || cfg->q_action_idx[k] >= cfg->in_width * cfg->in_height || cfg->q_anti_idx[k] < 0 ||
+          cfg->q_anti_idx[k] >= cfg->in_width * cfg->in_height)
+        return fail(h, BIDI_EINVAL, "bidi_create: action index outside the input");
+  }
   if (cfg->n_layers < 1 || cfg->n_layers > BIDI_MAX_LAYERS) return fail(h, BIDI_EINVAL, "bidi_create: n_layers out of range");
   if (n_agents < 1 || cfg->in_width < 1 || cfg->in_height < 1) return fail(h, BIDI_EINVAL, "bidi_create: bad sizes");
   int ndev = 0;
@@ -773,7 +843,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     cudaGetLastError();
     return fail(h, BIDI_ENODEV, "bidi_create: no usable CUDA device (this engine has no CPU path)");
   }
-  const int V = cfg->variant, L = cfg->n_layers;
+  const int V = qnet ? BIDI_ITERATIVE : cfg->variant, L = cfg->n_layers;  // a QPRSDR owns an IPredictiveRSDR
   for (int l = 0; l < L; l++) {
     const bidi_layer_desc& d = layers[l];
     if (d.width < 1 || d.height < 1 || d.r_ff < 0 || d.r_lat < 0 || d.r_pred < 0 || d.r_rec < -1 || (l < L - 1 && d.r_fb < 0))
@@ -789,6 +859,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
 
   h = new bidi_engine();
   h->cfg = *cfg; h->ld.assign(layers, layers + L);
+  h->cfg.variant = V; h->qnet = qnet;
   h->device = device; h->A = n_agents; h->L = L; h->n_in = cfg->in_width * cfg->in_height;
   h->layers.assign(L + 1, LayerDev());
   h->hl.resize(L + 1);
@@ -827,6 +898,10 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       build_win(H.pred, D.hw, D.hh, D.hw, D.hh, d.r_pred, true, false);
       if (l < L - 1) H.fb.d.w_off = al.take((long long)H.fb.d.nslots * D.pn);
       H.pred.d.w_off = al.take((long long)H.pred.d.nslots * D.pn);
+      if (qnet) {
+        D.q_state = al.take(D.nh); D.q_err = al.take(D.nh); D.q_bias_w = al.take(D.nh); D.q_bias_tr = al.take(D.nh);
+        D.q_w_off = al.take((long long)H.ff.d.nslots * D.nh); D.q_tr_off = al.take((long long)H.ff.d.nslots * D.nh);
+      }
       D.learn_ff = d.learn_ff; D.learn_rec = d.learn_rec; D.learn_lat = d.learn_lat; D.learn_threshold = d.learn_threshold;
       D.learn_fb = d.learn_fb; D.learn_pred = d.learn_pred; D.sparsity = d.sparsity;
       D.avg_surprise_decay = d.avg_surprise_decay; D.attention_factor = d.attention_factor;
@@ -893,6 +968,35 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       C.a_state = al.take(C.n * 3LL); C.a_expl = al.take(C.n * 3LL);
     }
   }
+  long long q_qc_w = 0, q_qc_tr = 0, q_act = 0, q_prev = 0;
+  if (qnet) {  // sdr/QPRSDR.cpp:13-31,86-96
+    h->q_half = cfg->q_n_actions; h->q_top = layers[L - 1].width * layers[L - 1].height; h->n_noise = h->q_half;
+    q_qc_w = al.take(h->q_top); q_qc_tr = al.take(h->q_top); q_act = al.take(8LL * h->q_half); q_prev = al.take(1);
+    h->q_act_index.assign(h->n_in, -1);
+    h->q_a_input.assign(2 * h->q_half, 0);
+    for (int k = 0; k < h->q_half; k++) {
+      h->q_act_index[cfg->q_action_idx[k]] = k;
+      h->q_a_input[k] = cfg->q_action_idx[k]; h->q_a_input[h->q_half + k] = cfg->q_anti_idx[k];
+    }
+    // kept connections: layer 0 sees the action inputs, a higher layer the nodes below that kept any (sdr/QPRSDR.cpp:72-81)
+    h->q_keep.resize(L);
+    std::vector<char> below_any;
+    for (int l = 0; l < L; l++) {
+      const WinHost& w = h->hl[l].ff;
+      const long long U = w.d.U;
+      h->q_keep[l].assign((size_t)w.d.nslots * U, 0);
+      std::vector<char> any((size_t)U, 0);
+      for (int uy = 0; uy < w.d.uh; uy++)
+        for (int ux = 0; ux < w.d.uw; ux++) {
+          const long long u = ux + (long long)uy * w.d.uw;
+          for_each_conn_host(w, ux, uy, [&](int s, int t) {
+            const bool keep = l == 0 ? h->q_act_index[t] != -1 : below_any[t] != 0;
+            if (keep) { h->q_keep[l][(size_t)s * U + u] = 1; any[u] = 1; }
+          });
+        }
+      below_any.swap(any);
+    }
+  }
   h->stride = al.top;
   if (V == BIDI_NEO_AGENT) {
     if (h->stride >= (1LL << 31)) { delete h; return fail(nullptr, BIDI_EINVAL, "bidi_create: agent state too large for 32-bit gather offsets"); }
@@ -921,6 +1025,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     for (int l = L - 1; l >= 0; l--) { h->layers[l].col.noise_base = base; base += h->layers[l].col.n; }
     h->layers[L].col.noise_base = base; base += h->layers[L].col.n;
     h->ncol = base;
+    h->n_noise = base * 3;
   }
 
   // ---- device memory
@@ -935,7 +1040,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   CU_CREATE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU_CREATE(cudaEventCreate(&h->ev0));
   CU_CREATE(cudaEventCreate(&h->ev1));
-  const size_t A = (size_t)n_agents, nin = (size_t)h->n_in, nn = std::max<size_t>(1, (size_t)h->ncol * 3);
+  const size_t A = (size_t)n_agents, nin = (size_t)h->n_in, nn = std::max<size_t>(1, (size_t)h->n_noise);
   CU_CREATE(cudaMalloc(&h->d_blob, sizeof(float) * A * (size_t)h->stride));
   CU_CREATE(cudaMemsetAsync(h->d_blob, 0, sizeof(float) * A * (size_t)h->stride, h->stream));
   CU_CREATE(cudaMalloc(&h->d_in0, sizeof(float) * A * nin));
@@ -987,6 +1092,18 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     LayerHost& H = h->hl[l];
     D.ff = H.ff.d; D.rec = H.rec.d; D.lat = H.lat.d; D.fb = H.fb.d; D.pred = H.pred.d;
   }
+  if (qnet) {  // one 0/1 mask per layer for all agents
+    size_t tot = 0;
+    for (int l = 0; l < L; l++) tot += h->q_keep[l].size();
+    std::vector<float> mask;
+    mask.reserve(tot);
+    for (int l = 0; l < L; l++) for (char c : h->q_keep[l]) mask.push_back(c ? 1.0f : 0.0f);
+    CU_CREATE(cudaMalloc(&h->d_qmask, sizeof(float) * std::max<size_t>(1, tot)));
+    CU_CREATE(cudaMemcpy(h->d_qmask, mask.data(), sizeof(float) * tot, cudaMemcpyHostToDevice));
+    size_t off = 0;
+    for (int l = 0; l < L; l++) { h->layers[l].q_mask = h->d_qmask + off; off += h->q_keep[l].size(); }
+    h->device_bytes += (long long)(sizeof(float) * tot);
+  }
   CU_CREATE(cudaMalloc(&h->d_layers, sizeof(LayerDev) * (L + 1)));
   CU_CREATE(cudaMemcpyAsync(h->d_layers, h->layers.data(), sizeof(LayerDev) * (L + 1), cudaMemcpyHostToDevice, h->stream));
   h->device_bytes += (long long)(sizeof(int) * pool.size() + sizeof(LayerDev) * (L + 1));
@@ -996,6 +1113,18 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   P.blob = h->d_blob; P.stride = h->stride; P.in0 = h->d_in0; P.pred_out = h->d_pred;
   P.rewards = h->d_rewards; P.noise_u = h->d_noise_u; P.noise_v = h->d_noise_v; P.col_actions = h->d_col_actions;
   P.ncol = h->ncol; P.layers = h->d_layers;
+  P.q_on = qnet ? 1 : 0;
+  if (qnet) {
+    P.q_half = h->q_half; P.q_top = h->q_top; P.q_iters = cfg->q_derive_iterations;
+    P.q_qc_w = q_qc_w; P.q_qc_tr = q_qc_tr; P.q_act = q_act; P.q_prev = q_prev;
+    P.q_alpha = cfg->q_alpha; P.q_action_alpha = cfg->q_action_alpha; P.q_derive_alpha = cfg->q_derive_alpha;
+    P.q_expl_break = cfg->q_expl_break; P.q_gamma = cfg->q_gamma; P.q_gamma_lambda = cfg->q_gamma_lambda; P.q_expl_std = cfg->q_expl_stddev;
+    std::vector<int> tab(h->q_act_index);
+    tab.insert(tab.end(), h->q_a_input.begin(), h->q_a_input.end());
+    CU_CREATE(cudaMalloc(&h->d_qtables, sizeof(int) * tab.size()));
+    CU_CREATE(cudaMemcpy(h->d_qtables, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
+    P.q_act_index = h->d_qtables; P.q_a_input = h->d_qtables + h->n_in;
+  }
   {  // constants the packed-pair arithmetic must not see at compile time (bidi_columns.cuh)
     const float one[2] = {1.0f, 1.0f}, negzero[2] = {-0.0f, -0.0f}, negone[2] = {-1.0f, -1.0f};
     memcpy(&P.k_one2, one, 8); memcpy(&P.k_negzero2, negzero, 8); memcpy(&P.k_negone2, negone, 8);
@@ -1076,6 +1205,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
 int bidi_num_agents(const bidi_engine* h) { return h ? h->A : 0; }
 int bidi_num_inputs(const bidi_engine* h) { return h ? h->n_in : 0; }
 int bidi_num_columns(const bidi_engine* h) { return h ? h->ncol : 0; }
+int bidi_num_noise(const bidi_engine* h) { return h ? h->n_noise : 0; }
 long long bidi_launch_count(const bidi_engine* h) { return h ? h->launches : 0; }
 long long bidi_device_bytes(const bidi_engine* h) { return h ? h->device_bytes : 0; }
 
@@ -1095,6 +1225,16 @@ int bidi_conn_counts(const bidi_engine* h, int which, int layer, int* counts, in
     case BIDI_LAT_W: w = &H.lat; break;
     case BIDI_FB_W: w = &H.fb; break;
     case BIDI_PRED_W: w = &H.pred; break;
+    case BIDI_Q_FF_W: {
+      if (!h->qnet || layer >= h->L || n_units != h->layers[layer].nh) return fail(hm, BIDI_EINVAL, "bidi_conn_counts: bad Q network query");
+      const WinHost& qw = H.ff;
+      for (int i = 0; i < n_units; i++) {
+        int n = 0;
+        for_each_conn_host(qw, i % qw.d.uw, i / qw.d.uw, [&](int s, int) { n += h->q_keep[layer][(size_t)s * qw.d.U + i]; });
+        counts[i] = n;
+      }
+      return BIDI_OK;
+    }
     case BIDI_COL_INPUT:
       if (h->cfg.variant != BIDI_NEO_AGENT || n_units != h->layers[layer].col.n) return fail(hm, BIDI_EINVAL, "bidi_conn_counts: bad column query");
       for (int i = 0; i < n_units; i++) counts[i] = H.col.in_off[i + 1] - H.col.in_off[i];
@@ -1132,6 +1272,7 @@ int bidi_set_array(bidi_engine* h, int agent, int which, int layer, const float*
   if (rc) return rc;
   if (r.kind == ArrayRef::PLANE) memcpy(h->mirror.data() + r.off, src, sizeof(float) * len);
   else if (r.kind == ArrayRef::COLUMN) walk_column(h, r.which, r.layer, h->mirror.data(), [&](float& v) { v = *src++; });
+  else if (r.kind == ArrayRef::QLIST) walk_qlist(h, r.layer, r.trace, h->mirror.data(), [&](float& v) { v = *src++; });
   else walk_list(*r.win, r.trace, h->mirror.data(), [&](float& v) { v = *src++; });
   h->mirror_dirty = true;
   return BIDI_OK;
@@ -1152,6 +1293,7 @@ int bidi_get_array(bidi_engine* h, int agent, int which, int layer, float* dst, 
   if (rc) return rc;
   if (r.kind == ArrayRef::PLANE) memcpy(dst, h->mirror.data() + r.off, sizeof(float) * len);
   else if (r.kind == ArrayRef::COLUMN) walk_column(h, r.which, r.layer, h->mirror.data(), [&](float& v) { *dst++ = v; });
+  else if (r.kind == ArrayRef::QLIST) walk_qlist(h, r.layer, r.trace, h->mirror.data(), [&](float& v) { *dst++ = v; });
   else walk_list(*r.win, r.trace, h->mirror.data(), [&](float& v) { *dst++ = v; });
   return BIDI_OK;
 }
@@ -1211,6 +1353,21 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
         if (V == BIDI_NEO_AGENT) draw_column(D.col, H.col, i);
       }
     }
+    if (h->qnet) {  // sdr/QPRSDR.cpp:30-31, then per layer and node: bias, one draw per in-bounds slot -- kept or not (:50-83)
+      for (int i = 0; i < h->q_top; i++) img[h->P.q_qc_w + i] = weightDist(gen) / static_cast<float>(h->q_top);
+      for (int l = 0; l < L; l++) {
+        const LayerDev& D = h->layers[l];
+        const WinHost& w = h->hl[l].ff;
+        const long long U = w.d.U;
+        for (int i = 0; i < D.nh; i++) {
+          img[D.q_bias_w + i] = weightDist(gen);
+          for_each_conn_host(w, i % D.hw, i / D.hw, [&](int s, int) {
+            const float v = weightDist(gen);
+            if (h->q_keep[l][(size_t)s * U + i]) img[D.q_w_off + (long long)s * U + i] = v;
+          });
+        }
+      }
+    }
   };
   std::vector<std::thread> pool;
   std::vector<cudaError_t> cuerr(nthreads, cudaSuccess);
@@ -1251,14 +1408,14 @@ int bidi_step(bidi_engine* h, const float* rewards, const float* noise_u, const 
   if (!h) return fail(h, BIDI_EINVAL, "null engine");
   if ((noise_u == nullptr) != (noise_v == nullptr)) return fail(h, BIDI_EINVAL, "bidi_step: noise_u and noise_v go together");
   CU(cudaSetDevice(h->device));
-  const bool agent = h->cfg.variant == BIDI_NEO_AGENT;
+  const bool agent = h->cfg.variant == BIDI_NEO_AGENT || h->qnet;  // variants with a reward and exploration draws
   if (agent) {
     CU(cudaStreamSynchronize(h->stream));
     if (rewards) memcpy(h->h_rewards, rewards, sizeof(float) * h->A);
     else memset(h->h_rewards, 0, sizeof(float) * h->A);
     CU(cudaMemcpyAsync(h->d_rewards, h->h_rewards, sizeof(float) * h->A, cudaMemcpyHostToDevice, h->stream));
     if (noise_u) {
-      const size_t n = (size_t)h->A * h->ncol * 3;
+      const size_t n = (size_t)h->A * h->n_noise;
       memcpy(h->h_noise, noise_u, sizeof(float) * n);
       memcpy(h->h_noise + n, noise_v, sizeof(float) * n);
       CU(cudaMemcpyAsync(h->d_noise_u, h->h_noise, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
@@ -1286,6 +1443,30 @@ int bidi_get_column_actions(bidi_engine* h, float* out) {
   CU(cudaStreamSynchronize(h->stream));
   memcpy(out, h->h_actions, bytes);
   return BIDI_OK;
+}
+
+int bidi_get_actions(bidi_engine* h, float* out) {
+  if (!h || !out || !h->qnet) return fail(h, BIDI_EINVAL, "bidi_get_actions: not a QPRSDR engine");
+  CU(cudaSetDevice(h->device));
+  const size_t row = sizeof(float) * 2 * (size_t)h->q_half;
+  CU(cudaMemcpy2DAsync(out, row, h->d_blob + h->P.q_act + 4 * h->q_half, sizeof(float) * (size_t)h->stride, row, (size_t)h->A,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BIDI_OK;
+}
+
+/* which of a layer's in-bounds feed-forward window slots the Q network keeps, list order (sdr/QPRSDR.cpp:72-81) */
+int bidi_q_kept(const bidi_engine* h, int layer, unsigned char* kept, long long len) {
+  bidi_engine* hm = const_cast<bidi_engine*>(h);
+  if (!h || !kept || !h->qnet || layer < 0 || layer >= h->L) return fail(hm, BIDI_EINVAL, "bidi_q_kept: bad argument");
+  const WinHost& w = h->hl[layer].ff;
+  long long k = 0;
+  for (int uy = 0; uy < w.d.uh; uy++)
+    for (int ux = 0; ux < w.d.uw; ux++) {
+      const long long u = ux + (long long)uy * w.d.uw;
+      for_each_conn_host(w, ux, uy, [&](int s, int) { if (k < len) kept[k] = (unsigned char)h->q_keep[layer][(size_t)s * w.d.U + u]; k++; });
+    }
+  return k == len ? BIDI_OK : fail(hm, BIDI_EINVAL, "bidi_q_kept: length mismatch");
 }
 
 int bidi_load_frames(bidi_engine* h, const float* frames, const float* rewards, int n_frames) {
@@ -1319,7 +1500,7 @@ int bidi_step_frame(bidi_engine* h, int t, int learn) {
                                                                       h->fb_reward ? h->d_rewards : nullptr);
     h->launches++;
   }
-  return run_step(h, learn != 0, h->cfg.variant == BIDI_NEO_AGENT);
+  return run_step(h, learn != 0, h->cfg.variant == BIDI_NEO_AGENT || h->qnet);
 }
 
 int bidi_set_feedback(bidi_engine* h, int n, const int* src, const int* dst, float scale, float bias, float noise_std,

@@ -98,6 +98,11 @@ struct LayerDev {
   int pn;                           // number of prediction nodes (nh, or n_in for the input nodes)
   long long p_state, p_state_prev, p_act, p_act_prev, p_baseline, p_mod; // p_mod: attention / reward scratch
   WinDev fb, pred;
+  // sdr::QPRSDR's Q layer over this layer's grid (bidi_qnet.cuh): same window geometry as `ff`;
+  // weight/trace slot planes, per-node planes; q_mask[slot][unit] = 1 where the reference keeps the
+  // connection (one copy for all agents, outside the blobs)
+  long long q_state, q_err, q_bias_w, q_bias_tr, q_w_off, q_tr_off;
+  const float* q_mask;
   ColumnsDev col;
   // hyper-parameters (bidi_layer_desc)
   float learn_ff, learn_rec, learn_lat, learn_threshold, learn_fb, learn_pred, sparsity;
@@ -121,6 +126,12 @@ struct EngineDev {
   // {1,1}, {-0,-0}, {-1,-1} as packed f32x2 bit patterns.  Passed at run time so that
   // ptxas cannot fold fma(a,b,-0) / fma(a,1,c) back into a fused multiply-add.
   unsigned long long k_one2, k_negzero2, k_negone2;
+  // sdr::QPRSDR (bidi_qnet.cuh)
+  int q_on, q_half, q_top, q_iters;       // 0/1; actions; nodes of the top layer; _actionDeriveIterations
+  long long q_qc_w, q_qc_tr, q_act, q_prev; // blob offsets: _qConnections (w, trace), action nodes [4][2*half], _prevValue
+  const int* q_act_index;                 // [n_in] input cell -> action node, -1 if none
+  const int* q_a_input;                   // [2*half] action node -> input cell
+  float q_alpha, q_action_alpha, q_derive_alpha, q_expl_break, q_gamma, q_gamma_lambda, q_expl_std;
 };
 
 #endif

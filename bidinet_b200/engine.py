@@ -26,6 +26,9 @@ ABI = {
     "bidi_num_agents": (C.c_int, [C.c_void_p]),
     "bidi_num_inputs": (C.c_int, [C.c_void_p]),
     "bidi_num_columns": (C.c_int, [C.c_void_p]),
+    "bidi_num_noise": (C.c_int, [C.c_void_p]),
+    "bidi_get_actions": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_q_kept": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ubyte), C.c_longlong]),
     "bidi_array_len": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int]),
     "bidi_conn_counts": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _IP, C.c_int]),
     "bidi_set_array": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _FP, C.c_longlong]),
@@ -104,6 +107,7 @@ class Engine:
             raise BidiError("bidi_create failed (%d): %s" % (rc, self.lib.bidi_last_error(None).decode()))
         self.h = h
         self.n_columns = self.lib.bidi_num_columns(self.h)
+        self.n_noise = self.lib.bidi_num_noise(self.h)
         if seed is not None:
             self.init_random(seed)
 
@@ -178,13 +182,19 @@ class Engine:
         if noise is not None:
             u = np.ascontiguousarray(noise[0], dtype=np.float32)
             v = np.ascontiguousarray(noise[1], dtype=np.float32)
-            assert u.size == v.size == self.n_agents * self.n_columns * 3
+            assert u.size == v.size == self.n_agents * self.n_noise
         self._check(self.lib.bidi_step(self.h, None if r is None else _fptr(r), None if u is None else _fptr(u),
                                        None if v is None else _fptr(v), int(bool(learn))), "bidi_step")
 
     def get_predictions(self):
         out = np.zeros((self.n_agents, self.n_in), dtype=np.float32)
         self._check(self.lib.bidi_get_predictions(self.h, _fptr(out)), "bidi_get_predictions")
+        return out
+
+    def get_actions(self):
+        """sdr::QPRSDR::getActionRel of every action node: [agent][2*n_actions] (actions, then anti-actions)."""
+        out = np.zeros((self.n_agents, 2 * self.cfg.q_n_actions), dtype=np.float32)
+        self._check(self.lib.bidi_get_actions(self.h, _fptr(out)), "bidi_get_actions")
         return out
 
     def get_column_actions(self):

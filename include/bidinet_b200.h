@@ -29,13 +29,15 @@ extern "C" {
 
 #define BIDI_MAX_LAYERS 16
 #define BIDI_COLUMN_ACTIONS 3 /* neo/Agent.h:9-11 _attention,_learnPrediction,_signal */
+#define BIDI_MAX_ACTIONS 64  /* action inputs of an sdr::QPRSDR */
 
 /* Which reference hierarchy the engine reproduces. */
 enum bidi_variant {
   BIDI_KWINNERS = 0,      /* sdr::PredictiveRSDR    sdr/PredictiveRSDR.cpp:100-194 */
   BIDI_ITERATIVE = 1,     /* sdr::IPredictiveRSDR   sdr/IPredictiveRSDR.cpp:138-240 */
   BIDI_NEO_HIERARCHY = 2, /* neo::PredictiveHierarchy neo/PredictiveHierarchy.cpp:137-245 */
-  BIDI_NEO_AGENT = 3      /* neo::Agent             neo/Agent.cpp:141-284 */
+  BIDI_NEO_AGENT = 3,     /* neo::Agent             neo/Agent.cpp:141-284 */
+  BIDI_QPRSDR = 4         /* sdr::QPRSDR: sdr::IPredictiveRSDR + the Q network and action derivation, sdr/QPRSDR.cpp:99-341 */
 };
 
 enum bidi_status {
@@ -88,6 +90,13 @@ typedef struct bidi_config {
   float col_expl_stddev, col_expl_break;
   /* createRandom arguments (sdr/IPredictiveRSDR.h:107) */
   float init_min_w, init_max_w, init_min_inh, init_max_inh, init_threshold;
+  /* sdr::QPRSDR only: public members (sdr/QPRSDR.h:84-107) and the action lists of its
+   * createRandom (sdr/QPRSDR.h:109): q_n_actions input cells carry actions, as many carry
+   * their complements ("anti-actions", value 1 - action) */
+  float q_alpha, q_action_alpha, q_derive_alpha, q_expl_break, q_expl_stddev, q_gamma, q_gamma_lambda;
+  int q_derive_iterations;
+  int q_n_actions;
+  int q_action_idx[BIDI_MAX_ACTIONS], q_anti_idx[BIDI_MAX_ACTIONS];
 } bidi_config;
 
 /*
@@ -117,6 +126,13 @@ enum bidi_array {
   BIDI_COL_PREV_VALUE,                            /* [node] */
   /* sdr::PredictiveRSDR::_prediction (sdr/PredictiveRSDR.h:77), layer 0 only */
   BIDI_PREDICTION,
+  /* sdr::QPRSDR (sdr/QPRSDR.h:10-55).  Per Q layer (= hierarchy layer): */
+  BIDI_Q_STATE, BIDI_Q_ERROR, BIDI_Q_BIAS_W, BIDI_Q_BIAS_TRACE, /* [node] */
+  BIDI_Q_FF_W, BIDI_Q_FF_TRACE,                  /* kept connections only, node after node, list order */
+  /* layer 0 only: */
+  BIDI_QCONN_W, BIDI_QCONN_TRACE,                /* _qConnections, one per node of the top layer */
+  BIDI_ACT_PREDICTED, BIDI_ACT_DERIVE, BIDI_ACT_EXPL, BIDI_ACT_ERROR, /* _actionNodes: actions, then anti-actions */
+  BIDI_Q_PREV_VALUE,                             /* [1] */
   BIDI_ARRAY_COUNT
 };
 
@@ -172,8 +188,8 @@ int bidi_set_input(bidi_engine* h, int agent, int index, float value);
 /*
  * simStep (sdr/PredictiveRSDR.h:82, sdr/IPredictiveRSDR.h:109, neo/Agent.h:148)
  * for all agents: one pass bottom-up coding -> top-down prediction -> learning.
- *   rewards  [n_agents] host, NEO_AGENT only (NULL = 0)
- *   noise_u, noise_v  [n_agents][n_columns][3] host, NEO_AGENT only: the values
+ *   rewards  [n_agents] host, NEO_AGENT and QPRSDR (NULL = 0)
+ *   noise_u, noise_v  [n_agents][bidi_num_noise] host; NEO_AGENT ([n_columns][3]): the values
  *            the reference draws per column visit (neo/Column.cpp:126-131):
  *            u = dist01(gen); v = u < breakChance ? dist01(gen) : pertDist(gen).
  *            Column visit order = layers top -> bottom, nodes ascending, then the
@@ -185,6 +201,20 @@ int bidi_set_input(bidi_engine* h, int agent, int index, float value);
 int bidi_step(bidi_engine* h, const float* rewards, const float* noise_u, const float* noise_v,
               int learn);
 int bidi_num_columns(const bidi_engine* h);
+/*
+ * Floats per agent in each of bidi_step's noise_u / noise_v: 3 per column for NEO_AGENT;
+ * one per action for QPRSDR, whose simStep draws, per action i, u = dist01(gen) and then
+ * v = u < _explorationBreak ? dist01(gen) : pertDist(gen) (sdr/QPRSDR.cpp:205-213).
+ */
+int bidi_num_noise(const bidi_engine* h);
+/* sdr::QPRSDR::getActionRel(i) (sdr/QPRSDR.h:124) of every action node: out[agent][2*q_n_actions]. */
+int bidi_get_actions(bidi_engine* h, float* out);
+/*
+ * QPRSDR: which of a layer's feed-forward window slots (the in-bounds ones, list order, node after
+ * node -- bidi_conn_counts(BIDI_FF_W) of them per node) the Q network keeps: createRandom draws a
+ * weight for every such slot and keeps it only on a path from an action input (sdr/QPRSDR.cpp:70-81).
+ */
+int bidi_q_kept(const bidi_engine* h, int layer, unsigned char* kept, long long len);
 
 /*
  * getPrediction(index) for every input of every agent (sdr/PredictiveRSDR.h:92,

@@ -113,10 +113,27 @@ typedef struct {
   columns col;
 } pnodes;
 
+/* sdr::QPRSDR (sdr/QPRSDR.h:10-75): a sparse Q network over the hierarchy's grids; only
+ * connections on a path from an action input are kept (sdr/QPRSDR.cpp:72-81). */
+typedef struct {
+  int n;
+  float *state, *err, *bias_w, *bias_tr;
+  conns ff; /* kept connections; idx = input cell (layer 0) or node of the layer below */
+} qlayer;
+typedef struct {
+  int half, n_nodes, n_top; /* actions; action nodes = 2*half; nodes of the top layer */
+  qlayer ql[BIDI_MAX_LAYERS];
+  float *qc_w, *qc_tr;
+  float *a_pred, *a_derive, *a_expl, *a_err;
+  int *a_input, *act_index; /* node -> input cell; input cell -> action node or -1 */
+  float prev_value[1];
+} qnet;
+
 typedef struct {
   bidi_config cfg;
   bidi_layer_desc ld[BIDI_MAX_LAYERS];
   int L, n_in;
+  qnet q;
   coder cod[BIDI_MAX_LAYERS];
   pnodes pn[BIDI_MAX_LAYERS + 1]; /* pn[L] = input prediction nodes */
   float* prediction;              /* k-winners only */
@@ -193,6 +210,57 @@ static void column_create_random(oracle* o, columns* c, int node, float thr) {
   }
   for (int a = 0; a < 3; a++)
     for (int k = 0; k < cells; k++) c->a_w[((size_t)node * 3 + a) * cells + k] = uniform_real(&o->gen, g->init_min_w, g->init_max_w);
+}
+
+/* sdr/QPRSDR.cpp:8-97, after _prsdr.createRandom has consumed its draws. */
+static void q_create_random(oracle* o) {
+  const bidi_config* g = &o->cfg;
+  qnet* q = &o->q;
+  const int L = o->L;
+  q->half = g->q_n_actions; q->n_nodes = 2 * q->half;
+  q->act_index = (int*)calloc((size_t)o->n_in, sizeof(int));
+  for (int i = 0; i < o->n_in; i++) q->act_index[i] = -1;
+  for (int i = 0; i < q->half; i++) q->act_index[g->q_action_idx[i]] = i; /* :13-20 (anti indices are never looked up) */
+  q->n_top = o->ld[L - 1].width * o->ld[L - 1].height;
+  q->qc_w = fzeros(q->n_top); q->qc_tr = fzeros(q->n_top);
+  for (int i = 0; i < q->n_top; i++) q->qc_w[i] = uniform_real(&o->gen, g->init_min_w, g->init_max_w) / (float)q->n_top; /* :30-31 */
+  int wp = g->in_width, hp = g->in_height;
+  for (int l = 0; l < L; l++) {
+    const bidi_layer_desc* d = &o->ld[l];
+    qlayer* ql = &q->ql[l];
+    ql->n = d->width * d->height;
+    ql->state = fzeros(ql->n); ql->err = fzeros(ql->n); ql->bias_w = fzeros(ql->n); ql->bias_tr = fzeros(ql->n);
+    const float rx = (float)wp / (float)d->width, ry = (float)hp / (float)d->height;
+    /* worst case: every in-bounds slot kept */
+    const int span = 2 * d->r_ff + 1;
+    ql->ff.n_units = ql->n;
+    ql->ff.off = (int*)calloc((size_t)ql->n + 1, sizeof(int));
+    ql->ff.idx = (int*)calloc((size_t)ql->n * span * span + 1, sizeof(int));
+    ql->ff.w = fzeros((size_t)ql->n * span * span); ql->ff.tr = fzeros((size_t)ql->n * span * span);
+    int k = 0;
+    for (int qi = 0; qi < ql->n; qi++) {
+      ql->ff.off[qi] = k;
+      ql->bias_w[qi] = uniform_real(&o->gen, g->init_min_w, g->init_max_w); /* :50 */
+      const int hx = qi % d->width, hy = qi / d->width;
+      const int cx = (int)roundf((float)hx * rx), cy = (int)roundf((float)hy * ry);
+      for (int dx = -d->r_ff; dx <= d->r_ff; dx++)
+        for (int dy = -d->r_ff; dy <= d->r_ff; dy++) {
+          const int tx = cx + dx, ty = cy + dy;
+          if (tx >= 0 && tx < wp && ty >= 0 && ty < hp) {
+            const int t = tx + ty * wp;
+            const float w = uniform_real(&o->gen, g->init_min_w, g->init_max_w); /* drawn whether kept or not, :70 */
+            const int keep = l == 0 ? q->act_index[t] != -1 : q->ql[l - 1].ff.off[t + 1] > q->ql[l - 1].ff.off[t];
+            if (keep) { ql->ff.idx[k] = t; ql->ff.w[k] = w; k++; }
+          }
+        }
+    }
+    ql->ff.off[ql->n] = k;
+    wp = d->width; hp = d->height;
+  }
+  q->a_pred = fzeros(q->n_nodes); q->a_derive = fzeros(q->n_nodes); q->a_expl = fzeros(q->n_nodes); q->a_err = fzeros(q->n_nodes);
+  q->a_input = (int*)calloc((size_t)q->n_nodes + 1, sizeof(int));
+  for (int i = 0; i < q->half; i++) { q->a_input[i] = g->q_action_idx[i]; q->a_input[q->half + i] = g->q_anti_idx[i]; }
+  q->prev_value[0] = 0.0f; /* _prevValue is not initialised by the reference (sdr/QPRSDR.h:66); 0 here and in the harness */
 }
 
 void* orc_create(const bidi_config* cfg, const bidi_layer_desc* layers, unsigned seed) {
@@ -280,12 +348,18 @@ void* orc_create(const bidi_config* cfg, const bidi_layer_desc* layers, unsigned
       if (agent) column_create_random(o, &p->col, pi, cfg->init_threshold);
     }
   }
+  if (V == BIDI_QPRSDR) q_create_random(o);
   return o;
 }
 
 void orc_destroy(void* h) {
   oracle* o = (oracle*)h;
   if (!o) return;
+  if (o->cfg.variant == BIDI_QPRSDR) {
+    qnet* q = &o->q;
+    for (int l = 0; l < o->L; l++) { qlayer* ql = &q->ql[l]; free(ql->state); free(ql->err); free(ql->bias_w); free(ql->bias_tr); free_conns(&ql->ff); }
+    free(q->qc_w); free(q->qc_tr); free(q->a_pred); free(q->a_derive); free(q->a_expl); free(q->a_err); free(q->a_input); free(q->act_index);
+  }
   for (int l = 0; l <= o->L; l++) {
     if (l < o->L) {
       coder* c = &o->cod[l];
@@ -580,10 +654,12 @@ static void draw_noise(const oracle* o, mt19937* g, float* u, float* v) {
     }
   }
 }
+static void q_draw_noise(const oracle* o, mt19937* g, float* u, float* v);
 int orc_peek_noise(void* h, float* u, float* v) {
   oracle* o = (oracle*)h;
-  if (o->cfg.variant != BIDI_NEO_AGENT) return -1;
   mt19937 g = o->gen;
+  if (o->cfg.variant == BIDI_QPRSDR) { q_draw_noise(o, &g, u, v); return 0; }
+  if (o->cfg.variant != BIDI_NEO_AGENT) return -1;
   draw_noise(o, &g, u, v);
   return 0;
 }
@@ -782,16 +858,111 @@ static void step_neo(oracle* o, float reward, const float* u, const float* v, in
   }
 }
 
+/* ---- sdr::QPRSDR::simStep after _prsdr.simStep (sdr/QPRSDR.cpp:102-341) */
+static float clamp11(float x) { return smin(1.0f, smax(-1.0f, x)); }
+/* forward pass of the Q network from the given action values (:111-144, :219-253) */
+static void q_forward(oracle* o, const float* actions) {
+  qnet* q = &o->q;
+  for (int l = 0; l < o->L; l++) {
+    qlayer* ql = &q->ql[l];
+    for (int qi = 0; qi < ql->n; qi++) {
+      float sum = 0.0f;
+      for (int k = ql->ff.off[qi]; k < ql->ff.off[qi + 1]; k++)
+        sum += ql->ff.w[k] * (l == 0 ? actions[q->act_index[ql->ff.idx[k]]] : q->ql[l - 1].state[ql->ff.idx[k]]);
+      ql->state[qi] = sigmoidf(sum) * o->pn[l].state[qi];
+      ql->err[qi] = 0.0f;
+    }
+  }
+}
+/* backpropagation of dQ/dstate from the top (:154-190, :268-301); to_actions: also into the action nodes */
+static void q_backward(oracle* o, int to_actions) {
+  qnet* q = &o->q;
+  const int L = o->L;
+  for (int i = 0; i < q->n_top; i++) q->ql[L - 1].err[i] = q->qc_w[i];
+  for (int l = L - 1; l >= 0; l--) {
+    qlayer* ql = &q->ql[l];
+    for (int qi = 0; qi < ql->n; qi++) {
+      ql->err[qi] = ql->err[qi] * ql->state[qi] * (1.0f - ql->state[qi]);
+      if (l > 0) for (int k = ql->ff.off[qi]; k < ql->ff.off[qi + 1]; k++) q->ql[l - 1].err[ql->ff.idx[k]] += ql->err[qi] * ql->ff.w[k];
+      else if (to_actions) for (int k = ql->ff.off[qi]; k < ql->ff.off[qi + 1]; k++) q->a_err[q->act_index[ql->ff.idx[k]]] += ql->err[qi] * ql->ff.w[k];
+    }
+  }
+}
+static int q_num_noise(const oracle* o) { return o->cfg.variant == BIDI_QPRSDR ? o->q.half : 0; }
+/* :202-213: one pertDist object for the whole loop, so its pair cache carries over between actions */
+static void q_draw_noise(const oracle* o, mt19937* g, float* u, float* v) {
+  normal_state ns = { 0, 0.0f };
+  for (int i = 0; i < o->q.half; i++) {
+    u[i] = uniform_real(g, 0.0f, 1.0f);
+    v[i] = u[i] < o->cfg.q_expl_break ? uniform_real(g, 0.0f, 1.0f) : normal_real(g, &ns, 0.0f, o->cfg.q_expl_stddev);
+  }
+}
+static void step_q(oracle* o, float reward, const float* u, const float* v, int learn) {
+  const bidi_config* g = &o->cfg;
+  qnet* q = &o->q;
+  const int L = o->L, half = q->half;
+  for (int i = 0; i < q->n_nodes; i++) q->a_pred[i] = q->a_derive[i] = clamp11(o->pn[L].state[q->a_input[i]]); /* :106-107 */
+  for (int iter = 0; iter < g->q_derive_iterations; iter++) { /* :110-200 */
+    q_forward(o, q->a_derive);
+    for (int i = 0; i < q->n_nodes; i++) q->a_err[i] = 0.0f;
+    q_backward(o, 1);
+    for (int i = 0; i < half; i++) q->a_derive[i] = clamp11(q->a_derive[i] + (q->a_err[i] > 0.0f ? 1.0f : -1.0f) * g->q_derive_alpha);
+    for (int i = 0; i < half; i++) q->a_derive[half + i] = 1.0f - q->a_derive[i];
+  }
+  for (int i = 0; i < half; i++) q->a_expl[i] = u[i] < g->q_expl_break ? v[i] : clamp11(q->a_derive[i] + v[i]); /* :205-213 */
+  for (int i = 0; i < half; i++) q->a_expl[half + i] = 1.0f - q->a_expl[i];
+  q_forward(o, q->a_expl);
+  float qv = 0.0f;
+  for (int i = 0; i < q->n_top; i++) qv += q->qc_w[i] * q->ql[L - 1].state[i];
+  const float td = reward + g->q_gamma * qv - q->prev_value[0];
+  const float q_alpha_td = g->q_alpha * td, action_alpha_td = g->q_action_alpha * td;
+  q->prev_value[0] = qv;
+  if (learn) { /* :266-331 */
+    q_backward(o, 0);
+    for (int l = 0; l < L; l++) {
+      qlayer* ql = &q->ql[l];
+      for (int qi = 0; qi < ql->n; qi++) {
+        ql->bias_w[qi] += action_alpha_td * ql->bias_tr[qi];
+        ql->bias_tr[qi] = g->q_gamma_lambda * ql->bias_tr[qi] + ql->err[qi];
+        for (int k = ql->ff.off[qi]; k < ql->ff.off[qi + 1]; k++) {
+          ql->ff.w[k] += action_alpha_td * ql->ff.tr[k];
+          const float src = l == 0 ? q->a_expl[q->act_index[ql->ff.idx[k]]] : q->ql[l - 1].state[ql->ff.idx[k]];
+          ql->ff.tr[k] = g->q_gamma_lambda * ql->ff.tr[k] + ql->err[qi] * src;
+        }
+      }
+    }
+  }
+  for (int i = 0; i < q->n_top; i++) { /* :334-340, also when not learning */
+    q->qc_w[i] += q_alpha_td * q->qc_tr[i];
+    q->qc_tr[i] = g->q_gamma_lambda * q->qc_tr[i] + q->ql[L - 1].state[i];
+  }
+}
+
+int orc_num_noise(void* h) {
+  oracle* o = (oracle*)h;
+  return o->cfg.variant == BIDI_QPRSDR ? q_num_noise(o) : orc_num_columns(h) * 3;
+}
+
 void orc_step_noise(void* h, float reward, const float* u, const float* v, int learn) {
   oracle* o = (oracle*)h;
   switch (o->cfg.variant) {
     case BIDI_KWINNERS: step_kwinners(o, learn); break;
     case BIDI_ITERATIVE: step_iterative(o, learn); break;
+    case BIDI_QPRSDR: step_iterative(o, learn); step_q(o, reward, u, v, learn); break;
     default: step_neo(o, reward, u, v, learn); break;
   }
 }
 void orc_step(void* h, float reward, int learn) {
   oracle* o = (oracle*)h;
+  if (o->cfg.variant == BIDI_QPRSDR) {
+    float* u = fzeros((size_t)o->q.half);
+    float* v = fzeros((size_t)o->q.half);
+    step_iterative(o, learn);  /* the hierarchy draws nothing (sdr/IRSDR.cpp:126 never samples) */
+    q_draw_noise(o, &o->gen, u, v);
+    step_q(o, reward, u, v, learn);
+    free(u); free(v);
+    return;
+  }
   if (o->cfg.variant == BIDI_NEO_AGENT) {
     size_t n = (size_t)orc_num_columns(h) * 3;
     float* u = fzeros(n);
@@ -843,6 +1014,31 @@ static float* find_array(oracle* o, int which, int layer, long long* len) {
     case BIDI_P_BASELINE: if (layer == L) return NULL; *len = p->n; return p->baseline;
     case BIDI_FB_W: *len = p->fb.off[p->n]; return p->fb.w;
     case BIDI_PRED_W: if (layer == L) return NULL; *len = p->pred.off[p->n]; return p->pred.w;
+  }
+  if (V == BIDI_QPRSDR) {
+    qnet* q = &o->q;
+    if (layer < L) {
+      qlayer* ql = &q->ql[layer];
+      switch (which) {
+        case BIDI_Q_STATE: *len = ql->n; return ql->state;
+        case BIDI_Q_ERROR: *len = ql->n; return ql->err;
+        case BIDI_Q_BIAS_W: *len = ql->n; return ql->bias_w;
+        case BIDI_Q_BIAS_TRACE: *len = ql->n; return ql->bias_tr;
+        case BIDI_Q_FF_W: *len = ql->ff.off[ql->n]; return ql->ff.w;
+        case BIDI_Q_FF_TRACE: *len = ql->ff.off[ql->n]; return ql->ff.tr;
+      }
+    }
+    if (layer == 0)
+      switch (which) {
+        case BIDI_QCONN_W: *len = q->n_top; return q->qc_w;
+        case BIDI_QCONN_TRACE: *len = q->n_top; return q->qc_tr;
+        case BIDI_ACT_PREDICTED: *len = q->n_nodes; return q->a_pred;
+        case BIDI_ACT_DERIVE: *len = q->n_nodes; return q->a_derive;
+        case BIDI_ACT_EXPL: *len = q->n_nodes; return q->a_expl;
+        case BIDI_ACT_ERROR: *len = q->n_nodes; return q->a_err;
+        case BIDI_Q_PREV_VALUE: *len = 1; return q->prev_value;
+      }
+    return NULL;
   }
   if (V != BIDI_NEO_AGENT) return NULL;
   columns* c = &p->col;
@@ -898,6 +1094,7 @@ int orc_conn_counts(void* h, int which, int layer, int* counts) {
     else if (which == BIDI_PRED_W) c = &o->pn[layer].pred;
   }
   if (which == BIDI_FB_W && (layer < L || o->cfg.variant != BIDI_KWINNERS)) c = &o->pn[layer].fb;
+  if (which == BIDI_Q_FF_W && o->cfg.variant == BIDI_QPRSDR && layer < L) c = &o->q.ql[layer].ff;
   if (c) { for (int i = 0; i < c->n_units; i++) counts[i] = c->off[i + 1] - c->off[i]; return 0; }
   if (which == BIDI_COL_INPUT && o->cfg.variant == BIDI_NEO_AGENT) {
     const columns* q = &o->pn[layer].col;

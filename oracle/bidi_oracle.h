@@ -21,6 +21,8 @@ void orc_set_inputs(void* h, const float* in, int n);
 float orc_get_prediction(void* h, int i);
 void orc_get_predictions(void* h, float* out, int n);
 int orc_num_columns(void* h);
+/* floats per step in each of u, v: 3 per column (neo::Agent), one per action (sdr::QPRSDR) */
+int orc_num_noise(void* h);
 /* exploration draws of the NEXT step: u,v [n_columns][3], column visit order */
 int orc_peek_noise(void* h, float* u, float* v);
 /* simStep drawing the exploration noise from the oracle's own mt19937 */

@@ -46,6 +46,7 @@ def _bind(lib, p):
         "set_inputs": (None, [C.c_void_p, _FP, C.c_int]),
         "get_predictions": (None, [C.c_void_p, _FP, C.c_int]),
         "num_columns": (C.c_int, [C.c_void_p]),
+        "num_noise": (C.c_int, [C.c_void_p]),
         "peek_noise": (C.c_int, [C.c_void_p, _FP, _FP]),
         "step": (None, [C.c_void_p, C.c_float, C.c_int]),
         "run": (None, [C.c_void_p, _FP, C.c_int, C.c_int, _FP, C.c_int, C.c_int]),
@@ -149,8 +150,12 @@ class _Hierarchy:
     def num_columns(self):
         return int(self._f("num_columns")(self.h))
 
+    def num_noise(self):
+        """floats per step in each of the exploration-noise arrays (neo::Agent columns, sdr::QPRSDR actions)"""
+        return int(self._f("num_noise")(self.h))
+
     def peek_noise(self):
-        n = self.num_columns() * 3
+        n = self.num_noise()
         u = np.zeros(n, dtype=np.float32)
         v = np.zeros(n, dtype=np.float32)
         if n:

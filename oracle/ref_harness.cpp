@@ -22,6 +22,7 @@
 #define private public
 #include <sdr/PredictiveRSDR.h>
 #include <sdr/IPredictiveRSDR.h>
+#include <sdr/QPRSDR.h>
 #include <neo/PredictiveHierarchy.h>
 #include <neo/Agent.h>
 #undef private
@@ -38,7 +39,15 @@ struct Ref {
   sdr::IPredictiveRSDR it;
   neo::PredictiveHierarchy nh;
   neo::Agent ag;
+  sdr::QPRSDR qp;
 };
+// sdr::QPRSDR::simStep prints q on every step (sdr/QPRSDR.cpp:259); keep the harness quiet
+struct QuietCout {
+  std::streambuf* old;
+  QuietCout() : old(std::cout.rdbuf(nullptr)) {}
+  ~QuietCout() { std::cout.rdbuf(old); }
+};
+sdr::IPredictiveRSDR& hierarchy_of(Ref& r) { return r.cfg.variant == BIDI_QPRSDR ? r.qp._prsdr : r.it; }
 
 template <class D> void fill_common(D& d, const bidi_layer_desc& s) {
   d._width = s.width; d._height = s.height;
@@ -136,9 +145,38 @@ template <class F> bool visit(Ref& r, int which, int layer, F&& f) {
       if (which == BIDI_PRED_W) return visit_pred_w(ly._predictionNodes, f);
       return visit_pnodes(ly._predictionNodes, which, f);
     }
+    case BIDI_QPRSDR:
+      if (which >= BIDI_Q_STATE) {
+        sdr::QPRSDR& q = r.qp;
+        if (layer < L) {
+          auto& nodes = q._qFunctionLayers[layer]._qFunctionNodes;
+          switch (which) {
+            case BIDI_Q_STATE: for (auto& n : nodes) f(n._state); return true;
+            case BIDI_Q_ERROR: for (auto& n : nodes) f(n._error); return true;
+            case BIDI_Q_BIAS_W: for (auto& n : nodes) f(n._bias._weight); return true;
+            case BIDI_Q_BIAS_TRACE: for (auto& n : nodes) f(n._bias._trace); return true;
+            case BIDI_Q_FF_W: for (auto& n : nodes) for (auto& c : n._feedForwardConnections) f(c._weight); return true;
+            case BIDI_Q_FF_TRACE: for (auto& n : nodes) for (auto& c : n._feedForwardConnections) f(c._trace); return true;
+          }
+        }
+        if (layer != 0) return false;
+        switch (which) {
+          case BIDI_QCONN_W: for (auto& c : q._qConnections) f(c._weight); return true;
+          case BIDI_QCONN_TRACE: for (auto& c : q._qConnections) f(c._trace); return true;
+          case BIDI_ACT_PREDICTED: for (auto& a : q._actionNodes) f(a._predictedAction); return true;
+          case BIDI_ACT_DERIVE: for (auto& a : q._actionNodes) f(a._deriveAction); return true;
+          case BIDI_ACT_EXPL: for (auto& a : q._actionNodes) f(a._exploratoryAction); return true;
+          case BIDI_ACT_ERROR: for (auto& a : q._actionNodes) f(a._error); return true;
+          case BIDI_Q_PREV_VALUE: f(q._prevValue); return true;
+        }
+        return false;
+      }
+      /* fall through: the hierarchy the QPRSDR owns */
     case BIDI_ITERATIVE: {
-      if (layer == L) return visit_pnodes(r.it._inputPredictionNodes, which, f);
-      auto& ly = const_cast<sdr::IPredictiveRSDR::Layer&>(r.it.getLayers()[layer]);
+      sdr::IPredictiveRSDR& it = hierarchy_of(r);
+      if (which >= BIDI_Q_STATE) return false;
+      if (layer == L) return visit_pnodes(it._inputPredictionNodes, which, f);
+      auto& ly = const_cast<sdr::IPredictiveRSDR::Layer&>(it.getLayers()[layer]);
       if (visit_icoder(ly._sdr, which, false, f)) return true;
       if (which == BIDI_P_BASELINE) { for (auto& p : ly._predictionNodes) f(p._baseline); return true; }
       if (which == BIDI_PRED_W) return visit_pred_w(ly._predictionNodes, f);
@@ -202,6 +240,7 @@ void* ref_create(const bidi_config* cfg, const bidi_layer_desc* layers, unsigned
                          cfg->init_threshold, r->gen);
       break;
     }
+    case BIDI_QPRSDR:
     case BIDI_ITERATIVE: {
       std::vector<sdr::IPredictiveRSDR::LayerDesc> d(L);
       for (int l = 0; l < L; l++) {
@@ -211,6 +250,18 @@ void* ref_create(const bidi_config* cfg, const bidi_layer_desc* layers, unsigned
         d[l]._sdrWeightDecay = layers[l].weight_decay; d[l]._sdrMaxWeightDelta = layers[l].max_weight_delta;
         d[l]._sdrSparsity = layers[l].sparsity; d[l]._sdrLearnThreshold = layers[l].learn_threshold;
         d[l]._sdrBaselineDecay = layers[l].baseline_decay; d[l]._sdrSensitivity = layers[l].sensitivity;
+      }
+      if (cfg->variant == BIDI_QPRSDR) {
+        sdr::QPRSDR& q = r->qp;
+        q._prsdr._learnInputFeedBack = cfg->learn_infb;
+        q._qAlpha = cfg->q_alpha; q._actionAlpha = cfg->q_action_alpha; q._actionDeriveIterations = cfg->q_derive_iterations;
+        q._actionDeriveAlpha = cfg->q_derive_alpha; q._explorationBreak = cfg->q_expl_break; q._explorationStdDev = cfg->q_expl_stddev;
+        q._gamma = cfg->q_gamma; q._gammaLambda = cfg->q_gamma_lambda;
+        q._prevValue = 0.0f;  // not initialised by the reference (sdr/QPRSDR.h:66)
+        std::vector<int> act(cfg->q_action_idx, cfg->q_action_idx + cfg->q_n_actions), anti(cfg->q_anti_idx, cfg->q_anti_idx + cfg->q_n_actions);
+        q.createRandom(cfg->in_width, cfg->in_height, cfg->r_infb, act, anti, d, cfg->init_min_w, cfg->init_max_w,
+                       cfg->init_min_inh, cfg->init_max_inh, cfg->init_threshold, r->gen);
+        break;
       }
       r->it._learnInputFeedBack = cfg->learn_infb;
       r->it.createRandom(cfg->in_width, cfg->in_height, cfg->r_infb, d, cfg->init_min_w, cfg->init_max_w,
@@ -275,6 +326,7 @@ void ref_set_input(void* h, int i, float v) {
   switch (r.cfg.variant) {
     case BIDI_KWINNERS: r.kw.setInput(i, v); break;
     case BIDI_ITERATIVE: r.it.setInput(i, v); break;
+    case BIDI_QPRSDR: r.qp.setState(i, v); break;
     case BIDI_NEO_HIERARCHY: r.nh.setInput(i, v); break;
     case BIDI_NEO_AGENT: r.ag.setInput(i, v); break;
   }
@@ -287,6 +339,7 @@ float ref_get_prediction(void* h, int i) {
   switch (r.cfg.variant) {
     case BIDI_KWINNERS: return r.kw.getPrediction(i);
     case BIDI_ITERATIVE: return r.it.getPrediction(i);
+    case BIDI_QPRSDR: return r.qp._prsdr.getPrediction(i);
     case BIDI_NEO_HIERARCHY: return r.nh.getPrediction(i);
     case BIDI_NEO_AGENT: return r.ag.getPrediction(i);
   }
@@ -301,6 +354,7 @@ void ref_step(void* h, float reward, int learn) {
   switch (r.cfg.variant) {
     case BIDI_KWINNERS: r.kw.simStep(learn != 0); break;
     case BIDI_ITERATIVE: r.it.simStep(r.gen, learn != 0); break;
+    case BIDI_QPRSDR: { QuietCout quiet; r.qp.simStep(reward, r.gen, learn != 0); break; }
     case BIDI_NEO_HIERARCHY: r.nh.simStep(r.gen, learn != 0); break;
     case BIDI_NEO_AGENT: r.ag.simStep(reward, r.gen, learn != 0); break;
   }
@@ -337,6 +391,7 @@ void ref_run_runner(void* h, const float* frames, int n_frames, int n_in, int st
   }
 }
 
+int ref_num_noise(void* h);
 int ref_num_columns(void* h) {
   Ref& r = *static_cast<Ref*>(h);
   if (r.cfg.variant != BIDI_NEO_AGENT) return 0;
@@ -351,6 +406,16 @@ int ref_num_columns(void* h) {
 // yields exactly what Column::simStep will see.  u,v: [n_columns][3].
 int ref_peek_noise(void* h, float* u, float* v) {
   Ref& r = *static_cast<Ref*>(h);
+  if (r.cfg.variant == BIDI_QPRSDR) {  // sdr/QPRSDR.cpp:202-213; the hierarchy's simStep draws nothing
+    std::mt19937 g = r.gen;
+    std::uniform_real_distribution<float> dist01(0.0f, 1.0f);
+    std::normal_distribution<float> pertDist(0.0f, r.cfg.q_expl_stddev);
+    for (int i = 0; i < r.cfg.q_n_actions; i++) {
+      u[i] = dist01(g);
+      v[i] = (u[i] < r.cfg.q_expl_break) ? dist01(g) : pertDist(g);
+    }
+    return 0;
+  }
   if (r.cfg.variant != BIDI_NEO_AGENT) return -1;
   std::mt19937 g = r.gen;
   const int L = r.cfg.n_layers;
@@ -369,6 +434,11 @@ int ref_peek_noise(void* h, float* u, float* v) {
   for (size_t pi = 0; pi < r.ag._inputPredictionNodes.size(); pi++)
     visit_col(r.cfg.col_expl_stddev, r.cfg.col_expl_break);
   return 0;
+}
+
+int ref_num_noise(void* h) {
+  Ref& r = *static_cast<Ref*>(h);
+  return r.cfg.variant == BIDI_QPRSDR ? r.cfg.q_n_actions : ref_num_columns(h) * BIDI_COLUMN_ACTIONS;
 }
 
 // Per-unit list lengths, as bidi_conn_counts.
@@ -390,11 +460,20 @@ int ref_conn_counts(void* h, int which, int layer, int* counts) {
       COUNT_CODER(const_cast<sdr::RSDR&>(r.kw._layers[layer]._sdr))
       COUNT_NODES(r.kw._layers[layer]._predictionNodes) COUNT_PRED(r.kw._layers[layer]._predictionNodes)
       break;
-    case BIDI_ITERATIVE:
-      if (layer == L) { COUNT_NODES(r.it._inputPredictionNodes) break; }
-      COUNT_CODER(r.it._layers[layer]._sdr)
-      COUNT_NODES(r.it._layers[layer]._predictionNodes) COUNT_PRED(r.it._layers[layer]._predictionNodes)
+    case BIDI_QPRSDR:
+      if (which == BIDI_Q_FF_W) {
+        if (layer >= L) return -1;
+        for (auto& n : r.qp._qFunctionLayers[layer]._qFunctionNodes) counts[k++] = (int)n._feedForwardConnections.size();
+        return 0;
+      }
+      /* fall through */
+    case BIDI_ITERATIVE: {
+      sdr::IPredictiveRSDR& it = hierarchy_of(r);
+      if (layer == L) { COUNT_NODES(it._inputPredictionNodes) break; }
+      COUNT_CODER(it._layers[layer]._sdr)
+      COUNT_NODES(it._layers[layer]._predictionNodes) COUNT_PRED(it._layers[layer]._predictionNodes)
       break;
+    }
     case BIDI_NEO_HIERARCHY:
       if (layer == L) { COUNT_NODES(r.nh._inputPredictionNodes) break; }
       COUNT_CODER(r.nh._layers[layer]._sdr)

@@ -1,6 +1,6 @@
 """The C restatement (oracle/bidi_oracle.c) against the UNMODIFIED reference compiled
 from /root/reference (oracle/_ref/libbidiref.so): every state array bit-identical
-after creation and after every step, for all four hierarchies.  CPU only."""
+after creation and after every step, for all four hierarchies and sdr::QPRSDR.  CPU only."""
 import numpy as np
 import pytest
 
@@ -20,7 +20,7 @@ def test_oracle_matches_reference(case):
         x = frame(t)
         ref.set_inputs(x)
         orc.set_inputs(x)
-        if ref.num_columns():
+        if ref.num_noise():
             ur, vr = ref.peek_noise()
             uo, vo = orc.peek_noise()
             assert np.array_equal(ur, uo) and np.array_equal(vr, vo)
@@ -35,7 +35,7 @@ def test_conn_counts_match_reference():
     for name, cfg, ld, _, _ in small_cases():
         ref, orc = RefHierarchy(cfg, ld, 7), OracleHierarchy(cfg, ld, 7)
         for layer in range(cfg.n_layers + 1):
-            for which in ("FF_W", "REC_W", "LAT_W", "FB_W", "PRED_W", "COL_INPUT"):
+            for which in ("FF_W", "REC_W", "LAT_W", "FB_W", "PRED_W", "COL_INPUT", "Q_FF_W"):
                 n = 4096
                 a, b = ref.conn_counts(which, layer, n), orc.conn_counts(which, layer, n)
                 assert (a is None) == (b is None), (name, which, layer)

@@ -77,7 +77,7 @@ def test_free_running_parity(case, path):
         x = frame(t)
         orc.set_inputs(x)
         eng.set_inputs(x)
-        noise = orc.peek_noise() if orc.num_columns() else None
+        noise = orc.peek_noise() if orc.num_noise() else None
         learn = t != 9
         orc.step(reward(t), learn)
         eng.step(rewards=[reward(t)], noise=noise, learn=learn)

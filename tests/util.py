@@ -39,6 +39,8 @@ def small_cases():
     cases.append(("experiment_prediction", cfg, ld, lambda t: EXPERIMENT_SEQ[t % 10], lambda t: 0.0))
     cfg, ld = cf.config_c2()
     cases.append(("c2_neo_agent", cfg, ld, lambda t: frames64[t % 64], lambda t: float(np.sin(0.3 * t))))
+    cfg, ld = cf.config_q_small()   # sdr::QPRSDR: hierarchy + Q network + action derivation
+    cases.append(("q_small_qprsdr", cfg, ld, lambda t: frames64[t % 64], lambda t: float(np.sin(0.3 * t))))
     # ragged: non-square grids, non-integer ratios, radius -1 recurrent, windows wider than the grid
     for v in (cf.KWINNERS, cf.ITERATIVE, cf.NEO_HIERARCHY, cf.NEO_AGENT):
         layers = [dict(width=6, height=4, r_ff=2, r_rec=1, r_lat=2, r_pred=1, r_fb=1),
@@ -53,4 +55,11 @@ def small_cases():
         cfg, ld = cf.make_config(v, 7, 5, layers, r_infb=0 if v == cf.KWINNERS else 2)
         cases.append(("ragged_" + cf.VARIANT_NAMES[v], cfg, ld, lambda t: frames35[t % 64],
                       lambda t: float(np.cos(0.7 * t))))
+    # sdr::QPRSDR on ragged grids: three Q layers, actions scattered over the input, a window wider than the grid
+    layers = [dict(width=6, height=4, r_ff=2, r_rec=1, r_lat=2, r_pred=1, r_fb=1),
+              dict(width=3, height=5, r_ff=1, r_rec=2, r_lat=1, r_pred=3, r_fb=2),
+              dict(width=2, height=2, r_ff=4, r_rec=1, r_lat=1, r_pred=1, r_fb=1)]
+    cfg, ld = cf.make_config(cf.QPRSDR, 7, 5, layers, r_infb=2, actions=[3, 10, 17, 30], anti_actions=[4, 11, 18, 31],
+                             init=(-0.3, 0.3, 0.01, 0.05, 0.0), q_derive_iterations=9)
+    cases.append(("ragged_qprsdr", cfg, ld, lambda t: frames35[t % 64], lambda t: float(np.cos(0.7 * t))))
     return cases
