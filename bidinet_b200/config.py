@@ -179,6 +179,13 @@ def config_q_small():
                        init=(-0.3, 0.3, 0.01, 0.05, 0.0))  # lively from the first steps: non-zero Q values, errors and traces
 
 
+def config_q_c1():
+    """sdr::QPRSDR over the C1 hierarchy (input 16x16, 16^2 -> 8^2 -> 4^2): 16 action cells + their complements."""
+    layers = [dict(width=16, height=16), dict(width=8, height=8), dict(width=4, height=4)]
+    return make_config(QPRSDR, 16, 16, layers, r_infb=16, actions=list(range(192, 208)), anti_actions=list(range(208, 224)),
+                       init=(-0.3, 0.3, 0.01, 0.05, 0.0))
+
+
 def config_c2():
     """C2/C3: neo::Agent of RunnerMain.cpp:141-154: input 8x8, layers 8^2 -> 4^2, inFB 8."""
     layers = [dict(width=8, height=8), dict(width=4, height=4)]

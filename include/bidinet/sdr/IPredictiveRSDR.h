@@ -34,6 +34,18 @@ public:
           _sdrBaselineDecay(0.01f), _sdrSensitivity(8.0f) {}
   };
 
+  // LayerDesc -> the C ABI's layer descriptor
+  static void fill(bidi_layer_desc& d, const LayerDesc& s) {
+    d.width = s._width; d.height = s._height;
+    d.r_ff = s._receptiveRadius; d.r_rec = s._recurrentRadius; d.r_lat = s._lateralRadius;
+    d.r_pred = s._predictiveRadius; d.r_fb = s._feedBackRadius;
+    d.learn_ff = s._learnFeedForward; d.learn_rec = s._learnRecurrent; d.learn_lat = s._learnLateral;
+    d.learn_fb = s._learnFeedBack; d.learn_pred = s._learnPrediction;
+    d.iter_settle = s._sdrIterSettle; d.iter_measure = s._sdrIterMeasure; d.leak = s._sdrLeak; d.lambda = s._sdrLambda;
+    d.weight_decay = s._sdrWeightDecay; d.max_weight_delta = s._sdrMaxWeightDelta; d.sparsity = s._sdrSparsity;
+    d.learn_threshold = s._sdrLearnThreshold; d.baseline_decay = s._sdrBaselineDecay; d.sensitivity = s._sdrSensitivity;
+  }
+
   float _learnInputFeedBack;
   IPredictiveRSDR() : _learnInputFeedBack(0.05f) {}
 
@@ -48,18 +60,7 @@ public:
     _cfg.init_min_w = initMinWeight; _cfg.init_max_w = initMaxWeight;
     _cfg.init_min_inh = initMinInhibition; _cfg.init_max_inh = initMaxInhibition; _cfg.init_threshold = initThreshold;
     _descs.assign(layerDescs.size(), bidi_layer_desc{});
-    for (size_t l = 0; l < layerDescs.size(); l++) {
-      const LayerDesc& s = layerDescs[l];
-      bidi_layer_desc& d = _descs[l];
-      d.width = s._width; d.height = s._height;
-      d.r_ff = s._receptiveRadius; d.r_rec = s._recurrentRadius; d.r_lat = s._lateralRadius;
-      d.r_pred = s._predictiveRadius; d.r_fb = s._feedBackRadius;
-      d.learn_ff = s._learnFeedForward; d.learn_rec = s._learnRecurrent; d.learn_lat = s._learnLateral;
-      d.learn_fb = s._learnFeedBack; d.learn_pred = s._learnPrediction;
-      d.iter_settle = s._sdrIterSettle; d.iter_measure = s._sdrIterMeasure; d.leak = s._sdrLeak; d.lambda = s._sdrLambda;
-      d.weight_decay = s._sdrWeightDecay; d.max_weight_delta = s._sdrMaxWeightDelta; d.sparsity = s._sdrSparsity;
-      d.learn_threshold = s._sdrLearnThreshold; d.baseline_decay = s._sdrBaselineDecay; d.sensitivity = s._sdrSensitivity;
-    }
+    for (size_t l = 0; l < layerDescs.size(); l++) fill(_descs[l], layerDescs[l]);
     create();
     drawWeights(generator);
   }

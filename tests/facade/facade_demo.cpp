@@ -1,13 +1,14 @@
 // tests/facade/facade_demo.cpp -- one source, two builds:
 //   reference build : -I/root/reference/BIDInet/source + the reference's own .cpp files
 //   facade build    : -Iinclude/bidinet + libbidinet_b200.so (the CUDA engine)
-// It drives the four hierarchy classes exactly the way the reference's experiment mains
+// It drives the four hierarchy classes and sdr::QPRSDR exactly the way the reference's experiment mains
 // do (Experiment_Prediction.cpp:113-153, RunnerMain.cpp:139-154,235-251) with fixed
 // seeds and prints a hash of every prediction vector; the two builds must print the
 // same text.  (The reference leaves _columnGamma/_columnGammaLambda uninitialised, so
 // the demo sets them explicitly in both builds.)
 #include <sdr/PredictiveRSDR.h>
 #include <sdr/IPredictiveRSDR.h>
+#include <sdr/QPRSDR.h>
 #include <neo/PredictiveHierarchy.h>
 #include <neo/Agent.h>
 
@@ -15,6 +16,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <new>
 #include <random>
 #include <vector>
 
@@ -112,6 +115,33 @@ int main() {
       report("agent", steps, agent, 64);
     }
     std::printf("agent generator %u\n", (unsigned)generator());
+  }
+  {  // sdr::QPRSDR: states in, actions fed back as inputs, reward, the way its createRandom/simStep/getAction are meant
+     // to be driven (sdr/QPRSDR.h:109-126).  The reference never initialises _prevValue (sdr/QPRSDR.h:66): the
+     // object is built in zeroed storage so that both builds start from 0.
+    std::mt19937 generator(4321);
+    std::vector<sdr::IPredictiveRSDR::LayerDesc> layerDescs(2);
+    layerDescs[0]._width = 8; layerDescs[0]._height = 8;
+    layerDescs[1]._width = 4; layerDescs[1]._height = 4;
+    std::vector<int> actionIndices, antiActionIndices;
+    for (int i = 0; i < 6; i++) { actionIndices.push_back(40 + i); antiActionIndices.push_back(48 + i); }
+    void* storage = std::calloc(1, sizeof(sdr::QPRSDR));
+    sdr::QPRSDR* agent = new (storage) sdr::QPRSDR();
+    agent->createRandom(8, 8, 4, actionIndices, antiActionIndices, layerDescs, -0.3f, 0.3f, 0.01f, 0.05f, 0.0f, generator);
+    for (int t = 0; t < 25; t++) {
+      for (int i = 0; i < 40; i++) agent->setState(i, 0.5f + 0.5f * std::sin(0.1f * t * (1 + i)));
+      for (int i = 0; i < 6; i++) {
+        agent->setState(40 + i, agent->getAction(40 + i));
+        agent->setState(48 + i, 1.0f - agent->getAction(40 + i));
+      }
+      const float reward = agent->getActionRel(0) - 0.5f;
+      agent->simStep(reward, generator, t % 7 != 6);
+      for (int i = 0; i < 12; i++) hashFloat(agent->getActionRel(i));
+      std::printf("qprsdr %d %016llx\n", t, g_hash);
+    }
+    std::printf("qprsdr generator %u\n", (unsigned)generator());
+    agent->~QPRSDR();
+    std::free(storage);
   }
   return 0;
 }

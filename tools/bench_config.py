@@ -40,10 +40,14 @@ def run(name, cfg, ld, frame, gpu_steps, cpu_steps, parity_steps):
     for t in range(parity_steps):
         x = frame(t)
         ref.set_inputs(x); eng.set_inputs(x)
-        ref.step(); eng.step()
+        noise = ref.peek_noise() if ref.num_noise() else None  # the exploration draws the reference is about to make
+        ref.step(); eng.step(rewards=[0.0], noise=noise)
         ok = ok and np.array_equal(ref.get_predictions(), eng.get_predictions()[0])
     if parity_steps:
-        for key in (("HID_STATE", 0), ("FF_W", 0), ("P_STATE", cfg.n_layers - 1)):
+        keys = [("HID_STATE", 0), ("FF_W", 0), ("P_STATE", cfg.n_layers - 1)]
+        if cfg.variant == cf.QPRSDR:
+            keys += [("Q_FF_W", 0), ("ACT_EXPL", 0), ("QCONN_TRACE", 0)]
+        for key in keys:
             ok = ok and np.array_equal(ref.get_array(*key), eng.get_array(*key))
     # CPU: one core
     frames = np.stack([frame(t) for t in range(16)])
@@ -82,6 +86,9 @@ def main(which):
             run("C1", cfg, ld, c1_frame, 200, 100, 20)
         cfg, ld = cf.config_c2()
         run("C2", cfg, ld, lambda t: np.random.RandomState(t).rand(64).astype(np.float32), 200, 100, 0)
+    if "q" in which:  # sdr::QPRSDR over the C1 hierarchy; the reward follows the frame index
+        cfg, ld = cf.config_q_c1()
+        run("C1+Q", cfg, ld, c1_frame, 200, 100, 20)
     if "c4" in which:
         cfg, ld = cf.config_c4(cf.KWINNERS)
         run("C4", cfg, ld, bars, 100, 20, 5)
