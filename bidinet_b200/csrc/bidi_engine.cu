@@ -1559,6 +1559,87 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   return BIDI_OK;
 }
 
+// ---- checkpoint / resume.  The reference has none for its hierarchies (only deep::FERL's text
+// dump, deep/FERL.cpp:330-407).  File = header + configuration + the device arrays verbatim (the
+// engine's own HBM layout), so saving and loading are plain copies.
+namespace {
+struct SnapHeader { char magic[8]; int version, config_bytes, desc_bytes, n_layers, n_agents, n_in; long long stride; unsigned long long step_index; };
+const char kSnapMagic[8] = {'B', 'I', 'D', 'I', 'S', 'N', 'A', 'P'};
+}
+
+int bidi_save_snapshot(bidi_engine* h, const char* path) {
+  if (!h || !path) return fail(h, BIDI_EINVAL, "bidi_save_snapshot: null argument");
+  CU(cudaSetDevice(h->device));
+  int rc = mirror_release(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(h, BIDI_EINVAL, std::string("bidi_save_snapshot: cannot open ") + path);
+  SnapHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  memcpy(hd.magic, kSnapMagic, 8);
+  hd.version = 1; hd.config_bytes = (int)sizeof(bidi_config); hd.desc_bytes = (int)sizeof(bidi_layer_desc);
+  hd.n_layers = h->L; hd.n_agents = h->A; hd.n_in = h->n_in; hd.stride = h->stride; hd.step_index = h->step_index;
+  bidi_config cfg = h->cfg;
+  if (h->qnet) cfg.variant = BIDI_QPRSDR;
+  bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && fwrite(&cfg, sizeof(cfg), 1, f) == 1 &&
+            fwrite(h->ld.data(), sizeof(bidi_layer_desc), (size_t)h->L, f) == (size_t)h->L;
+  std::vector<float> buf;
+  auto dump = [&](const float* dev, size_t n) {
+    const size_t chunk = (size_t)16 << 20;
+    for (size_t o = 0; o < n && ok; o += chunk) {
+      const size_t m = std::min(chunk, n - o);
+      buf.resize(m);
+      if (cudaMemcpy(buf.data(), dev + o, sizeof(float) * m, cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+      ok = fwrite(buf.data(), sizeof(float), m, f) == m;
+    }
+  };
+  dump(h->d_in0, (size_t)h->A * h->n_in);
+  dump(h->d_pred, (size_t)h->A * h->n_in);
+  dump(h->d_blob, (size_t)h->A * (size_t)h->stride);
+  ok = (fclose(f) == 0) && ok;
+  cudaGetLastError();
+  return ok ? BIDI_OK : fail(h, BIDI_EINVAL, std::string("bidi_save_snapshot: write to ") + path + " failed");
+}
+
+int bidi_load_snapshot(bidi_engine* h, const char* path) {
+  if (!h || !path) return fail(h, BIDI_EINVAL, "bidi_load_snapshot: null argument");
+  CU(cudaSetDevice(h->device));
+  int rc = mirror_release(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(h, BIDI_EINVAL, std::string("bidi_load_snapshot: cannot open ") + path);
+  SnapHeader hd;
+  bidi_config cfg;
+  std::vector<bidi_layer_desc> ld((size_t)h->L);
+  bidi_config mine = h->cfg;
+  if (h->qnet) mine.variant = BIDI_QPRSDR;
+  bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kSnapMagic, 8) == 0 && hd.version == 1 &&
+            hd.config_bytes == (int)sizeof(bidi_config) && hd.desc_bytes == (int)sizeof(bidi_layer_desc) && hd.n_layers == h->L &&
+            hd.n_agents == h->A && hd.n_in == h->n_in && hd.stride == h->stride && fread(&cfg, sizeof(cfg), 1, f) == 1 &&
+            fread(ld.data(), sizeof(bidi_layer_desc), (size_t)h->L, f) == (size_t)h->L && memcmp(&cfg, &mine, sizeof(cfg)) == 0 &&
+            memcmp(ld.data(), h->ld.data(), sizeof(bidi_layer_desc) * (size_t)h->L) == 0;
+  if (!ok) { fclose(f); return fail(h, BIDI_EINVAL, std::string("bidi_load_snapshot: ") + path + " is not a snapshot of an engine with this configuration"); }
+  std::vector<float> buf;
+  auto fill = [&](float* dev, size_t n) {
+    const size_t chunk = (size_t)16 << 20;
+    for (size_t o = 0; o < n && ok; o += chunk) {
+      const size_t m = std::min(chunk, n - o);
+      buf.resize(m);
+      ok = fread(buf.data(), sizeof(float), m, f) == m && cudaMemcpy(dev + o, buf.data(), sizeof(float) * m, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+  };
+  fill(h->d_in0, (size_t)h->A * h->n_in);
+  fill(h->d_pred, (size_t)h->A * h->n_in);
+  fill(h->d_blob, (size_t)h->A * (size_t)h->stride);
+  fclose(f);
+  cudaGetLastError();
+  if (!ok) return fail(h, BIDI_EINVAL, std::string("bidi_load_snapshot: ") + path + " is truncated");
+  h->step_index = hd.step_index;
+  return BIDI_OK;
+}
+
 int bidi_profile_select(bidi_engine* h, const char* kernel_name) {
   if (!h) return fail(h, BIDI_EINVAL, "null engine");
   CU(cudaSetDevice(h->device));

@@ -43,6 +43,8 @@ ABI = {
     "bidi_step_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "bidi_set_feedback": (C.c_int, [C.c_void_p, C.c_int, _IP, _IP, C.c_float, C.c_float, C.c_float, C.c_int]),
     "bidi_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "bidi_save_snapshot": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "bidi_load_snapshot": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bidi_profile_select": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bidi_profile_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "bidi_timer_start": (C.c_int, [C.c_void_p]),
@@ -221,6 +223,12 @@ class Engine:
         assert s.size == d.size
         self._check(self.lib.bidi_set_feedback(self.h, s.size, s.ctypes.data_as(_IP), d.ctypes.data_as(_IP), scale, bias,
                                                noise_std, int(bool(reward_from_actions))), "bidi_set_feedback")
+
+    def save_snapshot(self, path):
+        self._check(self.lib.bidi_save_snapshot(self.h, os.fsencode(path)), "bidi_save_snapshot")
+
+    def load_snapshot(self, path):
+        self._check(self.lib.bidi_load_snapshot(self.h, os.fsencode(path)), "bidi_load_snapshot")
 
     def set_option(self, name, value):
         self._check(self.lib.bidi_set_option(self.h, name.encode(), int(value)), "bidi_set_option")

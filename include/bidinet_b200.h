@@ -256,6 +256,15 @@ int bidi_profile_select(bidi_engine* h, const char* kernel_name);
 int bidi_profile_collect(bidi_engine* h, double* total_ms, long long* launches);
 
 /*
+ * Checkpoint / resume: every agent's complete state (weights, traces, unit state, inputs,
+ * predictions, the step counter of the engine's own exploration generator) to one file and back
+ * into an engine created with the SAME configuration and agent count.  The reference has no such
+ * facility for its hierarchies.  A resumed run continues bit-identically.
+ */
+int bidi_save_snapshot(bidi_engine* h, const char* path);
+int bidi_load_snapshot(bidi_engine* h, const char* path);
+
+/*
  * Engine options.  "force_phase_kernels" = 1: run one kernel per phase even where
  * the fused per-agent coder kernel applies (both paths give identical results; the
  * tests compare them).

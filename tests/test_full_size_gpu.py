@@ -1,0 +1,112 @@
+"""Parity at BASELINE.json's FULL sizes (the small-case tests are in test_parity_gpu.py).
+
+  C3  4096 neo::Agent hierarchies in one engine: sampled agents equal their own single-agent
+      oracle runs bit for bit (agents never interact, so the rest of the batch is free to differ)
+  C4  the large six-layer hierarchy (input 128x128, every radius 6): first steps of the k-winners
+      and the iterative variant against the oracle, every state array equal
+  C5  the largest single layer the oracle's reference (16-bit indices) can hold, 256x256: the 2-D
+      grid-tile kernels against the oracle; and a size-independent property at 1024x1024 --
+      splitting the layer into row strips changes nothing
+All comparisons are exact (np.array_equal)."""
+import numpy as np
+import pytest
+
+from bidinet_b200 import Engine, StripGroup
+from bidinet_b200 import config as cf
+from oracle.pyoracle import OracleHierarchy
+
+from util import diff_states
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c3_sampled_agents_of_the_full_batch():
+    cfg, ld = cf.config_c2()
+    A, sample, steps = 4096, (0, 1, 2047, 4095), 3
+    eng = Engine(cfg, ld, n_agents=A, seed=1234)
+    orcs = {a: OracleHierarchy(cfg, ld, 1234 + a) for a in sample}
+    rng = np.random.RandomState(5)
+    n = eng.n_noise
+    for t in range(steps):
+        x = rng.rand(A, 64).astype(np.float32)
+        r = rng.randn(A).astype(np.float32)
+        u, v = rng.rand(A, n).astype(np.float32), (0.05 * rng.randn(A, n)).astype(np.float32)
+        for a, o in orcs.items():
+            u[a], v[a] = o.peek_noise()
+            o.set_inputs(x[a])
+            o.step(float(r[a]))
+        eng.set_inputs(x)
+        eng.step(rewards=r, noise=(u, v))
+    pred = eng.get_predictions()
+    for a, o in orcs.items():
+        assert np.array_equal(o.get_predictions(), pred[a]), a
+        assert diff_states(o.state(), eng.state(agent=a)) == [], a
+
+
+def _bars(t, n=128, period=16):
+    x = np.arange(n)[None, :] + np.zeros((n, 1), dtype=int)
+    return (((x + t) % period) < period // 2).astype(np.float32).ravel()
+
+
+@pytest.mark.parametrize("variant,steps", [(cf.KWINNERS, 4), (cf.ITERATIVE, 2)])
+def test_c4_first_steps(variant, steps):
+    cfg, ld = cf.config_c4(variant)
+    orc = OracleHierarchy(cfg, ld, 1234)
+    eng = Engine(cfg, ld, n_agents=1, seed=1234)   # the engine replays createRandom itself
+    assert diff_states(orc.state(), eng.state()) == []
+    for t in range(steps):
+        x = _bars(t)
+        orc.set_inputs(x)
+        eng.set_inputs(x)
+        orc.step()
+        eng.step()
+        assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0]), t
+    bad = diff_states(orc.state(), eng.state())
+    assert bad == [], bad[:6]
+
+
+def _sparse(t, n, density=0.05, period=8):
+    return (np.random.RandomState(7 + t % period).rand(n * n) < density).astype(np.float32)
+
+
+def test_c5_256_grid_kernels():
+    n = 256
+    cfg, ld = cf.config_c5(n)
+    orc = OracleHierarchy(cfg, ld, 1234)
+    eng = Engine(cfg, ld, n_agents=1, seed=1234)
+    for t in range(3):
+        x = _sparse(t, n)
+        orc.set_inputs(x)
+        eng.set_inputs(x)
+        orc.step()
+        eng.step()
+    assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0])
+    for key in (("HID_STATE", 0), ("HID_ACTIVATION", 0), ("VIS_RECON", 0), ("P_STATE", 0), ("FF_W", 0), ("REC_W", 0), ("PRED_W", 0),
+                ("HID_THRESHOLD", 0)):
+        assert np.array_equal(orc.get_array(*key), eng.get_array(*key)), key
+    assert orc.get_array("HID_STATE", 0).sum() > 100  # winners existed, so the learning rule ran
+
+
+def test_c5_full_size_split_equals_unsplit():
+    """1024x1024, every radius 6: two row strips (same-process transport, one device) against the unsplit
+    engine from the same createRandom stream -- a property that needs no CPU run of a layer this size."""
+    from bidinet_b200 import assemble_rows
+    n = 1024
+    cfg, ld = cf.config_c5(n)
+    whole = Engine(cfg, ld, n_agents=1, seed=1234)
+    parts = StripGroup(cfg, ld, devices=[0, 0], seed=1234)
+    for t in range(3):
+        x = _sparse(t, n)
+        whole.set_inputs(x)
+        parts.set_inputs(x)
+        whole.step()
+        parts.step()
+    assert np.array_equal(whole.get_predictions(), parts.get_predictions())
+    for key, span in ((("HID_STATE", 0), "OWN_HID"), (("HID_ACTIVATION", 0), "OWN_HID"), (("VIS_RECON", 0), "OWN_VIS"),
+                      (("HID_RECON", 0), "OWN_HID"), (("P_STATE", 0), "OWN_HID"), (("P_ACTIVATION", 0), "OWN_HID"),
+                      (("HID_THRESHOLD", 0), "OWN_HID"), (("P_BASELINE", 0), "OWN_HID")):
+        got = assemble_rows([e.get_array(*key) for e in parts.parts], [e.spans[span] for e in parts.parts], n)
+        assert np.array_equal(whole.get_array(*key), got), key
+    assert whole.get_array("HID_STATE", 0).sum() > 1000
+    parts.close()
+    whole.close()

@@ -120,3 +120,31 @@ def test_device_noise_mode_runs_and_explores():
     act = eng.get_column_actions()
     assert np.all(act >= 0) and np.all(act <= 1) and np.isfinite(eng.get_predictions()).all()
     assert not np.array_equal(act[0], act[1])
+
+
+def test_snapshot_resume_is_bit_identical(tmp_path):
+    """bidi_save_snapshot / bidi_load_snapshot: a run resumed from a file continues exactly like the
+    uninterrupted one (device noise included: the generator's step counter is part of the snapshot);
+    a snapshot of a different configuration is refused."""
+    import bidinet_b200
+    cfg, ld = cf.config_c2()
+    x = np.random.RandomState(0).rand(8, 3, 64).astype(np.float32)
+    a = Engine(cfg, ld, n_agents=3, seed=11)
+    for t in range(3):
+        a.set_inputs(x[t])
+        a.step(rewards=np.full(3, 0.1 * t, np.float32))
+    path = str(tmp_path / "c2.snap")
+    a.save_snapshot(path)
+    b = Engine(cfg, ld, n_agents=3)
+    b.load_snapshot(path)
+    for t in range(3, 6):
+        for e in (a, b):
+            e.set_inputs(x[t])
+            e.step(rewards=np.full(3, 0.1 * t, np.float32))
+    assert np.array_equal(a.get_predictions(), b.get_predictions())
+    assert np.array_equal(a.get_column_actions(), b.get_column_actions())
+    for agent in (0, 2):
+        assert diff_states(a.state(agent), b.state(agent)) == []
+    other = Engine(*cf.config_c1(cf.KWINNERS))
+    with pytest.raises(bidinet_b200.BidiError, match="not a snapshot"):
+        other.load_snapshot(path)

@@ -55,6 +55,16 @@ def small_cases():
         cfg, ld = cf.make_config(v, 7, 5, layers, r_infb=0 if v == cf.KWINNERS else 2)
         cases.append(("ragged_" + cf.VARIANT_NAMES[v], cfg, ld, lambda t: frames35[t % 64],
                       lambda t: float(np.cos(0.7 * t))))
+    # degenerate sizes: a 1x1 input, a 1x1 top layer, radius 0 windows (each unit sees one cell)
+    for v in (cf.KWINNERS, cf.ITERATIVE, cf.NEO_AGENT):
+        layers = [dict(width=3, height=2, r_ff=0, r_rec=0, r_lat=1, r_pred=0, r_fb=0),
+                  dict(width=1, height=1, r_ff=1, r_rec=-1 if v == cf.KWINNERS else 0, r_lat=0, r_pred=0, r_fb=0)]
+        if v == cf.KWINNERS:
+            for l in layers:
+                l["sparsity"] = 0.6
+        cfg, ld = cf.make_config(v, 1, 1, layers, r_infb=0 if v == cf.KWINNERS else 1, init=(-0.5, 0.5, 0.01, 0.05, 0.0))
+        cases.append(("tiny_" + cf.VARIANT_NAMES[v], cfg, ld, lambda t: np.array([float(t % 3 == 0)], np.float32),
+                      lambda t: float(t % 2)))
     # sdr::QPRSDR on ragged grids: three Q layers, actions scattered over the input, a window wider than the grid
     layers = [dict(width=6, height=4, r_ff=2, r_rec=1, r_lat=2, r_pred=1, r_fb=1),
               dict(width=3, height=5, r_ff=1, r_rec=2, r_lat=1, r_pred=3, r_fb=2),
