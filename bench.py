@@ -317,7 +317,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents-per-gpu", type=int, default=4096)
-    ap.add_argument("--ref-inner-steps", type=int, default=20)
+    ap.add_argument("--ref-inner-steps", type=int, default=200)
     ap.add_argument("--cpu-baseline-steps", type=int, default=1500)
     ap.add_argument("--profile-kernel", default="columns")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -393,14 +393,25 @@ def main():
     # the synthetic environment's noise draws (RunnerMain.cpp:241-242) are data, made before the clock starts
     env_noise = rng.normal(0.0, 0.05, (W + K, A, len(FB_IDX))).astype(np.float32)
     e2e_i = 0
+    fb0, fb1 = int(FB_IDX[0]), int(FB_IDX[-1]) + 1     # the action inputs are one contiguous run of cells
+    assert np.array_equal(FB_IDX, np.arange(fb0, fb1))
+    act = np.empty((A, fb1 - fb0), dtype=np.float32)
+    tmp = np.empty_like(act)
+    inv_n = np.full(fb1 - fb0, 1.0 / (fb1 - fb0), dtype=np.float32)
 
     def host_step(tt):
+        """the caller's side of RunnerMain.cpp:235-251: state inputs, fed-back noisy actions, reward"""
         nonlocal pred, e2e_i
         np.copyto(x, frames[tt % T])
-        act = pred[:, FB_IDX] * 0.5 + 0.5
-        np.clip(act + env_noise[e2e_i], 0.0, 1.0, out=x[:, FB_IDX])
+        np.multiply(pred[:, fb0:fb1], 0.5, out=act)
+        np.add(act, 0.5, out=act)
+        np.add(act, env_noise[e2e_i], out=tmp)
         e2e_i += 1
-        np.subtract(np.clip(act, 0.0, 1.0).mean(axis=1), 0.5, out=rewards)
+        np.clip(tmp, 0.0, 1.0, out=tmp)
+        x[:, fb0:fb1] = tmp
+        np.clip(act, 0.0, 1.0, out=act)
+        np.dot(act, inv_n, out=rewards)
+        np.subtract(rewards, 0.5, out=rewards)
         eng.set_inputs(x)
         eng.step(rewards=rewards)
         pred = eng.get_predictions()

@@ -189,7 +189,7 @@ class Engine:
                                        None if v is None else _fptr(v), int(bool(learn))), "bidi_step")
 
     def get_predictions(self):
-        out = np.zeros((self.n_agents, self.n_in), dtype=np.float32)
+        out = np.empty((self.n_agents, self.n_in), dtype=np.float32)
         self._check(self.lib.bidi_get_predictions(self.h, _fptr(out)), "bidi_get_predictions")
         return out
 
