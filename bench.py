@@ -321,6 +321,9 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=1500)
     ap.add_argument("--profile-kernel", default="columns")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--burn-in", type=int, default=400,
+                    help="untimed steps before the warm-up: by then every column cell spikes once per step and every "
+                         "learning rule does its full work (a freshly initialised network does less)")
     ap.add_argument("--workload", default="c3", choices=["c3", "c5"])
     ap.add_argument("--c5-size", type=int, default=1024)
     ap.add_argument("--c5-transport", default="ipc", choices=["ipc", "nccl"])
@@ -365,6 +368,10 @@ def main():
 
     # ---- value: device-resident inputs, CUDA events on the engine's stream
     t = 0
+    for _ in range(args.burn_in):  # part of the set-up, like the weight initialisation
+        eng.step_frame(t)
+        t += 1
+    eng.sync()
     for _ in range(W):
         eng.step_frame(t)
         t += 1
@@ -480,7 +487,8 @@ def main():
         "config": {"workload": "C3: neo::Agent RunnerMain hierarchy (in 8x8, 8x8->4x4, 144 columns), headless runner loop",
                    "agents_per_gpu": A, "agents": world * A, "learn": True, "parallelism": "agents sharded over ranks, no collective",
                    "l2": "per-step working set %.1f GB per GPU exceeds the 126 MB L2" % (eng.device_bytes / 1e9),
-                   "exploration_noise": "engine counter-based generator", "state_bytes_per_gpu": eng.device_bytes},
+                   "exploration_noise": "engine counter-based generator", "state_bytes_per_gpu": eng.device_bytes,
+                   "burn_in_steps": args.burn_in},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,
                 "h2d_bytes_per_step": int(A * n_in * 4 + A * 4), "d2h_bytes_per_step": int(A * n_in * 4)},
         "gpu_launches": int(launches),

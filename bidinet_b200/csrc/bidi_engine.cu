@@ -142,6 +142,7 @@ struct bidi_engine {
   // whole step as one cooperative launch (bidi_coop.cuh): the program per value of `learn`
   int coop_mode = 0;                               // option "coop_step": 1 = use it when every layer runs the tile kernels (measured no faster than the graph: off by default)
   bidi::CoopOp* d_coop_ops[2] = {nullptr, nullptr}; int coop_n[2] = {0, 0}; int coop_grid = 0; size_t coop_smem = 0;
+  int col_extra_smem = 0;                          // experiment: pad the column kernel's shared memory to lower its residency
   bool strip_use_graph = true;                     // record the split step (NCCL exchanges included) into a CUDA graph
   cudaEvent_t strip_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t strip_done = nullptr;
@@ -510,7 +511,7 @@ void record_columns(Recorder& R, int l) {
   const int ppw = columns_pairs_per_warp(C);
   const int n_pairs = (C.n + 1) / 2;
   const long long warps = (long long)h->A * ((n_pairs + ppw - 1) / ppw);
-  const size_t smem = columns_smem_bytes(C);
+  const size_t smem = columns_smem_bytes(C) + (size_t)h->col_extra_smem;
   R.before("columns");
   if (C.planar) bidi::k_columns16<<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
   else if (ppw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
@@ -1538,6 +1539,12 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     if (rc) return rc;
   }
   else if (std::string(name) == "strip_graph") h->strip_use_graph = value != 0;
+  else if (std::string(name) == "col_extra_smem") {
+    h->col_extra_smem = value;
+    size_t smem = 0;
+    for (auto& D : h->layers) if (D.col.n > 0) smem = std::max(smem, columns_smem_bytes(D.col));
+    CU(cudaFuncSetAttribute(bidi::k_columns16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
+  }
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
