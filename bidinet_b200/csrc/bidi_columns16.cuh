@@ -16,6 +16,15 @@
 // what matters is the number of warp instructions per pair: the cell count is a compile
 // time constant, and nothing is computed for a column that did not spike.
 //
+// Residency: the kernel is bound by how many records an SM holds (its time goes as
+// 0.7 ms + 22 ms / resident warps per SM on C3, measured by padding shared memory), and a
+// record is 80 % weights.  So the first RH inputs of every weight row live in REGISTERS of
+// the lane that owns the row (RH = 64 or 32 floats per lane), loaded and stored with
+// coalesced 128-bit global accesses from a lane-major part of the record, and only the
+// rest of the row goes through shared memory with the TMA copy.  The sweep and the
+// element-wise update use the registers directly; for the reconstruction the few rows that
+// spiked are parked in a small shared scratch (four rows per column at a time).
+//
 // Rounding rules are those of bidi_columns.cuh: no fused multiply-add anywhere.
 #pragma once
 #include "bidi_columns.cuh"
@@ -25,9 +34,12 @@ namespace bidi {
 __device__ __forceinline__ float lo32(u64 v) { float x, y; upk(v, x, y); return x; }
 __device__ __forceinline__ float hi32(u64 v) { float x, y; upk(v, x, y); return y; }
 
+template <int RH>
 __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l) {
   extern __shared__ __align__(128) float smem[];
   constexpr int CC = 16;
+  constexpr int RB = 4;              // spiking rows per column parked in the scratch at a time
+  constexpr int RQ = RH / 4, RP = RH / 2, RT = RH / 32;  // register part: 128-bit chunks, input pairs, 16-pair trips
   const ColumnsDev& C = L.col;
   const Pair F{P.k_one2, P.k_negzero2, P.k_negone2};
   const int lane = threadIdx.x, c = lane >> 4, i = lane & 15;
@@ -38,15 +50,17 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   const bool has = node < C.n;
   float* B = blob_of(P, a);
 
-  const int S = C.stride[pair];
-  const int R = C.rec_off[pair + 1] - C.rec_off[pair];
+  const int S = C.stride[pair], SH = S - RH;             // row length; the part of it that lives in shared memory
+  const int R = C.rec_off[pair + 1] - C.rec_off[pair] - 32 * RH;  // floats of the shared-memory part of the record
   const int blk = R >> 1;
   float* rec = smem;
   float* in_s = smem + C.max_rec + c * C.max_s;          // gathered inputs of column c, [S], pad 0
   float* st_s = smem + C.max_rec + 2 * C.max_s + c * CC;  // final cell states of column c
   float* kf_s = st_s + 2 * CC;                            // feed-forward learning factors of column c
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C.max_rec + 2 * C.max_s + 4 * CC);
-  float* g_rec = B + C.rec_base + C.rec_off[pair];
+  float* scr = smem + C.max_rec + 2 * C.max_s + 4 * CC + c * (RB * RH);  // parked rows of column c, [RB][RH]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C.max_rec + 2 * C.max_s + 4 * CC + 2 * RB * RH);
+  float* g_reg = B + C.rec_base + C.rec_off[pair];       // register part: [RQ][32 lanes][4]
+  float* g_rec = g_reg + 32 * RH;
 
   // ---- the record starts on its way in (one TMA bulk copy)
   if (lane == 0) mbar_init(bar, 1);
@@ -55,9 +69,16 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
     mbar_expect_tx(bar, (uint32_t)R * 4u);
     tma_load_1d(rec, g_rec, (uint32_t)R * 4u, bar);
   }
+  // the first RH inputs of this lane's weight row, straight from HBM into registers
+  u64 wr[RP > 0 ? RP : 1];
+#pragma unroll
+  for (int q = 0; q < RQ; q++) {
+    const ulonglong2 v = reinterpret_cast<const ulonglong2*>(g_reg)[q * 32 + lane];
+    wr[2 * q] = v.x; wr[2 * q + 1] = v.y;
+  }
   // sections of column c's block
-  float* W = rec + c * blk;          // [16][S]
-  float* latT = W + CC * S;          // [16][16], latT[k][i] = lat[i][k]
+  float* W = rec + c * blk;          // [16][SH]
+  float* latT = W + CC * SH;         // [16][16], latT[k][i] = lat[i][k]
   float* v_thr = latT + CC * CC;
   float* v_qw = v_thr + CC; float* v_qtr = v_qw + CC;
   float* v_aw = v_qtr + CC;          // [3][16]
@@ -98,18 +119,24 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   unsigned m = (__ballot_sync(0xffffffffu, sp != 0.0f) >> (16 * c)) & 0xffffu;  // column c's spiking cells
   float act = 0.0f, st = 0.0f, counter = 0.0f, mult = 0.0f;
   const float oml = 1.0f - C.leak;
-  const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(W + i * S);
+  const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(W + i * SH);
   const ulonglong2* e4 = reinterpret_cast<const ulonglong2*>(err);
-  const int n4 = S >> 2, n2 = S >> 1;
+  const int n4 = SH >> 2, n2 = S >> 1;
   const u64* in2 = reinterpret_cast<const u64*>(in_s);
   u64* err2 = reinterpret_cast<u64*>(err);
   constexpr int NP = 5;  // input pairs per lane per trip: 16*5*2 = 160 inputs
   for (int it = 0; it < C.iter; it++) {
     // excitation += w * err, sequentially over the inputs
     float exc = 0.0f;
+#pragma unroll
+    for (int q = 0; q < RQ; q++) {
+      const ulonglong2 e = e4[q];
+      const u64 p01 = F.mul(wr[2 * q], e.x), p23 = F.mul(wr[2 * q + 1], e.y);
+      exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+    }
 #pragma unroll 4
     for (int j = 0; j < n4; j++) {
-      const ulonglong2 w = w4[j], e = e4[j];
+      const ulonglong2 w = w4[j], e = e4[RQ + j];
       const u64 p01 = F.mul(w.x, e.x), p23 = F.mul(w.y, e.y);
       exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
     }
@@ -126,23 +153,76 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
     // reconstruction from the spiking cells, ascending cell index (neo/Column.cpp:93-102):
     // recon += (spike*multiplier) * w ; error = input - recon
     const u64 mult2 = pk(mult, mult);
-    for (int p0 = 0; p0 < n2; p0 += 16 * NP) {
-      float rx[NP], ry[NP];
+    const int ns = n2 - RP;  // input pairs in the shared-memory part of a row
+    float rx[NP], ry[NP];
 #pragma unroll
-      for (int t = 0; t < NP; t++) { rx[t] = 0.0f; ry[t] = 0.0f; }
+    for (int t = 0; t < NP; t++) { rx[t] = 0.0f; ry[t] = 0.0f; }
+    if (RH > 0) {
+      // spiking rows RB at a time per column: their owners park the register part in the scratch,
+      // then every lane adds them to its input pairs, ascending cell index
+      const unsigned bal = __ballot_sync(0xffffffffu, sp != 0.0f);
+      const int most = max(__popc(bal & 0xffffu), __popc(bal >> 16));
+      const int rank = __popc(m & ((1u << i) - 1u));
+      unsigned mm = m;
+      for (int b0 = 0; b0 < most; b0 += RB) {
+        if (sp != 0.0f && rank >= b0 && rank < b0 + RB) {
+          ulonglong2* dst = reinterpret_cast<ulonglong2*>(scr + (rank - b0) * RH);
+#pragma unroll
+          for (int q = 0; q < RQ; q++) dst[q] = make_ulonglong2(wr[2 * q], wr[2 * q + 1]);
+        }
+        __syncwarp();
+        for (int b = 0; b < RB && mm; b++, mm &= mm - 1) {
+          const int k = __ffs(mm) - 1;
+          const u64* rrow = reinterpret_cast<const u64*>(scr + b * RH) + i;
+#pragma unroll
+          for (int t = 0; t < RT; t++) {
+            const u64 pr = F.mul(mult2, rrow[16 * t]);
+            rx[t] += lo32(pr); ry[t] += hi32(pr);
+          }
+          const u64* row = reinterpret_cast<const u64*>(W + k * SH) + i;
+#pragma unroll
+          for (int t = RT; t < NP; t++)
+            if (i + 16 * (t - RT) < ns) {
+              const u64 pr = F.mul(mult2, row[16 * (t - RT)]);
+              rx[t] += lo32(pr); ry[t] += hi32(pr);
+            }
+        }
+        __syncwarp();
+      }
+    } else {
       for (unsigned mm = m; mm; mm &= mm - 1) {
-        const u64* row = reinterpret_cast<const u64*>(W + (__ffs(mm) - 1) * S) + p0 + i;
+        const u64* row = reinterpret_cast<const u64*>(W + (__ffs(mm) - 1) * SH) + i;
+#pragma unroll
+        for (int t = 0; t < NP; t++)
+          if (i + 16 * t < ns) {
+            const u64 pr = F.mul(mult2, row[16 * t]);
+            rx[t] += lo32(pr); ry[t] += hi32(pr);
+          }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NP; t++) {
+      const int p = i + 16 * t;
+      if (p < n2) err2[p] = F.sub2(in2[p], pk(rx[t], ry[t]));
+    }
+    // rows longer than 16*NP pairs: the rest of the shared-memory part
+    for (int p0 = 16 * NP; p0 < n2; p0 += 16 * NP) {
+      float sx[NP], sy[NP];
+#pragma unroll
+      for (int t = 0; t < NP; t++) { sx[t] = 0.0f; sy[t] = 0.0f; }
+      for (unsigned mm = m; mm; mm &= mm - 1) {
+        const u64* row = reinterpret_cast<const u64*>(W + (__ffs(mm) - 1) * SH) + (p0 - RP) + i;
 #pragma unroll
         for (int t = 0; t < NP; t++)
           if (p0 + i + 16 * t < n2) {
             const u64 pr = F.mul(mult2, row[16 * t]);
-            rx[t] += lo32(pr); ry[t] += hi32(pr);
+            sx[t] += lo32(pr); sy[t] += hi32(pr);
           }
       }
 #pragma unroll
       for (int t = 0; t < NP; t++) {
         const int p = p0 + i + 16 * t;
-        if (p < n2) err2[p] = F.sub2(in2[p], pk(rx[t], ry[t]));
+        if (p < n2) err2[p] = F.sub2(in2[p], pk(sx[t], sy[t]));
       }
     }
     __syncwarp();
@@ -192,7 +272,17 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   kf_s[i] = C.a_ff * st;
   __syncwarp();
   const unsigned live = (__ballot_sync(0xffffffffu, st > 0.0f) >> (16 * c)) & 0xffffu;
-  for (int p0 = 0; p0 < n2; p0 += 16 * NP) {
+  if (RH > 0 && st > 0.0f) {  // the register part of this lane's own row
+    const float kf = kf_s[i];
+    const u64 k2 = pk(kf, kf);
+#pragma unroll
+    for (int q = 0; q < RQ; q++) {
+      const ulonglong2 e = e4[q];
+      wr[2 * q] = F.add2(F.mul(k2, e.x), wr[2 * q]);
+      wr[2 * q + 1] = F.add2(F.mul(k2, e.y), wr[2 * q + 1]);
+    }
+  }
+  for (int p0 = RP; p0 < n2; p0 += 16 * NP) {  // the shared-memory part, lanes over input pairs
     u64 e2[NP];
 #pragma unroll
     for (int t = 0; t < NP; t++) { const int p = p0 + i + 16 * t; e2[t] = p < n2 ? err2[p] : 0ull; }
@@ -200,7 +290,7 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
       const int r = __ffs(mm) - 1;
       const float kf = kf_s[r];
       const u64 k2 = pk(kf, kf);
-      u64* row = reinterpret_cast<u64*>(W + r * S) + p0 + i;
+      u64* row = reinterpret_cast<u64*>(W + r * SH) + (p0 - RP) + i;
 #pragma unroll
       for (int t = 0; t < NP; t++)
         if (p0 + i + 16 * t < n2) row[16 * t] = F.add2(F.mul(k2, e2[t]), row[16 * t]);
@@ -225,7 +315,9 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   __syncwarp();  // every lane has read prevValue
   if (i == 0) scal[0] = q;
 
-  // ---- record back to HBM (one TMA bulk copy)
+  // ---- record back to HBM: the register part with coalesced 128-bit stores, the rest as one TMA bulk copy
+#pragma unroll
+  for (int q = 0; q < RQ; q++) reinterpret_cast<ulonglong2*>(g_reg)[q * 32 + lane] = make_ulonglong2(wr[2 * q], wr[2 * q + 1]);
   fence_async_smem();
   __syncwarp();
   if (lane == 0) {

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <random>
 #include <string>
 #include <thread>
@@ -41,20 +42,29 @@ struct ColumnsHost {
 // stored in PAIRS (nodes 2p, 2p+1) with every element interleaved [..][2]
 // (layout: bidi_types.h, ColumnsDev), so element k of a section is ptr[2*k].
 struct ColRec {
-  float *W, *latT, *thr, *q_w, *q_tr, *a_w, *a_tr, *sprev, *err, *scal;
+  float *W, *Wreg, *latT, *thr, *q_w, *q_tr, *a_w, *a_tr, *sprev, *err, *scal;
   int S, Cq, nin;
-  int es;  // element stride: 2 in the pair-interleaved layout, 1 in the planar one
+  int es;        // element stride: 2 in the pair-interleaved layout, 1 in the planar one
+  int rh, lane0; // planar: inputs per row kept in the lane-major register part; this column's first lane (0 or 16)
+  // weight of cell i, input j
+  float& w(int i, int j) const {
+    if (j < rh) return Wreg[((long long)(j >> 2) * 32 + lane0 + i) * 4 + (j & 3)];
+    return W[(long long)es * ((long long)i * (S - rh) + (j - rh))];
+  }
 };
 ColRec col_rec(const ColumnsDev& C, const ColumnsHost& H, float* blob, int node) {
   ColRec r;
   const int pair = node >> 1, half = node & 1;
   r.S = H.stride[pair]; r.Cq = C.cq; r.nin = H.in_off[node + 1] - H.in_off[node];
-  const int block = C.cells * r.S + C.cells * C.cq + 10 * C.cq + r.S + 4;  // floats of ONE column
+  r.rh = C.planar ? C.rh : 0; r.lane0 = half * 16;
+  const int sh = r.S - r.rh;
+  const int block = C.cells * sh + C.cells * C.cq + 10 * C.cq + r.S + 4;  // floats of ONE column's shared-memory block
   r.es = C.planar ? 1 : 2;
-  // planar: column 2p's block, then column 2p+1's; interleaved: element k of a section is ptr[2*k]
-  r.W = blob + C.rec_base + H.rec_off[pair] + (C.planar ? half * block : half);
+  // planar: the register part, then column 2p's block, then column 2p+1's; interleaved: element k of a section is ptr[2*k]
+  r.Wreg = blob + C.rec_base + H.rec_off[pair];
+  r.W = r.Wreg + 32 * r.rh + (C.planar ? half * block : half);
   const int e = r.es;
-  r.latT = r.W + (long long)e * C.cells * r.S;
+  r.latT = r.W + (long long)e * C.cells * sh;
   r.thr = r.latT + e * C.cells * C.cq;
   r.q_w = r.thr + e * C.cq; r.q_tr = r.q_w + e * C.cq; r.a_w = r.q_tr + e * C.cq; r.a_tr = r.a_w + 3 * e * C.cq;
   r.sprev = r.a_tr + 3 * e * C.cq; r.err = r.sprev + e * C.cq; r.scal = r.err + e * r.S;
@@ -399,7 +409,7 @@ template <class F> void walk_column(const bidi_engine* h, int which, int layer, 
     const ColRec r = col_rec(C, H, blob, node);
     switch (which) {
       case BIDI_COL_RECON_ERR: for (int j = 0; j < r.nin; j++) f(r.err[r.es * j]); break;
-      case BIDI_COL_FF_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < r.nin; j++) f(r.W[r.es * ((long long)i * r.S + j)]); break;
+      case BIDI_COL_FF_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < r.nin; j++) f(r.w(i, j)); break;
       case BIDI_COL_LAT_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < C.cells; j++) f(r.latT[r.es * (j * r.Cq + i)]); break;
       case BIDI_COL_THRESHOLD: for (int i = 0; i < C.cells; i++) f(r.thr[r.es * i]); break;
       case BIDI_COL_SPIKE_PREV: for (int i = 0; i < C.cells; i++) f(r.sprev[r.es * i]); break;
@@ -513,7 +523,9 @@ void record_columns(Recorder& R, int l) {
   const long long warps = (long long)h->A * ((n_pairs + ppw - 1) / ppw);
   const size_t smem = columns_smem_bytes(C) + (size_t)h->col_extra_smem;
   R.before("columns");
-  if (C.planar) bidi::k_columns16<<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  if (C.planar && C.rh == 64) bidi::k_columns16<64><<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  else if (C.planar && C.rh == 32) bidi::k_columns16<32><<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  else if (C.planar) bidi::k_columns16<0><<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
   else if (ppw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   R.after("columns");
@@ -858,6 +870,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   if (V == BIDI_NEO_AGENT && (cfg->col_cells < 1 || cfg->col_cells > 32 || cfg->col_iter < 1))
     return fail(h, BIDI_EINVAL, "bidi_create: columns need 1..32 cells and >= 1 iteration");
 
+  const bool h_no_col_regs = getenv("BIDI_NO_COL_REGS") != nullptr;  // experiment switch: keep whole weight rows in shared memory
   h = new bidi_engine();
   h->cfg = *cfg; h->ld.assign(layers, layers + L);
   h->cfg.variant = V; h->qnet = qnet;
@@ -952,14 +965,21 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
         H.col.in_off[i + 1] = H.col.in_off[i] + nin;
         C.max_in = std::max(C.max_in, nin);
       }
+      int s_min = 1 << 30;
       for (int p = 0; p < n_pairs; p++) {
         const int na = H.col.in_off[2 * p + 1] - H.col.in_off[2 * p];
         const int nb = 2 * p + 1 < C.n ? H.col.in_off[2 * p + 2] - H.col.in_off[2 * p + 1] : 0;
-        const int S = column_pair_stride(std::max(na, nb), C.planar != 0);
-        const int rec = 2 * (C.cells * S + C.cells * C.cq + 10 * C.cq + S + 4);
-        H.col.rec_off[p + 1] = H.col.rec_off[p] + rec;
-        H.col.stride[p] = S;
-        C.max_s = std::max(C.max_s, S); C.max_rec = std::max(C.max_rec, rec);
+        H.col.stride[p] = column_pair_stride(std::max(na, nb), C.planar != 0);
+        s_min = std::min(s_min, H.col.stride[p]);
+      }
+      // planar: how much of every weight row lives in registers (bidi_columns16.cuh); every row keeps >= 4 inputs in shared memory
+      C.rh = !C.planar ? 0 : (s_min >= 68 ? 64 : (s_min >= 36 ? 32 : 0));
+      if (h_no_col_regs) C.rh = 0;
+      for (int p = 0; p < n_pairs; p++) {
+        const int S = H.col.stride[p];
+        const int part = 2 * (C.cells * (S - C.rh) + C.cells * C.cq + 10 * C.cq + S + 4);
+        H.col.rec_off[p + 1] = H.col.rec_off[p] + 32 * C.rh + part;
+        C.max_s = std::max(C.max_s, S); C.max_rec = std::max(C.max_rec, part);
       }
       C.tot_in = H.col.in_off[C.n];
       const long long nc = (long long)C.n * C.cells;
@@ -1197,7 +1217,9 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     if (smem > 227 * 1024) return bail(BIDI_EINVAL, "bidi_create: a column record does not fit in shared memory");
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   *out = h;
   return BIDI_OK;
@@ -1326,7 +1348,7 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
       const ColRec r = col_rec(C, CH, img.data(), node);
       for (int i = 0; i < C.cells; i++) {
         r.thr[r.es * i] = g.init_threshold;
-        for (int j = 0; j < r.nin; j++) r.W[r.es * ((long long)i * r.S + j)] = weightDist(gen);
+        for (int j = 0; j < r.nin; j++) r.w(i, j) = weightDist(gen);
         for (int j = 0; j < C.cells; j++) r.latT[r.es * (j * r.Cq + i)] = inhibitionDist(gen);
         r.q_w[r.es * i] = weightDist(gen);
       }
@@ -1543,7 +1565,9 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     h->col_extra_smem = value;
     size_t smem = 0;
     for (auto& D : h->layers) if (D.col.n > 0) smem = std::max(smem, columns_smem_bytes(D.col));
-    CU(cudaFuncSetAttribute(bidi::k_columns16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
+    CU(cudaFuncSetAttribute(bidi::k_columns16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
+    CU(cudaFuncSetAttribute(bidi::k_columns16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
+    CU(cudaFuncSetAttribute(bidi::k_columns16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
   }
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen

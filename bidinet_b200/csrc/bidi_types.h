@@ -70,7 +70,9 @@ struct ColumnsDev {
   int n, cells, cq, tot_in; // nodes, cells per column, cells rounded up to 4, sum of nIn
   int max_in;               // largest nIn
   int planar;               // record layout: 0 pair-interleaved (k_columns), 1 planar (k_columns16)
-  int max_s, max_rec;       // largest pair stride / pair record length (floats)
+  int rh;                   // planar only: the first rh inputs of every weight row form the record's lane-major
+                            // "register part" [rh/4][32 lanes][4] that precedes the two column blocks (0, 32 or 64)
+  int max_s, max_rec;       // largest pair stride / largest shared-memory part of a pair record (floats)
   const int* in_off;        // [n+1] prefix sums of nIn (same for every agent)
   const int* in_src;        // [tot_in] blob offset each column input is gathered from (neo/Agent.cpp:159-169)
   const int* rec_off;       // [n_pairs+1] pair record offsets (floats) relative to rec_base
