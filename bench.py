@@ -381,12 +381,17 @@ def main():
     if rank == 0:
         clocks.start()
     launches0 = eng.launch_count
+    ncu_range = os.environ.get("BIDI_NCU_RANGE") == "1"   # ncu --profile-from-start off: profile the timed steps only
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     eng.timer_start()
     for _ in range(K):
         eng.step_frame(t)
         t += 1
     ms = eng.timer_stop_ms()
     eng.sync()
+    if ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     barrier()
     launches = eng.launch_count - launches0
     ms = max_over_ranks(ms)
@@ -406,10 +411,12 @@ def main():
     tmp = np.empty_like(act)
     inv_n = np.full(fb1 - fb0, 1.0 / (fb1 - fb0), dtype=np.float32)
 
+    np.copyto(x, frames[t % T])
+
     def host_step(tt):
-        """the caller's side of RunnerMain.cpp:235-251: state inputs, fed-back noisy actions, reward"""
+        """the caller's side of RunnerMain.cpp:235-251: state inputs, fed-back noisy actions, reward.
+        The open-loop part of the NEXT frame is laid out while the GPU works on this step."""
         nonlocal pred, e2e_i
-        np.copyto(x, frames[tt % T])
         np.multiply(pred[:, fb0:fb1], 0.5, out=act)
         np.add(act, 0.5, out=act)
         np.add(act, env_noise[e2e_i], out=tmp)
@@ -420,8 +427,9 @@ def main():
         np.dot(act, inv_n, out=rewards)
         np.subtract(rewards, 0.5, out=rewards)
         eng.set_inputs(x)
-        eng.step(rewards=rewards)
-        pred = eng.get_predictions()
+        eng.step(rewards=rewards)        # asynchronous: returns once the step is enqueued
+        np.copyto(x, frames[(tt + 1) % T])
+        pred = eng.get_predictions()     # device -> host, synchronises
 
     for _ in range(W):
         host_step(t)
