@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(512) k_coder_cta(EngineDev P, LayerDev L, int 
   }
   __syncthreads();
   const float* wlat = B + L.lat.w_off;
+  const bool gen = NEO && P.gen_on;
+  const float* gen_nz = gen ? P.gen_normals + (long long)a * P.gen_per_agent + L.gen_off : nullptr;
+  const float gen_scale = gen ? *P.gen_scale : 0.0f;
   const int total = NEO ? L.iter_settle : L.iter_settle + L.iter_measure;
   const float measure_inv = NEO ? 0.0f : 1.0f / (float)L.iter_measure;
   float counter = 0.0f, mult = 1.0f;
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(512) k_coder_cta(EngineDev P, LayerDev L, int 
         float sp = 0.0f;
         if (i < nh) {
           const int cs = c_self[i], ux = cs & 0xffff, uy = cs >> 16;
-          float excitation = 0.0f;
+          float excitation = gen ? gen_nz[(long long)it * nh + i] * gen_scale : 0.0f;  // simStepGenerate (neo/SparseCoder.cpp:200)
           {
             const int cf = c_ff[i];
             const float* ep = ev + (L.ff.absx ? 0 : (cf & 0xffff)) + (L.ff.absy ? 0 : (cf >> 16)) * S.fpitch;

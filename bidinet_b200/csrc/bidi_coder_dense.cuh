@@ -143,6 +143,9 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
   };
   if (warp < sweep_warps) build_lat_list();
   const float* wlat = B + L.lat.w_off;
+  const bool gen = NEO && P.gen_on;
+  const float* gen_nz = gen ? P.gen_normals + (long long)a * P.gen_per_agent + L.gen_off : nullptr;
+  const float gen_scale = gen ? *P.gen_scale : 0.0f;
   const int total = NEO ? L.iter_settle : L.iter_settle + L.iter_measure;
   const float measure_inv = NEO ? 0.0f : 1.0f / (float)L.iter_measure;
   float counter = 0.0f, mult = 1.0f;
@@ -173,7 +176,8 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
             }
           }
         }
-        float excitation = 0.0f;
+        // simStepGenerate: the excitation starts from noiseDist(generator) * noise (neo/SparseCoder.cpp:200)
+        float excitation = gen ? gen_nz[(long long)it * nh + i] * gen_scale : 0.0f;
         const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wff + i * S.Sf);
 #pragma unroll 4
         for (int j = 0; j < nf4; j++) {

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_step_coop(EngineDev P, const
         case OP_KW_INHIBIT: t_kw_inhibit(P, L, o.l, o.a[0], o.a[1], o.a[2], b); break;
         case OP_RECONSTRUCT: t_reconstruct(P, L, o.l, o.a[0], o.i[0], o.f[0], o.i[1], o.i[2], b); break;
         case OP_KW_LEARN: t_kw_learn(P, L, o.l, b); break;
-        case OP_IC_SWEEP: t_ic_sweep(P, L, o.l, o.i[0], o.i[1], o.f[0], b); break;
+        case OP_IC_SWEEP: t_ic_sweep(P, L, o.l, o.i[0], o.i[1], o.f[0], o.i[2], b); break;
         case OP_IC_LEARN: t_ic_learn(P, L, o.l, o.i[0], b); break;
         case OP_PREDICT: t_predict(P, L, o.l, o.i[0], o.a[0], o.a[1], b); break;
         case OP_IC_FINISH: d_ic_finish(P, L, o.l, o.i[0], o.f[0], o.a[0], (long long)b * blockDim.x + threadIdx.x); break;

@@ -118,8 +118,10 @@ struct bidi_engine {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // one graph per value of the learn flag
-  cudaGraphExec_t graphs[2] = {nullptr, nullptr};
-  int graph_kernels[2] = {0, 0};
+  cudaGraphExec_t graphs[3] = {nullptr, nullptr, nullptr};   // learn off, learn on, simStepGenerate
+  int graph_kernels[3] = {0, 0, 0};
+  // simStepGenerate
+  int gen_per_agent = 0; float* d_gen = nullptr; float* d_gen_scale = nullptr; float* h_gen = nullptr;
   long long launches = 0;
   unsigned long long step_index = 0, noise_seed = 0x5DEECE66DULL;
   // feedback taps (bidi_set_feedback)
@@ -657,9 +659,11 @@ void record_step(Recorder& R, bool learn) {
     const size_t sm_sweep = tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec) + nslots_of(Y.lat));
     const size_t sm_rec = tile_bytes(std::max(Y.ff.max_cand, Y.rec.max_cand));
     const long long t_sweep = tiles_of(A, Y.nh), t_rec = tiles_of(A, Y.nv) + tiles_of(A, Y.nh);
+    int sweep_it = 0;
     auto sweep = [&](int first, int acc, float scale) {
-      if (tl) launch_tile(R, "ic_sweep", bidi::k_t_ic_sweep, t_sweep, sm_sweep, Y, l, first, acc, scale);
-      else R.launch("ic_sweep", bidi::k_ic_sweep, nh, Y, l, first, acc, scale);
+      if (tl) launch_tile(R, "ic_sweep", bidi::k_t_ic_sweep, t_sweep, sm_sweep, Y, l, first, acc, scale, sweep_it);
+      else R.launch("ic_sweep", bidi::k_ic_sweep, nh, Y, l, first, acc, scale, sweep_it);
+      sweep_it++;
     };
     auto recon = [&](long long drive, int scaled, float mult, int copy_spike) {
       if (tl) launch_tile(R, "reconstruct", bidi::k_t_reconstruct, t_rec, sm_rec, Y, l, drive, scaled, mult, copy_spike, 0);
@@ -713,20 +717,24 @@ void record_step(Recorder& R, bool learn) {
   }
 }
 
-int ensure_graph(bidi_engine* h, bool learn) {
-  cudaGraphExec_t& exec = h->graphs[learn];
+// mode 0 / 1: simStep with learn off / on; 2: simStepGenerate (no learning, noise-driven coders)
+int ensure_graph(bidi_engine* h, int mode) {
+  cudaGraphExec_t& exec = h->graphs[mode];
   if (exec) return BIDI_OK;
   cudaGraph_t graph = nullptr;
+  const bool learn = mode == 1;
   CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   Recorder R{h};
+  h->P.gen_on = mode == 2 ? 1 : 0;  // kernel arguments are captured by value
   record_step(R, learn);
+  h->P.gen_on = 0;
   cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
   if (e != cudaSuccess) return fail(h, BIDI_ECUDA, std::string("graph capture: ") + cudaGetErrorString(e));
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(h, BIDI_ECUDA, std::string("kernel launch during capture: ") + cudaGetErrorString(e));
   CU(cudaGraphInstantiate(&exec, graph, 0));
   CU(cudaGraphDestroy(graph));
-  h->graph_kernels[learn] = R.kernels;
+  h->graph_kernels[mode] = R.kernels;
   return BIDI_OK;
 }
 
@@ -793,7 +801,7 @@ int run_step(bidi_engine* h, bool learn, bool device_noise) {
         h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index);
     h->launches++;
   }
-  rc = ensure_graph(h, learn);
+  rc = ensure_graph(h, learn ? 1 : 0);
   if (rc) return rc;
   CU(cudaGraphLaunch(h->graphs[learn], h->stream));
   h->launches += h->graph_kernels[learn];
@@ -824,7 +832,7 @@ void bidi_destroy(bidi_engine* h) {
   cudaFree(h->d_blob); cudaFree(h->d_in0); cudaFree(h->d_pred); cudaFree(h->d_rewards); cudaFree(h->d_noise_u);
   cudaFree(h->d_noise_v); cudaFree(h->d_col_actions); cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
   cudaFree(h->d_tables); cudaFree(h->d_layers); cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
-  cudaFree(h->d_qmask); cudaFree(h->d_qtables);
+  cudaFree(h->d_qmask); cudaFree(h->d_qtables); cudaFree(h->d_gen); cudaFree(h->d_gen_scale); cudaFreeHost(h->h_gen);
   for (auto& e : h->profile_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_pred); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_noise); cudaFreeHost(h->h_actions);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1070,6 +1078,17 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   CU_CREATE(cudaMalloc(&h->d_noise_u, sizeof(float) * A * nn));
   CU_CREATE(cudaMalloc(&h->d_noise_v, sizeof(float) * A * nn));
   CU_CREATE(cudaMalloc(&h->d_col_actions, sizeof(float) * A * nn));
+  if (V == BIDI_NEO_HIERARCHY) {  // simStepGenerate's N(0,1) draws: per layer iter x units
+    int off = 0;
+    for (int l = 0; l < L; l++) { h->layers[l].gen_off = off; off += layers[l].iter_settle * h->layers[l].nh; }
+    h->gen_per_agent = off;
+    CU_CREATE(cudaMalloc(&h->d_gen, sizeof(float) * A * (size_t)off));
+    CU_CREATE(cudaMalloc(&h->d_gen_scale, sizeof(float)));
+    CU_CREATE(cudaMemsetAsync(h->d_gen, 0, sizeof(float) * A * (size_t)off, h->stream));
+    CU_CREATE(cudaMemsetAsync(h->d_gen_scale, 0, sizeof(float), h->stream));
+    CU_CREATE(cudaMallocHost(&h->h_gen, sizeof(float) * (A * (size_t)off + 1)));
+    h->device_bytes += (long long)sizeof(float) * (long long)(A * (size_t)off + 1);
+  }
   CU_CREATE(cudaMemsetAsync(h->d_in0, 0, sizeof(float) * A * nin, h->stream));
   CU_CREATE(cudaMemsetAsync(h->d_pred, 0, sizeof(float) * A * nin, h->stream));
   CU_CREATE(cudaMemsetAsync(h->d_rewards, 0, sizeof(float) * A, h->stream));
@@ -1134,6 +1153,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   P.blob = h->d_blob; P.stride = h->stride; P.in0 = h->d_in0; P.pred_out = h->d_pred;
   P.rewards = h->d_rewards; P.noise_u = h->d_noise_u; P.noise_v = h->d_noise_v; P.col_actions = h->d_col_actions;
   P.ncol = h->ncol; P.layers = h->d_layers;
+  P.gen_on = 0; P.gen_per_agent = h->gen_per_agent; P.gen_normals = h->d_gen; P.gen_scale = h->d_gen_scale;
   P.q_on = qnet ? 1 : 0;
   if (qnet) {
     P.q_half = h->q_half; P.q_top = h->q_top; P.q_iters = cfg->q_derive_iterations;
@@ -1446,6 +1466,33 @@ int bidi_step(bidi_engine* h, const float* rewards, const float* noise_u, const 
     }
   }
   return run_step(h, learn != 0, agent && noise_u == nullptr);
+}
+
+int bidi_num_generate_noise(const bidi_engine* h) { return h ? h->gen_per_agent : 0; }
+
+int bidi_step_generate(bidi_engine* h, const float* normals, float noise) {
+  if (!h || h->cfg.variant != BIDI_NEO_HIERARCHY || h->gen_per_agent == 0)
+    return fail(h, BIDI_EINVAL, "bidi_step_generate: only neo::PredictiveHierarchy has simStepGenerate");
+  CU(cudaSetDevice(h->device));
+  int rc = mirror_release(h);
+  if (rc) return rc;
+  const size_t n = (size_t)h->A * h->gen_per_agent;
+  CU(cudaStreamSynchronize(h->stream));  // the staging buffer may still be in flight
+  if (normals) {
+    memcpy(h->h_gen, normals, sizeof(float) * n);
+    CU(cudaMemcpyAsync(h->d_gen, h->h_gen, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    bidi::k_gen_normals<<<grid_for((long long)n, kBlock), kBlock, 0, h->stream>>>(h->d_gen, (long long)n, h->noise_seed ^ 0x6E6F697365ULL, h->step_index);
+    h->launches++;
+  }
+  h->h_gen[n] = noise;
+  CU(cudaMemcpyAsync(h->d_gen_scale, h->h_gen + n, sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  rc = ensure_graph(h, 2);
+  if (rc) return rc;
+  CU(cudaGraphLaunch(h->graphs[2], h->stream));
+  h->launches += h->graph_kernels[2];
+  h->step_index++;
+  return BIDI_OK;
 }
 
 int bidi_get_predictions(bidi_engine* h, float* out) {

@@ -273,7 +273,7 @@ __global__ void k_kw_learn(EngineDev P, LayerDev L, int l) {
 // neo/SparseCoder.cpp:129-158.  first: activation and state start from 0
 // (sdr/IRSDR.cpp:131-135).  acc: 0 = settle (no state change), 1 = state +=
 // scale*spike (measure; scale = 1/measureIter), 2 = state += spike (neo).
-__global__ void k_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale) {
+__global__ void k_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale, int it) {
   BIDI_THREAD_AGENT_HIDDEN
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
@@ -285,7 +285,8 @@ __global__ void k_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, f
   const float* wrec = B + L.rec.w_off;
   const float* wlat = B + L.lat.w_off;
   const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
-  float excitation = 0.0f;
+  // simStepGenerate: starts from noiseDist(generator) * noise (neo/SparseCoder.cpp:200)
+  float excitation = P.gen_on ? P.gen_normals[(long long)a * P.gen_per_agent + L.gen_off + (long long)it * L.nh + i] * *P.gen_scale : 0.0f;
   excitation = dot_conn(L.ff, ux, uy, wff, U, i, excitation, [&](int t) { return x[t] - vrec[t]; });
   excitation = dot_conn(L.rec, ux, uy, wrec, U, i, excitation, [&](int t) { return sprev[t] - hrec[t]; });
   float inhibition = 0.0f;
@@ -573,6 +574,15 @@ __global__ void k_noise(EngineDev P, float* u, float* v, unsigned long long seed
     u[gid * 3 + k] = uu;
     v[gid * 3 + k] = vv;
   }
+}
+
+// N(0,1) draws for simStepGenerate when the caller supplies none (counter-based, Box-Muller)
+__global__ void k_gen_normals(float* out, long long n, unsigned long long seed, unsigned long long step) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n) return;
+  const unsigned long long h = mix64(seed ^ mix64(step * 0x100000001B3ULL + (unsigned long long)gid));
+  const float r1 = fmaxf(u01(h), 5.9604645e-8f), r2 = u01(mix64(h));
+  out[gid] = sqrtf(-2.0f * logf(r1)) * cospif(2.0f * r2);
 }
 
 // The caller's side of the RunnerMain loop, for device-resident runs: input[dst] =

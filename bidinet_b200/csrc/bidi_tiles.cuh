@@ -183,7 +183,7 @@ __device__ __forceinline__ void t_kw_learn(const EngineDev& P, const LayerDev& L
 }
 
 // ---- one sweep of the iterative coders, per phase: sdr/IRSDR.cpp:138-168
-__device__ __forceinline__ void t_ic_sweep(const EngineDev& P, const LayerDev& L, int l, int first, int acc, float scale, int bid) {
+__device__ __forceinline__ void t_ic_sweep(const EngineDev& P, const LayerDev& L, int l, int first, int acc, float scale, int it, int bid) {
   extern __shared__ float Pbuf[];
   const TileId T = tile_id(L.nh, bid);
   float* B = blob_of(P, T.a);
@@ -199,7 +199,8 @@ __device__ __forceinline__ void t_ic_sweep(const EngineDev& P, const LayerDev& L
   __syncthreads();
   if (T.g == 0 && T.ok) {
     const int i = T.unit;
-    const float excitation = tile_sum(Pbuf, 0, nff + nrec, T.ul, 0.0f);
+    const float start = P.gen_on ? P.gen_normals[(long long)T.a * P.gen_per_agent + L.gen_off + (long long)it * L.nh + i] * *P.gen_scale : 0.0f;
+    const float excitation = tile_sum(Pbuf, 0, nff + nrec, T.ul, start);
     const float inhibition = tile_sum(Pbuf, nff + nrec, nlat, T.ul, 0.0f);
     float av = first ? 0.0f : B[L.act + i];
     float st = first ? 0.0f : B[L.state + i];
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_activate(EngineDev P, L
 __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_inhibit(EngineDev P, LayerDev L, int l, long long src, long long dst, long long dst_next) { t_kw_inhibit(P, L, l, src, dst, dst_next, (int)blockIdx.x); }
 __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_reconstruct(EngineDev P, LayerDev L, int l, long long drive_off, int scaled, float mult, int copy_spike, int mode) { t_reconstruct(P, L, l, drive_off, scaled, mult, copy_spike, mode, (int)blockIdx.x); }
 __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_kw_learn(EngineDev P, LayerDev L, int l) { t_kw_learn(P, L, l, (int)blockIdx.x); }
-__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale) { t_ic_sweep(P, L, l, first, acc, scale, (int)blockIdx.x); }
+__global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale, int it) { t_ic_sweep(P, L, l, first, acc, scale, it, (int)blockIdx.x); }
 __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_ic_learn(EngineDev P, LayerDev L, int l, int traced) { t_ic_learn(P, L, l, traced, (int)blockIdx.x); }
 __global__ void __launch_bounds__(TILE_U* TILE_G) k_t_predict(EngineDev P, LayerDev L, int l, int learn, long long up_p_state, long long up_p_state_prev) { t_predict(P, L, l, learn, up_p_state, up_p_state_prev, (int)blockIdx.x); }
 

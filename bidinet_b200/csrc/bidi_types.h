@@ -92,6 +92,7 @@ struct LayerDev {
   // Row strip a launch works on (hidden rows [row0,row1), visible rows [vrow0,vrow1)).
   // The whole grid except when one oversized layer is split across GPUs (bidi_strip_*).
   int row0, row1, vrow0, vrow1;
+  int gen_off;                      // simStepGenerate: offset of this layer's N(0,1) draws inside an agent's block
   // coder unit planes (offsets into the blob)
   long long vis_input, vis_recon;   // vis_input is -1 for layer 0 (dense input array)
   long long thr, state, state_prev, act, recon, spike, spike_prev;
@@ -128,6 +129,10 @@ struct EngineDev {
   // {1,1}, {-0,-0}, {-1,-1} as packed f32x2 bit patterns.  Passed at run time so that
   // ptxas cannot fold fma(a,b,-0) / fma(a,1,c) back into a fused multiply-add.
   unsigned long long k_one2, k_negzero2, k_negone2;
+  // neo::PredictiveHierarchy::simStepGenerate: the coders' excitation starts from gen_normals[...] * *gen_scale
+  int gen_on, gen_per_agent;
+  const float* gen_normals;               // [A][gen_per_agent]: layer 0 first; iteration outer, unit inner
+  const float* gen_scale;                 // the `noise` argument, in device memory so that the step graph need not change
   // sdr::QPRSDR (bidi_qnet.cuh)
   int q_on, q_half, q_top, q_iters;       // 0/1; actions; nodes of the top layer; _actionDeriveIterations
   long long q_qc_w, q_qc_tr, q_act, q_prev; // blob offsets: _qConnections (w, trace), action nodes [4][2*half], _prevValue

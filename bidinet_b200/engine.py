@@ -27,6 +27,8 @@ ABI = {
     "bidi_num_inputs": (C.c_int, [C.c_void_p]),
     "bidi_num_columns": (C.c_int, [C.c_void_p]),
     "bidi_num_noise": (C.c_int, [C.c_void_p]),
+    "bidi_num_generate_noise": (C.c_int, [C.c_void_p]),
+    "bidi_step_generate": (C.c_int, [C.c_void_p, _FP, C.c_float]),
     "bidi_get_actions": (C.c_int, [C.c_void_p, _FP]),
     "bidi_q_kept": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_ubyte), C.c_longlong]),
     "bidi_array_len": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int]),
@@ -187,6 +189,14 @@ class Engine:
             assert u.size == v.size == self.n_agents * self.n_noise
         self._check(self.lib.bidi_step(self.h, None if r is None else _fptr(r), None if u is None else _fptr(u),
                                        None if v is None else _fptr(v), int(bool(learn))), "bidi_step")
+
+    def step_generate(self, noise, normals=None):
+        """neo::PredictiveHierarchy::simStepGenerate; normals: [agent][bidi_num_generate_noise] N(0,1) draws or None."""
+        z = None
+        if normals is not None:
+            z = np.ascontiguousarray(normals, dtype=np.float32)
+            assert z.size == self.n_agents * self.lib.bidi_num_generate_noise(self.h)
+        self._check(self.lib.bidi_step_generate(self.h, None if z is None else _fptr(z), float(noise)), "bidi_step_generate")
 
     def get_predictions(self):
         out = np.empty((self.n_agents, self.n_in), dtype=np.float32)
@@ -357,6 +367,14 @@ class StripGroup:
     def sync(self):
         for e in self.parts:
             e.sync()
+
+    def step_generate(self, noise, normals=None):
+        """neo::PredictiveHierarchy::simStepGenerate; normals: [agent][bidi_num_generate_noise] N(0,1) draws or None."""
+        z = None
+        if normals is not None:
+            z = np.ascontiguousarray(normals, dtype=np.float32)
+            assert z.size == self.n_agents * self.lib.bidi_num_generate_noise(self.h)
+        self._check(self.lib.bidi_step_generate(self.h, None if z is None else _fptr(z), float(noise)), "bidi_step_generate")
 
     def get_predictions(self):
         return assemble_rows([e.get_predictions() for e in self.parts], [e.spans["OWN_VIS"] for e in self.parts],

@@ -1,6 +1,6 @@
 // Drop-in for the reference's neo/PredictiveHierarchy.h.  Same LayerDesc fields and
 // defaults (neo/PredictiveHierarchy.h:14-45) and signatures (:106-130).
-// simStepGenerate (noise-driven dreaming, no caller in the reference) is not provided.
+// simStepGenerate (noise-driven dreaming, neo/PredictiveHierarchy.h:110) included.
 #pragma once
 #include "../detail/Hierarchy.h"
 
@@ -53,6 +53,22 @@ public:
   }
 
   void simStep(std::mt19937& /*generator*/, bool learn = true) { step(nullptr, nullptr, nullptr, learn); }
+
+  // neo/PredictiveHierarchy.cpp:247-315.  The N(0,1) values come from the CALLER's generator exactly as
+  // SparseCoder::activateNoise draws them (neo/SparseCoder.cpp:179,200): layer 0 first, one
+  // normal_distribution per layer, iteration outer, hidden unit inner.
+  void simStepGenerate(std::mt19937& generator, float noise) {
+    std::vector<float> normals;
+    normals.reserve((size_t)bidi_num_generate_noise(_h));
+    for (const LayerDesc& d : _layerDescs) {
+      std::normal_distribution<float> noiseDist(0.0f, 1.0f);
+      const int n = d._sdrIter * d._width * d._height;
+      for (int k = 0; k < n; k++) normals.push_back(noiseDist(generator));
+    }
+    bidinet::detail::check(bidi_set_inputs(_h, _inputs.data()), _h, "bidi_set_inputs");
+    bidinet::detail::check(bidi_step_generate(_h, normals.data(), noise), _h, "bidi_step_generate");
+    _predictionsFresh = false;
+  }
 
   void setInput(int index, float value) { _inputs[(size_t)index] = value; }
   void setInput(int x, int y, float value) { setInput(x + y * _layerDescs.front()._width, value); }  // neo/PredictiveHierarchy.h:116-118

@@ -200,6 +200,17 @@ int bidi_set_input(bidi_engine* h, int agent, int index, float value);
  */
 int bidi_step(bidi_engine* h, const float* rewards, const float* noise_u, const float* noise_v,
               int learn);
+/*
+ * neo::PredictiveHierarchy::simStepGenerate(generator, noise) (neo/PredictiveHierarchy.h:110,
+ * neo/PredictiveHierarchy.cpp:247-315): a step WITHOUT learning in which every coder unit's
+ * excitation starts, in every iteration, from noiseDist(generator) * noise instead of 0
+ * (SparseCoder::activateNoise, neo/SparseCoder.cpp:178-240).  BIDI_NEO_HIERARCHY only.
+ *   normals  [n_agents][bidi_num_generate_noise] host: the N(0,1) values in the reference's draw
+ *            order -- layer 0 first, per layer iteration outer / unit inner, one
+ *            std::normal_distribution per layer; NULL = the engine's own counter-based generator.
+ */
+int bidi_num_generate_noise(const bidi_engine* h);
+int bidi_step_generate(bidi_engine* h, const float* normals, float noise);
 int bidi_num_columns(const bidi_engine* h);
 /*
  * Floats per agent in each of bidi_step's noise_u / noise_v: 3 per column for NEO_AGENT;

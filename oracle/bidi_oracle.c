@@ -437,9 +437,10 @@ static void rsdr_learn(coder* c, const float* att, float lr_ff, float lr_rec, fl
 /* ======================= iterative coders ===================================== */
 /* One leaky-integrate-and-fire sweep over the hidden units: sdr/IRSDR.cpp:138-168
  * (== :177-209, == neo/SparseCoder.cpp:129-158). */
-static void icoder_sweep(coder* c, const float* ve, const float* he, float leak) {
+/* start: per-unit initial excitation (activateNoise, neo/SparseCoder.cpp:200) or NULL for 0 */
+static void icoder_sweep(coder* c, const float* ve, const float* he, float leak, const float* start, float scale) {
   for (int hi = 0; hi < c->nh; hi++) {
-    float excitation = 0.0f;
+    float excitation = start ? start[hi] * scale : 0.0f;
     for (int k = c->ff.off[hi]; k < c->ff.off[hi + 1]; k++) excitation += ve[c->ff.idx[k]] * c->ff.w[k];
     for (int k = c->rec.off[hi]; k < c->rec.off[hi + 1]; k++) excitation += he[c->rec.idx[k]] * c->rec.w[k];
     float inhibition = 0.0f;
@@ -460,14 +461,14 @@ static void irsdr_activate(coder* c, int settle, int measure, float leak) {
   for (int hi = 0; hi < c->nh; hi++) { c->act[hi] = 0.0f; c->state[hi] = 0.0f; }
   for (int it = 0; it < settle; it++) {
     icoder_errors(c, ve, he);
-    icoder_sweep(c, ve, he, leak);
+    icoder_sweep(c, ve, he, leak, NULL, 0.0f);
     memcpy(c->spike_prev, c->spike, sizeof(float) * (size_t)c->nh);
     coder_reconstruct(c, c->spike, 0, 0.0f);
   }
   float measure_inv = 1.0f / (float)measure;
   for (int it = 0; it < measure; it++) {
     icoder_errors(c, ve, he);
-    icoder_sweep(c, ve, he, leak);
+    icoder_sweep(c, ve, he, leak, NULL, 0.0f);
     for (int hi = 0; hi < c->nh; hi++) c->state[hi] += measure_inv * c->spike[hi];
     memcpy(c->spike_prev, c->spike, sizeof(float) * (size_t)c->nh);
     coder_reconstruct(c, c->spike, 0, 0.0f);
@@ -476,14 +477,15 @@ static void irsdr_activate(coder* c, int settle, int measure, float leak) {
   free(ve); free(he);
 }
 /* neo/SparseCoder.cpp:116-176 */
-static void sparsecoder_activate(coder* c, int iter, float leak) {
+/* normals != NULL: SparseCoder::activateNoise (neo/SparseCoder.cpp:178-240), normals[it][hi] = noiseDist(generator) */
+static void sparsecoder_activate(coder* c, int iter, float leak, const float* normals, float noise) {
   float* ve = (float*)malloc(sizeof(float) * (size_t)c->nv);
   float* he = (float*)malloc(sizeof(float) * (size_t)c->nh);
   for (int hi = 0; hi < c->nh; hi++) { c->act[hi] = 0.0f; c->state[hi] = 0.0f; }
   float counter = 0.0f;
   for (int it = 0; it < iter; it++) {
     icoder_errors(c, ve, he);
-    icoder_sweep(c, ve, he, leak);
+    icoder_sweep(c, ve, he, leak, normals ? normals + (size_t)it * c->nh : NULL, noise);
     for (int hi = 0; hi < c->nh; hi++) c->state[hi] += c->spike[hi];
     memcpy(c->spike_prev, c->spike, sizeof(float) * (size_t)c->nh);
     counter += 1.0f;
@@ -794,12 +796,16 @@ static void step_iterative(oracle* o, int learn) {
 }
 
 /* neo/PredictiveHierarchy.cpp:137-245 and neo/Agent.cpp:141-284 */
-static void step_neo(oracle* o, float reward, const float* u, const float* v, int learn) {
+/* gen_normals != NULL: simStepGenerate (neo/PredictiveHierarchy.cpp:247-315) = the same pass without any learning,
+ * the coders driven by noise */
+static void step_neo_ex(oracle* o, float reward, const float* u, const float* v, int learn, const float* gen_normals, float gen_noise) {
   const int L = o->L;
   const int agent = o->cfg.variant == BIDI_NEO_AGENT;
+  size_t gen_off = 0;
   for (int l = 0; l < L; l++) {
     coder* c = &o->cod[l];
-    sparsecoder_activate(c, o->ld[l].iter_settle, o->ld[l].leak);
+    sparsecoder_activate(c, o->ld[l].iter_settle, o->ld[l].leak, gen_normals ? gen_normals + gen_off : NULL, gen_noise);
+    gen_off += (size_t)o->ld[l].iter_settle * c->nh;
     if (l < L - 1) {
       float* nin = o->cod[l + 1].vis_input;
       if (agent) for (int i = 0; i < c->nh; i++) nin[i] = c->state[i] * o->pn[l].col.a_expl[i * 3 + 0]; /* _attention, neo/Agent.cpp:149 */
@@ -856,6 +862,41 @@ static void step_neo(oracle* o, float reward, const float* u, const float* v, in
     memcpy(p->state_prev, p->state, sizeof(float) * (size_t)p->n);
     memcpy(p->act_prev, p->act, sizeof(float) * (size_t)p->n);
   }
+}
+
+static void step_neo(oracle* o, float reward, const float* u, const float* v, int learn) { step_neo_ex(o, reward, u, v, learn, NULL, 0.0f); }
+
+/* N(0,1) draws of one simStepGenerate: layer 0 first, iteration outer, unit inner, a fresh normal_distribution per layer */
+int orc_num_generate_noise(void* h) {
+  oracle* o = (oracle*)h;
+  if (o->cfg.variant != BIDI_NEO_HIERARCHY) return 0;
+  int n = 0;
+  for (int l = 0; l < o->L; l++) n += o->ld[l].iter_settle * o->cod[l].nh;
+  return n;
+}
+static void draw_generate(const oracle* o, mt19937* g, float* out) {
+  size_t k = 0;
+  for (int l = 0; l < o->L; l++) {
+    normal_state ns = { 0, 0.0f };
+    const int n = o->ld[l].iter_settle * o->cod[l].nh;
+    for (int j = 0; j < n; j++) out[k++] = normal_real(g, &ns, 0.0f, 1.0f);
+  }
+}
+int orc_peek_generate(void* h, float* out) {
+  oracle* o = (oracle*)h;
+  if (o->cfg.variant != BIDI_NEO_HIERARCHY) return -1;
+  mt19937 g = o->gen;
+  draw_generate(o, &g, out);
+  return 0;
+}
+/* simStepGenerate drawing from the oracle's own generator */
+void orc_step_generate(void* h, float noise) {
+  oracle* o = (oracle*)h;
+  if (o->cfg.variant != BIDI_NEO_HIERARCHY) return;
+  float* nz = fzeros((size_t)orc_num_generate_noise(h));
+  draw_generate(o, &o->gen, nz);
+  step_neo_ex(o, 0.0f, NULL, NULL, 0, nz, noise);
+  free(nz);
 }
 
 /* ---- sdr::QPRSDR::simStep after _prsdr.simStep (sdr/QPRSDR.cpp:102-341) */

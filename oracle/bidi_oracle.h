@@ -29,6 +29,10 @@ int orc_peek_noise(void* h, float* u, float* v);
 void orc_step(void* h, float reward, int learn);
 /* simStep with the exploration noise supplied (the generator is not advanced) */
 void orc_step_noise(void* h, float reward, const float* u, const float* v, int learn);
+/* neo::PredictiveHierarchy::simStepGenerate: the N(0,1) draws of the next call, and the call itself */
+int orc_num_generate_noise(void* h);
+int orc_peek_generate(void* h, float* out);
+void orc_step_generate(void* h, float noise);
 void orc_run(void* h, const float* frames, int n_frames, int n_in, const float* rewards, int steps, int learn);
 void orc_run_runner(void* h, const float* frames, int n_frames, int n_in, int steps, int n_fb, const int* src,
                     const int* dst, int learn);

@@ -47,6 +47,9 @@ def _bind(lib, p):
         "get_predictions": (None, [C.c_void_p, _FP, C.c_int]),
         "num_columns": (C.c_int, [C.c_void_p]),
         "num_noise": (C.c_int, [C.c_void_p]),
+        "num_generate_noise": (C.c_int, [C.c_void_p]),
+        "peek_generate": (C.c_int, [C.c_void_p, _FP]),
+        "step_generate": (None, [C.c_void_p, C.c_float]),
         "peek_noise": (C.c_int, [C.c_void_p, _FP, _FP]),
         "step": (None, [C.c_void_p, C.c_float, C.c_int]),
         "run": (None, [C.c_void_p, _FP, C.c_int, C.c_int, _FP, C.c_int, C.c_int]),
@@ -164,6 +167,15 @@ class _Hierarchy:
 
     def step(self, reward=0.0, learn=True):
         self._f("step")(self.h, float(reward), int(bool(learn)))
+
+    def peek_generate(self):
+        """the N(0,1) values the next simStepGenerate will draw (neo::PredictiveHierarchy only)"""
+        out = np.zeros(int(self._f("num_generate_noise")(self.h)), dtype=np.float32)
+        assert out.size and self._f("peek_generate")(self.h, _fptr(out)) == 0
+        return out
+
+    def step_generate(self, noise):
+        self._f("step_generate")(self.h, float(noise))
 
     def run(self, frames, steps, rewards=None, learn=True):
         fr = np.ascontiguousarray(frames, dtype=np.float32).reshape(-1, self.n_in)

@@ -436,6 +436,33 @@ int ref_peek_noise(void* h, float* u, float* v) {
   return 0;
 }
 
+// neo::PredictiveHierarchy::simStepGenerate (neo/PredictiveHierarchy.cpp:247-315): the N(0,1) values its
+// coders will draw (neo/SparseCoder.cpp:179,200: one normal_distribution per activateNoise call, iteration
+// outer, hidden unit inner), from a COPY of the generator; and the call itself.
+int ref_num_generate_noise(void* h) {
+  Ref& r = *static_cast<Ref*>(h);
+  if (r.cfg.variant != BIDI_NEO_HIERARCHY) return 0;
+  int n = 0;
+  for (int l = 0; l < r.cfg.n_layers; l++) n += r.ld[l].iter_settle * r.ld[l].width * r.ld[l].height;
+  return n;
+}
+int ref_peek_generate(void* h, float* out) {
+  Ref& r = *static_cast<Ref*>(h);
+  if (r.cfg.variant != BIDI_NEO_HIERARCHY) return -1;
+  std::mt19937 g = r.gen;
+  size_t k = 0;
+  for (int l = 0; l < r.cfg.n_layers; l++) {
+    std::normal_distribution<float> noiseDist(0.0f, 1.0f);
+    const int n = r.ld[l].iter_settle * r.ld[l].width * r.ld[l].height;
+    for (int j = 0; j < n; j++) out[k++] = noiseDist(g);
+  }
+  return 0;
+}
+void ref_step_generate(void* h, float noise) {
+  Ref& r = *static_cast<Ref*>(h);
+  if (r.cfg.variant == BIDI_NEO_HIERARCHY) r.nh.simStepGenerate(r.gen, noise);
+}
+
 int ref_num_noise(void* h) {
   Ref& r = *static_cast<Ref*>(h);
   return r.cfg.variant == BIDI_QPRSDR ? r.cfg.q_n_actions : ref_num_columns(h) * BIDI_COLUMN_ACTIONS;

@@ -87,6 +87,11 @@ int main() {
       ph.simStep(generator, t < 30);
       report("neoph", t, ph, 63);
     }
+    for (int t = 0; t < 6; t++) {  // noise-driven dreaming on its own predictions (neo/PredictiveHierarchy.h:110)
+      for (int i = 0; i < 63; i++) ph.setInput(i, ph.getPrediction(i));
+      ph.simStepGenerate(generator, 0.2f);
+      report("neoph-generate", t, ph, 63);
+    }
     std::printf("neoph generator %u\n", (unsigned)generator());
   }
   {  // RunnerMain.cpp:139-154,235-251, headless: sine state vector instead of the Box2D runner

@@ -41,3 +41,22 @@ def test_conn_counts_match_reference():
                 assert (a is None) == (b is None), (name, which, layer)
                 if a is not None:
                     assert np.array_equal(a, b), (name, which, layer)
+
+
+@pytest.mark.parametrize("case", [c for c in small_cases() if c[1].variant == 2], ids=lambda c: c[0])
+def test_step_generate_matches_reference(case):
+    """neo::PredictiveHierarchy::simStepGenerate: same N(0,1) draws, same state after every step."""
+    name, cfg, ld, frame, reward = case
+    ref, orc = RefHierarchy(cfg, ld, 1234), OracleHierarchy(cfg, ld, 1234)
+    for t in range(12):
+        x = frame(t)
+        ref.set_inputs(x)
+        orc.set_inputs(x)
+        if t % 3 == 2:
+            assert np.array_equal(ref.peek_generate(), orc.peek_generate())
+            ref.step_generate(0.25)
+            orc.step_generate(0.25)
+        else:
+            ref.step(reward(t))
+            orc.step(reward(t))
+        assert diff_states(ref.state(), orc.state()) == [], "step %d" % t

@@ -148,3 +148,39 @@ def test_snapshot_resume_is_bit_identical(tmp_path):
     other = Engine(*cf.config_c1(cf.KWINNERS))
     with pytest.raises(bidinet_b200.BidiError, match="not a snapshot"):
         other.load_snapshot(path)
+
+
+@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads"])
+@pytest.mark.parametrize("case", [c for c in small_cases() if c[1].variant == cf.NEO_HIERARCHY], ids=lambda c: c[0])
+def test_step_generate_parity(case, path):
+    """neo::PredictiveHierarchy::simStepGenerate (noise-driven coders, no learning) interleaved with ordinary
+    steps: every state array equal after every step, the N(0,1) draws taken from the oracle's generator."""
+    name, cfg, ld, frame, reward = case
+    orc = OracleHierarchy(cfg, ld, 1234)
+    eng = Engine(cfg, ld, n_agents=1)
+    if path == "fused_general":
+        eng.set_option("dense_coder", False)
+    elif path != "default":
+        eng.set_option("force_phase_kernels", True)
+    if path == "per_phase_threads":
+        eng.set_option("tile_kernels", False)
+    eng.load_state(orc.state())
+    generated = 0
+    for t in range(16):
+        x = frame(t)
+        orc.set_inputs(x)
+        eng.set_inputs(x)
+        if t % 3 == 2:
+            z = orc.peek_generate()
+            orc.step_generate(0.3)
+            eng.step_generate(0.3, normals=z)
+            generated += 1
+        else:
+            orc.step(reward(t))
+            eng.step()
+        bad = diff_states(orc.state(), eng.state())
+        assert bad == [], "step %d: %s" % (t, bad[:6])
+        assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0])
+    assert generated == 5
+    eng.step_generate(0.3)  # the engine's own generator: runs, stays finite
+    assert np.isfinite(eng.get_predictions()).all()
