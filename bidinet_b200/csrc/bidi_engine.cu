@@ -546,7 +546,7 @@ void launch_grid(Recorder& R, const char* name, K kernel, long long blocks, size
 // which layers run the 2-D tile kernels, and how much shared memory they stage
 int select_grid_kernels(bidi_engine* h) {
   h->gridk.assign(h->L, bidi_engine::GridSizes{0, 0, 0, 0, 0, 0, 0});
-  if (h->cfg.variant != BIDI_KWINNERS || h->grid_mode == 0) return BIDI_OK;
+  if (h->cfg.variant == BIDI_NEO_AGENT || h->grid_mode == 0) return BIDI_OK;
   size_t most = 0;
   for (int l = 0; l < h->L; l++) {
     const LayerHost& H = h->hl[l];
@@ -558,8 +558,12 @@ int select_grid_kernels(bidi_engine* h) {
     g.pred = bidi::grid_box_floats(H.pred.d, H.pred.cx.data(), H.pred.cy.data());
     g.gather = std::max(bidi::grid_gather_floats(H.ff.d, H.ff.gxlo.data(), H.ff.gxhi.data(), H.ff.gylo.data(), H.ff.gyhi.data()),
                         bidi::grid_gather_floats(H.rec.d, H.rec.gxlo.data(), H.rec.gxhi.data(), H.rec.gylo.data(), H.rec.gyhi.data()));
-    const size_t need = sizeof(float) * (size_t)std::max({g.ff + g.rec, g.lat, g.fb + g.pred, 3 * g.gather});
-    g.on = need <= 160 * 1024 && (h->grid_mode == 2 || (!h->tiled[l] && h->layers[l].hw >= 16)) ? 1 : 0;
+    const size_t need = sizeof(float) * (size_t)std::max({g.ff + g.rec + (h->cfg.variant == BIDI_KWINNERS ? 0 : g.lat), g.lat, g.fb + g.pred, 3 * g.gather});
+    // default: untiled (large-batch) layers at least 16 units wide; k-winners layers at least 24 wide even for one
+    // agent (C4: 0.44 ms against 0.49 ms with the slot-group tile kernels); the iterative sweeps of ONE agent stay on
+    // the tile kernels (C4: 7.4 ms against 9.1 ms: a 507-connection chain per thread is too long for a single agent)
+    const bool wide_kw = h->cfg.variant == BIDI_KWINNERS && h->layers[l].hw >= 24;
+    g.on = need <= 160 * 1024 && (h->grid_mode == 2 || ((!h->tiled[l] || wide_kw) && h->layers[l].hw >= 16)) ? 1 : 0;
     if (g.on) most = std::max(most, need);
     h->gridk[l] = g;
   }
@@ -568,6 +572,7 @@ int select_grid_kernels(bidi_engine* h) {
     CU(cudaFuncSetAttribute(bidi::k_g_kw_inhibit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
     CU(cudaFuncSetAttribute(bidi::k_g_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
     CU(cudaFuncSetAttribute(bidi::k_g_kw_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+    CU(cudaFuncSetAttribute(bidi::k_g_ic_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
   }
   return BIDI_OK;
 }
@@ -588,7 +593,7 @@ void record_step(Recorder& R, bool learn) {
         const long long th = A * bidi::grid_tiles(Y.hw, Y.hh), tv = A * bidi::grid_tiles(Y.vw, Y.vh);
         launch_grid(R, "kw_activate", bidi::k_g_kw_activate, th, G.ff + G.rec, Y, l, G.ff);
         launch_grid(R, "kw_inhibit", bidi::k_g_kw_inhibit, th, G.lat, Y, l, Y.act, Y.state, nxt);
-        launch_grid(R, "reconstruct", bidi::k_g_reconstruct, tv + th, 3 * G.gather, Y, l, Y.state, 1, 0, G.gather);
+        launch_grid(R, "reconstruct", bidi::k_g_reconstruct, tv + th, 3 * G.gather, Y, l, Y.state, 1, 0, G.gather, 0, 0.0f, 0);
       } else if (h->tiled[l]) {
         launch_tile(R, "kw_activate", bidi::k_t_kw_activate, tiles_of(A, Y.nh), tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec)), Y, l);
         launch_tile(R, "kw_inhibit", bidi::k_t_kw_inhibit, tiles_of(A, Y.nh), 0, Y, l, Y.act, Y.state, nxt);
@@ -627,7 +632,7 @@ void record_step(Recorder& R, bool learn) {
       }
     R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
     // :188-193
-    if (h->gridk[0].on && !R.collect) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather);
+    if (h->gridk[0].on && !R.collect) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather, 0, 0.0f, 0);
     else if (h->tiled[0])
       launch_tile(R, "kw_predict_input", bidi::k_t_reconstruct, tiles_of(A, ly[0].nv), tile_bytes(ly[0].ff.max_cand), ly[0], 0, ly[0].p_state, 0,
                   0.0f, 0, 1);
@@ -659,14 +664,19 @@ void record_step(Recorder& R, bool learn) {
     const size_t sm_sweep = tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec) + nslots_of(Y.lat));
     const size_t sm_rec = tile_bytes(std::max(Y.ff.max_cand, Y.rec.max_cand));
     const long long t_sweep = tiles_of(A, Y.nh), t_rec = tiles_of(A, Y.nv) + tiles_of(A, Y.nh);
+    const bool gk = h->gridk[l].on && !R.collect;  // large layer: 2-D tiles with the source boxes in shared memory
+    const auto& G = h->gridk[l];
+    const long long g_th = A * bidi::grid_tiles(Y.hw, Y.hh), g_tv = A * bidi::grid_tiles(Y.vw, Y.vh);
     int sweep_it = 0;
     auto sweep = [&](int first, int acc, float scale) {
-      if (tl) launch_tile(R, "ic_sweep", bidi::k_t_ic_sweep, t_sweep, sm_sweep, Y, l, first, acc, scale, sweep_it);
+      if (gk) launch_grid(R, "ic_sweep", bidi::k_g_ic_sweep, g_th, G.ff + G.rec + G.lat, Y, l, first, acc, scale, sweep_it, G.ff, G.rec);
+      else if (tl) launch_tile(R, "ic_sweep", bidi::k_t_ic_sweep, t_sweep, sm_sweep, Y, l, first, acc, scale, sweep_it);
       else R.launch("ic_sweep", bidi::k_ic_sweep, nh, Y, l, first, acc, scale, sweep_it);
       sweep_it++;
     };
     auto recon = [&](long long drive, int scaled, float mult, int copy_spike) {
-      if (tl) launch_tile(R, "reconstruct", bidi::k_t_reconstruct, t_rec, sm_rec, Y, l, drive, scaled, mult, copy_spike, 0);
+      if (gk) launch_grid(R, "reconstruct", bidi::k_g_reconstruct, g_tv + g_th, 3 * G.gather, Y, l, drive, 1, 0, G.gather, scaled, mult, copy_spike);
+      else if (tl) launch_tile(R, "reconstruct", bidi::k_t_reconstruct, t_rec, sm_rec, Y, l, drive, scaled, mult, copy_spike, 0);
       else R.launch("reconstruct", bidi::k_reconstruct, nvh, Y, l, drive, scaled, mult, copy_spike);
     };
     if (V == BIDI_ITERATIVE) { // sdr/IRSDR.cpp:125-216

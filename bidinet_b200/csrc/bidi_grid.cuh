@@ -61,20 +61,30 @@ __device__ __forceinline__ void stage_box(float* __restrict__ sm, const Box& b, 
 // sum += sm(target) * w[slot][unit] over the whole slot box, list order.  DYN = the
 // window's height when it is one of the usual 2r+1 (the inner loop is then fully unrolled:
 // all DYN weight loads of a window column are in flight together), 0 = any height.
-template <int DYN>
+template <int DYN, int NC>
 __device__ __forceinline__ float box_dot_n(const WinDev& w, const Box& b, const float* __restrict__ s0, const float* __restrict__ wp,
                                            long long U, float sum) {
   const int dyn = DYN ? DYN : w.dyn;
-  for (int sx = 0; sx < w.dxn; sx++) {
-    const float* sp = s0 + sx;
-    if (DYN) {
-      float wv[DYN ? DYN : 1], xv[DYN ? DYN : 1];
+  if (DYN) {
+    // NC window columns at a time: all NC*DYN weight loads are in flight before the first add
+    for (int sx0 = 0; sx0 < w.dxn; sx0 += NC) {
+      float wv[NC][DYN ? DYN : 1];
 #pragma unroll
-      for (int sy = 0; sy < DYN; sy++) { wv[sy] = wp[(long long)sy * U]; xv[sy] = sp[sy * b.w]; }
+      for (int c = 0; c < NC; c++)
 #pragma unroll
-      for (int sy = 0; sy < DYN; sy++) sum += xv[sy] * wv[sy];
-      wp += (long long)DYN * U;
-    } else {
+        for (int sy = 0; sy < DYN; sy++) wv[c][sy] = sx0 + c < w.dxn ? wp[(long long)(c * DYN + sy) * U] : 0.0f;
+#pragma unroll
+      for (int c = 0; c < NC; c++)
+        if (sx0 + c < w.dxn) {
+          const float* sp = s0 + sx0 + c;
+#pragma unroll
+          for (int sy = 0; sy < DYN; sy++) sum += sp[sy * b.w] * wv[c][sy];
+        }
+      wp += (long long)NC * DYN * U;
+    }
+  } else {
+    for (int sx = 0; sx < w.dxn; sx++) {
+      const float* sp = s0 + sx;
 #pragma unroll 4
       for (int sy = 0; sy < dyn; sy++) {
         sum += sp[sy * b.w] * wp[0];
@@ -89,12 +99,12 @@ __device__ __forceinline__ float box_dot(const WinDev& w, const Box& b, const fl
   if (w.r < 0) return sum;
   const float* s0 = sm + (w.absx ? 0 : w.cx[ux] - w.r - b.x0) + (w.absy ? 0 : w.cy[uy] - w.r - b.y0) * b.w;
   switch (w.dyn) {
-    case 5: return box_dot_n<5>(w, b, s0, wp, U, sum);
-    case 7: return box_dot_n<7>(w, b, s0, wp, U, sum);
-    case 9: return box_dot_n<9>(w, b, s0, wp, U, sum);
-    case 13: return box_dot_n<13>(w, b, s0, wp, U, sum);
-    case 17: return box_dot_n<17>(w, b, s0, wp, U, sum);
-    default: return box_dot_n<0>(w, b, s0, wp, U, sum);
+    case 5: return box_dot_n<5, 5>(w, b, s0, wp, U, sum);
+    case 7: return box_dot_n<7, 4>(w, b, s0, wp, U, sum);
+    case 9: return box_dot_n<9, 3>(w, b, s0, wp, U, sum);
+    case 13: return box_dot_n<13, 2>(w, b, s0, wp, U, sum);
+    case 17: return box_dot_n<17, 2>(w, b, s0, wp, U, sum);
+    default: return box_dot_n<0, 1>(w, b, s0, wp, U, sum);
   }
 }
 // largest window box of any tile, in floats (host: shared memory to reserve)
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_inhibit(EngineDev P, 
 // visible cells (feed-forward family), the rest hidden units (recurrent family);
 // to_pred: the visible result is the input-space prediction (sdr/PredictiveRSDR.cpp:188-193).
 __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_reconstruct(EngineDev P, LayerDev L, int l, long long drive_off, int hidden_too, int to_pred,
-                                                                      int cap) {
+                                                                      int cap, int scaled, float mult, int copy_spike) {
   extern __shared__ float sm[];
   const int vt = grid_tiles(L.vw, L.vrow1 - L.vrow0), ht = hidden_too ? grid_tiles(L.hw, L.row1 - L.row0) : 0;
   const int a = blockIdx.x / (vt + ht), tile = blockIdx.x % (vt + ht);
@@ -174,7 +184,10 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_reconstruct(EngineDev P,
   const float* drive = B + drive_off;
   float* out = vis ? (to_pred ? P.pred_out + (long long)a * P.n_in : B + L.vis_recon) : B + L.recon;
   if (w.r < 0) {  // no recurrent family: the reconstruction is 0
-    if (T.ok) out[T.unit] = 0.0f;
+    if (T.ok) {
+      out[T.unit] = 0.0f;
+      if (!vis && copy_spike) B[L.spike_prev + T.unit] = B[L.spike + T.unit];
+    }
     return;
   }
   // the units whose windows can contain a cell of this tile: a box of the unit grid
@@ -221,14 +234,29 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_reconstruct(EngineDev P,
   const int tx = T.ux, ty = T.uy, n = s_cnt[GRID_TY], r = w.r;
   const float* wp = B + w.w_off;
   float sum = 0.0f;
+  // list entries whose window contains this cell, NQ at a time: the weight loads of a batch are all
+  // issued before the batch is added up, in list order (neo/SparseCoder.cpp:242-259: w*state*multiplier)
+  constexpr int NQ = 8;
+  float wv[NQ], dv[NQ];
+  int q = 0;
   for (int k = 0; k < n; k++) {
     const int c = l_ctr[k], dx = tx - (c & 0xffff), dy = ty - (c >> 16);
     if (dx >= -r && dx <= r && dy >= -r && dy <= r && !(w.excl && (dx | dy) == 0)) {
       const int sx = w.absx ? tx : dx + r, sy = w.absy ? ty : dy + r;
-      sum += wp[(long long)(sx * w.dyn + sy) * w.U + l_unit[k]] * l_d[k];
+      wv[q] = wp[(long long)(sx * w.dyn + sy) * w.U + l_unit[k]];
+      dv[q] = l_d[k];
+      if (++q == NQ) {
+#pragma unroll
+        for (int j = 0; j < NQ; j++) sum += scaled ? wv[j] * dv[j] * mult : wv[j] * dv[j];
+        q = 0;
+      }
     }
   }
+#pragma unroll
+  for (int j = 0; j < NQ; j++)
+    if (j < q) sum += scaled ? wv[j] * dv[j] * mult : wv[j] * dv[j];
   out[T.unit] = sum;
+  if (!vis && copy_spike) B[L.spike_prev + T.unit] = B[L.spike + T.unit];  // spikePrev = spike (sdr/IRSDR.cpp:170-171)
 }
 // host: largest candidate box of any tile of targets, in floats
 inline int grid_gather_floats(const WinDev& w, const int* gxlo, const int* gxhi, const int* gylo, const int* gyhi) {
@@ -245,6 +273,44 @@ inline int grid_gather_floats(const WinDev& w, const int* gxlo, const int* gxhi,
     bh = max(bh, hi - lo + 1);
   }
   return max(0, bw) * max(0, bh);
+}
+
+// ---- one leaky-integrate-and-fire sweep of the iterative coders (sdr/IRSDR.cpp:138-168, neo/SparseCoder.cpp:129-158)
+// for large layers: the three source boxes (visible error, hidden error, previous spikes) staged once per tile
+__global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_ic_sweep(EngineDev P, LayerDev L, int l, int first, int acc, float scale, int it,
+                                                                   int ff_floats, int rec_floats) {
+  extern __shared__ float sm[];
+  const GridTile T = grid_tile(blockIdx.x, L.hw, L.row0, L.row1);
+  float* B = blob_of(P, T.a);
+  const float* x = vis_input_of(P, L, l, T.a);
+  const float* vrec = B + L.vis_recon;
+  const float* sprev = B + L.state_prev;
+  const float* hrec = B + L.recon;
+  const float* spk_prev = B + L.spike_prev;
+  const bool has_rec = L.rec.r >= 0;
+  const Box bf = window_box(L.ff, T), br = has_rec ? window_box(L.rec, T) : Box{0, 0, 0, 0}, bl = window_box(L.lat, T);
+  float* sm_rec = sm + ff_floats;
+  float* sm_lat = sm_rec + rec_floats;
+  stage_box(sm, bf, L.ff.tw, L.ff.th, [&](int t) { return x[t] - vrec[t]; });
+  if (has_rec) stage_box(sm_rec, br, L.rec.tw, L.rec.th, [&](int t) { return sprev[t] - hrec[t]; });
+  stage_box(sm_lat, bl, L.lat.tw, L.lat.th, [&](int t) { return spk_prev[t]; });
+  __syncthreads();
+  if (!T.ok) return;
+  const int i = T.unit;
+  float excitation = P.gen_on ? P.gen_normals[(long long)T.a * P.gen_per_agent + L.gen_off + (long long)it * L.nh + i] * *P.gen_scale : 0.0f;
+  excitation = box_dot(L.ff, bf, sm, T.ux, T.uy, B + L.ff.w_off + i, L.nh, excitation);
+  excitation = box_dot(L.rec, br, sm_rec, T.ux, T.uy, B + L.rec.w_off + i, L.nh, excitation);
+  const float inhibition = box_dot(L.lat, bl, sm_lat, T.ux, T.uy, B + L.lat.w_off + i, L.nh, 0.0f);
+  float av = first ? 0.0f : B[L.act + i];
+  float st = first ? 0.0f : B[L.state + i];
+  av = (1.0f - L.leak) * av + excitation - inhibition;
+  float spike;
+  if (av > B[L.thr + i]) { av = 0.0f; spike = 1.0f; } else spike = 0.0f;
+  if (acc == 1) st += scale * spike;
+  else if (acc == 2) st += spike;
+  B[L.act + i] = av;
+  B[L.spike + i] = spike;
+  B[L.state + i] = st;
 }
 
 // ---- prediction nodes of a k-winners layer: sdr/PredictiveRSDR.cpp:122-160 (delta rule

@@ -181,7 +181,7 @@ void strip_phase(bidi_engine* h, int phase, bool learn) {
       else strip_launch(h, bidi::k_kw_inhibit, nh, Y, 0, Y.act, Y.state, -1LL);
       break;
     case 2:
-      if (G.on) grid(bidi::k_g_reconstruct, tv + th, 3 * G.gather, Y, 0, Y.state, 1, 0, G.gather);
+      if (G.on) grid(bidi::k_g_reconstruct, tv + th, 3 * G.gather, Y, 0, Y.state, 1, 0, G.gather, 0, 0.0f, 0);
       else strip_launch(h, bidi::k_reconstruct, nv + nh, Y, 0, Y.state, 0, 0.0f, 0);
       break;
     case 3:
@@ -201,7 +201,7 @@ void strip_phase(bidi_engine* h, int phase, bool learn) {
       }
       const int s0 = span(BIDI_SPAN_STATE, 0), s1 = span(BIDI_SPAN_STATE, 1);
       strip_launch(h, bidi::k_strip_step_end, A * (s1 - s0) * Y.hw, Y, s0, s1, h->ipc_linked ? h->d_epoch : nullptr);
-      if (G.on) grid(bidi::k_g_reconstruct, tv, 3 * G.gather, Y, 0, Y.p_state, 0, 1, G.gather);
+      if (G.on) grid(bidi::k_g_reconstruct, tv, 3 * G.gather, Y, 0, Y.p_state, 0, 1, G.gather, 0, 0.0f, 0);
       else strip_launch(h, bidi::k_kw_predict_input, nv, Y);
       break;
     }

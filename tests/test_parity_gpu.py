@@ -67,9 +67,9 @@ def test_free_running_parity(case, path):
     if path == "per_phase_threads":
         eng.set_option("tile_kernels", False)
         eng.set_option("grid_kernels", 0)
-    if path == "per_phase_grid":  # the 2-D tile kernels for large k-winners layers, forced onto every layer
-        if cfg.variant != cf.KWINNERS:
-            pytest.skip("k-winners only")
+    if path == "per_phase_grid":  # the 2-D tile kernels for large layers, forced onto every layer
+        if cfg.variant == cf.NEO_AGENT:
+            pytest.skip("no grid kernels for the column hierarchy")
         eng.set_option("grid_kernels", 2)
     eng.load_state(orc.state())
     steps = 25
@@ -150,7 +150,7 @@ def test_snapshot_resume_is_bit_identical(tmp_path):
         other.load_snapshot(path)
 
 
-@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads"])
+@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
 @pytest.mark.parametrize("case", [c for c in small_cases() if c[1].variant == cf.NEO_HIERARCHY], ids=lambda c: c[0])
 def test_step_generate_parity(case, path):
     """neo::PredictiveHierarchy::simStepGenerate (noise-driven coders, no learning) interleaved with ordinary
@@ -164,6 +164,9 @@ def test_step_generate_parity(case, path):
         eng.set_option("force_phase_kernels", True)
     if path == "per_phase_threads":
         eng.set_option("tile_kernels", False)
+        eng.set_option("grid_kernels", 0)
+    if path == "per_phase_grid":
+        eng.set_option("grid_kernels", 2)
     eng.load_state(orc.state())
     generated = 0
     for t in range(16):
