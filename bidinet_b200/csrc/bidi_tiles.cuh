@@ -33,31 +33,47 @@ __device__ __forceinline__ TileId tile_id(int n_units, int bid) {
 
 // P[(base + s)*32 + ul] = src(target of slot s) * w[s][unit] for this thread's slots.
 // f(s, t, valid, w_ref) may first update the weight (delta rule) -- the thread owns it.
-template <class Upd, class Src>
+// do_upd: first w += k * usrc(target) for the connections the unit owns (the delta rule; the thread owns the weight).
+// The slots are taken NB at a time: every load of a batch -- weight, source, delta-rule source -- is issued before
+// the first product, so a batch costs one memory round trip (one agent's step is a chain of such round trips;
+// one load at a time made a C4 sweep tile 23 us of pure latency).
+template <class USrc, class Src>
 __device__ __forceinline__ void tile_products(const WinDev& w, const TileId& T, int uw, float* __restrict__ plane, long long U,
-                                              float* __restrict__ Pbuf, int base, Upd&& upd, Src&& src) {
+                                              float* __restrict__ Pbuf, int base, bool do_upd, float k, USrc&& usrc, Src&& src) {
   if (w.r < 0) return;
   const int ux = T.ok ? T.unit % uw : 0, uy = T.ok ? T.unit / uw : 0;
   const SlotBox b = slot_box(w, ux, uy);
   int sx = T.g / w.dyn, sy = T.g - sx * w.dyn;
-#pragma unroll 4
-  for (int s = T.g; s < w.nslots; s += TILE_G) {
-    const int txr = slot_tx(w, b, sx), tyr = slot_ty(w, b, sy);
-    const bool valid = T.ok && sx >= b.sx0 && sx <= b.sx1 && sy >= b.sy0 && sy <= b.sy1 && !(w.excl && txr == b.cx && tyr == b.cy);
-    const int t = min(max(txr, 0), w.tw - 1) + min(max(tyr, 0), w.th - 1) * w.tw;
-    float p = 0.0f;
-    if (T.ok) {
-      float* wp = plane + (long long)s * U + T.unit;
-      float wv = *wp;
-      if (valid && upd(t, wv)) *wp = wv;
-      p = src(t) * wv;  // slots the unit does not own hold 0: the product is +-0
+  constexpr int NB = 8;
+  for (int s0 = T.g; s0 < w.nslots; s0 += TILE_G * NB) {
+    float wv[NB], xv[NB], uv[NB];
+    bool valid[NB];
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+      const int s = s0 + q * TILE_G;
+      const int txr = slot_tx(w, b, sx), tyr = slot_ty(w, b, sy);
+      valid[q] = T.ok && s < w.nslots && sx >= b.sx0 && sx <= b.sx1 && sy >= b.sy0 && sy <= b.sy1 && !(w.excl && txr == b.cx && tyr == b.cy);
+      const int t = min(max(txr, 0), w.tw - 1) + min(max(tyr, 0), w.th - 1) * w.tw;
+      wv[q] = 0.0f; xv[q] = 0.0f; uv[q] = 0.0f;
+      if (T.ok && s < w.nslots) {
+        wv[q] = plane[(long long)s * U + T.unit];
+        xv[q] = src(t);
+        if (do_upd) uv[q] = usrc(t);
+      }
+      sy += TILE_G;
+      while (sy >= w.dyn) { sy -= w.dyn; sx++; }
     }
-    Pbuf[(base + s) * TILE_U + T.ul] = p;
-    sy += TILE_G;
-    while (sy >= w.dyn) { sy -= w.dyn; sx++; }
+#pragma unroll
+    for (int q = 0; q < NB; q++) {
+      const int s = s0 + q * TILE_G;
+      if (s < w.nslots) {
+        if (do_upd && valid[q]) { wv[q] += k * uv[q]; plane[(long long)s * U + T.unit] = wv[q]; }
+        Pbuf[(base + s) * TILE_U + T.ul] = xv[q] * wv[q];  // slots the unit does not own hold 0: the product is +-0
+      }
+    }
   }
 }
-struct NoUpdate { __device__ __forceinline__ bool operator()(int, float&) const { return false; } };
+struct NoSrc { __device__ __forceinline__ float operator()(int) const { return 0.0f; } };
 
 // f(slot, target) for this thread's share of the unit's connections (element-wise rules)
 template <class F>
@@ -88,8 +104,8 @@ __device__ __forceinline__ void t_kw_activate(const EngineDev& P, const LayerDev
   const float* x = vis_input_of(P, L, l, T.a);
   const float* sprev = B + L.state_prev;
   const int nff = L.ff.nslots, nrec = L.rec.r < 0 ? 0 : L.rec.nslots;
-  tile_products(L.ff, T, L.hw, B + L.ff.w_off, L.nh, Pbuf, 0, NoUpdate(), [&](int t) { return x[t]; });
-  tile_products(L.rec, T, L.hw, B + L.rec.w_off, L.nh, Pbuf, nff, NoUpdate(), [&](int t) { return sprev[t]; });
+  tile_products(L.ff, T, L.hw, B + L.ff.w_off, L.nh, Pbuf, 0, false, 0.0f, NoSrc(), [&](int t) { return x[t]; });
+  tile_products(L.rec, T, L.hw, B + L.rec.w_off, L.nh, Pbuf, nff, false, 0.0f, NoSrc(), [&](int t) { return sprev[t]; });
   __syncthreads();
   if (T.g == 0 && T.ok) B[L.act + T.unit] = tile_sum(Pbuf, 0, nff + nrec, T.ul, -B[L.thr + T.unit]);
 }
@@ -135,17 +151,32 @@ __device__ __forceinline__ void t_reconstruct(const EngineDev& P, const LayerDev
     const int x0 = w.gx_lo[tx], x1 = w.gx_hi[tx], y0 = w.gy_lo[ty], y1 = w.gy_hi[ty];
     const int nx = max(0, x1 - x0 + 1), ny = max(0, y1 - y0 + 1);
     ncand = nx * ny;
-    for (int c = g; c < ncand; c += TILE_G) {
-      const int uy = y0 + c / nx, ux = x0 + c % nx;
-      const int cx = w.cx[ux], cy = w.cy[uy], u = ux + uy * w.uw;
-      float p = 0.0f;
-      const float d = drive[u];
-      if (d != 0.0f && !(w.excl && cx == tx && cy == ty)) {
-        const int sx = w.absx ? tx : tx - cx + w.r, sy = w.absy ? ty : ty - cy + w.r;
-        const float wv = wp[(long long)(sx * w.dyn + sy) * w.U + u];
-        p = scaled ? wv * d * mult : wv * d;
+    // candidates NB at a time: first all their drives, then the weights of those that drive, then the products
+    constexpr int NB = 8;
+    for (int c0 = g; c0 < ncand; c0 += TILE_G * NB) {
+      float dv[NB], wv[NB];
+      long long wk[NB];
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int c = c0 + q * TILE_G;
+        dv[q] = 0.0f; wk[q] = -1;
+        if (c < ncand) {
+          const int uy = y0 + c / nx, ux = x0 + c % nx;
+          const int cx = w.cx[ux], cy = w.cy[uy], u = ux + uy * w.uw;
+          if (!(w.excl && cx == tx && cy == ty)) {
+            const int sx = w.absx ? tx : tx - cx + w.r, sy = w.absy ? ty : ty - cy + w.r;
+            dv[q] = drive[u];
+            wk[q] = (long long)(sx * w.dyn + sy) * w.U + u;
+          }
+        }
       }
-      Pbuf[c * TILE_U + ul] = p;
+#pragma unroll
+      for (int q = 0; q < NB; q++) wv[q] = (dv[q] != 0.0f && wk[q] >= 0) ? wp[wk[q]] : 0.0f;
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int c = c0 + q * TILE_G;
+        if (c < ncand) Pbuf[c * TILE_U + ul] = dv[q] != 0.0f ? (scaled ? wv[q] * dv[q] * mult : wv[q] * dv[q]) : 0.0f;
+      }
     }
   }
   __syncthreads();
@@ -193,9 +224,9 @@ __device__ __forceinline__ void t_ic_sweep(const EngineDev& P, const LayerDev& L
   const float* hrec = B + L.recon;
   const float* spk_prev = B + L.spike_prev;
   const int nff = L.ff.nslots, nrec = L.rec.r < 0 ? 0 : L.rec.nslots, nlat = L.lat.nslots;
-  tile_products(L.ff, T, L.hw, B + L.ff.w_off, L.nh, Pbuf, 0, NoUpdate(), [&](int t) { return x[t] - vrec[t]; });
-  tile_products(L.rec, T, L.hw, B + L.rec.w_off, L.nh, Pbuf, nff, NoUpdate(), [&](int t) { return sprev[t] - hrec[t]; });
-  tile_products(L.lat, T, L.hw, B + L.lat.w_off, L.nh, Pbuf, nff + nrec, NoUpdate(), [&](int t) { return spk_prev[t]; });
+  tile_products(L.ff, T, L.hw, B + L.ff.w_off, L.nh, Pbuf, 0, false, 0.0f, NoSrc(), [&](int t) { return x[t] - vrec[t]; });
+  tile_products(L.rec, T, L.hw, B + L.rec.w_off, L.nh, Pbuf, nff, false, 0.0f, NoSrc(), [&](int t) { return sprev[t] - hrec[t]; });
+  tile_products(L.lat, T, L.hw, B + L.lat.w_off, L.nh, Pbuf, nff + nrec, false, 0.0f, NoSrc(), [&](int t) { return spk_prev[t]; });
   __syncthreads();
   if (T.g == 0 && T.ok) {
     const int i = T.unit;
@@ -309,12 +340,10 @@ __device__ __forceinline__ void t_predict(const EngineDev& P, const LayerDev& L,
   const float kfb = L.learn_fb * err, kpr = L.learn_pred * err;
   const int uw = input_layer ? L.fb.uw : L.hw;
   if (nfb)
-    tile_products(L.fb, T, uw, B + L.fb.w_off, L.pn, Pbuf, 0,
-                  [&](int t, float& wv) { if (!learn) return false; wv += kfb * up_prev[t]; return true; },
+    tile_products(L.fb, T, uw, B + L.fb.w_off, L.pn, Pbuf, 0, learn != 0, kfb, [&](int t) { return up_prev[t]; },
                   [&](int t) { return up_state[t]; });
   if (npr)
-    tile_products(L.pred, T, uw, B + L.pred.w_off, L.pn, Pbuf, nfb,
-                  [&](int t, float& wv) { if (!learn) return false; wv += kpr * sprev[t]; return true; },
+    tile_products(L.pred, T, uw, B + L.pred.w_off, L.pn, Pbuf, nfb, learn != 0, kpr, [&](int t) { return sprev[t]; },
                   [&](int t) { return state[t]; });
   __syncthreads();
   if (T.g == 0 && T.ok) {
