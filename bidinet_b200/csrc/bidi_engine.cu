@@ -116,6 +116,9 @@ struct bidi_engine {
   // pinned staging
   float* h_in = nullptr; float* h_pred = nullptr; float* h_rewards = nullptr; float* h_noise = nullptr; float* h_actions = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;                     // second branch of the step graph (coder learning, see record_step)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_learn = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // one graph per value of the learn flag
   cudaGraphExec_t graphs[3] = {nullptr, nullptr, nullptr};   // learn off, learn on, simStepGenerate
@@ -431,9 +434,12 @@ constexpr int kBlock = 128;
 struct Recorder {
   bidi_engine* h;
   int kernels = 0;
+  cudaStream_t st = nullptr;  // where launches go: the engine's stream, or the side branch while it is open
+  cudaStream_t s() const { return st ? st : h->stream; }
   // collect mode: the launches become the program of the cooperative step kernel instead
   std::vector<bidi::CoopOp>* collect = nullptr;
   bool collect_ok = true;
+  bool capturing = false;  // inside a stream capture: the step may fork into a second branch
   size_t collect_smem = 0;
   int collect_blocks = 0;
   struct Pack {
@@ -475,16 +481,16 @@ struct Recorder {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     h->profile_events.push_back({a, b});
-    cudaEventRecordWithFlags(a, h->stream, cudaEventRecordExternal);
+    cudaEventRecordWithFlags(a, s(), cudaEventRecordExternal);
   }
   void after(const char* name) {
-    if (profiled(name)) cudaEventRecordWithFlags(h->profile_events.back().second, h->stream, cudaEventRecordExternal);
+    if (profiled(name)) cudaEventRecordWithFlags(h->profile_events.back().second, s(), cudaEventRecordExternal);
   }
   template <class K, class... Args> void launch(const char* name, K kernel, long long threads, Args... args) {
     if (collect) { add_op((const void*)kernel, grid_for(threads, TILE_U * TILE_G), 0, args...); return; }
     before(name);
     const int block = kBlock;
-    kernel<<<grid_for(threads, block), block, 0, h->stream>>>(h->P, args...);
+    kernel<<<grid_for(threads, block), block, 0, s()>>>(h->P, args...);
     after(name);
     kernels++;
   }
@@ -505,7 +511,7 @@ template <class K, class... Args>
 void launch_tile(Recorder& R, const char* name, K kernel, long long tiles, size_t smem, Args... args) {
   if (R.collect) { R.add_op((const void*)kernel, tiles, smem, args...); return; }
   R.before(name);
-  kernel<<<(unsigned)tiles, TILE_U * TILE_G, smem, R.h->stream>>>(R.h->P, args...);
+  kernel<<<(unsigned)tiles, TILE_U * TILE_G, smem, R.s()>>>(R.h->P, args...);
   R.after(name);
   R.kernels++;
 }
@@ -539,7 +545,7 @@ void launch_grid(Recorder& R, const char* name, K kernel, long long blocks, size
   if (blocks <= 0) return;
   if (R.collect) { R.collect_ok = false; return; }
   R.before(name);
-  kernel<<<(unsigned)blocks, GRID_TX * GRID_TY, sizeof(float) * smem_floats, R.h->stream>>>(R.h->P, args...);
+  kernel<<<(unsigned)blocks, GRID_TX * GRID_TY, sizeof(float) * smem_floats, R.s()>>>(R.h->P, args...);
   R.after(name);
   R.kernels++;
 }
@@ -697,6 +703,25 @@ void record_step(Recorder& R, bool learn) {
       R.launch("ic_finish", bidi::k_ic_finish, nh, Y, l, 1, 1.0f / counter, l < L - 1 ? ly[l + 1].vis_input : -1LL);
     }
   }
+  // Coder learning (sdr/IRSDR.cpp:287-319, neo/SparseCoder.cpp:326-361) reads only what the up pass and the
+  // PREVIOUS step left behind (errors, states, the previous prediction), and nothing before stepEnd reads what it
+  // writes, so in the step graph it is a second branch that runs beside the down pass instead of after it.
+  auto record_learn = [&]() {
+    for (int l = 0; l < L; l++) {
+      if (h->tiled[l]) launch_tile(R, "ic_learn", bidi::k_t_ic_learn, tiles_of(A, ly[l].nh), 0, ly[l], l, (int)(V != BIDI_ITERATIVE));
+      else if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
+      else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
+    }
+  };
+  const bool fork_learn = learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing;
+  if (fork_learn) {
+    cudaEventRecord(h->ev_fork, h->stream);
+    cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+    R.st = h->side;
+    record_learn();
+    R.st = nullptr;
+    cudaEventRecord(h->ev_join, h->side);
+  }
   for (int l = L - 1; l >= 0; l--) {
     const LayerDev& Y = ly[l];
     const LayerDev& Up = ly[l < L - 1 ? l + 1 : l];
@@ -711,12 +736,8 @@ void record_step(Recorder& R, bool learn) {
     launch_tile(R, "predict_input", bidi::k_t_predict, tiles_of(A, ly[L].pn), tile_bytes(nslots_of(ly[L].fb)), ly[L], L, (int)learn, ly[0].p_state,
                 ly[0].p_state_prev);
   else R.launch("predict_input", bidi::k_predict_input, A * h->n_in, ly[L], (int)learn, ly[0].p_state, ly[0].p_state_prev);
-  if (learn)
-    for (int l = 0; l < L; l++) {
-      if (h->tiled[l]) launch_tile(R, "ic_learn", bidi::k_t_ic_learn, tiles_of(A, ly[l].nh), 0, ly[l], l, (int)(V != BIDI_ITERATIVE));
-      else if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
-      else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
-    }
+  if (fork_learn) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+  else if (learn) record_learn();
   R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
   if (h->qnet) {  // sdr/QPRSDR.cpp:102-341, after _prsdr.simStep
     if (R.collect) { R.collect_ok = false; return; }
@@ -735,6 +756,7 @@ int ensure_graph(bidi_engine* h, int mode) {
   const bool learn = mode == 1;
   CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   Recorder R{h};
+  R.capturing = true;
   h->P.gen_on = mode == 2 ? 1 : 0;  // kernel arguments are captured by value
   record_step(R, learn);
   h->P.gen_on = 0;
@@ -849,6 +871,9 @@ void bidi_destroy(bidi_engine* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   strip_release(h);
   coop_release(h);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1077,6 +1102,9 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       return bail(e_ == cudaErrorMemoryAllocation ? BIDI_ENOMEM : BIDI_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
   CU_CREATE(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU_CREATE(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CU_CREATE(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CU_CREATE(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CU_CREATE(cudaEventCreate(&h->ev0));
   CU_CREATE(cudaEventCreate(&h->ev1));
   const size_t A = (size_t)n_agents, nin = (size_t)h->n_in, nn = std::max<size_t>(1, (size_t)h->n_noise);
@@ -1627,6 +1655,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     CU(cudaFuncSetAttribute(bidi::k_columns16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
   }
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
+  else if (std::string(name) == "overlap_learn") h->overlap_learn = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
       size_t smem = 0;
