@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   constexpr int CC = 16;
   constexpr int RB = 4;              // spiking rows per column parked in the scratch at a time
   constexpr int RQ = RH / 4, RP = RH / 2, RT = RH / 32;  // register part: 128-bit chunks, input pairs, 16-pair trips
+  constexpr int RS = RH ? RH + 4 : 0;         // scratch row pitch: +16 bytes, so that rows parked by different lanes do not share banks
   const ColumnsDev& C = L.col;
   const Pair F{P.k_one2, P.k_negzero2, P.k_negone2};
   const int lane = threadIdx.x, c = lane >> 4, i = lane & 15;
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   float* in_s = smem + C.max_rec + c * C.max_s;          // gathered inputs of column c, [S], pad 0
   float* st_s = smem + C.max_rec + 2 * C.max_s + c * CC;  // final cell states of column c
   float* kf_s = st_s + 2 * CC;                            // feed-forward learning factors of column c
-  float* scr = smem + C.max_rec + 2 * C.max_s + 4 * CC + c * (RB * RH);  // parked rows of column c, [RB][RH]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C.max_rec + 2 * C.max_s + 4 * CC + 2 * RB * RH);
+  float* scr = smem + C.max_rec + 2 * C.max_s + 4 * CC + c * (RB * RS);  // parked rows of column c, [RB][RS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C.max_rec + 2 * C.max_s + 4 * CC + 2 * RB * RS);
   float* g_reg = B + C.rec_base + C.rec_off[pair];       // register part: [RQ][32 lanes][4]
   float* g_rec = g_reg + 32 * RH;
 
@@ -166,14 +167,14 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
       unsigned mm = m;
       for (int b0 = 0; b0 < most; b0 += RB) {
         if (sp != 0.0f && rank >= b0 && rank < b0 + RB) {
-          ulonglong2* dst = reinterpret_cast<ulonglong2*>(scr + (rank - b0) * RH);
+          ulonglong2* dst = reinterpret_cast<ulonglong2*>(scr + (rank - b0) * RS);
 #pragma unroll
           for (int q = 0; q < RQ; q++) dst[q] = make_ulonglong2(wr[2 * q], wr[2 * q + 1]);
         }
         __syncwarp();
         for (int b = 0; b < RB && mm; b++, mm &= mm - 1) {
           const int k = __ffs(mm) - 1;
-          const u64* rrow = reinterpret_cast<const u64*>(scr + b * RH) + i;
+          const u64* rrow = reinterpret_cast<const u64*>(scr + b * RS) + i;
 #pragma unroll
           for (int t = 0; t < RT; t++) {
             const u64 pr = F.mul(mult2, rrow[16 * t]);

@@ -52,13 +52,21 @@ struct ColRec {
     return W[(long long)es * ((long long)i * (S - rh) + (j - rh))];
   }
 };
+// One column's block of a pair record: weights (the part not kept in registers), transposed lateral weights, ten
+// per-cell vectors, the reconstruction error, prevValue.  Planar blocks are padded to 16 (mod 32) floats so that the
+// two columns' 16-lane accesses to the same section fall in different halves of the shared-memory banks.
+int column_block_floats(const ColumnsDev& C, int S) {
+  int block = C.cells * (S - (C.planar ? C.rh : 0)) + C.cells * C.cq + 10 * C.cq + S + 4;
+  if (C.planar) block += (16 - block % 32 + 32) % 32;
+  return block;
+}
 ColRec col_rec(const ColumnsDev& C, const ColumnsHost& H, float* blob, int node) {
   ColRec r;
   const int pair = node >> 1, half = node & 1;
   r.S = H.stride[pair]; r.Cq = C.cq; r.nin = H.in_off[node + 1] - H.in_off[node];
   r.rh = C.planar ? C.rh : 0; r.lane0 = half * 16;
   const int sh = r.S - r.rh;
-  const int block = C.cells * sh + C.cells * C.cq + 10 * C.cq + r.S + 4;  // floats of ONE column's shared-memory block
+  const int block = column_block_floats(C, r.S);  // floats of ONE column's shared-memory block
   r.es = C.planar ? 1 : 2;
   // planar: the register part, then column 2p's block, then column 2p+1's; interleaved: element k of a section is ptr[2*k]
   r.Wreg = blob + C.rec_base + H.rec_off[pair];
@@ -1020,10 +1028,11 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       if (h_no_col_regs) C.rh = 0;
       for (int p = 0; p < n_pairs; p++) {
         const int S = H.col.stride[p];
-        const int part = 2 * (C.cells * (S - C.rh) + C.cells * C.cq + 10 * C.cq + S + 4);
+        const int part = 2 * column_block_floats(C, S);
         H.col.rec_off[p + 1] = H.col.rec_off[p] + 32 * C.rh + part;
         C.max_s = std::max(C.max_s, S); C.max_rec = std::max(C.max_rec, part);
       }
+      if (C.planar) C.max_s += (16 - C.max_s % 32 + 32) % 32;  // pitch of the two gathered-input vectors: disjoint bank halves
       C.tot_in = H.col.in_off[C.n];
       const long long nc = (long long)C.n * C.cells;
       C.rec_base = al.take(H.col.rec_off[n_pairs]);
