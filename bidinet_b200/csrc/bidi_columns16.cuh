@@ -283,18 +283,17 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
       wr[2 * q + 1] = F.add2(F.mul(k2, e.y), wr[2 * q + 1]);
     }
   }
-  for (int p0 = RP; p0 < n2; p0 += 16 * NP) {  // the shared-memory part, lanes over input pairs
-    u64 e2[NP];
-#pragma unroll
-    for (int t = 0; t < NP; t++) { const int p = p0 + i + 16 * t; e2[t] = p < n2 ? err2[p] : 0ull; }
-    for (unsigned mm = live; mm; mm &= mm - 1) {
-      const int r = __ffs(mm) - 1;
-      const float kf = kf_s[r];
-      const u64 k2 = pk(kf, kf);
-      u64* row = reinterpret_cast<u64*>(W + r * SH) + (p0 - RP) + i;
-#pragma unroll
-      for (int t = 0; t < NP; t++)
-        if (p0 + i + 16 * t < n2) row[16 * t] = F.add2(F.mul(k2, e2[t]), row[16 * t]);
+  if (st > 0.0f) {  // the shared-memory part of this lane's own row: 128-bit accesses, rows 4 (mod 8) floats apart
+    const float kf = kf_s[i];
+    const u64 k2 = pk(kf, kf);
+    ulonglong2* wrow = reinterpret_cast<ulonglong2*>(W + i * SH);
+#pragma unroll 4
+    for (int j = 0; j < n4; j++) {
+      ulonglong2 wv = wrow[j];
+      const ulonglong2 e = e4[RQ + j];
+      wv.x = F.add2(F.mul(k2, e.x), wv.x);
+      wv.y = F.add2(F.mul(k2, e.y), wv.y);
+      wrow[j] = wv;
     }
   }
   // lateral: lat[i][r] = max(0, lat[i][r] + alpha*(state_i*state_r - sparsity^2)), every (i, r)
