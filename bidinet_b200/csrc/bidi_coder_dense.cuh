@@ -32,7 +32,11 @@ __host__ __device__ inline bool coder_dense_applies(const LayerDev& L) {
   return L.ff.absx && L.ff.absy && (L.rec.r < 0 || (L.rec.absx && L.rec.absy));
 }
 __host__ __device__ inline int coder_dense_threads(const LayerDev& L) {
+#ifdef BIDI_CODER_SWEEP_THREADS
+  const int t = (L.nh + 31) / 32 * 32;  // experiment: only as many warps as the sweep uses
+#else
   const int t = (L.nv + L.nh + 31) / 32 * 32;
+#endif
   return t < 64 ? 64 : (t > 512 ? 512 : t);
 }
 __host__ __device__ inline CoderDenseShape coder_dense_shape(const LayerDev& L) {
