@@ -430,9 +430,12 @@ __global__ void k_predict(EngineDev P, LayerDev L, int l, int learn, long long u
     const float kfb = L.learn_fb * err, kpr = L.learn_pred * err;
     // w += k*src: a zero error or a zero source adds (+-0), which leaves w as it was, so
     // those weights are neither read nor written (binary, sparse states: almost all of them)
-    if (err != 0.0f) {
-      if (!top) for_each_conn(L.fb, ux, uy, [&](int s, int t) { const float v = up_prev[t]; if (v != 0.0f) wfb[(long long)s * U + i] += kfb * v; });
-      for_each_conn(L.pred, ux, uy, [&](int s, int t) { const float v = sprev[t]; if (v != 0.0f) wpr[(long long)s * U + i] += kpr * v; });
+    if (err != 0.0f) {  // slots in batches of 8: the loads of a batch are in flight together (for_each_slot_batched)
+      if (!top)
+        for_each_slot_batched<8, WE>(L.fb, ux, uy, [&](int s, int t) { return WE{wfb[(long long)s * U + i], up_prev[t]}; },
+                                     [&](int s, const WE& v) { if (v.e != 0.0f) wfb[(long long)s * U + i] = v.w + kfb * v.e; });
+      for_each_slot_batched<8, WE>(L.pred, ux, uy, [&](int s, int t) { return WE{wpr[(long long)s * U + i], sprev[t]}; },
+                                   [&](int s, const WE& v) { if (v.e != 0.0f) wpr[(long long)s * U + i] = v.w + kpr * v.e; });
     }
   }
   float activation = 0.0f;
@@ -454,7 +457,8 @@ __global__ void k_predict_input(EngineDev P, LayerDev L, int learn, long long p0
     float err = P.in0[(long long)a * P.n_in + i] - B[L.p_state_prev + i];
     if (P.variant == BIDI_NEO_AGENT) err = B[L.col.a_expl + i * 3 + 1] * err;
     const float k = L.learn_fb * err; // learn_fb of the input layer = _learnInputFeedBack
-    for_each_conn(L.fb, ux, uy, [&](int s, int t) { wfb[(long long)s * U + i] += k * p0_prev[t]; });
+    for_each_slot_batched<8, WE>(L.fb, ux, uy, [&](int s, int t) { return WE{wfb[(long long)s * U + i], p0_prev[t]}; },
+                                 [&](int s, const WE& v) { wfb[(long long)s * U + i] = v.w + k * v.e; });
   }
   float activation = 0.0f;
   activation = dot_conn(L.fb, ux, uy, wfb, U, i, activation, [&](int t) { return p0[t]; });
