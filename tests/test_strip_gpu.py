@@ -156,3 +156,30 @@ def test_multi_process_strips_match_the_whole_layer(transport):
     pred = assemble_rows([p for _, _, _, p in got], [s["OWN_VIS"] for _, s, _, _ in got], cfg.in_width)
     assert np.array_equal(orc.get_predictions(), pred[0])
     probe.close()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_strip_geometries(seed):
+    """Random single-layer shapes (ratios above and below 1, radii 0..5, a missing recurrent family) split into 2..5
+    parts with either kernel family: every assembled state array equals the oracle's whole-layer run."""
+    rng = np.random.RandomState(500 + seed)
+    g = (int(rng.randint(6, 40)), int(rng.randint(6, 40)), int(rng.randint(6, 40)), int(rng.randint(6, 40)), int(rng.randint(0, 6)),
+         int(rng.randint(-1, 5)), int(rng.randint(0, 5)), int(rng.randint(0, 6)), float(rng.choice([0.1, 0.3])))
+    n_parts = int(rng.randint(2, min(5, g[1], g[3]) + 1))
+    cfg, ld = _cfg(g)
+    orc = OracleHierarchy(cfg, ld, 99 + seed)
+    grp = StripGroup(cfg, ld, devices=[0] * n_parts)
+    for e in grp.parts:
+        e.set_option("grid_kernels", 2 if seed % 2 else 0)
+    grp.load_state(orc.state())
+    frames = _frames(g, seed=seed)
+    for t in range(6):
+        x = frames[t % len(frames)]
+        orc.set_inputs(x)
+        orc.step(0.0, t != 2)
+        grp.set_inputs(x)
+        grp.step(t != 2)
+        bad = diff_states(orc.state(), grp.state())
+        assert bad == [], "seed %d (%s, %d parts) step %d: %s" % (seed, g, n_parts, t, bad[:6])
+        assert np.array_equal(orc.get_predictions(), grp.get_predictions()[0])
+    grp.close()
