@@ -282,6 +282,8 @@ def run_c5(args, rank, world, local_rank):
     clk = clocks.stop() if rank == 0 else None
     step_bytes = c5_bytes_per_step(eng)
     halo = eng.strip_halo_floats * 4 if world > 1 else 0
+    # input rows a part uploads per step: the rows its windows reach (all of them when unsplit)
+    h2d_rows = size if world == 1 else (max(eng.spans["VIS_RECON"][1], eng.spans["OWN_VIS"][1]) - min(eng.spans["VIS_RECON"][0], eng.spans["OWN_VIS"][0]))
     dev_bytes = eng.device_bytes
     if world > 1:
         dist.destroy_process_group()
@@ -301,7 +303,7 @@ def run_c5(args, rank, world, local_rank):
                    "halo_bytes_sent_per_gpu_step": halo, "l2": "weights streamed per step: %.0f MB per GPU" % (per_gpu / 1e6),
                    "state_bytes_per_gpu": dev_bytes},
         "e2e": {"value": K / e2e_s, "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,
-                "h2d_bytes_per_step": int(4 * n_units), "d2h_bytes_per_step": int(4 * n_units)},
+                "h2d_bytes_per_step": int(4 * n_units * h2d_rows / size), "d2h_bytes_per_step": int(4 * n_units / world)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "whole step (6 phase kernels + halo exchanges)", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -1481,6 +1481,17 @@ int bidi_set_inputs(bidi_engine* h, const float* in) {
   CU(cudaSetDevice(h->device));
   const size_t bytes = sizeof(float) * (size_t)h->A * h->n_in;
   CU(cudaStreamSynchronize(h->stream)); // the staging buffer may still be in flight
+  if (h->strip_n > 1) {  // one part of a split layer reads only the input rows its windows reach
+    const size_t w = (size_t)h->cfg.in_width;
+    const size_t lo = std::min(h->strip_span[BIDI_SPAN_VIS_RECON][0], h->strip_span[BIDI_SPAN_OWN_VIS][0]) * w;
+    const size_t hi = std::max(h->strip_span[BIDI_SPAN_VIS_RECON][1], h->strip_span[BIDI_SPAN_OWN_VIS][1]) * w;
+    for (int a = 0; a < h->A; a++) {
+      const size_t o = (size_t)a * h->n_in + lo;
+      memcpy(h->h_in + o, in + o, sizeof(float) * (hi - lo));
+      CU(cudaMemcpyAsync(h->d_in0 + o, h->h_in + o, sizeof(float) * (hi - lo), cudaMemcpyHostToDevice, h->stream));
+    }
+    return BIDI_OK;
+  }
   memcpy(h->h_in, in, bytes);
   CU(cudaMemcpyAsync(h->d_in0, h->h_in, bytes, cudaMemcpyHostToDevice, h->stream));
   return BIDI_OK;
@@ -1546,6 +1557,20 @@ int bidi_get_predictions(bidi_engine* h, float* out) {
   if (!h || !out) return fail(h, BIDI_EINVAL, "bidi_get_predictions: null argument");
   CU(cudaSetDevice(h->device));
   const size_t bytes = sizeof(float) * (size_t)h->A * h->n_in;
+  if (h->strip_n > 1) {  // one part of a split layer: only the rows it owns are meaningful, only they are copied
+    const size_t w = (size_t)h->cfg.in_width;
+    const size_t lo = h->strip_span[BIDI_SPAN_OWN_VIS][0] * w, hi = h->strip_span[BIDI_SPAN_OWN_VIS][1] * w;
+    for (int a = 0; a < h->A; a++) {
+      const size_t o = (size_t)a * h->n_in + lo;
+      CU(cudaMemcpyAsync(h->h_pred + o, h->d_pred + o, sizeof(float) * (hi - lo), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    for (int a = 0; a < h->A; a++) {
+      const size_t o = (size_t)a * h->n_in + lo;
+      memcpy(out + o, h->h_pred + o, sizeof(float) * (hi - lo));
+    }
+    return BIDI_OK;
+  }
   CU(cudaMemcpyAsync(h->h_pred, h->d_pred, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   memcpy(out, h->h_pred, bytes);

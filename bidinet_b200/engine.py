@@ -392,8 +392,8 @@ def assemble_rows(arrays, spans, width):
     return out
 
 
-_VISIBLE_PLANES = ("VIS_RECON", "PREDICTION")
-_REPLICATED = ("VIS_INPUT",)
+_VISIBLE_PLANES = ("VIS_RECON", "PREDICTION", "VIS_INPUT")  # a part uploads only the input rows its windows reach
+_REPLICATED = ()
 
 
 def assemble_state(parts, agent=0):

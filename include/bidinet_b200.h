@@ -307,8 +307,10 @@ int bidi_set_option(bidi_engine* h, const char* name, int value);
  *   - one process per GPU, NCCL: bidi_strip_nccl_unique_id on rank 0, ship the 128 bytes
  *     to every rank, bidi_strip_link_nccl; halos go through ncclSend/ncclRecv on the
  *     engine's stream (also inside the step's graph).
- * bidi_get_predictions / bidi_get_array return whole-grid arrays of which only the rows
- * the part owns are meaningful (bidi_strip_plan tells which).
+ * bidi_get_predictions writes ONLY the rows the part owns into the caller's whole-grid array (the
+ * rest is left untouched), bidi_set_inputs reads only the rows its windows reach, and
+ * bidi_get_array returns whole-grid arrays of which only the owned rows are meaningful
+ * (bidi_strip_plan tells which).
  */
 enum bidi_strip_span { /* row intervals [lo,hi) of part p, see bidi_strip_plan */
   BIDI_SPAN_OWN_HID = 0,  /* hidden rows the part owns */
