@@ -3,16 +3,16 @@
 //
 // A single-layer k-winners hierarchy (sdr::PredictiveRSDR, sdr/PredictiveRSDR.cpp:100-194)
 // is cut into horizontal row strips, one engine ("part") per GPU.  The step becomes six
-// compute phases with a halo exchange of unit-state rows after each of the first five:
+// compute phases with four halo exchanges of unit-state rows in between:
 //
 //   phase 0  activate            a = -theta + sum_ff + sum_rec          sdr/RSDR.cpp:123-133
 //     X0     activations, r_lat rows either side
 //   phase 1  k-winner rank       state                                  sdr/RSDR.cpp:135-145
 //     X1     winners, rows the reconstruction / prediction / learning windows reach
 //   phase 2  reconstruct         vis_recon (owned visible rows), recon  sdr/RSDR.cpp:165-194
-//     X2     both reconstructions (learning steps only)
 //   phase 3  predict             delta rule + activation                sdr/PredictiveRSDR.cpp:122-160
-//     X3     prediction activations (r_lat rows), attentions (halo units)
+//     X3     prediction activations (r_lat rows), attentions (halo units), and both reconstructions (made in
+//            phase 2, first read by the learning rule in phase 5)
 //   phase 4  k-winner rank       predicted state                        sdr/PredictiveRSDR.cpp:163-170
 //     X4     predicted winners (rows the input prediction gathers from)
 //   phase 5  learn, stepEnd, input prediction                           sdr/RSDR.cpp:241-266,196-212
@@ -208,7 +208,7 @@ void strip_phase(bidi_engine* h, int phase, bool learn) {
   }
 }
 constexpr int kStripPhases = 6;
-inline bool strip_point_used(int point, bool learn) { return point != 2 || learn; }
+inline bool strip_point_used(int point, bool) { return point != 2; }  // X2's rows (the reconstructions) travel with X3
 
 // ---- the exchange plan: which rows of which plane go to / come from which part
 void strip_build_plan(bidi_engine* h) {
@@ -227,12 +227,12 @@ void strip_build_plan(bidi_engine* h) {
   std::vector<Item> items = {
       {0, Y.act, Y.hw, BIDI_SPAN_ACT, BIDI_SPAN_OWN_HID},
       {1, Y.state, Y.hw, BIDI_SPAN_STATE, BIDI_SPAN_OWN_HID},
-      {2, Y.vis_recon, Y.vw, BIDI_SPAN_VIS_RECON, BIDI_SPAN_OWN_VIS},
+      {3, Y.vis_recon, Y.vw, BIDI_SPAN_VIS_RECON, BIDI_SPAN_OWN_VIS},  // made in phase 2, first read in phase 5: rides with X3
       {3, Y.p_act, Y.hw, BIDI_SPAN_ACT, BIDI_SPAN_OWN_HID},
       {3, Y.p_mod, Y.hw, BIDI_SPAN_EXT_HID, BIDI_SPAN_OWN_HID},
       {4, Y.p_state, Y.hw, BIDI_SPAN_PRED_STATE, BIDI_SPAN_OWN_HID},
   };
-  if (d.r_rec >= 0) items.insert(items.begin() + 3, Item{2, Y.recon, Y.hw, BIDI_SPAN_HID_RECON, BIDI_SPAN_OWN_HID});
+  if (d.r_rec >= 0) items.insert(items.begin() + 3, Item{3, Y.recon, Y.hw, BIDI_SPAN_HID_RECON, BIDI_SPAN_OWN_HID});
   h->strip_send.clear(); h->strip_recv.clear();
   for (const Item& it : items)
     for (int q = 0; q < n; q++) {
