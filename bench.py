@@ -227,21 +227,23 @@ def run_c5(args, rank, world, local_rank):
     eng = Engine(cfg, ld, n_agents=1, device=local_rank)
     if world > 1:
         eng.strip_configure(rank, world)
+    eng.init_random(1234)  # before linking: once linked over peer memory, the neighbours write into this part's state
+    frames = c5_frames(size)
+    T = len(frames)
+    eng.load_frames(frames[:, None, :])
+    if world > 1:
         if args.c5_transport == "nccl":
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
                 uid.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
             dist.broadcast(uid, 0)
             eng.strip_link_nccl(bytes(uid.cpu().numpy().tobytes()))
-        else:  # peer memory: gather every part's CUDA IPC handles
+        else:  # peer memory: gather every part's CUDA IPC handles (the gather is the barrier the linking needs)
             mine = torch.frombuffer(bytearray(eng.strip_ipc_export()), dtype=torch.uint8).cuda()
             allh = [torch.zeros(128, dtype=torch.uint8, device="cuda") for _ in range(world)]
             dist.all_gather(allh, mine)
             eng.strip_link_ipc([bytes(t.cpu().numpy().tobytes()) for t in allh])
-    eng.init_random(1234)
-    frames = c5_frames(size)
-    T = len(frames)
-    eng.load_frames(frames[:, None, :])
+    barrier()
     t = 0
     for _ in range(W):
         eng.step_frame(t)

@@ -1358,6 +1358,7 @@ int bidi_set_array(bidi_engine* h, int agent, int which, int layer, const float*
     CU(cudaStreamSynchronize(h->stream));
     return BIDI_OK;
   }
+  if (h->ipc_linked) return fail(h, BIDI_EINVAL, "bidi_set_array: not after bidi_strip_link_ipc (the neighbours store into this memory): initialise the state before bidi_strip_ipc_export");
   int rc = mirror_load(h, agent);
   if (rc) return rc;
   if (r.kind == ArrayRef::PLANE) memcpy(h->mirror.data() + r.off, src, sizeof(float) * len);
@@ -1392,6 +1393,7 @@ int bidi_get_array(bidi_engine* h, int agent, int which, int layer, float* dst, 
 // standard-library engine and distribution the reference uses.
 int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
   if (!h || first < 0 || count < 0 || first + count > h->A) return fail(h, BIDI_EINVAL, "bidi_init_random: bad agent range");
+  if (h->ipc_linked) return fail(h, BIDI_EINVAL, "bidi_init_random: not after bidi_strip_link_ipc (the neighbours store into this memory): initialise the state before bidi_strip_ipc_export");
   CU(cudaSetDevice(h->device));
   int rc = mirror_release(h);
   if (rc) return rc;

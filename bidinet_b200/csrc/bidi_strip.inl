@@ -480,6 +480,11 @@ int bidi_strip_ipc_export(bidi_engine* h, void* handle128) {
   if (!h || !handle128 || h->strip_n < 2) return fail(h, BIDI_EINVAL, "bidi_strip_ipc_export: configure the part first (bidi_strip_configure, n_parts >= 2)");
   static_assert(2 * sizeof(cudaIpcMemHandle_t) <= 128, "two IPC handles fit the 128-byte record");
   CU(cudaSetDevice(h->device));
+  {  // everything uploaded so far is in place before any neighbour can learn this memory's address
+    int rc = mirror_release(h);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+  }
   if (!h->d_flags) {
     CU(cudaMalloc(&h->d_flags, sizeof(unsigned) * 5 * h->strip_n));
     CU(cudaMemset(h->d_flags, 0, sizeof(unsigned) * 5 * h->strip_n));

@@ -299,7 +299,9 @@ int bidi_set_option(bidi_engine* h, const char* name, int value);
  * bidi_strip_configure must precede bidi_init_random / bidi_set_array.  Two transports:
  *   - same process (one host thread drives all parts, any mix of devices, peer copies
  *     over NVLink): bidi_strip_link_local, then bidi_strip_step_local per step;
- *   - one process per GPU (torchrun), peer memory: every rank calls bidi_strip_ipc_export,
+ *   - one process per GPU (torchrun), peer memory: every rank FIRST initialises its state
+ *     (bidi_init_random / bidi_set_array -- refused once linked, because from then on the
+ *     neighbours store into this memory at their own pace), then calls bidi_strip_ipc_export,
  *     the 128-byte records are gathered to all ranks (any host channel), then
  *     bidi_strip_link_ipc and plain bidi_step / bidi_step_frame.  One small kernel per
  *     exchange point stores the halo rows straight into the neighbours' memory over

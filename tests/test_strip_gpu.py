@@ -88,14 +88,16 @@ def _nccl_worker(rank, world, uid, g, steps, q, pipes=None):
         cfg, ld = _cfg(g)
         e = Engine(cfg, ld, device=rank)
         e.strip_configure(rank, world)
+        orc = OracleHierarchy(cfg, ld, 1234)   # only to produce the identical initial state
+        e.load_state(orc.state())              # before linking: once linked, the neighbours write into this part's memory
         if uid is not None:
             e.strip_link_nccl(uid)
-        else:  # CUDA IPC: every part exports its handles, all parts get all of them
+        else:  # CUDA IPC: every part exports its handles, all parts get all of them (a barrier as well)
             to_parent, from_parent = pipes
             to_parent.put((rank, e.strip_ipc_export()))
             e.strip_link_ipc(from_parent.get(timeout=300))
-        orc = OracleHierarchy(cfg, ld, 1234)   # only to produce the identical initial state
-        e.load_state(orc.state())
+            with pytest.raises(Exception, match="not after bidi_strip_link_ipc"):
+                e.set_array("HID_STATE", 0, np.zeros(g[2] * g[3], np.float32))
         frames = _frames(g)
         for t in range(steps):
             e.set_inputs(frames[t % len(frames)])
