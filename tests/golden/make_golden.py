@@ -4,8 +4,10 @@
 Run in the build container:  python tests/golden/make_golden.py
 For every case of tests/util.small_cases() it records, over STEPS steps from seed
 1234: getPrediction of every input after every step, and a SHA-256 of every state
-array at the end (-0.0 normalised to +0.0).  The reference itself ships no golden
-vectors; these are outputs of the reference run here."""
+array at the end (-0.0 normalised to +0.0).  golden_random.npz holds the same for
+the N_RANDOM randomly drawn geometries of tests/util.random_case (all five variants,
+6 steps each).  The reference itself ships no golden vectors (SURVEY section 4);
+these are outputs of the reference run here."""
 import hashlib
 import os
 import sys
@@ -17,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 
 from oracle.pyoracle import RefHierarchy  # noqa: E402
-from util import small_cases  # noqa: E402
+from util import N_RANDOM, run_random_case, small_cases  # noqa: E402
 
 STEPS = 40
 SEED = 1234
@@ -49,6 +51,14 @@ def main():
         out[name + "/digests"] = np.array(digests)
         print(name, preds.shape, len(keys))
     np.savez_compressed(os.path.join(HERE, "golden.npz"), **out)
+    out = {}
+    for seed in range(N_RANDOM):
+        preds, keys, digests = run_random_case(RefHierarchy, seed)
+        out["r%d/pred" % seed] = preds
+        out["r%d/keys" % seed] = np.array(keys)
+        out["r%d/digests" % seed] = np.array(digests)
+    np.savez_compressed(os.path.join(HERE, "golden_random.npz"), **out)
+    print("random geometries:", N_RANDOM)
 
 
 if __name__ == "__main__":

@@ -9,7 +9,7 @@ import pytest
 from bidinet_b200 import config as cf
 from oracle.pyoracle import OracleHierarchy, c1_frame
 
-from util import small_cases
+from util import N_RANDOM, run_random_case, small_cases
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.npz")
 
@@ -29,6 +29,17 @@ def test_oracle_reproduces_golden(case, golden):
     assert np.array_equal(preds, golden[name + "/pred"])
     assert list(keys) == list(golden[name + "/keys"])
     assert list(digests) == list(golden[name + "/digests"])
+
+
+@pytest.mark.parametrize("seed", range(N_RANDOM))
+def test_oracle_reproduces_random_golden(seed):
+    """tests/util.random_case geometries: the oracle against outputs of the unmodified reference
+    (tests/golden/golden_random.npz), predictions after every step and every state array at the end."""
+    g = np.load(os.path.join(os.path.dirname(GOLDEN), "golden_random.npz"))
+    preds, keys, digests = run_random_case(OracleHierarchy, seed)
+    assert np.array_equal(preds, g["r%d/pred" % seed])
+    assert list(keys) == list(g["r%d/keys" % seed])
+    assert list(digests) == list(g["r%d/digests" % seed])
 
 
 # SURVEY App. D: MSE over the last 100 steps of (getPrediction before the step - input)^2

@@ -6,7 +6,7 @@ import pytest
 
 from oracle.pyoracle import OracleHierarchy, RefHierarchy, have_ref
 
-from util import diff_states, small_cases
+from util import N_RANDOM, RANDOM_STEPS, diff_states, random_case, random_schedule, small_cases
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libbidiref.so not built (needs /root/reference)")
 
@@ -60,3 +60,19 @@ def test_step_generate_matches_reference(case):
             ref.step(reward(t))
             orc.step(reward(t))
         assert diff_states(ref.state(), orc.state()) == [], "step %d" % t
+
+
+@pytest.mark.parametrize("seed", range(N_RANDOM))
+def test_oracle_matches_reference_random_geometries(seed):
+    """The randomly drawn shapes of the GPU parity test (1x1 grids, ratios above and below 1, radius 0 to wider
+    than the grid, 3..16-cell columns, all five variants): state identical after creation and after every step."""
+    cfg, ld, frames = random_case(seed)
+    ref, orc = RefHierarchy(cfg, ld, 4321 + seed), OracleHierarchy(cfg, ld, 4321 + seed)
+    assert diff_states(ref.state(), orc.state()) == []
+    for t in range(RANDOM_STEPS):
+        x = frames[t % len(frames)]
+        ref.set_inputs(x)
+        orc.set_inputs(x)
+        ref.step(*random_schedule(t))
+        orc.step(*random_schedule(t))
+        assert diff_states(ref.state(), orc.state()) == [], "seed %d step %d" % (seed, t)

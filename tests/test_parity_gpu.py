@@ -12,7 +12,7 @@ from bidinet_b200 import Engine
 from bidinet_b200 import config as cf
 from oracle.pyoracle import OracleHierarchy
 
-from util import diff_states, small_cases
+from util import RANDOM_STEPS, diff_states, random_case, random_schedule, small_cases, state_digests
 
 pytestmark = pytest.mark.gpu
 
@@ -189,48 +189,15 @@ def test_step_generate_parity(case, path):
     assert np.isfinite(eng.get_predictions()).all()
 
 
-def _random_case(seed):
-    """A random small hierarchy: grids 1..20 wide, ratios above and below 1, radii from 0 to wider than the grid."""
-    rng = np.random.RandomState(1000 + seed)
-    variant = [cf.KWINNERS, cf.ITERATIVE, cf.NEO_HIERARCHY, cf.NEO_AGENT, cf.QPRSDR][seed % 5]
-    n_layers = int(rng.randint(1, 4))
-    iw, ih = int(rng.randint(1, 21)), int(rng.randint(1, 21))
-    layers = []
-    for l in range(n_layers):
-        d = dict(width=int(rng.randint(1, 21)), height=int(rng.randint(1, 21)), r_ff=int(rng.randint(0, 6)),
-                 r_rec=int(rng.randint(-1, 4)) if variant == cf.KWINNERS else int(rng.randint(0, 4)),
-                 r_lat=int(rng.randint(0, 5)), r_pred=int(rng.randint(0, 5)), r_fb=int(rng.randint(0, 5)))
-        if variant == cf.KWINNERS:
-            d["sparsity"] = float(rng.choice([0.05, 0.2, 0.5]))
-        else:
-            d["iter_settle"] = int(rng.randint(1, 7))
-            if variant == cf.ITERATIVE or variant == cf.QPRSDR:
-                d["iter_measure"] = int(rng.randint(1, 4))
-        if variant == cf.NEO_AGENT:
-            d["col_cells"] = int(rng.choice([16, 16, 7, 3]))
-            d["col_iter"] = int(rng.randint(1, 5))
-        layers.append(d)
-    kw = dict(init=(-0.4, 0.4, 0.01, 0.05, float(rng.choice([0.0, 0.05]))))
-    if variant == cf.QPRSDR:
-        n_in = iw * ih
-        if n_in < 2:
-            iw, n_in = 2, 2 * ih
-        k = int(rng.randint(1, min(8, n_in // 2) + 1))
-        cells = rng.permutation(n_in)[:2 * k]
-        kw.update(actions=[int(c) for c in cells[:k]], anti_actions=[int(c) for c in cells[k:]], q_derive_iterations=int(rng.randint(1, 6)))
-    if variant == cf.NEO_AGENT:
-        kw.update(col_cells=int(rng.choice([16, 5])), col_iter=int(rng.randint(1, 4)))
-    cfg, ld = cf.make_config(variant, iw, ih, layers, r_infb=0 if variant == cf.KWINNERS else int(rng.randint(0, 5)), **kw)
-    frames = (rng.rand(8, iw * ih) < 0.4).astype(np.float32) * rng.rand(8, iw * ih).astype(np.float32)
-    return cfg, ld, frames
-
-
 @pytest.mark.parametrize("seed", range(40))
 def test_random_geometries(seed):
     """Randomly drawn shapes (all five variants; 1x1 grids, up- and down-sampling ratios, windows from radius 0 to
     wider than the grid, 3..16-cell columns): exact parity with the oracle over 6 steps on the default engine path,
-    and for the k-winners variant also on the 2-D grid-tile kernels."""
-    cfg, ld, frames = _random_case(seed)
+    and for the k-winners variant also on the 2-D grid-tile kernels.  The final state is also held against the
+    digests of the unmodified reference's own run (tests/golden/golden_random.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_random.npz"))
+    cfg, ld, frames = random_case(seed)
     paths = ["default"] + (["grid"] if cfg.variant == cf.KWINNERS else [])
     for path in paths:
         orc = OracleHierarchy(cfg, ld, 4321 + seed)
@@ -238,13 +205,17 @@ def test_random_geometries(seed):
         if path == "grid":
             eng.set_option("grid_kernels", 2)
         eng.load_state(orc.state())
-        for t in range(6):
+        for t in range(RANDOM_STEPS):
             x = frames[t % len(frames)]
             orc.set_inputs(x)
             eng.set_inputs(x)
             noise = orc.peek_noise() if orc.num_noise() else None
-            orc.step(0.3 * t - 0.5, t != 3)
-            eng.step(rewards=[0.3 * t - 0.5], noise=noise, learn=t != 3)
+            reward, learn = random_schedule(t)
+            orc.step(reward, learn)
+            eng.step(rewards=[reward], noise=noise, learn=learn)
             bad = diff_states(orc.state(), eng.state())
             assert bad == [], "seed %d path %s step %d: %s" % (seed, path, t, bad[:6])
+        keys, digests = state_digests(eng.state())
+        assert list(keys) == list(g["r%d/keys" % seed])
+        assert list(digests) == list(g["r%d/digests" % seed]), "seed %d path %s: differs from the reference's golden digests" % (seed, path)
         eng.close()

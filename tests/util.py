@@ -73,3 +73,76 @@ def small_cases():
                              init=(-0.3, 0.3, 0.01, 0.05, 0.0), q_derive_iterations=9)
     cases.append(("ragged_qprsdr", cfg, ld, lambda t: frames35[t % 64], lambda t: float(np.cos(0.7 * t))))
     return cases
+
+
+N_RANDOM = 40
+
+
+def random_case(seed):
+    """A random small hierarchy: grids 1..20 wide, ratios above and below 1, radii from 0 to wider than the grid."""
+    rng = np.random.RandomState(1000 + seed)
+    variant = [cf.KWINNERS, cf.ITERATIVE, cf.NEO_HIERARCHY, cf.NEO_AGENT, cf.QPRSDR][seed % 5]
+    n_layers = int(rng.randint(1, 4))
+    iw, ih = int(rng.randint(1, 21)), int(rng.randint(1, 21))
+    layers = []
+    for l in range(n_layers):
+        d = dict(width=int(rng.randint(1, 21)), height=int(rng.randint(1, 21)), r_ff=int(rng.randint(0, 6)),
+                 r_rec=int(rng.randint(-1, 4)) if variant == cf.KWINNERS else int(rng.randint(0, 4)),
+                 r_lat=int(rng.randint(0, 5)), r_pred=int(rng.randint(0, 5)), r_fb=int(rng.randint(0, 5)))
+        if variant == cf.KWINNERS:
+            d["sparsity"] = float(rng.choice([0.05, 0.2, 0.5]))
+        else:
+            d["iter_settle"] = int(rng.randint(1, 7))
+            if variant == cf.ITERATIVE or variant == cf.QPRSDR:
+                d["iter_measure"] = int(rng.randint(1, 4))
+        if variant == cf.NEO_AGENT:
+            d["col_cells"] = int(rng.choice([16, 16, 7, 3]))
+            d["col_iter"] = int(rng.randint(1, 5))
+        layers.append(d)
+    kw = dict(init=(-0.4, 0.4, 0.01, 0.05, float(rng.choice([0.0, 0.05]))))
+    if variant == cf.QPRSDR:
+        n_in = iw * ih
+        if n_in < 2:
+            iw, n_in = 2, 2 * ih
+        k = int(rng.randint(1, min(8, n_in // 2) + 1))
+        cells = rng.permutation(n_in)[:2 * k]
+        kw.update(actions=[int(c) for c in cells[:k]], anti_actions=[int(c) for c in cells[k:]], q_derive_iterations=int(rng.randint(1, 6)))
+    if variant == cf.NEO_AGENT:
+        kw.update(col_cells=int(rng.choice([16, 5])), col_iter=int(rng.randint(1, 4)))
+    cfg, ld = cf.make_config(variant, iw, ih, layers, r_infb=0 if variant == cf.KWINNERS else int(rng.randint(0, 5)), **kw)
+    frames = (rng.rand(8, iw * ih) < 0.4).astype(np.float32) * rng.rand(8, iw * ih).astype(np.float32)
+    return cfg, ld, frames
+
+
+RANDOM_STEPS = 6
+
+
+def random_schedule(t):
+    """(reward, learn) of step t in the random-geometry runs: one no-learn step in the middle."""
+    return 0.3 * t - 0.5, t != 3
+
+
+def state_digests(st):
+    """sorted "ARRAY:layer" keys and the SHA-256 of every state array (-0.0 normalised to +0.0)."""
+    import hashlib
+    keys = sorted("%s:%d" % k for k in st)
+    out = []
+    for k in keys:
+        name, layer = k.split(":")
+        a = np.asarray(st[(name, int(layer))], dtype="<f4") + np.float32(0.0)
+        out.append(hashlib.sha256(a.tobytes()).hexdigest())
+    return keys, out
+
+
+def run_random_case(cls, seed):
+    """Steps hierarchy class `cls` (reference, oracle) through random case `seed` on its own noise draws:
+    predictions after every step, digests of every state array at the end."""
+    cfg, ld, frames = random_case(seed)
+    h = cls(cfg, ld, 4321 + seed)
+    preds = []
+    for t in range(RANDOM_STEPS):
+        h.set_inputs(frames[t % len(frames)])
+        h.step(*random_schedule(t))
+        preds.append(h.get_predictions())
+    keys, digests = state_digests(h.state())
+    return np.stack(preds), keys, digests
