@@ -5,23 +5,33 @@
 // through zero weights), and the up pass is a dense mat-vec per iteration whose order of
 // summation is the slot order.  So, unlike the general kernel:
 //   * the slot planes w[slot][unit] are transposed into rows w[unit][slot] in shared
-//     memory (row pitch = 4 mod 8: conflict-free 128-bit loads, one row per lane) and the
-//     error vectors are kept in slot order, so the sweep is the column kernel's loop:
-//     two 128-bit loads, two packed products, four chained adds per four connections;
+//     memory, feed-forward and recurrent part in ONE row per unit (row pitch = 4 mod 8:
+//     conflict-free 128-bit loads, one row per lane) and the error vectors are kept in
+//     slot order, so the sweep is the column kernel's loop: two 128-bit loads, two packed
+//     products, four chained adds per four connections, software-pipelined four quads deep;
 //   * the gather-form reconstruction needs no window test (a unit outside the window has
-//     weight 0 and adds +-0): each warp compacts the units with a non-zero drive into a
-//     private (unit, drive) list, ascending unit index = the reference's scatter order,
-//     and thread s sums w[unit][s]*drive over the list.
+//     weight 0 and adds +-0): each reconstructing warp compacts the units with a non-zero
+//     drive into a private list of 16-byte entries (row offset, unit, drive twice), ascending
+//     unit index = the reference's scatter order, and a lane owns a PAIR (or four) of
+//     adjacent slots: per listed unit one broadcast 128-bit load, one 64-bit weight load,
+//     one or two packed products and two independent adds.  A CTA has as many warps as the
+//     larger of the two phases needs (RunnerMain layers: two and one), so none idles at the
+//     barriers;
+//   * the lateral lists carry the precomputed slot-plane offset of every spiking unit.
 // Same arithmetic, same order, same bits as bidi_coder.cuh / bidi_kernels.cuh.
 #pragma once
 #include "bidi_coder.cuh"
 
 namespace bidi {
 
+// Shared-memory row of unit u: [ feed-forward slots, padded to 4 | recurrent slots, padded to 4 | pad ],
+// pitch = 4 (mod 8) floats.  The error, input and reconstruction vectors have the same layout.
 struct CoderDenseShape {
-  int Sf, Sr;        // row pitch of the feed-forward / recurrent weight rows (floats)
-  int warps;
-  long long floats;  // dynamic shared memory, in floats
+  int nf, nr, pitch;  // floats of the feed-forward / recurrent part of a row; row pitch
+  int sweep_warps, recon_warps, warps;
+  int quad;           // the reconstruction gives a lane four adjacent slots instead of two
+  int tasks;          // slot pairs (or quads) the reconstruction covers
+  long long floats;   // dynamic shared memory, in floats
 };
 __host__ __device__ inline int dense_pitch(int n) {
   int s = (n + 3) / 4 * 4;
@@ -31,121 +41,207 @@ __host__ __device__ inline int dense_pitch(int n) {
 __host__ __device__ inline bool coder_dense_applies(const LayerDev& L) {
   return L.ff.absx && L.ff.absy && (L.rec.r < 0 || (L.rec.absx && L.rec.absy));
 }
-__host__ __device__ inline int coder_dense_threads(const LayerDev& L) {
-#ifdef BIDI_CODER_SWEEP_THREADS
-  const int t = (L.nh + 31) / 32 * 32;  // experiment: only as many warps as the sweep uses
-#else
-  const int t = (L.nv + L.nh + 31) / 32 * 32;
-#endif
-  return t < 64 ? 64 : (t > 512 ? 512 : t);
-}
 __host__ __device__ inline CoderDenseShape coder_dense_shape(const LayerDev& L) {
   CoderDenseShape s;
-  const bool has_rec = L.rec.r >= 0;
-  s.Sf = dense_pitch(L.nv); s.Sr = has_rec ? dense_pitch(L.nh) : 0;
-  s.warps = coder_dense_threads(L) / 32;
-  s.floats = (long long)L.nh * (s.Sf + s.Sr)     // weight rows
-             + s.Sf + s.Sr                        // errors, slot order
-             + 2LL * L.nv + 2LL * L.nh            // x, vrec, statePrev, hrec: slot order
-             + 4LL * L.nh                         // act, state, spike, thr: unit order
-             + 3LL * s.warps * L.nh + s.warps     // per warp: lateral list, drive list (unit, value), counts
+  s.nf = (L.nv + 3) & ~3; s.nr = L.rec.r >= 0 ? (L.nh + 3) & ~3 : 0;
+  s.pitch = dense_pitch(s.nf + s.nr);
+  s.sweep_warps = (L.nh + 31) / 32;                 // one lane per unit
+  const int pairs = (s.nf + s.nr) / 2;
+  s.quad = (pairs + 31) / 32 > s.sweep_warps;       // pairs while they need no more warps than the sweep
+  s.tasks = s.quad ? pairs / 2 : pairs;
+  s.recon_warps = (s.tasks + 31) / 32;
+  if (s.recon_warps > 16) s.recon_warps = 16;
+  s.warps = s.sweep_warps > s.recon_warps ? s.sweep_warps : s.recon_warps;
+  s.floats = (long long)L.nh * s.pitch              // weight rows
+             + 3LL * s.pitch                        // errors, inputs (x | statePrev), reconstructions
+             + 4LL * s.recon_warps * L.nh           // per reconstructing warp: drive list, 16-byte entries
+             + 4LL * L.nh                           // act, state, spike, thr: unit order
+             + 2LL * L.nh                           // lateral-order table: (coordinates, slot plane offset)
+             + 2LL * s.sweep_warps * L.nh           // per sweeping warp: lateral list, same entries
              + 8;
   return s;
 }
+__host__ __device__ inline int coder_dense_threads(const LayerDev& L) { return 32 * coder_dense_shape(L).warps; }
 
-// the units with src != 0, ascending unit index, into this warp's private list
-__device__ __forceinline__ int compact_drive(const float* __restrict__ src, int nh, int lane, int* lu, float* ld) {
+// the units with src != 0, ascending unit index, into this warp's private list:
+// entry = (row offset, unit, drive, drive)
+__device__ __forceinline__ int compact_drive(const float* __restrict__ src, int nh, int lane, int pitch, int4* ent) {
   int base = 0;
   for (int p0 = 0; p0 < nh; p0 += 32) {
     const int p = p0 + lane;
     const float d = p < nh ? src[p] : 0.0f;
     const unsigned m = __ballot_sync(0xffffffffu, d != 0.0f);
-    if (d != 0.0f) { const int k = base + __popc(m & ((1u << lane) - 1u)); lu[k] = p; ld[k] = d; }
+    if (d != 0.0f) ent[base + __popc(m & ((1u << lane) - 1u))] = make_int4(p * pitch, p, __float_as_int(d), __float_as_int(d));
     base += __popc(m);
   }
   __syncwarp();
   return base;
 }
 
+// acc + sum of w[j]*e[j] over n4 quads, added strictly in order; the 128-bit loads of the next four
+// quads are issued before the sixteen chained adds of the current four
+__device__ __forceinline__ float dot_row_seq(const Pair& F, const ulonglong2* __restrict__ w4, const ulonglong2* __restrict__ e4, int n4, float acc) {
+  ulonglong2 wa[4], ea[4], wb[4], eb[4];
+  const int nb = n4 >> 2;
+  auto load = [&](ulonglong2* w, ulonglong2* e, int j) {
+#pragma unroll
+    for (int t = 0; t < 4; t++) { w[t] = w4[j + t]; e[t] = e4[j + t]; }
+  };
+  auto eat = [&](const ulonglong2* w, const ulonglong2* e) {
+    u64 pr[8];
+#pragma unroll
+    for (int t = 0; t < 4; t++) { pr[2 * t] = F.mul(e[t].x, w[t].x); pr[2 * t + 1] = F.mul(e[t].y, w[t].y); }
+#pragma unroll
+    for (int t = 0; t < 8; t++) { acc += lo32(pr[t]); acc += hi32(pr[t]); }
+  };
+  if (nb > 0) load(wa, ea, 0);
+  int b = 0;
+  for (; b + 2 <= nb; b += 2) {
+    load(wb, eb, 4 * (b + 1));
+    eat(wa, ea);
+    if (b + 2 < nb) load(wa, ea, 4 * (b + 2));
+    eat(wb, eb);
+  }
+  if (b < nb) eat(wa, ea);
+  for (int j = nb * 4; j < n4; j++) {
+    const ulonglong2 w = w4[j], e = e4[j];
+    const u64 p01 = F.mul(e.x, w.x), p23 = F.mul(e.y, w.y);
+    acc += lo32(p01); acc += hi32(p01); acc += lo32(p23); acc += hi32(p23);
+  }
+  return acc;
+}
+
 template <int NEO>
 __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, int l, long long next_vis_input) {
   extern __shared__ __align__(16) float sm[];
-  const int a = blockIdx.x, tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Pair F{P.k_one2, P.k_negzero2, P.k_negone2};
   float* B = blob_of(P, a);
   const int nv = L.nv, nh = L.nh, hw = L.hw, hh = L.hh, vw = L.vw, vh = L.vh;
   const CoderDenseShape S = coder_dense_shape(L);
+  const int W = S.warps, T = 32 * W, pitch = S.pitch;
   const bool has_rec = L.rec.r >= 0;
-  float* wff = sm;                       // [nh][Sf]
-  float* wrec = wff + (size_t)nh * S.Sf; // [nh][Sr]
-  float* ef = wrec + (size_t)nh * S.Sr;  // [Sf] visible error, slot order, pad 0
-  float* er = ef + S.Sf;                 // [Sr]
-  float* x = er + S.Sr;                  // slot order
-  float* vrec = x + nv;
-  float* sprev = vrec + nv;              // statePrev, slot order
-  float* hrec = sprev + nh;
-  float* act = hrec + nh;                // unit order from here
+  float* w = sm;                              // [nh][pitch]
+  float* err = w + (size_t)nh * pitch;        // [pitch] errors, slot order, pads 0
+  float* xin = err + pitch;                   // [pitch] x | statePrev
+  float* rec = xin + pitch;                   // [pitch] visible | hidden reconstruction
+  int4* ent = reinterpret_cast<int4*>(rec + pitch) + (warp < S.recon_warps ? warp : 0) * nh;  // this warp's drive list
+  float* act = rec + pitch + 4 * S.recon_warps * nh;  // unit order from here
   float* state = act + nh;
   float* spike = state + nh;
   float* thr = spike + nh;
-  int* lat_list = reinterpret_cast<int*>(thr + nh) + warp * nh;      // this warp's spiking units, lateral-list order
-  int* lu = reinterpret_cast<int*>(thr + nh) + S.warps * nh + warp * nh;
-  float* ld = thr + nh + 2 * S.warps * nh + warp * nh;
+  int2* lat_tab = reinterpret_cast<int2*>(thr + nh);  // [nh], lateral-list order: (x | y << 16, slot plane offset)
+  int2* lat_list = lat_tab + nh + (warp < S.sweep_warps ? warp : 0) * nh;  // this warp's spiking units, same entries
 
-  // ---- stage: slot planes -> rows, unit state
+  // ---- stage: slot planes -> rows.  A task is four slots of 32 units: four coalesced loads per lane, one
+  //      128-bit store (rows are 4 (mod 8) floats apart: a quarter warp's stores fall in distinct banks);
+  //      the loads of four tasks are in flight at a time
   {
-    const float* gff = B + L.ff.w_off;
-    for (int k = tid; k < nv * nh; k += T) { const int s = k / nh, u = k - s * nh; wff[u * S.Sf + s] = gff[k]; }
-    for (int k = tid; k < nh * (S.Sf - nv); k += T) { const int u = k / (S.Sf - nv), s = nv + k - u * (S.Sf - nv); wff[u * S.Sf + s] = 0.0f; }
-    if (has_rec) {
-      const float* grec = B + L.rec.w_off;
-      for (int k = tid; k < nh * nh; k += T) { const int s = k / nh, u = k - s * nh; wrec[u * S.Sr + s] = grec[k]; }
-      for (int k = tid; k < nh * (S.Sr - nh); k += T) { const int u = k / (S.Sr - nh), s = nh + k - u * (S.Sr - nh); wrec[u * S.Sr + s] = 0.0f; }
-    }
+    const int ub = (nh + 31) >> 5;
+    auto stage_rows = [&](float* dst, const float* __restrict__ src, int n_slots, int nq) {
+      constexpr int NT = 4;
+      int q = 0, b = warp;
+      while (b >= ub) { b -= ub; q++; }
+      while (q < nq) {
+        float v[NT][4];
+        int qq[NT], uu[NT];
+#pragma unroll
+        for (int h = 0; h < NT; h++) {
+          qq[h] = q; uu[h] = b * 32 + lane;
+          const bool ok = q < nq && uu[h] < nh;
+          const float* g = src + (long long)(4 * q) * nh + uu[h];
+#pragma unroll
+          for (int e = 0; e < 4; e++) v[h][e] = (ok && 4 * q + e < n_slots) ? g[(long long)e * nh] : 0.0f;
+          b += W;
+          while (b >= ub) { b -= ub; q++; }
+        }
+#pragma unroll
+        for (int h = 0; h < NT; h++)
+          if (qq[h] < nq && uu[h] < nh)
+            *reinterpret_cast<float4*>(dst + (size_t)uu[h] * pitch + 4 * qq[h]) = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
+      }
+    };
+    stage_rows(w, B + L.ff.w_off, nv, S.nf >> 2);
+    if (has_rec) stage_rows(w + S.nf, B + L.rec.w_off, nh, S.nr >> 2);
+    for (int u = tid; u < nh; u += T)
+      for (int s = S.nf + S.nr; s < pitch; s += 4) *reinterpret_cast<float4*>(w + (size_t)u * pitch + s) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const float* gx = vis_input_of(P, L, l, a);
-    for (int s = tid; s < S.Sf; s += T) {
-      float e = 0.0f;
+    for (int s = tid; s < pitch; s += T) {
+      float xv = 0.0f, rv = 0.0f;
       if (s < nv) {
         const int t = s / vh + (s % vh) * vw;  // slot (tx, ty) = tx*vh + ty <-> cell tx + ty*vw
-        x[s] = gx[t]; vrec[s] = B[L.vis_recon + t];
-        e = x[s] - vrec[s];
+        xv = gx[t]; rv = B[L.vis_recon + t];
+      } else if (s >= S.nf && s - S.nf < nh && has_rec) {
+        const int k = s - S.nf, u = k / hh + (k % hh) * hw;
+        xv = B[L.state_prev + u]; rv = B[L.recon + u];
       }
-      ef[s] = e;
-    }
-    for (int s = tid; s < S.Sr; s += T) {
-      float e = 0.0f;
-      if (s < nh) {
-        const int u = s / hh + (s % hh) * hw;
-        sprev[s] = B[L.state_prev + u]; hrec[s] = B[L.recon + u];
-        e = sprev[s] - hrec[s];
-      }
-      er[s] = e;
+      xin[s] = xv; rec[s] = rv; err[s] = xv - rv;
     }
     for (int k = tid; k < nh; k += T) {
       thr[k] = B[L.thr + k];
       spike[k] = B[L.spike_prev + k];  // spikePrev persists across steps (sdr/IRSDR.cpp:131-135 resets only act, state)
       act[k] = 0.0f; state[k] = 0.0f;
+      const int tx = k / hh, ty = k - tx * hh;  // position k of the lateral lists' order (x-major: dx outer, dy inner)
+      lat_tab[k] = make_int2(tx | (ty << 16), (tx * L.lat.dyn + ty) * nh);
     }
   }
   __syncthreads();
-  // spikePrev in the lateral lists' order (x-major: dx outer, dy inner), one private copy per
-  // sweep warp; rebuilt after every sweep, once all units' new spikes are in shared memory
-  const int sweep_warps = (nh + 31) >> 5;
+  // spikePrev in the lateral lists' order, one private copy per sweep warp; rebuilt after every
+  // sweep, once all units' new spikes are in shared memory
   int n_spk = 0;
   auto build_lat_list = [&]() {
     n_spk = 0;
     for (int p0 = 0; p0 < nh; p0 += 32) {
       const int p = p0 + lane;
-      int cc = 0;
+      int2 t = make_int2(0, 0);
       bool f = false;
-      if (p < nh) { const int ux = p / hh, uy = p - ux * hh; cc = ux | (uy << 16); f = spike[ux + uy * hw] != 0.0f; }
+      if (p < nh) { t = lat_tab[p]; f = spike[(t.x & 0xffff) + (t.x >> 16) * hw] != 0.0f; }
       const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (f) lat_list[n_spk + __popc(m & ((1u << lane) - 1u))] = cc;
+      if (f) lat_list[n_spk + __popc(m & ((1u << lane) - 1u))] = t;
       n_spk += __popc(m);
     }
     __syncwarp();
   };
-  if (warp < sweep_warps) build_lat_list();
+  // reconstruction of both sides from the units with a non-zero drive, ascending unit index
+  // (sdr/IRSDR.cpp:218-235, neo/SparseCoder.cpp:164-168): a lane owns adjacent slots of the row layout
+  auto reconstruct = [&](const float* drive, bool scaled, float mult) {
+    if (warp >= S.recon_warps) return;
+    const int n = compact_drive(drive, nh, lane, pitch, ent);
+    const u64 mult2 = pk(mult, mult);
+    if (S.quad) {
+      for (int j = tid; j < S.tasks; j += 32 * S.recon_warps) {
+        const float* col = w + 4 * j;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+        for (int k = 0; k < n; k++) {
+          const int4 e = ent[k];
+          const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(col + e.x);
+          const u64 dd = pk(__int_as_float(e.z), __int_as_float(e.w));
+          u64 p01 = F.mul(wv.x, dd), p23 = F.mul(wv.y, dd);
+          if (scaled) { p01 = F.mul(p01, mult2); p23 = F.mul(p23, mult2); }
+          s0 += lo32(p01); s1 += hi32(p01); s2 += lo32(p23); s3 += hi32(p23);
+        }
+        const ulonglong2 sum = make_ulonglong2(pk(s0, s1), pk(s2, s3));
+        reinterpret_cast<ulonglong2*>(rec)[j] = sum;
+        const ulonglong2 xv = reinterpret_cast<const ulonglong2*>(xin)[j];
+        reinterpret_cast<ulonglong2*>(err)[j] = make_ulonglong2(F.sub2(xv.x, sum.x), F.sub2(xv.y, sum.y));
+      }
+    } else {
+      for (int j = tid; j < S.tasks; j += 32 * S.recon_warps) {
+        const float* col = w + 2 * j;
+        float s0 = 0.0f, s1 = 0.0f;
+        for (int k = 0; k < n; k++) {
+          const int4 e = ent[k];
+          u64 pr = F.mul(*reinterpret_cast<const u64*>(col + e.x), pk(__int_as_float(e.z), __int_as_float(e.w)));
+          if (scaled) pr = F.mul(pr, mult2);
+          s0 += lo32(pr); s1 += hi32(pr);
+        }
+        const u64 sum = pk(s0, s1);
+        reinterpret_cast<u64*>(rec)[j] = sum;
+        reinterpret_cast<u64*>(err)[j] = F.sub2(reinterpret_cast<const u64*>(xin)[j], sum);
+      }
+    }
+  };
+  if (warp < S.sweep_warps) build_lat_list();
   const float* wlat = B + L.lat.w_off;
   const bool gen = NEO && P.gen_on;
   const float* gen_nz = gen ? P.gen_normals + (long long)a * P.gen_per_agent + L.gen_off : nullptr;
@@ -153,125 +249,74 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
   const int total = NEO ? L.iter_settle : L.iter_settle + L.iter_measure;
   const float measure_inv = NEO ? 0.0f : 1.0f / (float)L.iter_measure;
   float counter = 0.0f, mult = 1.0f;
-  const int nf4 = S.Sf >> 2, nr4 = S.Sr >> 2;
-  const ulonglong2* ef4 = reinterpret_cast<const ulonglong2*>(ef);
-  const ulonglong2* er4 = reinterpret_cast<const ulonglong2*>(er);
+  // this lane's unit in the sweeps: window test and slot plane of a lateral-list entry (cc, base) are
+  //   |tx - ux| <= r  <=>  unsigned(tx + r - ux) <= 2r ;  wlat[base + lat_off]
+  const int i = tid;
+  const int r = L.lat.r, ux = i % hw, uy = i / hw, own = ux | (uy << 16), tcx = r - ux, tcy = r - uy;
+  const unsigned r2 = 2u * (unsigned)r;
+  const bool lat_on = r >= 0;
+  const int lat_off = ((L.lat.absx ? 0 : tcx) * L.lat.dyn + (L.lat.absy ? 0 : tcy)) * nh + i;
+  auto lat_weight = [&](int2 t) -> float {
+    const bool in = lat_on && (unsigned)((t.x & 0xffff) + tcx) <= r2 && (unsigned)((t.x >> 16) + tcy) <= r2 && t.x != own;
+    return in ? wlat[t.y + lat_off] : 0.0f;
+  };
 
   for (int it = 0; it < total; it++) {
     // ---- leaky integrate-and-fire sweep (sdr/IRSDR.cpp:144-168, neo/SparseCoder.cpp:129-158)
-    if (warp < sweep_warps) {
-      const int i = tid;
+    if (warp < S.sweep_warps && i < nh) {
       const bool measuring = !NEO && it >= L.iter_settle;
-      float sp = 0.0f, av = 0.0f, stv = 0.0f;
-      if (i < nh) {
-        // the lateral weights of the first few spiking neighbours are fetched from HBM/L2 now,
-        // so that their latency hides behind the excitation sums (an absent entry adds +0)
-        constexpr int LATQ = 8;
-        const int r = L.lat.r, ux = i % hw, uy = i / hw;
-        float lw[LATQ];
+      // the lateral weights of the first few spiking neighbours are fetched from HBM/L2 now,
+      // so that their latency hides behind the excitation sums (an absent entry adds +0)
+      constexpr int LATQ = 8;
+      float lw[LATQ];
 #pragma unroll
-        for (int e = 0; e < LATQ; e++) {
-          lw[e] = 0.0f;
-          if (e < n_spk) {
-            const int cc = lat_list[e], tx = cc & 0xffff, ty = cc >> 16, dx = tx - ux, dy = ty - uy;
-            if (dx >= -r && dx <= r && dy >= -r && dy <= r && (dx | dy) != 0) {
-              const int sx = L.lat.absx ? tx : dx + r, sy = L.lat.absy ? ty : dy + r;
-              lw[e] = wlat[(long long)(sx * L.lat.dyn + sy) * nh + i];
-            }
-          }
-        }
-        // simStepGenerate: the excitation starts from noiseDist(generator) * noise (neo/SparseCoder.cpp:200)
-        float excitation = gen ? gen_nz[(long long)it * nh + i] * gen_scale : 0.0f;
-        const ulonglong2* w4 = reinterpret_cast<const ulonglong2*>(wff + i * S.Sf);
-#pragma unroll 4
-        for (int j = 0; j < nf4; j++) {
-          const ulonglong2 w = w4[j], e = ef4[j];
-          const u64 p01 = F.mul(e.x, w.x), p23 = F.mul(e.y, w.y);
-          excitation += lo32(p01); excitation += hi32(p01); excitation += lo32(p23); excitation += hi32(p23);
-        }
-        if (has_rec) {
-          const ulonglong2* r4 = reinterpret_cast<const ulonglong2*>(wrec + i * S.Sr);
-#pragma unroll 4
-          for (int j = 0; j < nr4; j++) {
-            const ulonglong2 w = r4[j], e = er4[j];
-            const u64 p01 = F.mul(e.x, w.x), p23 = F.mul(e.y, w.y);
-            excitation += lo32(p01); excitation += hi32(p01); excitation += lo32(p23); excitation += hi32(p23);
-          }
-        }
-        float inhibition = 0.0f;
+      for (int e = 0; e < LATQ; e++) lw[e] = e < n_spk ? lat_weight(lat_list[e]) : 0.0f;
+      // simStepGenerate: the excitation starts from noiseDist(generator) * noise (neo/SparseCoder.cpp:200)
+      float excitation = gen ? gen_nz[(long long)it * nh + i] * gen_scale : 0.0f;
+      excitation = dot_row_seq(F, reinterpret_cast<const ulonglong2*>(w + (size_t)i * pitch), reinterpret_cast<const ulonglong2*>(err),
+                               pitch >> 2, excitation);
+      float inhibition = 0.0f;
 #pragma unroll
-        for (int e = 0; e < LATQ; e++) inhibition += lw[e];
-        for (int e = LATQ; e < n_spk; e++) {
-          const int cc = lat_list[e], tx = cc & 0xffff, ty = cc >> 16, dx = tx - ux, dy = ty - uy;
-          if (dx >= -r && dx <= r && dy >= -r && dy <= r && (dx | dy) != 0) {
-            const int sx = L.lat.absx ? tx : dx + r, sy = L.lat.absy ? ty : dy + r;
-            inhibition += wlat[(long long)(sx * L.lat.dyn + sy) * nh + i];
-          }
-        }
-        av = (1.0f - L.leak) * act[i] + excitation - inhibition;
-        if (av > thr[i]) { av = 0.0f; sp = 1.0f; }
-        stv = state[i];
-        if (NEO) stv += sp;
-        else if (measuring) stv += measure_inv * sp;
+      for (int e = 0; e < LATQ; e++) inhibition += lw[e];
+      for (int e = LATQ; e < n_spk; e++) {
+        const int2 t = lat_list[e];
+        const bool in = lat_on && (unsigned)((t.x & 0xffff) + tcx) <= r2 && (unsigned)((t.x >> 16) + tcy) <= r2 && t.x != own;
+        if (in) inhibition += wlat[t.y + lat_off];
       }
-      if (i < nh) { act[i] = av; spike[i] = sp; state[i] = stv; }
+      float av = (1.0f - L.leak) * act[i] + excitation - inhibition, sp = 0.0f;
+      if (av > thr[i]) { av = 0.0f; sp = 1.0f; }
+      float stv = state[i];
+      if (NEO) stv += sp;
+      else if (measuring) stv += measure_inv * sp;
+      act[i] = av; spike[i] = sp; state[i] = stv;
     }
     counter += 1.0f;
     mult = 1.0f / counter;
     __syncthreads();
     // ---- reconstruction + errors (sdr/IRSDR.cpp:139-142, :218-235; neo/SparseCoder.cpp:164-168)
-    {
-      if (warp < sweep_warps) build_lat_list();
-      const int n = compact_drive(NEO ? state : spike, nh, lane, lu, ld);
-      for (int j = tid; j < nv + nh; j += T) {
-        if (j < nv) {
-          const float* col = wff + j;
-          float sum = 0.0f;
-          for (int k = 0; k < n; k++) { const float wv = col[lu[k] * S.Sf], d = ld[k]; sum += NEO ? wv * d * mult : wv * d; }
-          vrec[j] = sum;
-          ef[j] = x[j] - sum;
-        } else if (has_rec) {
-          const int s = j - nv;
-          const float* col = wrec + s;
-          float sum = 0.0f;
-          for (int k = 0; k < n; k++) { const float wv = col[lu[k] * S.Sr], d = ld[k]; sum += NEO ? wv * d * mult : wv * d; }
-          hrec[s] = sum;
-          er[s] = sprev[s] - sum;
-        }
-      }
-    }
+    if (warp < S.sweep_warps) build_lat_list();
+    reconstruct(NEO ? state : spike, NEO != 0, mult);
     __syncthreads();
   }
 
   // ---- results back to the blob, unit order
-  if (!NEO) {  // reconstructFromStates, sdr/IRSDR.cpp:215
-    const int n = compact_drive(state, nh, lane, lu, ld);
-    for (int j = tid; j < nv + nh; j += T) {
-      float sum = 0.0f;
-      if (j < nv) {
-        for (int k = 0; k < n; k++) sum += wff[lu[k] * S.Sf + j] * ld[k];
-        B[L.vis_recon + j / vh + (j % vh) * vw] = sum;
-      } else {
-        const int s = j - nv;
-        if (has_rec) for (int k = 0; k < n; k++) sum += wrec[lu[k] * S.Sr + s] * ld[k];
-        B[L.recon + s / hh + (s % hh) * hw] = sum;
-      }
-    }
-  } else {
-    for (int s = tid; s < nv; s += T) B[L.vis_recon + s / vh + (s % vh) * vw] = vrec[s];
-    for (int s = tid; s < nh; s += T) B[L.recon + s / hh + (s % hh) * hw] = has_rec ? hrec[s] : 0.0f;
+  if (!NEO) {  // reconstructFromStates, sdr/IRSDR.cpp:215 (the errors it also rewrites are not used again)
+    reconstruct(state, false, 1.0f);
+    __syncthreads();
   }
+  for (int s = tid; s < nv; s += T) B[L.vis_recon + s / vh + (s % vh) * vw] = rec[s];
+  for (int s = tid; s < nh; s += T) B[L.recon + s / hh + (s % hh) * hw] = has_rec ? rec[S.nf + s] : 0.0f;
   const bool has_next = next_vis_input >= 0;
-  for (int i = tid; i < nh; i += T) {
-    float st = state[i];
+  for (int k = tid; k < nh; k += T) {
+    float st = state[k];
     if (NEO) st *= mult;  // neo/SparseCoder.cpp:171-175
-    B[L.state + i] = st;
-    B[L.act + i] = act[i];
-    B[L.spike + i] = spike[i];
-    B[L.spike_prev + i] = spike[i];
+    B[L.state + k] = st;
+    B[L.act + k] = act[k];
+    B[L.spike + k] = spike[k];
+    B[L.spike_prev + k] = spike[k];
     if (has_next) {  // next layer's input (neo/Agent.cpp:147-151)
-      if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + i * 3 + 0];
-      B[next_vis_input + i] = st;
+      if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + k * 3 + 0];
+      B[next_vis_input + k] = st;
     }
   }
 }
