@@ -127,19 +127,45 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   u64* err2 = reinterpret_cast<u64*>(err);
   constexpr int NP = 5;  // input pairs per lane per trip: 16*5*2 = 160 inputs
   for (int it = 0; it < C.iter; it++) {
-    // excitation += w * err, sequentially over the inputs
+    // excitation += w * err, sequentially over the inputs.  The shared-memory loads run two quads ahead of
+    // the add chain (a quad's four chained adds are 16 cycles, a load is ~30); the last two prefetches of a
+    // row read past its end (inside the slab) and are never used
     float exc = 0.0f;
+    ulonglong2 eq0 = e4[0], eq1 = e4[1], wq0, wq1;
+    if (RH == 0) { wq0 = w4[0]; wq1 = w4[1]; }
 #pragma unroll
-    for (int q = 0; q < RQ; q++) {
-      const ulonglong2 e = e4[q];
-      const u64 p01 = F.mul(wr[2 * q], e.x), p23 = F.mul(wr[2 * q + 1], e.y);
-      exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+    for (int q = 0; q < RQ; q += 2) {
+      {
+        const u64 p01 = F.mul(wr[2 * q], eq0.x), p23 = F.mul(wr[2 * q + 1], eq0.y);
+        eq0 = e4[q + 2];
+        if (q + 2 == RQ) wq0 = w4[0];
+        exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+      }
+      {
+        const u64 p01 = F.mul(wr[2 * q + 2], eq1.x), p23 = F.mul(wr[2 * q + 3], eq1.y);
+        eq1 = e4[q + 3];
+        if (q + 2 == RQ) wq1 = w4[1];
+        exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+      }
     }
-#pragma unroll 4
-    for (int j = 0; j < n4; j++) {
-      const ulonglong2 w = w4[j], e = e4[RQ + j];
-      const u64 p01 = F.mul(w.x, e.x), p23 = F.mul(w.y, e.y);
-      exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+    {
+      int j = 0;
+      for (; j + 2 <= n4; j += 2) {
+        {
+          const u64 p01 = F.mul(wq0.x, eq0.x), p23 = F.mul(wq0.y, eq0.y);
+          wq0 = w4[j + 2]; eq0 = e4[RQ + j + 2];
+          exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+        }
+        {
+          const u64 p01 = F.mul(wq1.x, eq1.x), p23 = F.mul(wq1.y, eq1.y);
+          wq1 = w4[j + 3]; eq1 = e4[RQ + j + 3];
+          exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+        }
+      }
+      if (j < n4) {
+        const u64 p01 = F.mul(wq0.x, eq0.x), p23 = F.mul(wq0.y, eq0.y);
+        exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
+      }
     }
     // inhibition += lat * spikePrev over the cells that spiked (the others add +-0)
     float inh = 0.0f;
