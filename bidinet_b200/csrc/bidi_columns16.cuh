@@ -127,6 +127,17 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   u64* err2 = reinterpret_cast<u64*>(err);
   constexpr int NP = 5;  // input pairs per lane per trip: 16*5*2 = 160 inputs
   for (int it = 0; it < C.iter; it++) {
+    // inhibition += lat * spikePrev over the cells that spiked (the others add +-0; an absent entry adds +0,
+    // which leaves a sum that started at +0 unchanged).  Done before the sweep, four loads in flight, so that
+    // their latency is not on the path between the sweep and the threshold test
+    float inh = 0.0f;
+    for (unsigned mm = m; mm;) {
+      float lv[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) { lv[q] = mm ? latT[(__ffs(mm) - 1) * CC + i] : 0.0f; mm &= mm - 1; }
+#pragma unroll
+      for (int q = 0; q < 4; q++) inh += lv[q];
+    }
     // excitation += w * err, sequentially over the inputs.  The shared-memory loads run two quads ahead of
     // the add chain (a quad's four chained adds are 16 cycles, a load is ~30); the last two prefetches of a
     // row read past its end (inside the slab) and are never used
@@ -167,9 +178,6 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
         exc += lo32(p01); exc += hi32(p01); exc += lo32(p23); exc += hi32(p23);
       }
     }
-    // inhibition += lat * spikePrev over the cells that spiked (the others add +-0)
-    float inh = 0.0f;
-    for (unsigned mm = m; mm; mm &= mm - 1) inh += latT[(__ffs(mm) - 1) * CC + i];
     float av = oml * act + exc - inh;
     if (av > thr) { av = 0.0f; sp = 1.0f; } else sp = 0.0f;
     st += sp;

@@ -97,6 +97,46 @@ __device__ __forceinline__ void for_each_slot_batched(const WinDev& w, int ux, i
 struct WE { float w, e; };
 struct WTE { float w, tr, e; };
 
+// The delta rule w += k*prev(target) and the product sum += now(target)*w that uses the updated weight, over
+// the whole slot box in ONE pass: every weight is read once, NB slots' loads in flight together.  The rule
+// touches only the unit's own connections (and, with SKIP_ZERO, only those whose source is not zero: k*0 = +-0
+// leaves w as it was); the sum runs over every slot like dot_conn (the others hold 0).
+template <int NB, bool SKIP_ZERO, class Prev, class Now>
+__device__ __forceinline__ float learn_dot(const WinDev& w, int ux, int uy, float* __restrict__ plane, long long U, int i, bool do_learn,
+                                           float k, float sum, Prev&& prev, Now&& now) {
+  if (w.r < 0) return sum;
+  const SlotBox b = slot_box(w, ux, uy);
+  float* wp = plane + i;
+  for (int sx = 0; sx < w.dxn; sx++) {
+    const bool okx = sx >= b.sx0 && sx <= b.sx1;
+    const int txr = slot_tx(w, b, sx), tx = min(max(txr, 0), w.tw - 1);
+    for (int sy0 = 0; sy0 < w.dyn; sy0 += NB) {
+      float wv[NB], pv[NB], nv[NB];
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int sy = min(sy0 + q, w.dyn - 1);
+        const int t = tx + min(max(slot_ty(w, b, sy), 0), w.th - 1) * w.tw;
+        wv[q] = wp[(long long)(sx * w.dyn + sy) * U];
+        nv[q] = now(t);
+        pv[q] = do_learn ? prev(t) : 0.0f;
+      }
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int sy = sy0 + q, tyr = slot_ty(w, b, sy);
+        if (sy < w.dyn) {
+          bool ok = do_learn && okx && sy >= b.sy0 && sy <= b.sy1;
+          if (w.excl && txr == b.cx && tyr == b.cy) ok = false;
+          if (SKIP_ZERO && pv[q] == 0.0f) ok = false;
+          float wn = wv[q];
+          if (ok) { wn = wv[q] + k * pv[q]; wp[(long long)(sx * w.dyn + sy) * U] = wn; }
+          sum += nv[q] * wn;
+        }
+      }
+    }
+  }
+  return sum;
+}
+
 // sum += src(target) * w[slot][unit] over the WHOLE slot box, in the reference's list
 // order, with no per-slot test: the slot planes hold 0 wherever the unit has no
 // connection (off-grid, outside the radius, excluded centre), the target index is
@@ -415,6 +455,8 @@ __global__ void k_predict(EngineDev P, LayerDev L, int l, int learn, long long u
   float* wfb = B + L.fb.w_off;
   float* wpr = B + L.pred.w_off;
   const int ux = i % L.hw, uy = i / L.hw, U = L.pn;
+  float kfb = 0.0f, kpr = 0.0f;
+  bool upd = false;
   if (learn) {
     float err = state[i] - B[L.p_state_prev + i];
     if (P.variant == BIDI_KWINNERS) {
@@ -427,20 +469,15 @@ __global__ void k_predict(EngineDev P, LayerDev L, int l, int learn, long long u
     } else if (P.variant == BIDI_NEO_AGENT) {
       err = B[L.col.a_expl + i * 3 + 1] * err; // _learnPrediction gate, neo/Agent.cpp:181
     }
-    const float kfb = L.learn_fb * err, kpr = L.learn_pred * err;
-    // w += k*src: a zero error or a zero source adds (+-0), which leaves w as it was, so
-    // those weights are neither read nor written (binary, sparse states: almost all of them)
-    if (err != 0.0f) {  // slots in batches of 8: the loads of a batch are in flight together (for_each_slot_batched)
-      if (!top)
-        for_each_slot_batched<8, WE>(L.fb, ux, uy, [&](int s, int t) { return WE{wfb[(long long)s * U + i], up_prev[t]}; },
-                                     [&](int s, const WE& v) { if (v.e != 0.0f) wfb[(long long)s * U + i] = v.w + kfb * v.e; });
-      for_each_slot_batched<8, WE>(L.pred, ux, uy, [&](int s, int t) { return WE{wpr[(long long)s * U + i], sprev[t]}; },
-                                   [&](int s, const WE& v) { if (v.e != 0.0f) wpr[(long long)s * U + i] = v.w + kpr * v.e; });
-    }
+    kfb = L.learn_fb * err; kpr = L.learn_pred * err;
+    // w += k*src: a zero error or a zero source adds (+-0), which leaves w as it was, so those
+    // weights are not rewritten (binary, sparse states: almost all of them)
+    upd = err != 0.0f;
   }
   float activation = 0.0f;
-  if (!top) activation = dot_conn(L.fb, ux, uy, wfb, U, i, activation, [&](int t) { return up_state[t]; });
-  activation = dot_conn(L.pred, ux, uy, wpr, U, i, activation, [&](int t) { return state[t]; });
+  if (!top)
+    activation = learn_dot<8, true>(L.fb, ux, uy, wfb, U, i, upd, kfb, activation, [&](int t) { return up_prev[t]; }, [&](int t) { return up_state[t]; });
+  activation = learn_dot<8, true>(L.pred, ux, uy, wpr, U, i, upd, kpr, activation, [&](int t) { return sprev[t]; }, [&](int t) { return state[t]; });
   B[L.p_act + i] = activation;
   if (P.variant != BIDI_KWINNERS) B[L.p_state + i] = bidi_clamp01(activation);
 }
@@ -453,15 +490,14 @@ __global__ void k_predict_input(EngineDev P, LayerDev L, int learn, long long p0
   const float* p0_prev = B + p0_state_prev;
   float* wfb = B + L.fb.w_off;
   const int ux = i % L.fb.uw, uy = i / L.fb.uw, U = L.pn;
+  float k = 0.0f;
   if (learn) {
     float err = P.in0[(long long)a * P.n_in + i] - B[L.p_state_prev + i];
     if (P.variant == BIDI_NEO_AGENT) err = B[L.col.a_expl + i * 3 + 1] * err;
-    const float k = L.learn_fb * err; // learn_fb of the input layer = _learnInputFeedBack
-    for_each_slot_batched<8, WE>(L.fb, ux, uy, [&](int s, int t) { return WE{wfb[(long long)s * U + i], p0_prev[t]}; },
-                                 [&](int s, const WE& v) { wfb[(long long)s * U + i] = v.w + k * v.e; });
+    k = L.learn_fb * err; // learn_fb of the input layer = _learnInputFeedBack
   }
   float activation = 0.0f;
-  activation = dot_conn(L.fb, ux, uy, wfb, U, i, activation, [&](int t) { return p0[t]; });
+  activation = learn_dot<8, false>(L.fb, ux, uy, wfb, U, i, learn != 0, k, activation, [&](int t) { return p0_prev[t]; }, [&](int t) { return p0[t]; });
   B[L.p_act + i] = activation;
   P.pred_out[(long long)a * P.n_in + i] = activation;
 }
