@@ -128,6 +128,7 @@ struct bidi_engine {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_learn = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_in = nullptr;                     // the last bidi_set_inputs' host->device copy has read the host buffer
   // one graph per value of the learn flag
   cudaGraphExec_t graphs[3] = {nullptr, nullptr, nullptr};   // learn off, learn on, simStepGenerate
   int graph_kernels[3] = {0, 0, 0};
@@ -877,6 +878,7 @@ void bidi_destroy(bidi_engine* h) {
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_pred); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_noise); cudaFreeHost(h->h_actions);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_in) cudaEventDestroy(h->ev_in);
   strip_release(h);
   coop_release(h);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -1116,6 +1118,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   CU_CREATE(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   CU_CREATE(cudaEventCreate(&h->ev0));
   CU_CREATE(cudaEventCreate(&h->ev1));
+  CU_CREATE(cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
   const size_t A = (size_t)n_agents, nin = (size_t)h->n_in, nn = std::max<size_t>(1, (size_t)h->n_noise);
   CU_CREATE(cudaMalloc(&h->d_blob, sizeof(float) * A * (size_t)h->stride));
   CU_CREATE(cudaMemsetAsync(h->d_blob, 0, sizeof(float) * A * (size_t)h->stride, h->stream));
@@ -1489,13 +1492,25 @@ int bidi_set_inputs(bidi_engine* h, const float* in) {
     const size_t hi = std::max(h->strip_span[BIDI_SPAN_VIS_RECON][1], h->strip_span[BIDI_SPAN_OWN_VIS][1]) * w;
     for (int a = 0; a < h->A; a++) {
       const size_t o = (size_t)a * h->n_in + lo;
-      memcpy(h->h_in + o, in + o, sizeof(float) * (hi - lo));
+      if (in != h->h_in) memcpy(h->h_in + o, in + o, sizeof(float) * (hi - lo));
       CU(cudaMemcpyAsync(h->d_in0 + o, h->h_in + o, sizeof(float) * (hi - lo), cudaMemcpyHostToDevice, h->stream));
     }
+    CU(cudaEventRecord(h->ev_in, h->stream));
     return BIDI_OK;
   }
-  memcpy(h->h_in, in, bytes);
+  if (in != h->h_in) memcpy(h->h_in, in, bytes);  // bidi_host_inputs: the caller wrote the pinned buffer itself
   CU(cudaMemcpyAsync(h->d_in0, h->h_in, bytes, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaEventRecord(h->ev_in, h->stream));
+  return BIDI_OK;
+}
+
+float* bidi_host_inputs(bidi_engine* h) { return h ? h->h_in : nullptr; }
+const float* bidi_host_predictions(bidi_engine* h) { return h ? h->h_pred : nullptr; }
+
+int bidi_wait_inputs(bidi_engine* h) {
+  if (!h) return fail(h, BIDI_EINVAL, "null engine");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventSynchronize(h->ev_in));
   return BIDI_OK;
 }
 
@@ -1569,13 +1584,13 @@ int bidi_get_predictions(bidi_engine* h, float* out) {
     CU(cudaStreamSynchronize(h->stream));
     for (int a = 0; a < h->A; a++) {
       const size_t o = (size_t)a * h->n_in + lo;
-      memcpy(out + o, h->h_pred + o, sizeof(float) * (hi - lo));
+      if (out != h->h_pred) memcpy(out + o, h->h_pred + o, sizeof(float) * (hi - lo));
     }
     return BIDI_OK;
   }
   CU(cudaMemcpyAsync(h->h_pred, h->d_pred, bytes, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
-  memcpy(out, h->h_pred, bytes);
+  if (out != h->h_pred) memcpy(out, h->h_pred, bytes);  // bidi_host_predictions: the caller reads the pinned buffer itself
   return BIDI_OK;
 }
 

@@ -36,6 +36,9 @@ ABI = {
     "bidi_set_array": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _FP, C.c_longlong]),
     "bidi_get_array": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _FP, C.c_longlong]),
     "bidi_set_inputs": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_host_inputs": (_FP, [C.c_void_p]),
+    "bidi_host_predictions": (_FP, [C.c_void_p]),
+    "bidi_wait_inputs": (C.c_int, [C.c_void_p]),
     "bidi_set_input": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float]),
     "bidi_step": (C.c_int, [C.c_void_p, _FP, _FP, _FP, C.c_int]),
     "bidi_get_predictions": (C.c_int, [C.c_void_p, _FP]),
@@ -198,10 +201,27 @@ class Engine:
             assert z.size == self.n_agents * self.lib.bidi_num_generate_noise(self.h)
         self._check(self.lib.bidi_step_generate(self.h, None if z is None else _fptr(z), float(noise)), "bidi_step_generate")
 
-    def get_predictions(self):
-        out = np.empty((self.n_agents, self.n_in), dtype=np.float32)
+    def get_predictions(self, out=None):
+        """out: optional [agent][index] float32 array to fill (host_predictions() saves the staging copy)."""
+        if out is None:
+            out = np.empty((self.n_agents, self.n_in), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.n_agents * self.n_in
         self._check(self.lib.bidi_get_predictions(self.h, _fptr(out)), "bidi_get_predictions")
         return out
+
+    def host_inputs(self):
+        """The engine's page-locked input buffer as an [agent][index] array: fill it, pass it to set_inputs (no
+        staging copy), and do not rewrite it before wait_inputs() returns."""
+        p = self.lib.bidi_host_inputs(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.n_agents, self.n_in))
+
+    def host_predictions(self):
+        """The engine's page-locked prediction buffer: pass it to get_predictions(out=...) (no staging copy)."""
+        p = self.lib.bidi_host_predictions(self.h)
+        return np.ctypeslib.as_array(p, shape=(self.n_agents, self.n_in))
+
+    def wait_inputs(self):
+        self._check(self.lib.bidi_wait_inputs(self.h), "bidi_wait_inputs")
 
     def get_actions(self):
         """sdr::QPRSDR::getActionRel of every action node: [agent][2*n_actions] (actions, then anti-actions)."""

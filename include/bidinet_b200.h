@@ -183,6 +183,17 @@ int bidi_get_array(bidi_engine* h, int agent, int which, int layer, float* dst, 
  * in[agent][index], host memory; copied host->device on the engine's stream.
  */
 int bidi_set_inputs(bidi_engine* h, const float* in);
+/*
+ * Zero-copy variant of the two host-buffer calls: the engine's own page-locked staging buffers,
+ * [agent][index] like the arguments of bidi_set_inputs / bidi_get_predictions.  A caller that
+ * writes its inputs into bidi_host_inputs() and passes that pointer to bidi_set_inputs (or passes
+ * bidi_host_predictions() to bidi_get_predictions) saves the staging memcpy.  The input buffer may
+ * be rewritten once bidi_wait_inputs returns (the host->device copy has read it); the prediction
+ * buffer is valid until the next bidi_get_predictions.
+ */
+float* bidi_host_inputs(bidi_engine* h);
+const float* bidi_host_predictions(bidi_engine* h);
+int bidi_wait_inputs(bidi_engine* h);
 int bidi_set_input(bidi_engine* h, int agent, int index, float value);
 
 /*

@@ -109,6 +109,32 @@ def test_batched_agents_are_independent():
         assert diff_states(orcs[a].state(), eng.state(agent=a)) == []
 
 
+def test_host_buffers_in_place():
+    """bidi_host_inputs / bidi_host_predictions: stepping through the engine's own page-locked buffers gives
+    the same predictions as the copying calls."""
+    cfg, ld = cf.config_c2()
+    rng = np.random.RandomState(5)
+    frames = rng.rand(6, 3, 64).astype(np.float32)
+    a, b = Engine(cfg, ld, n_agents=3), Engine(cfg, ld, n_agents=3)
+    for e in (a, b):
+        e.init_random(77)
+    x, pred = b.host_inputs(), b.host_predictions()
+    assert x.shape == (3, 64) and pred.shape == (3, 64)
+    for t in range(6):
+        a.set_inputs(frames[t])
+        a.step(rewards=[0.1, 0.2, 0.3])
+        np.copyto(x, frames[t])
+        b.set_inputs(x)
+        b.step(rewards=[0.1, 0.2, 0.3])
+        b.wait_inputs()
+        x[:] = -1.0  # the copy has read the buffer: rewriting it now must not matter
+        out = b.get_predictions(out=pred)
+        assert out is pred
+        assert np.array_equal(a.get_predictions(), pred), "step %d" % t
+    a.close()
+    b.close()
+
+
 def test_device_noise_mode_runs_and_explores():
     """noise=None: the engine's own generator; actions stay in [0,1] and differ between agents."""
     cfg, ld = cf.config_c2()
