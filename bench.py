@@ -413,25 +413,22 @@ def main():
     e2e_i = 0
     fb0, fb1 = int(FB_IDX[0]), int(FB_IDX[-1]) + 1     # the action inputs are one contiguous run of cells
     assert np.array_equal(FB_IDX, np.arange(fb0, fb1))
-    act = np.empty((A, fb1 - fb0), dtype=np.float32)
-    tmp = np.empty_like(act)
-    inv_n = np.full(fb1 - fb0, 1.0 / (fb1 - fb0), dtype=np.float32)
+    import ctypes
+    from bidinet_b200.build import build_runner_env
+    env_lib = ctypes.CDLL(build_runner_env())  # tools/runner_env.c: the environment in compiled code, as in the reference
+    fp = ctypes.POINTER(ctypes.c_float)
+    env_lib.runner_env_step.argtypes = [ctypes.c_int] * 4 + [fp] * 4
+    env_lib.runner_env_step.restype = None
+    pred_p, x_p, rew_p = (a.ctypes.data_as(fp) for a in (pred, x, rewards))
 
     np.copyto(x, frames[t % T])
 
     def host_step(tt):
         """the caller's side of RunnerMain.cpp:235-251: state inputs, fed-back noisy actions, reward.
         The open-loop part of the NEXT frame is laid out while the GPU works on this step."""
-        nonlocal pred, e2e_i
-        np.multiply(pred[:, fb0:fb1], 0.5, out=act)
-        np.add(act, 0.5, out=act)
-        np.add(act, env_noise[e2e_i], out=tmp)
+        nonlocal e2e_i
+        env_lib.runner_env_step(A, n_in, fb0, fb1 - fb0, pred_p, env_noise[e2e_i].ctypes.data_as(fp), x_p, rew_p)
         e2e_i += 1
-        np.clip(tmp, 0.0, 1.0, out=tmp)
-        x[:, fb0:fb1] = tmp
-        np.clip(act, 0.0, 1.0, out=act)
-        np.dot(act, inv_n, out=rewards)
-        np.subtract(rewards, 0.5, out=rewards)
         eng.set_inputs(x)
         eng.step(rewards=rewards)        # asynchronous: returns once the step is enqueued
         eng.wait_inputs()                # the host->device copy has read x

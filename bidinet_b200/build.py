@@ -16,4 +16,19 @@ def build(force=False, verbose=False):
         raise RuntimeError("building libbidinet_b200.so failed:\n" + out.stdout + out.stderr)
     if verbose:
         print(out.stdout + out.stderr)
+    build_runner_env()
     return LIB_PATH
+
+
+RUNNER_ENV_PATH = os.path.join(os.path.dirname(_HERE), "tools", "librunner_env.so")
+
+
+def build_runner_env():
+    """gcc: the synthetic environment of bench.py's end-to-end loop (tools/runner_env.c), host code only."""
+    src = os.path.join(os.path.dirname(_HERE), "tools", "runner_env.c")
+    if os.path.exists(RUNNER_ENV_PATH) and os.path.getmtime(RUNNER_ENV_PATH) >= os.path.getmtime(src):
+        return RUNNER_ENV_PATH
+    out = subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", RUNNER_ENV_PATH, src], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise RuntimeError("building librunner_env.so failed:\n" + out.stdout + out.stderr)
+    return RUNNER_ENV_PATH
