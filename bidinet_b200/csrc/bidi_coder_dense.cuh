@@ -11,13 +11,16 @@
 //     products, four chained adds per four connections, software-pipelined four quads deep;
 //   * the gather-form reconstruction needs no window test (a unit outside the window has
 //     weight 0 and adds +-0): each reconstructing warp compacts the units with a non-zero
-//     drive into a private list of 16-byte entries (row offset, unit, drive twice), ascending
+//     drive into a private list of 8-byte entries (row offset, drive), ascending
 //     unit index = the reference's scatter order, and a lane owns a PAIR (or four) of
-//     adjacent slots: per listed unit one broadcast 128-bit load, one 64-bit weight load,
+//     adjacent slots: per listed unit one broadcast 64-bit load, one 64-bit weight load,
 //     one or two packed products and two independent adds.  A CTA has as many warps as the
 //     larger of the two phases needs (RunnerMain layers: two and one), so none idles at the
 //     barriers;
-//   * the lateral lists carry the precomputed slot-plane offset of every spiking unit.
+//   * the lateral lists index a table with the precomputed slot-plane offset of every unit;
+//   * everything but the weight rows is kept small (activations and thresholds in registers,
+//     the reconstructions written over the errors at the end), so that six CTAs of the
+//     RunnerMain layer 0 fit an SM: 4096 agents are then five waves instead of six.
 // Same arithmetic, same order, same bits as bidi_coder.cuh / bidi_kernels.cuh.
 #pragma once
 #include "bidi_coder.cuh"
@@ -53,25 +56,24 @@ __host__ __device__ inline CoderDenseShape coder_dense_shape(const LayerDev& L) 
   if (s.recon_warps > 16) s.recon_warps = 16;
   s.warps = s.sweep_warps > s.recon_warps ? s.sweep_warps : s.recon_warps;
   s.floats = (long long)L.nh * s.pitch              // weight rows
-             + 3LL * s.pitch                        // errors, inputs (x | statePrev), reconstructions
-             + 4LL * s.recon_warps * L.nh           // per reconstructing warp: drive list, 16-byte entries
-             + 4LL * L.nh                           // act, state, spike, thr: unit order
+             + 2LL * s.pitch                        // errors (the reconstructions at the end), inputs (x | statePrev)
+             + 2LL * s.recon_warps * L.nh           // per reconstructing warp: drive list, 8-byte entries
+             + 2LL * L.nh                           // state, spike: unit order (act and thr live in registers)
              + 2LL * L.nh                           // lateral-order table: (coordinates, slot plane offset)
-             + 2LL * s.sweep_warps * L.nh           // per sweeping warp: lateral list, same entries
-             + 8;
+             + (long long)s.sweep_warps * L.nh      // per sweeping warp: lateral list (positions in the table)
+             + 8;                                   // RunnerMain layer 0: 37.4 KB, six CTAs per SM
   return s;
 }
 __host__ __device__ inline int coder_dense_threads(const LayerDev& L) { return 32 * coder_dense_shape(L).warps; }
 
-// the units with src != 0, ascending unit index, into this warp's private list:
-// entry = (row offset, unit, drive, drive)
-__device__ __forceinline__ int compact_drive(const float* __restrict__ src, int nh, int lane, int pitch, int4* ent) {
+// the units with src != 0, ascending unit index, into this warp's private list: entry = (row offset, drive)
+__device__ __forceinline__ int compact_drive(const float* __restrict__ src, int nh, int lane, int pitch, int2* ent) {
   int base = 0;
   for (int p0 = 0; p0 < nh; p0 += 32) {
     const int p = p0 + lane;
     const float d = p < nh ? src[p] : 0.0f;
     const unsigned m = __ballot_sync(0xffffffffu, d != 0.0f);
-    if (d != 0.0f) ent[base + __popc(m & ((1u << lane) - 1u))] = make_int4(p * pitch, p, __float_as_int(d), __float_as_int(d));
+    if (d != 0.0f) ent[base + __popc(m & ((1u << lane) - 1u))] = make_int2(p * pitch, __float_as_int(d));
     base += __popc(m);
   }
   __syncwarp();
@@ -122,16 +124,13 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
   const int W = S.warps, T = 32 * W, pitch = S.pitch;
   const bool has_rec = L.rec.r >= 0;
   float* w = sm;                              // [nh][pitch]
-  float* err = w + (size_t)nh * pitch;        // [pitch] errors, slot order, pads 0
+  float* err = w + (size_t)nh * pitch;        // [pitch] errors, slot order, pads 0; after the last iteration: the reconstructions
   float* xin = err + pitch;                   // [pitch] x | statePrev
-  float* rec = xin + pitch;                   // [pitch] visible | hidden reconstruction
-  int4* ent = reinterpret_cast<int4*>(rec + pitch) + (warp < S.recon_warps ? warp : 0) * nh;  // this warp's drive list
-  float* act = rec + pitch + 4 * S.recon_warps * nh;  // unit order from here
-  float* state = act + nh;
+  int2* ent = reinterpret_cast<int2*>(xin + pitch) + (warp < S.recon_warps ? warp : 0) * nh;  // this warp's drive list
+  float* state = xin + pitch + 2 * S.recon_warps * nh;  // unit order
   float* spike = state + nh;
-  float* thr = spike + nh;
-  int2* lat_tab = reinterpret_cast<int2*>(thr + nh);  // [nh], lateral-list order: (x | y << 16, slot plane offset)
-  int2* lat_list = lat_tab + nh + (warp < S.sweep_warps ? warp : 0) * nh;  // this warp's spiking units, same entries
+  int2* lat_tab = reinterpret_cast<int2*>(spike + nh);  // [nh], lateral-list order: (x | y << 16, slot plane offset)
+  int* lat_list = reinterpret_cast<int*>(lat_tab + nh) + (warp < S.sweep_warps ? warp : 0) * nh;  // this warp's spiking units: positions in lat_tab
 
   // ---- stage: slot planes -> rows.  A task is four slots of 32 units: four coalesced loads per lane, one
   //      128-bit store (rows are 4 (mod 8) floats apart: a quarter warp's stores fall in distinct banks);
@@ -175,12 +174,11 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
         const int k = s - S.nf, u = k / hh + (k % hh) * hw;
         xv = B[L.state_prev + u]; rv = B[L.recon + u];
       }
-      xin[s] = xv; rec[s] = rv; err[s] = xv - rv;
+      xin[s] = xv; err[s] = xv - rv;
     }
     for (int k = tid; k < nh; k += T) {
-      thr[k] = B[L.thr + k];
       spike[k] = B[L.spike_prev + k];  // spikePrev persists across steps (sdr/IRSDR.cpp:131-135 resets only act, state)
-      act[k] = 0.0f; state[k] = 0.0f;
+      state[k] = 0.0f;
       const int tx = k / hh, ty = k - tx * hh;  // position k of the lateral lists' order (x-major: dx outer, dy inner)
       lat_tab[k] = make_int2(tx | (ty << 16), (tx * L.lat.dyn + ty) * nh);
     }
@@ -193,18 +191,19 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
     n_spk = 0;
     for (int p0 = 0; p0 < nh; p0 += 32) {
       const int p = p0 + lane;
-      int2 t = make_int2(0, 0);
       bool f = false;
-      if (p < nh) { t = lat_tab[p]; f = spike[(t.x & 0xffff) + (t.x >> 16) * hw] != 0.0f; }
+      if (p < nh) { const int cc = lat_tab[p].x; f = spike[(cc & 0xffff) + (cc >> 16) * hw] != 0.0f; }
       const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (f) lat_list[n_spk + __popc(m & ((1u << lane) - 1u))] = t;
+      if (f) lat_list[n_spk + __popc(m & ((1u << lane) - 1u))] = p;
       n_spk += __popc(m);
     }
     __syncwarp();
   };
   // reconstruction of both sides from the units with a non-zero drive, ascending unit index
-  // (sdr/IRSDR.cpp:218-235, neo/SparseCoder.cpp:164-168): a lane owns adjacent slots of the row layout
-  auto reconstruct = [&](const float* drive, bool scaled, float mult) {
+  // (sdr/IRSDR.cpp:218-235, neo/SparseCoder.cpp:164-168): a lane owns adjacent slots of the row layout.
+  // It leaves the errors input - reconstruction in err[]; `last`: the reconstruction itself (the errors
+  // are not read again), which is what goes back to the blob
+  auto reconstruct = [&](const float* drive, bool scaled, float mult, bool last) {
     if (warp >= S.recon_warps) return;
     const int n = compact_drive(drive, nh, lane, pitch, ent);
     const u64 mult2 = pk(mult, mult);
@@ -213,31 +212,32 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
         const float* col = w + 4 * j;
         float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
         for (int k = 0; k < n; k++) {
-          const int4 e = ent[k];
+          const int2 e = ent[k];
           const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(col + e.x);
-          const u64 dd = pk(__int_as_float(e.z), __int_as_float(e.w));
+          const u64 dd = pk(__int_as_float(e.y), __int_as_float(e.y));
           u64 p01 = F.mul(wv.x, dd), p23 = F.mul(wv.y, dd);
           if (scaled) { p01 = F.mul(p01, mult2); p23 = F.mul(p23, mult2); }
           s0 += lo32(p01); s1 += hi32(p01); s2 += lo32(p23); s3 += hi32(p23);
         }
-        const ulonglong2 sum = make_ulonglong2(pk(s0, s1), pk(s2, s3));
-        reinterpret_cast<ulonglong2*>(rec)[j] = sum;
-        const ulonglong2 xv = reinterpret_cast<const ulonglong2*>(xin)[j];
-        reinterpret_cast<ulonglong2*>(err)[j] = make_ulonglong2(F.sub2(xv.x, sum.x), F.sub2(xv.y, sum.y));
+        ulonglong2 out = make_ulonglong2(pk(s0, s1), pk(s2, s3));
+        if (!last) {
+          const ulonglong2 xv = reinterpret_cast<const ulonglong2*>(xin)[j];
+          out = make_ulonglong2(F.sub2(xv.x, out.x), F.sub2(xv.y, out.y));
+        }
+        reinterpret_cast<ulonglong2*>(err)[j] = out;
       }
     } else {
       for (int j = tid; j < S.tasks; j += 32 * S.recon_warps) {
         const float* col = w + 2 * j;
         float s0 = 0.0f, s1 = 0.0f;
         for (int k = 0; k < n; k++) {
-          const int4 e = ent[k];
-          u64 pr = F.mul(*reinterpret_cast<const u64*>(col + e.x), pk(__int_as_float(e.z), __int_as_float(e.w)));
+          const int2 e = ent[k];
+          u64 pr = F.mul(*reinterpret_cast<const u64*>(col + e.x), pk(__int_as_float(e.y), __int_as_float(e.y)));
           if (scaled) pr = F.mul(pr, mult2);
           s0 += lo32(pr); s1 += hi32(pr);
         }
         const u64 sum = pk(s0, s1);
-        reinterpret_cast<u64*>(rec)[j] = sum;
-        reinterpret_cast<u64*>(err)[j] = F.sub2(reinterpret_cast<const u64*>(xin)[j], sum);
+        reinterpret_cast<u64*>(err)[j] = last ? sum : F.sub2(reinterpret_cast<const u64*>(xin)[j], sum);
       }
     }
   };
@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
   const unsigned r2 = 2u * (unsigned)r;
   const bool lat_on = r >= 0;
   const int lat_off = ((L.lat.absx ? 0 : tcx) * L.lat.dyn + (L.lat.absy ? 0 : tcy)) * nh + i;
+  float act_r = 0.0f;                                         // this lane's unit: activation and threshold stay in registers
+  const float thr_r = (warp < S.sweep_warps && i < nh) ? B[L.thr + i] : 0.0f;
   auto lat_weight = [&](int2 t) -> float {
     const bool in = lat_on && (unsigned)((t.x & 0xffff) + tcx) <= r2 && (unsigned)((t.x >> 16) + tcy) <= r2 && t.x != own;
     return in ? wlat[t.y + lat_off] : 0.0f;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
       constexpr int LATQ = 8;
       float lw[LATQ];
 #pragma unroll
-      for (int e = 0; e < LATQ; e++) lw[e] = e < n_spk ? lat_weight(lat_list[e]) : 0.0f;
+      for (int e = 0; e < LATQ; e++) lw[e] = e < n_spk ? lat_weight(lat_tab[lat_list[e]]) : 0.0f;
       // simStepGenerate: the excitation starts from noiseDist(generator) * noise (neo/SparseCoder.cpp:200)
       float excitation = gen ? gen_nz[(long long)it * nh + i] * gen_scale : 0.0f;
       excitation = dot_row_seq(F, reinterpret_cast<const ulonglong2*>(w + (size_t)i * pitch), reinterpret_cast<const ulonglong2*>(err),
@@ -279,39 +281,42 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
 #pragma unroll
       for (int e = 0; e < LATQ; e++) inhibition += lw[e];
       for (int e = LATQ; e < n_spk; e++) {
-        const int2 t = lat_list[e];
+        const int2 t = lat_tab[lat_list[e]];
         const bool in = lat_on && (unsigned)((t.x & 0xffff) + tcx) <= r2 && (unsigned)((t.x >> 16) + tcy) <= r2 && t.x != own;
         if (in) inhibition += wlat[t.y + lat_off];
       }
-      float av = (1.0f - L.leak) * act[i] + excitation - inhibition, sp = 0.0f;
-      if (av > thr[i]) { av = 0.0f; sp = 1.0f; }
+      float av = (1.0f - L.leak) * act_r + excitation - inhibition, sp = 0.0f;
+      if (av > thr_r) { av = 0.0f; sp = 1.0f; }
       float stv = state[i];
       if (NEO) stv += sp;
       else if (measuring) stv += measure_inv * sp;
-      act[i] = av; spike[i] = sp; state[i] = stv;
+      act_r = av; spike[i] = sp; state[i] = stv;
     }
     counter += 1.0f;
     mult = 1.0f / counter;
     __syncthreads();
     // ---- reconstruction + errors (sdr/IRSDR.cpp:139-142, :218-235; neo/SparseCoder.cpp:164-168)
-    if (warp < S.sweep_warps) build_lat_list();
-    reconstruct(NEO ? state : spike, NEO != 0, mult);
+    const bool last = NEO && it == total - 1;
+    if (warp < S.sweep_warps && !last) build_lat_list();
+    reconstruct(NEO ? state : spike, NEO != 0, mult, last);
     __syncthreads();
   }
 
   // ---- results back to the blob, unit order
   if (!NEO) {  // reconstructFromStates, sdr/IRSDR.cpp:215 (the errors it also rewrites are not used again)
-    reconstruct(state, false, 1.0f);
+    reconstruct(state, false, 1.0f, true);
     __syncthreads();
   }
-  for (int s = tid; s < nv; s += T) B[L.vis_recon + s / vh + (s % vh) * vw] = rec[s];
-  for (int s = tid; s < nh; s += T) B[L.recon + s / hh + (s % hh) * hw] = has_rec ? rec[S.nf + s] : 0.0f;
+  if (!NEO || total > 0) {  // (no iteration: the blob keeps the reconstructions it has)
+    for (int s = tid; s < nv; s += T) B[L.vis_recon + s / vh + (s % vh) * vw] = err[s];
+    for (int s = tid; s < nh; s += T) B[L.recon + s / hh + (s % hh) * hw] = has_rec ? err[S.nf + s] : 0.0f;
+  }
   const bool has_next = next_vis_input >= 0;
+  if (warp < S.sweep_warps && i < nh) B[L.act + i] = act_r;
   for (int k = tid; k < nh; k += T) {
     float st = state[k];
     if (NEO) st *= mult;  // neo/SparseCoder.cpp:171-175
     B[L.state + k] = st;
-    B[L.act + k] = act[k];
     B[L.spike + k] = spike[k];
     B[L.spike_prev + k] = spike[k];
     if (has_next) {  // next layer's input (neo/Agent.cpp:147-151)
