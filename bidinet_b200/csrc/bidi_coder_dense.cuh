@@ -81,8 +81,19 @@ __device__ __forceinline__ int compact_drive(const float* __restrict__ src, int 
 }
 
 // acc + sum of w[j]*e[j] over n4 quads, added strictly in order; the 128-bit loads of the next four
-// quads are issued before the sixteen chained adds of the current four
+// quads are issued before the sixteen chained adds of the current four.  LIGHT: two quads per trip, no
+// explicit double buffering (the one-warp CTAs of small layers trade it for registers: 28 CTAs per SM)
+template <int LIGHT>
 __device__ __forceinline__ float dot_row_seq(const Pair& F, const ulonglong2* __restrict__ w4, const ulonglong2* __restrict__ e4, int n4, float acc) {
+  if (LIGHT) {
+#pragma unroll 2
+    for (int j = 0; j < n4; j++) {
+      const ulonglong2 w = w4[j], e = e4[j];
+      const u64 p01 = F.mul(e.x, w.x), p23 = F.mul(e.y, w.y);
+      acc += lo32(p01); acc += hi32(p01); acc += lo32(p23); acc += hi32(p23);
+    }
+    return acc;
+  }
   ulonglong2 wa[4], ea[4], wb[4], eb[4];
   const int nb = n4 >> 2;
   auto load = [&](ulonglong2* w, ulonglong2* e, int j) {
@@ -113,8 +124,9 @@ __device__ __forceinline__ float dot_row_seq(const Pair& F, const ulonglong2* __
   return acc;
 }
 
-template <int NEO>
-__global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, int l, long long next_vis_input) {
+// LIGHT: the one-warp launch of a small layer (coder_dense_threads == 32), compiled for 28 CTAs per SM
+template <int NEO, int LIGHT>
+__global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dense(EngineDev P, LayerDev L, int l, long long next_vis_input) {
   extern __shared__ __align__(16) float sm[];
   const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Pair F{P.k_one2, P.k_negzero2, P.k_negone2};
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(512) k_coder_dense(EngineDev P, LayerDev L, in
       for (int e = 0; e < LATQ; e++) lw[e] = e < n_spk ? lat_weight(lat_tab[lat_list[e]]) : 0.0f;
       // simStepGenerate: the excitation starts from noiseDist(generator) * noise (neo/SparseCoder.cpp:200)
       float excitation = gen ? gen_nz[(long long)it * nh + i] * gen_scale : 0.0f;
-      excitation = dot_row_seq(F, reinterpret_cast<const ulonglong2*>(w + (size_t)i * pitch), reinterpret_cast<const ulonglong2*>(err),
+      excitation = dot_row_seq<LIGHT>(F, reinterpret_cast<const ulonglong2*>(w + (size_t)i * pitch), reinterpret_cast<const ulonglong2*>(err),
                                pitch >> 2, excitation);
       float inhibition = 0.0f;
 #pragma unroll

@@ -662,8 +662,14 @@ void record_step(Recorder& R, bool learn) {
       if (h->coder_cta[l] == 2) {  // windows span the grid: dense rows (bidi_coder_dense.cuh)
         const int threads = bidi::coder_dense_threads(ly[l]);
         const size_t smem = sizeof(float) * (size_t)bidi::coder_dense_shape(ly[l]).floats;
-        if (V == BIDI_ITERATIVE) bidi::k_coder_dense<0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
-        else bidi::k_coder_dense<1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+        const bool light = threads == 32;  // one warp per agent: the register-lean build, 28 CTAs per SM
+        if (V == BIDI_ITERATIVE) {
+          if (light) bidi::k_coder_dense<0, 1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+          else bidi::k_coder_dense<0, 0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+        } else {
+          if (light) bidi::k_coder_dense<1, 1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+          else bidi::k_coder_dense<1, 0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+        }
       } else {
         const int threads = std::min(512, std::max(64, (ly[l].nv + ly[l].nh + 31) / 32 * 32));
         const size_t smem = sizeof(float) * (size_t)bidi::coder_cta_shape(ly[l]).floats;
@@ -1253,8 +1259,10 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_cta<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     if (smem_dense > 0) {
-      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
-      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
+      CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
     }
   }
   // node layers with few (agent, unit) threads use the cooperative tile kernels
