@@ -150,7 +150,10 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
   {
     const int ub = (nh + 31) >> 5;
     auto stage_rows = [&](float* dst, const float* __restrict__ src, int n_slots, int nq) {
-      constexpr int NT = 4;
+#ifndef BIDI_STAGE_NT
+#define BIDI_STAGE_NT 4   // tasks whose loads are in flight together (8: slower, more registers)
+#endif
+      constexpr int NT = BIDI_STAGE_NT;
       int q = 0, b = warp;
       while (b >= ub) { b -= ub; q++; }
       while (q < nq) {
@@ -281,7 +284,10 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
       const bool measuring = !NEO && it >= L.iter_settle;
       // the lateral weights of the first few spiking neighbours are fetched from HBM/L2 now,
       // so that their latency hides behind the excitation sums (an absent entry adds +0)
-      constexpr int LATQ = 8;
+#ifndef BIDI_LATQ
+#define BIDI_LATQ 4   // measured on C3: 2..4 within 0.1 %, 8 is 0.5 % slower, 12 is 1.3 % slower
+#endif
+      constexpr int LATQ = BIDI_LATQ;
       float lw[LATQ];
 #pragma unroll
       for (int e = 0; e < LATQ; e++) lw[e] = e < n_spk ? lat_weight(lat_tab[lat_list[e]]) : 0.0f;
