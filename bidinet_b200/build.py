@@ -28,7 +28,11 @@ def build_runner_env():
     src = os.path.join(os.path.dirname(_HERE), "tools", "runner_env.c")
     if os.path.exists(RUNNER_ENV_PATH) and os.path.getmtime(RUNNER_ENV_PATH) >= os.path.getmtime(src):
         return RUNNER_ENV_PATH
-    out = subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", RUNNER_ENV_PATH, src], capture_output=True, text=True)
+    tmp = "%s.%d.tmp" % (RUNNER_ENV_PATH, os.getpid())  # several ranks may build at once: write aside, rename atomically
+    out = subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", tmp, src], capture_output=True, text=True)
     if out.returncode != 0:
+        if os.path.exists(RUNNER_ENV_PATH):
+            return RUNNER_ENV_PATH
         raise RuntimeError("building librunner_env.so failed:\n" + out.stdout + out.stderr)
+    os.replace(tmp, RUNNER_ENV_PATH)
     return RUNNER_ENV_PATH
