@@ -521,5 +521,23 @@ def main():
         dist.destroy_process_group()
 
 
+def _emit_one_line():
+    """The contract is ONE JSON line on stdout, but native libraries write banners to file descriptor 1
+    (NCCL prints its version there when NCCL_DEBUG is set in the environment).  Everything written to fd 1
+    while the bench runs goes to stderr; only the lines this script prints reach the real stdout."""
+    import io
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    py_stdout, sys.stdout = sys.stdout, buf
+    try:
+        main()
+    finally:
+        sys.stdout = py_stdout
+        os.write(real, buf.getvalue().encode())
+        os.close(real)
+
+
 if __name__ == "__main__":
-    main()
+    _emit_one_line()
