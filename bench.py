@@ -363,6 +363,9 @@ def main():
     A, K, W = args.agents_per_gpu, args.steps, max(3, args.warmup)
     cfg, ld = cf.config_c2()
     eng = Engine(cfg, ld, n_agents=A, device=local_rank)
+    for kv in filter(None, os.environ.get("BIDI_OPTS", "").split(",")):  # experiments only, e.g. BIDI_OPTS=early_learn=0
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     eng.init_random(seed_base_for(rank, A))  # global agent g <- std::mt19937(1234 + g)
     n_in = eng.n_in
     T = min(W + K, 64)

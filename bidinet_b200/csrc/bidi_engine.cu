@@ -127,6 +127,7 @@ struct bidi_engine {
   cudaStream_t side = nullptr;                     // second branch of the step graph (coder learning, see record_step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_learn = true;
+  bool early_learn = false;                        // option: a fused layer's learning starts right after its own up pass (measured slower, see DESIGN)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_in = nullptr;                     // the last bidi_set_inputs' host->device copy has read the host buffer
   // one graph per value of the learn flag
@@ -654,6 +655,18 @@ void record_step(Recorder& R, bool learn) {
     else R.launch("kw_predict_input", bidi::k_kw_predict_input, A * h->n_in, ly[0]);
     return;
   }
+  // Coder learning (sdr/IRSDR.cpp:287-319, neo/SparseCoder.cpp:326-361) reads only what the layer's own up pass and
+  // the PREVIOUS step left behind (errors, states, the previous prediction), and nothing before stepEnd reads what it
+  // writes, so in the step graph it is a second branch: beside the down pass, and -- where every layer's up pass is
+  // one fused launch -- already beside the up pass of the layers above.
+  auto record_learn_layer = [&](int l) {
+    if (h->tiled[l]) launch_tile(R, "ic_learn", bidi::k_t_ic_learn, tiles_of(A, ly[l].nh), 0, ly[l], l, (int)(V != BIDI_ITERATIVE));
+    else if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
+    else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
+  };
+  const bool fork_learn = learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing;
+  bool early_learn = fork_learn && h->early_learn;
+  for (int l = 0; l < L; l++) early_learn = early_learn && h->coder_cta[l] && !h->force_phase_kernels;
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
     if (h->coder_cta[l] && !h->force_phase_kernels && !R.collect) { // whole up pass of the layer in one launch
@@ -678,6 +691,13 @@ void record_step(Recorder& R, bool learn) {
       }
       R.after("coder");
       R.kernels++;
+      if (early_learn) {  // this layer's learning starts now, beside the next layer's up pass (which moves no HBM traffic)
+        cudaEventRecord(h->ev_fork, h->stream);
+        cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+        R.st = h->side;
+        record_learn_layer(l);
+        R.st = nullptr;
+      }
       continue;
     }
     const LayerDev& Y = ly[l];
@@ -718,18 +738,12 @@ void record_step(Recorder& R, bool learn) {
       R.launch("ic_finish", bidi::k_ic_finish, nh, Y, l, 1, 1.0f / counter, l < L - 1 ? ly[l + 1].vis_input : -1LL);
     }
   }
-  // Coder learning (sdr/IRSDR.cpp:287-319, neo/SparseCoder.cpp:326-361) reads only what the up pass and the
-  // PREVIOUS step left behind (errors, states, the previous prediction), and nothing before stepEnd reads what it
-  // writes, so in the step graph it is a second branch that runs beside the down pass instead of after it.
   auto record_learn = [&]() {
-    for (int l = 0; l < L; l++) {
-      if (h->tiled[l]) launch_tile(R, "ic_learn", bidi::k_t_ic_learn, tiles_of(A, ly[l].nh), 0, ly[l], l, (int)(V != BIDI_ITERATIVE));
-      else if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
-      else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
-    }
+    for (int l = 0; l < L; l++) record_learn_layer(l);
   };
-  const bool fork_learn = learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing;
-  if (fork_learn) {
+  if (early_learn) {
+    cudaEventRecord(h->ev_join, h->side);
+  } else if (fork_learn) {
     cudaEventRecord(h->ev_fork, h->stream);
     cudaStreamWaitEvent(h->side, h->ev_fork, 0);
     R.st = h->side;
@@ -1715,6 +1729,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   }
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "overlap_learn") h->overlap_learn = value != 0;
+  else if (std::string(name) == "early_learn") h->early_learn = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
       size_t smem = 0;
