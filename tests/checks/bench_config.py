@@ -2,7 +2,7 @@
 """Single-agent timings of the BASELINE.json configurations other than the bench headline:
 C1 (small), C4 (large 6-layer, radius 6), C5-size single layer -- engine ms/step on the GPU,
 the compiled reference (oracle/_ref) ms/step on one host core, and an exact-parity check
-of the first steps at full size.  usage: python tools/bench_config.py [c1|c4|c5] ...
+of the first steps at full size.  usage: python tests/checks/bench_config.py [c1|c4|c5] ...
 Prints one JSON object per configuration."""
 import json
 import os
@@ -11,7 +11,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from bidinet_b200 import Engine, config as cf  # noqa: E402
 from oracle.pyoracle import OracleHierarchy, RefHierarchy, have_ref, c1_frame  # noqa: E402

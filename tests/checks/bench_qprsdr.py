@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """sdr::QPRSDR batched: A agents of the small QPRSDR configuration (tests/util q_small) on one GPU against the
-compiled reference on the host cores.  usage: python tools/bench_qprsdr.py [agents]"""
+compiled reference on the host cores.  usage: python tests/checks/bench_qprsdr.py [agents]"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from bidinet_b200 import Engine, config as cf  # noqa: E402
 from oracle.pyoracle import RefHierarchy, have_ref, OracleHierarchy  # noqa: E402

@@ -2,10 +2,10 @@
 """One-off parity sweep on the GPU over many more random geometries than the test suite holds
 (tests/util.random_case: all five variants, 1-3 layers, grids 1-20 wide, radii 0 to wider than the grid,
 3-16-cell columns): every state array after each of 6 steps against the oracle, default engine path.
-usage: python tools/random_sweep.py first_seed last_seed max_seconds"""
+usage: python tests/checks/random_sweep.py first_seed last_seed max_seconds"""
 import sys, time
 import os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
 import numpy as np
 from bidinet_b200 import Engine, config as cf

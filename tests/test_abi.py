@@ -62,3 +62,8 @@ def test_product_does_not_touch_the_oracle():
         p = os.path.join(ROOT, "include", f)
         if os.path.isfile(p):
             assert "oracle/" not in open(p).read()
+    # developer tools outside tests/ may not run the oracle either (checker scripts live in tests/checks/)
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            src = open(os.path.join(ROOT, "tools", f)).read()
+            assert "import oracle" not in src and "from oracle" not in src, f
