@@ -367,6 +367,7 @@ def main():
         k, v = kv.split("=")
         eng.set_option(k, int(v))
     eng.init_random(seed_base_for(rank, A))  # global agent g <- std::mt19937(1234 + g)
+    eng.set_noise_stream(0x5DEECE66D, rank * A)  # every global agent explores on its own noise stream
     n_in = eng.n_in
     T = min(W + K, 64)
     frames = base_frames(T, A, rank * A, n_in)

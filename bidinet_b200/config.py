@@ -199,6 +199,14 @@ def config_c4(variant=KWINNERS):
     return make_config(variant, 128, 128, layers, r_infb=0 if variant == KWINNERS else 6)
 
 
+def config_videotest():
+    """VideoTest.cpp:52-65: sdr::IPredictiveRSDR, input 128x128, layers 32^2 -> 24^2 -> 16^2 (class defaults: every
+    radius 3), input feedback radius 16 -> 9.8 M input-feedback connections; free-runs on its own predictions with
+    learn = false (VideoTest.cpp:180-186)."""
+    layers = [dict(width=32, height=32), dict(width=24, height=24), dict(width=16, height=16)]
+    return make_config(ITERATIVE, 128, 128, layers, r_infb=16)
+
+
 def config_c5(size=1024, variant=KWINNERS):
     """C5: one same-size layer (size x size over size x size), every radius 6."""
     r = dict(r_ff=6, r_rec=6, r_lat=6, r_pred=6, r_fb=6)

@@ -119,6 +119,7 @@ struct bidi_engine {
   float* d_blob = nullptr; float* d_in0 = nullptr; float* d_pred = nullptr;
   float* d_rewards = nullptr; float* d_noise_u = nullptr; float* d_noise_v = nullptr; float* d_col_actions = nullptr;
   float* d_frames = nullptr; float* d_frame_rewards = nullptr; int n_frames = 0;
+  float* d_frame_noise_u = nullptr; float* d_frame_noise_v = nullptr; int n_noise_frames = 0;  // bidi_load_frame_noise
   int* d_tables = nullptr; LayerDev* d_layers = nullptr;
   long long device_bytes = 0;
   // pinned staging
@@ -127,7 +128,6 @@ struct bidi_engine {
   cudaStream_t side = nullptr;                     // second branch of the step graph (coder learning, see record_step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_learn = true;
-  bool early_learn = false;                        // option: a fused layer's learning starts right after its own up pass (measured slower, see DESIGN)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_in = nullptr;                     // the last bidi_set_inputs' host->device copy has read the host buffer
   // one graph per value of the learn flag
@@ -137,6 +137,7 @@ struct bidi_engine {
   int gen_per_agent = 0; float* d_gen = nullptr; float* d_gen_scale = nullptr; float* h_gen = nullptr;
   long long launches = 0;
   unsigned long long step_index = 0, noise_seed = 0x5DEECE66DULL;
+  long long first_agent = 0;                       // global index of agent 0 (bidi_set_noise_stream)
   // feedback taps (bidi_set_feedback)
   int fb_n = 0; int* d_fb_src = nullptr; int* d_fb_dst = nullptr; float fb_scale = 0, fb_bias = 0, fb_std = 0; int fb_reward = 0;
   // kernel profiling (bidi_profile_select): external events around the launches of one kernel
@@ -665,8 +666,6 @@ void record_step(Recorder& R, bool learn) {
     else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
   };
   const bool fork_learn = learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing;
-  bool early_learn = fork_learn && h->early_learn;
-  for (int l = 0; l < L; l++) early_learn = early_learn && h->coder_cta[l] && !h->force_phase_kernels;
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
     if (h->coder_cta[l] && !h->force_phase_kernels && !R.collect) { // whole up pass of the layer in one launch
@@ -691,13 +690,6 @@ void record_step(Recorder& R, bool learn) {
       }
       R.after("coder");
       R.kernels++;
-      if (early_learn) {  // this layer's learning starts now, beside the next layer's up pass (which moves no HBM traffic)
-        cudaEventRecord(h->ev_fork, h->stream);
-        cudaStreamWaitEvent(h->side, h->ev_fork, 0);
-        R.st = h->side;
-        record_learn_layer(l);
-        R.st = nullptr;
-      }
       continue;
     }
     const LayerDev& Y = ly[l];
@@ -741,9 +733,7 @@ void record_step(Recorder& R, bool learn) {
   auto record_learn = [&]() {
     for (int l = 0; l < L; l++) record_learn_layer(l);
   };
-  if (early_learn) {
-    cudaEventRecord(h->ev_join, h->side);
-  } else if (fork_learn) {
+  if (fork_learn) {
     cudaEventRecord(h->ev_fork, h->stream);
     cudaStreamWaitEvent(h->side, h->ev_fork, 0);
     R.st = h->side;
@@ -834,7 +824,8 @@ int ensure_coop(bidi_engine* h, bool learn) {
   h->coop_smem = smem;
   h->coop_grid = std::max(1, std::min(per_sm * sms, std::max(R.collect_blocks, h->coop_grid)));
   if (cudaMalloc(&h->d_coop_ops[learn], sizeof(bidi::CoopOp) * ops.size()) != cudaSuccess) { cudaGetLastError(); h->coop_mode = 0; return 0; }
-  cudaMemcpy(h->d_coop_ops[learn], ops.data(), sizeof(bidi::CoopOp) * ops.size(), cudaMemcpyHostToDevice);
+  if (cudaMemcpyAsync(h->d_coop_ops[learn], ops.data(), sizeof(bidi::CoopOp) * ops.size(), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
+      cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); coop_release(h); h->coop_mode = 0; return 0; }
   h->coop_n[learn] = (int)ops.size();
   return 1;
 }
@@ -853,13 +844,13 @@ int run_step(bidi_engine* h, bool learn, bool device_noise) {
     return BIDI_OK;
   }
   if (h->qnet && device_noise) {
-    bidi::k_noise_q<<<grid_for((long long)h->A * h->q_half, kBlock), kBlock, 0, h->stream>>>(h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index);
+    bidi::k_noise_q<<<grid_for((long long)h->A * h->q_half, kBlock), kBlock, 0, h->stream>>>(h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index, h->first_agent);
     h->launches++;
   }
   if (h->cfg.variant == BIDI_NEO_AGENT && device_noise) {
     // the step counter changes every call, so this launch stays outside the graph
     bidi::k_noise<<<grid_for((long long)h->A * h->ncol, kBlock), kBlock, 0, h->stream>>>(
-        h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index);
+        h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index, h->first_agent);
     h->launches++;
   }
   rc = ensure_graph(h, learn ? 1 : 0);
@@ -892,6 +883,7 @@ void bidi_destroy(bidi_engine* h) {
   for (auto& g : h->graphs) if (g) cudaGraphExecDestroy(g);
   cudaFree(h->d_blob); cudaFree(h->d_in0); cudaFree(h->d_pred); cudaFree(h->d_rewards); cudaFree(h->d_noise_u);
   cudaFree(h->d_noise_v); cudaFree(h->d_col_actions); cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
+  cudaFree(h->d_frame_noise_u); cudaFree(h->d_frame_noise_v);
   cudaFree(h->d_tables); cudaFree(h->d_layers); cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
   cudaFree(h->d_qmask); cudaFree(h->d_qtables); cudaFree(h->d_gen); cudaFree(h->d_gen_scale); cudaFreeHost(h->h_gen);
   for (auto& e : h->profile_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -1209,7 +1201,8 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     mask.reserve(tot);
     for (int l = 0; l < L; l++) for (char c : h->q_keep[l]) mask.push_back(c ? 1.0f : 0.0f);
     CU_CREATE(cudaMalloc(&h->d_qmask, sizeof(float) * std::max<size_t>(1, tot)));
-    CU_CREATE(cudaMemcpy(h->d_qmask, mask.data(), sizeof(float) * tot, cudaMemcpyHostToDevice));
+    CU_CREATE(cudaMemcpyAsync(h->d_qmask, mask.data(), sizeof(float) * tot, cudaMemcpyHostToDevice, h->stream));
+    CU_CREATE(cudaStreamSynchronize(h->stream));
     size_t off = 0;
     for (int l = 0; l < L; l++) { h->layers[l].q_mask = h->d_qmask + off; off += h->q_keep[l].size(); }
     h->device_bytes += (long long)(sizeof(float) * tot);
@@ -1233,7 +1226,8 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     std::vector<int> tab(h->q_act_index);
     tab.insert(tab.end(), h->q_a_input.begin(), h->q_a_input.end());
     CU_CREATE(cudaMalloc(&h->d_qtables, sizeof(int) * tab.size()));
-    CU_CREATE(cudaMemcpy(h->d_qtables, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
+    CU_CREATE(cudaMemcpyAsync(h->d_qtables, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, h->stream));
+    CU_CREATE(cudaStreamSynchronize(h->stream));
     P.q_act_index = h->d_qtables; P.q_a_input = h->d_qtables + h->n_in;
   }
   {  // constants the packed-pair arithmetic must not see at compile time (bidi_columns.cuh)
@@ -1422,6 +1416,7 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
   CU(cudaSetDevice(h->device));
   int rc = mirror_release(h);
   if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));  // a queued step may still be reading or writing the agents being re-seeded
   const int L = h->L, V = h->cfg.variant;
   const bidi_config& g = h->cfg;
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -1490,13 +1485,20 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
   std::vector<cudaError_t> cuerr(nthreads, cudaSuccess);
   for (int t = 0; t < nthreads; t++)
     pool.emplace_back([&, t]() {
+      // every worker uploads on its own stream and waits for each copy to land before it reuses the image; the engine's
+      // stream is idle (synchronised above) and nothing is queued on it before all workers have joined
       cudaSetDevice(h->device);
+      cudaStream_t up = nullptr;
+      cudaError_t e = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+      if (e != cudaSuccess) { cuerr[t] = e; return; }
       images[t].resize((size_t)h->stride);
       for (int a = first + t; a < first + count; a += nthreads) {
         fill_agent(images[t], seed_base + (unsigned)a);
-        cudaError_t e = cudaMemcpy(h->d_blob + (long long)a * h->stride, images[t].data(), sizeof(float) * h->stride, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { cuerr[t] = e; return; }
+        e = cudaMemcpyAsync(h->d_blob + (long long)a * h->stride, images[t].data(), sizeof(float) * h->stride, cudaMemcpyHostToDevice, up);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(up);
+        if (e != cudaSuccess) { cuerr[t] = e; break; }
       }
+      cudaStreamDestroy(up);
     });
   for (auto& t : pool) t.join();
   for (auto e : cuerr) if (e != cudaSuccess) return fail(h, BIDI_ECUDA, std::string("bidi_init_random upload: ") + cudaGetErrorString(e));
@@ -1523,6 +1525,14 @@ int bidi_set_inputs(bidi_engine* h, const float* in) {
   if (in != h->h_in) memcpy(h->h_in, in, bytes);  // bidi_host_inputs: the caller wrote the pinned buffer itself
   CU(cudaMemcpyAsync(h->d_in0, h->h_in, bytes, cudaMemcpyHostToDevice, h->stream));
   CU(cudaEventRecord(h->ev_in, h->stream));
+  return BIDI_OK;
+}
+
+int bidi_get_inputs(bidi_engine* h, float* out) {
+  if (!h || !out) return fail(h, BIDI_EINVAL, "bidi_get_inputs: null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(out, h->d_in0, sizeof(float) * (size_t)h->A * h->n_in, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
   return BIDI_OK;
 }
 
@@ -1579,7 +1589,8 @@ int bidi_step_generate(bidi_engine* h, const float* normals, float noise) {
     memcpy(h->h_gen, normals, sizeof(float) * n);
     CU(cudaMemcpyAsync(h->d_gen, h->h_gen, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
   } else {
-    bidi::k_gen_normals<<<grid_for((long long)n, kBlock), kBlock, 0, h->stream>>>(h->d_gen, (long long)n, h->noise_seed ^ 0x6E6F697365ULL, h->step_index);
+    bidi::k_gen_normals<<<grid_for((long long)n, kBlock), kBlock, 0, h->stream>>>(h->d_gen, (long long)n, h->noise_seed ^ 0x6E6F697365ULL, h->step_index,
+                                                                                 h->first_agent * h->gen_per_agent);
     h->launches++;
   }
   h->h_gen[n] = noise;
@@ -1658,11 +1669,12 @@ int bidi_load_frames(bidi_engine* h, const float* frames, const float* rewards, 
   h->d_frames = nullptr; h->d_frame_rewards = nullptr; h->n_frames = 0;
   const size_t n = (size_t)n_frames * h->A * h->n_in;
   CU(cudaMalloc(&h->d_frames, sizeof(float) * n));
-  CU(cudaMemcpy(h->d_frames, frames, sizeof(float) * n, cudaMemcpyHostToDevice));
+  CU(cudaMemcpyAsync(h->d_frames, frames, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
   if (rewards) {
     CU(cudaMalloc(&h->d_frame_rewards, sizeof(float) * (size_t)n_frames * h->A));
-    CU(cudaMemcpy(h->d_frame_rewards, rewards, sizeof(float) * (size_t)n_frames * h->A, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(h->d_frame_rewards, rewards, sizeof(float) * (size_t)n_frames * h->A, cudaMemcpyHostToDevice, h->stream));
   }
+  CU(cudaStreamSynchronize(h->stream));
   h->n_frames = n_frames;
   return BIDI_OK;
 }
@@ -1678,10 +1690,51 @@ int bidi_step_frame(bidi_engine* h, int t, int learn) {
   if (h->fb_n > 0) {
     bidi::k_feedback<<<grid_for(h->A, kBlock), kBlock, 0, h->stream>>>(h->P, h->fb_n, h->d_fb_src, h->d_fb_dst, h->fb_scale, h->fb_bias,
                                                                       h->fb_std, h->noise_seed ^ 0xFEEDULL, h->step_index,
-                                                                      h->fb_reward ? h->d_rewards : nullptr);
+                                                                      h->first_agent, h->fb_reward ? h->d_rewards : nullptr);
     h->launches++;
   }
-  return run_step(h, learn != 0, h->cfg.variant == BIDI_NEO_AGENT || h->qnet);
+  bool device_noise = h->cfg.variant == BIDI_NEO_AGENT || h->qnet;
+  if (device_noise && h->n_noise_frames > 0) {  // the caller's draws (bidi_load_frame_noise) instead of the engine's generator
+    const size_t nn = (size_t)h->A * h->n_noise, fo = (size_t)(t % h->n_noise_frames) * nn;
+    CU(cudaMemcpyAsync(h->d_noise_u, h->d_frame_noise_u + fo, sizeof(float) * nn, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_noise_v, h->d_frame_noise_v + fo, sizeof(float) * nn, cudaMemcpyDeviceToDevice, h->stream));
+    device_noise = false;
+  }
+  return run_step(h, learn != 0, device_noise);
+}
+
+int bidi_load_frame_noise(bidi_engine* h, const float* noise_u, const float* noise_v, int n_frames) {
+  if (!h || n_frames < 0 || (n_frames > 0 && (!noise_u || !noise_v))) return fail(h, BIDI_EINVAL, "bidi_load_frame_noise: bad argument");
+  if (n_frames > 0 && h->n_noise == 0) return fail(h, BIDI_EINVAL, "bidi_load_frame_noise: this variant draws no exploration noise");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_frame_noise_u); cudaFree(h->d_frame_noise_v);
+  h->d_frame_noise_u = h->d_frame_noise_v = nullptr; h->n_noise_frames = 0;
+  if (n_frames == 0) return BIDI_OK;
+  const size_t n = (size_t)n_frames * h->A * h->n_noise;
+  CU(cudaMalloc(&h->d_frame_noise_u, sizeof(float) * n));
+  CU(cudaMalloc(&h->d_frame_noise_v, sizeof(float) * n));
+  CU(cudaMemcpyAsync(h->d_frame_noise_u, noise_u, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_frame_noise_v, noise_v, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->n_noise_frames = n_frames;
+  return BIDI_OK;
+}
+
+int bidi_set_noise_stream(bidi_engine* h, unsigned long long seed, long long first_global_agent) {
+  if (!h || first_global_agent < 0) return fail(h, BIDI_EINVAL, "bidi_set_noise_stream: bad argument");
+  h->noise_seed = seed; h->first_agent = first_global_agent;
+  return BIDI_OK;
+}
+
+int bidi_get_noise(bidi_engine* h, float* noise_u, float* noise_v) {
+  if (!h || h->n_noise == 0) return fail(h, BIDI_EINVAL, "bidi_get_noise: this variant draws no exploration noise");
+  CU(cudaSetDevice(h->device));
+  const size_t bytes = sizeof(float) * (size_t)h->A * h->n_noise;
+  if (noise_u) CU(cudaMemcpyAsync(noise_u, h->d_noise_u, bytes, cudaMemcpyDeviceToHost, h->stream));
+  if (noise_v) CU(cudaMemcpyAsync(noise_v, h->d_noise_v, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BIDI_OK;
 }
 
 int bidi_set_feedback(bidi_engine* h, int n, const int* src, const int* dst, float scale, float bias, float noise_std,
@@ -1696,8 +1749,9 @@ int bidi_set_feedback(bidi_engine* h, int n, const int* src, const int* dst, flo
   if (n > 0) {
     CU(cudaMalloc(&h->d_fb_src, sizeof(int) * n));
     CU(cudaMalloc(&h->d_fb_dst, sizeof(int) * n));
-    CU(cudaMemcpy(h->d_fb_src, src, sizeof(int) * n, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(h->d_fb_dst, dst, sizeof(int) * n, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(h->d_fb_src, src, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_fb_dst, dst, sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
   }
   h->fb_n = n; h->fb_scale = scale; h->fb_bias = bias; h->fb_std = noise_std; h->fb_reward = reward_from_actions;
   return BIDI_OK;
@@ -1729,7 +1783,6 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   }
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "overlap_learn") h->overlap_learn = value != 0;
-  else if (std::string(name) == "early_learn") h->early_learn = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
       size_t smem = 0;
@@ -1754,7 +1807,11 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
 // dump, deep/FERL.cpp:330-407).  File = header + configuration + the device arrays verbatim (the
 // engine's own HBM layout), so saving and loading are plain copies.
 namespace {
-struct SnapHeader { char magic[8]; int version, config_bytes, desc_bytes, n_layers, n_agents, n_in; long long stride; unsigned long long step_index; };
+struct SnapHeader {
+  char magic[8]; int version, config_bytes, desc_bytes, n_layers, n_agents, n_in; long long stride;
+  unsigned long long step_index, noise_seed; long long first_agent;
+};
+constexpr int kSnapVersion = 2;
 const char kSnapMagic[8] = {'B', 'I', 'D', 'I', 'S', 'N', 'A', 'P'};
 }
 
@@ -1769,8 +1826,9 @@ int bidi_save_snapshot(bidi_engine* h, const char* path) {
   SnapHeader hd;
   memset(&hd, 0, sizeof(hd));
   memcpy(hd.magic, kSnapMagic, 8);
-  hd.version = 1; hd.config_bytes = (int)sizeof(bidi_config); hd.desc_bytes = (int)sizeof(bidi_layer_desc);
+  hd.version = kSnapVersion; hd.config_bytes = (int)sizeof(bidi_config); hd.desc_bytes = (int)sizeof(bidi_layer_desc);
   hd.n_layers = h->L; hd.n_agents = h->A; hd.n_in = h->n_in; hd.stride = h->stride; hd.step_index = h->step_index;
+  hd.noise_seed = h->noise_seed; hd.first_agent = h->first_agent;
   bidi_config cfg = h->cfg;
   if (h->qnet) cfg.variant = BIDI_QPRSDR;
   bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && fwrite(&cfg, sizeof(cfg), 1, f) == 1 &&
@@ -1781,7 +1839,8 @@ int bidi_save_snapshot(bidi_engine* h, const char* path) {
     for (size_t o = 0; o < n && ok; o += chunk) {
       const size_t m = std::min(chunk, n - o);
       buf.resize(m);
-      if (cudaMemcpy(buf.data(), dev + o, sizeof(float) * m, cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; break; }
+      if (cudaMemcpyAsync(buf.data(), dev + o, sizeof(float) * m, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess ||
+          cudaStreamSynchronize(h->stream) != cudaSuccess) { ok = false; break; }
       ok = fwrite(buf.data(), sizeof(float), m, f) == m;
     }
   };
@@ -1806,7 +1865,7 @@ int bidi_load_snapshot(bidi_engine* h, const char* path) {
   std::vector<bidi_layer_desc> ld((size_t)h->L);
   bidi_config mine = h->cfg;
   if (h->qnet) mine.variant = BIDI_QPRSDR;
-  bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kSnapMagic, 8) == 0 && hd.version == 1 &&
+  bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kSnapMagic, 8) == 0 && hd.version == kSnapVersion &&
             hd.config_bytes == (int)sizeof(bidi_config) && hd.desc_bytes == (int)sizeof(bidi_layer_desc) && hd.n_layers == h->L &&
             hd.n_agents == h->A && hd.n_in == h->n_in && hd.stride == h->stride && fread(&cfg, sizeof(cfg), 1, f) == 1 &&
             fread(ld.data(), sizeof(bidi_layer_desc), (size_t)h->L, f) == (size_t)h->L && memcmp(&cfg, &mine, sizeof(cfg)) == 0 &&
@@ -1818,7 +1877,9 @@ int bidi_load_snapshot(bidi_engine* h, const char* path) {
     for (size_t o = 0; o < n && ok; o += chunk) {
       const size_t m = std::min(chunk, n - o);
       buf.resize(m);
-      ok = fread(buf.data(), sizeof(float), m, f) == m && cudaMemcpy(dev + o, buf.data(), sizeof(float) * m, cudaMemcpyHostToDevice) == cudaSuccess;
+      ok = fread(buf.data(), sizeof(float), m, f) == m &&
+           cudaMemcpyAsync(dev + o, buf.data(), sizeof(float) * m, cudaMemcpyHostToDevice, h->stream) == cudaSuccess &&
+           cudaStreamSynchronize(h->stream) == cudaSuccess;  // on the engine's stream: ordered before the next step
     }
   };
   fill(h->d_in0, (size_t)h->A * h->n_in);
@@ -1827,7 +1888,7 @@ int bidi_load_snapshot(bidi_engine* h, const char* path) {
   fclose(f);
   cudaGetLastError();
   if (!ok) return fail(h, BIDI_EINVAL, std::string("bidi_load_snapshot: ") + path + " is truncated");
-  h->step_index = hd.step_index;
+  h->step_index = hd.step_index; h->noise_seed = hd.noise_seed; h->first_agent = hd.first_agent;
   return BIDI_OK;
 }
 

@@ -591,10 +591,12 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 }
 __device__ __forceinline__ float u01(unsigned long long h) { return (float)(h >> 40) * (1.0f / 16777216.0f); }
 
-__global__ void k_noise(EngineDev P, float* u, float* v, unsigned long long seed, unsigned long long step) {
+// `first`: global index of this engine's agent 0 (bidi_set_noise_stream), so that shards of one population never share a stream
+__global__ void k_noise(EngineDev P, float* u, float* v, unsigned long long seed, unsigned long long step, long long first) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n = (long long)P.A * P.ncol;
   if (gid >= n) return;
+  const unsigned long long key0 = (unsigned long long)(gid + first * P.ncol) * 3;
   const int c = (int)(gid % P.ncol);
   float std = 0.0f, brk = 0.0f;
   for (int l = 0; l <= P.L; l++) {
@@ -602,7 +604,7 @@ __global__ void k_noise(EngineDev P, float* u, float* v, unsigned long long seed
     if (c >= C.noise_base && c < C.noise_base + C.n) { std = C.expl_std; brk = C.expl_break; }
   }
   for (int k = 0; k < 3; k++) {
-    unsigned long long h = mix64(seed ^ mix64(step * 0x100000001B3ULL + (unsigned long long)gid * 3 + k));
+    unsigned long long h = mix64(seed ^ mix64(step * 0x100000001B3ULL + key0 + k));
     const float uu = u01(h);
     h = mix64(h);
     float vv;
@@ -617,10 +619,10 @@ __global__ void k_noise(EngineDev P, float* u, float* v, unsigned long long seed
 }
 
 // N(0,1) draws for simStepGenerate when the caller supplies none (counter-based, Box-Muller)
-__global__ void k_gen_normals(float* out, long long n, unsigned long long seed, unsigned long long step) {
+__global__ void k_gen_normals(float* out, long long n, unsigned long long seed, unsigned long long step, long long first_key) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= n) return;
-  const unsigned long long h = mix64(seed ^ mix64(step * 0x100000001B3ULL + (unsigned long long)gid));
+  const unsigned long long h = mix64(seed ^ mix64(step * 0x100000001B3ULL + (unsigned long long)(gid + first_key)));
   const float r1 = fmaxf(u01(h), 5.9604645e-8f), r2 = u01(mix64(h));
   out[gid] = sqrtf(-2.0f * logf(r1)) * cospif(2.0f * r2);
 }
@@ -630,7 +632,7 @@ __global__ void k_gen_normals(float* out, long long n, unsigned long long seed, 
 // if asked, reward = mean(clamp01(prediction[src]*scale + bias)) - 0.5, the
 // headless stand-in for the Box2D body velocity.
 __global__ void k_feedback(EngineDev P, int n, const int* __restrict__ src, const int* __restrict__ dst, float scale,
-                           float bias, float std, unsigned long long seed, unsigned long long step, float* rewards) {
+                           float bias, float std, unsigned long long seed, unsigned long long step, long long first, float* rewards) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= P.A) return;
   const float* pred = P.pred_out + (long long)a * P.n_in;
@@ -639,7 +641,7 @@ __global__ void k_feedback(EngineDev P, int n, const int* __restrict__ src, cons
   for (int k = 0; k < n; k++) {
     const float act = pred[src[k]] * scale + bias;
     sum += bidi_clamp01(act);
-    unsigned long long h = mix64(seed ^ mix64(step * 0x9E3779B1ULL + (unsigned long long)a * n + k));
+    unsigned long long h = mix64(seed ^ mix64(step * 0x9E3779B1ULL + (unsigned long long)(a + first) * n + k));
     const float r1 = fmaxf(u01(h), 5.9604645e-8f), r2 = u01(mix64(h));
     in[dst[k]] = bidi_clamp01(act + sqrtf(-2.0f * logf(r1)) * cospif(2.0f * r2) * std);
   }

@@ -140,10 +140,10 @@ __global__ void __launch_bounds__(256) k_qnet(EngineDev P, int learn) {
 }
 
 // exploration draws when the caller supplies none (counter-based, like k_noise)
-__global__ void k_noise_q(EngineDev P, float* u, float* v, unsigned long long seed, unsigned long long step) {
+__global__ void k_noise_q(EngineDev P, float* u, float* v, unsigned long long seed, unsigned long long step, long long first) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)P.A * P.q_half) return;
-  unsigned long long h = mix64(seed ^ mix64(step * 0x100000001B3ULL + (unsigned long long)gid));
+  unsigned long long h = mix64(seed ^ mix64(step * 0x100000001B3ULL + (unsigned long long)(gid + first * P.q_half)));
   const float uu = u01(h);
   h = mix64(h);
   float vv;

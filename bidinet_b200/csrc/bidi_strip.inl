@@ -540,7 +540,8 @@ int bidi_strip_link_ipc(bidi_engine* h, const void* handles) {
     using T = typename std::remove_reference<decltype(v)>::type::value_type;
     cudaError_t e = cudaMalloc(dst, sizeof(T) * std::max<size_t>(1, v.size()));
     if (e != cudaSuccess) return e;
-    return cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+    e = cudaMemcpyAsync(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, h->stream);  // ordered before the next step
+    return e != cudaSuccess ? e : cudaStreamSynchronize(h->stream);
   };
   CU(upload(&h->d_peer_blob, blobs));
   CU(upload(&h->d_peer_flags, flags));

@@ -36,6 +36,7 @@ ABI = {
     "bidi_set_array": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _FP, C.c_longlong]),
     "bidi_get_array": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _FP, C.c_longlong]),
     "bidi_set_inputs": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_get_inputs": (C.c_int, [C.c_void_p, _FP]),
     "bidi_host_inputs": (_FP, [C.c_void_p]),
     "bidi_host_predictions": (_FP, [C.c_void_p]),
     "bidi_wait_inputs": (C.c_int, [C.c_void_p]),
@@ -46,6 +47,9 @@ ABI = {
     "bidi_sync": (C.c_int, [C.c_void_p]),
     "bidi_load_frames": (C.c_int, [C.c_void_p, _FP, _FP, C.c_int]),
     "bidi_step_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bidi_load_frame_noise": (C.c_int, [C.c_void_p, _FP, _FP, C.c_int]),
+    "bidi_set_noise_stream": (C.c_int, [C.c_void_p, C.c_ulonglong, C.c_longlong]),
+    "bidi_get_noise": (C.c_int, [C.c_void_p, _FP, _FP]),
     "bidi_set_feedback": (C.c_int, [C.c_void_p, C.c_int, _IP, _IP, C.c_float, C.c_float, C.c_float, C.c_int]),
     "bidi_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "bidi_save_snapshot": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -209,6 +213,12 @@ class Engine:
         self._check(self.lib.bidi_get_predictions(self.h, _fptr(out)), "bidi_get_predictions")
         return out
 
+    def get_inputs(self):
+        """[agent][index]: the layer-0 inputs as the last step consumed them."""
+        out = np.empty((self.n_agents, self.n_in), dtype=np.float32)
+        self._check(self.lib.bidi_get_inputs(self.h, _fptr(out)), "bidi_get_inputs")
+        return out
+
     def host_inputs(self):
         """The engine's page-locked input buffer as an [agent][index] array: fill it, pass it to set_inputs (no
         staging copy), and do not rewrite it before wait_inputs() returns."""
@@ -246,6 +256,26 @@ class Engine:
 
     def step_frame(self, t, learn=True):
         self._check(self.lib.bidi_step_frame(self.h, int(t), int(bool(learn))), "bidi_step_frame")
+
+    def load_frame_noise(self, noise_u, noise_v):
+        """[T][agent][n_noise] exploration draws for step_frame (frame t % T); None unloads (engine generator again)."""
+        if noise_u is None:
+            self._check(self.lib.bidi_load_frame_noise(self.h, None, None, 0), "bidi_load_frame_noise")
+            return
+        u = np.ascontiguousarray(noise_u, dtype=np.float32).reshape(-1, self.n_agents, self.n_noise)
+        v = np.ascontiguousarray(noise_v, dtype=np.float32).reshape(-1, self.n_agents, self.n_noise)
+        assert u.shape == v.shape
+        self._check(self.lib.bidi_load_frame_noise(self.h, _fptr(u), _fptr(v), u.shape[0]), "bidi_load_frame_noise")
+
+    def set_noise_stream(self, seed, first_global_agent=0):
+        self._check(self.lib.bidi_set_noise_stream(self.h, int(seed), int(first_global_agent)), "bidi_set_noise_stream")
+
+    def get_noise(self):
+        """(u, v), [agent][n_noise] each: the exploration draws the last step consumed."""
+        u = np.zeros((self.n_agents, self.n_noise), dtype=np.float32)
+        v = np.zeros((self.n_agents, self.n_noise), dtype=np.float32)
+        self._check(self.lib.bidi_get_noise(self.h, _fptr(u), _fptr(v)), "bidi_get_noise")
+        return u, v
 
     def set_feedback(self, src, dst, scale=0.5, bias=0.5, noise_std=0.05, reward_from_actions=True):
         s = np.ascontiguousarray(src, dtype=np.int32)
@@ -387,14 +417,6 @@ class StripGroup:
     def sync(self):
         for e in self.parts:
             e.sync()
-
-    def step_generate(self, noise, normals=None):
-        """neo::PredictiveHierarchy::simStepGenerate; normals: [agent][bidi_num_generate_noise] N(0,1) draws or None."""
-        z = None
-        if normals is not None:
-            z = np.ascontiguousarray(normals, dtype=np.float32)
-            assert z.size == self.n_agents * self.lib.bidi_num_generate_noise(self.h)
-        self._check(self.lib.bidi_step_generate(self.h, None if z is None else _fptr(z), float(noise)), "bidi_step_generate")
 
     def get_predictions(self):
         return assemble_rows([e.get_predictions() for e in self.parts], [e.spans["OWN_VIS"] for e in self.parts],

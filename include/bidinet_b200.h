@@ -191,6 +191,8 @@ int bidi_set_inputs(bidi_engine* h, const float* in);
  * be rewritten once bidi_wait_inputs returns (the host->device copy has read it); the prediction
  * buffer is valid until the next bidi_get_predictions.
  */
+/* The layer-0 inputs as the last step consumed them (after bidi_set_feedback's taps), out[agent][index], host. */
+int bidi_get_inputs(bidi_engine* h, float* out);
 float* bidi_host_inputs(bidi_engine* h);
 const float* bidi_host_predictions(bidi_engine* h);
 int bidi_wait_inputs(bidi_engine* h);
@@ -257,6 +259,22 @@ int bidi_sync(bidi_engine* h);
  */
 int bidi_load_frames(bidi_engine* h, const float* frames, const float* rewards, int n_frames);
 int bidi_step_frame(bidi_engine* h, int t, int learn);
+/*
+ * Exploration draws for device-resident stepping: noise_u / noise_v [n_frames][n_agents][bidi_num_noise],
+ * the same values bidi_step takes per call (neo/Column.cpp:126-131, sdr/QPRSDR.cpp:205-213).  Once loaded,
+ * bidi_step_frame(t) uses frame t % n_frames of them instead of the engine's own generator, so that the
+ * device-resident path can be held bit for bit against the host-driven one.  n_frames = 0 unloads.
+ */
+int bidi_load_frame_noise(bidi_engine* h, const float* noise_u, const float* noise_v, int n_frames);
+/*
+ * The engine's own counter-based generator (exploration, simStepGenerate and feedback noise when the caller
+ * supplies none) is keyed by (seed, step, first_global_agent + local agent, ...): engines that hold different
+ * shards of one population pass their first global agent index so that no two agents share a noise stream.
+ * Part of the snapshot.
+ */
+int bidi_set_noise_stream(bidi_engine* h, unsigned long long seed, long long first_global_agent);
+/* The exploration draws the last step consumed, [n_agents][bidi_num_noise] each (either may be NULL). */
+int bidi_get_noise(bidi_engine* h, float* noise_u, float* noise_v);
 
 /*
  * The caller's half of the RunnerMain loop for device-resident runs

@@ -2,11 +2,12 @@
 
   C3  4096 neo::Agent hierarchies in one engine: sampled agents equal their own single-agent
       oracle runs bit for bit (agents never interact, so the rest of the batch is free to differ)
-  C4  the large six-layer hierarchy (input 128x128, every radius 6): first steps of the k-winners
-      and the iterative variant against the oracle, every state array equal
-  C5  the largest single layer the oracle's reference (16-bit indices) can hold, 256x256: the 2-D
-      grid-tile kernels against the oracle; and a size-independent property at 1024x1024 --
-      splitting the layer into row strips changes nothing
+  C4  the large six-layer hierarchy (input 128x128, every radius 6): 50 steps of the k-winners and 5
+      of the iterative variant against the oracle, every state array equal; the VideoTest
+      configuration (input feedback radius 16) trained and free-run
+  C5  the largest single layer the reference (16-bit indices) can hold, 256x256, and the full
+      1024x1024 against the oracle; and a size-independent property at 1024x1024 -- splitting the
+      layer into row strips changes nothing
 All comparisons are exact (np.array_equal)."""
 import numpy as np
 import pytest
@@ -48,8 +49,11 @@ def _bars(t, n=128, period=16):
     return (((x + t) % period) < period // 2).astype(np.float32).ravel()
 
 
-@pytest.mark.parametrize("variant,steps", [(cf.KWINNERS, 4), (cf.ITERATIVE, 2)])
-def test_c4_first_steps(variant, steps):
+@pytest.mark.parametrize("variant,steps", [(cf.KWINNERS, 50), (cf.ITERATIVE, 5)])
+def test_c4_steps(variant, steps):
+    """C4 at full size: 50 steps of the k-winners variant (the winners' learning rule and the prediction delta rule
+    have long since left their initial regime), 5 of the iterative one (35 coder iterations each); predictions
+    after every step, every state array at the end."""
     cfg, ld = cf.config_c4(variant)
     orc = OracleHierarchy(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1, seed=1234)   # the engine replays createRandom itself
@@ -60,6 +64,41 @@ def test_c4_first_steps(variant, steps):
         eng.set_inputs(x)
         orc.step()
         eng.step()
+        assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0]), t
+    bad = diff_states(orc.state(), eng.state())
+    assert bad == [], bad[:6]
+    if variant == cf.KWINNERS:   # the run learned: weights of winners moved away from their initial values
+        fresh = OracleHierarchy(cfg, ld, 1234)
+        assert not np.array_equal(fresh.get_array("FF_W", 0), orc.get_array("FF_W", 0))
+        assert not np.array_equal(fresh.get_array("PRED_W", 2), orc.get_array("PRED_W", 2))
+
+
+def test_videotest_configuration_trains_then_free_runs():
+    """VideoTest.cpp:52-65,136-139,180-186: in 128x128, layers 32^2/24^2/16^2, input feedback radius 16 (33x33
+    windows into layer 0 for every one of the 16384 input nodes); a few training steps, then the free run on its
+    own predictions with learn = false -- fed back through setInput(x, y), which indexes with the HIDDEN width
+    (sdr/IPredictiveRSDR.h:115-117: the caller's loop writes input[x + 32*y], x outer / y inner)."""
+    cfg, ld = cf.config_videotest()
+    orc = OracleHierarchy(cfg, ld, 1234)
+    eng = Engine(cfg, ld, n_agents=1, seed=1234)
+    assert eng.array_len("FB_W", 3) == 9821956           # SURVEY section 8: N_infb of the VideoTest row
+    assert diff_states(orc.state(), eng.state()) == []
+    hid_w = ld[0].width
+    xs, ys = np.meshgrid(np.arange(128), np.arange(128), indexing="ij")   # x outer, y inner
+    dst, src = (xs + hid_w * ys).ravel(), (xs + 128 * ys).ravel()
+    x = None
+    for t in range(8):
+        train = t < 4
+        if train:
+            x = _bars(t)
+        else:               # prsdr.setInput(x, y, prsdr.getPrediction(x, y)) for every x, y: later writes win
+            pred = orc.get_predictions()
+            x = x.copy()
+            x[dst] = pred[src]
+        orc.set_inputs(x)
+        eng.set_inputs(x)
+        orc.step(0.0, train)
+        eng.step(learn=train)
         assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0]), t
     bad = diff_states(orc.state(), eng.state())
     assert bad == [], bad[:6]
@@ -85,6 +124,29 @@ def test_c5_256_grid_kernels():
                 ("HID_THRESHOLD", 0)):
         assert np.array_equal(orc.get_array(*key), eng.get_array(*key)), key
     assert orc.get_array("HID_STATE", 0).sum() > 100  # winners existed, so the learning rule ran
+
+
+def test_c5_1024_against_the_oracle():
+    """C5 at its full size, unsplit, against the oracle (the reference itself cannot index this layer: 16-bit
+    connection indices; the oracle is the same restatement that is pinned to the reference at every size the
+    reference can hold).  Two steps, learning on: unit planes and every weight list equal."""
+    n = 1024
+    cfg, ld = cf.config_c5(n)
+    orc = OracleHierarchy(cfg, ld, 1234)
+    eng = Engine(cfg, ld, n_agents=1, seed=1234)
+    for t in range(2):
+        x = _sparse(t, n)
+        orc.set_inputs(x)
+        eng.set_inputs(x)
+        orc.step()
+        eng.step()
+        assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0]), t
+    for key in (("HID_STATE", 0), ("HID_ACTIVATION", 0), ("VIS_RECON", 0), ("HID_RECON", 0), ("P_STATE", 0), ("P_ACTIVATION", 0),
+                ("P_BASELINE", 0), ("HID_THRESHOLD", 0), ("FF_W", 0), ("REC_W", 0), ("PRED_W", 0)):
+        assert np.array_equal(orc.get_array(*key), eng.get_array(*key)), key
+    assert orc.get_array("HID_STATE", 0).sum() > 1000
+    eng.close()
+    orc.close()
 
 
 def test_c5_full_size_split_equals_unsplit():

@@ -86,6 +86,61 @@ def test_free_running_parity(case, path):
         assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0])
 
 
+@pytest.mark.parametrize("path", ["default", "coop", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
+@pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
+def test_batched_free_running_parity(case, path):
+    """Three agents in one engine, every variant on every engine path: each agent against its OWN oracle (own
+    weights, own inputs, own reward) after every step -- the agent decomposition of the tile kernels (tiles_of),
+    the 2-D grid tiles, the Q network's one-CTA-per-agent launch, the cooperative interpreter and the pitched copy
+    of bidi_get_actions.  The cooperative path must really have been taken: one launch per step."""
+    name, cfg, ld, frame, reward = case
+    A, steps = 3, 10
+    eng = Engine(cfg, ld, n_agents=A, seed=1234)
+    orcs = [OracleHierarchy(cfg, ld, 1234 + a) for a in range(A)]
+    if path == "coop":
+        if cfg.variant == cf.NEO_AGENT:
+            pytest.skip("no columns in the cooperative step")
+        eng.set_option("coop_step", True)
+    if path == "fused_general":
+        eng.set_option("dense_coder", False)
+    elif path not in ("default", "coop"):
+        eng.set_option("force_phase_kernels", True)
+    if path == "per_phase_threads":
+        eng.set_option("tile_kernels", False)
+        eng.set_option("grid_kernels", 0)
+    if path == "per_phase_grid":
+        if cfg.variant == cf.NEO_AGENT:
+            pytest.skip("no grid kernels for the column hierarchy")
+        eng.set_option("grid_kernels", 2)
+    for a in range(A):
+        assert diff_states(orcs[a].state(), eng.state(agent=a)) == [], a
+    for t in range(steps):
+        x = np.stack([frame(t + 3 * a) for a in range(A)])
+        r = np.array([reward(t + a) for a in range(A)], np.float32)
+        noise = None
+        if orcs[0].num_noise():
+            nz = [o.peek_noise() for o in orcs]
+            noise = (np.stack([n[0] for n in nz]), np.stack([n[1] for n in nz]))
+        learn = t != 4
+        for a, o in enumerate(orcs):
+            o.set_inputs(x[a])
+            o.step(float(r[a]), learn)
+        before = eng.launch_count
+        eng.set_inputs(x)
+        eng.step(rewards=r, noise=noise, learn=learn)
+        if path == "coop" and cfg.variant != cf.QPRSDR:
+            assert eng.launch_count - before == 1, "the cooperative step was not taken"
+        pred = eng.get_predictions()
+        for a, o in enumerate(orcs):
+            assert np.array_equal(o.get_predictions(), pred[a]), (t, a)
+            bad = diff_states(o.state(), eng.state(agent=a))
+            assert bad == [], "step %d agent %d: %s" % (t, a, bad[:6])
+    if cfg.variant == cf.QPRSDR:
+        acts = eng.get_actions()
+        for a, o in enumerate(orcs):
+            assert np.array_equal(acts[a], o.get_array("ACT_EXPL", 0)), a
+
+
 def test_batched_agents_are_independent():
     """Agents in one engine evolve exactly like separate single-agent runs."""
     cfg, ld = cf.config_c2()
