@@ -20,7 +20,13 @@
 //   * the lateral lists index a table with the precomputed slot-plane offset of every unit;
 //   * everything but the weight rows is kept small (activations and thresholds in registers,
 //     the reconstructions written over the errors at the end), so that six CTAs of the
-//     RunnerMain layer 0 fit an SM: 4096 agents are then five waves instead of six.
+//     RunnerMain layer 0 fit an SM: 4096 agents are then five waves instead of six;
+//   * the layer's LEARNING is the kernel's tail (`learn`): everything the rules of sdr/IRSDR.cpp:287-319 and
+//     neo/SparseCoder.cpp:326-361 (+ the reward of neo/Agent.cpp:252-265) read is known once the layer's own
+//     up pass is over -- the final states, the last reconstructions, the PREVIOUS step's prediction -- and
+//     nothing the down pass reads is written by them.  The weight rows are still in shared memory, so the
+//     rule reads only the traces from HBM and writes weights and traces back: no second sweep of the
+//     weights, no separate learning launch competing with the column kernels for HBM.
 // Same arithmetic, same order, same bits as bidi_coder.cuh / bidi_kernels.cuh.
 #pragma once
 #include "bidi_coder.cuh"
@@ -126,7 +132,7 @@ __device__ __forceinline__ float dot_row_seq(const Pair& F, const ulonglong2* __
 
 // LIGHT: the one-warp launch of a small layer (coder_dense_threads == 32), compiled for 28 CTAs per SM
 template <int NEO, int LIGHT>
-__global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dense(EngineDev P, LayerDev L, int l, long long next_vis_input) {
+__global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dense(EngineDev P, LayerDev L, int l, long long next_vis_input, int learn) {
   extern __shared__ __align__(16) float sm[];
   const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Pair F{P.k_one2, P.k_negzero2, P.k_negone2};
@@ -341,6 +347,78 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
       if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + k * 3 + 0];
       B[next_vis_input + k] = st;
     }
+  }
+  if (!learn) return;
+
+  // ---- learning (sdr/IRSDR.cpp:287-319; neo/Agent.cpp:252-265 + neo/SparseCoder.cpp:326-361), the operations of
+  //      k_ic_learn / k_neo_learn in their order.  err[] holds the final reconstructions: xin becomes the error
+  //      vector (slot order), state[] the learning factor of every unit, spike[] its reward
+  __syncthreads();
+  for (int s = tid; s < pitch; s += T) xin[s] = xin[s] - err[s];
+  float* lrn = state;
+  float* rwd = spike;
+  for (int k = tid; k < nh; k += T) {
+    const float lv = NEO ? state[k] * mult : state[k];
+    if (NEO) {
+      const float perr = lv - B[L.p_state_prev + k];
+      const float error2 = perr * perr, base = B[L.p_baseline + k];
+      rwd[k] = bidi_sigmoid(L.sensitivity * (error2 - base));
+      B[L.p_baseline + k] = (1.0f - L.baseline_decay) * base + L.baseline_decay * error2;
+    }
+    lrn[k] = lv;
+  }
+  __syncthreads();
+  {  // feed-forward and recurrent weights: a task = four slots of 32 units (the reverse of the staging)
+    const int ub = (nh + 31) >> 5, nq_ff = S.nf >> 2, nq = (S.nf + S.nr) >> 2;
+    const float maxd = L.max_weight_delta, decay = L.weight_decay;
+    for (int t = warp; t < nq * ub; t += W) {
+      const int q = t / ub, u = (t - q * ub) * 32 + lane;
+      if (u >= nh) continue;
+      const bool ffp = q < nq_ff;
+      const WinDev& wd = ffp ? L.ff : L.rec;
+      const int s0 = ffp ? 4 * q : 4 * q - S.nf;  // first slot of the quad inside its family
+      const int n_slots = ffp ? nv : nh, dyn = wd.dyn, r = wd.r;
+      const float lr = ffp ? L.learn_ff : L.learn_rec;
+      float* wpl = B + wd.w_off + u;
+      float* tpl = NEO ? B + wd.tr_off + u : nullptr;
+      const int cx = wd.cx[u % hw], cy = wd.cy[u / hw];
+      const float4 wv4 = *reinterpret_cast<const float4*>(w + (size_t)u * pitch + 4 * q);
+      const float4 ev4 = *reinterpret_cast<const float4*>(xin + 4 * q);
+      const float wv[4] = {wv4.x, wv4.y, wv4.z, wv4.w}, ev[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
+      const float lv = lrn[u], rw = NEO ? rwd[u] : 0.0f;
+      // the unit's own connections only: slot (tx, ty) inside the radius, the recurrent centre excluded
+      bool ok[4];
+      float trv[4];
+      int tx = s0 / dyn, ty = s0 - tx * dyn;
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        ok[e] = s0 + e < n_slots && abs(tx - cx) <= r && abs(ty - cy) <= r && !(wd.excl && tx == cx && ty == cy);
+        trv[e] = (NEO && ok[e]) ? tpl[(long long)(s0 + e) * nh] : 0.0f;
+        if (++ty == dyn) { ty = 0; tx++; }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (ok[e]) {
+          const long long g = (long long)(s0 + e) * nh;
+          if (NEO) {
+            const float delta = lr * rw * trv[e] - decay * wv[e];
+            wpl[g] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
+            tpl[g] = L.lambda * trv[e] + lv * ev[e];
+          } else {
+            const float delta = lr * lv * ev[e] - decay * wv[e];
+            wpl[g] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
+          }
+        }
+    }
+  }
+  // lateral weights and the threshold of this lane's unit (sdr/IRSDR.cpp:313-317)
+  if (warp < S.sweep_warps && i < nh) {
+    float* __restrict__ wl = B + L.lat.w_off;
+    const float si = lrn[i], sp2 = L.sparsity * L.sparsity;
+    for_each_slot_batched<8, WE>(L.lat, ux, uy,
+        [&](int s, int t) { return WE{wl[(long long)s * nh + i], lrn[t]}; },
+        [&](int s, const WE& v) { wl[(long long)s * nh + i] = bidi_max(0.0f, v.w + L.learn_lat * (si * v.e - sp2)); });
+    B[L.thr + i] = bidi_max(0.0f, thr_r + (si - L.sparsity) * L.learn_threshold);
   }
 }
 

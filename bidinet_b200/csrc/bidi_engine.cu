@@ -128,6 +128,7 @@ struct bidi_engine {
   cudaStream_t side = nullptr;                     // second branch of the step graph (coder learning, see record_step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_learn = true;
+  bool fuse_learn = true;                          // dense-coder layers learn in the coder kernel's tail (option "fuse_learn")
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_in = nullptr;                     // the last bidi_set_inputs' host->device copy has read the host buffer
   // one graph per value of the learn flag
@@ -660,12 +661,17 @@ void record_step(Recorder& R, bool learn) {
   // the PREVIOUS step left behind (errors, states, the previous prediction), and nothing before stepEnd reads what it
   // writes, so in the step graph it is a second branch: beside the down pass, and -- where every layer's up pass is
   // one fused launch -- already beside the up pass of the layers above.
+  // layers on the dense fused coder kernel learn in that kernel's tail (bidi_coder_dense.cuh)
+  auto learns_in_coder = [&](int l) { return h->coder_cta[l] == 2 && !h->force_phase_kernels && !R.collect && h->fuse_learn; };
   auto record_learn_layer = [&](int l) {
+    if (learns_in_coder(l)) return;
     if (h->tiled[l]) launch_tile(R, "ic_learn", bidi::k_t_ic_learn, tiles_of(A, ly[l].nh), 0, ly[l], l, (int)(V != BIDI_ITERATIVE));
     else if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
     else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
   };
-  const bool fork_learn = learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing;
+  bool any_separate_learn = false;
+  for (int l = 0; l < L; l++) any_separate_learn = any_separate_learn || !learns_in_coder(l);
+  const bool fork_learn = learn && any_separate_learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing;
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
     if (h->coder_cta[l] && !h->force_phase_kernels && !R.collect) { // whole up pass of the layer in one launch
@@ -675,12 +681,13 @@ void record_step(Recorder& R, bool learn) {
         const int threads = bidi::coder_dense_threads(ly[l]);
         const size_t smem = sizeof(float) * (size_t)bidi::coder_dense_shape(ly[l]).floats;
         const bool light = threads == 32;  // one warp per agent: the register-lean build, 28 CTAs per SM
+        const int fused_learn = learn && learns_in_coder(l) ? 1 : 0;
         if (V == BIDI_ITERATIVE) {
-          if (light) bidi::k_coder_dense<0, 1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
-          else bidi::k_coder_dense<0, 0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+          if (light) bidi::k_coder_dense<0, 1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt, fused_learn);
+          else bidi::k_coder_dense<0, 0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt, fused_learn);
         } else {
-          if (light) bidi::k_coder_dense<1, 1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
-          else bidi::k_coder_dense<1, 0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt);
+          if (light) bidi::k_coder_dense<1, 1><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt, fused_learn);
+          else bidi::k_coder_dense<1, 0><<<(unsigned)A, threads, smem, h->stream>>>(h->P, ly[l], l, nxt, fused_learn);
         }
       } else {
         const int threads = std::min(512, std::max(64, (ly[l].nv + ly[l].nh + 31) / 32 * 32));
@@ -1783,6 +1790,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   }
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "overlap_learn") h->overlap_learn = value != 0;
+  else if (std::string(name) == "fuse_learn") h->fuse_learn = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
       size_t smem = 0;
