@@ -150,6 +150,13 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
   int2* lat_tab = reinterpret_cast<int2*>(spike + nh);  // [nh], lateral-list order: (x | y << 16, slot plane offset)
   int* lat_list = reinterpret_cast<int*>(lat_tab + nh) + (warp < S.sweep_warps ? warp : 0) * nh;  // this warp's spiking units: positions in lat_tab
 
+  // the learning tail reads the eligibility traces once, ~all iterations from now: bring their planes into the L2
+  // meanwhile (one bulk prefetch per plane), so that the tail's loads are L2 hits
+  if (NEO && learn && tid == 0) {
+    const unsigned fb = (unsigned)(L.ff.nslots * nh) * 4u & ~15u, rb = has_rec ? (unsigned)(L.rec.nslots * nh) * 4u & ~15u : 0u;
+    if (fb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(B + L.ff.tr_off), "r"(fb) : "memory");
+    if (rb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(B + L.rec.tr_off), "r"(rb) : "memory");
+  }
   // ---- stage: slot planes -> rows.  A task is four slots of 32 units: four coalesced loads per lane, one
   //      128-bit store (rows are 4 (mod 8) floats apart: a quarter warp's stores fall in distinct banks);
   //      the loads of four tasks are in flight at a time
@@ -368,47 +375,58 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
     lrn[k] = lv;
   }
   __syncthreads();
-  {  // feed-forward and recurrent weights: a task = four slots of 32 units (the reverse of the staging)
+  {  // feed-forward and recurrent weights.  Warp `warp` owns the 32 units of block warp % ub (its lane's unit never
+     // changes: reward and learning factor stay in registers) and shares that block's row quads with the other
+     // warps of the block.  Which of a quad's four slots are the unit's own connections (inside the radius, the
+     // recurrent centre excluded) comes from the layer's mask table; the trace loads of NB quads are in flight
+     // together and hit the L2 (the planes were prefetched at kernel start).
+    constexpr int NB = LIGHT ? 2 : 4;
     const int ub = (nh + 31) >> 5, nq_ff = S.nf >> 2, nq = (S.nf + S.nr) >> 2;
-    const float maxd = L.max_weight_delta, decay = L.weight_decay;
-    for (int t = warp; t < nq * ub; t += W) {
-      const int q = t / ub, u = (t - q * ub) * 32 + lane;
-      if (u >= nh) continue;
-      const bool ffp = q < nq_ff;
-      const WinDev& wd = ffp ? L.ff : L.rec;
-      const int s0 = ffp ? 4 * q : 4 * q - S.nf;  // first slot of the quad inside its family
-      const int n_slots = ffp ? nv : nh, dyn = wd.dyn, r = wd.r;
-      const float lr = ffp ? L.learn_ff : L.learn_rec;
-      float* wpl = B + wd.w_off + u;
-      float* tpl = NEO ? B + wd.tr_off + u : nullptr;
-      const int cx = wd.cx[u % hw], cy = wd.cy[u / hw];
-      const float4 wv4 = *reinterpret_cast<const float4*>(w + (size_t)u * pitch + 4 * q);
-      const float4 ev4 = *reinterpret_cast<const float4*>(xin + 4 * q);
-      const float wv[4] = {wv4.x, wv4.y, wv4.z, wv4.w}, ev[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
+    const int g = warp % ub, u = g * 32 + lane, k0 = warp / ub, ng = (W - g + ub - 1) / ub;
+    if (u < nh) {
+      const float maxd = L.max_weight_delta, decay = L.weight_decay, lambda = L.lambda;
       const float lv = lrn[u], rw = NEO ? rwd[u] : 0.0f;
-      // the unit's own connections only: slot (tx, ty) inside the radius, the recurrent centre excluded
-      bool ok[4];
-      float trv[4];
-      int tx = s0 / dyn, ty = s0 - tx * dyn;
+      const float kf = NEO ? L.learn_ff * rw : L.learn_ff * lv, kr = NEO ? L.learn_rec * rw : L.learn_rec * lv;
+      const int* __restrict__ mk = L.dense_mask + u;
+      const float* wrow = w + (size_t)u * pitch;
+      float* wf = B + L.ff.w_off + u; float* wr_ = has_rec ? B + L.rec.w_off + u - (long long)S.nf * nh : nullptr;
+      float* tf = NEO ? B + L.ff.tr_off + u : nullptr; float* tr_ = (NEO && has_rec) ? B + L.rec.tr_off + u - (long long)S.nf * nh : nullptr;
+      for (int q0 = k0; q0 < nq; q0 += NB * ng) {
+        float trv[NB][4];
+        int msk[NB];
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        ok[e] = s0 + e < n_slots && abs(tx - cx) <= r && abs(ty - cy) <= r && !(wd.excl && tx == cx && ty == cy);
-        trv[e] = (NEO && ok[e]) ? tpl[(long long)(s0 + e) * nh] : 0.0f;
-        if (++ty == dyn) { ty = 0; tx++; }
-      }
+        for (int h = 0; h < NB; h++) {
+          const int q = q0 + h * ng;
+          msk[h] = q < nq ? mk[q * nh] : 0;
+          const float* tp = (q < nq_ff ? tf : tr_) + (long long)(4 * q) * nh;
 #pragma unroll
-      for (int e = 0; e < 4; e++)
-        if (ok[e]) {
-          const long long g = (long long)(s0 + e) * nh;
-          if (NEO) {
-            const float delta = lr * rw * trv[e] - decay * wv[e];
-            wpl[g] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
-            tpl[g] = L.lambda * trv[e] + lv * ev[e];
-          } else {
-            const float delta = lr * lv * ev[e] - decay * wv[e];
-            wpl[g] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
-          }
+          for (int e = 0; e < 4; e++) trv[h][e] = (NEO && ((msk[h] >> e) & 1)) ? tp[e * nh] : 0.0f;
         }
+#pragma unroll
+        for (int h = 0; h < NB; h++) {
+          if (!msk[h]) continue;
+          const int q = q0 + h * ng;
+          const bool ffp = q < nq_ff;
+          const float k = ffp ? kf : kr;
+          float* wp = (ffp ? wf : wr_) + (long long)(4 * q) * nh;
+          float* tp = NEO ? (ffp ? tf : tr_) + (long long)(4 * q) * nh : nullptr;
+          const float4 wv4 = *reinterpret_cast<const float4*>(wrow + 4 * q);
+          const float4 ev4 = *reinterpret_cast<const float4*>(xin + 4 * q);
+          const float wv[4] = {wv4.x, wv4.y, wv4.z, wv4.w}, ev[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if ((msk[h] >> e) & 1) {
+              if (NEO) {  // delta = lr*reward*trace - decay*w; w += clamp(delta); trace = lambda*trace + state*e
+                const float delta = k * trv[h][e] - decay * wv[e];
+                wp[e * nh] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
+                tp[e * nh] = lambda * trv[h][e] + lv * ev[e];
+              } else {    // delta = lr*state*e - decay*w
+                const float delta = k * ev[e] - decay * wv[e];
+                wp[e * nh] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
+              }
+            }
+        }
+      }
     }
   }
   // lateral weights and the threshold of this lane's unit (sdr/IRSDR.cpp:313-317)

@@ -44,9 +44,8 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   const ColumnsDev& C = L.col;
   const Pair F{P.k_one2, P.k_negzero2, P.k_negone2};
   const int lane = threadIdx.x, c = lane >> 4, i = lane & 15;
-  const int n_pairs = (C.n + 1) >> 1;
-  const long long task = blockIdx.x;
-  const int a = (int)(task / n_pairs), pair = (int)(task % n_pairs);
+  const int a = blockIdx.z * gridDim.y + blockIdx.y, pair = blockIdx.x;  // consecutive CTAs are the pairs of one agent
+  if (a >= P.A) return;
   const int node = 2 * pair + c;
   const bool has = node < C.n;
   float* B = blob_of(P, a);
@@ -79,13 +78,10 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   }
   // sections of column c's block
   float* W = rec + c * blk;          // [16][SH]
-  float* latT = W + CC * SH;         // [16][16], latT[k][i] = lat[i][k]
-  float* v_thr = latT + CC * CC;
-  float* v_qw = v_thr + CC; float* v_qtr = v_qw + CC;
-  float* v_aw = v_qtr + CC;          // [3][16]
+  float* cellr = W + CC * SH + i * BIDI_COL_ROW;  // this lane's cell row: lat[i][0..15], threshold, q w, q trace, spikePrev
+  float* v_aw = W + CC * SH + CC * BIDI_COL_ROW;  // [3][16]
   float* v_atr = v_aw + 3 * CC;
-  float* v_sprev = v_atr + 3 * CC;
-  float* err = v_sprev + CC;         // [S]
+  float* err = v_atr + 3 * CC;       // [S]
   float* scal = err + S;             // [4]
 
   // ---- gather column c's inputs while the copy is in flight (neo/Agent.cpp:159-169, :217-220)
@@ -97,7 +93,6 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
     const int in0 = has ? C.in_off[node] : 0;
     const int nin = has ? C.in_off[node + 1] - in0 : 0;
     const int* src = C.in_src + in0;
-    float* g_in = B + C.inputs + in0;
     constexpr int GT = 9;  // 144 inputs per trip
     for (int j0 = 0; j0 < S; j0 += 16 * GT) {
       float gv[GT];
@@ -106,8 +101,7 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
 #pragma unroll
       for (int t = 0; t < GT; t++) {
         const int j = j0 + i + 16 * t;
-        if (j < S) in_s[j] = gv[t];
-        if (j < nin) g_in[j] = gv[t];
+        if (j < S) in_s[j] = gv[t];  // (the COL_INPUT plane is not written: the host regathers it on demand)
       }
     }
   }
@@ -115,8 +109,12 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   mbar_wait(bar, 0);
 
   // ---- iterate (neo/Column.cpp:58-103)
-  const float thr = v_thr[i];
-  float sp = v_sprev[i];
+  float thr, sp;
+  {
+    const float4 c4 = *reinterpret_cast<const float4*>(cellr + CC);
+    thr = c4.x; sp = c4.w;
+  }
+  const ulonglong2* lat4 = reinterpret_cast<const ulonglong2*>(cellr);
   unsigned m = (__ballot_sync(0xffffffffu, sp != 0.0f) >> (16 * c)) & 0xffffu;  // column c's spiking cells
   float act = 0.0f, st = 0.0f, counter = 0.0f, mult = 0.0f;
   const float oml = 1.0f - C.leak;
@@ -131,12 +129,15 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
     // which leaves a sum that started at +0 unchanged).  Done before the sweep, four loads in flight, so that
     // their latency is not on the path between the sweep and the threshold test
     float inh = 0.0f;
-    for (unsigned mm = m; mm;) {
-      float lv[4];
+    if (m) {
 #pragma unroll
-      for (int q = 0; q < 4; q++) { lv[q] = mm ? latT[(__ffs(mm) - 1) * CC + i] : 0.0f; mm &= mm - 1; }
-#pragma unroll
-      for (int q = 0; q < 4; q++) inh += lv[q];
+      for (int q = 0; q < 4; q++) {  // the lane's lateral row, four 128-bit loads; ascending cell index
+        const ulonglong2 v = lat4[q];
+        if (m & (1u << (4 * q))) inh += lo32(v.x);
+        if (m & (2u << (4 * q))) inh += hi32(v.x);
+        if (m & (4u << (4 * q))) inh += lo32(v.y);
+        if (m & (8u << (4 * q))) inh += hi32(v.y);
+      }
     }
     // excitation += w * err, sequentially over the inputs.  The shared-memory loads run two quads ahead of
     // the add chain (a quad's four chained adds are 16 cycles, a load is ~30); the last two prefetches of a
@@ -189,9 +190,10 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
     // recon += (spike*multiplier) * w ; error = input - recon
     const u64 mult2 = pk(mult, mult);
     const int ns = n2 - RP;  // input pairs in the shared-memory part of a row
-    float rx[NP], ry[NP];
+    // the sums over the (few) spiking rows are packed: NP independent accumulators per lane hide the packed add's latency
+    u64 r2[NP];
 #pragma unroll
-    for (int t = 0; t < NP; t++) { rx[t] = 0.0f; ry[t] = 0.0f; }
+    for (int t = 0; t < NP; t++) r2[t] = 0ull;
     if (RH > 0) {
       // spiking rows RB at a time per column: their owners park the register part in the scratch,
       // then every lane adds them to its input pairs, ascending cell index
@@ -210,17 +212,11 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
           const int k = __ffs(mm) - 1;
           const u64* rrow = reinterpret_cast<const u64*>(scr + b * RS) + i;
 #pragma unroll
-          for (int t = 0; t < RT; t++) {
-            const u64 pr = F.mul(mult2, rrow[16 * t]);
-            rx[t] += lo32(pr); ry[t] += hi32(pr);
-          }
+          for (int t = 0; t < RT; t++) r2[t] = F.add2(F.mul(mult2, rrow[16 * t]), r2[t]);
           const u64* row = reinterpret_cast<const u64*>(W + k * SH) + i;
 #pragma unroll
           for (int t = RT; t < NP; t++)
-            if (i + 16 * (t - RT) < ns) {
-              const u64 pr = F.mul(mult2, row[16 * (t - RT)]);
-              rx[t] += lo32(pr); ry[t] += hi32(pr);
-            }
+            if (i + 16 * (t - RT) < ns) r2[t] = F.add2(F.mul(mult2, row[16 * (t - RT)]), r2[t]);
         }
         __syncwarp();
       }
@@ -229,35 +225,29 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
         const u64* row = reinterpret_cast<const u64*>(W + (__ffs(mm) - 1) * SH) + i;
 #pragma unroll
         for (int t = 0; t < NP; t++)
-          if (i + 16 * t < ns) {
-            const u64 pr = F.mul(mult2, row[16 * t]);
-            rx[t] += lo32(pr); ry[t] += hi32(pr);
-          }
+          if (i + 16 * t < ns) r2[t] = F.add2(F.mul(mult2, row[16 * t]), r2[t]);
       }
     }
 #pragma unroll
     for (int t = 0; t < NP; t++) {
       const int p = i + 16 * t;
-      if (p < n2) err2[p] = F.sub2(in2[p], pk(rx[t], ry[t]));
+      if (p < n2) err2[p] = F.sub2(in2[p], r2[t]);
     }
     // rows longer than 16*NP pairs: the rest of the shared-memory part
     for (int p0 = 16 * NP; p0 < n2; p0 += 16 * NP) {
-      float sx[NP], sy[NP];
+      u64 s2[NP];
 #pragma unroll
-      for (int t = 0; t < NP; t++) { sx[t] = 0.0f; sy[t] = 0.0f; }
+      for (int t = 0; t < NP; t++) s2[t] = 0ull;
       for (unsigned mm = m; mm; mm &= mm - 1) {
         const u64* row = reinterpret_cast<const u64*>(W + (__ffs(mm) - 1) * SH) + (p0 - RP) + i;
 #pragma unroll
         for (int t = 0; t < NP; t++)
-          if (p0 + i + 16 * t < n2) {
-            const u64 pr = F.mul(mult2, row[16 * t]);
-            sx[t] += lo32(pr); sy[t] += hi32(pr);
-          }
+          if (p0 + i + 16 * t < n2) s2[t] = F.add2(F.mul(mult2, row[16 * t]), s2[t]);
       }
 #pragma unroll
       for (int t = 0; t < NP; t++) {
         const int p = p0 + i + 16 * t;
-        if (p < n2) err2[p] = F.sub2(in2[p], pk(sx[t], sy[t]));
+        if (p < n2) err2[p] = F.sub2(in2[p], s2[t]);
       }
     }
     __syncwarp();
@@ -269,10 +259,11 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   // ---- value and actions, sequential over the cells (neo/Column.cpp:111-123):
   // lanes 0..2 of each half accumulate one action each, lane 3 the value
   float accum = 0.0f;
-  if (i < 4) {
-    const float* wv = i < 3 ? v_aw + i * CC : v_qw;
+  if (i < 4) {  // q weights are element 17 of the cell rows
+    const float* wv = i < 3 ? v_aw + i * CC : cellr - i * BIDI_COL_ROW + CC + 1;
+    const int ws = i < 3 ? 1 : BIDI_COL_ROW;
 #pragma unroll
-    for (int k = 0; k < CC; k++) accum += wv[k] * st_s[k];
+    for (int k = 0; k < CC; k++) accum += wv[k * ws] * st_s[k];
   }
   const float q = __shfl_sync(0xffffffffu, accum, 16 * c + 3);
   float as = 0.0f, ae = 0.0f;
@@ -291,10 +282,14 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   const float gl = C.gamma_lambda;
 
   // ---- learning (neo/Column.cpp:139-166), all inside the shared-memory record
-  {
-    const float tr = v_qtr[i];
-    v_qw[i] = v_qw[i] + q_alpha_td * tr;
-    v_qtr[i] = tr * gl + st;
+  {  // the cell's four scalars: threshold += alpha*(state - sparsity), q weight and trace, spikePrev
+    float4 c4 = *reinterpret_cast<const float4*>(cellr + CC);
+    const float tr = c4.z;
+    c4.x = thr + C.a_thr * (st - C.sparsity);
+    c4.y = c4.y + q_alpha_td * tr;
+    c4.z = tr * gl + st;
+    c4.w = sp;
+    *reinterpret_cast<float4*>(cellr + CC) = c4;
   }
 #pragma unroll
   for (int ai = 0; ai < 3; ai++) {
@@ -330,18 +325,26 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
       wrow[j] = wv;
     }
   }
-  // lateral: lat[i][r] = max(0, lat[i][r] + alpha*(state_i*state_r - sparsity^2)), every (i, r)
+  // lateral: lat[i][r] = max(0, lat[i][r] + alpha*(state_i*state_r - sparsity^2)), every (i, r): the lane's own row,
+  // packed (x - s == x + (-s) exactly)
   {
     const float sp2 = C.sparsity * C.sparsity;
+    const u64 st2 = pk(st, st), nsp2 = pk(-sp2, -sp2), al2 = pk(C.a_lat, C.a_lat);
+    ulonglong2* lrow = reinterpret_cast<ulonglong2*>(cellr);
+    const ulonglong2* s4 = reinterpret_cast<const ulonglong2*>(st_s);
+    auto upd = [&](u64 lv, u64 sr) {
+      const u64 nv = F.add2(lv, F.mul(al2, F.add2(F.mul(st2, sr), nsp2)));
+      float x, y; upk(nv, x, y);
+      return pk(bidi_max(0.0f, x), bidi_max(0.0f, y));
+    };
 #pragma unroll
-    for (int r = 0; r < CC; r++) {
-      float* p = latT + r * CC + i;
-      *p = bidi_max(0.0f, *p + C.a_lat * (st * st_s[r] - sp2));
+    for (int q = 0; q < 4; q++) {
+      ulonglong2 v = lrow[q];
+      const ulonglong2 sr = s4[q];
+      v.x = upd(v.x, sr.x); v.y = upd(v.y, sr.y);
+      lrow[q] = v;
     }
   }
-  // threshold += alpha*(state - sparsity)
-  v_thr[i] = thr + C.a_thr * (st - C.sparsity);
-  v_sprev[i] = sp;
   if (has) {
     const int cb = node * CC + i;
     B[C.act + cb] = act; B[C.spike + cb] = sp; B[C.state + cb] = st;

@@ -45,7 +45,12 @@ struct ColRec {
   float *W, *Wreg, *latT, *thr, *q_w, *q_tr, *a_w, *a_tr, *sprev, *err, *scal;
   int S, Cq, nin;
   int es;        // element stride: 2 in the pair-interleaved layout, 1 in the planar one
+  int cs;        // stride of the per-cell scalars thr, q_w, q_tr, sprev: es, or the pitch of the planar layout's cell rows
+  bool planar;
   int rh, lane0; // planar: inputs per row kept in the lane-major register part; this column's first lane (0 or 16)
+  // lateral weight of cell i from cell j: planar rows [i][BIDI_COL_ROW] = (lat[i][0..15], thr, q_w, q_tr, sprev);
+  // interleaved: transposed, latT[j][i]
+  float& lat(int i, int j) const { return planar ? latT[i * BIDI_COL_ROW + j] : latT[es * (j * Cq + i)]; }
   // weight of cell i, input j
   float& w(int i, int j) const {
     if (j < rh) return Wreg[((long long)(j >> 2) * 32 + lane0 + i) * 4 + (j & 3)];
@@ -73,6 +78,15 @@ ColRec col_rec(const ColumnsDev& C, const ColumnsHost& H, float* blob, int node)
   r.W = r.Wreg + 32 * r.rh + (C.planar ? half * block : half);
   const int e = r.es;
   r.latT = r.W + (long long)e * C.cells * sh;
+  r.planar = C.planar != 0;
+  if (r.planar) {  // cell rows: 16 lateral weights + the cell's four scalars, one 128-bit access each (bidi_columns16.cuh)
+    r.cs = BIDI_COL_ROW;
+    r.thr = r.latT + 16; r.q_w = r.latT + 17; r.q_tr = r.latT + 18; r.sprev = r.latT + 19;
+    r.a_w = r.latT + C.cells * BIDI_COL_ROW; r.a_tr = r.a_w + 3 * C.cq;
+    r.err = r.a_tr + 3 * C.cq; r.scal = r.err + r.S;
+    return r;
+  }
+  r.cs = e;
   r.thr = r.latT + e * C.cells * C.cq;
   r.q_w = r.thr + e * C.cq; r.q_tr = r.q_w + e * C.cq; r.a_w = r.q_tr + e * C.cq; r.a_tr = r.a_w + 3 * e * C.cq;
   r.sprev = r.a_tr + 3 * e * C.cq; r.err = r.sprev + e * C.cq; r.scal = r.err + e * r.S;
@@ -96,6 +110,7 @@ int column_pair_stride(int nin, bool planar) {
 struct LayerHost {
   WinHost ff, rec, lat, fb, pred;
   ColumnsHost col;
+  std::vector<int> dense_mask;  // LayerDev::dense_mask
 };
 
 } // namespace
@@ -146,6 +161,9 @@ struct bidi_engine {
   double profile_ms = 0; long long profile_launches = 0;
   // host mirror of ONE agent's blob for set/get_array
   std::vector<float> mirror; int mirror_agent = -1; bool mirror_dirty = false;
+  // the 16-cell column kernel gathers its inputs into shared memory only; the BIDI_COL_INPUT planes are regathered
+  // on the host when somebody asks for them (stale since the last step, unless uploaded since)
+  bool col_inputs_stale = false; std::vector<char> col_inputs_set;
   // spatial strip split of one oversized layer (bidi_strip.inl)
   int strip_part = 0, strip_n = 1;
   int strip_span[BIDI_SPAN_COUNT][2] = {};
@@ -384,6 +402,13 @@ int mirror_load(bidi_engine* h, int agent) {
   CU(cudaStreamSynchronize(h->stream));
   h->mirror_agent = agent;
   h->mirror_dirty = false;
+  if (h->col_inputs_stale && !h->col_inputs_set[agent])
+    for (int l = 0; l <= h->L; l++) {  // neo/Agent.cpp:159-169: the inputs the columns of the last step consumed
+      const ColumnsDev& C = h->layers[l].col;
+      if (!C.planar || C.n == 0) continue;
+      const std::vector<int>& src = h->hl[l].col.in_src;
+      for (int j = 0; j < C.tot_in; j++) h->mirror[C.inputs + j] = h->mirror[src[j]];
+    }
   return BIDI_OK;
 }
 // device state is about to change: the mirror must be written back and dropped
@@ -427,11 +452,11 @@ template <class F> void walk_column(const bidi_engine* h, int which, int layer, 
     switch (which) {
       case BIDI_COL_RECON_ERR: for (int j = 0; j < r.nin; j++) f(r.err[r.es * j]); break;
       case BIDI_COL_FF_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < r.nin; j++) f(r.w(i, j)); break;
-      case BIDI_COL_LAT_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < C.cells; j++) f(r.latT[r.es * (j * r.Cq + i)]); break;
-      case BIDI_COL_THRESHOLD: for (int i = 0; i < C.cells; i++) f(r.thr[r.es * i]); break;
-      case BIDI_COL_SPIKE_PREV: for (int i = 0; i < C.cells; i++) f(r.sprev[r.es * i]); break;
-      case BIDI_COL_Q_W: for (int i = 0; i < C.cells; i++) f(r.q_w[r.es * i]); break;
-      case BIDI_COL_Q_TRACE: for (int i = 0; i < C.cells; i++) f(r.q_tr[r.es * i]); break;
+      case BIDI_COL_LAT_W: for (int i = 0; i < C.cells; i++) for (int j = 0; j < C.cells; j++) f(r.lat(i, j)); break;
+      case BIDI_COL_THRESHOLD: for (int i = 0; i < C.cells; i++) f(r.thr[r.cs * i]); break;
+      case BIDI_COL_SPIKE_PREV: for (int i = 0; i < C.cells; i++) f(r.sprev[r.cs * i]); break;
+      case BIDI_COL_Q_W: for (int i = 0; i < C.cells; i++) f(r.q_w[r.cs * i]); break;
+      case BIDI_COL_Q_TRACE: for (int i = 0; i < C.cells; i++) f(r.q_tr[r.cs * i]); break;
       case BIDI_COL_ACT_W: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_w[r.es * (a * r.Cq + i)]); break;
       case BIDI_COL_ACT_TRACE: for (int a = 0; a < 3; a++) for (int i = 0; i < C.cells; i++) f(r.a_tr[r.es * (a * r.Cq + i)]); break;
       case BIDI_COL_PREV_VALUE: f(r.scal[0]); break;
@@ -543,9 +568,12 @@ void record_columns(Recorder& R, int l) {
   const long long warps = (long long)h->A * ((n_pairs + ppw - 1) / ppw);
   const size_t smem = columns_smem_bytes(C) + (size_t)h->col_extra_smem;
   R.before("columns");
-  if (C.planar && C.rh == 64) bidi::k_columns16<64><<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
-  else if (C.planar && C.rh == 32) bidi::k_columns16<32><<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
-  else if (C.planar) bidi::k_columns16<0><<<(unsigned)((long long)h->A * n_pairs), 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  // x = pair (fastest: consecutive CTAs are one agent's pairs), (y, z) = agent
+  const unsigned ay = (unsigned)std::min(h->A, 32768);
+  const dim3 pa((unsigned)n_pairs, ay, (unsigned)((h->A + ay - 1) / ay));
+  if (C.planar && C.rh == 64) bidi::k_columns16<64><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  else if (C.planar && C.rh == 32) bidi::k_columns16<32><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  else if (C.planar) bidi::k_columns16<0><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l);
   else if (ppw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   R.after("columns");
@@ -862,6 +890,7 @@ int run_step(bidi_engine* h, bool learn, bool device_noise) {
   }
   rc = ensure_graph(h, learn ? 1 : 0);
   if (rc) return rc;
+  if (h->cfg.variant == BIDI_NEO_AGENT) { h->col_inputs_stale = true; std::fill(h->col_inputs_set.begin(), h->col_inputs_set.end(), 0); }
   CU(cudaGraphLaunch(h->graphs[learn], h->stream));
   h->launches += h->graph_kernels[learn];
   h->step_index++;
@@ -947,6 +976,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   h->cfg = *cfg; h->ld.assign(layers, layers + L);
   h->cfg.variant = V; h->qnet = qnet;
   h->device = device; h->A = n_agents; h->L = L; h->n_in = cfg->in_width * cfg->in_height;
+  h->col_inputs_set.assign((size_t)n_agents, 0);
   h->layers.assign(L + 1, LayerDev());
   h->hl.resize(L + 1);
   for (auto& d : h->layers) memset(&d, 0, sizeof(LayerDev));
@@ -1186,6 +1216,17 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       push(w->cx, &w->d.cx); push(w->cy, &w->d.cy);
       push(w->gxlo, &w->d.gx_lo); push(w->gxhi, &w->d.gx_hi); push(w->gylo, &w->d.gy_lo); push(w->gyhi, &w->d.gy_hi);
     }
+    if (l < L && is_iter(V) && H.ff.d.absx && H.ff.d.absy && (H.rec.d.r < 0 || (H.rec.d.absx && H.rec.d.absy))) {
+      // the dense coder's learning mask: which slots of a unit's row [feed-forward | recurrent] are its own connections
+      const int nh = h->layers[l].nh, nf = (h->layers[l].nv + 3) & ~3, nr = H.rec.d.r >= 0 ? (nh + 3) & ~3 : 0;
+      H.dense_mask.assign((size_t)((nf + nr) / 4) * nh, 0);
+      for (int u = 0; u < nh; u++) {
+        const int ux = u % H.ff.d.uw, uy = u / H.ff.d.uw;
+        for_each_conn_host(H.ff, ux, uy, [&](int s, int) { H.dense_mask[(size_t)(s / 4) * nh + u] |= 1 << (s % 4); });
+        for_each_conn_host(H.rec, ux, uy, [&](int s, int) { H.dense_mask[(size_t)((nf + s) / 4) * nh + u] |= 1 << ((nf + s) % 4); });
+      }
+      push(H.dense_mask, &h->layers[l].dense_mask);
+    }
     if (V == BIDI_NEO_AGENT) {
       push(H.col.in_off, &h->layers[l].col.in_off);
       push(H.col.rec_off, &h->layers[l].col.rec_off);
@@ -1252,7 +1293,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       if (V == BIDI_NEO_AGENT)
         for (int node = 0; node < D.col.n; node++) {
           const ColRec r = col_rec(D.col, h->hl[l].col, img.data(), node);
-          for (int i = 0; i < D.col.cells; i++) r.thr[r.es * i] = cfg->init_threshold;
+          for (int i = 0; i < D.col.cells; i++) r.thr[r.cs * i] = cfg->init_threshold;
         }
     }
     for (int a = 0; a < n_agents; a++)
@@ -1387,6 +1428,7 @@ int bidi_set_array(bidi_engine* h, int agent, int which, int layer, const float*
   if (h->ipc_linked) return fail(h, BIDI_EINVAL, "bidi_set_array: not after bidi_strip_link_ipc (the neighbours store into this memory): initialise the state before bidi_strip_ipc_export");
   int rc = mirror_load(h, agent);
   if (rc) return rc;
+  if (which == BIDI_COL_INPUT) h->col_inputs_set[agent] = 1;
   if (r.kind == ArrayRef::PLANE) memcpy(h->mirror.data() + r.off, src, sizeof(float) * len);
   else if (r.kind == ArrayRef::COLUMN) walk_column(h, r.which, r.layer, h->mirror.data(), [&](float& v) { v = *src++; });
   else if (r.kind == ArrayRef::QLIST) walk_qlist(h, r.layer, r.trace, h->mirror.data(), [&](float& v) { v = *src++; });
@@ -1443,10 +1485,10 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
     auto draw_column = [&](const ColumnsDev& C, const ColumnsHost& CH, int node) { // neo/Column.cpp:22-43
       const ColRec r = col_rec(C, CH, img.data(), node);
       for (int i = 0; i < C.cells; i++) {
-        r.thr[r.es * i] = g.init_threshold;
+        r.thr[r.cs * i] = g.init_threshold;
         for (int j = 0; j < r.nin; j++) r.w(i, j) = weightDist(gen);
-        for (int j = 0; j < C.cells; j++) r.latT[r.es * (j * r.Cq + i)] = inhibitionDist(gen);
-        r.q_w[r.es * i] = weightDist(gen);
+        for (int j = 0; j < C.cells; j++) r.lat(i, j) = inhibitionDist(gen);
+        r.q_w[r.cs * i] = weightDist(gen);
       }
       for (int a = 0; a < 3; a++)
         for (int k = 0; k < C.cells; k++) r.a_w[r.es * (a * r.Cq + k)] = weightDist(gen);
@@ -1897,6 +1939,7 @@ int bidi_load_snapshot(bidi_engine* h, const char* path) {
   cudaGetLastError();
   if (!ok) return fail(h, BIDI_EINVAL, std::string("bidi_load_snapshot: ") + path + " is truncated");
   h->step_index = hd.step_index; h->noise_seed = hd.noise_seed; h->first_agent = hd.first_agent;
+  if (h->cfg.variant == BIDI_NEO_AGENT) { h->col_inputs_stale = true; std::fill(h->col_inputs_set.begin(), h->col_inputs_set.end(), 0); }
   return BIDI_OK;
 }
 

@@ -23,6 +23,7 @@
 #include "bidinet_b200.h"
 
 #define BIDI_MAX_NODE_LAYERS (BIDI_MAX_LAYERS + 1)
+#define BIDI_COL_ROW 20 /* floats per cell row of a planar column block: 16 lateral weights + 4 scalars */
 
 // One connection family: units of a uw x uh grid look at a window of radius r
 // around a centre in a tw x th target grid.
@@ -61,9 +62,14 @@ struct WinDev {
 //   scal2[4][2]         prevValue, pad
 // A layer with an odd number of nodes ends with a phantom column of zeros.
 // Columns of 16 cells (the reference's default, neo/Agent.h:22) use the PLANAR variant of
-// the record instead: column 2p's block followed by column 2p+1's, each block holding the
-// same sections in the same order without the [2] interleave, W rows S floats apart with
-// S = 4 (mod 8).  bidi_columns16.cuh works on it with lane = (column, cell).
+// the record instead: column 2p's block followed by column 2p+1's, without the [2]
+// interleave.  A block is
+//   W[16][S - rh]          weight rows (the part not kept in registers), S = 4 (mod 8)
+//   cell[16][BIDI_COL_ROW] per cell i: lat[i][0..15] (row-major), threshold, q w, q trace, spikePrev
+//                          -- the lane that owns the cell reads its lateral row and its four scalars
+//                          with 128-bit accesses, rows 20 floats apart fall in distinct banks
+//   3 action w [16], 3 action traces [16], err[S], scal[4]
+// bidi_columns16.cuh works on it with lane = (column, cell).
 // Write-only per-step outputs (inputs, activation, spike, state, action states) stay
 // in plain planes.
 struct ColumnsDev {
@@ -107,6 +113,9 @@ struct LayerDev {
   long long q_state, q_err, q_bias_w, q_bias_tr, q_w_off, q_tr_off;
   const float* q_mask;
   ColumnsDev col;
+  // layers whose windows span the grid (bidi_coder_dense.cuh): per (row quad q, unit u) the four bits "slot 4q+e of
+  // the row [feed-forward | recurrent] is one of u's own connections", [q][unit]; one table for all agents
+  const int* dense_mask;
   // hyper-parameters (bidi_layer_desc)
   float learn_ff, learn_rec, learn_lat, learn_threshold, learn_fb, learn_pred, sparsity;
   float avg_surprise_decay, attention_factor;
