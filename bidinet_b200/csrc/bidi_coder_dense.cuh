@@ -4,11 +4,13 @@
 // of this kind.  There a slot IS a target cell, every unit sees every cell (edge units
 // through zero weights), and the up pass is a dense mat-vec per iteration whose order of
 // summation is the slot order.  So, unlike the general kernel:
-//   * the slot planes w[slot][unit] are transposed into rows w[unit][slot] in shared
-//     memory, feed-forward and recurrent part in ONE row per unit (row pitch = 4 mod 8:
-//     conflict-free 128-bit loads, one row per lane) and the error vectors are kept in
-//     slot order, so the sweep is the column kernel's loop: two 128-bit loads, two packed
-//     products, four chained adds per four connections, software-pipelined four quads deep;
+//   * a layer that runs this kernel keeps its weights (and eligibility traces) in HBM as ROWS
+//     w[unit][slot] (WinDev::row_pitch), feed-forward and recurrent part in ONE row per unit
+//     (row pitch = 4 mod 8: conflict-free 128-bit loads, one row per lane) -- exactly the
+//     shared-memory image, so staging is ONE TMA bulk copy (cp.async.bulk + mbarrier) and the
+//     updated rows go back with one bulk store.  The error vectors are kept in slot order, so
+//     the sweep is the column kernel's loop: two 128-bit loads, two packed products, four
+//     chained adds per four connections, software-pipelined four quads deep;
 //   * the gather-form reconstruction needs no window test (a unit outside the window has
 //     weight 0 and adds +-0): each reconstructing warp compacts the units with a non-zero
 //     drive into a private list of 8-byte entries (row offset, drive), ascending
@@ -61,7 +63,8 @@ __host__ __device__ inline CoderDenseShape coder_dense_shape(const LayerDev& L) 
   s.recon_warps = (s.tasks + 31) / 32;
   if (s.recon_warps > 16) s.recon_warps = 16;
   s.warps = s.sweep_warps > s.recon_warps ? s.sweep_warps : s.recon_warps;
-  s.floats = (long long)L.nh * s.pitch              // weight rows
+  s.floats = 4                                      // the staging copy's mbarrier (keeps the rows 16-byte aligned)
+             + (long long)L.nh * s.pitch            // weight rows
              + 2LL * s.pitch                        // errors (the reconstructions at the end), inputs (x | statePrev)
              + 2LL * s.recon_warps * L.nh           // per reconstructing warp: drive list, 8-byte entries
              + 2LL * L.nh                           // state, spike: unit order (act and thr live in registers)
@@ -141,7 +144,8 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
   const CoderDenseShape S = coder_dense_shape(L);
   const int W = S.warps, T = 32 * W, pitch = S.pitch;
   const bool has_rec = L.rec.r >= 0;
-  float* w = sm;                              // [nh][pitch]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm);
+  float* w = sm + 4;                          // [nh][pitch]
   float* err = w + (size_t)nh * pitch;        // [pitch] errors, slot order, pads 0; after the last iteration: the reconstructions
   float* xin = err + pitch;                   // [pitch] x | statePrev
   int2* ent = reinterpret_cast<int2*>(xin + pitch) + (warp < S.recon_warps ? warp : 0) * nh;  // this warp's drive list
@@ -150,48 +154,18 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
   int2* lat_tab = reinterpret_cast<int2*>(spike + nh);  // [nh], lateral-list order: (x | y << 16, slot plane offset)
   int* lat_list = reinterpret_cast<int*>(lat_tab + nh) + (warp < S.sweep_warps ? warp : 0) * nh;  // this warp's spiking units: positions in lat_tab
 
-  // the learning tail reads the eligibility traces once, ~all iterations from now: bring their planes into the L2
-  // meanwhile (one bulk prefetch per plane), so that the tail's loads are L2 hits
-  if (NEO && learn && tid == 0) {
-    const unsigned fb = (unsigned)(L.ff.nslots * nh) * 4u & ~15u, rb = has_rec ? (unsigned)(L.rec.nslots * nh) * 4u & ~15u : 0u;
-    if (fb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(B + L.ff.tr_off), "r"(fb) : "memory");
-    if (rb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(B + L.rec.tr_off), "r"(rb) : "memory");
+  // ---- stage: the layer's rows [unit][feed-forward | recurrent | pad] are one contiguous image in HBM: one TMA
+  //      bulk copy, overlapped with the staging of the vectors below
+  const uint32_t row_bytes = (uint32_t)(nh * pitch) * 4u;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(bar, row_bytes);
+    tma_load_1d(w, B + L.ff.w_off, row_bytes, bar);
+    // the learning tail reads the eligibility traces once, ~all iterations from now: bring them into the L2 meanwhile
+    if (NEO && learn) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(B + L.ff.tr_off), "r"(row_bytes) : "memory");
   }
-  // ---- stage: slot planes -> rows.  A task is four slots of 32 units: four coalesced loads per lane, one
-  //      128-bit store (rows are 4 (mod 8) floats apart: a quarter warp's stores fall in distinct banks);
-  //      the loads of four tasks are in flight at a time
   {
-    const int ub = (nh + 31) >> 5;
-    auto stage_rows = [&](float* dst, const float* __restrict__ src, int n_slots, int nq) {
-#ifndef BIDI_STAGE_NT
-#define BIDI_STAGE_NT 4   // tasks whose loads are in flight together (8: slower, more registers)
-#endif
-      constexpr int NT = BIDI_STAGE_NT;
-      int q = 0, b = warp;
-      while (b >= ub) { b -= ub; q++; }
-      while (q < nq) {
-        float v[NT][4];
-        int qq[NT], uu[NT];
-#pragma unroll
-        for (int h = 0; h < NT; h++) {
-          qq[h] = q; uu[h] = b * 32 + lane;
-          const bool ok = q < nq && uu[h] < nh;
-          const float* g = src + (long long)(4 * q) * nh + uu[h];
-#pragma unroll
-          for (int e = 0; e < 4; e++) v[h][e] = (ok && 4 * q + e < n_slots) ? g[(long long)e * nh] : 0.0f;
-          b += W;
-          while (b >= ub) { b -= ub; q++; }
-        }
-#pragma unroll
-        for (int h = 0; h < NT; h++)
-          if (qq[h] < nq && uu[h] < nh)
-            *reinterpret_cast<float4*>(dst + (size_t)uu[h] * pitch + 4 * qq[h]) = make_float4(v[h][0], v[h][1], v[h][2], v[h][3]);
-      }
-    };
-    stage_rows(w, B + L.ff.w_off, nv, S.nf >> 2);
-    if (has_rec) stage_rows(w + S.nf, B + L.rec.w_off, nh, S.nr >> 2);
-    for (int u = tid; u < nh; u += T)
-      for (int s = S.nf + S.nr; s < pitch; s += 4) *reinterpret_cast<float4*>(w + (size_t)u * pitch + s) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const float* gx = vis_input_of(P, L, l, a);
     for (int s = tid; s < pitch; s += T) {
       float xv = 0.0f, rv = 0.0f;
@@ -211,6 +185,7 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
       lat_tab[k] = make_int2(tx | (ty << 16), (tx * L.lat.dyn + ty) * nh);
     }
   }
+  mbar_wait(bar, 0);
   __syncthreads();
   // spikePrev in the lateral lists' order, one private copy per sweep warp; rebuilt after every
   // sweep, once all units' new spikes are in shared memory
@@ -375,59 +350,62 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
     lrn[k] = lv;
   }
   __syncthreads();
-  {  // feed-forward and recurrent weights.  Warp `warp` owns the 32 units of block warp % ub (its lane's unit never
-     // changes: reward and learning factor stay in registers) and shares that block's row quads with the other
-     // warps of the block.  Which of a quad's four slots are the unit's own connections (inside the radius, the
-     // recurrent centre excluded) comes from the layer's mask table; the trace loads of NB quads are in flight
-     // together and hit the L2 (the planes were prefetched at kernel start).
+  {  // feed-forward and recurrent weights, row by row: an element is four adjacent slots of one unit (128-bit
+     // accesses, consecutive lanes = consecutive quads of a row).  Which of the four are the unit's own connections
+     // (inside the radius, the recurrent centre excluded) comes from the layer's mask table.  The traces stream
+     // through registers (HBM rows like the weights; prefetched into the L2 at kernel start), the new weights go
+     // into the shared-memory rows, which one bulk copy then takes back to HBM.
     constexpr int NB = LIGHT ? 2 : 4;
-    const int ub = (nh + 31) >> 5, nq_ff = S.nf >> 2, nq = (S.nf + S.nr) >> 2;
-    const int g = warp % ub, u = g * 32 + lane, k0 = warp / ub, ng = (W - g + ub - 1) / ub;
-    if (u < nh) {
-      const float maxd = L.max_weight_delta, decay = L.weight_decay, lambda = L.lambda;
-      const float lv = lrn[u], rw = NEO ? rwd[u] : 0.0f;
-      const float kf = NEO ? L.learn_ff * rw : L.learn_ff * lv, kr = NEO ? L.learn_rec * rw : L.learn_rec * lv;
-      const int* __restrict__ mk = L.dense_mask + u;
-      const float* wrow = w + (size_t)u * pitch;
-      float* wf = B + L.ff.w_off + u; float* wr_ = has_rec ? B + L.rec.w_off + u - (long long)S.nf * nh : nullptr;
-      float* tf = NEO ? B + L.ff.tr_off + u : nullptr; float* tr_ = (NEO && has_rec) ? B + L.rec.tr_off + u - (long long)S.nf * nh : nullptr;
-      for (int q0 = k0; q0 < nq; q0 += NB * ng) {
-        float trv[NB][4];
-        int msk[NB];
+    const int pq = pitch >> 2, nq_ff = S.nf >> 2, total_q = nh * pq;
+    const float maxd = L.max_weight_delta, decay = L.weight_decay, lambda = L.lambda;
+    const int* __restrict__ mk = L.dense_mask;
+    float4* tr4 = NEO ? reinterpret_cast<float4*>(B + L.ff.tr_off) : nullptr;
+    float4* w4 = reinterpret_cast<float4*>(w);
+    const float4* e4 = reinterpret_cast<const float4*>(xin);
+    int u = tid / pq, q = tid - u * pq;
+    const int du = T / pq, dq = T - du * pq;   // one step of T elements
+    for (int idx = tid; idx < total_q; idx += NB * T) {
+      float4 trv[NB];
+      int msk[NB], uu[NB], qq[NB];
 #pragma unroll
-        for (int h = 0; h < NB; h++) {
-          const int q = q0 + h * ng;
-          msk[h] = q < nq ? mk[q * nh] : 0;
-          const float* tp = (q < nq_ff ? tf : tr_) + (long long)(4 * q) * nh;
+      for (int h = 0; h < NB; h++) {
+        const int id = idx + h * T;
+        uu[h] = u; qq[h] = q;
+        msk[h] = id < total_q ? mk[id] : 0;
+        if (NEO && msk[h]) trv[h] = tr4[id];
+        u += du; q += dq;
+        if (q >= pq) { q -= pq; u++; }
+      }
 #pragma unroll
-          for (int e = 0; e < 4; e++) trv[h][e] = (NEO && ((msk[h] >> e) & 1)) ? tp[e * nh] : 0.0f;
-        }
+      for (int h = 0; h < NB; h++) {
+        if (!msk[h]) continue;
+        const int id = idx + h * T;
+        const float lv = lrn[uu[h]];
+        const float k = (qq[h] < nq_ff ? L.learn_ff : L.learn_rec) * (NEO ? rwd[uu[h]] : lv);
+        const float4 wv4 = w4[id], ev4 = e4[qq[h]];
+        float wv[4] = {wv4.x, wv4.y, wv4.z, wv4.w};
+        const float ev[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
+        float tv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (NEO) { tv[0] = trv[h].x; tv[1] = trv[h].y; tv[2] = trv[h].z; tv[3] = trv[h].w; }
 #pragma unroll
-        for (int h = 0; h < NB; h++) {
-          if (!msk[h]) continue;
-          const int q = q0 + h * ng;
-          const bool ffp = q < nq_ff;
-          const float k = ffp ? kf : kr;
-          float* wp = (ffp ? wf : wr_) + (long long)(4 * q) * nh;
-          float* tp = NEO ? (ffp ? tf : tr_) + (long long)(4 * q) * nh : nullptr;
-          const float4 wv4 = *reinterpret_cast<const float4*>(wrow + 4 * q);
-          const float4 ev4 = *reinterpret_cast<const float4*>(xin + 4 * q);
-          const float wv[4] = {wv4.x, wv4.y, wv4.z, wv4.w}, ev[4] = {ev4.x, ev4.y, ev4.z, ev4.w};
-#pragma unroll
-          for (int e = 0; e < 4; e++)
-            if ((msk[h] >> e) & 1) {
-              if (NEO) {  // delta = lr*reward*trace - decay*w; w += clamp(delta); trace = lambda*trace + state*e
-                const float delta = k * trv[h][e] - decay * wv[e];
-                wp[e * nh] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
-                tp[e * nh] = lambda * trv[h][e] + lv * ev[e];
-              } else {    // delta = lr*state*e - decay*w
-                const float delta = k * ev[e] - decay * wv[e];
-                wp[e * nh] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
-              }
+        for (int e = 0; e < 4; e++)
+          if ((msk[h] >> e) & 1) {
+            if (NEO) {  // delta = lr*reward*trace - decay*w; w += clamp(delta); trace = lambda*trace + state*e
+              const float delta = k * tv[e] - decay * wv[e];
+              wv[e] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
+              tv[e] = lambda * tv[e] + lv * ev[e];
+            } else {    // delta = lr*state*e - decay*w
+              const float delta = k * ev[e] - decay * wv[e];
+              wv[e] = wv[e] + bidi_min(maxd, bidi_max(-maxd, delta));
             }
-        }
+          }
+        w4[id] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        if (NEO) tr4[id] = make_float4(tv[0], tv[1], tv[2], tv[3]);
       }
     }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) tma_store_1d(B + L.ff.w_off, w, row_bytes);  // waited for at the end of the kernel
   }
   // lateral weights and the threshold of this lane's unit (sdr/IRSDR.cpp:313-317)
   if (warp < S.sweep_warps && i < nh) {
@@ -438,6 +416,7 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
         [&](int s, const WE& v) { wl[(long long)s * nh + i] = bidi_max(0.0f, v.w + L.learn_lat * (si * v.e - sp2)); });
     B[L.thr + i] = bidi_max(0.0f, thr_r + (si - L.sparsity) * L.learn_threshold);
   }
+  if (tid == 0) tma_store_commit_and_wait();  // the rows in shared memory must outlive the bulk store's reads
 }
 
 } // namespace bidi

@@ -111,6 +111,11 @@ struct LayerHost {
   WinHost ff, rec, lat, fb, pred;
   ColumnsHost col;
   std::vector<int> dense_mask;  // LayerDev::dense_mask
+  // layers the dense fused coder can run: the region that holds the feed-forward + recurrent weights (and one for
+  // their traces) in either layout -- slot planes (ff at region, rec at region + rec_plane) or rows (WinDev::row_pitch)
+  bool dense_geom = false;
+  long long w_region = -1, tr_region = -1, rec_plane = 0, region_len = 0;
+  int row_nf = 0, row_pitch = 0;
 };
 
 } // namespace
@@ -143,7 +148,8 @@ struct bidi_engine {
   cudaStream_t side = nullptr;                     // second branch of the step graph (coder learning, see record_step)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool overlap_learn = true;
-  bool fuse_learn = true;                          // dense-coder layers learn in the coder kernel's tail (option "fuse_learn")
+  std::vector<int> dense_rows;                     // per layer: its feed-forward/recurrent weights are currently laid out as rows (apply_layout)
+  bool state_touched = false;                      // some state beyond the zero/threshold initialisation may be in the blobs
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_in = nullptr;                     // the last bidi_set_inputs' host->device copy has read the host buffer
   // one graph per value of the learn flag
@@ -421,11 +427,11 @@ int mirror_release(bidi_engine* h) {
 // Serialised list <-> slot planes inside a host blob image.
 template <class F> void walk_list(const WinHost& w, bool trace, float* blob, F&& f) {
   float* base = blob + (trace ? w.d.tr_off : w.d.w_off);
-  const long long U = w.d.U;
+  const long long U = w.d.U, ss = w.d.row_pitch ? 1 : U, us = w.d.row_pitch ? w.d.row_pitch : 1;
   for (int uy = 0; uy < w.d.uh; uy++)
     for (int ux = 0; ux < w.d.uw; ux++) {
       const long long u = ux + (long long)uy * w.d.uw;
-      for_each_conn_host(w, ux, uy, [&](int s, int) { f(base[(long long)s * U + u]); });
+      for_each_conn_host(w, ux, uy, [&](int s, int) { f(base[(long long)s * ss + u * us]); });
     }
 }
 
@@ -690,7 +696,7 @@ void record_step(Recorder& R, bool learn) {
   // writes, so in the step graph it is a second branch: beside the down pass, and -- where every layer's up pass is
   // one fused launch -- already beside the up pass of the layers above.
   // layers on the dense fused coder kernel learn in that kernel's tail (bidi_coder_dense.cuh)
-  auto learns_in_coder = [&](int l) { return h->coder_cta[l] == 2 && !h->force_phase_kernels && !R.collect && h->fuse_learn; };
+  auto learns_in_coder = [&](int l) { return h->dense_rows[l] != 0; };
   auto record_learn_layer = [&](int l) {
     if (learns_in_coder(l)) return;
     if (h->tiled[l]) launch_tile(R, "ic_learn", bidi::k_t_ic_learn, tiles_of(A, ly[l].nh), 0, ly[l], l, (int)(V != BIDI_ITERATIVE));
@@ -702,7 +708,7 @@ void record_step(Recorder& R, bool learn) {
   const bool fork_learn = learn && any_separate_learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing;
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
-    if (h->coder_cta[l] && !h->force_phase_kernels && !R.collect) { // whole up pass of the layer in one launch
+    if (h->coder_cta[l] && !h->force_phase_kernels && !R.collect && (h->coder_cta[l] != 2 || h->dense_rows[l])) { // whole up pass of the layer in one launch
       const long long nxt = l < L - 1 ? ly[l + 1].vis_input : -1LL;
       R.before("coder");
       if (h->coder_cta[l] == 2) {  // windows span the grid: dense rows (bidi_coder_dense.cuh)
@@ -802,6 +808,59 @@ void record_step(Recorder& R, bool learn) {
   }
 }
 
+// ---- layout of the layers the dense fused coder runs (bidi_coder_dense.cuh): rows while that kernel is the layer's
+// path, slot planes while any other kernel family is (the per-phase kernels, the general fused kernel, the cooperative
+// step -- all of which the tests select through bidi_set_option).  Switching converts every agent's region in place.
+bool dense_wanted(const bidi_engine* h, int l) { return h->coder_cta[l] == 2 && !h->force_phase_kernels && h->coop_mode == 0; }
+
+void convert_region(float* R, const LayerHost& H, int nh, bool to_rows) {
+  std::vector<float> tmp(R, R + H.region_len);
+  std::fill(R, R + H.region_len, 0.0f);
+  const int nsf = H.ff.d.nslots, nsr = H.rec.d.r >= 0 ? H.rec.d.nslots : 0, pitch = H.row_pitch, nf = H.row_nf;
+  for (int u = 0; u < nh; u++) {
+    for (int s = 0; s < nsf; s++) {
+      const long long row = (long long)u * pitch + s, pl = (long long)s * nh + u;
+      if (to_rows) R[row] = tmp[pl]; else R[pl] = tmp[row];
+    }
+    for (int k = 0; k < nsr; k++) {
+      const long long row = (long long)u * pitch + nf + k, pl = H.rec_plane + (long long)k * nh + u;
+      if (to_rows) R[row] = tmp[pl]; else R[pl] = tmp[row];
+    }
+  }
+}
+
+int apply_layout(bidi_engine* h) {
+  bool changed = false;
+  for (int l = 0; l < h->L; l++) {
+    LayerHost& H = h->hl[l];
+    if (!H.dense_geom) continue;
+    const int want = dense_wanted(h, l) ? 1 : 0;
+    if (want == h->dense_rows[l]) continue;
+    if (h->state_touched)
+      for (int a = 0; a < h->A; a++) {
+        int rc = mirror_load(h, a);
+        if (rc) return rc;
+        convert_region(h->mirror.data() + H.w_region, H, h->layers[l].nh, want != 0);
+        if (H.tr_region >= 0) convert_region(h->mirror.data() + H.tr_region, H, h->layers[l].nh, want != 0);
+        h->mirror_dirty = true;
+      }
+    const bool rec = H.rec.d.r >= 0;
+    H.ff.d.row_pitch = want ? H.row_pitch : 0;
+    if (rec) { H.rec.d.row_pitch = H.ff.d.row_pitch; H.rec.d.w_off = H.w_region + (want ? H.row_nf : H.rec_plane); }
+    if (H.tr_region >= 0 && rec) H.rec.d.tr_off = H.tr_region + (want ? H.row_nf : H.rec_plane);
+    h->layers[l].ff = H.ff.d; h->layers[l].rec = H.rec.d;
+    h->dense_rows[l] = want;
+    changed = true;
+  }
+  if (!changed) return BIDI_OK;
+  int rc = mirror_release(h);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->d_layers, h->layers.data(), sizeof(LayerDev) * (h->L + 1), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+  return BIDI_OK;
+}
+
 // mode 0 / 1: simStep with learn off / on; 2: simStepGenerate (no learning, noise-driven coders)
 int ensure_graph(bidi_engine* h, int mode) {
   cudaGraphExec_t& exec = h->graphs[mode];
@@ -868,6 +927,7 @@ int ensure_coop(bidi_engine* h, bool learn) {
 int run_step(bidi_engine* h, bool learn, bool device_noise) {
   int rc = mirror_release(h);
   if (rc) return rc;
+  h->state_touched = true;
   if (h->strip_n > 1) return strip_step_nccl(h, learn);
   if (coop_eligible(h) && ensure_coop(h, learn)) {
     const bidi::CoopOp* ops = h->d_coop_ops[learn];
@@ -1000,10 +1060,28 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       build_win(H.ff, D.hw, D.hh, vw, vh, d.r_ff, false, false);
       build_win(H.rec, D.hw, D.hh, D.hw, D.hh, d.r_rec, true, true);
       build_win(H.lat, D.hw, D.hh, D.hw, D.hh, d.r_lat, true, true);
-      H.ff.d.w_off = al.take((long long)H.ff.d.nslots * D.nh);
-      if (d.r_rec >= 0) H.rec.d.w_off = al.take((long long)H.rec.d.nslots * D.nh);
+      H.dense_geom = is_iter(V) && H.ff.d.absx && H.ff.d.absy && (d.r_rec < 0 || (H.rec.d.absx && H.rec.d.absy));
+      if (H.dense_geom) {  // one region for either layout (slot planes now; rows once the dense coder is chosen, apply_layout)
+        auto r32 = [](long long n) { return (n + 31) / 32 * 32; };
+        H.row_nf = (D.nv + 3) & ~3;
+        H.row_pitch = bidi::dense_pitch(H.row_nf + (d.r_rec >= 0 ? ((D.nh + 3) & ~3) : 0));
+        H.rec_plane = r32((long long)H.ff.d.nslots * D.nh);
+        const long long region = std::max(H.rec_plane + (d.r_rec >= 0 ? r32((long long)H.rec.d.nslots * D.nh) : 0), r32((long long)D.nh * H.row_pitch));
+        H.region_len = region;
+        H.w_region = al.take(region);
+        H.ff.d.w_off = H.w_region;
+        if (d.r_rec >= 0) H.rec.d.w_off = H.w_region + H.rec_plane;
+        if (is_traced(V)) {
+          H.tr_region = al.take(region);
+          H.ff.d.tr_off = H.tr_region;
+          if (d.r_rec >= 0) H.rec.d.tr_off = H.tr_region + H.rec_plane;
+        }
+      } else {
+        H.ff.d.w_off = al.take((long long)H.ff.d.nslots * D.nh);
+        if (d.r_rec >= 0) H.rec.d.w_off = al.take((long long)H.rec.d.nslots * D.nh);
+      }
       if (is_iter(V)) H.lat.d.w_off = al.take((long long)H.lat.d.nslots * D.nh);
-      if (is_traced(V)) {
+      if (is_traced(V) && !H.dense_geom) {
         H.ff.d.tr_off = al.take((long long)H.ff.d.nslots * D.nh);
         if (d.r_rec >= 0) H.rec.d.tr_off = al.take((long long)H.rec.d.nslots * D.nh);
       }
@@ -1216,14 +1294,14 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       push(w->cx, &w->d.cx); push(w->cy, &w->d.cy);
       push(w->gxlo, &w->d.gx_lo); push(w->gxhi, &w->d.gx_hi); push(w->gylo, &w->d.gy_lo); push(w->gyhi, &w->d.gy_hi);
     }
-    if (l < L && is_iter(V) && H.ff.d.absx && H.ff.d.absy && (H.rec.d.r < 0 || (H.rec.d.absx && H.rec.d.absy))) {
-      // the dense coder's learning mask: which slots of a unit's row [feed-forward | recurrent] are its own connections
-      const int nh = h->layers[l].nh, nf = (h->layers[l].nv + 3) & ~3, nr = H.rec.d.r >= 0 ? (nh + 3) & ~3 : 0;
-      H.dense_mask.assign((size_t)((nf + nr) / 4) * nh, 0);
+    if (l < L && H.dense_geom) {
+      // the dense coder's learning mask: which slots of a unit's row [feed-forward | recurrent | pad] are its own connections
+      const int nh = h->layers[l].nh, nf = H.row_nf, pq = H.row_pitch / 4;
+      H.dense_mask.assign((size_t)pq * nh, 0);
       for (int u = 0; u < nh; u++) {
         const int ux = u % H.ff.d.uw, uy = u / H.ff.d.uw;
-        for_each_conn_host(H.ff, ux, uy, [&](int s, int) { H.dense_mask[(size_t)(s / 4) * nh + u] |= 1 << (s % 4); });
-        for_each_conn_host(H.rec, ux, uy, [&](int s, int) { H.dense_mask[(size_t)((nf + s) / 4) * nh + u] |= 1 << ((nf + s) % 4); });
+        for_each_conn_host(H.ff, ux, uy, [&](int s, int) { H.dense_mask[(size_t)u * pq + s / 4] |= 1 << (s % 4); });
+        for_each_conn_host(H.rec, ux, uy, [&](int s, int) { H.dense_mask[(size_t)u * pq + (nf + s) / 4] |= 1 << ((nf + s) % 4); });
       }
       push(H.dense_mask, &h->layers[l].dense_mask);
     }
@@ -1321,6 +1399,8 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       CU_CREATE(cudaFuncSetAttribute(bidi::k_coder_dense<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dense));
     }
   }
+  h->dense_rows.assign(L, 0);
+  if (apply_layout(h) != BIDI_OK) return bail(BIDI_ECUDA, g_last_error);
   // node layers with few (agent, unit) threads use the cooperative tile kernels
   h->tiled.assign(L + 1, 0);
   {
@@ -1429,6 +1509,7 @@ int bidi_set_array(bidi_engine* h, int agent, int which, int layer, const float*
   int rc = mirror_load(h, agent);
   if (rc) return rc;
   if (which == BIDI_COL_INPUT) h->col_inputs_set[agent] = 1;
+  h->state_touched = true;
   if (r.kind == ArrayRef::PLANE) memcpy(h->mirror.data() + r.off, src, sizeof(float) * len);
   else if (r.kind == ArrayRef::COLUMN) walk_column(h, r.which, r.layer, h->mirror.data(), [&](float& v) { v = *src++; });
   else if (r.kind == ArrayRef::QLIST) walk_qlist(h, r.layer, r.trace, h->mirror.data(), [&](float& v) { v = *src++; });
@@ -1466,6 +1547,7 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
   int rc = mirror_release(h);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));  // a queued step may still be reading or writing the agents being re-seeded
+  h->state_touched = true;
   const int L = h->L, V = h->cfg.variant;
   const bidi_config& g = h->cfg;
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
@@ -1480,7 +1562,8 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
     auto draw_list = [&](const WinHost& w, long long u, int ux, int uy, std::uniform_real_distribution<float>& dist) {
       if (w.d.w_off < 0) return;
       float* base = img.data() + w.d.w_off;
-      for_each_conn_host(w, ux, uy, [&](int s, int) { base[(long long)s * w.d.U + u] = dist(gen); });
+      const long long ss = w.d.row_pitch ? 1 : w.d.U, us = w.d.row_pitch ? w.d.row_pitch : 1;
+      for_each_conn_host(w, ux, uy, [&](int s, int) { base[(long long)s * ss + u * us] = dist(gen); });
     };
     auto draw_column = [&](const ColumnsDev& C, const ColumnsHost& CH, int node) { // neo/Column.cpp:22-43
       const ColRec r = col_rec(C, CH, img.data(), node);
@@ -1633,6 +1716,7 @@ int bidi_step_generate(bidi_engine* h, const float* normals, float noise) {
   int rc = mirror_release(h);
   if (rc) return rc;
   const size_t n = (size_t)h->A * h->gen_per_agent;
+  h->state_touched = true;
   CU(cudaStreamSynchronize(h->stream));  // the staging buffer may still be in flight
   if (normals) {
     memcpy(h->h_gen, normals, sizeof(float) * n);
@@ -1832,7 +1916,6 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   }
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "overlap_learn") h->overlap_learn = value != 0;
-  else if (std::string(name) == "fuse_learn") h->fuse_learn = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
       size_t smem = 0;
@@ -1850,7 +1933,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   else return fail(h, BIDI_EINVAL, "bidi_set_option: unknown option");
   for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
   coop_release(h);
-  return BIDI_OK;
+  return apply_layout(h);  // the dense coder's layers are rows exactly while that kernel is their path
 }
 
 // ---- checkpoint / resume.  The reference has none for its hierarchies (only deep::FERL's text
@@ -1860,8 +1943,14 @@ namespace {
 struct SnapHeader {
   char magic[8]; int version, config_bytes, desc_bytes, n_layers, n_agents, n_in; long long stride;
   unsigned long long step_index, noise_seed; long long first_agent;
+  unsigned layout_rows;  // bit l: layer l's coder weights are stored as rows (bidi_engine::dense_rows)
 };
-constexpr int kSnapVersion = 2;
+constexpr int kSnapVersion = 3;
+unsigned layout_mask(const bidi_engine* h) {
+  unsigned m = 0;
+  for (int l = 0; l < h->L; l++) if (h->dense_rows[l]) m |= 1u << l;
+  return m;
+}
 const char kSnapMagic[8] = {'B', 'I', 'D', 'I', 'S', 'N', 'A', 'P'};
 }
 
@@ -1878,7 +1967,7 @@ int bidi_save_snapshot(bidi_engine* h, const char* path) {
   memcpy(hd.magic, kSnapMagic, 8);
   hd.version = kSnapVersion; hd.config_bytes = (int)sizeof(bidi_config); hd.desc_bytes = (int)sizeof(bidi_layer_desc);
   hd.n_layers = h->L; hd.n_agents = h->A; hd.n_in = h->n_in; hd.stride = h->stride; hd.step_index = h->step_index;
-  hd.noise_seed = h->noise_seed; hd.first_agent = h->first_agent;
+  hd.noise_seed = h->noise_seed; hd.first_agent = h->first_agent; hd.layout_rows = layout_mask(h);
   bidi_config cfg = h->cfg;
   if (h->qnet) cfg.variant = BIDI_QPRSDR;
   bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && fwrite(&cfg, sizeof(cfg), 1, f) == 1 &&
@@ -1917,7 +2006,8 @@ int bidi_load_snapshot(bidi_engine* h, const char* path) {
   if (h->qnet) mine.variant = BIDI_QPRSDR;
   bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kSnapMagic, 8) == 0 && hd.version == kSnapVersion &&
             hd.config_bytes == (int)sizeof(bidi_config) && hd.desc_bytes == (int)sizeof(bidi_layer_desc) && hd.n_layers == h->L &&
-            hd.n_agents == h->A && hd.n_in == h->n_in && hd.stride == h->stride && fread(&cfg, sizeof(cfg), 1, f) == 1 &&
+            hd.n_agents == h->A && hd.n_in == h->n_in && hd.stride == h->stride && hd.layout_rows == layout_mask(h) &&
+            fread(&cfg, sizeof(cfg), 1, f) == 1 &&
             fread(ld.data(), sizeof(bidi_layer_desc), (size_t)h->L, f) == (size_t)h->L && memcmp(&cfg, &mine, sizeof(cfg)) == 0 &&
             memcmp(ld.data(), h->ld.data(), sizeof(bidi_layer_desc) * (size_t)h->L) == 0;
   if (!ok) { fclose(f); return fail(h, BIDI_EINVAL, std::string("bidi_load_snapshot: ") + path + " is not a snapshot of an engine with this configuration"); }
@@ -1939,6 +2029,7 @@ int bidi_load_snapshot(bidi_engine* h, const char* path) {
   cudaGetLastError();
   if (!ok) return fail(h, BIDI_EINVAL, std::string("bidi_load_snapshot: ") + path + " is truncated");
   h->step_index = hd.step_index; h->noise_seed = hd.noise_seed; h->first_agent = hd.first_agent;
+  h->state_touched = true;
   if (h->cfg.variant == BIDI_NEO_AGENT) { h->col_inputs_stale = true; std::fill(h->col_inputs_set.begin(), h->col_inputs_set.end(), 0); }
   return BIDI_OK;
 }

@@ -44,6 +44,11 @@ struct WinDev {
   const int* gy_lo; const int* gy_hi;  // [th]
   long long w_off;   // float offset of w[slot][unit] inside the agent blob, -1 if none
   long long tr_off;  // eligibility traces, same shape, -1 if none
+  // 0: slot planes, element (slot, unit) at w_off + slot*U + unit.  > 0: ROWS, element (slot, unit) at
+  // w_off + unit*row_pitch + slot -- the layout of a layer that runs the dense fused coder (bidi_coder_dense.cuh):
+  // one row per unit holding its feed-forward slots, then (rec.w_off = ff.w_off + padded feed-forward length) its
+  // recurrent ones, identical to the kernel's shared-memory image
+  int row_pitch;
 };
 
 // The columns (neo::Column) of one node layer.  Columns are stored in PAIRS (nodes
@@ -113,8 +118,8 @@ struct LayerDev {
   long long q_state, q_err, q_bias_w, q_bias_tr, q_w_off, q_tr_off;
   const float* q_mask;
   ColumnsDev col;
-  // layers whose windows span the grid (bidi_coder_dense.cuh): per (row quad q, unit u) the four bits "slot 4q+e of
-  // the row [feed-forward | recurrent] is one of u's own connections", [q][unit]; one table for all agents
+  // layers whose windows span the grid (bidi_coder_dense.cuh): per (unit u, row quad q) the four bits "slot 4q+e of
+  // the row [feed-forward | recurrent | pad] is one of u's own connections", [unit][pitch/4]; one table for all agents
   const int* dense_mask;
   // hyper-parameters (bidi_layer_desc)
   float learn_ff, learn_rec, learn_lat, learn_threshold, learn_fb, learn_pred, sparsity;
