@@ -163,13 +163,63 @@ def cpu_reference_rate(cfg, ld, cores, steps_per_thread, warmup=10):
     return kind, hs, timed
 
 
+def cpu_baseline_dict(value, cores, kind, sample):
+    """per_thread: the figure that is comparable between boxes with different core counts."""
+    return {"value": value, "unit": "agent-steps/s", "cores": cores, "per_thread": value / max(1, cores), "kind": kind, "sample": sample}
+
+
+def hierarchy_cpu_rate(cfg, ld, frames, steps, warmup=3):
+    """agent-steps/s of the reference's CPU code on ONE thread for a single hierarchy (C1 / C4): the reference is
+    single threaded and a single agent cannot use more."""
+    from oracle import pyoracle
+    kind = "reference" if pyoracle.have_ref() else "port"
+    cls = pyoracle.RefHierarchy if kind == "reference" else pyoracle.OracleHierarchy
+    h = cls(cfg, ld, 1234)
+    h.run(frames, warmup)
+
+    def timed(n):
+        t0 = time.perf_counter()
+        h.run(frames, n)
+        return time.perf_counter() - t0
+    return kind, timed
+
+
+def workload_label(args):
+    from bidinet_b200 import workloads as wl
+    if args.workload in wl.WORKLOADS:
+        return "%s, %s (%s), 1 agent" % (wl.WORKLOADS[args.workload][2], args.variant, wl.CLASS_NAMES[wl.VARIANTS[args.variant]])
+    if args.workload == "c2":
+        return "C2: neo::Agent RunnerMain hierarchy (in 8x8, 8x8->4x4, 144 columns), headless runner loop, 1 agent"
+    return "C3: neo::Agent RunnerMain hierarchy (in 8x8, 8x8->4x4, 144 columns), headless runner loop"
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path on the host cores."""
     if rank != 0:
         return
     from bidinet_b200 import config as cf
+    from bidinet_b200 import workloads as wl
+    if args.workload in wl.WORKLOADS:  # one hierarchy, one thread
+        build, frames_fn, _ = wl.WORKLOADS[args.workload]
+        cfg, ld = build(wl.VARIANTS[args.variant])
+        inner = args.ref_inner_steps
+        kind, timed = hierarchy_cpu_rate(cfg, ld, frames_fn(), inner, warmup=min(3, inner))
+        for _ in range(args.warmup):
+            timed(inner)
+        total = sum(timed(inner) for _ in range(args.steps))
+        value = inner * args.steps / total
+        print(json.dumps({
+            "impl": "reference", "metric": "agent_steps_per_s", "value": value, "unit": "agent-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_label(args), "agents": 1, "learn": True},
+            "cpu_baseline": cpu_baseline_dict(value, 1, kind, "1 thread x 1 agent x %d simSteps per bench step" % inner),
+            "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }))
+        return
     cfg, ld = cf.config_c2()
-    cores = host_cores()
+    cores = 1 if args.workload == "c2" else host_cores()
     inner = args.ref_inner_steps
     kind, hs, timed = cpu_reference_rate(cfg, ld, cores, inner)
     for _ in range(args.warmup):
@@ -182,18 +232,14 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "agent_steps_per_s", "value": value, "unit": "agent-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: neo::Agent RunnerMain hierarchy (in 8x8, 8x8->4x4, 144 columns), headless runner loop",
-                   "agents": cores, "learn": True},
-        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": workload_label(args), "agents": cores, "learn": True},
+        "cpu_baseline": cpu_baseline_dict(value, cores, kind, sample),
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
 
 
-def c5_frames(size, n_frames=8, density=0.05, seed=7):
-    """sparse random binary frames (density 5 %, seed 7), period 8."""
-    rng = np.random.RandomState(seed)
-    return (rng.rand(n_frames, size * size) < density).astype(np.float32)
+from bidinet_b200.workloads import c5_frames  # noqa: E402
 
 
 def c5_bytes_per_step(eng, rho=0.0):
@@ -314,10 +360,118 @@ def run_c5(args, rank, world, local_rank):
     }))
 
 
+def run_hierarchy(args, rank, world, local_rank):
+    """--workload c1 | c4 [--variant kwinners|iterative]: ONE hierarchy (sdr::PredictiveRSDR or sdr::IPredictiveRSDR)
+    stepping on a repeating synthetic sequence, learning on.  These single-agent configurations fit the L2 and are
+    bound by the latency of their dependent launches, not by HBM: the roofline object is reported for
+    completeness, the figures to read are value / e2e against the one-thread cpu_baseline.  Multi-GPU: replicas only
+    (every rank steps its own copy; no collective)."""
+    import torch
+    from bidinet_b200 import Engine
+    from bidinet_b200 import workloads as wl
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    build, frames_fn, _ = wl.WORKLOADS[args.workload]
+    variant = wl.VARIANTS[args.variant]
+    cfg, ld = build(variant)
+    frames = frames_fn()
+    T, n_in = frames.shape
+    K, W = args.steps, max(3, args.warmup)
+    eng = Engine(cfg, ld, n_agents=1, device=local_rank, seed=1234)
+    for kv in filter(None, os.environ.get("BIDI_OPTS", "").split(",")):
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
+    eng.load_frames(frames[:, None, :])
+    t = 0
+    for _ in range(W + args.burn_in):
+        eng.step_frame(t)
+        t += 1
+    eng.sync()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launch_count
+    eng.timer_start()
+    for _ in range(K):
+        eng.step_frame(t)
+        t += 1
+    ms = eng.timer_stop_ms()
+    eng.sync()
+    barrier()
+    launches = eng.launch_count - launches0
+    ms = _max_over_ranks(ms, dist, "cuda")
+    value = whole_job_rate(1, world, K, ms * 1e-3)
+
+    # e2e: the frame goes up from (pinned) host memory, the prediction comes back, every step
+    x, pred = eng.host_inputs(), eng.host_predictions()
+    for _ in range(W):
+        np.copyto(x[0], frames[t % T])
+        eng.set_inputs(x)
+        eng.step()
+        eng.get_predictions(out=pred)
+        t += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        np.copyto(x[0], frames[t % T])
+        eng.set_inputs(x)
+        eng.step()
+        eng.get_predictions(out=pred)
+        t += 1
+    eng.sync()
+    e2e_s = _max_over_ranks(time.perf_counter() - t0, dist, "cuda")
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    step_bytes = wl.hierarchy_bytes_per_step(eng, variant)
+    dev_bytes = eng.device_bytes
+    if dist is not None:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    peak, peak_src = hbm_peak()
+    achieved = step_bytes / (ms / K * 1e-3) / 1e9
+    out = {
+        "metric": "agent_steps_per_s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_label(args), "agents": world, "learn": True,
+                   "parallelism": "replicas only (one hierarchy per GPU, no collective)" if world > 1 else "one GPU",
+                   "l2": "working set %.1f MB fits the 126 MB L2: bound by the latency of %d dependent launches per step, not by HBM"
+                         % (dev_bytes / 1e6, launches // max(1, K)),
+                   "state_bytes_per_gpu": dev_bytes, "burn_in_steps": args.burn_in},
+        "e2e": {"value": whole_job_rate(1, world, K, e2e_s), "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,
+                "h2d_bytes_per_step": int(4 * n_in), "d2h_bytes_per_step": int(4 * n_in)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "whole step (%d launches)" % (launches // max(1, K)), "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": step_bytes, "avg_launch_ms": ms / K, "launches_per_step": 1,
+                     "note": "algorithmic bytes per step (SURVEY 8d) over the step time; the state is L2-resident"},
+        "clocks": clk,
+    }
+    if not args.no_cpu_baseline:
+        kind, timed = hierarchy_cpu_rate(cfg, ld, frames, 2)
+        n = max(3, min(20000, int(args.cpu_baseline_seconds / max(1e-6, timed(2) / 2))))
+        dt = timed(n)
+        out["cpu_baseline"] = cpu_baseline_dict(n / dt, 1, kind, "1 thread x 1 agent x %d simSteps of the same sequence (%.1f s)" % (n, dt))
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 30 for c3/c5; enough for a ~1 s timed region for the single-agent workloads)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents-per-gpu", type=int, default=4096)
@@ -328,17 +482,31 @@ def main():
     ap.add_argument("--burn-in", type=int, default=400,
                     help="untimed steps before the warm-up: by then every column cell spikes once per step and every "
                          "learning rule does its full work (a freshly initialised network does less)")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--variant", default="kwinners", choices=["kwinners", "iterative"], help="c1 / c4: which reference class")
+    ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0, help="c1 / c4: CPU time of the one-thread baseline sample")
     ap.add_argument("--c5-size", type=int, default=1024)
     ap.add_argument("--c5-transport", default="ipc", choices=["ipc", "nccl"])
     args = ap.parse_args()
     rank, world, local_rank = rank_info()
+    if args.steps is None:  # a timed region of about a second where a step is a fraction of a millisecond
+        args.steps = {"c1": 4000 if args.variant == "kwinners" else 1000, "c2": 2000,
+                      "c4": 2000 if args.variant == "kwinners" else 200}.get(args.workload, 30)
+        if args.impl == "reference":
+            args.steps = 5
+    if args.workload in ("c1", "c4") and args.burn_in == 400:
+        args.burn_in = 50
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
     if args.workload == "c5":
         run_c5(args, rank, world, local_rank)
         return
+    if args.workload in ("c1", "c4"):
+        run_hierarchy(args, rank, world, local_rank)
+        return
+    if args.workload == "c2":  # the RunnerMain hierarchy with ONE agent (per GPU: replicas only)
+        args.agents_per_gpu = 1
 
     import torch
     from bidinet_b200 import Engine
@@ -490,19 +658,20 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = host_cores()
+        cores = 1 if args.workload == "c2" else host_cores()
         kind, hs, timed = cpu_reference_rate(cfg, ld, cores, args.cpu_baseline_steps)
         dt = timed()
-        cpu = {"value": cores * args.cpu_baseline_steps / dt, "unit": "agent-steps/s", "cores": cores, "kind": kind,
-               "sample": "%d threads x 1 agent x %d simSteps of the same runner loop (%.1f s)" % (cores, args.cpu_baseline_steps, dt)}
+        cpu = cpu_baseline_dict(cores * args.cpu_baseline_steps / dt, cores, kind,
+                                "%d threads x 1 agent x %d simSteps of the same runner loop (%.1f s)" % (cores, args.cpu_baseline_steps, dt))
 
     out = {
         "metric": "agent_steps_per_s", "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: neo::Agent RunnerMain hierarchy (in 8x8, 8x8->4x4, 144 columns), headless runner loop",
+        "config": {"workload": workload_label(args),
                    "agents_per_gpu": A, "agents": world * A, "learn": True, "parallelism": "agents sharded over ranks, no collective",
-                   "l2": "per-step working set %.1f GB per GPU exceeds the 126 MB L2" % (eng.device_bytes / 1e9),
+                   "l2": ("per-step working set %.1f GB per GPU exceeds the 126 MB L2" % (eng.device_bytes / 1e9)) if A > 64 else
+                         ("working set %.1f MB fits the L2: launch-latency bound" % (eng.device_bytes / 1e6)),
                    "exploration_noise": "engine counter-based generator", "state_bytes_per_gpu": eng.device_bytes,
                    "burn_in_steps": args.burn_in},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,

@@ -164,6 +164,11 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
     tma_load_1d(w, B + L.ff.w_off, row_bytes, bar);
     // the learning tail reads the eligibility traces once, ~all iterations from now: bring them into the L2 meanwhile
     if (NEO && learn) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(B + L.ff.tr_off), "r"(row_bytes) : "memory");
+    // ... and every lateral plane (the sweeps touch only the planes of spiking neighbours)
+    if (learn && L.lat.r >= 0) {
+      const uint32_t lb = ((uint32_t)(L.lat.nslots * nh) * 4u) & ~15u;
+      if (lb) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(B + L.lat.w_off), "r"(lb) : "memory");
+    }
   }
   {
     const float* gx = vis_input_of(P, L, l, a);
@@ -411,7 +416,7 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
   if (warp < S.sweep_warps && i < nh) {
     float* __restrict__ wl = B + L.lat.w_off;
     const float si = lrn[i], sp2 = L.sparsity * L.sparsity;
-    for_each_slot_batched<8, WE>(L.lat, ux, uy,
+    for_each_slot_batched<LIGHT ? 8 : 16, WE>(L.lat, ux, uy,
         [&](int s, int t) { return WE{wl[(long long)s * nh + i], lrn[t]}; },
         [&](int s, const WE& v) { wl[(long long)s * nh + i] = bidi_max(0.0f, v.w + L.learn_lat * (si * v.e - sp2)); });
     B[L.thr + i] = bidi_max(0.0f, thr_r + (si - L.sparsity) * L.learn_threshold);
