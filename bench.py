@@ -491,7 +491,7 @@ def main():
     rank, world, local_rank = rank_info()
     if args.steps is None:  # a timed region of about a second where a step is a fraction of a millisecond
         args.steps = {"c1": 4000 if args.variant == "kwinners" else 1000, "c2": 2000,
-                      "c4": 2000 if args.variant == "kwinners" else 200}.get(args.workload, 30)
+                      "c4": 2000 if args.variant == "kwinners" else 200, "c5": 1000}.get(args.workload, 30)
         if args.impl == "reference":
             args.steps = 5
     if args.workload in ("c1", "c4") and args.burn_in == 400:
