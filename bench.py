@@ -468,6 +468,92 @@ def run_hierarchy(args, rank, world, local_rank):
     print(json.dumps(out))
 
 
+def run_c3_single_process(args):
+    """--single-process: C3 over --gpus N devices WITHOUT torchrun -- one host thread drives all devices through
+    bidi_create_sharded (agents partitioned contiguously, one engine per device, no collective).  Same metric;
+    time = the slowest shard's CUDA-event time."""
+    import torch
+    from bidinet_b200 import ShardedEngine
+    from bidinet_b200 import config as cf
+    N, A, K, W = args.gpus, args.agents_per_gpu, args.steps, max(3, args.warmup)
+    if torch.cuda.device_count() < N:
+        raise SystemExit("bench.py --single-process: %d devices asked, %d visible" % (N, torch.cuda.device_count()))
+    cfg, ld = cf.config_c2()
+    eng = ShardedEngine(cfg, ld, N * A, devices=list(range(N)), seed=1234)
+    n_in = eng.n_in
+    T = min(W + K, 64)
+    frames = base_frames(T, N * A, 0, n_in)
+    eng.load_frames(frames)
+    eng.set_feedback(FB_IDX, FB_IDX, 0.5, 0.5, 0.05, True)
+    t = 0
+    for _ in range(args.burn_in + W):
+        eng.step_frame(t)
+        t += 1
+    eng.sync()
+    clocks = ClockSampler(0)
+    clocks.start()
+    launches0 = eng.launch_count
+    eng.timer_start()
+    for _ in range(K):
+        eng.step_frame(t)
+        t += 1
+    ms = eng.timer_stop_ms()
+    eng.sync()
+    launches = eng.launch_count - launches0
+    value = N * A * K / (ms * 1e-3)
+    # e2e: host buffers of the WHOLE population through the sharded calls
+    import ctypes
+    from bidinet_b200.build import build_runner_env
+    env_lib = ctypes.CDLL(build_runner_env())
+    fp = ctypes.POINTER(ctypes.c_float)
+    env_lib.runner_env_step.argtypes = [ctypes.c_int] * 4 + [fp] * 4
+    env_lib.runner_env_step.restype = None
+    rng = np.random.RandomState(0)
+    env_noise = rng.normal(0.0, 0.05, (W + K, N * A, len(FB_IDX))).astype(np.float32)
+    pred = eng.get_predictions()
+    x = frames[t % T].copy()
+    rewards = np.zeros(N * A, np.float32)
+    fb0, nfb = int(FB_IDX[0]), len(FB_IDX)
+
+    def host_step(i, tt):
+        nonlocal pred
+        env_lib.runner_env_step(N * A, n_in, fb0, nfb, pred.ctypes.data_as(fp), env_noise[i].ctypes.data_as(fp), x.ctypes.data_as(fp),
+                                rewards.ctypes.data_as(fp))
+        eng.set_inputs(x)
+        eng.step(rewards=rewards)
+        np.copyto(x, frames[(tt + 1) % T])
+        pred = eng.get_predictions()
+
+    for i in range(W):
+        host_step(i, t)
+        t += 1
+    t0 = time.perf_counter()
+    for i in range(K):
+        host_step(W + i, t)
+        t += 1
+    eng.sync()
+    e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    step_bytes = algorithmic_bytes_per_agent_step(eng.shards[0])
+    peak, peak_src = hbm_peak()
+    achieved = step_bytes * A / (ms / K * 1e-3) / 1e9   # per GPU
+    print(json.dumps({
+        "metric": "agent_steps_per_s", "value": value, "unit": "agent-steps/s", "n_gpus": N, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_label(args), "agents_per_gpu": A, "agents": N * A, "learn": True,
+                   "parallelism": "ONE process, %d devices through bidi_create_sharded: agents partitioned contiguously, no collective" % N,
+                   "l2": "per-step working set %.1f GB per GPU exceeds the 126 MB L2" % (eng.device_bytes / N / 1e9),
+                   "exploration_noise": "engine counter-based generator", "burn_in_steps": args.burn_in},
+        "e2e": {"value": N * A * K / e2e_s, "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,
+                "h2d_bytes_per_step": int(N * A * (n_in + 1) * 4), "d2h_bytes_per_step": int(N * A * n_in * 4)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "whole step, per GPU", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": step_bytes * A,
+                     "avg_launch_ms": ms / K, "launches_per_step": 1},
+        "clocks": clk,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -485,6 +571,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--variant", default="kwinners", choices=["kwinners", "iterative"], help="c1 / c4: which reference class")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0, help="c1 / c4: CPU time of the one-thread baseline sample")
+    ap.add_argument("--single-process", action="store_true",
+                    help="c3 over --gpus N devices from ONE process (bidi_create_sharded) instead of one torchrun rank per GPU")
     ap.add_argument("--c5-size", type=int, default=1024)
     ap.add_argument("--c5-transport", default="ipc", choices=["ipc", "nccl"])
     args = ap.parse_args()
@@ -507,6 +595,9 @@ def main():
         return
     if args.workload == "c2":  # the RunnerMain hierarchy with ONE agent (per GPU: replicas only)
         args.agents_per_gpu = 1
+    if args.single_process and world == 1 and args.workload == "c3":
+        run_c3_single_process(args)
+        return
 
     import torch
     from bidinet_b200 import Engine

@@ -5,5 +5,5 @@ its sources (csrc/), the build recipe and a thin ctypes binding used by the test
 and bench.py.
 """
 from . import config  # noqa: F401
-from .engine import (ABI, BidiError, Engine, StripGroup, assemble_rows, assemble_state, load_library,  # noqa: F401
+from .engine import (ABI, BidiError, Engine, ShardedEngine, StripGroup, assemble_rows, assemble_state, load_library,  # noqa: F401
                      nccl_unique_id, strip_plan)

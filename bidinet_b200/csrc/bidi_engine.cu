@@ -2093,3 +2093,4 @@ int bidi_abi_sizes(int* config_bytes, int* layer_desc_bytes) {
 } // extern "C"
 
 #include "bidi_strip.inl"
+#include "bidi_sharded.inl"

@@ -71,6 +71,23 @@ ABI = {
     "bidi_strip_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "bidi_strip_link_nccl": (C.c_int, [C.c_void_p, C.c_void_p]),
     "bidi_strip_halo_floats": (C.c_longlong, [C.c_void_p]),
+    "bidi_create_sharded": (C.c_int, [C.POINTER(Config), C.POINTER(LayerDesc), C.c_int, _IP, C.c_int, C.POINTER(C.c_void_p)]),
+    "bidi_sharded_destroy": (None, [C.c_void_p]),
+    "bidi_sharded_last_error": (C.c_char_p, [C.c_void_p]),
+    "bidi_sharded_num_shards": (C.c_int, [C.c_void_p]),
+    "bidi_sharded_num_agents": (C.c_int, [C.c_void_p]),
+    "bidi_sharded_shard": (C.c_void_p, [C.c_void_p, C.c_int, _IP, _IP]),
+    "bidi_sharded_init_random": (C.c_int, [C.c_void_p, C.c_uint]),
+    "bidi_sharded_set_inputs": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_sharded_step": (C.c_int, [C.c_void_p, _FP, _FP, _FP, C.c_int]),
+    "bidi_sharded_get_predictions": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_sharded_get_column_actions": (C.c_int, [C.c_void_p, _FP]),
+    "bidi_sharded_load_frames": (C.c_int, [C.c_void_p, _FP, _FP, C.c_int]),
+    "bidi_sharded_step_frame": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "bidi_sharded_set_feedback": (C.c_int, [C.c_void_p, C.c_int, _IP, _IP, C.c_float, C.c_float, C.c_float, C.c_int]),
+    "bidi_sharded_sync": (C.c_int, [C.c_void_p]),
+    "bidi_sharded_timer_start": (C.c_int, [C.c_void_p]),
+    "bidi_sharded_timer_stop_ms": (C.c_int, [C.c_void_p, _FP]),
 }
 SPAN_NAMES = ["OWN_HID", "OWN_VIS", "EXT_HID", "STATE", "ACT", "VIS_RECON", "HID_RECON", "PRED_STATE"]
 
@@ -364,6 +381,133 @@ def nccl_unique_id():
     if rc != 0:
         raise BidiError("bidi_strip_nccl_unique_id failed (%d): %s" % (rc, lib.bidi_last_error(None).decode()))
     return buf.raw
+
+
+class _ShardView(Engine):
+    """An Engine view of one shard of a ShardedEngine (owned by the sharded handle: never destroyed here)."""
+
+    def __init__(self, lib, h, cfg, layers, n_agents):
+        self.lib, self.h, self.cfg, self.layers = lib, C.c_void_p(h), cfg, layers
+        self.n_layers, self.n_agents, self.n_in = cfg.n_layers, n_agents, cfg.in_width * cfg.in_height
+        self.n_columns = lib.bidi_num_columns(self.h)
+        self.n_noise = lib.bidi_num_noise(self.h)
+
+    def close(self):
+        self.h = None
+
+
+class ShardedEngine:
+    """n_agents independent hierarchies over several devices of this process (bidi_create_sharded): global agent g
+    lives on shard k with first[k] <= g < first[k] + count[k].  Same calls as Engine, arrays indexed by global agent."""
+
+    def __init__(self, cfg, layers, n_agents, devices, seed=None):
+        self.lib = load_library()
+        self.cfg, self.layers = cfg, layers
+        self.n_layers, self.n_agents, self.n_in = cfg.n_layers, n_agents, cfg.in_width * cfg.in_height
+        dev = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.bidi_create_sharded(C.byref(cfg), layers, n_agents, dev, len(devices), C.byref(h))
+        if rc != 0:
+            raise BidiError("bidi_create_sharded failed (%d): %s" % (rc, self.lib.bidi_sharded_last_error(None).decode()))
+        self.h = h
+        self.shards, self.first, self.count = [], [], []
+        for k in range(self.lib.bidi_sharded_num_shards(self.h)):
+            f, c = C.c_int(), C.c_int()
+            e = self.lib.bidi_sharded_shard(self.h, k, C.byref(f), C.byref(c))
+            self.shards.append(_ShardView(self.lib, e, cfg, layers, c.value))
+            self.first.append(f.value)
+            self.count.append(c.value)
+        self.n_columns, self.n_noise = self.shards[0].n_columns, self.shards[0].n_noise
+        if seed is not None:
+            self.init_random(seed)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise BidiError("%s failed (%d): %s" % (what, rc, self.lib.bidi_sharded_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bidi_sharded_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def locate(self, agent):
+        """(shard view, local agent index) of a global agent."""
+        for e, f, c in zip(self.shards, self.first, self.count):
+            if f <= agent < f + c:
+                return e, agent - f
+        raise IndexError(agent)
+
+    def state(self, agent=0):
+        e, a = self.locate(agent)
+        return e.state(agent=a)
+
+    def init_random(self, seed_base):
+        self._check(self.lib.bidi_sharded_init_random(self.h, seed_base), "bidi_sharded_init_random")
+
+    def set_inputs(self, x):
+        a = np.ascontiguousarray(x, dtype=np.float32)
+        assert a.size == self.n_agents * self.n_in
+        self._check(self.lib.bidi_sharded_set_inputs(self.h, _fptr(a)), "bidi_sharded_set_inputs")
+
+    def step(self, rewards=None, noise=None, learn=True):
+        r = None if rewards is None else np.ascontiguousarray(rewards, dtype=np.float32).reshape(self.n_agents)
+        u = v = None
+        if noise is not None:
+            u = np.ascontiguousarray(noise[0], dtype=np.float32)
+            v = np.ascontiguousarray(noise[1], dtype=np.float32)
+            assert u.size == v.size == self.n_agents * self.n_noise
+        self._check(self.lib.bidi_sharded_step(self.h, None if r is None else _fptr(r), None if u is None else _fptr(u),
+                                               None if v is None else _fptr(v), int(bool(learn))), "bidi_sharded_step")
+
+    def get_predictions(self):
+        out = np.empty((self.n_agents, self.n_in), dtype=np.float32)
+        self._check(self.lib.bidi_sharded_get_predictions(self.h, _fptr(out)), "bidi_sharded_get_predictions")
+        return out
+
+    def get_column_actions(self):
+        out = np.zeros((self.n_agents, self.n_columns, 3), dtype=np.float32)
+        self._check(self.lib.bidi_sharded_get_column_actions(self.h, _fptr(out)), "bidi_sharded_get_column_actions")
+        return out
+
+    def load_frames(self, frames, rewards=None):
+        f = np.ascontiguousarray(frames, dtype=np.float32).reshape(-1, self.n_agents, self.n_in)
+        r = None if rewards is None else np.ascontiguousarray(rewards, dtype=np.float32).reshape(f.shape[0], self.n_agents)
+        self._check(self.lib.bidi_sharded_load_frames(self.h, _fptr(f), None if r is None else _fptr(r), f.shape[0]),
+                    "bidi_sharded_load_frames")
+
+    def step_frame(self, t, learn=True):
+        self._check(self.lib.bidi_sharded_step_frame(self.h, int(t), int(bool(learn))), "bidi_sharded_step_frame")
+
+    def set_feedback(self, src, dst, scale=0.5, bias=0.5, noise_std=0.05, reward_from_actions=True):
+        s = np.ascontiguousarray(src, dtype=np.int32)
+        d = np.ascontiguousarray(dst, dtype=np.int32)
+        self._check(self.lib.bidi_sharded_set_feedback(self.h, s.size, s.ctypes.data_as(_IP), d.ctypes.data_as(_IP), scale, bias,
+                                                       noise_std, int(bool(reward_from_actions))), "bidi_sharded_set_feedback")
+
+    def sync(self):
+        self._check(self.lib.bidi_sharded_sync(self.h), "bidi_sharded_sync")
+
+    def timer_start(self):
+        self._check(self.lib.bidi_sharded_timer_start(self.h), "bidi_sharded_timer_start")
+
+    def timer_stop_ms(self):
+        ms = C.c_float()
+        self._check(self.lib.bidi_sharded_timer_stop_ms(self.h, C.byref(ms)), "bidi_sharded_timer_stop_ms")
+        return ms.value
+
+    @property
+    def launch_count(self):
+        return sum(e.launch_count for e in self.shards)
+
+    @property
+    def device_bytes(self):
+        return sum(e.device_bytes for e in self.shards)
 
 
 class StripGroup:

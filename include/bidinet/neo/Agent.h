@@ -75,6 +75,19 @@ public:
   void createRandom(int inputWidth, int inputHeight, int inputFeedBackRadius, const std::vector<LayerDesc>& layerDescs,
                     float initMinWeight, float initMaxWeight, float initMinInhibition, float initMaxInhibition,
                     float initThreshold, std::mt19937& generator) {
+    describe(inputWidth, inputHeight, inputFeedBackRadius, layerDescs, initMinWeight, initMaxWeight, initMinInhibition,
+             initMaxInhibition, initThreshold);
+    create();
+    drawWeights(generator);
+    _columns = bidi_num_columns(_h);
+    _noiseU.assign((size_t)_columns * 3, 0.0f);
+    _noiseV.assign((size_t)_columns * 3, 0.0f);
+  }
+
+  // The engine-side description (bidi_config + bidi_layer_desc list) of this agent's hyper-parameters and of
+  // createRandom's arguments, without creating anything: neo::AgentBatch builds many agents from one description.
+  void describe(int inputWidth, int inputHeight, int inputFeedBackRadius, const std::vector<LayerDesc>& layerDescs,
+                float initMinWeight, float initMaxWeight, float initMinInhibition, float initMaxInhibition, float initThreshold) {
     _layerDescs = layerDescs;
     _cfg = bidi_config{};
     _cfg.variant = BIDI_NEO_AGENT;
@@ -98,12 +111,10 @@ public:
       d.col_alpha_q = s._columnQAlpha; d.col_alpha_action = s._columnActionAlpha;
       d.col_expl_stddev = s._columnExplorationStdDev; d.col_expl_break = s._columnExplorationBreakChance;
     }
-    create();
-    drawWeights(generator);
-    _columns = bidi_num_columns(_h);
-    _noiseU.assign((size_t)_columns * 3, 0.0f);
-    _noiseV.assign((size_t)_columns * 3, 0.0f);
+    _cfg.n_layers = (int)_descs.size();
   }
+  const bidi_config& config() const { return _cfg; }
+  const std::vector<bidi_layer_desc>& descs() const { return _descs; }
 
   // The exploration samples are drawn from the CALLER's generator exactly as
   // neo::Column::simStep draws them (neo/Column.cpp:47-48,126-131: per column visit a
@@ -112,14 +123,19 @@ public:
   // input nodes (neo/Agent.cpp:155-156,212).  The draws do not depend on the network
   // state, so they can all be taken before the step is launched.
   void simStep(float reward, std::mt19937& generator, bool learn = true) {
+    drawExploration(generator, _noiseU.data(), _noiseV.data());
+    step(&reward, _noiseU.data(), _noiseV.data(), learn);
+  }
+  // u, v: [columns][3] in the reference's column visit order
+  void drawExploration(std::mt19937& generator, float* u, float* v) const {
     size_t k = 0;
     auto visit = [&](int nodes, float stddev, float breakChance) {
       for (int n = 0; n < nodes; n++) {
         std::uniform_real_distribution<float> dist01(0.0f, 1.0f);
         std::normal_distribution<float> pertDist(0.0f, stddev);
         for (int a = 0; a < _numColumnActions; a++, k++) {
-          _noiseU[k] = dist01(generator);
-          _noiseV[k] = _noiseU[k] < breakChance ? dist01(generator) : pertDist(generator);
+          u[k] = dist01(generator);
+          v[k] = u[k] < breakChance ? dist01(generator) : pertDist(generator);
         }
       }
     };
@@ -127,7 +143,6 @@ public:
       visit(_layerDescs[l]._width * _layerDescs[l]._height, _layerDescs[l]._columnExplorationStdDev,
             _layerDescs[l]._columnExplorationBreakChance);
     visit(_cfg.in_width * _cfg.in_height, _columnExplorationStdDev, _columnExplorationBreakChance);
-    step(&reward, _noiseU.data(), _noiseV.data(), learn);
   }
 
   void setInput(int index, float value) { _inputs[(size_t)index] = value; }

@@ -368,6 +368,40 @@ int bidi_strip_link_nccl(bidi_engine* h, const void* id128);
 /* floats this part sends per step over the transport (all exchange points, learn on) */
 long long bidi_strip_halo_floats(const bidi_engine* h);
 
+/*
+ * Many hierarchies over several devices of ONE process.  In the reference a second agent is a
+ * second object (RunnerMain.cpp:100-106) and agents never interact, so the population of n_agents identical
+ * hierarchies is cut into contiguous blocks: shard k = global agents [k*n/n_devices, (k+1)*n/n_devices) on
+ * CUDA device devices[k] (a device may repeat), one bidi_engine each.  Every call fans out: the shards
+ * enqueue on their own devices' streams and run concurrently; there is no data-path collective.  All arrays
+ * are indexed by GLOBAL agent: in / out [n_agents][n_in], rewards [n_agents], noise [n_agents][bidi_num_noise],
+ * frames [n_frames][n_agents][n_in].  Agent g is created from std::mt19937(seed_base + g) and draws the
+ * engine's own exploration noise from stream g (bidi_set_noise_stream), whatever the number of shards.
+ * bidi_sharded_shard gives the engine that holds an agent range, e.g. for bidi_get_array / bidi_set_array
+ * with the agent index local to the shard.
+ */
+typedef struct bidi_sharded bidi_sharded;
+int bidi_create_sharded(const bidi_config* cfg, const bidi_layer_desc* layers, int n_agents, const int* devices, int n_devices,
+                        bidi_sharded** out);
+void bidi_sharded_destroy(bidi_sharded* s);
+const char* bidi_sharded_last_error(const bidi_sharded* s);
+int bidi_sharded_num_shards(const bidi_sharded* s);
+int bidi_sharded_num_agents(const bidi_sharded* s);
+bidi_engine* bidi_sharded_shard(bidi_sharded* s, int k, int* first_agent, int* n_agents);
+int bidi_sharded_init_random(bidi_sharded* s, unsigned seed_base);
+int bidi_sharded_set_inputs(bidi_sharded* s, const float* in);
+int bidi_sharded_step(bidi_sharded* s, const float* rewards, const float* noise_u, const float* noise_v, int learn);
+int bidi_sharded_get_predictions(bidi_sharded* s, float* out);
+int bidi_sharded_get_column_actions(bidi_sharded* s, float* out);
+int bidi_sharded_load_frames(bidi_sharded* s, const float* frames, const float* rewards, int n_frames);
+int bidi_sharded_step_frame(bidi_sharded* s, int t, int learn);
+int bidi_sharded_set_feedback(bidi_sharded* s, int n, const int* src, const int* dst, float scale, float bias, float noise_std,
+                              int reward_from_actions);
+int bidi_sharded_sync(bidi_sharded* s);
+/* CUDA-event timing on every shard's stream; stop returns the slowest shard's milliseconds */
+int bidi_sharded_timer_start(bidi_sharded* s);
+int bidi_sharded_timer_stop_ms(bidi_sharded* s, float* ms);
+
 /* Timing helpers on the engine's stream (CUDA events), for bench.py. */
 int bidi_timer_start(bidi_engine* h);
 int bidi_timer_stop_ms(bidi_engine* h, float* ms);

@@ -18,14 +18,35 @@ GOLDEN = os.path.join(ROOT, "tests", "golden", "facade_demo.txt")
 
 @pytest.mark.gpu
 def test_facade_demo_prints_what_the_reference_prints():
-    if not os.path.exists(DEMO):
-        subprocess.check_call(["make", "-C", os.path.dirname(DEMO), "facade_demo"])
+    subprocess.check_call(["make", "-C", os.path.dirname(DEMO), "facade_demo"])  # incremental: never a stale binary
     out = subprocess.run([DEMO], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr
     got, want = out.stdout.splitlines(), open(GOLDEN).read().splitlines()
     assert len(got) == len(want)
     for k, (g, w) in enumerate(zip(got, want)):
         assert g == w, "line %d: facade %r != reference %r" % (k, g, w)
+
+
+@pytest.mark.gpu
+def test_agent_batch_equals_separate_agents():
+    """neo::AgentBatch over two shards (bidi_create_sharded) against separate neo::Agent objects, bit for bit."""
+    d = os.path.dirname(DEMO)
+    subprocess.check_call(["make", "-C", d, "batch_demo"])
+    out = subprocess.run([os.path.join(d, "batch_demo")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.strip().endswith("mismatches 0")
+
+
+@pytest.mark.gpu
+@pytest.mark.gpu2
+def test_agent_batch_on_two_devices():
+    from conftest import require_two_gpus
+    require_two_gpus()
+    d = os.path.dirname(DEMO)
+    subprocess.check_call(["make", "-C", d, "batch_demo"])
+    out = subprocess.run([os.path.join(d, "batch_demo"), "0", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "shards 2" in out.stdout and out.stdout.strip().endswith("mismatches 0")
 
 
 def test_reference_build_still_matches_golden():
