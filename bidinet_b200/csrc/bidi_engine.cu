@@ -24,6 +24,7 @@
 #include "bidi_grid.cuh"
 #include "bidi_coop.cuh"
 #include "bidi_qnet.cuh"
+#include "bidi_env.cuh"
 
 namespace {
 
@@ -160,6 +161,8 @@ struct bidi_engine {
   long long launches = 0;
   unsigned long long step_index = 0, noise_seed = 0x5DEECE66DULL;
   long long first_agent = 0;                       // global index of agent 0 (bidi_set_noise_stream)
+  // batched headless environment (bidi_env_*, bidi_env.cuh)
+  int env_kind = 0; float* d_env = nullptr; float* d_env_noise = nullptr; int env_steps = 0;
   // feedback taps (bidi_set_feedback)
   int fb_n = 0; int* d_fb_src = nullptr; int* d_fb_dst = nullptr; float fb_scale = 0, fb_bias = 0, fb_std = 0; int fb_reward = 0;
   // kernel profiling (bidi_profile_select): external events around the launches of one kernel
@@ -979,7 +982,7 @@ void bidi_destroy(bidi_engine* h) {
   for (auto& g : h->graphs) if (g) cudaGraphExecDestroy(g);
   cudaFree(h->d_blob); cudaFree(h->d_in0); cudaFree(h->d_pred); cudaFree(h->d_rewards); cudaFree(h->d_noise_u);
   cudaFree(h->d_noise_v); cudaFree(h->d_col_actions); cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
-  cudaFree(h->d_frame_noise_u); cudaFree(h->d_frame_noise_v);
+  cudaFree(h->d_frame_noise_u); cudaFree(h->d_frame_noise_v); cudaFree(h->d_env); cudaFree(h->d_env_noise);
   cudaFree(h->d_tables); cudaFree(h->d_layers); cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
   cudaFree(h->d_qmask); cudaFree(h->d_qtables); cudaFree(h->d_gen); cudaFree(h->d_gen_scale); cudaFreeHost(h->h_gen);
   for (auto& e : h->profile_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
@@ -1866,6 +1869,70 @@ int bidi_get_noise(bidi_engine* h, float* noise_u, float* noise_v) {
   const size_t bytes = sizeof(float) * (size_t)h->A * h->n_noise;
   if (noise_u) CU(cudaMemcpyAsync(noise_u, h->d_noise_u, bytes, cudaMemcpyDeviceToHost, h->stream));
   if (noise_v) CU(cudaMemcpyAsync(noise_v, h->d_noise_v, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BIDI_OK;
+}
+
+// ---- batched headless environment (bidi_env.cuh)
+int bidi_env_attach(bidi_engine* h, int kind) {
+  if (!h || kind != BIDI_ENV_RUNNER) return fail(h, BIDI_EINVAL, "bidi_env_attach: unknown environment");
+  if (h->n_in < 20 + BIDI_ENV_JOINTS) return fail(h, BIDI_EINVAL, "bidi_env_attach: the runner needs at least 30 inputs (15 state, 4 clocks, 1 spare, 10 actions)");
+  static_assert(BIDI_ENV_FLOATS == BIDI_ENV_STATE_FLOATS, "header and kernel disagree on the environment's state size");
+  CU(cudaSetDevice(h->device));
+  if (!h->d_env) {
+    CU(cudaMalloc(&h->d_env, sizeof(float) * (size_t)h->A * BIDI_ENV_FLOATS));
+    CU(cudaMalloc(&h->d_env_noise, sizeof(float) * (size_t)h->A * BIDI_ENV_JOINTS));
+    h->device_bytes += (long long)sizeof(float) * h->A * (BIDI_ENV_FLOATS + BIDI_ENV_JOINTS);
+  }
+  h->env_kind = kind;
+  return bidi_env_reset(h);
+}
+
+int bidi_env_reset(bidi_engine* h) {
+  if (!h || !h->env_kind) return fail(h, BIDI_EINVAL, "bidi_env_reset: no environment attached");
+  CU(cudaSetDevice(h->device));
+  bidi::k_env_reset<<<grid_for(h->A, kBlock), kBlock, 0, h->stream>>>(bidi::env_default_params(), h->d_env, h->A);
+  h->launches++;
+  h->env_steps = 0;
+  return BIDI_OK;
+}
+
+int bidi_env_step(bidi_engine* h, const float* noise_u, const float* noise_v, const float* env_noise, int learn) {
+  if (!h || !h->env_kind) return fail(h, BIDI_EINVAL, "bidi_env_step: no environment attached");
+  if ((noise_u == nullptr) != (noise_v == nullptr)) return fail(h, BIDI_EINVAL, "bidi_env_step: noise_u and noise_v go together");
+  CU(cudaSetDevice(h->device));
+  const bool draws = h->cfg.variant == BIDI_NEO_AGENT || h->qnet;
+  if (noise_u || env_noise) CU(cudaStreamSynchronize(h->stream));  // the staging buffers may still be in flight
+  if (noise_u && draws) {
+    const size_t n = (size_t)h->A * h->n_noise;
+    memcpy(h->h_noise, noise_u, sizeof(float) * n);
+    memcpy(h->h_noise + n, noise_v, sizeof(float) * n);
+    CU(cudaMemcpyAsync(h->d_noise_u, h->h_noise, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->d_noise_v, h->h_noise + n, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (env_noise) {
+    CU(cudaMemcpyAsync(h->d_env_noise, env_noise, sizeof(float) * (size_t)h->A * BIDI_ENV_JOINTS, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));  // pageable source: the caller may reuse it on return
+  }
+  // the four clock inputs, RunnerMain.cpp:235-236, in the host's fp32 arithmetic like the reference's
+  float ck[4];
+  for (int a = 0; a < 4; a++) ck[a] = std::sin(h->env_steps / 60.0f * 2.0f * a * 2.0f * 3.141596f) * 0.5f + 0.5f;
+  bidi::k_env_pre<<<grid_for(h->A, kBlock), kBlock, 0, h->stream>>>(h->P, h->d_env, make_float4(ck[0], ck[1], ck[2], ck[3]), BIDI_ENV_STATE, 20,
+                                                                     BIDI_ENV_JOINTS, env_noise ? h->d_env_noise : nullptr, 0.05f,
+                                                                     h->noise_seed ^ 0xE27ULL, h->step_index, h->first_agent, h->d_rewards);
+  h->launches++;
+  int rc = run_step(h, learn != 0, draws && noise_u == nullptr);
+  if (rc) return rc;
+  bidi::k_env_post<<<grid_for(h->A, kBlock), kBlock, 0, h->stream>>>(h->P, bidi::env_default_params(), h->d_env, 20);
+  h->launches++;
+  h->env_steps++;
+  return BIDI_OK;
+}
+
+int bidi_env_get_state(bidi_engine* h, float* out) {
+  if (!h || !out || !h->env_kind) return fail(h, BIDI_EINVAL, "bidi_env_get_state: no environment attached");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(out, h->d_env, sizeof(float) * (size_t)h->A * BIDI_ENV_FLOATS, cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return BIDI_OK;
 }

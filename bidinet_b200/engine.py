@@ -52,6 +52,10 @@ ABI = {
     "bidi_get_noise": (C.c_int, [C.c_void_p, _FP, _FP]),
     "bidi_set_feedback": (C.c_int, [C.c_void_p, C.c_int, _IP, _IP, C.c_float, C.c_float, C.c_float, C.c_int]),
     "bidi_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
+    "bidi_env_attach": (C.c_int, [C.c_void_p, C.c_int]),
+    "bidi_env_reset": (C.c_int, [C.c_void_p]),
+    "bidi_env_step": (C.c_int, [C.c_void_p, _FP, _FP, _FP, C.c_int]),
+    "bidi_env_get_state": (C.c_int, [C.c_void_p, _FP]),
     "bidi_save_snapshot": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bidi_load_snapshot": (C.c_int, [C.c_void_p, C.c_char_p]),
     "bidi_profile_select": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -300,6 +304,31 @@ class Engine:
         assert s.size == d.size
         self._check(self.lib.bidi_set_feedback(self.h, s.size, s.ctypes.data_as(_IP), d.ctypes.data_as(_IP), scale, bias,
                                                noise_std, int(bool(reward_from_actions))), "bidi_set_feedback")
+
+    # ---- batched headless environment on the device (bidi_env_*)
+    def env_attach(self, kind=1):
+        self._check(self.lib.bidi_env_attach(self.h, kind), "bidi_env_attach")
+
+    def env_reset(self):
+        self._check(self.lib.bidi_env_reset(self.h), "bidi_env_reset")
+
+    def env_step(self, noise=None, env_noise=None, learn=True):
+        """One pass of the RunnerMain loop for every agent: reward and inputs from the environment, simStep, motors, physics."""
+        u = v = z = None
+        if noise is not None:
+            u = np.ascontiguousarray(noise[0], dtype=np.float32)
+            v = np.ascontiguousarray(noise[1], dtype=np.float32)
+            assert u.size == v.size == self.n_agents * self.n_noise
+        if env_noise is not None:
+            z = np.ascontiguousarray(env_noise, dtype=np.float32)
+            assert z.size == self.n_agents * 10
+        self._check(self.lib.bidi_env_step(self.h, None if u is None else _fptr(u), None if v is None else _fptr(v),
+                                           None if z is None else _fptr(z), int(bool(learn))), "bidi_env_step")
+
+    def env_state(self):
+        out = np.zeros((self.n_agents, 24), dtype=np.float32)
+        self._check(self.lib.bidi_env_get_state(self.h, _fptr(out)), "bidi_env_get_state")
+        return out
 
     def save_snapshot(self, path):
         self._check(self.lib.bidi_save_snapshot(self.h, os.fsencode(path)), "bidi_save_snapshot")

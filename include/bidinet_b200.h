@@ -287,6 +287,26 @@ int bidi_set_feedback(bidi_engine* h, int n, const int* src, const int* dst, flo
                       float noise_std, int reward_from_actions);
 
 /*
+ * A batched headless environment on the device, one instance per agent, so that the RunnerMain loop runs closed
+ * without leaving the GPU.  BIDI_ENV_RUNNER stands in for the Box2D quadruped of runner/Runner.cpp
+ * (not installable here): the same interface -- Runner::getStateVector's 15 floats (runner/Runner.cpp:260-339: ten
+ * joint angles, the body angle, four foot contacts), Runner::motorUpdate's ten targets (:341), reward = body
+ * velocity x (RunnerMain.cpp:207-210) -- over a small deterministic planar surrogate of the rigid-body world
+ * (bidi_env.cuh).  bidi_env_step is one pass of RunnerMain.cpp:204-251 for every agent:
+ *   reward <- body vx; inputs 0..14 <- state, 15..18 <- the four clock sines, 20..29 <- clamp01(prediction*0.5 +
+ *   0.5 + N(0, 0.05)); simStep(reward); action <- clamp01(prediction*0.5 + 0.5); motorUpdate; physics tick.
+ * noise_u / noise_v as for bidi_step; env_noise [n_agents][10] host: the N(0, 0.05) draws of the action feedback
+ * (NULL: the engine's generator).  The engine needs at least 30 inputs.  bidi_env_get_state: out[agent][24] =
+ * 10 joint angles, body angle, 4 contacts, body vx, angular velocity, body x, 4 foot positions, pad.
+ */
+#define BIDI_ENV_RUNNER 1
+#define BIDI_ENV_STATE_FLOATS 24
+int bidi_env_attach(bidi_engine* h, int kind);
+int bidi_env_reset(bidi_engine* h);
+int bidi_env_step(bidi_engine* h, const float* noise_u, const float* noise_v, const float* env_noise, int learn);
+int bidi_env_get_state(bidi_engine* h, float* out);
+
+/*
  * Kernel-level timing inside the step graph: the launches of the named kernel
  * ("columns", "ic_sweep", "reconstruct", "predict", ...) are bracketed by CUDA
  * events on the engine's stream.  bidi_profile_collect, called after a step,

@@ -208,6 +208,54 @@ class OracleHierarchy(_Hierarchy):
                                 _fptr(v) if v.size else None, int(bool(learn)))
 
 
+class RunnerEnv:
+    """CPU twin of the device environment BIDI_ENV_RUNNER (oracle/runner_env_oracle.c), one agent's world."""
+
+    def __init__(self):
+        lib = _lib("orc_")
+        if not hasattr(lib, "_renv_bound"):
+            lib.renv_create.restype = C.c_void_p
+            lib.renv_create.argtypes = []
+            lib.renv_destroy.restype = None
+            lib.renv_destroy.argtypes = [C.c_void_p]
+            lib.renv_reward.restype = C.c_float
+            lib.renv_reward.argtypes = [C.c_void_p]
+            for n in ("renv_state", "renv_clocks", "renv_motor_update", "renv_dump"):
+                getattr(lib, n).restype = None
+                getattr(lib, n).argtypes = [C.c_void_p, _FP]
+            lib._renv_bound = True
+        self.lib = lib
+        self.h = lib.renv_create()
+
+    def __del__(self):
+        try:
+            self.lib.renv_destroy(self.h)
+        except Exception:
+            pass
+
+    def reward(self):
+        return float(self.lib.renv_reward(self.h))
+
+    def _get(self, name, n):
+        out = np.zeros(n, dtype=np.float32)
+        getattr(self.lib, name)(self.h, _fptr(out))
+        return out
+
+    def state(self):
+        return self._get("renv_state", 15)
+
+    def clocks(self):
+        return self._get("renv_clocks", 4)
+
+    def dump(self):
+        return self._get("renv_dump", 24)
+
+    def motor_update(self, action):
+        a = np.ascontiguousarray(action, dtype=np.float32)
+        assert a.size == 10
+        self.lib.renv_motor_update(self.h, _fptr(a))
+
+
 def fnv1a64(h, arr):
     """FNV-1a-64 over the raw little-endian bytes of a float32 array."""
     for b in np.ascontiguousarray(arr, dtype="<f4").tobytes():
