@@ -9,10 +9,10 @@ members of the hierarchy objects (sdr/IPredictiveRSDR.h:101-105, neo/Agent.h:137
 """
 import ctypes as C
 
-KWINNERS, ITERATIVE, NEO_HIERARCHY, NEO_AGENT, QPRSDR = 0, 1, 2, 3, 4
+KWINNERS, ITERATIVE, NEO_HIERARCHY, NEO_AGENT, QPRSDR, CSRL = 0, 1, 2, 3, 4, 5
 MAX_ACTIONS = 64
 VARIANT_NAMES = {KWINNERS: "kwinners", ITERATIVE: "iterative",
-                 NEO_HIERARCHY: "neo_hierarchy", NEO_AGENT: "neo_agent", QPRSDR: "qprsdr"}
+                 NEO_HIERARCHY: "neo_hierarchy", NEO_AGENT: "neo_agent", QPRSDR: "qprsdr", CSRL: "csrl"}
 COLUMN_ACTIONS = 3
 
 ARRAY_NAMES = [
@@ -28,6 +28,8 @@ ARRAY_NAMES = [
     "COL_PREV_VALUE", "PREDICTION",
     "Q_STATE", "Q_ERROR", "Q_BIAS_W", "Q_BIAS_TRACE", "Q_FF_W", "Q_FF_TRACE",
     "QCONN_W", "QCONN_TRACE", "ACT_PREDICTED", "ACT_DERIVE", "ACT_EXPL", "ACT_ERROR", "Q_PREV_VALUE",
+    "FB_TRACE", "PRED_TRACE", "P_LOCAL_REWARD", "COL_ACT_ERROR", "COL_CELL_ACT_STATE", "COL_CELL_ACT_ERROR",
+    "COL_AVG_SURPRISE", "REWARD_OFFSETS",
 ]
 ARRAY = {n: i for i, n in enumerate(ARRAY_NAMES)}
 # arrays that hold a per-unit connection list (bidi_conn_counts is defined for them)
@@ -53,6 +55,8 @@ class LayerDesc(C.Structure):
         ("col_alpha_ff", C.c_float), ("col_alpha_lat", C.c_float), ("col_alpha_threshold", C.c_float),
         ("col_alpha_q", C.c_float), ("col_alpha_action", C.c_float),
         ("col_expl_stddev", C.c_float), ("col_expl_break", C.c_float),
+        ("csrl_n_recurrent", C.c_int), ("csrl_derive_iterations", C.c_int),
+        ("csrl_derive_alpha", C.c_float), ("csrl_surprise_factor", C.c_float),
     ]
 
 
@@ -74,6 +78,10 @@ class Config(C.Structure):
         ("q_expl_break", C.c_float), ("q_expl_stddev", C.c_float), ("q_gamma", C.c_float), ("q_gamma_lambda", C.c_float),
         ("q_derive_iterations", C.c_int), ("q_n_actions", C.c_int),
         ("q_action_idx", C.c_int * MAX_ACTIONS), ("q_anti_idx", C.c_int * MAX_ACTIONS),
+        ("csrl_n_recurrent", C.c_int), ("csrl_derive_iterations", C.c_int),
+        ("csrl_iter_settle", C.c_int), ("csrl_iter_measure", C.c_int),
+        ("csrl_derive_alpha", C.c_float), ("csrl_surprise_factor", C.c_float),
+        ("csrl_avg_surprise_decay", C.c_float), ("csrl_leak", C.c_float),
     ]
 
 
@@ -104,9 +112,25 @@ _LAYER_DEFAULTS = {
         baseline_decay=0.01, sensitivity=6.0),
 }
 _LAYER_DEFAULTS[NEO_AGENT] = dict(_LAYER_DEFAULTS[NEO_HIERARCHY], **_COLUMN_DEFAULTS)
+# deep/CSRL.h:77-101 (LayerDesc) and :213-242 (the CSRL object's members for the input nodes)
+_LAYER_DEFAULTS[CSRL] = dict(
+    width=16, height=16, r_ff=5, r_rec=4, r_lat=4, r_pred=4, r_fb=5,
+    learn_ff=0.01, learn_rec=0.01, learn_lat=0.2, learn_fb=0.05, learn_pred=0.05,
+    iter_settle=17, iter_measure=4, leak=0.1, lambda_=0.95, weight_decay=0.0001, max_weight_delta=0.5,
+    sparsity=0.08, learn_threshold=0.01, avg_surprise_decay=0.01,
+    col_cells=8, col_sparsity=0.2, col_gamma=0.99, col_gamma_lambda=0.95,
+    col_alpha_ff=0.05, col_alpha_lat=0.2, col_alpha_threshold=0.01, col_alpha_q=0.02, col_alpha_action=0.2,
+    col_expl_stddev=0.1, col_expl_break=0.01,
+    csrl_n_recurrent=4, csrl_derive_iterations=30, csrl_derive_alpha=0.05, csrl_surprise_factor=2.0)
+_CSRL_CONFIG_DEFAULTS = dict(
+    learn_infb=0.05, col_cells=8, col_sparsity=0.2, col_gamma=0.99, col_gamma_lambda=0.95,
+    col_alpha_ff=0.05, col_alpha_lat=0.1, col_alpha_threshold=0.005, col_alpha_q=0.02, col_alpha_action=0.2,
+    col_expl_stddev=0.1, col_expl_break=0.01,
+    csrl_n_recurrent=4, csrl_derive_iterations=30, csrl_iter_settle=17, csrl_iter_measure=4,
+    csrl_derive_alpha=0.05, csrl_surprise_factor=2.0, csrl_avg_surprise_decay=0.01, csrl_leak=0.1)
 _LAYER_DEFAULTS[QPRSDR] = _LAYER_DEFAULTS[ITERATIVE]  # sdr::QPRSDR owns an sdr::IPredictiveRSDR
 
-_LEARN_INFB = {KWINNERS: 0.0, ITERATIVE: 0.05, NEO_HIERARCHY: 0.1, NEO_AGENT: 0.1, QPRSDR: 0.05}
+_LEARN_INFB = {KWINNERS: 0.0, ITERATIVE: 0.05, NEO_HIERARCHY: 0.1, NEO_AGENT: 0.1, QPRSDR: 0.05, CSRL: 0.05}
 # sdr/QPRSDR.h:96-106
 _Q_DEFAULTS = dict(q_alpha=0.01, q_action_alpha=0.1, q_derive_iterations=32, q_derive_alpha=0.05,
                    q_expl_break=0.01, q_expl_stddev=0.05, q_gamma=0.99, q_gamma_lambda=0.98)
@@ -146,6 +170,10 @@ def make_config(variant, in_width, in_height, layers, r_infb=0,
         setattr(cfg, k, v)
     for k, v in _Q_DEFAULTS.items():
         setattr(cfg, k, v)
+    if variant == CSRL:  # actions = the input cells of type _action; no anti-action cells
+        for k, v in _CSRL_CONFIG_DEFAULTS.items():
+            setattr(cfg, k, v)
+        anti_actions = list(actions)
     assert len(actions) == len(anti_actions) <= MAX_ACTIONS
     cfg.q_n_actions = len(actions)
     for k, (a, b) in enumerate(zip(actions, anti_actions)):
@@ -184,6 +212,16 @@ def config_q_c1():
     layers = [dict(width=16, height=16), dict(width=8, height=8), dict(width=4, height=4)]
     return make_config(QPRSDR, 16, 16, layers, r_infb=16, actions=list(range(192, 208)), anti_actions=list(range(208, 224)),
                        init=(-0.3, 0.3, 0.01, 0.05, 0.0))
+
+
+def config_csrl_small():
+    """A small deep::CSRL: input 6x5 (cells 20..25 of type _action), layers 6x6 -> 3x3, short SDRRL loops."""
+    layers = [dict(width=6, height=6, r_ff=2, r_rec=1, r_lat=2, r_pred=1, r_fb=1, csrl_n_recurrent=2, csrl_derive_iterations=5,
+                   iter_settle=5, iter_measure=2, col_cells=4),
+              dict(width=3, height=3, r_ff=2, r_rec=1, r_lat=1, r_pred=1, r_fb=1, csrl_n_recurrent=3, csrl_derive_iterations=4,
+                   iter_settle=4, iter_measure=3, col_cells=5)]
+    return make_config(CSRL, 6, 5, layers, r_infb=2, actions=[20, 21, 22, 23, 24, 25], init=(-0.3, 0.3, 0.01, 0.05, 0.05),
+                       csrl_n_recurrent=2, csrl_derive_iterations=6, csrl_iter_settle=4, csrl_iter_measure=2, col_cells=3)
 
 
 def config_c2():

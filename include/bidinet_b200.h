@@ -37,7 +37,8 @@ enum bidi_variant {
   BIDI_ITERATIVE = 1,     /* sdr::IPredictiveRSDR   sdr/IPredictiveRSDR.cpp:138-240 */
   BIDI_NEO_HIERARCHY = 2, /* neo::PredictiveHierarchy neo/PredictiveHierarchy.cpp:137-245 */
   BIDI_NEO_AGENT = 3,     /* neo::Agent             neo/Agent.cpp:141-284 */
-  BIDI_QPRSDR = 4         /* sdr::QPRSDR: sdr::IPredictiveRSDR + the Q network and action derivation, sdr/QPRSDR.cpp:99-341 */
+  BIDI_QPRSDR = 4,        /* sdr::QPRSDR: sdr::IPredictiveRSDR + the Q network and action derivation, sdr/QPRSDR.cpp:99-341 */
+  BIDI_CSRL = 5           /* deep::CSRL: sdr::IRSDR coders + one deep::SDRRL unit per prediction node, deep/CSRL.cpp:189-449, deep/SDRRL.cpp:46-277 */
 };
 
 enum bidi_status {
@@ -75,6 +76,15 @@ typedef struct bidi_layer_desc {
   float col_sparsity, col_leak, col_gamma, col_gamma_lambda;
   float col_alpha_ff, col_alpha_lat, col_alpha_threshold, col_alpha_q, col_alpha_action;
   float col_expl_stddev, col_expl_break;
+  /* deep::CSRL only (deep/CSRL.h:29-75).  It also uses: learn_fb/learn_pred = _learnFeedBackRL/_learnPredictionRL,
+   * avg_surprise_decay, sparsity, iter_settle/iter_measure/leak (coder AND SDRRL units), lambda, weight_decay,
+   * max_weight_delta, learn_threshold, and the col_* fields for the SDRRL units (col_cells = _cellsPerColumn,
+   * col_sparsity = _cellSparsity, col_alpha_ff/lat/threshold = the _gate*Alpha, col_alpha_q = _qAlpha,
+   * col_alpha_action = _actionAlpha, col_gamma, col_gamma_lambda, col_expl_*) */
+  int csrl_n_recurrent;       /* _numRecurrentInputs */
+  int csrl_derive_iterations; /* _actionDeriveIterations */
+  float csrl_derive_alpha;    /* _actionDeriveAlpha */
+  float csrl_surprise_factor; /* _surpriseLearnFactor */
 } bidi_layer_desc;
 
 typedef struct bidi_config {
@@ -97,6 +107,11 @@ typedef struct bidi_config {
   int q_derive_iterations;
   int q_n_actions;
   int q_action_idx[BIDI_MAX_ACTIONS], q_anti_idx[BIDI_MAX_ACTIONS];
+  /* deep::CSRL only: the public members for the input nodes' SDRRL units (deep/CSRL.h:183-243); the input cells of
+   * type _action are q_action_idx[0..q_n_actions) (deep/CSRL.h:11-13, createRandom's inputTypes).  It also uses
+   * learn_infb = _learnFeedBackRL and the col_* fields as the layers do. */
+  int csrl_n_recurrent, csrl_derive_iterations, csrl_iter_settle, csrl_iter_measure;
+  float csrl_derive_alpha, csrl_surprise_factor, csrl_avg_surprise_decay, csrl_leak;
 } bidi_config;
 
 /*
@@ -133,6 +148,16 @@ enum bidi_array {
   BIDI_QCONN_W, BIDI_QCONN_TRACE,                /* _qConnections, one per node of the top layer */
   BIDI_ACT_PREDICTED, BIDI_ACT_DERIVE, BIDI_ACT_EXPL, BIDI_ACT_ERROR, /* _actionNodes: actions, then anti-actions */
   BIDI_Q_PREV_VALUE,                             /* [1] */
+  /* deep::CSRL (deep/CSRL.h:77-136) and its deep::SDRRL units (deep/SDRRL.h:8-62).  CSRL reuses the names above:
+   * P_ACTIVATION(_PREV) = _state(Prev), P_STATE(_PREV) = _stateOutput(Prev); the COL_* arrays are the SDRRL unit of
+   * every node ([node][cell]... as for neo::Column, except COL_ACT_W / COL_ACT_TRACE = _actionConnections
+   * [node][cell][action] and COL_ACT_STATE / COL_ACT_EXPL [node][2*(3 + recurrent inputs)]) */
+  BIDI_FB_TRACE, BIDI_PRED_TRACE,                /* traces of the feedback / predictive connections */
+  BIDI_P_LOCAL_REWARD,                           /* [node] _localReward */
+  BIDI_COL_ACT_ERROR,                            /* [node][action] Action::_error */
+  BIDI_COL_CELL_ACT_STATE, BIDI_COL_CELL_ACT_ERROR, /* [node][cell] Cell::_actionState, _actionError */
+  BIDI_COL_AVG_SURPRISE,                         /* [node] */
+  BIDI_REWARD_OFFSETS,                           /* _lastLayerRewardOffsets, layer n_layers-1 only */
   BIDI_ARRAY_COUNT
 };
 

@@ -95,6 +95,8 @@ typedef struct {
 /* All columns of one node layer, pooled so every array is contiguous. */
 typedef struct {
   int n, cells;
+  int na;       /* action entries per node: 3 (neo::Column) or 2*(3 + recurrent inputs) (deep::SDRRL: actions, then anti-actions) */
+  float *a_err, *cell_as, *cell_ae, *avg_surprise; /* deep::SDRRL only: Action::_error [node][na]; Cell::_actionState/_actionError [node][cell]; [node] */
   int* in_off;  /* [n+1] prefix sums of nIn */
   float *inputs, *recon_err;            /* [sum nIn] */
   float* ff_w;                          /* [node][cell][input] at cells*in_off[node] */
@@ -109,8 +111,9 @@ typedef struct {
 typedef struct {
   int n;
   float *state, *state_prev, *act, *act_prev, *baseline;
+  float* local_reward; /* deep::CSRL only */
   conns fb, pred;
-  columns col;
+  columns col;         /* neo::Column per node, or deep::SDRRL per node (deep::CSRL) */
 } pnodes;
 
 /* sdr::QPRSDR (sdr/QPRSDR.h:10-75): a sparse Q network over the hierarchy's grids; only
@@ -137,6 +140,7 @@ typedef struct {
   coder cod[BIDI_MAX_LAYERS];
   pnodes pn[BIDI_MAX_LAYERS + 1]; /* pn[L] = input prediction nodes */
   float* prediction;              /* k-winners only */
+  float* reward_offsets;          /* deep::CSRL only: _lastLayerRewardOffsets [units of the top layer] */
   mt19937 gen;
 } oracle;
 
@@ -177,7 +181,7 @@ static void build_conns(conns* c, int n_units, int uw, int tw, int th, int radiu
 static void free_conns(conns* c) { free(c->off); free(c->idx); free(c->w); free(c->tr); }
 
 static void alloc_columns(columns* c, int n, int cells, const int* n_in) {
-  c->n = n; c->cells = cells;
+  c->n = n; c->cells = cells; c->na = 3;
   c->in_off = (int*)calloc((size_t)n + 1, sizeof(int));
   for (int i = 0; i < n; i++) c->in_off[i + 1] = c->in_off[i] + n_in[i];
   size_t tot = (size_t)c->in_off[n], nc = (size_t)n * cells;
@@ -263,12 +267,14 @@ static void q_create_random(oracle* o) {
   q->prev_value[0] = 0.0f; /* _prevValue is not initialised by the reference (sdr/QPRSDR.h:66); 0 here and in the harness */
 }
 
+static void csrl_create(oracle* o);
 void* orc_create(const bidi_config* cfg, const bidi_layer_desc* layers, unsigned seed) {
   if (cfg->n_layers < 1 || cfg->n_layers > BIDI_MAX_LAYERS) return NULL;
   oracle* o = (oracle*)calloc(1, sizeof(oracle));
   o->cfg = *cfg; o->L = cfg->n_layers; o->n_in = cfg->in_width * cfg->in_height;
   memcpy(o->ld, layers, sizeof(bidi_layer_desc) * (size_t)o->L);
   mt_seed(&o->gen, seed);
+  if (cfg->variant == BIDI_CSRL) { csrl_create(o); return o; }
   const int V = cfg->variant, L = o->L;
   const int kw = V == BIDI_KWINNERS, agent = V == BIDI_NEO_AGENT;
   const int traced = V == BIDI_NEO_HIERARCHY || V == BIDI_NEO_AGENT;
@@ -634,7 +640,7 @@ static col_params input_col_params(const bidi_config* g) {
 
 int orc_num_columns(void* h) {
   oracle* o = (oracle*)h;
-  if (o->cfg.variant != BIDI_NEO_AGENT) return 0;
+  if (o->cfg.variant != BIDI_NEO_AGENT && o->cfg.variant != BIDI_CSRL) return 0;
   int n = 0;
   for (int l = 0; l <= o->L; l++) n += o->pn[l].n;
   return n;
@@ -657,10 +663,14 @@ static void draw_noise(const oracle* o, mt19937* g, float* u, float* v) {
   }
 }
 static void q_draw_noise(const oracle* o, mt19937* g, float* u, float* v);
+static int csrl_num_noise(const oracle* o);
+static void csrl_draw_noise(const oracle* o, mt19937* g, float* u, float* v);
+static void step_csrl(oracle* o, float reward, const float* u, const float* v, int learn);
 int orc_peek_noise(void* h, float* u, float* v) {
   oracle* o = (oracle*)h;
   mt19937 g = o->gen;
   if (o->cfg.variant == BIDI_QPRSDR) { q_draw_noise(o, &g, u, v); return 0; }
+  if (o->cfg.variant == BIDI_CSRL) { csrl_draw_noise(o, &g, u, v); return 0; }
   if (o->cfg.variant != BIDI_NEO_AGENT) return -1;
   draw_noise(o, &g, u, v);
   return 0;
@@ -981,6 +991,7 @@ static void step_q(oracle* o, float reward, const float* u, const float* v, int 
 
 int orc_num_noise(void* h) {
   oracle* o = (oracle*)h;
+  if (o->cfg.variant == BIDI_CSRL) return csrl_num_noise(o);
   return o->cfg.variant == BIDI_QPRSDR ? q_num_noise(o) : orc_num_columns(h) * 3;
 }
 
@@ -990,6 +1001,7 @@ void orc_step_noise(void* h, float reward, const float* u, const float* v, int l
     case BIDI_KWINNERS: step_kwinners(o, learn); break;
     case BIDI_ITERATIVE: step_iterative(o, learn); break;
     case BIDI_QPRSDR: step_iterative(o, learn); step_q(o, reward, u, v, learn); break;
+    case BIDI_CSRL: step_csrl(o, reward, u, v, learn); break;
     default: step_neo(o, reward, u, v, learn); break;
   }
 }
@@ -1001,6 +1013,15 @@ void orc_step(void* h, float reward, int learn) {
     step_iterative(o, learn);  /* the hierarchy draws nothing (sdr/IRSDR.cpp:126 never samples) */
     q_draw_noise(o, &o->gen, u, v);
     step_q(o, reward, u, v, learn);
+    free(u); free(v);
+    return;
+  }
+  if (o->cfg.variant == BIDI_CSRL) {
+    size_t n = (size_t)csrl_num_noise(o);
+    float* u = fzeros(n);
+    float* v = fzeros(n);
+    csrl_draw_noise(o, &o->gen, u, v);
+    step_csrl(o, reward, u, v, learn);
     free(u); free(v);
     return;
   }
@@ -1023,7 +1044,11 @@ static float* find_array(oracle* o, int which, int layer, long long* len) {
     if (V != BIDI_KWINNERS || layer != 0) return NULL;
     *len = o->n_in; return o->prediction;
   }
-  const int iter = V != BIDI_KWINNERS, traced = V == BIDI_NEO_HIERARCHY || V == BIDI_NEO_AGENT;
+  const int iter = V != BIDI_KWINNERS, traced = V == BIDI_NEO_HIERARCHY || V == BIDI_NEO_AGENT || V == BIDI_CSRL;
+  if (which == BIDI_REWARD_OFFSETS) {
+    if (V != BIDI_CSRL || layer != L - 1) return NULL;
+    *len = o->cod[L - 1].nh; return o->reward_offsets;
+  }
   if (which <= BIDI_REC_TRACE) {
     if (layer >= L) return NULL;
     coder* c = &o->cod[layer];
@@ -1055,6 +1080,9 @@ static float* find_array(oracle* o, int which, int layer, long long* len) {
     case BIDI_P_BASELINE: if (layer == L) return NULL; *len = p->n; return p->baseline;
     case BIDI_FB_W: *len = p->fb.off[p->n]; return p->fb.w;
     case BIDI_PRED_W: if (layer == L) return NULL; *len = p->pred.off[p->n]; return p->pred.w;
+    case BIDI_FB_TRACE: if (V != BIDI_CSRL) return NULL; *len = p->fb.off[p->n]; return p->fb.tr;
+    case BIDI_PRED_TRACE: if (V != BIDI_CSRL || layer == L) return NULL; *len = p->pred.off[p->n]; return p->pred.tr;
+    case BIDI_P_LOCAL_REWARD: if (V != BIDI_CSRL) return NULL; *len = p->n; return p->local_reward;
   }
   if (V == BIDI_QPRSDR) {
     qnet* q = &o->q;
@@ -1081,9 +1109,16 @@ static float* find_array(oracle* o, int which, int layer, long long* len) {
       }
     return NULL;
   }
-  if (V != BIDI_NEO_AGENT) return NULL;
+  if (V != BIDI_NEO_AGENT && V != BIDI_CSRL) return NULL;
   columns* c = &p->col;
   long long tot = c->in_off[c->n], nc = (long long)c->n * c->cells;
+  if (V == BIDI_CSRL)
+    switch (which) {
+      case BIDI_COL_ACT_ERROR: *len = (long long)c->n * c->na; return c->a_err;
+      case BIDI_COL_CELL_ACT_STATE: *len = nc; return c->cell_as;
+      case BIDI_COL_CELL_ACT_ERROR: *len = nc; return c->cell_ae;
+      case BIDI_COL_AVG_SURPRISE: *len = c->n; return c->avg_surprise;
+    }
   switch (which) {
     case BIDI_COL_INPUT: *len = tot; return c->inputs;
     case BIDI_COL_RECON_ERR: *len = tot; return c->recon_err;
@@ -1096,10 +1131,10 @@ static float* find_array(oracle* o, int which, int layer, long long* len) {
     case BIDI_COL_STATE: *len = nc; return c->state;
     case BIDI_COL_Q_W: *len = nc; return c->q_w;
     case BIDI_COL_Q_TRACE: *len = nc; return c->q_tr;
-    case BIDI_COL_ACT_STATE: *len = (long long)c->n * 3; return c->a_state;
-    case BIDI_COL_ACT_EXPL: *len = (long long)c->n * 3; return c->a_expl;
-    case BIDI_COL_ACT_W: *len = nc * 3; return c->a_w;
-    case BIDI_COL_ACT_TRACE: *len = nc * 3; return c->a_tr;
+    case BIDI_COL_ACT_STATE: *len = (long long)c->n * c->na; return c->a_state;
+    case BIDI_COL_ACT_EXPL: *len = (long long)c->n * c->na; return c->a_expl;
+    case BIDI_COL_ACT_W: *len = nc * c->na; return c->a_w;
+    case BIDI_COL_ACT_TRACE: *len = nc * c->na; return c->a_tr;
     case BIDI_COL_PREV_VALUE: *len = c->n; return c->prev_value;
   }
   return NULL;
@@ -1137,7 +1172,7 @@ int orc_conn_counts(void* h, int which, int layer, int* counts) {
   if (which == BIDI_FB_W && (layer < L || o->cfg.variant != BIDI_KWINNERS)) c = &o->pn[layer].fb;
   if (which == BIDI_Q_FF_W && o->cfg.variant == BIDI_QPRSDR && layer < L) c = &o->q.ql[layer].ff;
   if (c) { for (int i = 0; i < c->n_units; i++) counts[i] = c->off[i + 1] - c->off[i]; return 0; }
-  if (which == BIDI_COL_INPUT && o->cfg.variant == BIDI_NEO_AGENT) {
+  if (which == BIDI_COL_INPUT && (o->cfg.variant == BIDI_NEO_AGENT || o->cfg.variant == BIDI_CSRL)) {
     const columns* q = &o->pn[layer].col;
     for (int i = 0; i < q->n; i++) counts[i] = q->in_off[i + 1] - q->in_off[i];
     return 0;
@@ -1176,3 +1211,5 @@ void orc_run_runner(void* h, const float* frames, int n_frames, int n_in, int st
     orc_step(h, n_fb ? sum / (float)n_fb - 0.5f : 0.0f, learn);
   }
 }
+
+#include "csrl_oracle.inc"

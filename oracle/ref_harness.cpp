@@ -25,6 +25,7 @@
 #include <sdr/QPRSDR.h>
 #include <neo/PredictiveHierarchy.h>
 #include <neo/Agent.h>
+#include <deep/CSRL.h>
 #undef private
 
 #include "bidinet_b200.h"
@@ -40,6 +41,7 @@ struct Ref {
   neo::PredictiveHierarchy nh;
   neo::Agent ag;
   sdr::QPRSDR qp;
+  deep::CSRL cs;
 };
 // sdr::QPRSDR::simStep prints q on every step (sdr/QPRSDR.cpp:259); keep the harness quiet
 struct QuietCout {
@@ -128,10 +130,68 @@ template <class Nodes, class F> bool visit_columns(Nodes& nodes, int which, F&& 
   }
 }
 
+// deep::CSRL's nodes: P_ACTIVATION(_PREV) = _state(Prev), P_STATE(_PREV) = _stateOutput(Prev); the COL_* arrays
+// are the node's deep::SDRRL unit
+template <class Nodes, class F> bool visit_csrl_nodes(Nodes& nodes, int which, bool has_pred, F&& f) {
+  switch (which) {
+    case BIDI_P_STATE: for (auto& p : nodes) f(p._stateOutput); return true;
+    case BIDI_P_STATE_PREV: for (auto& p : nodes) f(p._stateOutputPrev); return true;
+    case BIDI_P_ACTIVATION: for (auto& p : nodes) f(p._state); return true;
+    case BIDI_P_ACTIVATION_PREV: for (auto& p : nodes) f(p._statePrev); return true;
+    case BIDI_P_BASELINE: if (!has_pred) return false; for (auto& p : nodes) f(p._baseline); return true;
+    case BIDI_P_LOCAL_REWARD: for (auto& p : nodes) f(p._localReward); return true;
+    case BIDI_FB_W: for (auto& p : nodes) for (auto& k : p._feedBackConnections) f(k._weight); return true;
+    case BIDI_FB_TRACE: for (auto& p : nodes) for (auto& k : p._feedBackConnections) f(k._trace); return true;
+    case BIDI_COL_INPUT: for (auto& p : nodes) for (auto& v : p._sdrrl._inputs) f(v); return true;
+    case BIDI_COL_RECON_ERR: for (auto& p : nodes) for (auto& v : p._sdrrl._reconstructionError) f(v); return true;
+    case BIDI_COL_FF_W: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) for (auto& k : c._feedForwardConnections) f(k._weight); return true;
+    case BIDI_COL_LAT_W: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) for (auto& k : c._lateralConnections) f(k._weight); return true;
+    case BIDI_COL_THRESHOLD: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) f(c._threshold); return true;
+    case BIDI_COL_ACTIVATION: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) f(c._activation); return true;
+    case BIDI_COL_SPIKE: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) f(c._spike); return true;
+    case BIDI_COL_SPIKE_PREV: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) f(c._spikePrev); return true;
+    case BIDI_COL_STATE: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) f(c._state); return true;
+    case BIDI_COL_CELL_ACT_STATE: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) f(c._actionState); return true;
+    case BIDI_COL_CELL_ACT_ERROR: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) f(c._actionError); return true;
+    case BIDI_COL_Q_W: for (auto& p : nodes) for (auto& k : p._sdrrl._qConnections) f(k._weight); return true;
+    case BIDI_COL_Q_TRACE: for (auto& p : nodes) for (auto& k : p._sdrrl._qConnections) f(k._trace); return true;
+    case BIDI_COL_ACT_STATE: for (auto& p : nodes) for (auto& a : p._sdrrl._actions) f(a._state); return true;
+    case BIDI_COL_ACT_EXPL: for (auto& p : nodes) for (auto& a : p._sdrrl._actions) f(a._exploratoryState); return true;
+    case BIDI_COL_ACT_ERROR: for (auto& p : nodes) for (auto& a : p._sdrrl._actions) f(a._error); return true;
+    case BIDI_COL_ACT_W: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) for (auto& k : c._actionConnections) f(k._weight); return true;
+    case BIDI_COL_ACT_TRACE: for (auto& p : nodes) for (auto& c : p._sdrrl._cells) for (auto& k : c._actionConnections) f(k._trace); return true;
+    case BIDI_COL_PREV_VALUE: for (auto& p : nodes) f(p._sdrrl._prevValue); return true;
+    case BIDI_COL_AVG_SURPRISE: for (auto& p : nodes) f(p._sdrrl._averageSurprise); return true;
+    default: return false;
+  }
+}
+// deep::SDRRL leaves Cell::_activation/_spike/_state/_threshold-independent scratch and Action::_error uninitialised until
+// the first simStep (deep/SDRRL.h:25-41); zero them so a dump taken before the first step is defined
+template <class Nodes> void zero_sdrrl_scratch(Nodes& nodes) {
+  for (auto& p : nodes) {
+    for (auto& c : p._sdrrl._cells) { c._activation = 0.0f; c._spike = 0.0f; c._state = 0.0f; }
+    for (auto& a : p._sdrrl._actions) a._error = 0.0f;
+  }
+}
+
 template <class F> bool visit(Ref& r, int which, int layer, F&& f) {
   const int L = r.cfg.n_layers;
   if (layer < 0 || layer > L) return false;
   switch (r.cfg.variant) {
+    case BIDI_CSRL: {
+      deep::CSRL& cs = r.cs;
+      if (which == BIDI_REWARD_OFFSETS) {
+        if (layer != L - 1) return false;
+        for (auto& v : cs._lastLayerRewardOffsets) f(v);
+        return true;
+      }
+      if (layer == L) return visit_csrl_nodes(cs._inputPredictionNodes, which, false, f);
+      auto& ly = cs._layers[layer];
+      if (visit_icoder(ly._sdr, which, true, f)) return true;
+      if (which == BIDI_PRED_W) return visit_pred_w(ly._predictionNodes, f);
+      if (which == BIDI_PRED_TRACE) { for (auto& p : ly._predictionNodes) for (auto& k : p._predictiveConnections) f(k._trace); return true; }
+      return visit_csrl_nodes(ly._predictionNodes, which, true, f);
+    }
     case BIDI_KWINNERS: {
       if (which == BIDI_PREDICTION) {
         if (layer != 0) return false;
@@ -302,6 +362,44 @@ void* ref_create(const bidi_config* cfg, const bidi_layer_desc* layers, unsigned
       zero_column_scratch(a._inputPredictionNodes);
       break;
     }
+    case BIDI_CSRL: {
+      std::vector<deep::CSRL::LayerDesc> d(L);
+      for (int l = 0; l < L; l++) {
+        const bidi_layer_desc& s = layers[l];
+        deep::CSRL::LayerDesc& t = d[l];
+        t._width = s.width; t._height = s.height;
+        t._receptiveRadius = s.r_ff; t._recurrentRadius = s.r_rec; t._lateralRadius = s.r_lat;
+        t._predictiveRadius = s.r_pred; t._feedBackRadius = s.r_fb;
+        t._numRecurrentInputs = s.csrl_n_recurrent;
+        t._learnFeedForward = s.learn_ff; t._learnRecurrent = s.learn_rec; t._learnLateral = s.learn_lat;
+        t._learnFeedBackRL = s.learn_fb; t._learnPredictionRL = s.learn_pred;
+        t._sdrIterSettle = s.iter_settle; t._sdrIterMeasure = s.iter_measure; t._sdrLeak = s.leak;
+        t._sdrLambda = s.lambda; t._sdrWeightDecay = s.weight_decay; t._sparsity = s.sparsity; t._sdrLearnThreshold = s.learn_threshold;
+        t._averageSurpriseDecay = s.avg_surprise_decay; t._surpriseLearnFactor = s.csrl_surprise_factor;
+        t._cellsPerColumn = s.col_cells; t._cellSparsity = s.col_sparsity; t._gamma = s.col_gamma; t._gammaLambda = s.col_gamma_lambda;
+        t._gateFeedForwardAlpha = s.col_alpha_ff; t._gateLateralAlpha = s.col_alpha_lat; t._gateThresholdAlpha = s.col_alpha_threshold;
+        t._qAlpha = s.col_alpha_q; t._actionAlpha = s.col_alpha_action; t._actionDeriveAlpha = s.csrl_derive_alpha;
+        t._actionDeriveIterations = s.csrl_derive_iterations;
+        t._explorationStdDev = s.col_expl_stddev; t._explorationBreak = s.col_expl_break;
+      }
+      deep::CSRL& c = r->cs;
+      c._learnFeedBackRL = cfg->learn_infb;
+      c._averageSurpriseDecay = cfg->csrl_avg_surprise_decay; c._surpriseLearnFactor = cfg->csrl_surprise_factor;
+      c._numRecurrentInputs = cfg->csrl_n_recurrent;
+      c._cellsPerColumn = cfg->col_cells; c._cellSparsity = cfg->col_sparsity; c._gamma = cfg->col_gamma; c._gammaLambda = cfg->col_gamma_lambda;
+      c._gateFeedForwardAlpha = cfg->col_alpha_ff; c._gateLateralAlpha = cfg->col_alpha_lat; c._gateThresholdAlpha = cfg->col_alpha_threshold;
+      c._qAlpha = cfg->col_alpha_q; c._actionAlpha = cfg->col_alpha_action; c._actionDeriveAlpha = cfg->csrl_derive_alpha;
+      c._actionDeriveIterations = cfg->csrl_derive_iterations;
+      c._explorationStdDev = cfg->col_expl_stddev; c._explorationBreak = cfg->col_expl_break;
+      c._sdrIterSettle = cfg->csrl_iter_settle; c._sdrIterMeasure = cfg->csrl_iter_measure; c._sdrLeak = cfg->csrl_leak;
+      std::vector<deep::CSRL::InputType> types((size_t)cfg->in_width * cfg->in_height, deep::CSRL::_state);
+      for (int k = 0; k < cfg->q_n_actions; k++) types[(size_t)cfg->q_action_idx[k]] = deep::CSRL::_action;
+      c.createRandom(cfg->in_width, cfg->in_height, cfg->r_infb, types, d, cfg->init_min_w, cfg->init_max_w,
+                     cfg->init_min_inh, cfg->init_max_inh, cfg->init_threshold, r->gen);
+      for (auto& ly : c._layers) zero_sdrrl_scratch(ly._predictionNodes);
+      zero_sdrrl_scratch(c._inputPredictionNodes);
+      break;
+    }
     default: delete r; return nullptr;
   }
   return r;
@@ -329,6 +427,7 @@ void ref_set_input(void* h, int i, float v) {
     case BIDI_QPRSDR: r.qp.setState(i, v); break;
     case BIDI_NEO_HIERARCHY: r.nh.setInput(i, v); break;
     case BIDI_NEO_AGENT: r.ag.setInput(i, v); break;
+    case BIDI_CSRL: r.cs._layers.front()._sdr.setVisibleState(i, v); break;  // setInput asserts the cell is of type _state; the harness writes any cell
   }
 }
 void ref_set_inputs(void* h, const float* in, int n) {
@@ -342,6 +441,7 @@ float ref_get_prediction(void* h, int i) {
     case BIDI_QPRSDR: return r.qp._prsdr.getPrediction(i);
     case BIDI_NEO_HIERARCHY: return r.nh.getPrediction(i);
     case BIDI_NEO_AGENT: return r.ag.getPrediction(i);
+    case BIDI_CSRL: return r.cs.getPrediction(i);
   }
   return 0.0f;
 }
@@ -357,6 +457,7 @@ void ref_step(void* h, float reward, int learn) {
     case BIDI_QPRSDR: { QuietCout quiet; r.qp.simStep(reward, r.gen, learn != 0); break; }
     case BIDI_NEO_HIERARCHY: r.nh.simStep(r.gen, learn != 0); break;
     case BIDI_NEO_AGENT: r.ag.simStep(reward, r.gen, learn != 0); break;
+    case BIDI_CSRL: r.cs.simStep(reward, r.gen, learn != 0); break;
   }
 }
 
@@ -394,6 +495,11 @@ void ref_run_runner(void* h, const float* frames, int n_frames, int n_in, int st
 int ref_num_noise(void* h);
 int ref_num_columns(void* h) {
   Ref& r = *static_cast<Ref*>(h);
+  if (r.cfg.variant == BIDI_CSRL) {
+    int n = (int)r.cs._inputPredictionNodes.size();
+    for (auto& ly : r.cs._layers) n += (int)ly._predictionNodes.size();
+    return n;
+  }
   if (r.cfg.variant != BIDI_NEO_AGENT) return 0;
   int n = (int)r.ag._inputPredictionNodes.size();
   for (auto& ly : r.ag._layers) n += (int)ly._predictionNodes.size();
@@ -414,6 +520,30 @@ int ref_peek_noise(void* h, float* u, float* v) {
       u[i] = dist01(g);
       v[i] = (u[i] < r.cfg.q_expl_break) ? dist01(g) : pertDist(g);
     }
+    return 0;
+  }
+  if (r.cfg.variant == BIDI_CSRL) {  // deep/CSRL.cpp:205,232,246-253 then the SDRRL units in visit order, deep/SDRRL.cpp:53-54,203-208
+    std::mt19937 g = r.gen;
+    size_t k = 0;
+    std::uniform_real_distribution<float> dist01(0.0f, 1.0f);
+    std::normal_distribution<float> shared(0.0f, r.cfg.col_expl_stddev);
+    for (size_t pi = 0; pi < r.cs._inputPredictionNodes.size(); pi++)
+      if (r.cs._inputTypes[pi] == deep::CSRL::_action) {
+        u[k] = dist01(g);
+        v[k] = (u[k] < r.cfg.col_expl_break) ? dist01(g) : shared(g);
+        k++;
+      }
+    auto unit = [&](int na, float stddev, float brk) {
+      std::uniform_real_distribution<float> d01(0.0f, 1.0f);
+      std::normal_distribution<float> pert(0.0f, stddev);
+      for (int a = 0; a < na; a++, k++) {
+        u[k] = d01(g);
+        v[k] = (u[k] < brk) ? d01(g) : pert(g);
+      }
+    };
+    for (int l = r.cfg.n_layers - 1; l >= 0; l--)
+      for (auto& p : r.cs._layers[l]._predictionNodes) unit(p._sdrrl.getNumActions(), r.ld[l].col_expl_stddev, r.ld[l].col_expl_break);
+    for (auto& p : r.cs._inputPredictionNodes) unit(p._sdrrl.getNumActions(), r.cfg.col_expl_stddev, r.cfg.col_expl_break);
     return 0;
   }
   if (r.cfg.variant != BIDI_NEO_AGENT) return -1;
@@ -465,6 +595,12 @@ void ref_step_generate(void* h, float noise) {
 
 int ref_num_noise(void* h) {
   Ref& r = *static_cast<Ref*>(h);
+  if (r.cfg.variant == BIDI_CSRL) {
+    int n = r.cfg.q_n_actions;
+    for (auto& ly : r.cs._layers) for (auto& p : ly._predictionNodes) n += p._sdrrl.getNumActions();
+    for (auto& p : r.cs._inputPredictionNodes) n += p._sdrrl.getNumActions();
+    return n;
+  }
   return r.cfg.variant == BIDI_QPRSDR ? r.cfg.q_n_actions : ref_num_columns(h) * BIDI_COLUMN_ACTIONS;
 }
 
@@ -505,6 +641,16 @@ int ref_conn_counts(void* h, int which, int layer, int* counts) {
       if (layer == L) { COUNT_NODES(r.nh._inputPredictionNodes) break; }
       COUNT_CODER(r.nh._layers[layer]._sdr)
       COUNT_NODES(r.nh._layers[layer]._predictionNodes) COUNT_PRED(r.nh._layers[layer]._predictionNodes)
+      break;
+    case BIDI_CSRL:
+      if (layer == L) {
+        COUNT_NODES(r.cs._inputPredictionNodes)
+        if (which == BIDI_COL_INPUT) { for (auto& p : r.cs._inputPredictionNodes) counts[k++] = p._sdrrl.getNumStates(); return 0; }
+        break;
+      }
+      COUNT_CODER(r.cs._layers[layer]._sdr)
+      COUNT_NODES(r.cs._layers[layer]._predictionNodes) COUNT_PRED(r.cs._layers[layer]._predictionNodes)
+      if (which == BIDI_COL_INPUT) { for (auto& p : r.cs._layers[layer]._predictionNodes) counts[k++] = p._sdrrl.getNumStates(); return 0; }
       break;
     case BIDI_NEO_AGENT:
       if (layer == L) {
