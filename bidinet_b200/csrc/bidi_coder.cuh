@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(512) k_coder_cta(EngineDev P, LayerDev L, int 
     B[L.spike_prev + i] = spike[i];
     if (has_next) {  // next layer's input (neo/Agent.cpp:147-151)
       if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + i * 3 + 0];
+      else if (P.csrl) st = st * B[L.sd.a_expl + (long long)i * L.sd.na + 0];
       B[next_vis_input + i] = st;
     }
   }

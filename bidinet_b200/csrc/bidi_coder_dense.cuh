@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
     B[L.spike_prev + k] = spike[k];
     if (has_next) {  // next layer's input (neo/Agent.cpp:147-151)
       if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + k * 3 + 0];
+      else if (P.csrl) st = st * B[L.sd.a_expl + (long long)k * L.sd.na + 0];
       B[next_vis_input + k] = st;
     }
   }

@@ -25,6 +25,7 @@
 #include "bidi_coop.cuh"
 #include "bidi_qnet.cuh"
 #include "bidi_env.cuh"
+#include "bidi_csrl.cuh"
 
 namespace {
 
@@ -37,6 +38,9 @@ struct WinHost {
 
 struct ColumnsHost {
   std::vector<int> in_off, rec_off, stride, in_src;
+};
+struct SdrrlHost {
+  std::vector<int> in_off, in_src;
 };
 
 // Pointers to the sections of one column inside a host blob image.  Columns are
@@ -111,6 +115,7 @@ int column_pair_stride(int nin, bool planar) {
 struct LayerHost {
   WinHost ff, rec, lat, fb, pred;
   ColumnsHost col;
+  SdrrlHost sd;
   std::vector<int> dense_mask;  // LayerDev::dense_mask
   // layers the dense fused coder can run: the region that holds the feed-forward + recurrent weights (and one for
   // their traces) in either layout -- slot planes (ff at region, rec at region + rec_plane) or rows (WinDev::row_pitch)
@@ -189,6 +194,8 @@ struct bidi_engine {
   struct PushArgs { int send0, n_sends, notify0, n_notify, await0, n_await; } push[5] = {};
   // sdr::QPRSDR: the engine runs the ITERATIVE hierarchy (cfg.variant is normalised to it) plus the Q network
   bool qnet = false;
+  bool csrl = false;                                // deep::CSRL: the ITERATIVE coders + one deep::SDRRL unit per node (bidi_csrl.cuh)
+  std::vector<int> csrl_is_action; int* d_csrl_tables = nullptr;
   int q_half = 0, q_top = 0, n_noise = 0;           // n_noise: floats per agent in noise_u / noise_v
   std::vector<std::vector<char>> q_keep;            // per layer: [slot][unit] the reference keeps the connection
   std::vector<int> q_act_index, q_a_input;
@@ -326,8 +333,8 @@ ArrayRef find_array(const bidi_engine* h, int which, int layer) {
       case BIDI_FF_W: return list(H.ff, false);
       case BIDI_REC_W: return list(H.rec, false);
       case BIDI_LAT_W: return is_iter(V) ? list(H.lat, false) : r;
-      case BIDI_FF_TRACE: return is_traced(V) ? list(H.ff, true) : r;
-      case BIDI_REC_TRACE: return is_traced(V) ? list(H.rec, true) : r;
+      case BIDI_FF_TRACE: return (is_traced(V) || h->csrl) ? list(H.ff, true) : r;
+      case BIDI_REC_TRACE: return (is_traced(V) || h->csrl) ? list(H.rec, true) : r;
     }
     return r;
   }
@@ -342,6 +349,37 @@ ArrayRef find_array(const bidi_engine* h, int which, int layer) {
     case BIDI_P_BASELINE: return layer == L ? r : plane(D.p_baseline, D.pn);
     case BIDI_FB_W: return list(H.fb, false);
     case BIDI_PRED_W: return layer == L ? r : list(H.pred, false);
+  }
+  if (h->csrl) {  // deep::CSRL: traces of the prediction weights, _localReward, and the SDRRL unit of every node (plain planes)
+    const SdrrlDev& S = D.sd;
+    const long long nc = (long long)S.n * S.cells, nan = (long long)S.n * S.na;
+    switch (which) {
+      case BIDI_FB_TRACE: return list(H.fb, true);
+      case BIDI_PRED_TRACE: return layer == L ? r : list(H.pred, true);
+      case BIDI_P_LOCAL_REWARD: return plane(D.p_mod, D.pn);
+      case BIDI_REWARD_OFFSETS: return layer == L - 1 ? plane(h->P.csrl_reward_offsets, h->layers[L - 1].nh) : r;
+      case BIDI_COL_INPUT: return plane(S.inputs, S.tot_in);
+      case BIDI_COL_RECON_ERR: return plane(S.recon_err, S.tot_in);
+      case BIDI_COL_FF_W: return plane(S.ff_w, (long long)S.tot_in * S.cells);
+      case BIDI_COL_LAT_W: return plane(S.lat_w, nc * S.cells);
+      case BIDI_COL_THRESHOLD: return plane(S.thr, nc);
+      case BIDI_COL_ACTIVATION: return plane(S.act, nc);
+      case BIDI_COL_SPIKE: return plane(S.spike, nc);
+      case BIDI_COL_SPIKE_PREV: return plane(S.spike_prev, nc);
+      case BIDI_COL_STATE: return plane(S.state, nc);
+      case BIDI_COL_CELL_ACT_STATE: return plane(S.cell_as, nc);
+      case BIDI_COL_CELL_ACT_ERROR: return plane(S.cell_ae, nc);
+      case BIDI_COL_Q_W: return plane(S.q_w, nc);
+      case BIDI_COL_Q_TRACE: return plane(S.q_tr, nc);
+      case BIDI_COL_ACT_STATE: return plane(S.a_state, nan);
+      case BIDI_COL_ACT_EXPL: return plane(S.a_expl, nan);
+      case BIDI_COL_ACT_ERROR: return plane(S.a_err, nan);
+      case BIDI_COL_ACT_W: return plane(S.a_w, nc * S.na);
+      case BIDI_COL_ACT_TRACE: return plane(S.a_tr, nc * S.na);
+      case BIDI_COL_PREV_VALUE: return plane(S.prev_value, S.n);
+      case BIDI_COL_AVG_SURPRISE: return plane(S.avg_surprise, S.n);
+    }
+    return r;
   }
   if (h->qnet && which >= BIDI_Q_STATE) {
     if (layer < L) {
@@ -702,13 +740,16 @@ void record_step(Recorder& R, bool learn) {
   auto learns_in_coder = [&](int l) { return h->dense_rows[l] != 0; };
   auto record_learn_layer = [&](int l) {
     if (learns_in_coder(l)) return;
+    if (h->csrl) { R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l); return; }  // sdr/IRSDR.cpp:321-356 with the units' _reward actions
     if (h->tiled[l]) launch_tile(R, "ic_learn", bidi::k_t_ic_learn, tiles_of(A, ly[l].nh), 0, ly[l], l, (int)(V != BIDI_ITERATIVE));
     else if (V == BIDI_ITERATIVE) R.launch("ic_learn", bidi::k_ic_learn, A * ly[l].nh, ly[l], l);
     else R.launch("neo_learn", bidi::k_neo_learn, A * ly[l].nh, ly[l], l);
   };
   bool any_separate_learn = false;
   for (int l = 0; l < L; l++) any_separate_learn = any_separate_learn || !learns_in_coder(l);
-  const bool fork_learn = learn && any_separate_learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing;
+  const bool fork_learn = learn && any_separate_learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing && !h->csrl;
+  if (h->csrl && R.collect) { R.collect_ok = false; return; }
+  const int plearn = h->csrl ? 0 : (int)learn;  // deep::CSRL's prediction weights learn through traces after the SDRRL pass
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
     if (h->coder_cta[l] && !h->force_phase_kernels && !R.collect && (h->coder_cta[l] != 2 || h->dense_rows[l])) { // whole up pass of the layer in one launch
@@ -790,15 +831,30 @@ void record_step(Recorder& R, bool learn) {
     const LayerDev& Up = ly[l < L - 1 ? l + 1 : l];
     if (V == BIDI_NEO_AGENT) record_columns(R, l);
     if (h->tiled[l] && V != BIDI_NEO_AGENT)
-      launch_tile(R, "predict", bidi::k_t_predict, tiles_of(A, Y.pn), tile_bytes(nslots_of(Y.fb) + nslots_of(Y.pred)), Y, l, (int)learn, Up.p_state,
+      launch_tile(R, "predict", bidi::k_t_predict, tiles_of(A, Y.pn), tile_bytes(nslots_of(Y.fb) + nslots_of(Y.pred)), Y, l, plearn, Up.p_state,
                   Up.p_state_prev);
-    else R.launch("predict", bidi::k_predict, A * Y.pn, Y, l, (int)learn, Up.p_state, Up.p_state_prev);
+    else R.launch("predict", bidi::k_predict, A * Y.pn, Y, l, plearn, Up.p_state, Up.p_state_prev);
   }
   if (V == BIDI_NEO_AGENT) record_columns(R, L);
   if (h->tiled[L] && V != BIDI_NEO_AGENT)
-    launch_tile(R, "predict_input", bidi::k_t_predict, tiles_of(A, ly[L].pn), tile_bytes(nslots_of(ly[L].fb)), ly[L], L, (int)learn, ly[0].p_state,
+    launch_tile(R, "predict_input", bidi::k_t_predict, tiles_of(A, ly[L].pn), tile_bytes(nslots_of(ly[L].fb)), ly[L], L, plearn, ly[0].p_state,
                 ly[0].p_state_prev);
-  else R.launch("predict_input", bidi::k_predict_input, A * h->n_in, ly[L], (int)learn, ly[0].p_state, ly[0].p_state_prev);
+  else R.launch("predict_input", bidi::k_predict_input, A * h->n_in, ly[L], plearn, ly[0].p_state, ly[0].p_state_prev);
+  if (h->csrl) {  // deep/CSRL.cpp:246-419
+    if (h->P.csrl_n_actions > 0) R.launch("csrl_explore", bidi::k_csrl_explore, A * h->P.csrl_n_actions);
+    for (int k = 0; k <= L; k++) {  // the SDRRL units: top layer first (reward flows down), the input nodes last
+      const int l = k < L ? L - 1 - k : L;
+      const size_t smem = sizeof(float) * BIDI_SDRRL_WARPS * (size_t)bidi::sdrrl_warp_floats(ly[l].sd.max_in);
+      R.before("sdrrl");
+      bidi::k_sdrrl<<<grid_for(A * ly[l].sd.n, BIDI_SDRRL_WARPS), 32 * BIDI_SDRRL_WARPS, smem, R.s()>>>(h->P, ly[l], l);
+      R.after("sdrrl");
+      R.kernels++;
+    }
+    if (learn) {
+      for (int l = 0; l < L; l++) R.launch("csrl_pred_learn", bidi::k_csrl_pred_learn, A * ly[l].pn, ly[l], l, ly[l < L - 1 ? l + 1 : l].p_state_prev);
+      R.launch("csrl_pred_learn", bidi::k_csrl_pred_learn, A * ly[L].pn, ly[L], L, ly[0].p_state_prev);
+    }
+  }
   if (fork_learn) cudaStreamWaitEvent(h->stream, h->ev_join, 0);
   else if (learn) record_learn();
   R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
@@ -814,7 +870,10 @@ void record_step(Recorder& R, bool learn) {
 // ---- layout of the layers the dense fused coder runs (bidi_coder_dense.cuh): rows while that kernel is the layer's
 // path, slot planes while any other kernel family is (the per-phase kernels, the general fused kernel, the cooperative
 // step -- all of which the tests select through bidi_set_option).  Switching converts every agent's region in place.
-bool dense_wanted(const bidi_engine* h, int l) { return h->coder_cta[l] == 2 && !h->force_phase_kernels && h->coop_mode == 0; }
+bool dense_wanted(const bidi_engine* h, int l) {
+  // (a deep::CSRL's coder learns from rewards its SDRRL units produce in the down pass: not in the coder kernel's tail)
+  return h->coder_cta[l] == 2 && !h->force_phase_kernels && h->coop_mode == 0 && !h->csrl;
+}
 
 void convert_region(float* R, const LayerHost& H, int nh, bool to_rows) {
   std::vector<float> tmp(R, R + H.region_len);
@@ -945,6 +1004,10 @@ int run_step(bidi_engine* h, bool learn, bool device_noise) {
     bidi::k_noise_q<<<grid_for((long long)h->A * h->q_half, kBlock), kBlock, 0, h->stream>>>(h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index, h->first_agent);
     h->launches++;
   }
+  if (h->csrl && device_noise) {
+    bidi::k_csrl_noise<<<grid_for((long long)h->A * h->n_noise, kBlock), kBlock, 0, h->stream>>>(h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index, h->first_agent);
+    h->launches++;
+  }
   if (h->cfg.variant == BIDI_NEO_AGENT && device_noise) {
     // the step counter changes every call, so this launch stays outside the graph
     bidi::k_noise<<<grid_for((long long)h->A * h->ncol, kBlock), kBlock, 0, h->stream>>>(
@@ -984,7 +1047,7 @@ void bidi_destroy(bidi_engine* h) {
   cudaFree(h->d_noise_v); cudaFree(h->d_col_actions); cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
   cudaFree(h->d_frame_noise_u); cudaFree(h->d_frame_noise_v); cudaFree(h->d_env); cudaFree(h->d_env_noise);
   cudaFree(h->d_tables); cudaFree(h->d_layers); cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
-  cudaFree(h->d_qmask); cudaFree(h->d_qtables); cudaFree(h->d_gen); cudaFree(h->d_gen_scale); cudaFreeHost(h->h_gen);
+  cudaFree(h->d_qmask); cudaFree(h->d_qtables); cudaFree(h->d_csrl_tables); cudaFree(h->d_gen); cudaFree(h->d_gen_scale); cudaFreeHost(h->h_gen);
   for (auto& e : h->profile_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_pred); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_noise); cudaFreeHost(h->h_actions);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -1003,8 +1066,17 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   bidi_engine* h = nullptr;
   if (!cfg || !layers || !out) return fail(h, BIDI_EINVAL, "bidi_create: null argument");
   *out = nullptr;
-  if (cfg->variant < BIDI_KWINNERS || cfg->variant > BIDI_QPRSDR) return fail(h, BIDI_EINVAL, "bidi_create: unknown variant");
-  const bool qnet = cfg->variant == BIDI_QPRSDR;
+  if (cfg->variant < BIDI_KWINNERS || cfg->variant > BIDI_CSRL) return fail(h, BIDI_EINVAL, "bidi_create: unknown variant");
+  const bool qnet = cfg->variant == BIDI_QPRSDR, csrl = cfg->variant == BIDI_CSRL;
+  if (csrl) {
+    if (cfg->q_n_actions < 0 || cfg->q_n_actions > BIDI_MAX_ACTIONS) return fail(h, BIDI_EINVAL, "bidi_create: a CSRL has 0..BIDI_MAX_ACTIONS action inputs");
+    for (int k = 0; k < cfg->q_n_actions; k++)
+      if (cfg->q_action_idx[k] < 0 || cfg->q_action_idx[k] >= cfg->in_width * cfg->in_height || (k > 0 && cfg->q_action_idx[k] <= cfg->q_action_idx[k - 1]))
+        return fail(h, BIDI_EINVAL, "bidi_create: action inputs must be inside the input and ascending");
+    if (cfg->col_cells < 1 || cfg->col_cells > 32 || cfg->csrl_n_recurrent < 0 || 2 * (3 + cfg->csrl_n_recurrent) > BIDI_SDRRL_MAX_ACTIONS ||
+        cfg->csrl_iter_measure < 1 || cfg->csrl_iter_settle < 0 || cfg->csrl_derive_iterations < 0)
+      return fail(h, BIDI_EINVAL, "bidi_create: bad SDRRL parameters of the input nodes");
+  }
   if (qnet) {
     if (cfg->q_n_actions < 1 || cfg->q_n_actions > BIDI_MAX_ACTIONS || cfg->q_derive_iterations < 0)
       return fail(h, BIDI_EINVAL, "bidi_create: a QPRSDR needs 1..BIDI_MAX_ACTIONS actions");
@@ -1020,7 +1092,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     cudaGetLastError();
     return fail(h, BIDI_ENODEV, "bidi_create: no usable CUDA device (this engine has no CPU path)");
   }
-  const int V = qnet ? BIDI_ITERATIVE : cfg->variant, L = cfg->n_layers;  // a QPRSDR owns an IPredictiveRSDR
+  const int V = (qnet || csrl) ? BIDI_ITERATIVE : cfg->variant, L = cfg->n_layers;  // a QPRSDR owns an IPredictiveRSDR; a CSRL runs IRSDR coders
   for (int l = 0; l < L; l++) {
     const bidi_layer_desc& d = layers[l];
     if (d.width < 1 || d.height < 1 || d.r_ff < 0 || d.r_lat < 0 || d.r_pred < 0 || d.r_rec < -1 || (l < L - 1 && d.r_fb < 0))
@@ -1029,6 +1101,9 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     if ((V == BIDI_NEO_HIERARCHY || V == BIDI_NEO_AGENT) && d.iter_settle < 1) return fail(h, BIDI_EINVAL, "bidi_create: no coder iterations");
     if (V == BIDI_NEO_AGENT && (d.col_cells < 1 || d.col_cells > 32 || d.col_iter < 1))
       return fail(h, BIDI_EINVAL, "bidi_create: columns need 1..32 cells and >= 1 iteration");
+    if (csrl && (d.col_cells < 1 || d.col_cells > 32 || d.csrl_n_recurrent < 0 || 2 * (3 + d.csrl_n_recurrent) > BIDI_SDRRL_MAX_ACTIONS ||
+                 d.iter_measure < 1 || d.csrl_derive_iterations < 0 || d.r_fb < 0))
+      return fail(h, BIDI_EINVAL, "bidi_create: bad SDRRL parameters in a layer descriptor");
   }
   if (V != BIDI_KWINNERS && cfg->r_infb < 0) return fail(h, BIDI_EINVAL, "bidi_create: bad input feedback radius");
   if (V == BIDI_NEO_AGENT && (cfg->col_cells < 1 || cfg->col_cells > 32 || cfg->col_iter < 1))
@@ -1037,7 +1112,8 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   const bool h_no_col_regs = getenv("BIDI_NO_COL_REGS") != nullptr;  // experiment switch: keep whole weight rows in shared memory
   h = new bidi_engine();
   h->cfg = *cfg; h->ld.assign(layers, layers + L);
-  h->cfg.variant = V; h->qnet = qnet;
+  h->cfg.variant = V; h->qnet = qnet; h->csrl = csrl;
+  const bool traced = is_traced(V) || csrl;
   h->device = device; h->A = n_agents; h->L = L; h->n_in = cfg->in_width * cfg->in_height;
   h->col_inputs_set.assign((size_t)n_agents, 0);
   h->layers.assign(L + 1, LayerDev());
@@ -1074,7 +1150,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
         H.w_region = al.take(region);
         H.ff.d.w_off = H.w_region;
         if (d.r_rec >= 0) H.rec.d.w_off = H.w_region + H.rec_plane;
-        if (is_traced(V)) {
+        if (traced) {
           H.tr_region = al.take(region);
           H.ff.d.tr_off = H.tr_region;
           if (d.r_rec >= 0) H.rec.d.tr_off = H.tr_region + H.rec_plane;
@@ -1084,17 +1160,22 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
         if (d.r_rec >= 0) H.rec.d.w_off = al.take((long long)H.rec.d.nslots * D.nh);
       }
       if (is_iter(V)) H.lat.d.w_off = al.take((long long)H.lat.d.nslots * D.nh);
-      if (is_traced(V) && !H.dense_geom) {
+      if (traced && !H.dense_geom) {
         H.ff.d.tr_off = al.take((long long)H.ff.d.nslots * D.nh);
         if (d.r_rec >= 0) H.rec.d.tr_off = al.take((long long)H.rec.d.nslots * D.nh);
       }
       D.pn = D.nh;
       D.p_state = al.take(D.pn);
       if (l < L - 1) build_win(H.fb, D.hw, D.hh, layers[l + 1].width, layers[l + 1].height, d.r_fb, false, false);
+      else if (csrl) build_win(H.fb, D.hw, D.hh, D.hw, D.hh, d.r_fb, true, false);  // the top layer looks at the rewards around its own position, deep/CSRL.cpp:92-114
       else build_win(H.fb, D.hw, D.hh, 1, 1, -1, true, false);
       build_win(H.pred, D.hw, D.hh, D.hw, D.hh, d.r_pred, true, false);
-      if (l < L - 1) H.fb.d.w_off = al.take((long long)H.fb.d.nslots * D.pn);
+      if (l < L - 1 || csrl) H.fb.d.w_off = al.take((long long)H.fb.d.nslots * D.pn);
       H.pred.d.w_off = al.take((long long)H.pred.d.nslots * D.pn);
+      if (csrl) {
+        H.fb.d.tr_off = al.take((long long)H.fb.d.nslots * D.pn);
+        H.pred.d.tr_off = al.take((long long)H.pred.d.nslots * D.pn);
+      }
       if (qnet) {
         D.q_state = al.take(D.nh); D.q_err = al.take(D.nh); D.q_bias_w = al.take(D.nh); D.q_bias_tr = al.take(D.nh);
         D.q_w_off = al.take((long long)H.ff.d.nslots * D.nh); D.q_tr_off = al.take((long long)H.ff.d.nslots * D.nh);
@@ -1115,6 +1196,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       build_win(H.pred, cfg->in_width, cfg->in_height, 1, 1, -1, true, false);
       build_win(H.ff, 1, 1, 1, 1, -1, true, false); build_win(H.rec, 1, 1, 1, 1, -1, true, false); build_win(H.lat, 1, 1, 1, 1, -1, true, false);
       H.fb.d.w_off = al.take((long long)H.fb.d.nslots * D.pn);
+      if (csrl) H.fb.d.tr_off = al.take((long long)H.fb.d.nslots * D.pn);
       D.learn_fb = cfg->learn_infb;
     }
     D.p_state_prev = al.take(D.pn); D.p_act = al.take(D.pn); D.p_act_prev = al.take(D.pn);
@@ -1172,6 +1254,71 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       C.act = al.take(nc); C.spike = al.take(nc); C.state = al.take(nc);
       C.a_state = al.take(C.n * 3LL); C.a_expl = al.take(C.n * 3LL);
     }
+  }
+  long long csrl_offsets = 0;
+  if (csrl) {  // one deep::SDRRL unit per node: plain planes in the reference's order (bidi_types.h, SdrrlDev)
+    csrl_offsets = al.take(h->layers[L - 1].nh);
+    for (int l = 0; l <= L; l++) {
+      LayerDev& D = h->layers[l];
+      LayerHost& H = h->hl[l];
+      SdrrlDev& S = D.sd;
+      S.n = D.pn;
+      if (l < L) {
+        const bidi_layer_desc& d = layers[l];
+        S.cells = d.col_cells; S.n_rec = d.csrl_n_recurrent;
+        S.sparsity = d.col_sparsity; S.gamma = d.col_gamma; S.leak = d.leak; S.a_ff = d.col_alpha_ff; S.a_lat = d.col_alpha_lat;
+        S.a_thr = d.col_alpha_threshold; S.a_q = d.col_alpha_q; S.a_act = d.col_alpha_action; S.derive_alpha = d.csrl_derive_alpha;
+        S.gamma_lambda = d.col_gamma_lambda; S.expl_std = d.col_expl_stddev; S.expl_break = d.col_expl_break;
+        S.surprise_decay = d.avg_surprise_decay; S.settle = d.iter_settle; S.measure = d.iter_measure; S.derive_iter = d.csrl_derive_iterations;
+      } else {
+        S.cells = cfg->col_cells; S.n_rec = cfg->csrl_n_recurrent;
+        S.sparsity = cfg->col_sparsity; S.gamma = cfg->col_gamma; S.leak = cfg->csrl_leak; S.a_ff = cfg->col_alpha_ff; S.a_lat = cfg->col_alpha_lat;
+        S.a_thr = cfg->col_alpha_threshold; S.a_q = cfg->col_alpha_q; S.a_act = cfg->col_alpha_action; S.derive_alpha = cfg->csrl_derive_alpha;
+        S.gamma_lambda = cfg->col_gamma_lambda; S.expl_std = cfg->col_expl_stddev; S.expl_break = cfg->col_expl_break;
+        S.surprise_decay = cfg->csrl_avg_surprise_decay; S.settle = cfg->csrl_iter_settle; S.measure = cfg->csrl_iter_measure;
+        S.derive_iter = cfg->csrl_derive_iterations;
+      }
+      S.na = 2 * (3 + S.n_rec);
+      H.sd.in_off.assign(S.n + 1, 0);
+      S.max_in = 0;
+      for (int i = 0; i < S.n; i++) {  // numStates = |feedback| + |predictive| + recurrent inputs, deep/CSRL.cpp:136,184
+        const int ux = i % H.fb.d.uw, uy = i / H.fb.d.uw;
+        int nin = S.n_rec;
+        for_each_conn_host(H.fb, ux, uy, [&](int, int) { nin++; });
+        if (l < L) for_each_conn_host(H.pred, ux, uy, [&](int, int) { nin++; });
+        H.sd.in_off[i + 1] = H.sd.in_off[i] + nin;
+        S.max_in = std::max(S.max_in, nin);
+      }
+      S.tot_in = H.sd.in_off[S.n];
+      const long long nc = (long long)S.n * S.cells, nan = (long long)S.n * S.na;
+      S.inputs = al.take(S.tot_in); S.recon_err = al.take(S.tot_in); S.ff_w = al.take((long long)S.tot_in * S.cells);
+      S.lat_w = al.take(nc * S.cells);
+      S.thr = al.take(nc); S.act = al.take(nc); S.spike = al.take(nc); S.spike_prev = al.take(nc); S.state = al.take(nc);
+      S.cell_as = al.take(nc); S.cell_ae = al.take(nc); S.q_w = al.take(nc); S.q_tr = al.take(nc);
+      S.a_state = al.take(nan); S.a_expl = al.take(nan); S.a_err = al.take(nan);
+      S.a_w = al.take(nc * S.na); S.a_tr = al.take(nc * S.na);
+      S.prev_value = al.take(S.n); S.avg_surprise = al.take(S.n);
+    }
+    if (al.top >= (1LL << 31)) { delete h; return fail(nullptr, BIDI_EINVAL, "bidi_create: agent state too large for 32-bit gather offsets"); }
+    for (int l = 0; l <= L; l++) {  // where every SDRRL input comes from, deep/CSRL.cpp:267-276, 295-304, 320-324
+      const LayerDev& D = h->layers[l];
+      LayerHost& H = h->hl[l];
+      const SdrrlDev& S = D.sd;
+      const bool input = l == L, top = l == L - 1;
+      const LayerDev& Up = h->layers[input ? 0 : (top ? l : l + 1)];
+      for (int i = 0; i < S.n; i++) {
+        const int ux = i % H.fb.d.uw, uy = i / H.fb.d.uw;
+        for_each_conn_host(H.fb, ux, uy, [&](int, int t) { H.sd.in_src.push_back(top ? -(1 + t) : (int)(Up.p_mod + t)); });
+        if (!input) for_each_conn_host(H.pred, ux, uy, [&](int, int t) { H.sd.in_src.push_back((int)(D.state + t)); });
+        for (int k = 0; k < S.n_rec; k++) H.sd.in_src.push_back((int)(S.a_expl + (long long)i * S.na + 3 + k));
+      }
+    }
+    int base = cfg->q_n_actions;  // noise entries: the action inputs, then the units in visit order
+    for (int l = L - 1; l >= 0; l--) { h->layers[l].sd.noise_base = base; base += h->layers[l].sd.n * h->layers[l].sd.na; }
+    h->layers[L].sd.noise_base = base; base += h->layers[L].sd.n * h->layers[L].sd.na;
+    h->n_noise = base;
+    h->csrl_is_action.assign(h->n_in, 0);
+    for (int k = 0; k < cfg->q_n_actions; k++) h->csrl_is_action[cfg->q_action_idx[k]] = 1;
   }
   long long q_qc_w = 0, q_qc_tr = 0, q_act = 0, q_prev = 0;
   if (qnet) {  // sdr/QPRSDR.cpp:13-31,86-96
@@ -1308,6 +1455,10 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       }
       push(H.dense_mask, &h->layers[l].dense_mask);
     }
+    if (csrl) {
+      push(H.sd.in_off, &h->layers[l].sd.in_off);
+      push(H.sd.in_src, &h->layers[l].sd.in_src);
+    }
     if (V == BIDI_NEO_AGENT) {
       push(H.col.in_off, &h->layers[l].col.in_off);
       push(H.col.rec_off, &h->layers[l].col.rec_off);
@@ -1347,6 +1498,21 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   P.ncol = h->ncol; P.layers = h->d_layers;
   P.gen_on = 0; P.gen_per_agent = h->gen_per_agent; P.gen_normals = h->d_gen; P.gen_scale = h->d_gen_scale;
   P.q_on = qnet ? 1 : 0;
+  P.csrl = csrl ? 1 : 0; P.n_noise = h->n_noise;
+  if (csrl) {
+    P.csrl_n_actions = cfg->q_n_actions; P.csrl_reward_offsets = csrl_offsets;
+    P.csrl_expl_std = cfg->col_expl_stddev; P.csrl_expl_break = cfg->col_expl_break;
+    std::vector<int> tab(cfg->q_action_idx, cfg->q_action_idx + cfg->q_n_actions);
+    tab.insert(tab.end(), h->csrl_is_action.begin(), h->csrl_is_action.end());
+    CU_CREATE(cudaMalloc(&h->d_csrl_tables, sizeof(int) * tab.size()));
+    CU_CREATE(cudaMemcpyAsync(h->d_csrl_tables, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, h->stream));
+    CU_CREATE(cudaStreamSynchronize(h->stream));
+    P.csrl_action_idx = h->d_csrl_tables; P.csrl_is_action = h->d_csrl_tables + cfg->q_n_actions;
+    size_t sm = 0;
+    for (int l = 0; l <= L; l++) sm = std::max(sm, sizeof(float) * BIDI_SDRRL_WARPS * (size_t)bidi::sdrrl_warp_floats(h->layers[l].sd.max_in));
+    if (sm > 200 * 1024) return bail(BIDI_EINVAL, "bidi_create: an SDRRL unit has too many inputs for shared memory");
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_sdrrl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
+  }
   if (qnet) {
     P.q_half = h->q_half; P.q_top = h->q_top; P.q_iters = cfg->q_derive_iterations;
     P.q_qc_w = q_qc_w; P.q_qc_tr = q_qc_tr; P.q_act = q_act; P.q_prev = q_prev;
@@ -1376,6 +1542,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
           const ColRec r = col_rec(D.col, h->hl[l].col, img.data(), node);
           for (int i = 0; i < D.col.cells; i++) r.thr[r.cs * i] = cfg->init_threshold;
         }
+      if (csrl) for (long long k = 0; k < (long long)D.sd.n * D.sd.cells; k++) img[D.sd.thr + k] = cfg->init_threshold;
     }
     for (int a = 0; a < n_agents; a++)
       CU_CREATE(cudaMemcpyAsync(h->d_blob + (long long)a * h->stride, img.data(), sizeof(float) * h->stride, cudaMemcpyHostToDevice, h->stream));
@@ -1388,7 +1555,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     for (int l = 0; l < L; l++) {
       const size_t need = sizeof(float) * (size_t)bidi::coder_cta_shape(h->layers[l]).floats;
       const size_t need_dense = sizeof(float) * (size_t)bidi::coder_dense_shape(h->layers[l]).floats;
-      if (bidi::coder_dense_applies(h->layers[l]) && need_dense <= 200 * 1024 && !h->no_dense_coder) { h->coder_cta[l] = 2; smem_dense = std::max(smem_dense, need_dense); }
+      if (bidi::coder_dense_applies(h->layers[l]) && need_dense <= 200 * 1024 && !h->no_dense_coder && !csrl) { h->coder_cta[l] = 2; smem_dense = std::max(smem_dense, need_dense); }
       else if (need <= 200 * 1024) { h->coder_cta[l] = 1; smem = std::max(smem, need); }
     }
     if (smem > 0) {
@@ -1476,6 +1643,10 @@ int bidi_conn_counts(const bidi_engine* h, int which, int layer, int* counts, in
       return BIDI_OK;
     }
     case BIDI_COL_INPUT:
+      if (h->csrl && n_units == h->layers[layer].sd.n) {
+        for (int i = 0; i < n_units; i++) counts[i] = H.sd.in_off[i + 1] - H.sd.in_off[i];
+        return BIDI_OK;
+      }
       if (h->cfg.variant != BIDI_NEO_AGENT || n_units != h->layers[layer].col.n) return fail(hm, BIDI_EINVAL, "bidi_conn_counts: bad column query");
       for (int i = 0; i < n_units; i++) counts[i] = H.col.in_off[i + 1] - H.col.in_off[i];
       return BIDI_OK;
@@ -1579,6 +1750,21 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
       for (int a = 0; a < 3; a++)
         for (int k = 0; k < C.cells; k++) r.a_w[r.es * (a * r.Cq + k)] = weightDist(gen);
     };
+    auto draw_sdrrl = [&](const SdrrlDev& S, const SdrrlHost& SH, int node) {  // deep/SDRRL.cpp:23-43
+      const int in0 = SH.in_off[node], nin = SH.in_off[node + 1] - in0;
+      for (int i = 0; i < S.cells; i++) {
+        const long long ck = (long long)node * S.cells + i;
+        img[S.thr + ck] = g.init_threshold;
+        for (int j = 0; j < nin; j++) img[S.ff_w + (long long)in0 * S.cells + (long long)i * nin + j] = weightDist(gen);
+        for (int j = 0; j < S.cells; j++) img[S.lat_w + ck * S.cells + j] = inhibitionDist(gen);
+        for (int j = 0; j < S.na; j++) img[S.a_w + ck * S.na + j] = weightDist(gen);
+        img[S.q_w + ck] = weightDist(gen);
+      }
+    };
+    if (h->csrl) {  // _lastLayerRewardOffsets, deep/CSRL.cpp:32-35
+      std::uniform_real_distribution<float> dist01(0.0f, 1.0f);
+      for (int i = 0; i < h->layers[L - 1].nh; i++) img[h->P.csrl_reward_offsets + i] = dist01(gen) * 2.0f - 1.0f;
+    }
     for (int l = 0; l <= L; l++) {
       if (l == L && V == BIDI_KWINNERS) break;
       const LayerDev& D = h->layers[l];
@@ -1598,6 +1784,7 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
         draw_list(H.fb, i, ux, uy, weightDist);
         if (l < L) draw_list(H.pred, i, ux, uy, weightDist);
         if (V == BIDI_NEO_AGENT) draw_column(D.col, H.col, i);
+        if (h->csrl) draw_sdrrl(D.sd, H.sd, i);
       }
     }
     if (h->qnet) {  // sdr/QPRSDR.cpp:30-31, then per layer and node: bias, one draw per in-bounds slot -- kept or not (:50-83)
@@ -1693,7 +1880,7 @@ int bidi_step(bidi_engine* h, const float* rewards, const float* noise_u, const 
   if (!h) return fail(h, BIDI_EINVAL, "null engine");
   if ((noise_u == nullptr) != (noise_v == nullptr)) return fail(h, BIDI_EINVAL, "bidi_step: noise_u and noise_v go together");
   CU(cudaSetDevice(h->device));
-  const bool agent = h->cfg.variant == BIDI_NEO_AGENT || h->qnet;  // variants with a reward and exploration draws
+  const bool agent = h->cfg.variant == BIDI_NEO_AGENT || h->qnet || h->csrl;  // variants with a reward and exploration draws
   if (agent) {
     CU(cudaStreamSynchronize(h->stream));
     if (rewards) memcpy(h->h_rewards, rewards, sizeof(float) * h->A);
@@ -1829,7 +2016,7 @@ int bidi_step_frame(bidi_engine* h, int t, int learn) {
                                                                       h->first_agent, h->fb_reward ? h->d_rewards : nullptr);
     h->launches++;
   }
-  bool device_noise = h->cfg.variant == BIDI_NEO_AGENT || h->qnet;
+  bool device_noise = h->cfg.variant == BIDI_NEO_AGENT || h->qnet || h->csrl;
   if (device_noise && h->n_noise_frames > 0) {  // the caller's draws (bidi_load_frame_noise) instead of the engine's generator
     const size_t nn = (size_t)h->A * h->n_noise, fo = (size_t)(t % h->n_noise_frames) * nn;
     CU(cudaMemcpyAsync(h->d_noise_u, h->d_frame_noise_u + fo, sizeof(float) * nn, cudaMemcpyDeviceToDevice, h->stream));
@@ -1901,7 +2088,7 @@ int bidi_env_step(bidi_engine* h, const float* noise_u, const float* noise_v, co
   if (!h || !h->env_kind) return fail(h, BIDI_EINVAL, "bidi_env_step: no environment attached");
   if ((noise_u == nullptr) != (noise_v == nullptr)) return fail(h, BIDI_EINVAL, "bidi_env_step: noise_u and noise_v go together");
   CU(cudaSetDevice(h->device));
-  const bool draws = h->cfg.variant == BIDI_NEO_AGENT || h->qnet;
+  const bool draws = h->cfg.variant == BIDI_NEO_AGENT || h->qnet || h->csrl;
   if (noise_u || env_noise) CU(cudaStreamSynchronize(h->stream));  // the staging buffers may still be in flight
   if (noise_u && draws) {
     const size_t n = (size_t)h->A * h->n_noise;
@@ -2037,6 +2224,7 @@ int bidi_save_snapshot(bidi_engine* h, const char* path) {
   hd.noise_seed = h->noise_seed; hd.first_agent = h->first_agent; hd.layout_rows = layout_mask(h);
   bidi_config cfg = h->cfg;
   if (h->qnet) cfg.variant = BIDI_QPRSDR;
+  if (h->csrl) cfg.variant = BIDI_CSRL;
   bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1 && fwrite(&cfg, sizeof(cfg), 1, f) == 1 &&
             fwrite(h->ld.data(), sizeof(bidi_layer_desc), (size_t)h->L, f) == (size_t)h->L;
   std::vector<float> buf;
@@ -2071,6 +2259,7 @@ int bidi_load_snapshot(bidi_engine* h, const char* path) {
   std::vector<bidi_layer_desc> ld((size_t)h->L);
   bidi_config mine = h->cfg;
   if (h->qnet) mine.variant = BIDI_QPRSDR;
+  if (h->csrl) mine.variant = BIDI_CSRL;
   bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kSnapMagic, 8) == 0 && hd.version == kSnapVersion &&
             hd.config_bytes == (int)sizeof(bidi_config) && hd.desc_bytes == (int)sizeof(bidi_layer_desc) && hd.n_layers == h->L &&
             hd.n_agents == h->A && hd.n_in == h->n_in && hd.stride == h->stride && hd.layout_rows == layout_mask(h) &&

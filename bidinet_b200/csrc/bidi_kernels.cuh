@@ -356,6 +356,7 @@ __device__ __forceinline__ void d_ic_finish(const EngineDev& P, const LayerDev& 
   if (scale_state) { st *= mult; B[L.state + i] = st; }
   if (next_vis_input >= 0) {
     if (P.variant == BIDI_NEO_AGENT) st = st * B[L.col.a_expl + i * 3 + 0];
+    else if (P.csrl) st = st * B[L.sd.a_expl + (long long)i * L.sd.na + 0];  // the unit's _attention action, deep/CSRL.cpp:198
     B[next_vis_input + i] = st;
   }
 }
@@ -415,11 +416,15 @@ __global__ void k_neo_learn(EngineDev P, LayerDev L, int l) {
   float* __restrict__ wrec = B + L.rec.w_off; float* __restrict__ trec = B + L.rec.tr_off;
   const int ux = i % L.hw, uy = i / L.hw, U = L.nh;
   const float learn = B[L.state + i], maxd = L.max_weight_delta, decay = L.weight_decay;
-  const float err = learn - B[L.p_state_prev + i];
-  const float error2 = err * err;
-  const float base = B[L.p_baseline + i];
-  const float reward = bidi_sigmoid(L.sensitivity * (error2 - base));
-  B[L.p_baseline + i] = (1.0f - L.baseline_decay) * base + L.baseline_decay * error2;
+  float reward;
+  if (P.csrl) reward = B[L.p_mod + i];  // deep::CSRL: the node's _reward action (deep/CSRL.cpp:278-281,421-424); rule sdr/IRSDR.cpp:321-356
+  else {
+    const float err = learn - B[L.p_state_prev + i];
+    const float error2 = err * err;
+    const float base = B[L.p_baseline + i];
+    reward = bidi_sigmoid(L.sensitivity * (error2 - base));
+    B[L.p_baseline + i] = (1.0f - L.baseline_decay) * base + L.baseline_decay * error2;
+  }
   for_each_slot_batched<8, WTE>(L.ff, ux, uy,
       [&](int s, int t) { const long long k = (long long)s * U + i; return WTE{wff[k], tff[k], x[t] - vrec[t]}; },
       [&](int s, const WTE& v) {
@@ -518,6 +523,8 @@ __device__ __forceinline__ void d_step_end(const EngineDev& P, int max_units, lo
       B[L.p_act_prev + i] = B[L.p_act + i];
     }
   }
+  // deep::CSRL: every input cell takes its own prediction (the caller then overwrites the state cells), deep/CSRL.cpp:445
+  if (P.csrl && i < P.n_in) P.in0[(long long)a * P.n_in + i] = P.pred_out[(long long)a * P.n_in + i];
 }
 __global__ void k_step_end(EngineDev P, int max_units) { d_step_end(P, max_units, (long long)blockIdx.x * blockDim.x + threadIdx.x); }
 

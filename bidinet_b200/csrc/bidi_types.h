@@ -96,6 +96,20 @@ struct ColumnsDev {
   int iter;
 };
 
+// The deep::SDRRL units (deep/SDRRL.h:8-62) of one node layer of a deep::CSRL: plain planes in the reference's
+// serialised order ([node][cell][input], [node][cell][cell], [node][cell], [node][action], [node][cell][action]).
+struct SdrrlDev {
+  int n, cells, na, n_rec;   // nodes, cells per unit, 2*(3 + recurrent inputs) action entries, recurrent inputs
+  int tot_in, max_in;
+  const int* in_off;         // [n+1] prefix sums of numStates
+  const int* in_src;         // [tot_in] blob offset an input is gathered from; -(1+k): _lastLayerRewardOffsets[k] + reward
+  long long inputs, recon_err, ff_w, lat_w, thr, act, spike, spike_prev, state, cell_as, cell_ae, q_w, q_tr;
+  long long a_state, a_expl, a_err, a_w, a_tr, prev_value, avg_surprise;
+  int noise_base;            // first entry of this layer's units in an agent's exploration-noise arrays
+  float sparsity, gamma, leak, a_ff, a_lat, a_thr, a_q, a_act, derive_alpha, gamma_lambda, expl_std, expl_break, surprise_decay;
+  int settle, measure, derive_iter;
+};
+
 // One layer: the sparse coder (visible -> hidden) and its prediction nodes.
 // Index n_layers holds only the input prediction nodes (pn_*, fb, col).
 struct LayerDev {
@@ -118,6 +132,7 @@ struct LayerDev {
   long long q_state, q_err, q_bias_w, q_bias_tr, q_w_off, q_tr_off;
   const float* q_mask;
   ColumnsDev col;
+  SdrrlDev sd;
   // layers whose windows span the grid (bidi_coder_dense.cuh): per (unit u, row quad q) the four bits "slot 4q+e of
   // the row [feed-forward | recurrent | pad] is one of u's own connections", [unit][pitch/4]; one table for all agents
   const int* dense_mask;
@@ -153,6 +168,12 @@ struct EngineDev {
   const int* q_act_index;                 // [n_in] input cell -> action node, -1 if none
   const int* q_a_input;                   // [2*half] action node -> input cell
   float q_alpha, q_action_alpha, q_derive_alpha, q_expl_break, q_gamma, q_gamma_lambda, q_expl_std;
+  // deep::CSRL (bidi_csrl.cuh): the hierarchy runs the ITERATIVE coders; every node owns a deep::SDRRL unit
+  int csrl, n_noise, csrl_n_actions;
+  long long csrl_reward_offsets;          // blob offset of _lastLayerRewardOffsets
+  const int* csrl_action_idx;             // [csrl_n_actions] input cells of type _action, ascending
+  const int* csrl_is_action;              // [n_in]
+  float csrl_expl_std, csrl_expl_break;   // the CSRL object's own (input nodes)
 };
 
 #endif

@@ -6,7 +6,8 @@ import pytest
 
 from oracle.pyoracle import OracleHierarchy, RefHierarchy, have_ref
 
-from util import N_RANDOM, RANDOM_STEPS, diff_states, random_case, random_schedule, small_cases
+from util import (N_CSRL_RANDOM, N_RANDOM, RANDOM_STEPS, csrl_random_case, diff_states, random_case, random_schedule,
+                  small_cases)
 
 pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libbidiref.so not built (needs /root/reference)")
 
@@ -91,3 +92,24 @@ def test_oracle_matches_reference_more_random_geometries():
             ref.step(*random_schedule(t))
             orc.step(*random_schedule(t))
             assert diff_states(ref.state(), orc.state()) == [], "seed %d step %d" % (seed, t)
+
+
+@pytest.mark.parametrize("seed", range(N_CSRL_RANDOM))
+def test_csrl_oracle_matches_reference_random_geometries(seed):
+    """deep::CSRL / deep::SDRRL on randomly drawn shapes (1x1 grids, zero recurrent inputs, zero derive or settle
+    iterations, one-cell units): the restatement equals the compiled reference after creation and after every step."""
+    cfg, ld, frames = csrl_random_case(seed)
+    ref, orc = RefHierarchy(cfg, ld, 99 + seed), OracleHierarchy(cfg, ld, 99 + seed)
+    assert diff_states(ref.state(), orc.state()) == []
+    for t in range(RANDOM_STEPS):
+        x = frames[t % len(frames)]
+        ref.set_inputs(x)
+        orc.set_inputs(x)
+        ur, vr = ref.peek_noise()
+        uo, vo = orc.peek_noise()
+        assert np.array_equal(ur, uo) and np.array_equal(vr, vo)
+        reward, learn = random_schedule(t)
+        ref.step(reward, learn)
+        orc.step(reward, learn)
+        assert diff_states(ref.state(), orc.state()) == [], "seed %d step %d" % (seed, t)
+        assert np.array_equal(ref.get_predictions(), orc.get_predictions())

@@ -12,7 +12,8 @@ from bidinet_b200 import Engine
 from bidinet_b200 import config as cf
 from oracle.pyoracle import OracleHierarchy
 
-from util import RANDOM_STEPS, diff_states, random_case, random_schedule, small_cases, state_digests
+from util import (N_CSRL_RANDOM, RANDOM_STEPS, csrl_random_case, diff_states, random_case, random_schedule, small_cases,
+                  state_digests)
 
 pytestmark = pytest.mark.gpu
 
@@ -57,8 +58,8 @@ def test_free_running_parity(case, path):
     orc = OracleHierarchy(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1)
     if path == "coop":  # the whole step as one cooperative launch interpreting the phase list
-        if cfg.variant == cf.NEO_AGENT:
-            pytest.skip("no columns in the cooperative step")
+        if cfg.variant in (cf.NEO_AGENT, cf.CSRL):
+            pytest.skip("no columns / SDRRL units in the cooperative step")
         eng.set_option("coop_step", True)
     if path == "fused_general":
         eng.set_option("dense_coder", False)
@@ -98,8 +99,8 @@ def test_batched_free_running_parity(case, path):
     eng = Engine(cfg, ld, n_agents=A, seed=1234)
     orcs = [OracleHierarchy(cfg, ld, 1234 + a) for a in range(A)]
     if path == "coop":
-        if cfg.variant == cf.NEO_AGENT:
-            pytest.skip("no columns in the cooperative step")
+        if cfg.variant in (cf.NEO_AGENT, cf.CSRL):
+            pytest.skip("no columns / SDRRL units in the cooperative step")
         eng.set_option("coop_step", True)
     if path == "fused_general":
         eng.set_option("dense_coder", False)
@@ -300,3 +301,31 @@ def test_random_geometries(seed):
         assert list(keys) == list(g["r%d/keys" % seed])
         assert list(digests) == list(g["r%d/digests" % seed]), "seed %d path %s: differs from the reference's golden digests" % (seed, path)
         eng.close()
+
+
+@pytest.mark.parametrize("seed", range(N_CSRL_RANDOM))
+def test_csrl_random_geometries(seed):
+    """deep::CSRL on randomly drawn shapes (the oracle is pinned to the compiled reference on the same shapes by
+    tests/test_oracle_vs_ref.py): every state array -- coders, prediction nodes with their traces, every SDRRL unit --
+    equal after every step, two agents in the engine."""
+    cfg, ld, frames = csrl_random_case(seed)
+    eng = Engine(cfg, ld, n_agents=2, seed=99 + seed)
+    orcs = [OracleHierarchy(cfg, ld, 99 + seed + a) for a in range(2)]
+    for a in range(2):
+        assert diff_states(orcs[a].state(), eng.state(agent=a)) == [], a
+    for t in range(RANDOM_STEPS):
+        x = np.stack([frames[(t + a) % len(frames)] for a in range(2)])
+        nz = [o.peek_noise() for o in orcs]
+        reward, learn = random_schedule(t)
+        for a, o in enumerate(orcs):
+            o.set_inputs(x[a])
+            o.step(reward + a, learn)
+        eng.set_inputs(x)
+        eng.step(rewards=[reward, reward + 1], noise=(np.stack([n[0] for n in nz]), np.stack([n[1] for n in nz])), learn=learn)
+        pred = eng.get_predictions()
+        for a, o in enumerate(orcs):
+            assert np.array_equal(o.get_predictions(), pred[a]), (seed, t, a)
+            bad = diff_states(o.state(), eng.state(agent=a))
+            assert bad == [], "seed %d step %d agent %d: %s" % (seed, t, a, bad[:6])
+    eng.step(rewards=[0.0, 0.0])  # the engine's own exploration draws: runs, stays finite
+    assert np.isfinite(eng.get_predictions()).all()

@@ -72,10 +72,47 @@ def small_cases():
     cfg, ld = cf.make_config(cf.QPRSDR, 7, 5, layers, r_infb=2, actions=[3, 10, 17, 30], anti_actions=[4, 11, 18, 31],
                              init=(-0.3, 0.3, 0.01, 0.05, 0.0), q_derive_iterations=9)
     cases.append(("ragged_qprsdr", cfg, ld, lambda t: frames35[t % 64], lambda t: float(np.cos(0.7 * t))))
+    # deep::CSRL: sdr::IRSDR coders + one deep::SDRRL unit per node; a small one, and a ragged three-layer one (a layer
+    # without recurrent SDRRL inputs, windows wider than the grid, a 1x1 top layer, no action inputs in the first)
+    cfg, ld = cf.config_csrl_small()
+    cases.append(("csrl_small", cfg, ld, lambda t: frames35[t % 64][:30], lambda t: float(np.sin(0.3 * t))))
+    layers = [dict(width=5, height=4, r_ff=2, r_rec=1, r_lat=2, r_pred=1, r_fb=1, csrl_n_recurrent=0, csrl_derive_iterations=3,
+                   iter_settle=3, iter_measure=1, col_cells=3),
+              dict(width=3, height=2, r_ff=1, r_rec=2, r_lat=1, r_pred=3, r_fb=2, csrl_n_recurrent=1, csrl_derive_iterations=2,
+                   iter_settle=2, iter_measure=2, col_cells=6),
+              dict(width=1, height=1, r_ff=4, r_rec=0, r_lat=0, r_pred=0, r_fb=3, csrl_n_recurrent=5, csrl_derive_iterations=0,
+                   iter_settle=0, iter_measure=3, col_cells=2)]
+    cfg, ld = cf.make_config(cf.CSRL, 7, 5, layers, r_infb=2, actions=[3, 10, 17, 30], init=(-0.4, 0.4, 0.01, 0.05, 0.02),
+                             csrl_n_recurrent=1, csrl_derive_iterations=3, csrl_iter_settle=1, csrl_iter_measure=2, col_cells=7)
+    cases.append(("ragged_csrl", cfg, ld, lambda t: frames35[t % 64], lambda t: float(np.cos(0.7 * t))))
     return cases
 
 
 N_RANDOM = 40
+N_CSRL_RANDOM = 10
+
+
+def csrl_random_case(seed):
+    """A random small deep::CSRL: grids 1..10 wide, 1..3 layers, radii 0..3, 1..8 cells per SDRRL unit."""
+    rng = np.random.RandomState(7000 + seed)
+    n_layers = int(rng.randint(1, 4))
+    iw, ih = int(rng.randint(1, 9)), int(rng.randint(1, 9))
+    layers = []
+    for l in range(n_layers):
+        layers.append(dict(width=int(rng.randint(1, 11)), height=int(rng.randint(1, 11)), r_ff=int(rng.randint(0, 4)),
+                           r_rec=int(rng.randint(0, 3)), r_lat=int(rng.randint(0, 3)), r_pred=int(rng.randint(0, 3)),
+                           r_fb=int(rng.randint(0, 3)), csrl_n_recurrent=int(rng.randint(0, 4)),
+                           csrl_derive_iterations=int(rng.randint(0, 5)), iter_settle=int(rng.randint(0, 4)),
+                           iter_measure=int(rng.randint(1, 4)), col_cells=int(rng.randint(1, 9))))
+    n_in = iw * ih
+    k = int(rng.randint(0, min(6, n_in) + 1))
+    actions = sorted(int(c) for c in rng.permutation(n_in)[:k])
+    cfg, ld = cf.make_config(cf.CSRL, iw, ih, layers, r_infb=int(rng.randint(0, 4)), actions=actions,
+                             init=(-0.4, 0.4, 0.01, 0.05, float(rng.choice([0.0, 0.05]))), csrl_n_recurrent=int(rng.randint(0, 4)),
+                             csrl_derive_iterations=int(rng.randint(0, 5)), csrl_iter_settle=int(rng.randint(0, 4)),
+                             csrl_iter_measure=int(rng.randint(1, 4)), col_cells=int(rng.randint(1, 9)))
+    frames = (rng.rand(8, n_in) < 0.4).astype(np.float32) * rng.rand(8, n_in).astype(np.float32)
+    return cfg, ld, frames
 
 
 def random_case(seed):
