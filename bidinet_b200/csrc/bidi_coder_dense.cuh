@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
      // (inside the radius, the recurrent centre excluded) comes from the layer's mask table.  The traces stream
      // through registers (HBM rows like the weights; prefetched into the L2 at kernel start), the new weights go
      // into the shared-memory rows, which one bulk copy then takes back to HBM.
-    constexpr int NB = LIGHT ? 2 : 4;
+    constexpr int NB = LIGHT ? 2 : 8;
     const int pq = pitch >> 2, nq_ff = S.nf >> 2, total_q = nh * pq;
     const float maxd = L.max_weight_delta, decay = L.weight_decay, lambda = L.lambda;
     const int* __restrict__ mk = L.dense_mask;
@@ -413,10 +413,52 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
     __syncthreads();
     if (tid == 0) tma_store_1d(B + L.ff.w_off, w, row_bytes);  // waited for at the end of the kernel
   }
-  // lateral weights and the threshold of this lane's unit (sdr/IRSDR.cpp:313-317)
-  if (warp < S.sweep_warps && i < nh) {
+  // lateral weights (sdr/IRSDR.cpp:313-317): w = max(0, w + lr*(state_i*state_j - sparsity^2)), every connection, every step.
+  // A layer whose lateral windows span the grid keeps one slot plane per TARGET unit, so the rule is a flat pass over
+  // [slot][unit quad] with 128-bit accesses, all loads of a batch in flight before the first store; a unit owns the
+  // slot of target t iff t is inside its radius and is not the unit itself
+  const float sp2 = L.sparsity * L.sparsity;
+  if (L.lat.r >= 0 && L.lat.absx && L.lat.absy && (hw & 3) == 0) {
+    constexpr int NL = LIGHT ? 4 : 8;
+    const int nq = nh >> 2, total_l = L.lat.nslots * nq, rl = L.lat.r;
+    float4* wl4 = reinterpret_cast<float4*>(B + L.lat.w_off);
+    const float ll = L.learn_lat;
+    int s = tid / nq, q = tid - s * nq;
+    const int ds = T / nq, dq = T - ds * nq;
+    for (int idx = tid; idx < total_l; idx += NL * T) {
+      float4 v[NL];
+      int ss[NL], qq[NL];
+#pragma unroll
+      for (int h = 0; h < NL; h++) {
+        const int id = idx + h * T;
+        ss[h] = s; qq[h] = q;
+        if (id < total_l) v[h] = wl4[id];
+        s += ds; q += dq;
+        if (q >= nq) { q -= nq; s++; }
+      }
+#pragma unroll
+      for (int h = 0; h < NL; h++) {
+        const int id = idx + h * T;
+        if (id >= total_l) continue;
+        const int tx = ss[h] / hh, ty = ss[h] - tx * hh, t = tx + ty * hw;
+        const int u0 = 4 * qq[h], uy0 = u0 / hw, ux0 = u0 - uy0 * hw;
+        const float st = lrn[t];
+        const float4 su = *reinterpret_cast<const float4*>(lrn + u0);
+        const bool oky = (unsigned)(ty - uy0 + rl) <= 2u * (unsigned)rl;
+        float wv[4] = {v[h].x, v[h].y, v[h].z, v[h].w};
+        const float sv[4] = {su.x, su.y, su.z, su.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const bool ok = oky && (unsigned)(tx - ux0 - e + rl) <= 2u * (unsigned)rl && t != u0 + e;
+          if (ok) wv[e] = bidi_max(0.0f, wv[e] + ll * (sv[e] * st - sp2));
+        }
+        wl4[id] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      }
+    }
+    if (warp < S.sweep_warps && i < nh) B[L.thr + i] = bidi_max(0.0f, thr_r + (lrn[i] - L.sparsity) * L.learn_threshold);
+  } else if (warp < S.sweep_warps && i < nh) {
     float* __restrict__ wl = B + L.lat.w_off;
-    const float si = lrn[i], sp2 = L.sparsity * L.sparsity;
+    const float si = lrn[i];
     for_each_slot_batched<LIGHT ? 8 : 16, WE>(L.lat, ux, uy,
         [&](int s, int t) { return WE{wl[(long long)s * nh + i], lrn[t]}; },
         [&](int s, const WE& v) { wl[(long long)s * nh + i] = bidi_max(0.0f, v.w + L.learn_lat * (si * v.e - sp2)); });

@@ -116,7 +116,12 @@ struct Pair {
 __device__ __forceinline__ u64 shfl64(u64 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // floats of shared memory one column pair needs: its record, the gathered inputs, the final cell states and learning factors
-__host__ __device__ inline int column_slab_floats(const ColumnsDev& C) { return C.max_rec + 2 * C.max_s + 4 * C.cq + (C.rh ? 8 * (C.rh + 4) : 0); }
+// (+ the scratch of the 16-cell kernel: its parked rows, which first serve as the staging of the input planes)
+__host__ __device__ inline int column_scratch_floats(const ColumnsDev& C) {
+  const int park = C.rh ? 8 * (C.rh + 4) : 0, stage = (C.stage_n + 3) & ~3;
+  return park > stage ? park : stage;
+}
+__host__ __device__ inline int column_slab_floats(const ColumnsDev& C) { return C.max_rec + 2 * C.max_s + 4 * C.cq + column_scratch_floats(C); }
 
 template <int LPC>
 __global__ void __launch_bounds__(BIDI_COL_WARPS * 32) k_columns(EngineDev P, LayerDev L, int l) {

@@ -35,7 +35,7 @@ __device__ __forceinline__ float lo32(u64 v) { float x, y; upk(v, x, y); return 
 __device__ __forceinline__ float hi32(u64 v) { float x, y; upk(v, x, y); return y; }
 
 template <int RH>
-__global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l) {
+__global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l, ColPairTab T) {
   extern __shared__ __align__(128) float smem[];
   constexpr int CC = 16;
   constexpr int RB = 4;              // spiking rows per column parked in the scratch at a time
@@ -50,16 +50,20 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   const bool has = node < C.n;
   float* B = blob_of(P, a);
 
-  const int S = C.stride[pair], SH = S - RH;             // row length; the part of it that lives in shared memory
-  const int R = C.rec_off[pair + 1] - C.rec_off[pair] - 32 * RH;  // floats of the shared-memory part of the record
+  // the pair's geometry: from the constant bank where the layer's table fits there (no load between launch and bulk copy)
+  const bool tab = T.n > 0;
+  const int S = tab ? (int)T.stride[pair] : C.stride[pair], SH = S - RH;  // row length; the part of it that lives in shared memory
+  const int ro0 = tab ? T.rec_off[pair] : C.rec_off[pair], ro1 = tab ? T.rec_off[pair + 1] : C.rec_off[pair + 1];
+  const int R = ro1 - ro0 - 32 * RH;                     // floats of the shared-memory part of the record
   const int blk = R >> 1;
   float* rec = smem;
   float* in_s = smem + C.max_rec + c * C.max_s;          // gathered inputs of column c, [S], pad 0
   float* st_s = smem + C.max_rec + 2 * C.max_s + c * CC;  // final cell states of column c
   float* kf_s = st_s + 2 * CC;                            // feed-forward learning factors of column c
-  float* scr = smem + C.max_rec + 2 * C.max_s + 4 * CC + c * (RB * RS);  // parked rows of column c, [RB][RS]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C.max_rec + 2 * C.max_s + 4 * CC + 2 * RB * RS);
-  float* g_reg = B + C.rec_base + C.rec_off[pair];       // register part: [RQ][32 lanes][4]
+  float* stg = smem + C.max_rec + 2 * C.max_s + 4 * CC;   // staging of the input planes, then the scratch rows
+  float* scr = stg + c * (RB * RS);                       // parked rows of column c, [RB][RS]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(stg + column_scratch_floats(C));
+  float* g_reg = B + C.rec_base + ro0;                   // register part: [RQ][32 lanes][4]
   float* g_rec = g_reg + 32 * RH;
 
   // ---- the record starts on its way in (one TMA bulk copy)
@@ -90,18 +94,51 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   const long long nk = ((long long)a * P.ncol + C.noise_base + node) * 3 + i;
   if (has && i < 3) { nz_u = P.noise_u[nk]; nz_v = P.noise_v[nk]; }
   {
-    const int in0 = has ? C.in_off[node] : 0;
-    const int nin = has ? C.in_off[node + 1] - in0 : 0;
-    const int* src = C.in_src + in0;
+    const int in0 = !has ? 0 : (tab ? T.in_off[node] : C.in_off[node]);
+    const int nin = !has ? 0 : (tab ? T.in_off[node + 1] : C.in_off[node + 1]) - in0;
     constexpr int GT = 9;  // 144 inputs per trip
-    for (int j0 = 0; j0 < S; j0 += 16 * GT) {
-      float gv[GT];
+    if (C.stage_n > 0) {
+      // the few planes every input of this layer comes from go to shared memory with independent, coalesced loads
+      // (issued together with the loads of the inputs' positions), and the inputs are picked there
+      const unsigned short* loc = C.in_loc + in0;
+      const int n0 = C.stage_len[0], n01 = n0 + C.stage_len[1], sn = C.stage_n;
+      for (int j0 = 0; j0 < S; j0 += 16 * GT) {
+        int lv[GT];
 #pragma unroll
-      for (int t = 0; t < GT; t++) { const int j = j0 + i + 16 * t; gv[t] = j < nin ? B[src[j]] : 0.0f; }
+        for (int t = 0; t < GT; t++) { const int j = j0 + i + 16 * t; lv[t] = j < nin ? (int)loc[j] : -1; }
+        if (j0 == 0) {
+          for (int k0 = 0; k0 < sn; k0 += 128) {
+            float sv[4];
 #pragma unroll
-      for (int t = 0; t < GT; t++) {
-        const int j = j0 + i + 16 * t;
-        if (j < S) in_s[j] = gv[t];  // (the COL_INPUT plane is not written: the host regathers it on demand)
+            for (int t = 0; t < 4; t++) {
+              const int k = k0 + lane + 32 * t;
+              const long long off = k < n0 ? C.stage_off[0] + (long long)k * C.stage_step[0]
+                                  : k < n01 ? C.stage_off[1] + (long long)(k - n0) * C.stage_step[1]
+                                            : C.stage_off[2] + (long long)(k - n01) * C.stage_step[2];
+              sv[t] = k < sn ? B[off] : 0.0f;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) { const int k = k0 + lane + 32 * t; if (k < sn) stg[k] = sv[t]; }
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int t = 0; t < GT; t++) {
+          const int j = j0 + i + 16 * t;
+          if (j < S) in_s[j] = lv[t] >= 0 ? stg[lv[t]] : 0.0f;
+        }
+      }
+    } else {
+      const int* src = C.in_src + in0;
+      for (int j0 = 0; j0 < S; j0 += 16 * GT) {
+        float gv[GT];
+#pragma unroll
+        for (int t = 0; t < GT; t++) { const int j = j0 + i + 16 * t; gv[t] = j < nin ? B[src[j]] : 0.0f; }
+#pragma unroll
+        for (int t = 0; t < GT; t++) {
+          const int j = j0 + i + 16 * t;
+          if (j < S) in_s[j] = gv[t];  // (the COL_INPUT plane is not written: the host regathers it on demand)
+        }
       }
     }
   }

@@ -38,6 +38,8 @@ struct WinHost {
 
 struct ColumnsHost {
   std::vector<int> in_off, rec_off, stride, in_src;
+  std::vector<int> in_loc;   // ColumnsDev::in_loc, two 16-bit entries per int
+  ColPairTab tab;            // k_columns16's constant-bank copy of in_off / rec_off / stride
 };
 struct SdrrlHost {
   std::vector<int> in_off, in_src;
@@ -618,9 +620,10 @@ void record_columns(Recorder& R, int l) {
   // x = pair (fastest: consecutive CTAs are one agent's pairs), (y, z) = agent
   const unsigned ay = (unsigned)std::min(h->A, 32768);
   const dim3 pa((unsigned)n_pairs, ay, (unsigned)((h->A + ay - 1) / ay));
-  if (C.planar && C.rh == 64) bidi::k_columns16<64><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l);
-  else if (C.planar && C.rh == 32) bidi::k_columns16<32><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l);
-  else if (C.planar) bidi::k_columns16<0><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l);
+  const ColPairTab& T = h->hl[l].col.tab;
+  if (C.planar && C.rh == 64) bidi::k_columns16<64><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l, T);
+  else if (C.planar && C.rh == 32) bidi::k_columns16<32><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l, T);
+  else if (C.planar) bidi::k_columns16<0><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l, T);
   else if (ppw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   R.after("columns");
@@ -1109,6 +1112,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
   if (V == BIDI_NEO_AGENT && (cfg->col_cells < 1 || cfg->col_cells > 32 || cfg->col_iter < 1))
     return fail(h, BIDI_EINVAL, "bidi_create: columns need 1..32 cells and >= 1 iteration");
 
+  const bool h_no_col_stage = getenv("BIDI_NO_COL_STAGE") != nullptr;  // experiment switch: gather the column inputs straight from the blob
   const bool h_no_col_regs = getenv("BIDI_NO_COL_REGS") != nullptr;  // experiment switch: keep whole weight rows in shared memory
   h = new bidi_engine();
   h->cfg = *cfg; h->ld.assign(layers, layers + L);
@@ -1361,14 +1365,41 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       const bool input_layer = l == L;
       const LayerDev& Up = h->layers[input_layer ? 0 : (l == L - 1 ? l : l + 1)];
       H.col.in_src.clear();
+      // the same inputs as positions in a staging of their source planes (ColumnsDev::stage_*): segment 0 = the upper
+      // columns' _signal actions, 1 = the upper prediction states, 2 = this layer's coder states
+      ColumnsDev& C = h->layers[l].col;
+      const bool has_fb = input_layer || l < L - 1;
+      const int n_up = has_fb ? H.fb.d.tw * H.fb.d.th : 0, n_own = input_layer ? 0 : H.pred.d.tw * H.pred.d.th;
+      C.stage_len[0] = n_up; C.stage_step[0] = 3; C.stage_off[0] = Up.col.a_expl + 2;
+      C.stage_len[1] = n_up; C.stage_step[1] = 1; C.stage_off[1] = Up.p_state;
+      C.stage_len[2] = n_own; C.stage_step[2] = 1; C.stage_off[2] = D.state;
+      std::vector<unsigned short> loc;
       for (int i = 0; i < D.col.n; i++) {
         const int ux = i % H.fb.d.uw, uy = i / H.fb.d.uw;
-        if (input_layer || l < L - 1)
+        if (has_fb)
           for_each_conn_host(H.fb, ux, uy, [&](int, int t) {
             H.col.in_src.push_back((int)(Up.col.a_expl + t * 3 + 2));
             H.col.in_src.push_back((int)(Up.p_state + t));
+            loc.push_back((unsigned short)t); loc.push_back((unsigned short)(n_up + t));
           });
-        if (!input_layer) for_each_conn_host(H.pred, ux, uy, [&](int, int t) { H.col.in_src.push_back((int)(D.state + t)); });
+        if (!input_layer) for_each_conn_host(H.pred, ux, uy, [&](int, int t) {
+          H.col.in_src.push_back((int)(D.state + t));
+          loc.push_back((unsigned short)(2 * n_up + t));
+        });
+      }
+      // staged only where the planes fit the kernel's scratch rows (bidi_columns16.cuh; 8*(rh+4) floats) or are tiny
+      const int total = 2 * n_up + n_own;
+      C.stage_n = (C.planar && !h_no_col_stage && total > 0 && total <= std::max(64, C.rh ? 8 * (C.rh + 4) : 0)) ? total : 0;
+      H.col.in_loc.assign((loc.size() + 1) / 2 + 1, 0);
+      memcpy(H.col.in_loc.data(), loc.data(), loc.size() * sizeof(unsigned short));
+      ColPairTab& T = H.col.tab;
+      memset(&T, 0, sizeof(T));
+      const int n_pairs = (C.n + 1) / 2;
+      if (C.planar && n_pairs <= BIDI_PAIRTAB_MAX && n_pairs > 0) {
+        T.n = n_pairs;
+        for (int p = 0; p <= n_pairs; p++) T.rec_off[p] = H.col.rec_off[p];
+        for (int p = 0; p < n_pairs; p++) T.stride[p] = (short)H.col.stride[p];
+        for (int i = 0; i <= 2 * n_pairs; i++) T.in_off[i] = H.col.in_off[std::min(i, C.n)];
       }
     }
   }
@@ -1464,6 +1495,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       push(H.col.rec_off, &h->layers[l].col.rec_off);
       push(H.col.stride, &h->layers[l].col.stride);
       push(H.col.in_src, &h->layers[l].col.in_src);
+      push(H.col.in_loc, reinterpret_cast<const int**>(&h->layers[l].col.in_loc));
     }
   }
   CU_CREATE(cudaMalloc(&h->d_tables, sizeof(int) * pool.size()));

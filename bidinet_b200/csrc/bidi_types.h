@@ -86,6 +86,14 @@ struct ColumnsDev {
   int max_s, max_rec;       // largest pair stride / largest shared-memory part of a pair record (floats)
   const int* in_off;        // [n+1] prefix sums of nIn (same for every agent)
   const int* in_src;        // [tot_in] blob offset each column input is gathered from (neo/Agent.cpp:159-169)
+  // The inputs of a layer's columns come from at most three short planes of the agent (the upper columns' _signal
+  // actions, the upper prediction states, the layer's own coder states).  stage_n > 0: bidi_columns16.cuh copies those
+  // planes into shared memory with independent coalesced loads and picks the inputs there (in_loc[j] = position of
+  // input j in the staging), instead of a dependent index -> value chain of global loads per input.
+  int stage_n;              // floats staged (0: gather straight from the blob through in_src)
+  int stage_len[3], stage_step[3];
+  long long stage_off[3];   // segment k: stage[base_k + q] = blob[stage_off[k] + q*stage_step[k]], q < stage_len[k]
+  const unsigned short* in_loc;  // [tot_in]
   const int* rec_off;       // [n_pairs+1] pair record offsets (floats) relative to rec_base
   const int* stride;        // [n_pairs] S
   long long rec_base;       // blob offset of the first record
@@ -98,6 +106,17 @@ struct ColumnsDev {
 
 // The deep::SDRRL units (deep/SDRRL.h:8-62) of one node layer of a deep::CSRL: plain planes in the reference's
 // serialised order ([node][cell][input], [node][cell][cell], [node][cell], [node][action], [node][cell][action]).
+// Per-pair geometry of one layer's columns as a kernel argument (constant bank): the record offset, the row stride and
+// the input range of a pair are then known without a global load, so the record's bulk copy starts at once.
+// n = 0: the layer has more pairs than fit; the kernel reads the ColumnsDev tables instead.
+#define BIDI_PAIRTAB_MAX 48
+struct ColPairTab {
+  int n;
+  int rec_off[BIDI_PAIRTAB_MAX + 1];
+  int in_off[2 * BIDI_PAIRTAB_MAX + 1];
+  short stride[BIDI_PAIRTAB_MAX];
+};
+
 struct SdrrlDev {
   int n, cells, na, n_rec;   // nodes, cells per unit, 2*(3 + recurrent inputs) action entries, recurrent inputs
   int tot_in, max_in;
