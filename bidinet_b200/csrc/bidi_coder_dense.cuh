@@ -69,7 +69,7 @@ __host__ __device__ inline CoderDenseShape coder_dense_shape(const LayerDev& L) 
              + 2LL * s.recon_warps * L.nh           // per reconstructing warp: drive list, 8-byte entries
              + 2LL * L.nh                           // state, spike: unit order (act and thr live in registers)
              + 2LL * L.nh                           // lateral-order table: (coordinates, slot plane offset)
-             + (long long)s.sweep_warps * L.nh      // per sweeping warp: lateral list (positions in the table)
+             + 2LL * ((L.nh + 31) / 32) + 2         // the spiking units as bit masks in lateral-list order, this sweep's and the next's
              + 8;                                   // RunnerMain layer 0: 37.4 KB, six CTAs per SM
   return s;
 }
@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
   float* state = xin + pitch + 2 * S.recon_warps * nh;  // unit order
   float* spike = state + nh;
   int2* lat_tab = reinterpret_cast<int2*>(spike + nh);  // [nh], lateral-list order: (x | y << 16, slot plane offset)
-  int* lat_list = reinterpret_cast<int*>(lat_tab + nh) + (warp < S.sweep_warps ? warp : 0) * nh;  // this warp's spiking units: positions in lat_tab
+  const int nw = (nh + 31) >> 5;
+  unsigned* msk = reinterpret_cast<unsigned*>(lat_tab + nh);  // [2][nw] bit p = the unit at position p of the lateral lists' order spiked
 
   // ---- stage: the layer's rows [unit][feed-forward | recurrent | pad] are one contiguous image in HBM: one TMA
   //      bulk copy, overlapped with the staging of the vectors below
@@ -172,41 +173,40 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
   }
   {
     const float* gx = vis_input_of(P, L, l, a);
-    for (int s = tid; s < pitch; s += T) {
-      float xv = 0.0f, rv = 0.0f;
-      if (s < nv) {
-        const int t = s / vh + (s % vh) * vw;  // slot (tx, ty) = tx*vh + ty <-> cell tx + ty*vw
-        xv = gx[t]; rv = B[L.vis_recon + t];
-      } else if (s >= S.nf && s - S.nf < nh && has_rec) {
-        const int k = s - S.nf, u = k / hh + (k % hh) * hw;
-        xv = B[L.state_prev + u]; rv = B[L.recon + u];
+    constexpr int SB = LIGHT ? 2 : 4;  // loads of SB trips in flight before the first store
+    for (int s0 = tid; s0 < pitch; s0 += SB * T) {
+      float xv[SB], rv[SB];
+#pragma unroll
+      for (int h = 0; h < SB; h++) {
+        const int s = s0 + h * T;
+        xv[h] = 0.0f; rv[h] = 0.0f;
+        if (s < nv) {
+          const int t = s / vh + (s % vh) * vw;  // slot (tx, ty) = tx*vh + ty <-> cell tx + ty*vw
+          xv[h] = gx[t]; rv[h] = B[L.vis_recon + t];
+        } else if (s >= S.nf && s - S.nf < nh && has_rec) {
+          const int k = s - S.nf, u = k / hh + (k % hh) * hw;
+          xv[h] = B[L.state_prev + u]; rv[h] = B[L.recon + u];
+        }
       }
-      xin[s] = xv; err[s] = xv - rv;
+#pragma unroll
+      for (int h = 0; h < SB; h++) {
+        const int s = s0 + h * T;
+        if (s < pitch) { xin[s] = xv[h]; err[s] = xv[h] - rv[h]; }
+      }
     }
+    if (tid < 2 * nw) msk[tid] = 0u;
+    __syncthreads();
     for (int k = tid; k < nh; k += T) {
-      spike[k] = B[L.spike_prev + k];  // spikePrev persists across steps (sdr/IRSDR.cpp:131-135 resets only act, state)
+      const float sp0 = B[L.spike_prev + k];
+      spike[k] = sp0;  // spikePrev persists across steps (sdr/IRSDR.cpp:131-135 resets only act, state)
       state[k] = 0.0f;
       const int tx = k / hh, ty = k - tx * hh;  // position k of the lateral lists' order (x-major: dx outer, dy inner)
       lat_tab[k] = make_int2(tx | (ty << 16), (tx * L.lat.dyn + ty) * nh);
+      if (sp0 != 0.0f) { const int pp = (k % hw) * hh + k / hw; atomicOr(&msk[pp >> 5], 1u << (pp & 31)); }
     }
   }
   mbar_wait(bar, 0);
   __syncthreads();
-  // spikePrev in the lateral lists' order, one private copy per sweep warp; rebuilt after every
-  // sweep, once all units' new spikes are in shared memory
-  int n_spk = 0;
-  auto build_lat_list = [&]() {
-    n_spk = 0;
-    for (int p0 = 0; p0 < nh; p0 += 32) {
-      const int p = p0 + lane;
-      bool f = false;
-      if (p < nh) { const int cc = lat_tab[p].x; f = spike[(cc & 0xffff) + (cc >> 16) * hw] != 0.0f; }
-      const unsigned m = __ballot_sync(0xffffffffu, f);
-      if (f) lat_list[n_spk + __popc(m & ((1u << lane) - 1u))] = p;
-      n_spk += __popc(m);
-    }
-    __syncwarp();
-  };
   // reconstruction of both sides from the units with a non-zero drive, ascending unit index
   // (sdr/IRSDR.cpp:218-235, neo/SparseCoder.cpp:164-168): a lane owns adjacent slots of the row layout.
   // It leaves the errors input - reconstruction in err[]; `last`: the reconstruction itself (the errors
@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
       }
     }
   };
-  if (warp < S.sweep_warps) build_lat_list();
   const float* wlat = B + L.lat.w_off;
   const bool gen = NEO && P.gen_on;
   const float* gen_nz = gen ? P.gen_normals + (long long)a * P.gen_per_agent + L.gen_off : nullptr;
@@ -261,6 +260,7 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
   //   |tx - ux| <= r  <=>  unsigned(tx + r - ux) <= 2r ;  wlat[base + lat_off]
   const int i = tid;
   const int r = L.lat.r, ux = i % hw, uy = i / hw, own = ux | (uy << 16), tcx = r - ux, tcy = r - uy;
+  const int my_pos = ux * hh + uy;
   const unsigned r2 = 2u * (unsigned)r;
   const bool lat_on = r >= 0;
   const int lat_off = ((L.lat.absx ? 0 : tcx) * L.lat.dyn + (L.lat.absy ? 0 : tcy)) * nh + i;
@@ -281,9 +281,19 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
 #define BIDI_LATQ 4   // measured on C3: 2..4 within 0.1 %, 8 is 0.5 % slower, 12 is 1.3 % slower
 #endif
       constexpr int LATQ = BIDI_LATQ;
+      // the spiking units, ascending position in the lateral lists (the order of the reference's sum): set bits of cur
+      const unsigned* cur = msk + (it & 1) * nw;
+      int mw = 0;
+      unsigned bits = cur[0];
+      auto next_pos = [&]() -> int {
+        while (bits == 0u) { if (++mw >= nw) return -1; bits = cur[mw]; }
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        return mw * 32 + b;
+      };
       float lw[LATQ];
 #pragma unroll
-      for (int e = 0; e < LATQ; e++) lw[e] = e < n_spk ? lat_weight(lat_tab[lat_list[e]]) : 0.0f;
+      for (int e = 0; e < LATQ; e++) { const int pp = next_pos(); lw[e] = pp >= 0 ? lat_weight(lat_tab[pp]) : 0.0f; }
       // simStepGenerate: the excitation starts from noiseDist(generator) * noise (neo/SparseCoder.cpp:200)
       float excitation = gen ? gen_nz[(long long)it * nh + i] * gen_scale : 0.0f;
       excitation = dot_row_seq<LIGHT>(F, reinterpret_cast<const ulonglong2*>(w + (size_t)i * pitch), reinterpret_cast<const ulonglong2*>(err),
@@ -291,8 +301,8 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
       float inhibition = 0.0f;
 #pragma unroll
       for (int e = 0; e < LATQ; e++) inhibition += lw[e];
-      for (int e = LATQ; e < n_spk; e++) {
-        const int2 t = lat_tab[lat_list[e]];
+      for (int pp = next_pos(); pp >= 0; pp = next_pos()) {
+        const int2 t = lat_tab[pp];
         const bool in = lat_on && (unsigned)((t.x & 0xffff) + tcx) <= r2 && (unsigned)((t.x >> 16) + tcy) <= r2 && t.x != own;
         if (in) inhibition += wlat[t.y + lat_off];
       }
@@ -302,13 +312,14 @@ __global__ void __launch_bounds__(LIGHT ? 32 : 512, LIGHT ? 28 : 0) k_coder_dens
       if (NEO) stv += sp;
       else if (measuring) stv += measure_inv * sp;
       act_r = av; spike[i] = sp; state[i] = stv;
+      if (sp != 0.0f) atomicOr(&msk[((it + 1) & 1) * nw + (my_pos >> 5)], 1u << (my_pos & 31));
     }
     counter += 1.0f;
     mult = 1.0f / counter;
     __syncthreads();
     // ---- reconstruction + errors (sdr/IRSDR.cpp:139-142, :218-235; neo/SparseCoder.cpp:164-168)
     const bool last = NEO && it == total - 1;
-    if (warp < S.sweep_warps && !last) build_lat_list();
+    if (tid < nw) msk[(it & 1) * nw + tid] = 0u;  // read by this sweep, written by the next but one
     reconstruct(NEO ? state : spike, NEO != 0, mult, last);
     __syncthreads();
   }
