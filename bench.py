@@ -735,10 +735,14 @@ def main():
     bytes_per_launch = kern_bytes_step * A / launches_per_step
     achieved = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
     peak, peak_src = hbm_peak()
-    traffic = None
+    traffic, traffic_stale = None, None
     try:  # measured DRAM bytes of this kernel (ncu dram__bytes_read.sum + dram__bytes_write.sum), per launch like `achieved`
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))[kern]
+        tj = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
+        tr = tj[kern]
         traffic = tr["dram_bytes_per_agent_step"] * A / tr["launches_per_step"]
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from steady_launches import kernel_source_sha
+        traffic_stale = tj.get("kernel_source_sha") != kernel_source_sha()  # the capture was taken on other kernel sources
     except Exception:
         pass
 
@@ -770,7 +774,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_source": "profiles/r1_traffic.json (ncu, same build, 4096 agents; scaled by agents)",
+                     "traffic_source": "profiles/%s (ncu launch list of 4096 agents; scaled by agents)" % TRAFFIC_FILE,
+                     "traffic_stale": traffic_stale,
                      "bytes_per_launch": bytes_per_launch, "avg_launch_ms": 1e3 * avg_launch_s,
                      "launches_per_step": int(launches_per_step),
                      "whole_step": {"algorithmic_bytes_per_agent_step": step_bytes,
@@ -783,6 +788,9 @@ def main():
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+TRAFFIC_FILE = "r2_traffic.json"
 
 
 def _emit_one_line():

@@ -114,6 +114,10 @@ int column_pair_stride(int nin, bool planar) {
   return s;
 }
 
+// row pitch of a k-winners family laid out as rows (bidi_grid.cuh): >= its slots, 4 (mod 8) floats so that a warp's
+// 128-bit shared-memory loads of 32 staged rows never conflict and every row starts 16-byte aligned
+inline int kw_pitch(int nslots) { return bidi::dense_pitch(std::max(1, nslots)); }
+
 struct LayerHost {
   WinHost ff, rec, lat, fb, pred;
   ColumnsHost col;
@@ -139,7 +143,7 @@ struct bidi_engine {
   std::vector<int> tiled;          // per node layer: few threads, use the cooperative tile kernels (bidi_tiles.cuh)
   bool force_phase_kernels = false, no_dense_coder = false;
   // per layer: the 2-D tile kernels of bidi_grid.cuh apply (large k-winners layers); shared-memory floats they stage
-  struct GridSizes { int on, ff, rec, lat, fb, pred, gather; };
+  struct GridSizes { int on, ff, rec, lat, fb, pred, gather; int act_slab, act_box, act_cap, act_dense; };  // act_*: k_g_kw_activate (row segments)
   std::vector<GridSizes> gridk;
   int grid_mode = 1;               // 0 off, 1 layers at least 16 units wide that are not tiled, 2 every layer
   EngineDev P;                     // kernel argument
@@ -639,9 +643,27 @@ void launch_grid(Recorder& R, const char* name, K kernel, long long blocks, size
   R.after(name);
   R.kernels++;
 }
+inline size_t act_smem_bytes(const bidi_engine::GridSizes& G) { return sizeof(float) * (size_t)(G.act_slab + G.act_box + 2 * G.act_cap) + 16; }
+// k_g_kw_activate over the hidden rows [Y.row0, Y.row1): one warp per 32-unit row segment
+void launch_kw_activate(bidi_engine* h, cudaStream_t st, const bidi_engine::GridSizes& G, const LayerDev& Y, int l) {
+  const long long blocks = (long long)h->A * (Y.row1 - Y.row0) * ((Y.hw + 31) / 32);
+  if (blocks <= 0) return;
+  const size_t smem = act_smem_bytes(G);
+  const int dyn = (G.act_dense && Y.ff.dxn == Y.ff.dyn && !Y.ff.absx && !Y.ff.absy) ? Y.ff.dyn : 0;
+#define BIDI_ACT(D) bidi::k_g_kw_activate<D><<<(unsigned)blocks, 32, smem, st>>>(h->P, Y, l, G.act_dense, G.act_slab, G.act_box, G.act_cap)
+  switch (dyn) {
+    case 5: BIDI_ACT(5); break;
+    case 7: BIDI_ACT(7); break;
+    case 9: BIDI_ACT(9); break;
+    case 13: BIDI_ACT(13); break;
+    case 17: BIDI_ACT(17); break;
+    default: BIDI_ACT(0); break;
+  }
+#undef BIDI_ACT
+}
 // which layers run the 2-D tile kernels, and how much shared memory they stage
 int select_grid_kernels(bidi_engine* h) {
-  h->gridk.assign(h->L, bidi_engine::GridSizes{0, 0, 0, 0, 0, 0, 0});
+  h->gridk.assign(h->L, bidi_engine::GridSizes{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
   if (h->cfg.variant == BIDI_NEO_AGENT || h->grid_mode == 0) return BIDI_OK;
   size_t most = 0;
   for (int l = 0; l < h->L; l++) {
@@ -654,7 +676,18 @@ int select_grid_kernels(bidi_engine* h) {
     g.pred = bidi::grid_box_floats(H.pred.d, H.pred.cx.data(), H.pred.cy.data());
     g.gather = std::max(bidi::grid_gather_floats(H.ff.d, H.ff.gxlo.data(), H.ff.gxhi.data(), H.ff.gylo.data(), H.ff.gyhi.data()),
                         bidi::grid_gather_floats(H.rec.d, H.rec.gxlo.data(), H.rec.gxhi.data(), H.rec.gylo.data(), H.rec.gyhi.data()));
-    const size_t need = sizeof(float) * (size_t)std::max({g.ff + g.rec + (h->cfg.variant == BIDI_KWINNERS ? 0 : g.lat), g.lat, g.fb + g.pred, 3 * g.gather});
+    size_t need = sizeof(float) * (size_t)std::max({g.ff + g.rec + (h->cfg.variant == BIDI_KWINNERS ? 0 : g.lat), g.lat, g.fb + g.pred, 3 * g.gather});
+    g.act_slab = g.act_box = g.act_cap = g.act_dense = 0;
+    if (h->cfg.variant == BIDI_KWINNERS) {
+      // k_g_kw_activate: layer 0 reads a dense input (rows staged in shared memory); a higher layer reads the binary state below
+      g.act_dense = l == 0 ? 1 : 0;
+      const int fbox = bidi::grid_rowbox_floats(H.ff.d, H.ff.cx.data()), rbox = bidi::grid_rowbox_floats(H.rec.d, H.rec.cx.data());
+      g.act_slab = g.act_dense ? 32 * kw_pitch(H.ff.d.nslots) : 0;
+      g.act_box = g.act_dense ? (fbox + 3) / 4 * 4 : 0;
+      g.act_cap = std::max(g.act_dense ? 0 : fbox, rbox) + 2;
+      need = std::max({sizeof(float) * (size_t)g.lat, sizeof(float) * 3 * (size_t)g.gather, sizeof(float) * 4 * (size_t)(g.fb + g.pred)});
+      if (sizeof(float) * (size_t)(g.act_slab + g.act_box + 2 * g.act_cap) + 16 > 200 * 1024) need = 1 << 30;  // (no such layer in practice)
+    }
     // default: untiled (large-batch) layers at least 16 units wide; k-winners layers at least 24 wide even for one
     // agent (C4: 0.44 ms against 0.49 ms with the slot-group tile kernels); the iterative sweeps of ONE agent stay on
     // the tile kernels (C4: 7.4 ms against 9.1 ms: a 507-connection chain per thread is too long for a single agent)
@@ -664,11 +697,20 @@ int select_grid_kernels(bidi_engine* h) {
     h->gridk[l] = g;
   }
   if (most > 48 * 1024) {
-    CU(cudaFuncSetAttribute(bidi::k_g_kw_activate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
     CU(cudaFuncSetAttribute(bidi::k_g_kw_inhibit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
     CU(cudaFuncSetAttribute(bidi::k_g_reconstruct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
     CU(cudaFuncSetAttribute(bidi::k_g_kw_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
     CU(cudaFuncSetAttribute(bidi::k_g_ic_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most));
+  }
+  size_t act_most = 0;
+  for (int l = 0; l < h->L; l++) if (h->gridk[l].on) act_most = std::max(act_most, act_smem_bytes(h->gridk[l]));
+  if (act_most > 48 * 1024) {
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_activate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_most));
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_activate<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_most));
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_activate<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_most));
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_activate<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_most));
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_activate<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_most));
+    CU(cudaFuncSetAttribute(bidi::k_g_kw_activate<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)act_most));
   }
   return BIDI_OK;
 }
@@ -687,7 +729,10 @@ void record_step(Recorder& R, bool learn) {
       if (h->gridk[l].on && !R.collect) {
         const auto& G = h->gridk[l];
         const long long th = A * bidi::grid_tiles(Y.hw, Y.hh), tv = A * bidi::grid_tiles(Y.vw, Y.vh);
-        launch_grid(R, "kw_activate", bidi::k_g_kw_activate, th, G.ff + G.rec, Y, l, G.ff);
+        R.before("kw_activate");
+        launch_kw_activate(h, R.s(), G, Y, l);
+        R.after("kw_activate");
+        R.kernels++;
         launch_grid(R, "kw_inhibit", bidi::k_g_kw_inhibit, th, G.lat, Y, l, Y.act, Y.state, nxt);
         launch_grid(R, "reconstruct", bidi::k_g_reconstruct, tv + th, 3 * G.gather, Y, l, Y.state, 1, 0, G.gather, 0, 0.0f, 0);
       } else if (h->tiled[l]) {
@@ -708,7 +753,7 @@ void record_step(Recorder& R, bool learn) {
       if (h->gridk[l].on && !R.collect) {
         const auto& G = h->gridk[l];
         const long long th = A * bidi::grid_tiles(Y.hw, Y.hh);
-        launch_grid(R, "predict", bidi::k_g_kw_predict, th, G.fb + G.pred, Y, l, (int)learn, Up.p_state, Up.p_state_prev, G.fb);
+        launch_grid(R, "predict", bidi::k_g_kw_predict, th, 4 * (G.fb + G.pred), Y, l, (int)learn, Up.p_state, Up.p_state_prev, G.pred, G.fb);
         launch_grid(R, "kw_inhibit", bidi::k_g_kw_inhibit, th, G.lat, Y, l, Y.p_act, Y.p_state, -1LL);
       } else if (h->tiled[l]) {
         launch_tile(R, "predict", bidi::k_t_predict, tiles_of(A, Y.pn), tile_bytes(nslots_of(Y.fb) + nslots_of(Y.pred)), Y, l, (int)learn,
@@ -894,8 +939,39 @@ void convert_region(float* R, const LayerHost& H, int nh, bool to_rows) {
   }
 }
 
+// one family of a k-winners layer between slot planes [slot][U] and rows [unit][pitch] (bidi_grid.cuh), in place
+void convert_family(float* R, int nslots, long long U, int pitch, bool to_rows) {
+  const long long len = (long long)pitch * U;
+  std::vector<float> tmp(R, R + len);
+  std::fill(R, R + len, 0.0f);
+  for (long long u = 0; u < U; u++)
+    for (int s = 0; s < nslots; s++) {
+      const long long row = u * pitch + s, pl = (long long)s * U + u;
+      if (to_rows) R[row] = tmp[pl]; else R[pl] = tmp[row];
+    }
+}
+
 int apply_layout(bidi_engine* h) {
   bool changed = false;
+  // k-winners layers: rows exactly while the 2-D grid kernels are the layer's path
+  for (int l = 0; l < h->L && h->cfg.variant == BIDI_KWINNERS; l++) {
+    LayerHost& H = h->hl[l];
+    const int want = h->gridk[l].on ? 1 : 0;
+    if (want == h->dense_rows[l]) continue;
+    WinHost* fams[4] = {&H.ff, &H.rec, &H.fb, &H.pred};
+    if (h->state_touched)
+      for (int a = 0; a < h->A; a++) {
+        int rc = mirror_load(h, a);
+        if (rc) return rc;
+        for (WinHost* w : fams)
+          if (w->d.r >= 0 && w->d.w_off >= 0) convert_family(h->mirror.data() + w->d.w_off, w->d.nslots, w->d.U, kw_pitch(w->d.nslots), want != 0);
+        h->mirror_dirty = true;
+      }
+    for (WinHost* w : fams) w->d.row_pitch = (want && w->d.r >= 0) ? kw_pitch(w->d.nslots) : 0;
+    h->layers[l].ff = H.ff.d; h->layers[l].rec = H.rec.d; h->layers[l].fb = H.fb.d; h->layers[l].pred = H.pred.d;
+    h->dense_rows[l] = want;
+    changed = true;
+  }
   for (int l = 0; l < h->L; l++) {
     LayerHost& H = h->hl[l];
     if (!H.dense_geom) continue;
@@ -1159,6 +1235,9 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
           H.ff.d.tr_off = H.tr_region;
           if (d.r_rec >= 0) H.rec.d.tr_off = H.tr_region + H.rec_plane;
         }
+      } else if (V == BIDI_KWINNERS) {  // room for either layout: slot planes, or one row of kw_pitch(nslots) floats per unit (apply_layout)
+        H.ff.d.w_off = al.take((long long)kw_pitch(H.ff.d.nslots) * D.nh);
+        if (d.r_rec >= 0) H.rec.d.w_off = al.take((long long)kw_pitch(H.rec.d.nslots) * D.nh);
       } else {
         H.ff.d.w_off = al.take((long long)H.ff.d.nslots * D.nh);
         if (d.r_rec >= 0) H.rec.d.w_off = al.take((long long)H.rec.d.nslots * D.nh);
@@ -1174,8 +1253,8 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
       else if (csrl) build_win(H.fb, D.hw, D.hh, D.hw, D.hh, d.r_fb, true, false);  // the top layer looks at the rewards around its own position, deep/CSRL.cpp:92-114
       else build_win(H.fb, D.hw, D.hh, 1, 1, -1, true, false);
       build_win(H.pred, D.hw, D.hh, D.hw, D.hh, d.r_pred, true, false);
-      if (l < L - 1 || csrl) H.fb.d.w_off = al.take((long long)H.fb.d.nslots * D.pn);
-      H.pred.d.w_off = al.take((long long)H.pred.d.nslots * D.pn);
+      if (l < L - 1 || csrl) H.fb.d.w_off = al.take((long long)(V == BIDI_KWINNERS ? kw_pitch(H.fb.d.nslots) : H.fb.d.nslots) * D.pn);
+      H.pred.d.w_off = al.take((long long)(V == BIDI_KWINNERS ? kw_pitch(H.pred.d.nslots) : H.pred.d.nslots) * D.pn);
       if (csrl) {
         H.fb.d.tr_off = al.take((long long)H.fb.d.nslots * D.pn);
         H.pred.d.tr_off = al.take((long long)H.pred.d.nslots * D.pn);
@@ -1602,7 +1681,6 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     }
   }
   h->dense_rows.assign(L, 0);
-  if (apply_layout(h) != BIDI_OK) return bail(BIDI_ECUDA, g_last_error);
   // node layers with few (agent, unit) threads use the cooperative tile kernels
   h->tiled.assign(L + 1, 0);
   {
@@ -1626,6 +1704,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     }
   }
   if (select_grid_kernels(h) != BIDI_OK) return bail(BIDI_ECUDA, g_last_error);
+  if (apply_layout(h) != BIDI_OK) return bail(BIDI_ECUDA, g_last_error);  // (after the kernel families are chosen: they decide the layouts)
   // the column kernel may need more than the default 48 KB of dynamic shared memory
   if (V == BIDI_NEO_AGENT) {
     size_t smem = 0;

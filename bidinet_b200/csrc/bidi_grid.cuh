@@ -17,11 +17,17 @@
 // rows [row0,row1) the launch works on (a row strip, or the whole grid).
 #pragma once
 #include "bidi_kernels.cuh"
+#include "bidi_columns.cuh"  // mbarrier / bulk-copy helpers
 
 namespace bidi {
 
 #define GRID_TX 32
 #define GRID_TY 8
+
+// Element (slot, unit) of a connection family in either layout (bidi_types.h, WinDev::row_pitch).
+__device__ __forceinline__ long long widx(const WinDev& w, int slot, int unit) {
+  return w.row_pitch ? (long long)unit * w.row_pitch + slot : (long long)slot * w.U + unit;
+}
 
 struct GridTile { int a, ux0, uy0, ux, uy, unit, row_end; bool ok; };
 __host__ __device__ inline int grid_tiles(int uw, int rows) { return ((uw + GRID_TX - 1) / GRID_TX) * ((rows + GRID_TY - 1) / GRID_TY); }
@@ -116,23 +122,201 @@ inline int grid_box_floats(const WinDev& w, const int* cx, const int* cy) {
   return bw * bh;
 }
 
-// ---- sdr/RSDR.cpp:123-133: a = -theta + sum_ff x*w + sum_rec sPrev*w
-__global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_activate(EngineDev P, LayerDev L, int l, int ff_floats) {
-  extern __shared__ float sm[];
-  const GridTile T = grid_tile(blockIdx.x, L.hw, L.row0, L.row1);
-  float* B = blob_of(P, T.a);
-  const float* x = vis_input_of(P, L, l, T.a);
-  const float* sprev = B + L.state_prev;
-  const Box bf = window_box(L.ff, T), br = L.rec.r >= 0 ? window_box(L.rec, T) : Box{0, 0, 0, 0};
-  float* sm_rec = sm + ff_floats;
-  stage_box(sm, bf, L.ff.tw, L.ff.th, [&](int t) { return x[t]; });
-  if (L.rec.r >= 0) stage_box(sm_rec, br, L.rec.tw, L.rec.th, [&](int t) { return sprev[t]; });
+// host: largest window box of a 32x1 row segment, in floats
+inline int grid_rowbox_floats(const WinDev& w, const int* cx) {
+  if (w.r < 0) return 0;
+  int bw = w.tw;
+  if (!w.absx) { bw = 0; for (int u = 0; u < w.uw; u += GRID_TX) bw = max(bw, cx[min(u + GRID_TX, w.uw) - 1] - cx[u] + 2 * w.r + 1); }
+  const int bh = w.absy ? w.th : 2 * w.r + 1;
+  return bw * bh;
+}
+
+// ---- Large k-winners layers keep every family as ROWS, w[unit][slot] (pitch = 4 mod 8 floats): a unit's window is
+// contiguous in HBM.  What that buys, given that the sources of a k-winners hierarchy are SPARSE (the states and
+// predictions are binary with ~1 % ones; only the input of layer 0 is dense):
+//   * a sum over a sparse source walks the few non-zero cells of the tile's window box (compacted once per CTA, in
+//     x-major order = the order of every unit's connection list) and reads ONE weight per hit -- the other
+//     (2r+1)^2 - hits products are (+-0) and leave the running sum unchanged, so they are not formed and their
+//     weights never leave HBM;
+//   * the dense feed-forward sum of layer 0 stages the 32 rows of a row segment with ONE TMA bulk copy
+//     (cp.async.bulk + mbarrier) and reads them with conflict-free 128-bit shared-memory loads;
+//   * the winners-only learning rule and the gather reconstructions touch a winner's row as consecutive sectors
+//     instead of one 32-byte sector per weight.
+// Non-zero cells of plane[] inside box b, in x-major order (tx outer, ty inner), as (tx | ty << 16, value bits).
+// One warp: returns the count.  The box may reach outside the grid (cells there are 0 and never listed).
+__device__ __forceinline__ int compact_box_warp(const float* __restrict__ plane, const Box& b, int tw, int th, int2* __restrict__ ent, int lane) {
+  const int n = b.w * b.h;
+  int base = 0;
+  for (int k0 = 0; k0 < n; k0 += 128) {  // four independent loads in flight per lane
+    float v[4]; int cc[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const int k = k0 + 32 * t + lane, bx = k / b.h, gx = b.x0 + bx, gy = b.y0 + k - bx * b.h;
+      const bool in = k < n && gx >= 0 && gx < tw && gy >= 0 && gy < th;
+      v[t] = in ? plane[gx + gy * tw] : 0.0f;
+      cc[t] = gx | (gy << 16);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const unsigned m = __ballot_sync(0xffffffffu, v[t] != 0.0f);
+      if (v[t] != 0.0f) ent[base + __popc(m & ((1u << lane) - 1u))] = make_int2(cc[t], __float_as_int(v[t]));
+      base += __popc(m);
+    }
+  }
+  __syncwarp();
+  return base;
+}
+// The same by a whole CTA of GRID_TY warps (two barriers inside): warp g lists the g-th part of the traversal.
+__device__ __forceinline__ int compact_box_cta(const float* __restrict__ plane, const Box& b, int tw, int th, int2* __restrict__ ent, int* s_cnt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = b.w * b.h;
+  const int chunk = ((n + GRID_TY - 1) / GRID_TY + 31) / 32 * 32, k0 = warp * chunk, k1 = min(n, k0 + chunk);
+  int mine = 0;
+  for (int k = k0 + lane; k < k0 + chunk; k += 32) {
+    float d = 0.0f;
+    if (k < k1) {
+      const int bx = k / b.h, gx = b.x0 + bx, gy = b.y0 + k - bx * b.h;
+      if (gx >= 0 && gx < tw && gy >= 0 && gy < th) d = plane[gx + gy * tw];
+    }
+    mine += __popc(__ballot_sync(0xffffffffu, d != 0.0f));
+  }
+  __syncthreads();  // (the previous list's readers are done with s_cnt)
+  if (lane == 0) s_cnt[warp + 1] = mine;
   __syncthreads();
-  if (!T.ok) return;
-  float sum = -B[L.thr + T.unit];
-  sum = box_dot(L.ff, bf, sm, T.ux, T.uy, B + L.ff.w_off + T.unit, L.nh, sum);
-  sum = box_dot(L.rec, br, sm_rec, T.ux, T.uy, B + L.rec.w_off + T.unit, L.nh, sum);
-  B[L.act + T.unit] = sum;
+  int pos = 0;
+  for (int g = 0; g < warp; g++) pos += s_cnt[g + 1];
+  int total = 0;
+  for (int g = 0; g < GRID_TY; g++) total += s_cnt[g + 1];
+  for (int k = k0 + lane; k < k0 + chunk; k += 32) {
+    float d = 0.0f;
+    int cc = 0;
+    if (k < k1) {
+      const int bx = k / b.h, gx = b.x0 + bx, gy = b.y0 + k - bx * b.h;
+      cc = gx | (gy << 16);
+      if (gx >= 0 && gx < tw && gy >= 0 && gy < th) d = plane[gx + gy * tw];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, d != 0.0f);
+    if (d != 0.0f) ent[pos + __popc(m & ((1u << lane) - 1u))] = make_int2(cc, __float_as_int(d));
+    pos += __popc(m);
+  }
+  __syncthreads();
+  return total;
+}
+// sum += value * w[unit][slot] over the listed cells inside the unit's window, list order.  Pass 1 marks the hits among
+// the list entries (64 at a time, a bit each); pass 2 loads the weights of four hits together before adding them in order.
+__device__ __forceinline__ float list_dot(const WinDev& w, const int2* __restrict__ ent, int n, int ux, int uy, const float* __restrict__ wrow, float sum) {
+  if (w.r < 0) return sum;
+  const int cx = w.cx[ux], cy = w.cy[uy], r = w.r;
+  const unsigned r2 = 2u * (unsigned)r;
+  auto slot_of = [&](int c) { const int tx = c & 0xffff, ty = c >> 16; return (w.absx ? tx : tx - cx + r) * w.dyn + (w.absy ? ty : ty - cy + r); };
+  for (int k0 = 0; k0 < n; k0 += 64) {
+    unsigned long long hits = 0ull;
+    const int kn = min(64, n - k0);
+    for (int k = 0; k < kn; k++) {
+      const int c = ent[k0 + k].x, dx = (c & 0xffff) - cx, dy = (c >> 16) - cy;
+      const bool in = (unsigned)(dx + r) <= r2 && (unsigned)(dy + r) <= r2 && !(w.excl && (dx | dy) == 0);
+      hits |= (unsigned long long)in << k;
+    }
+    while (hits) {
+      float wv[4], dv[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        wv[j] = 0.0f; dv[j] = 0.0f;
+        if (hits) {
+          const int k = __ffsll((long long)hits) - 1;
+          hits &= hits - 1ull;
+          const int2 e = ent[k0 + k];
+          wv[j] = wrow[slot_of(e.x)]; dv[j] = __int_as_float(e.y);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) sum += dv[j] * wv[j];  // (an absent hit adds +0)
+    }
+  }
+  return sum;
+}
+
+// ---- sdr/RSDR.cpp:123-133: a = -theta + sum_ff x*w + sum_rec sPrev*w.  One WARP per row segment of 32 units.
+// dense_ff: the visible plane is dense (layer 0): its 32 weight rows are staged by one bulk copy and the window box
+// by the warp.  Otherwise (the visible plane is the binary state of the layer below) the feed-forward sum is sparse too.
+// smem: [32*pitch slab | ff box] (dense) , list entries, mbarrier
+template <int DYN>
+__global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, int l, int dense_ff, int slab_floats, int box_floats, int cap) {
+  extern __shared__ __align__(16) float sm[];
+  const int lane = threadIdx.x;
+  const int nseg = (L.hw + 31) >> 5, rows = L.row1 - L.row0;
+  int bi = blockIdx.x;
+  const int seg = bi % nseg; bi /= nseg;
+  const int a = bi / rows, uy = L.row0 + bi % rows;
+  GridTile T;
+  T.a = a; T.ux0 = seg * 32; T.uy0 = uy; T.ux = T.ux0 + lane; T.uy = uy; T.row_end = uy + 1;
+  T.ok = T.ux < L.hw; T.unit = T.ux + uy * L.hw;
+  float* B = blob_of(P, a);
+  const float* x = vis_input_of(P, L, l, a);
+  float* slab = sm;
+  float* xbox = sm + slab_floats;
+  int2* ent = reinterpret_cast<int2*>(xbox + box_floats);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(ent + cap);
+  const int nun = min(32, L.hw - T.ux0);
+  const WinDev& wf = L.ff;
+  if (dense_ff) {
+    if (lane == 0) mbar_init(bar, 1);
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(nun * wf.row_pitch) * 4u;
+      mbar_expect_tx(bar, bytes);
+      tma_load_1d(slab, B + wf.w_off + (long long)(T.ux0 + uy * L.hw) * wf.row_pitch, bytes, bar);
+    }
+  }
+  float sum = T.ok ? -B[L.thr + T.unit] : 0.0f;
+  const Box bf = window_box(wf, T);
+  if (dense_ff) {
+    // the window box of the segment: coalesced rows, zero outside the grid
+    const int n = bf.w * bf.h;
+    for (int k0 = 0; k0 < n; k0 += 256) {
+      float v[8];
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const int k = k0 + 32 * t + lane, by = k / bf.w, gx = bf.x0 + k - by * bf.w, gy = bf.y0 + by;
+        v[t] = (k < n && gx >= 0 && gx < wf.tw && gy >= 0 && gy < wf.th) ? x[gx + gy * wf.tw] : 0.0f;
+      }
+#pragma unroll
+      for (int t = 0; t < 8; t++) { const int k = k0 + 32 * t + lane; if (k < n) xbox[k] = v[t]; }
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    if (T.ok) {
+      const float* s0 = xbox + (wf.absx ? 0 : wf.cx[T.ux] - wf.r - bf.x0) + (wf.absy ? 0 : wf.cy[uy] - wf.r - bf.y0) * bf.w;
+      const float* wrow = slab + lane * wf.row_pitch;
+      if (DYN > 0) {
+        // whole window unrolled: DYN*DYN slots, 128-bit weight loads (rows 4 mod 8 floats apart: conflict-free)
+        constexpr int DD = DYN > 0 ? DYN : 1, NS = DYN * DYN, NQ4 = (NS + 3) / 4;
+#pragma unroll
+        for (int q = 0; q < NQ4; q++) {
+          const float4 w4 = reinterpret_cast<const float4*>(wrow)[q];
+          const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int s = 4 * q + e;
+            if (s < NS) sum += s0[(s / DD) + (s % DD) * bf.w] * wv[e];
+          }
+        }
+      } else {
+        for (int sx = 0; sx < wf.dxn; sx++)
+          for (int sy = 0; sy < wf.dyn; sy++) sum += s0[sx + sy * bf.w] * wrow[sx * wf.dyn + sy];
+      }
+    }
+  } else if (wf.r >= 0) {
+    const int n = compact_box_warp(x, bf, wf.tw, wf.th, ent, lane);
+    if (T.ok) sum = list_dot(wf, ent, n, T.ux, uy, B + wf.w_off + (long long)T.unit * wf.row_pitch, sum);
+    __syncwarp();
+  }
+  if (L.rec.r >= 0) {
+    const Box br = window_box(L.rec, T);
+    const int n = compact_box_warp(B + L.state_prev, br, L.rec.tw, L.rec.th, ent, lane);
+    if (T.ok) sum = list_dot(L.rec, ent, n, T.ux, uy, B + L.rec.w_off + (long long)T.unit * L.rec.row_pitch, sum);
+  }
+  if (T.ok) B[L.act + T.unit] = sum;
 }
 
 // ---- sdr/RSDR.cpp:135-145, :148-163: rank among the lateral neighbours
@@ -243,7 +427,7 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_reconstruct(EngineDev P,
     const int c = l_ctr[k], dx = tx - (c & 0xffff), dy = ty - (c >> 16);
     if (dx >= -r && dx <= r && dy >= -r && dy <= r && !(w.excl && (dx | dy) == 0)) {
       const int sx = w.absx ? tx : dx + r, sy = w.absy ? ty : dy + r;
-      wv[q] = wp[(long long)(sx * w.dyn + sy) * w.U + l_unit[k]];
+      wv[q] = wp[widx(w, sx * w.dyn + sy, l_unit[k])];
       dv[q] = l_d[k];
       if (++q == NQ) {
 #pragma unroll
@@ -313,66 +497,65 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_ic_sweep(EngineDev P, La
   B[L.state + i] = st;
 }
 
-// ---- prediction nodes of a k-winners layer: sdr/PredictiveRSDR.cpp:122-160 (delta rule
-// first -- it only touches the few units whose prediction was wrong -- then the activation)
+// ---- prediction nodes of a k-winners layer: sdr/PredictiveRSDR.cpp:122-160 (delta rule first -- it only touches
+// the few units whose prediction was wrong -- then the activation).  Every source here is a binary k-winners plane
+// (the layer's states, the prediction of the layer above), so both the rule and the sums walk the lists of the
+// non-zero cells of the tile's window boxes: rule  w += k*source  is a no-op where the source is 0 (adds +-0), the
+// activation  sum w*source  likewise.  Rows layout; a lane owns its unit's two rows.
+// smem: four lists of `cap` entries (state, previous state; upper prediction, its previous value)
 __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_predict(EngineDev P, LayerDev L, int l, int learn, long long up_p_state,
-                                                                     long long up_p_state_prev, int fb_floats) {
-  extern __shared__ float sm[];
+                                                                     long long up_p_state_prev, int cap_pred, int cap_fb) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ int s_cnt[GRID_TY + 1];
   const GridTile T = grid_tile(blockIdx.x, L.hw, L.row0, L.row1);
   float* B = blob_of(P, T.a);
-  const bool top = l == P.L - 1;
-  const float* up_state = B + up_p_state;
-  const float* up_prev = B + up_p_state_prev;
-  const float* state = B + L.state;
-  const float* sprev = B + L.state_prev;
-  float* wfb = B + L.fb.w_off;
-  float* wpr = B + L.pred.w_off;
-  const long long U = L.pn;
-  const Box bf = top ? Box{0, 0, 0, 0} : window_box(L.fb, T), bp = window_box(L.pred, T);
-  float* sm_pred = sm + fb_floats;
-  if (!top) stage_box(sm, bf, L.fb.tw, L.fb.th, [&](int t) { return up_state[t]; });
-  stage_box(sm_pred, bp, L.pred.tw, L.pred.th, [&](int t) { return state[t]; });
-  __syncthreads();
+  const bool top = l == P.L - 1 || L.fb.r < 0;
+  int2* l_state = reinterpret_cast<int2*>(sm);
+  int2* l_sprev = l_state + cap_pred;
+  int2* l_up = l_sprev + cap_pred;
+  int2* l_upprev = l_up + cap_fb;
+  const Box bp = window_box(L.pred, T);
+  const int n_state = compact_box_cta(B + L.state, bp, L.pred.tw, L.pred.th, l_state, s_cnt);
+  const int n_sprev = learn ? compact_box_cta(B + L.state_prev, bp, L.pred.tw, L.pred.th, l_sprev, s_cnt) : 0;
+  int n_up = 0, n_upprev = 0;
+  if (!top) {
+    const Box bf = window_box(L.fb, T);
+    n_up = compact_box_cta(B + up_p_state, bf, L.fb.tw, L.fb.th, l_up, s_cnt);
+    if (learn) n_upprev = compact_box_cta(B + up_p_state_prev, bf, L.fb.tw, L.fb.th, l_upprev, s_cnt);
+  }
+  if (!T.ok) return;
   const int i = T.unit;
-  float kfb = 0.0f, kpr = 0.0f;
-  bool wrong = false;
-  if (learn && T.ok) {
-    const float err = state[i] - B[L.p_state_prev + i];
+  float* wfb = top ? nullptr : B + L.fb.w_off + (long long)i * L.fb.row_pitch;
+  float* wpr = B + L.pred.w_off + (long long)i * L.pred.row_pitch;
+  if (learn) {
+    const float err = B[L.state + i] - B[L.p_state_prev + i];
     const float surprise = err * err, avg = B[L.p_baseline + i];
     B[L.p_mod + i] = bidi_sigmoid(L.attention_factor * (surprise - avg));
     B[L.p_baseline + i] = (1.0f - L.avg_surprise_decay) * avg + L.avg_surprise_decay * surprise;
-    kfb = L.learn_fb * err; kpr = L.learn_pred * err;
-    wrong = err != 0.0f;
-  }
-  // delta rule: w += k*source for the few units whose prediction was wrong (a zero error or
-  // a zero source adds +-0).  The rule is element-wise, so the 32 lanes of the warp share the
-  // connections of each such unit instead of one lane walking all (2r+1)^2 of them.
-  for (unsigned todo = __ballot_sync(0xffffffffu, wrong); todo; todo &= todo - 1) {
-    const int src = __ffs(todo) - 1, lane = threadIdx.x & 31;
-    const int ux = T.ux0 + src, uy = T.uy, unit = ux + uy * L.hw;
-    const float kfb_w = __shfl_sync(0xffffffffu, kfb, src), kpr_w = __shfl_sync(0xffffffffu, kpr, src);
-    for (int fam = top ? 1 : 0; fam < 2; fam++) {
-      const WinDev& w = fam ? L.pred : L.fb;
-      if (w.r < 0) continue;
-      float* wq = (fam ? wpr : wfb) + unit;
-      const float* from = fam ? sprev : up_prev;
-      const float k = fam ? kpr_w : kfb_w;
-      const SlotBox sb = slot_box(w, ux, uy);
-      for (int sl = lane; sl < w.nslots; sl += 32) {
-        const int sx = sl / w.dyn, sy = sl - sx * w.dyn;
-        const int tx = slot_tx(w, sb, sx), ty = slot_ty(w, sb, sy);
-        if (sx >= sb.sx0 && sx <= sb.sx1 && sy >= sb.sy0 && sy <= sb.sy1 && !(w.excl && tx == sb.cx && ty == sb.cy)) {
-          const float v = from[tx + ty * w.tw];
-          if (v != 0.0f) wq[(long long)sl * U] += k * v;
+    if (err != 0.0f) {
+      const float kfb = L.learn_fb * err, kpr = L.learn_pred * err;
+      for (int fam = top ? 1 : 0; fam < 2; fam++) {
+        const WinDev& w = fam ? L.pred : L.fb;
+        if (w.r < 0) continue;
+        float* wr = fam ? wpr : wfb;
+        const int2* ent = fam ? l_sprev : l_upprev;
+        const int n = fam ? n_sprev : n_upprev;
+        const float k = fam ? kpr : kfb;
+        const int cx = w.cx[T.ux], cy = w.cy[T.uy], r = w.r;
+        for (int q = 0; q < n; q++) {
+          const int2 e = ent[q];
+          const int tx = e.x & 0xffff, ty = e.x >> 16, dx = tx - cx, dy = ty - cy;
+          if (dx >= -r && dx <= r && dy >= -r && dy <= r && !(w.excl && (dx | dy) == 0)) {
+            const int sl = (w.absx ? tx : dx + r) * w.dyn + (w.absy ? ty : dy + r);
+            wr[sl] += k * __int_as_float(e.y);
+          }
         }
       }
     }
   }
-  __syncwarp();
-  if (!T.ok) return;
   float activation = 0.0f;
-  if (!top) activation = box_dot(L.fb, bf, sm, T.ux, T.uy, wfb + i, U, activation);
-  activation = box_dot(L.pred, bp, sm_pred, T.ux, T.uy, wpr + i, U, activation);
+  if (!top) activation = list_dot(L.fb, l_up, n_up, T.ux, T.uy, wfb, activation);
+  activation = list_dot(L.pred, l_state, n_state, T.ux, T.uy, wpr, activation);
   B[L.p_act + i] = activation;
 }
 
@@ -387,7 +570,6 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_learn(EngineDev P, La
   const float* sprev = B + L.state_prev;
   const float* hrec = B + L.recon;
   const int lane = threadIdx.x & 31;
-  const long long U = L.nh;
   const float learn = T.ok ? B[L.state + T.unit] : 0.0f;
   const float att = learn > 0.0f ? B[L.p_mod + T.unit] : 0.0f;
   const float kf = L.learn_ff * att * learn, kr = L.learn_rec * att * learn;
@@ -399,7 +581,7 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_learn(EngineDev P, La
     for (int fam = 0; fam < 2; fam++) {
       const WinDev& w = fam ? L.rec : L.ff;
       if (w.r < 0) continue;
-      float* wp = B + w.w_off + unit;
+      float* wp = B + w.w_off;
       const float* a = fam ? sprev : x;
       const float* b = fam ? hrec : vrec;
       const float k = fam ? kr_w : kf_w;
@@ -409,7 +591,7 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_learn(EngineDev P, La
         const int tx = slot_tx(w, sb, sx), ty = slot_ty(w, sb, sy);
         if (sx >= sb.sx0 && sx <= sb.sx1 && sy >= sb.sy0 && sy <= sb.sy1 && !(w.excl && tx == sb.cx && ty == sb.cy)) {
           const int t = tx + ty * w.tw;
-          wp[(long long)s * U] += k * (a[t] - b[t]);
+          wp[widx(w, s, unit)] += k * (a[t] - b[t]);
         }
       }
     }

@@ -173,7 +173,7 @@ void strip_phase(bidi_engine* h, int phase, bool learn) {
   };
   switch (phase) {
     case 0:
-      if (G.on) grid(bidi::k_g_kw_activate, th, G.ff + G.rec, Y, 0, G.ff);
+      if (G.on) { launch_kw_activate(h, h->stream, G, Y, 0); h->launches++; }
       else strip_launch(h, bidi::k_kw_activate, nh, Y, 0);
       break;
     case 1:
@@ -185,7 +185,7 @@ void strip_phase(bidi_engine* h, int phase, bool learn) {
       else strip_launch(h, bidi::k_reconstruct, nv + nh, Y, 0, Y.state, 0, 0.0f, 0);
       break;
     case 3:
-      if (G.on) grid(bidi::k_g_kw_predict, th, G.fb + G.pred, Y, 0, (int)learn, Y.p_state, Y.p_state_prev, G.fb);
+      if (G.on) grid(bidi::k_g_kw_predict, th, 4 * (G.fb + G.pred), Y, 0, (int)learn, Y.p_state, Y.p_state_prev, G.pred, G.fb);
       else strip_launch(h, bidi::k_predict, nh, Y, 0, (int)learn, Y.p_state, Y.p_state_prev);
       break;
     case 4:
@@ -411,6 +411,8 @@ int bidi_strip_configure(bidi_engine* h, int part, int n_parts) {
   std::fill(h->tiled.begin(), h->tiled.end(), 0);
   {
     int rc2 = select_grid_kernels(h);
+    if (rc2) return rc2;
+    rc2 = apply_layout(h);  // the chosen kernel family decides the layer's layout
     if (rc2) return rc2;
   }
   strip_build_plan(h);

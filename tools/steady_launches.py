@@ -6,10 +6,24 @@ a markdown table of the launches of ONE step and the DRAM traffic per agent-step
 usage: python tools/steady_launches.py launches.csv agents [traffic.json] > profiles/xxx.md
 The capture holds the launches of two steps (the range brackets `--steps 2`); the second step is used."""
 import csv
+import glob
+import hashlib
 import io
 import json
+import os
 import sys
 from collections import OrderedDict
+
+
+def kernel_source_sha():
+    """sha256 over the CUDA sources of the library: bench.py marks `roofline.traffic` stale when the build it runs
+    was compiled from other sources than the ones this capture was taken on."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bidinet_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(root, "*.cu")) + glob.glob(os.path.join(root, "*.cuh")) + glob.glob(os.path.join(root, "*.inl")) + glob.glob(os.path.join(root, "*.h"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 def main():
@@ -46,7 +60,8 @@ def main():
     if len(sys.argv) > 3:
         json.dump({"columns": {"dram_bytes_per_agent_step": col_b / agents, "launches_per_step": col_n, "agents": agents,
                                "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, k_columns*, one steady-state step (tools/steady_launches.py)"},
-                   "whole_step": {"dram_bytes_per_agent_step": tot_b / agents}}, open(sys.argv[3], "w"), indent=1)
+                   "whole_step": {"dram_bytes_per_agent_step": tot_b / agents},
+                   "kernel_source_sha": kernel_source_sha()}, open(sys.argv[3], "w"), indent=1)
 
 
 if __name__ == "__main__":
