@@ -271,6 +271,9 @@ def run_c5(args, rank, world, local_rank):
 
     cfg, ld = cf.config_c5(size)
     eng = Engine(cfg, ld, n_agents=1, device=local_rank)
+    for kv in filter(None, os.environ.get("BIDI_OPTS", "").split(",")):  # experiments only
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     if world > 1:
         eng.strip_configure(rank, world)
     eng.init_random(1234)  # before linking: once linked over peer memory, the neighbours write into this part's state

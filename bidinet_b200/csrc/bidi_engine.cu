@@ -209,6 +209,7 @@ struct bidi_engine {
   // whole step as one cooperative launch (bidi_coop.cuh): the program per value of `learn`
   int coop_mode = 0;                               // option "coop_step": 1 = use it when every layer runs the tile kernels (measured no faster than the graph: off by default)
   bidi::CoopOp* d_coop_ops[2] = {nullptr, nullptr}; int coop_n[2] = {0, 0}; int coop_grid = 0; size_t coop_smem = 0;
+  int dbg_act = 0;                                 // timing experiments on k_g_kw_activate (results are then wrong): 2 skip the dense sum, 4 skip the recurrent sum
   int col_extra_smem = 0;                          // experiment: pad the column kernel's shared memory to lower its residency
   bool strip_use_graph = true;                     // record the split step (NCCL exchanges included) into a CUDA graph
   cudaEvent_t strip_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -650,7 +651,7 @@ void launch_kw_activate(bidi_engine* h, cudaStream_t st, const bidi_engine::Grid
   if (blocks <= 0) return;
   const size_t smem = act_smem_bytes(G);
   const int dyn = (G.act_dense && Y.ff.dxn == Y.ff.dyn && !Y.ff.absx && !Y.ff.absy) ? Y.ff.dyn : 0;
-#define BIDI_ACT(D) bidi::k_g_kw_activate<D><<<(unsigned)blocks, 32, smem, st>>>(h->P, Y, l, G.act_dense, G.act_slab, G.act_box, G.act_cap)
+#define BIDI_ACT(D) bidi::k_g_kw_activate<D><<<(unsigned)blocks, 32, smem, st>>>(h->P, Y, l, G.act_dense | (G.act_dense ? h->dbg_act : 0), G.act_slab, G.act_box, G.act_cap)
   switch (dyn) {
     case 5: BIDI_ACT(5); break;
     case 7: BIDI_ACT(7); break;
@@ -722,6 +723,10 @@ void record_step(Recorder& R, bool learn) {
   const long long A = h->A;
   auto& ly = h->layers;
   if (V == BIDI_KWINNERS) {
+    // The reconstructions of a layer (sdr/RSDR.cpp:165-194) are read by nothing before the learning rule: where the
+    // step is captured into a graph they form a second branch, beside the rest of the up pass and the down pass.
+    const bool fork_recon = R.capturing && !R.collect && h->side != nullptr && h->overlap_learn && h->profile_name.empty();
+    bool forked = false;
     // sdr/PredictiveRSDR.cpp:102-112
     for (int l = 0; l < L; l++) {
       const LayerDev& Y = ly[l];
@@ -734,7 +739,14 @@ void record_step(Recorder& R, bool learn) {
         R.after("kw_activate");
         R.kernels++;
         launch_grid(R, "kw_inhibit", bidi::k_g_kw_inhibit, th, G.lat, Y, l, Y.act, Y.state, nxt);
+        if (fork_recon) {
+          cudaEventRecord(h->ev_fork, h->stream);
+          cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+          R.st = h->side;
+          forked = true;
+        }
         launch_grid(R, "reconstruct", bidi::k_g_reconstruct, tv + th, 3 * G.gather, Y, l, Y.state, 1, 0, G.gather, 0, 0.0f, 0);
+        R.st = nullptr;
       } else if (h->tiled[l]) {
         launch_tile(R, "kw_activate", bidi::k_t_kw_activate, tiles_of(A, Y.nh), tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec)), Y, l);
         launch_tile(R, "kw_inhibit", bidi::k_t_kw_inhibit, tiles_of(A, Y.nh), 0, Y, l, Y.act, Y.state, nxt);
@@ -764,6 +776,10 @@ void record_step(Recorder& R, bool learn) {
         R.launch("kw_inhibit", bidi::k_kw_inhibit, A * Y.nh, Y, l, Y.p_act, Y.p_state, -1LL);
       }
     }
+    if (forked) {  // the reconstructions are in before anything reads them (learning) or overwrites their inputs (stepEnd)
+      cudaEventRecord(h->ev_join, h->side);
+      cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+    }
     // :173-185
     if (learn)
       for (int l = 0; l < L; l++) {
@@ -771,8 +787,20 @@ void record_step(Recorder& R, bool learn) {
         else if (h->tiled[l]) launch_tile(R, "kw_learn", bidi::k_t_kw_learn, tiles_of(A, ly[l].nh), 0, ly[l], l);
         else R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, ly[l], l);
       }
+    // :188-193 -- the input-space prediction gathers from the predicted states and the (just updated) feed-forward
+    // weights; stepEnd's copies touch neither: in a captured graph the two run side by side
+    if (fork_recon && h->gridk[0].on) {
+      cudaEventRecord(h->ev_fork, h->stream);
+      cudaStreamWaitEvent(h->side, h->ev_fork, 0);
+      R.st = h->side;
+      R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
+      R.st = nullptr;
+      cudaEventRecord(h->ev_join, h->side);
+      launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather, 0, 0.0f, 0);
+      cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+      return;
+    }
     R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
-    // :188-193
     if (h->gridk[0].on && !R.collect) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather, 0, 0.0f, 0);
     else if (h->tiled[0])
       launch_tile(R, "kw_predict_input", bidi::k_t_reconstruct, tiles_of(A, ly[0].nv), tile_bytes(ly[0].ff.max_cand), ly[0], 0, ly[0].p_state, 0,
@@ -2279,6 +2307,7 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     CU(cudaFuncSetAttribute(bidi::k_columns16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
     CU(cudaFuncSetAttribute(bidi::k_columns16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
   }
+  else if (std::string(name) == "dbg_act") h->dbg_act = value;
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "overlap_learn") h->overlap_learn = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen

@@ -24,6 +24,10 @@ namespace bidi {
 #define GRID_TX 32
 #define GRID_TY 8
 
+// k / d for 0 <= k < 65536, 1 <= d <= 256 without an integer division: the quotient of (k + 0.5) / d is at least
+// 0.5/d away from an integer, far more than the float error of the product.
+__device__ __forceinline__ int fast_div(int k, float inv_d) { return (int)(((float)k + 0.5f) * inv_d); }
+
 // Element (slot, unit) of a connection family in either layout (bidi_types.h, WinDev::row_pitch).
 __device__ __forceinline__ long long widx(const WinDev& w, int slot, int unit) {
   return w.row_pitch ? (long long)unit * w.row_pitch + slot : (long long)slot * w.U + unit;
@@ -142,65 +146,68 @@ inline int grid_rowbox_floats(const WinDev& w, const int* cx) {
 //     (cp.async.bulk + mbarrier) and reads them with conflict-free 128-bit shared-memory loads;
 //   * the winners-only learning rule and the gather reconstructions touch a winner's row as consecutive sectors
 //     instead of one 32-byte sector per weight.
-// Non-zero cells of plane[] inside box b, in x-major order (tx outer, ty inner), as (tx | ty << 16, value bits).
-// One warp: returns the count.  The box may reach outside the grid (cells there are 0 and never listed).
-__device__ __forceinline__ int compact_box_warp(const float* __restrict__ plane, const Box& b, int tw, int th, int2* __restrict__ ent, int lane) {
-  const int n = b.w * b.h;
-  int base = 0;
-  for (int k0 = 0; k0 < n; k0 += 128) {  // four independent loads in flight per lane
-    float v[4]; int cc[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const int k = k0 + 32 * t + lane, bx = k / b.h, gx = b.x0 + bx, gy = b.y0 + k - bx * b.h;
-      const bool in = k < n && gx >= 0 && gx < tw && gy >= 0 && gy < th;
-      v[t] = in ? plane[gx + gy * tw] : 0.0f;
-      cc[t] = gx | (gy << 16);
-    }
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      const unsigned m = __ballot_sync(0xffffffffu, v[t] != 0.0f);
-      if (v[t] != 0.0f) ent[base + __popc(m & ((1u << lane) - 1u))] = make_int2(cc[t], __float_as_int(v[t]));
-      base += __popc(m);
-    }
-  }
-  __syncwarp();
-  return base;
-}
-// The same by a whole CTA of GRID_TY warps (two barriers inside): warp g lists the g-th part of the traversal.
-__device__ __forceinline__ int compact_box_cta(const float* __restrict__ plane, const Box& b, int tw, int th, int2* __restrict__ ent, int* s_cnt) {
+// Non-zero cells of NL planes inside NL boxes, compacted at once by a CTA of GRID_TY warps.  XMAJOR: traversal tx outer,
+// ty inner (the order of every unit's connection list); else ty outer, tx inner (ascending unit index, the order of
+// the reference's scatter).  A box may reach outside its grid (cells there are 0 and never listed).  Every list's loads
+// are issued before any value is consumed -- one memory round trip for all lists -- and the values stay in registers
+// between the counting and the filling pass.  emit(list, position, gx, gy, value) stores an entry.  s_cnt: [NL][GRID_TY+1].
+template <int NL, bool XMAJOR, class Emit>
+__device__ __forceinline__ void compact_boxes_cta(const float* const (&plane)[NL], const Box (&b)[NL], const int (&tw)[NL], const int (&th)[NL],
+                                                  int (&n_out)[NL], int (*s_cnt)[GRID_TY + 1], Emit&& emit) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = b.w * b.h;
-  const int chunk = ((n + GRID_TY - 1) / GRID_TY + 31) / 32 * 32, k0 = warp * chunk, k1 = min(n, k0 + chunk);
-  int mine = 0;
-  for (int k = k0 + lane; k < k0 + chunk; k += 32) {
-    float d = 0.0f;
-    if (k < k1) {
-      const int bx = k / b.h, gx = b.x0 + bx, gy = b.y0 + k - bx * b.h;
-      if (gx >= 0 && gx < tw && gy >= 0 && gy < th) d = plane[gx + gy * tw];
-    }
-    mine += __popc(__ballot_sync(0xffffffffu, d != 0.0f));
+  constexpr int VM = 4, ROUND = GRID_TY * 32 * VM;  // cells of a list one round covers
+  int nmax = 0;
+  float inv[NL];
+#pragma unroll
+  for (int l = 0; l < NL; l++) {
+    n_out[l] = 0;
+    nmax = max(nmax, b[l].w * b[l].h);
+    inv[l] = 1.0f / (float)max(1, XMAJOR ? b[l].h : b[l].w);
   }
-  __syncthreads();  // (the previous list's readers are done with s_cnt)
-  if (lane == 0) s_cnt[warp + 1] = mine;
-  __syncthreads();
-  int pos = 0;
-  for (int g = 0; g < warp; g++) pos += s_cnt[g + 1];
-  int total = 0;
-  for (int g = 0; g < GRID_TY; g++) total += s_cnt[g + 1];
-  for (int k = k0 + lane; k < k0 + chunk; k += 32) {
-    float d = 0.0f;
-    int cc = 0;
-    if (k < k1) {
-      const int bx = k / b.h, gx = b.x0 + bx, gy = b.y0 + k - bx * b.h;
-      cc = gx | (gy << 16);
-      if (gx >= 0 && gx < tw && gy >= 0 && gy < th) d = plane[gx + gy * tw];
+  for (int r0 = 0; r0 < nmax; r0 += ROUND) {
+    float v[NL][VM];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      const int n = b[l].w * b[l].h;
+#pragma unroll
+      for (int t = 0; t < VM; t++) {
+        const int k = r0 + (warp * VM + t) * 32 + lane;
+        const int q = fast_div(k, inv[l]);
+        const int gx = b[l].x0 + (XMAJOR ? q : k - q * b[l].w), gy = b[l].y0 + (XMAJOR ? k - q * b[l].h : q);
+        v[l][t] = (plane[l] != nullptr && k < n && gx >= 0 && gx < tw[l] && gy >= 0 && gy < th[l]) ? plane[l][gx + gy * tw[l]] : 0.0f;
+      }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, d != 0.0f);
-    if (d != 0.0f) ent[pos + __popc(m & ((1u << lane) - 1u))] = make_int2(cc, __float_as_int(d));
-    pos += __popc(m);
+    int mine[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      mine[l] = 0;
+#pragma unroll
+      for (int t = 0; t < VM; t++) mine[l] += __popc(__ballot_sync(0xffffffffu, v[l][t] != 0.0f));
+    }
+    __syncthreads();  // (the readers of the previous counts are done)
+    if (lane == 0) {
+#pragma unroll
+      for (int l = 0; l < NL; l++) s_cnt[l][warp + 1] = mine[l];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+      int pos = n_out[l], tot = 0;
+      for (int g = 0; g < GRID_TY; g++) { const int c = s_cnt[l][g + 1]; tot += c; if (g < warp) pos += c; }
+#pragma unroll
+      for (int t = 0; t < VM; t++) {
+        const unsigned m = __ballot_sync(0xffffffffu, v[l][t] != 0.0f);
+        if (v[l][t] != 0.0f) {
+          const int k = r0 + (warp * VM + t) * 32 + lane;
+          const int q = fast_div(k, inv[l]);
+          emit(l, pos + __popc(m & ((1u << lane) - 1u)), b[l].x0 + (XMAJOR ? q : k - q * b[l].w), b[l].y0 + (XMAJOR ? k - q * b[l].h : q), v[l][t]);
+        }
+        pos += __popc(m);
+      }
+      n_out[l] += tot;
+    }
   }
   __syncthreads();
-  return total;
 }
 // sum += value * w[unit][slot] over the listed cells inside the unit's window, list order.  Pass 1 marks the hits among
 // the list entries (64 at a time, a bit each); pass 2 loads the weights of four hits together before adding them in order.
@@ -236,13 +243,66 @@ __device__ __forceinline__ float list_dot(const WinDev& w, const int2* __restric
   return sum;
 }
 
+// list_dot in two halves, so that the weight loads of the first hits are in flight while something else runs:
+// list_hits marks the hits among the first 64 entries and loads the weights of the first NP of them.
+template <int NP> struct ListHits { unsigned long long rest; float w[NP], d[NP]; };
+template <int NP>
+__device__ __forceinline__ ListHits<NP> list_hits(const WinDev& w, const int2* __restrict__ ent, int n, int ux, int uy, const float* __restrict__ wrow) {
+  ListHits<NP> H;
+  H.rest = 0ull;
+#pragma unroll
+  for (int j = 0; j < NP; j++) { H.w[j] = 0.0f; H.d[j] = 0.0f; }
+  if (w.r < 0) return H;
+  const int cx = w.cx[ux], cy = w.cy[uy], r = w.r;
+  const unsigned r2 = 2u * (unsigned)r;
+  const int kn = min(64, n);
+  unsigned long long hits = 0ull;
+  for (int k = 0; k < kn; k++) {
+    const int c = ent[k].x, dx = (c & 0xffff) - cx, dy = (c >> 16) - cy;
+    const bool in = (unsigned)(dx + r) <= r2 && (unsigned)(dy + r) <= r2 && !(w.excl && (dx | dy) == 0);
+    hits |= (unsigned long long)in << k;
+  }
+#pragma unroll
+  for (int j = 0; j < NP; j++)
+    if (hits) {
+      const int k = __ffsll((long long)hits) - 1;
+      hits &= hits - 1ull;
+      const int2 e = ent[k];
+      const int tx = e.x & 0xffff, ty = e.x >> 16;
+      H.w[j] = wrow[(w.absx ? tx : tx - cx + r) * w.dyn + (w.absy ? ty : ty - cy + r)];
+      H.d[j] = __int_as_float(e.y);
+    }
+  H.rest = hits;
+  return H;
+}
+template <int NP>
+__device__ __forceinline__ float list_finish(const WinDev& w, const ListHits<NP>& H, const int2* __restrict__ ent, int n, int ux, int uy,
+                                             const float* __restrict__ wrow, float sum) {
+  if (w.r < 0) return sum;
+#pragma unroll
+  for (int j = 0; j < NP; j++) sum += H.d[j] * H.w[j];  // (an absent hit adds +0)
+  if (H.rest) {  // more than NP hits among the first 64 entries
+    const int cx = w.cx[ux], cy = w.cy[uy], r = w.r;
+    for (unsigned long long hits = H.rest; hits; hits &= hits - 1ull) {
+      const int2 e = ent[__ffsll((long long)hits) - 1];
+      const int tx = e.x & 0xffff, ty = e.x >> 16;
+      sum += __int_as_float(e.y) * wrow[(w.absx ? tx : tx - cx + r) * w.dyn + (w.absy ? ty : ty - cy + r)];
+    }
+  }
+  if (n > 64) sum = list_dot(w, ent + 64, n - 64, ux, uy, wrow, sum);
+  return sum;
+}
+
 // ---- sdr/RSDR.cpp:123-133: a = -theta + sum_ff x*w + sum_rec sPrev*w.  One WARP per row segment of 32 units.
 // dense_ff: the visible plane is dense (layer 0): its 32 weight rows are staged by one bulk copy and the window box
 // by the warp.  Otherwise (the visible plane is the binary state of the layer below) the feed-forward sum is sparse too.
+// Every global load the segment needs -- the weight rows, the input box, the box of previous states -- is issued
+// before the first one is consumed, and the recurrent weights of the first hits are fetched under the dense sum.
 // smem: [32*pitch slab | ff box] (dense) , list entries, mbarrier
 template <int DYN>
 __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, int l, int dense_ff, int slab_floats, int box_floats, int cap) {
   extern __shared__ __align__(16) float sm[];
+  constexpr int NB = 20;  // box cells per lane per trip: a 44x13 box (radius 6, 32 units) is one trip
   const int lane = threadIdx.x;
   const int nseg = (L.hw + 31) >> 5, rows = L.row1 - L.row0;
   int bi = blockIdx.x;
@@ -259,6 +319,7 @@ __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, i
   uint64_t* bar = reinterpret_cast<uint64_t*>(ent + cap);
   const int nun = min(32, L.hw - T.ux0);
   const WinDev& wf = L.ff;
+  const WinDev& wr = L.rec;
   if (dense_ff) {
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
@@ -270,22 +331,63 @@ __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, i
   }
   float sum = T.ok ? -B[L.thr + T.unit] : 0.0f;
   const Box bf = window_box(wf, T);
-  if (dense_ff) {
-    // the window box of the segment: coalesced rows, zero outside the grid
-    const int n = bf.w * bf.h;
-    for (int k0 = 0; k0 < n; k0 += 256) {
-      float v[8];
+  const Box br = wr.r >= 0 ? window_box(wr, T) : Box{0, 0, 0, 0};
+  const float* sprev = B + L.state_prev;
+  // non-zero cells of a box, x-major, from a plane: all loads of a trip first, then the ballots
+  auto compact = [&](const float* __restrict__ plane, const Box& b, int tw, int th) -> int {
+    const int n = b.w * b.h;
+    const float inv_h = 1.0f / (float)b.h;
+    int base = 0;
+    for (int k0 = 0; k0 < n; k0 += 32 * NB) {
+      float v[NB];
 #pragma unroll
-      for (int t = 0; t < 8; t++) {
-        const int k = k0 + 32 * t + lane, by = k / bf.w, gx = bf.x0 + k - by * bf.w, gy = bf.y0 + by;
-        v[t] = (k < n && gx >= 0 && gx < wf.tw && gy >= 0 && gy < wf.th) ? x[gx + gy * wf.tw] : 0.0f;
+      for (int t = 0; t < NB; t++) {
+        const int k = k0 + 32 * t + lane, bx = fast_div(k, inv_h), gx = b.x0 + bx, gy = b.y0 + k - bx * b.h;
+        v[t] = (k < n && gx >= 0 && gx < tw && gy >= 0 && gy < th) ? plane[gx + gy * tw] : 0.0f;
       }
 #pragma unroll
-      for (int t = 0; t < 8; t++) { const int k = k0 + 32 * t + lane; if (k < n) xbox[k] = v[t]; }
+      for (int t = 0; t < NB; t++) {
+        const unsigned m = __ballot_sync(0xffffffffu, v[t] != 0.0f);
+        if (m) {
+          if (v[t] != 0.0f) {
+            const int k = k0 + 32 * t + lane, bx = fast_div(k, inv_h);
+            ent[base + __popc(m & ((1u << lane) - 1u))] = make_int2((b.x0 + bx) | ((b.y0 + k - bx * b.h) << 16), __float_as_int(v[t]));
+          }
+          base += __popc(m);
+        }
+      }
     }
     __syncwarp();
+    return base;
+  };
+  if (dense_ff) {
+    // the window box of the segment (coalesced rows, zero outside the grid) and the box of previous states: the loads
+    // of both are in flight together with the bulk copy of the rows
+    const int n = bf.w * bf.h;
+    const float inv_w = 1.0f / (float)bf.w;
+    float xv[NB];
+#pragma unroll
+    for (int t = 0; t < NB; t++) {
+      const int k = 32 * t + lane, by = fast_div(k, inv_w), gx = bf.x0 + k - by * bf.w, gy = bf.y0 + by;
+      xv[t] = (k < n && gx >= 0 && gx < wf.tw && gy >= 0 && gy < wf.th) ? x[gx + gy * wf.tw] : 0.0f;
+    }
+    const int n_rec = (wr.r >= 0 && !(dense_ff & 4)) ? compact(sprev, br, wr.tw, wr.th) : 0;
+#pragma unroll
+    for (int t = 0; t < NB; t++) { const int k = 32 * t + lane; if (k < n) xbox[k] = xv[t]; }
+    for (int k0 = 32 * NB; k0 < n; k0 += 32 * NB) {  // (larger boxes: the rest, trip by trip)
+#pragma unroll
+      for (int t = 0; t < NB; t++) {
+        const int k = k0 + 32 * t + lane, by = fast_div(k, inv_w), gx = bf.x0 + k - by * bf.w, gy = bf.y0 + by;
+        xv[t] = (k < n && gx >= 0 && gx < wf.tw && gy >= 0 && gy < wf.th) ? x[gx + gy * wf.tw] : 0.0f;
+      }
+#pragma unroll
+      for (int t = 0; t < NB; t++) { const int k = k0 + 32 * t + lane; if (k < n) xbox[k] = xv[t]; }
+    }
+    __syncwarp();
+    const float* rrow = B + wr.w_off + (long long)(T.ok ? T.unit : 0) * wr.row_pitch;
+    const ListHits<8> H = (T.ok && wr.r >= 0) ? list_hits<8>(wr, ent, n_rec, T.ux, uy, rrow) : ListHits<8>{};
     mbar_wait(bar, 0);
-    if (T.ok) {
+    if (T.ok && !(dense_ff & 2)) {
       const float* s0 = xbox + (wf.absx ? 0 : wf.cx[T.ux] - wf.r - bf.x0) + (wf.absy ? 0 : wf.cy[uy] - wf.r - bf.y0) * bf.w;
       const float* wrow = slab + lane * wf.row_pitch;
       if (DYN > 0) {
@@ -305,21 +407,27 @@ __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, i
         for (int sx = 0; sx < wf.dxn; sx++)
           for (int sy = 0; sy < wf.dyn; sy++) sum += s0[sx + sy * bf.w] * wrow[sx * wf.dyn + sy];
       }
+      if (wr.r >= 0) sum = list_finish<8>(wr, H, ent, n_rec, T.ux, uy, rrow, sum);
+      B[L.act + T.unit] = sum;
     }
-  } else if (wf.r >= 0) {
-    const int n = compact_box_warp(x, bf, wf.tw, wf.th, ent, lane);
+    return;
+  }
+  if (wf.r >= 0) {
+    const int n = compact(x, bf, wf.tw, wf.th);
     if (T.ok) sum = list_dot(wf, ent, n, T.ux, uy, B + wf.w_off + (long long)T.unit * wf.row_pitch, sum);
     __syncwarp();
   }
-  if (L.rec.r >= 0) {
-    const Box br = window_box(L.rec, T);
-    const int n = compact_box_warp(B + L.state_prev, br, L.rec.tw, L.rec.th, ent, lane);
-    if (T.ok) sum = list_dot(L.rec, ent, n, T.ux, uy, B + L.rec.w_off + (long long)T.unit * L.rec.row_pitch, sum);
+  if (wr.r >= 0) {
+    const int n = compact(sprev, br, wr.tw, wr.th);
+    if (T.ok) sum = list_dot(wr, ent, n, T.ux, uy, B + wr.w_off + (long long)T.unit * wr.row_pitch, sum);
   }
   if (T.ok) B[L.act + T.unit] = sum;
 }
 
-// ---- sdr/RSDR.cpp:135-145, :148-163: rank among the lateral neighbours
+// ---- sdr/RSDR.cpp:135-145, :148-163: rank among the lateral neighbours: s = #{j in lat(i): a_j >= a_i} < sparsity*|lat(i)|.
+// The count only matters up to that limit (1-2 for the usual 1 %), and it can only grow: a lane scans the first two
+// columns of its window alone -- after them ~95 % of the units are known losers -- and the few lanes still in the
+// race get the rest of their window counted by the whole warp, 32 cells per ballot, stopping at the limit.
 __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_inhibit(EngineDev P, LayerDev L, int l, long long src, long long dst, long long dst_next) {
   extern __shared__ float sm[];
   const GridTile T = grid_tile(blockIdx.x, L.hw, L.row0, L.row1);
@@ -329,28 +437,50 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_inhibit(EngineDev P, 
   const Box b = window_box(w, T);
   stage_box(sm, b, w.tw, w.th, [&](int t) { return act[t]; });
   __syncthreads();
-  if (!T.ok) return;
-  const SlotBox sb = slot_box(w, T.ux, T.uy);
-  const float mine = sm[(T.ux - b.x0) + (T.uy - b.y0) * b.w];
-  int cnt = 0;
-  const int ny = sb.sy1 - sb.sy0 + 1;
-  for (int sx = sb.sx0; sx <= sb.sx1; sx++) {
-    const float* sp = sm + (slot_tx(w, sb, sx) - b.x0) + (slot_ty(w, sb, sb.sy0) - b.y0) * b.w;
-    if (ny == 13) {  // an interior unit of a radius-6 layer: the whole column at once
+  const int lane = threadIdx.x & 31;
+  float mine = 0.0f, lim = 0.0f;
+  int cnt = 0, col = 0, sx1 = -1, ny = 0, bx = 0, by = 0, selfcol = 0;  // bx, by: box coordinates of the window's column `col`, row sy0
+  if (T.ok) {
+    const SlotBox sb = slot_box(w, T.ux, T.uy);
+    mine = sm[(T.ux - b.x0) + (T.uy - b.y0) * b.w];
+    lim = L.sparsity * (float)slot_count(w, sb);
+    col = sb.sx0; sx1 = sb.sx1; ny = sb.sy1 - sb.sy0 + 1;
+    by = slot_ty(w, sb, sb.sy0) - b.y0;
+    selfcol = w.absx ? sb.cx : w.r;
+    constexpr int NC1 = 2;
+    for (int c = 0; c < NC1 && col <= sx1; c++, col++) {
+      const float* sp = sm + (slot_tx(w, sb, col) - b.x0) + by * b.w;
+      if (ny == 13) {
 #pragma unroll
-      for (int q = 0; q < 13; q++) cnt += sp[q * b.w] >= mine ? 1 : 0;
-    } else if (ny == 7) {
-#pragma unroll
-      for (int q = 0; q < 7; q++) cnt += sp[q * b.w] >= mine ? 1 : 0;
-    } else {
+        for (int q = 0; q < 13; q++) cnt += sp[q * b.w] >= mine ? 1 : 0;
+      } else {
 #pragma unroll 4
-      for (int q = 0; q < ny; q++) cnt += sp[q * b.w] >= mine ? 1 : 0;
+        for (int q = 0; q < ny; q++) cnt += sp[q * b.w] >= mine ? 1 : 0;
+      }
     }
+    bx = slot_tx(w, sb, col) - b.x0;
   }
-  cnt -= 1;  // the loop counted the unit itself (mine >= mine); the lateral list excludes the centre
-  const float s = (float)cnt < L.sparsity * (float)slot_count(w, sb) ? 1.0f : 0.0f;
-  B[dst + T.unit] = s;
-  if (dst_next >= 0) B[dst_next + T.unit] = s;
+  // the unit itself is inside its window (mine >= mine) but not in the lateral list: it counts once the scan has passed its column
+  const bool lost = T.ok && (float)(cnt - (selfcol < col ? 1 : 0)) >= lim;
+  for (unsigned todo = __ballot_sync(0xffffffffu, T.ok && !lost && col <= sx1); todo; todo &= todo - 1) {
+    const int s = __ffs(todo) - 1;
+    const float mine_s = __shfl_sync(0xffffffffu, mine, s), lim_s = __shfl_sync(0xffffffffu, lim, s);
+    const int ny_s = __shfl_sync(0xffffffffu, ny, s), bx_s = __shfl_sync(0xffffffffu, bx, s), by_s = __shfl_sync(0xffffffffu, by, s);
+    const int cols_s = __shfl_sync(0xffffffffu, sx1 - col + 1, s), cnt_s = __shfl_sync(0xffffffffu, cnt, s);
+    const int rem = cols_s * ny_s;
+    int c = 0;
+    for (int j0 = 0; j0 < rem; j0 += 32) {
+      const int j = j0 + lane, jx = j / ny_s, jy = j - jx * ny_s;
+      const bool ge = j < rem && sm[(bx_s + jx) + (by_s + jy) * b.w] >= mine_s;
+      c += __popc(__ballot_sync(0xffffffffu, ge));
+      if ((float)(cnt_s + c - 1) >= lim_s) break;  // (at most one of them is the unit itself)
+    }
+    if (lane == s) { cnt += c; col = sx1 + 1; }
+  }
+  if (!T.ok) return;
+  const float st = (!lost && (float)(cnt - 1) < lim) ? 1.0f : 0.0f;
+  B[dst + T.unit] = st;
+  if (dst_next >= 0) B[dst_next + T.unit] = st;
 }
 
 // ---- gather-form reconstruction (sdr/RSDR.cpp:165-212): tiles [0,vt) of an agent own
@@ -388,57 +518,47 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_reconstruct(EngineDev P,
   int* l_unit = reinterpret_cast<int*>(sm);   // [nb] unit index
   int* l_ctr = l_unit + cap;                  // [nb] window centre, cx | cy << 16
   float* l_d = sm + 2 * cap;                  // [nb] drive
-  __shared__ int s_cnt[GRID_TY + 1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk = ((nb + GRID_TY - 1) / GRID_TY + 31) / 32 * 32, k0 = warp * chunk, k1 = min(nb, k0 + chunk);
-  int mine = 0;
-  for (int k = k0 + lane; k < k0 + chunk; k += 32) {
-    float d = 0.0f;
-    if (k < k1) { const int by = k / bw; d = drive[(bx0 + k - by * bw) + (by0 + by) * w.uw]; }
-    mine += __popc(__ballot_sync(0xffffffffu, d != 0.0f));
-  }
-  if (lane == 0) s_cnt[warp + 1] = mine;
-  __syncthreads();
-  if (threadIdx.x == 0) { s_cnt[0] = 0; for (int g = 0; g < GRID_TY; g++) s_cnt[g + 1] += s_cnt[g]; }
-  __syncthreads();
-  int pos = s_cnt[warp];
-  for (int k = k0 + lane; k < k0 + chunk; k += 32) {
-    float d = 0.0f;
-    int ux = 0, uy = 0;
-    if (k < k1) { const int by = k / bw; ux = bx0 + k - by * bw; uy = by0 + by; d = drive[ux + uy * w.uw]; }
-    const unsigned m = __ballot_sync(0xffffffffu, d != 0.0f);
-    if (d != 0.0f) {
-      const int q = pos + __popc(m & ((1u << lane) - 1u));
-      l_unit[q] = ux + uy * w.uw; l_ctr[q] = w.cx[ux] | (w.cy[uy] << 16); l_d[q] = d;
-    }
-    pos += __popc(m);
-  }
-  __syncthreads();
+  __shared__ int s_cnt[1][GRID_TY + 1];
+  const float* const planes[1] = {drive};
+  const Box boxes[1] = {Box{bx0, by0, bw, bh}};
+  const int tws[1] = {w.uw}, ths[1] = {w.uh};
+  int cnt[1];
+  compact_boxes_cta<1, false>(planes, boxes, tws, ths, cnt, s_cnt, [&](int, int q, int ux, int uy, float d) {
+    l_unit[q] = ux + uy * w.uw; l_ctr[q] = w.cx[ux] | (w.cy[uy] << 16); l_d[q] = d;
+  });
   if (!T.ok) return;
-  const int tx = T.ux, ty = T.uy, n = s_cnt[GRID_TY], r = w.r;
+  const int tx = T.ux, ty = T.uy, n = cnt[0], r = w.r;
+  const unsigned r2 = 2u * (unsigned)r;
   const float* wp = B + w.w_off;
   float sum = 0.0f;
-  // list entries whose window contains this cell, NQ at a time: the weight loads of a batch are all
-  // issued before the batch is added up, in list order (neo/SparseCoder.cpp:242-259: w*state*multiplier)
-  constexpr int NQ = 8;
-  float wv[NQ], dv[NQ];
-  int q = 0;
-  for (int k = 0; k < n; k++) {
-    const int c = l_ctr[k], dx = tx - (c & 0xffff), dy = ty - (c >> 16);
-    if (dx >= -r && dx <= r && dy >= -r && dy <= r && !(w.excl && (dx | dy) == 0)) {
-      const int sx = w.absx ? tx : dx + r, sy = w.absy ? ty : dy + r;
-      wv[q] = wp[widx(w, sx * w.dyn + sy, l_unit[k])];
-      dv[q] = l_d[k];
-      if (++q == NQ) {
+  // list entries whose window contains this cell: marked 64 entries at a time, then the weights of four hits are
+  // loaded together and added in list order (neo/SparseCoder.cpp:242-259: w*state*multiplier)
+  for (int k0 = 0; k0 < n; k0 += 64) {
+    unsigned long long hits = 0ull;
+    const int kn = min(64, n - k0);
+    for (int k = 0; k < kn; k++) {
+      const int c = l_ctr[k0 + k], dx = tx - (c & 0xffff), dy = ty - (c >> 16);
+      const bool in = (unsigned)(dx + r) <= r2 && (unsigned)(dy + r) <= r2 && !(w.excl && (dx | dy) == 0);
+      hits |= (unsigned long long)in << k;
+    }
+    while (hits) {
+      float wv[4], dv[4];
 #pragma unroll
-        for (int j = 0; j < NQ; j++) sum += scaled ? wv[j] * dv[j] * mult : wv[j] * dv[j];
-        q = 0;
+      for (int j = 0; j < 4; j++) {
+        wv[j] = 0.0f; dv[j] = 0.0f;
+        if (hits) {
+          const int k = k0 + __ffsll((long long)hits) - 1;
+          hits &= hits - 1ull;
+          const int c = l_ctr[k];
+          const int sx = w.absx ? tx : tx - (c & 0xffff) + r, sy = w.absy ? ty : ty - (c >> 16) + r;
+          wv[j] = wp[widx(w, sx * w.dyn + sy, l_unit[k])];
+          dv[j] = l_d[k];
+        }
       }
+#pragma unroll
+      for (int j = 0; j < 4; j++) sum += scaled ? wv[j] * dv[j] * mult : wv[j] * dv[j];  // (an absent hit adds +0)
     }
   }
-#pragma unroll
-  for (int j = 0; j < NQ; j++)
-    if (j < q) sum += scaled ? wv[j] * dv[j] * mult : wv[j] * dv[j];
   out[T.unit] = sum;
   if (!vis && copy_spike) B[L.spike_prev + T.unit] = B[L.spike + T.unit];  // spikePrev = spike (sdr/IRSDR.cpp:170-171)
 }
@@ -506,7 +626,7 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_ic_sweep(EngineDev P, La
 __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_predict(EngineDev P, LayerDev L, int l, int learn, long long up_p_state,
                                                                      long long up_p_state_prev, int cap_pred, int cap_fb) {
   extern __shared__ __align__(16) float sm[];
-  __shared__ int s_cnt[GRID_TY + 1];
+  __shared__ int s_cnt[4][GRID_TY + 1];
   const GridTile T = grid_tile(blockIdx.x, L.hw, L.row0, L.row1);
   float* B = blob_of(P, T.a);
   const bool top = l == P.L - 1 || L.fb.r < 0;
@@ -514,15 +634,24 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_predict(EngineDev P, 
   int2* l_sprev = l_state + cap_pred;
   int2* l_up = l_sprev + cap_pred;
   int2* l_upprev = l_up + cap_fb;
-  const Box bp = window_box(L.pred, T);
-  const int n_state = compact_box_cta(B + L.state, bp, L.pred.tw, L.pred.th, l_state, s_cnt);
-  const int n_sprev = learn ? compact_box_cta(B + L.state_prev, bp, L.pred.tw, L.pred.th, l_sprev, s_cnt) : 0;
-  int n_up = 0, n_upprev = 0;
-  if (!top) {
-    const Box bf = window_box(L.fb, T);
-    n_up = compact_box_cta(B + up_p_state, bf, L.fb.tw, L.fb.th, l_up, s_cnt);
-    if (learn) n_upprev = compact_box_cta(B + up_p_state_prev, bf, L.fb.tw, L.fb.th, l_upprev, s_cnt);
+  const Box bp = window_box(L.pred, T), bfb = top ? Box{0, 0, 0, 0} : window_box(L.fb, T);
+  int cnt[4] = {0, 0, 0, 0};
+  int2* const lists[4] = {l_state, l_sprev, l_up, l_upprev};
+  auto emit = [&](int li, int q, int gx, int gy, float v) { lists[li][q] = make_int2(gx | (gy << 16), __float_as_int(v)); };
+  if (top) {
+    const float* const planes[2] = {B + L.state, learn ? B + L.state_prev : nullptr};
+    const Box boxes[2] = {bp, bp};
+    const int tws[2] = {L.pred.tw, L.pred.tw}, ths[2] = {L.pred.th, L.pred.th};
+    int c2[2];
+    compact_boxes_cta<2, true>(planes, boxes, tws, ths, c2, s_cnt, emit);
+    cnt[0] = c2[0]; cnt[1] = c2[1];
+  } else {
+    const float* const planes[4] = {B + L.state, learn ? B + L.state_prev : nullptr, B + up_p_state, learn ? B + up_p_state_prev : nullptr};
+    const Box boxes[4] = {bp, bp, bfb, bfb};
+    const int tws[4] = {L.pred.tw, L.pred.tw, L.fb.tw, L.fb.tw}, ths[4] = {L.pred.th, L.pred.th, L.fb.th, L.fb.th};
+    compact_boxes_cta<4, true>(planes, boxes, tws, ths, cnt, s_cnt, emit);
   }
+  const int n_state = cnt[0], n_sprev = cnt[1], n_up = cnt[2], n_upprev = cnt[3];
   if (!T.ok) return;
   const int i = T.unit;
   float* wfb = top ? nullptr : B + L.fb.w_off + (long long)i * L.fb.row_pitch;
@@ -559,44 +688,61 @@ __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_predict(EngineDev P, 
   B[L.p_act + i] = activation;
 }
 
-// ---- sdr/RSDR.cpp:241-266: winners only; theta for every unit.  A warp owns 32 adjacent
-// units; for each winner among them the 32 lanes share its connections (the rule is
-// element-wise), so a winner's 2*(2r+1)^2 weights take a dozen round trips, not hundreds.
+// ---- sdr/RSDR.cpp:241-266: winners only; theta for every unit.  The tile's winners are listed in shared memory and
+// dealt to its warps one each: the 32 lanes share a winner's connections (the rule is element-wise and a winner's
+// row is contiguous), every load of a family in flight before the first store.
 __global__ void __launch_bounds__(GRID_TX* GRID_TY) k_g_kw_learn(EngineDev P, LayerDev L, int l) {
+  __shared__ int s_n;
+  __shared__ int s_who[GRID_TX * GRID_TY];
+  __shared__ float s_kf[GRID_TX * GRID_TY], s_kr[GRID_TX * GRID_TY];
   const GridTile T = grid_tile(blockIdx.x, L.hw, L.row0, L.row1);
   float* B = blob_of(P, T.a);
   const float* x = vis_input_of(P, L, l, T.a);
   const float* vrec = B + L.vis_recon;
   const float* sprev = B + L.state_prev;
   const float* hrec = B + L.recon;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
   const float learn = T.ok ? B[L.state + T.unit] : 0.0f;
-  const float att = learn > 0.0f ? B[L.p_mod + T.unit] : 0.0f;
-  const float kf = L.learn_ff * att * learn, kr = L.learn_rec * att * learn;
-  unsigned winners = __ballot_sync(0xffffffffu, learn > 0.0f);
-  for (; winners; winners &= winners - 1) {
-    const int src = __ffs(winners) - 1;
-    const int ux = T.ux0 + src, uy = T.uy, unit = ux + uy * L.hw;
-    const float kf_w = __shfl_sync(0xffffffffu, kf, src), kr_w = __shfl_sync(0xffffffffu, kr, src);
+  if (learn > 0.0f) {
+    const float att = B[L.p_mod + T.unit];
+    const int q = atomicAdd(&s_n, 1);
+    s_who[q] = T.ux | (T.uy << 16);
+    s_kf[q] = L.learn_ff * att * learn; s_kr[q] = L.learn_rec * att * learn;
+  }
+  if (T.ok) B[L.thr + T.unit] += L.learn_threshold * (learn - L.sparsity);
+  __syncthreads();
+  const int nwin = s_n;
+  for (int q = warp; q < nwin; q += GRID_TY) {
+    const int ux = s_who[q] & 0xffff, uy = s_who[q] >> 16, unit = ux + uy * L.hw;
     for (int fam = 0; fam < 2; fam++) {
       const WinDev& w = fam ? L.rec : L.ff;
       if (w.r < 0) continue;
       float* wp = B + w.w_off;
       const float* a = fam ? sprev : x;
       const float* b = fam ? hrec : vrec;
-      const float k = fam ? kr_w : kf_w;
+      const float k = fam ? s_kr[q] : s_kf[q];
       const SlotBox sb = slot_box(w, ux, uy);
-      for (int s = lane; s < w.nslots; s += 32) {
-        const int sx = s / w.dyn, sy = s - sx * w.dyn;
-        const int tx = slot_tx(w, sb, sx), ty = slot_ty(w, sb, sy);
-        if (sx >= sb.sx0 && sx <= sb.sx1 && sy >= sb.sy0 && sy <= sb.sy1 && !(w.excl && tx == sb.cx && ty == sb.cy)) {
-          const int t = tx + ty * w.tw;
-          wp[widx(w, s, unit)] += k * (a[t] - b[t]);
+      const float inv_dyn = 1.0f / (float)w.dyn;
+      constexpr int NJ = 6;  // 192 slots per trip: a radius-6 window (169 slots) is one trip of independent loads
+      for (int s0 = 0; s0 < w.nslots; s0 += 32 * NJ) {
+        float wv[NJ], av[NJ], bv[NJ];
+        bool ok[NJ];
+#pragma unroll
+        for (int j = 0; j < NJ; j++) {
+          const int s = s0 + 32 * j + lane, sx = fast_div(s, inv_dyn), sy = s - sx * w.dyn;
+          const int tx = slot_tx(w, sb, sx), ty = slot_ty(w, sb, sy);
+          ok[j] = s < w.nslots && sx >= sb.sx0 && sx <= sb.sx1 && sy >= sb.sy0 && sy <= sb.sy1 && !(w.excl && tx == sb.cx && ty == sb.cy);
+          wv[j] = 0.0f; av[j] = 0.0f; bv[j] = 0.0f;
+          if (ok[j]) { const int t = tx + ty * w.tw; wv[j] = wp[widx(w, s, unit)]; av[j] = a[t]; bv[j] = b[t]; }
         }
+#pragma unroll
+        for (int j = 0; j < NJ; j++)
+          if (ok[j]) wp[widx(w, s0 + 32 * j + lane, unit)] = wv[j] + k * (av[j] - bv[j]);
       }
     }
   }
-  if (T.ok) B[L.thr + T.unit] += L.learn_threshold * (learn - L.sparsity);
 }
 
 } // namespace bidi
