@@ -22,6 +22,7 @@
 #include "bidi_coder_dense.cuh"
 #include "bidi_tiles.cuh"
 #include "bidi_grid.cuh"
+#include "bidi_persist.cuh"
 #include "bidi_coop.cuh"
 #include "bidi_qnet.cuh"
 #include "bidi_env.cuh"
@@ -145,6 +146,9 @@ struct bidi_engine {
   // per layer: the 2-D tile kernels of bidi_grid.cuh apply (large k-winners layers); shared-memory floats they stage
   struct GridSizes { int on, ff, rec, lat, fb, pred, gather; int act_slab, act_box, act_cap, act_dense; };  // act_*: k_g_kw_activate (row segments)
   std::vector<GridSizes> gridk;
+  std::vector<bidi::PersistShape> persist;  // per layer: the whole iterative coder as one cooperative launch (bidi_persist.cuh)
+  unsigned* d_persist_ctr = nullptr;        // its grid barrier's arrival counters, one per layer
+  int persist_mode = 1;            // option "persist_coder"
   int grid_mode = 1;               // 0 off, 1 layers at least 16 units wide that are not tiled, 2 every layer
   EngineDev P;                     // kernel argument
   // device memory
@@ -662,6 +666,107 @@ void launch_kw_activate(bidi_engine* h, cudaStream_t st, const bidi_engine::Grid
   }
 #undef BIDI_ACT
 }
+// ---- bidi_persist.cuh: which layers of a single ITERATIVE agent run their whole coder as one cooperative launch
+template <int DYN> int persist_prepare(bidi_engine* h, size_t smem) {
+  if (smem > 48 * 1024) CU(cudaFuncSetAttribute(bidi::k_ic_layer_persist<DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return BIDI_OK;
+}
+int select_persist(bidi_engine* h) {
+  h->persist.assign(h->L, bidi::PersistShape{});
+  if (h->cfg.variant != BIDI_ITERATIVE || h->A != 1 || !h->persist_mode || h->csrl || h->strip_n > 1) return BIDI_OK;
+  int sms = 0, coop = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+  if (!coop || sms < 1) return BIDI_OK;
+  size_t most = 0;
+  for (int l = 0; l < h->L; l++) {
+    const LayerDev& D = h->layers[l];
+    const LayerHost& H = h->hl[l];
+    if (D.lat.r < 0 || D.nh < 256 || h->coder_cta[l] == 2) continue;  // small or dense layers have their fused one-CTA kernels
+    const int nslots = D.ff.nslots + (D.rec.r >= 0 ? D.rec.nslots : 0) + D.lat.nslots;
+    bidi::PersistShape S{};
+    // hidden tiles: as many as there are SMs at most -- but at least ~16 units each, the grid barrier costs with the number
+    // of CTAs --, weights of a tile within ~150 KB, at most 128 units (two sums per unit on 256 threads)
+    const int cap = std::min(sms, std::max(8, D.nh / 16));
+    const int vcap = std::min(sms, std::max(cap, (D.nv + 127) / 128));
+    int best = 0;
+    for (int tx : {2, 4, 8, 16, 32})
+      for (int ty : {1, 2, 4, 8, 16}) {
+        const int ut = tx * ty, nx = (D.hw + tx - 1) / tx, ny = (D.hh + ty - 1) / ty;
+        if (ut > 128 || (size_t)ut * nslots * 4 > 150 * 1024 || nx * ny > cap) continue;
+        const int score = nx * ny * 64 - std::abs(tx - ty);  // most tiles, then the squarest
+        if (score > best) { best = score; S.htx = tx; S.hty = ty; S.hnx = nx; S.hny = ny; }
+      }
+    if (!best) continue;
+    best = 0;
+    for (int tx : {2, 4, 8, 16, 32})
+      for (int ty : {1, 2, 4, 8, 16}) {
+        const int nx = (D.vw + tx - 1) / tx, ny = (D.vh + ty - 1) / ty;
+        if (tx * ty > 128 || nx * ny > vcap) continue;
+        const int score = nx * ny * 64 - std::abs(tx - ty);
+        if (score > best) { best = score; S.vtx = tx; S.vty = ty; S.vnx = nx; S.vny = ny; }
+      }
+    if (!best) continue;
+    S.ut = S.htx * S.hty;
+    auto box = [](const WinHost& w, int tx, int ty) {
+      if (w.d.r < 0) return 0;
+      int bw = w.d.tw, bh = w.d.th;
+      if (!w.d.absx) { bw = 0; for (int u = 0; u < w.d.uw; u += tx) bw = std::max(bw, w.cx[std::min(u + tx, w.d.uw) - 1] - w.cx[u] + 2 * w.d.r + 1); }
+      if (!w.d.absy) { bh = 0; for (int u = 0; u < w.d.uh; u += ty) bh = std::max(bh, w.cy[std::min(u + ty, w.d.uh) - 1] - w.cy[u] + 2 * w.d.r + 1); }
+      return bw * bh;
+    };
+    auto cand = [](const WinHost& w, int tx, int ty) {
+      if (w.d.r < 0) return 0;
+      int bw = 0, bh = 0;
+      for (int t0 = 0; t0 < w.d.tw; t0 += tx) {
+        int lo = w.d.uw, hi = -1;
+        for (int t = t0; t < std::min(t0 + tx, w.d.tw); t++) { lo = std::min(lo, w.gxlo[t]); hi = std::max(hi, w.gxhi[t]); }
+        bw = std::max(bw, hi - lo + 1);
+      }
+      for (int t0 = 0; t0 < w.d.th; t0 += ty) {
+        int lo = w.d.uh, hi = -1;
+        for (int t = t0; t < std::min(t0 + ty, w.d.th); t++) { lo = std::min(lo, w.gylo[t]); hi = std::max(hi, w.gyhi[t]); }
+        bh = std::max(bh, hi - lo + 1);
+      }
+      return std::max(0, bw) * std::max(0, bh);
+    };
+    S.box_ff = (box(H.ff, S.htx, S.hty) + 3) & ~3; S.box_rec = (box(H.rec, S.htx, S.hty) + 3) & ~3; S.box_lat = (box(H.lat, S.htx, S.hty) + 3) & ~3;
+    S.cap_ff = cand(H.ff, S.vtx, S.vty) + 4; S.cap_rec = cand(H.rec, S.htx, S.hty) + 4;
+    S.blocks = std::max(S.hnx * S.hny, S.vnx * S.vny);
+    const int dy = D.ff.dyn;
+    S.dyn = (dy == D.lat.dyn && (D.rec.r < 0 || dy == D.rec.dyn) && (dy == 7 || dy == 13)) ? dy : 0;
+    S.smem_floats = (long long)nslots * S.ut + S.box_ff + S.box_rec + S.box_lat + S.ut + 3LL * (S.cap_ff + S.cap_rec) + 2LL * (D.hw + D.hh) + 8;
+    if (S.smem_floats * 4 > 200 * 1024) continue;
+    S.on = 1;
+    most = std::max(most, (size_t)S.smem_floats * 4);
+    h->persist[l] = S;
+  }
+  if (most > 0) {
+    int rc = persist_prepare<0>(h, most); if (rc) return rc;
+    rc = persist_prepare<7>(h, most); if (rc) return rc;
+    rc = persist_prepare<13>(h, most); if (rc) return rc;
+    if (!h->d_persist_ctr) CU(cudaMalloc(&h->d_persist_ctr, sizeof(unsigned) * BIDI_MAX_LAYERS));
+  }
+  return BIDI_OK;
+}
+// one cooperative launch: the up pass of layer l
+int launch_persist(bidi_engine* h, cudaStream_t st, int l) {
+  const bidi::PersistShape& S = h->persist[l];
+  unsigned* ctr = h->d_persist_ctr + l;
+  CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned), st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)S.blocks); cfg.blockDim = dim3(BIDI_PERSIST_THREADS);
+  cfg.dynamicSmemBytes = (size_t)S.smem_floats * 4; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  switch (S.dyn) {
+    case 7: CU(cudaLaunchKernelEx(&cfg, bidi::k_ic_layer_persist<7>, h->P, h->layers[l], l, S, ctr)); break;
+    case 13: CU(cudaLaunchKernelEx(&cfg, bidi::k_ic_layer_persist<13>, h->P, h->layers[l], l, S, ctr)); break;
+    default: CU(cudaLaunchKernelEx(&cfg, bidi::k_ic_layer_persist<0>, h->P, h->layers[l], l, S, ctr)); break;
+  }
+  return BIDI_OK;
+}
 // which layers run the 2-D tile kernels, and how much shared memory they stage
 int select_grid_kernels(bidi_engine* h) {
   h->gridk.assign(h->L, bidi_engine::GridSizes{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
@@ -854,6 +959,14 @@ void record_step(Recorder& R, bool learn) {
       continue;
     }
     const LayerDev& Y = ly[l];
+    if (V == BIDI_ITERATIVE && h->persist[l].on && !h->force_phase_kernels && !R.collect && h->coop_mode == 0) {  // bidi_persist.cuh
+      R.before("coder");
+      launch_persist(h, R.s(), l);
+      R.after("coder");
+      R.kernels++;
+      if (l < L - 1) R.launch("ic_finish", bidi::k_ic_finish, nh, Y, l, 0, 0.0f, ly[l + 1].vis_input);
+      continue;
+    }
     const bool tl = h->tiled[l] != 0;
     const size_t sm_sweep = tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec) + nslots_of(Y.lat));
     const size_t sm_rec = tile_bytes(std::max(Y.ff.max_cand, Y.rec.max_cand));
@@ -1153,7 +1266,7 @@ void bidi_destroy(bidi_engine* h) {
   cudaFree(h->d_blob); cudaFree(h->d_in0); cudaFree(h->d_pred); cudaFree(h->d_rewards); cudaFree(h->d_noise_u);
   cudaFree(h->d_noise_v); cudaFree(h->d_col_actions); cudaFree(h->d_frames); cudaFree(h->d_frame_rewards);
   cudaFree(h->d_frame_noise_u); cudaFree(h->d_frame_noise_v); cudaFree(h->d_env); cudaFree(h->d_env_noise);
-  cudaFree(h->d_tables); cudaFree(h->d_layers); cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
+  cudaFree(h->d_persist_ctr); cudaFree(h->d_tables); cudaFree(h->d_layers); cudaFree(h->d_fb_src); cudaFree(h->d_fb_dst);
   cudaFree(h->d_qmask); cudaFree(h->d_qtables); cudaFree(h->d_csrl_tables); cudaFree(h->d_gen); cudaFree(h->d_gen_scale); cudaFreeHost(h->h_gen);
   for (auto& e : h->profile_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   cudaFreeHost(h->h_in); cudaFreeHost(h->h_pred); cudaFreeHost(h->h_rewards); cudaFreeHost(h->h_noise); cudaFreeHost(h->h_actions);
@@ -1732,6 +1845,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     }
   }
   if (select_grid_kernels(h) != BIDI_OK) return bail(BIDI_ECUDA, g_last_error);
+  if (select_persist(h) != BIDI_OK) return bail(BIDI_ECUDA, g_last_error);
   if (apply_layout(h) != BIDI_OK) return bail(BIDI_ECUDA, g_last_error);  // (after the kernel families are chosen: they decide the layouts)
   // the column kernel may need more than the default 48 KB of dynamic shared memory
   if (V == BIDI_NEO_AGENT) {
@@ -2308,6 +2422,11 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     CU(cudaFuncSetAttribute(bidi::k_columns16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
   }
   else if (std::string(name) == "dbg_act") h->dbg_act = value;
+  else if (std::string(name) == "persist_coder") {  // 0: the per-phase kernels for the large layers of a single iterative agent
+    h->persist_mode = value != 0;
+    int rc = select_persist(h);
+    if (rc) return rc;
+  }
   else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "overlap_learn") h->overlap_learn = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen

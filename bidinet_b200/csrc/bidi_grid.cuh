@@ -174,7 +174,8 @@ __device__ __forceinline__ void compact_boxes_cta(const float* const (&plane)[NL
         const int k = r0 + (warp * VM + t) * 32 + lane;
         const int q = fast_div(k, inv[l]);
         const int gx = b[l].x0 + (XMAJOR ? q : k - q * b[l].w), gy = b[l].y0 + (XMAJOR ? k - q * b[l].h : q);
-        v[l][t] = (plane[l] != nullptr && k < n && gx >= 0 && gx < tw[l] && gy >= 0 && gy < th[l]) ? plane[l][gx + gy * tw[l]] : 0.0f;
+        // (through the L2: in the persistent layer kernel other CTAs rewrite these planes between two barriers)
+        v[l][t] = (plane[l] != nullptr && k < n && gx >= 0 && gx < tw[l] && gy >= 0 && gy < th[l]) ? __ldcg(plane[l] + gx + gy * tw[l]) : 0.0f;
       }
     }
     int mine[NL];

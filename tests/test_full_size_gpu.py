@@ -172,3 +172,38 @@ def test_c5_full_size_split_equals_unsplit():
     assert whole.get_array("HID_STATE", 0).sum() > 1000
     parts.close()
     whole.close()
+
+
+@pytest.mark.parametrize("geom", ["ragged_r3", "wide_r5_norec"])
+def test_persistent_coder_of_a_single_iterative_agent(geom):
+    """bidi_persist.cuh: the whole iterative coder of a large layer of ONE agent as one cooperative launch (weights of a
+    tile of units resident in shared memory for all 35 iterations, grid barrier between sweep and reconstruction).
+    Geometries whose grids are not multiples of the tile sizes, with ratios above and below 1, with and without a
+    recurrent family; the second layer is too small for it and runs the per-phase kernels.  Exact against the oracle,
+    every array, and equal to the per-phase kernels of the same engine build (option persist_coder = 0)."""
+    if geom == "ragged_r3":
+        cfg, ld = cf.make_config(cf.ITERATIVE, 40, 28, [dict(width=27, height=21), dict(width=14, height=12)], r_infb=5)
+        n_in = 40 * 28
+    else:
+        layers = [dict(width=36, height=30, r_ff=5, r_lat=5, r_rec=-1, r_pred=2, r_fb=2), dict(width=20, height=24, r_ff=4)]
+        cfg, ld = cf.make_config(cf.ITERATIVE, 30, 33, layers, r_infb=3)
+        n_in = 30 * 33
+    orc = OracleHierarchy(cfg, ld, 77)
+    eng = Engine(cfg, ld, n_agents=1, seed=77)
+    ref = Engine(cfg, ld, n_agents=1, seed=77)
+    ref.set_option("persist_coder", 0)
+    assert eng.launch_count == ref.launch_count == 0
+    rng = np.random.RandomState(3)
+    for t in range(6):
+        x = (rng.rand(n_in) < 0.3).astype(np.float32) * rng.rand(n_in).astype(np.float32)
+        for e in (orc, eng, ref):
+            e.set_inputs(x)
+        orc.step()
+        eng.step()
+        ref.step()
+        assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0]), t
+    assert eng.launch_count < ref.launch_count, "the persistent kernel was not the path taken"
+    assert diff_states(orc.state(), eng.state()) == []
+    assert diff_states(ref.state(), eng.state()) == []
+    for e in (eng, ref):
+        e.close()
