@@ -574,6 +574,8 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--variant", default="kwinners", choices=["kwinners", "iterative"], help="c1 / c4: which reference class")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0, help="c1 / c4: CPU time of the one-thread baseline sample")
+    ap.add_argument("--e2e-groups", type=int, default=2,
+                    help="c3: agent groups the end-to-end loop steps in turn (host I/O of one overlaps the GPU step of the other)")
     ap.add_argument("--single-process", action="store_true",
                     help="c3 over --gpus N devices from ONE process (bidi_create_sharded) instead of one torchrun rank per GPU")
     ap.add_argument("--c5-size", type=int, default=1024)
@@ -667,52 +669,75 @@ def main():
     ms = max_over_ranks(ms)
     value = whole_job_rate(A, world, K, ms * 1e-3)
 
-    # ---- e2e: host buffers through the C ABI, host<->device copies inside the timed region
+    # ---- e2e: host buffers through the C ABI, host<->device copies inside the timed region.
+    # The population is driven as G agent groups of one sharded handle on this device (bidi_create_sharded with the
+    # device listed G times: agents never interact, RunnerMain.cpp:100-106), stepped in turn: while the GPU runs one
+    # group's step the host reads the other group's results, runs its environment and uploads its next inputs.  Every
+    # step of every agent still has its host->device copy of the inputs and its device->host read of the predictions.
+    import ctypes
+    from bidinet_b200 import ShardedEngine
+    from bidinet_b200.build import build_runner_env
+    G = max(1, min(args.e2e_groups, A))
+    pipe = ShardedEngine(cfg, ld, A, devices=[local_rank] * G)
+    pipe.init_random(seed_base_for(rank, A))
+    for g, sh in enumerate(pipe.shards):
+        sh.set_noise_stream(0x5DEECE66D, rank * A + pipe.first[g])
+    pipe.load_frames(frames)
+    pipe.set_feedback(FB_IDX, FB_IDX, 0.5, 0.5, 0.05, True)
+    tp = 0
+    for _ in range(args.burn_in):     # the same regime as the device-resident measurement
+        pipe.step_frame(tp)
+        tp += 1
+    pipe.sync()
     rng = np.random.RandomState(rank)
-    # the engine's page-locked staging buffers, used in place (bidi_host_inputs / bidi_host_predictions): the
-    # host<->device copies are still made every step, the extra host-side staging memcpy is not
-    pred = eng.get_predictions(out=eng.host_predictions())
-    x = eng.host_inputs()
-    rewards = np.zeros(A, dtype=np.float32)
     # the synthetic environment's noise draws (RunnerMain.cpp:241-242) are data, made before the clock starts
     env_noise = rng.normal(0.0, 0.05, (W + K, A, len(FB_IDX))).astype(np.float32)
-    e2e_i = 0
     fb0, fb1 = int(FB_IDX[0]), int(FB_IDX[-1]) + 1     # the action inputs are one contiguous run of cells
     assert np.array_equal(FB_IDX, np.arange(fb0, fb1))
-    import ctypes
-    from bidinet_b200.build import build_runner_env
     env_lib = ctypes.CDLL(build_runner_env())  # tools/runner_env.c: the environment in compiled code, as in the reference
     fp = ctypes.POINTER(ctypes.c_float)
     env_lib.runner_env_step.argtypes = [ctypes.c_int] * 4 + [fp] * 4
     env_lib.runner_env_step.restype = None
-    pred_p, x_p, rew_p = (a.ctypes.data_as(fp) for a in (pred, x, rewards))
+    # the engines' page-locked staging buffers, used in place (bidi_host_inputs / bidi_host_predictions): the
+    # host<->device copies are still made every step, the extra host-side staging memcpy is not
+    grp = []
+    for g, sh in enumerate(pipe.shards):
+        lo, n = pipe.first[g], pipe.count[g]
+        pred = sh.get_predictions(out=sh.host_predictions())
+        x = sh.host_inputs()
+        np.copyto(x, frames[tp % T][lo:lo + n])
+        grp.append({"sh": sh, "lo": lo, "n": n, "pred": pred, "x": x, "rew": np.zeros(n, dtype=np.float32)})
 
-    np.copyto(x, frames[t % T])
+    def host_step(i, tt):
+        """the caller's side of RunnerMain.cpp:235-251, group by group: read the group's predictions (device -> host,
+        waits for its previous step), state inputs + fed-back noisy actions + reward, upload, enqueue the step."""
+        for q in grp:
+            sh, lo, n = q["sh"], q["lo"], q["n"]
+            sh.get_predictions(out=q["pred"])
+            nz = np.ascontiguousarray(env_noise[i][lo:lo + n])
+            env_lib.runner_env_step(n, n_in, fb0, fb1 - fb0, q["pred"].ctypes.data_as(fp), nz.ctypes.data_as(fp),
+                                    q["x"].ctypes.data_as(fp), q["rew"].ctypes.data_as(fp))
+            sh.set_inputs(q["x"])
+            sh.step(rewards=q["rew"])        # asynchronous: returns once the step is enqueued
+            sh.wait_inputs()                 # the host->device copy has read x
+            np.copyto(q["x"], frames[(tt + 1) % T][lo:lo + n])
 
-    def host_step(tt):
-        """the caller's side of RunnerMain.cpp:235-251: state inputs, fed-back noisy actions, reward.
-        The open-loop part of the NEXT frame is laid out while the GPU works on this step."""
-        nonlocal e2e_i
-        env_lib.runner_env_step(A, n_in, fb0, fb1 - fb0, pred_p, env_noise[e2e_i].ctypes.data_as(fp), x_p, rew_p)
-        e2e_i += 1
-        eng.set_inputs(x)
-        eng.step(rewards=rewards)        # asynchronous: returns once the step is enqueued
-        eng.wait_inputs()                # the host->device copy has read x
-        np.copyto(x, frames[(tt + 1) % T])
-        eng.get_predictions(out=pred)    # device -> host, synchronises
-
-    for _ in range(W):
-        host_step(t)
-        t += 1
+    for i in range(W):
+        host_step(i, tp)
+        tp += 1
+    pipe.sync()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(K):
-        host_step(t)
-        t += 1
-    eng.sync()
+    for i in range(K):
+        host_step(W + i, tp)
+        tp += 1
+    for q in grp:                            # the last step's results, read like every other step's
+        q["sh"].get_predictions(out=q["pred"])
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = whole_job_rate(A, world, K, e2e_s)
+    e2e_launches = pipe.launch_count if hasattr(pipe, "launch_count") else None
+    pipe.close()
     if rank == 0:
         clk = clocks.stop()
 
@@ -773,7 +798,10 @@ def main():
                    "exploration_noise": "engine counter-based generator", "state_bytes_per_gpu": eng.device_bytes,
                    "burn_in_steps": args.burn_in},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "ms_per_step": 1e3 * e2e_s / K,
-                "h2d_bytes_per_step": int(A * n_in * 4 + A * 4), "d2h_bytes_per_step": int(A * n_in * 4)},
+                "h2d_bytes_per_step": int(A * n_in * 4 + A * 4), "d2h_bytes_per_step": int(A * n_in * 4),
+                "agent_groups": G,
+                "note": "every step copies every agent's inputs host->device and its predictions device->host; the agents are "
+                        "stepped as %d groups in turn so that one group's host work overlaps the other's GPU step" % G},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
