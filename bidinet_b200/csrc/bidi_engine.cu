@@ -144,7 +144,8 @@ struct bidi_engine {
   std::vector<int> tiled;          // per node layer: few threads, use the cooperative tile kernels (bidi_tiles.cuh)
   bool force_phase_kernels = false, no_dense_coder = false;
   // per layer: the 2-D tile kernels of bidi_grid.cuh apply (large k-winners layers); shared-memory floats they stage
-  struct GridSizes { int on, ff, rec, lat, fb, pred, gather; int act_slab, act_box, act_cap, act_dense; };  // act_*: k_g_kw_activate (row segments)
+  struct GridSizes { int on, ff, rec, lat, fb, pred, gather; int act_slab, act_box, act_cap, act_dense; int tm_bw, tm_bh; };  // act_*: k_g_kw_activate (row segments); tm_*: its input box through a TMA tensor map
+  CUtensorMap act_tmap;            // layer 0's input array [agent][y][x] for k_g_kw_activate's tiled loads
   std::vector<GridSizes> gridk;
   std::vector<bidi::PersistShape> persist;  // per layer: the whole iterative coder as one cooperative launch (bidi_persist.cuh)
   unsigned* d_persist_ctr = nullptr;        // its grid barrier's arrival counters, one per layer
@@ -213,6 +214,7 @@ struct bidi_engine {
   // whole step as one cooperative launch (bidi_coop.cuh): the program per value of `learn`
   int coop_mode = 0;                               // option "coop_step": 1 = use it when every layer runs the tile kernels (measured no faster than the graph: off by default)
   bidi::CoopOp* d_coop_ops[2] = {nullptr, nullptr}; int coop_n[2] = {0, 0}; int coop_grid = 0; size_t coop_smem = 0;
+  bool use_tma_box = true;                         // option "tma_box": k_g_kw_activate's input box through a TMA tensor map
   int dbg_act = 0;                                 // timing experiments on k_g_kw_activate (results are then wrong): 2 skip the dense sum, 4 skip the recurrent sum
   int col_extra_smem = 0;                          // experiment: pad the column kernel's shared memory to lower its residency
   bool strip_use_graph = true;                     // record the split step (NCCL exchanges included) into a CUDA graph
@@ -648,6 +650,28 @@ void launch_grid(Recorder& R, const char* name, K kernel, long long blocks, size
   R.after(name);
   R.kernels++;
 }
+// Tensor map of the layer-0 input array [agent][in_height][in_width] with box (bw x bh x 1), zero fill outside.  The
+// encoder is a driver entry point fetched at run time (no link-time libcuda dependency).  false: not available.
+bool encode_input_tmap(bidi_engine* h, int bw, int bh) {
+  typedef CUresult (*Encode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      return false;
+    }
+    encode = reinterpret_cast<Encode>(fn);
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)h->cfg.in_width, (cuuint64_t)h->cfg.in_height, (cuuint64_t)h->A};
+  const cuuint64_t strides[2] = {(cuuint64_t)h->cfg.in_width * 4, (cuuint64_t)h->n_in * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode(&h->act_tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, h->d_in0, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 inline size_t act_smem_bytes(const bidi_engine::GridSizes& G) { return sizeof(float) * (size_t)(G.act_slab + G.act_box + 2 * G.act_cap) + 16; }
 // k_g_kw_activate over the hidden rows [Y.row0, Y.row1): one warp per 32-unit row segment
 void launch_kw_activate(bidi_engine* h, cudaStream_t st, const bidi_engine::GridSizes& G, const LayerDev& Y, int l) {
@@ -655,7 +679,7 @@ void launch_kw_activate(bidi_engine* h, cudaStream_t st, const bidi_engine::Grid
   if (blocks <= 0) return;
   const size_t smem = act_smem_bytes(G);
   const int dyn = (G.act_dense && Y.ff.dxn == Y.ff.dyn && !Y.ff.absx && !Y.ff.absy) ? Y.ff.dyn : 0;
-#define BIDI_ACT(D) bidi::k_g_kw_activate<D><<<(unsigned)blocks, 32, smem, st>>>(h->P, Y, l, G.act_dense | (G.act_dense ? h->dbg_act : 0), G.act_slab, G.act_box, G.act_cap)
+#define BIDI_ACT(D) bidi::k_g_kw_activate<D><<<(unsigned)blocks, 32, smem, st>>>(h->P, Y, l, G.act_dense | (G.act_dense ? h->dbg_act : 0), G.act_slab, G.act_box, G.act_cap, h->act_tmap, G.tm_bw, G.tm_bh)
   switch (dyn) {
     case 5: BIDI_ACT(5); break;
     case 7: BIDI_ACT(7); break;
@@ -769,7 +793,8 @@ int launch_persist(bidi_engine* h, cudaStream_t st, int l) {
 }
 // which layers run the 2-D tile kernels, and how much shared memory they stage
 int select_grid_kernels(bidi_engine* h) {
-  h->gridk.assign(h->L, bidi_engine::GridSizes{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
+  h->gridk.assign(h->L, bidi_engine::GridSizes{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0});
+  memset(&h->act_tmap, 0, sizeof(h->act_tmap));
   if (h->cfg.variant == BIDI_NEO_AGENT || h->grid_mode == 0) return BIDI_OK;
   size_t most = 0;
   for (int l = 0; l < h->L; l++) {
@@ -790,6 +815,18 @@ int select_grid_kernels(bidi_engine* h) {
       const int fbox = bidi::grid_rowbox_floats(H.ff.d, H.ff.cx.data()), rbox = bidi::grid_rowbox_floats(H.rec.d, H.rec.cx.data());
       g.act_slab = g.act_dense ? 32 * kw_pitch(H.ff.d.nslots) : 0;
       g.act_box = g.act_dense ? (fbox + 3) / 4 * 4 : 0;
+      g.tm_bw = g.tm_bh = 0;
+      if (g.act_dense && h->use_tma_box) {
+        // the input box as ONE tiled TMA load: rows padded to 16 bytes, at most 256 cells a side; the input array's
+        // rows must be 16-byte multiples
+        int bw, bh;
+        bidi::grid_rowbox_dims(H.ff.d, H.ff.cx.data(), bw, bh);
+        const int bwp = (bw + 3 + 3) / 4 * 4;  // the box starts on a multiple of four cells: up to three cells of slack on the left
+        if (bwp <= 256 && bh <= 256 && h->cfg.in_width % 4 == 0 && encode_input_tmap(h, bwp, bh)) {
+          g.tm_bw = bwp; g.tm_bh = bh;
+          g.act_box = (bwp * bh + 31) / 32 * 32;  // keeps the weight slab behind it 128-byte aligned
+        }
+      }
       g.act_cap = std::max(g.act_dense ? 0 : fbox, rbox) + 2;
       need = std::max({sizeof(float) * (size_t)g.lat, sizeof(float) * 3 * (size_t)g.gather, sizeof(float) * 4 * (size_t)(g.fb + g.pred)});
       if (sizeof(float) * (size_t)(g.act_slab + g.act_box + 2 * g.act_cap) + 16 > 200 * 1024) need = 1 << 30;  // (no such layer in practice)
@@ -2422,6 +2459,11 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     CU(cudaFuncSetAttribute(bidi::k_columns16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
   }
   else if (std::string(name) == "dbg_act") h->dbg_act = value;
+  else if (std::string(name) == "tma_box") {
+    h->use_tma_box = value != 0;
+    int rc = select_grid_kernels(h);
+    if (rc) return rc;
+  }
   else if (std::string(name) == "persist_coder") {  // 0: the per-phase kernels for the large layers of a single iterative agent
     h->persist_mode = value != 0;
     int rc = select_persist(h);

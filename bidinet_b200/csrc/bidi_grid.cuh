@@ -16,6 +16,7 @@
 // Launch geometry: blockIdx.x = (agent * tiles_y + tile_y) * tiles_x + tile_x over the
 // rows [row0,row1) the launch works on (a row strip, or the whole grid).
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched from the driver at run time)
 #include "bidi_kernels.cuh"
 #include "bidi_columns.cuh"  // mbarrier / bulk-copy helpers
 
@@ -126,12 +127,17 @@ inline int grid_box_floats(const WinDev& w, const int* cx, const int* cy) {
   return bw * bh;
 }
 
-// host: largest window box of a 32x1 row segment, in floats
-inline int grid_rowbox_floats(const WinDev& w, const int* cx) {
-  if (w.r < 0) return 0;
-  int bw = w.tw;
+// host: largest window box of a 32x1 row segment (width, height; floats)
+inline void grid_rowbox_dims(const WinDev& w, const int* cx, int& bw, int& bh) {
+  bw = bh = 0;
+  if (w.r < 0) return;
+  bw = w.tw;
   if (!w.absx) { bw = 0; for (int u = 0; u < w.uw; u += GRID_TX) bw = max(bw, cx[min(u + GRID_TX, w.uw) - 1] - cx[u] + 2 * w.r + 1); }
-  const int bh = w.absy ? w.th : 2 * w.r + 1;
+  bh = w.absy ? w.th : 2 * w.r + 1;
+}
+inline int grid_rowbox_floats(const WinDev& w, const int* cx) {
+  int bw, bh;
+  grid_rowbox_dims(w, cx, bw, bh);
   return bw * bh;
 }
 
@@ -300,9 +306,19 @@ __device__ __forceinline__ float list_finish(const WinDev& w, const ListHits<NP>
 // Every global load the segment needs -- the weight rows, the input box, the box of previous states -- is issued
 // before the first one is consumed, and the recurrent weights of the first hits are fetched under the dense sum.
 // smem: [32*pitch slab | ff box] (dense) , list entries, mbarrier
+// One 3-D tiled TMA load (cp.async.bulk.tensor, SASS UTMALDG): box (bw x bh x 1) of the [agent][y][x] input array at
+// (x0, y0, a) into shared memory, rows bw floats apart; cells outside the grid arrive as zeros (no index tests, no
+// per-cell loads: the halo is the TMA unit's out-of-bounds fill).
+__device__ __forceinline__ void tma_load_box(void* dst_smem, const void* tmap, int x0, int y0, int a, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst_smem)),
+               "l"(tmap), "r"(x0), "r"(y0), "r"(a), "r"(smem_u32(bar))
+               : "memory");
+}
+// tmap_bw > 0: the input box is brought in by the TMA unit through `tmap` (rows tmap_bw floats apart, tmap_bw x tmap_bh cells)
 template <int DYN>
-__global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, int l, int dense_ff, int slab_floats, int box_floats, int cap) {
-  extern __shared__ __align__(16) float sm[];
+__global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, int l, int dense_ff, int slab_floats, int box_floats, int cap,
+                                                      const __grid_constant__ CUtensorMap tmap, int tmap_bw, int tmap_bh) {
+  extern __shared__ __align__(128) float sm[];
   constexpr int NB = 20;  // box cells per lane per trip: a 44x13 box (radius 6, 32 units) is one trip
   const int lane = threadIdx.x;
   const int nseg = (L.hw + 31) >> 5, rows = L.row1 - L.row0;
@@ -314,9 +330,9 @@ __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, i
   T.ok = T.ux < L.hw; T.unit = T.ux + uy * L.hw;
   float* B = blob_of(P, a);
   const float* x = vis_input_of(P, L, l, a);
-  float* slab = sm;
-  float* xbox = sm + slab_floats;
-  int2* ent = reinterpret_cast<int2*>(xbox + box_floats);
+  float* xbox = sm;                 // (first: the tensor load wants 128-byte alignment)
+  float* slab = sm + box_floats;
+  int2* ent = reinterpret_cast<int2*>(slab + slab_floats);
   uint64_t* bar = reinterpret_cast<uint64_t*>(ent + cap);
   const int nun = min(32, L.hw - T.ux0);
   const WinDev& wf = L.ff;
@@ -324,14 +340,20 @@ __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, i
   if (dense_ff) {
     if (lane == 0) mbar_init(bar, 1);
     __syncwarp();
+  }
+  Box bf = window_box(wf, T);
+  if (dense_ff) {
     if (lane == 0) {
       const uint32_t bytes = (uint32_t)(nun * wf.row_pitch) * 4u;
-      mbar_expect_tx(bar, bytes);
+      mbar_expect_tx(bar, bytes + (tmap_bw > 0 ? (uint32_t)(tmap_bw * tmap_bh) * 4u : 0u));
       tma_load_1d(slab, B + wf.w_off + (long long)(T.ux0 + uy * L.hw) * wf.row_pitch, bytes, bar);
+      if (tmap_bw > 0) tma_load_box(xbox, &tmap, bf.x0 & ~3, bf.y0, a, bar);
     }
+    // (the innermost coordinate of a tiled load must be a multiple of 16 bytes -- anything else faults with "illegal
+    // instruction" on this GPU: the box starts at the multiple of four cells at or below x0 and is up to three wider)
+    if (tmap_bw > 0) { bf.x0 &= ~3; bf.w = tmap_bw; }  // the staged rows are tmap_bw apart
   }
   float sum = T.ok ? -B[L.thr + T.unit] : 0.0f;
-  const Box bf = window_box(wf, T);
   const Box br = wr.r >= 0 ? window_box(wr, T) : Box{0, 0, 0, 0};
   const float* sprev = B + L.state_prev;
   // non-zero cells of a box, x-major, from a plane: all loads of a trip first, then the ballots
@@ -364,7 +386,7 @@ __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, i
   if (dense_ff) {
     // the window box of the segment (coalesced rows, zero outside the grid) and the box of previous states: the loads
     // of both are in flight together with the bulk copy of the rows
-    const int n = bf.w * bf.h;
+    const int n = tmap_bw > 0 ? 0 : bf.w * bf.h;  // (nothing to stage by hand when the TMA unit brings the box)
     const float inv_w = 1.0f / (float)bf.w;
     float xv[NB];
 #pragma unroll
