@@ -287,8 +287,24 @@ void strip_exchange_push(bidi_engine* h, int point) {
 }
 
 int strip_record_nccl(bidi_engine* h, bool learn) {
+  // inside a stream capture the reconstructions (phase 2, first needed by exchange X3) become a second branch of the
+  // graph, beside the prediction phase
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(h->stream, &cap);
+  const bool fork = cap == cudaStreamCaptureStatusActive && h->side != nullptr && h->overlap_learn;
   for (int phase = 0; phase < kStripPhases; phase++) {
+    if (fork && phase == 2) {
+      CU(cudaEventRecord(h->ev_fork, h->stream));
+      CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      cudaStream_t main_stream = h->stream;
+      h->stream = h->side;
+      strip_phase(h, 2, learn);
+      h->stream = main_stream;
+      CU(cudaEventRecord(h->ev_join, h->side));
+      continue;
+    }
     strip_phase(h, phase, learn);
+    if (fork && phase == 3) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     if (phase < kStripPhases - 1 && strip_point_used(phase, learn)) {
       if (h->ipc_linked) strip_exchange_push(h, phase);
       else {
