@@ -23,7 +23,6 @@
 #include "bidi_tiles.cuh"
 #include "bidi_grid.cuh"
 #include "bidi_persist.cuh"
-#include "bidi_coop.cuh"
 #include "bidi_qnet.cuh"
 #include "bidi_env.cuh"
 #include "bidi_csrl.cuh"
@@ -141,7 +140,7 @@ struct bidi_engine {
   std::vector<LayerHost> hl;
   long long stride = 0;            // floats per agent blob
   std::vector<int> coder_cta;      // per layer: the fused one-CTA-per-agent coder kernel applies
-  std::vector<int> tiled;          // per node layer: few threads, use the cooperative tile kernels (bidi_tiles.cuh)
+  std::vector<int> tiled;          // per node layer: few threads, use the tile kernels (bidi_tiles.cuh)
   bool force_phase_kernels = false, no_dense_coder = false;
   // per layer: the 2-D tile kernels of bidi_grid.cuh apply (large k-winners layers); shared-memory floats they stage
   struct GridSizes { int on, ff, rec, lat, fb, pred, gather; int act_slab, act_box, act_cap, act_dense; int tm_bw, tm_bh; };  // act_*: k_g_kw_activate (row segments); tm_*: its input box through a TMA tensor map
@@ -211,9 +210,6 @@ struct bidi_engine {
   std::vector<std::vector<char>> q_keep;            // per layer: [slot][unit] the reference keeps the connection
   std::vector<int> q_act_index, q_a_input;
   float* d_qmask = nullptr; int* d_qtables = nullptr;
-  // whole step as one cooperative launch (bidi_coop.cuh): the program per value of `learn`
-  int coop_mode = 0;                               // option "coop_step": 1 = use it when every layer runs the tile kernels (measured no faster than the graph: off by default)
-  bidi::CoopOp* d_coop_ops[2] = {nullptr, nullptr}; int coop_n[2] = {0, 0}; int coop_grid = 0; size_t coop_smem = 0;
   bool use_tma_box = true;                         // option "tma_box": k_g_kw_activate's input box through a TMA tensor map
   int dbg_act = 0;                                 // timing experiments on k_g_kw_activate (results are then wrong): 2 skip the dense sum, 4 skip the recurrent sum
   int col_extra_smem = 0;                          // experiment: pad the column kernel's shared memory to lower its residency
@@ -533,44 +529,7 @@ struct Recorder {
   int kernels = 0;
   cudaStream_t st = nullptr;  // where launches go: the engine's stream, or the side branch while it is open
   cudaStream_t s() const { return st ? st : h->stream; }
-  // collect mode: the launches become the program of the cooperative step kernel instead
-  std::vector<bidi::CoopOp>* collect = nullptr;
-  bool collect_ok = true;
   bool capturing = false;  // inside a stream capture: the step may fork into a second branch
-  size_t collect_smem = 0;
-  int collect_blocks = 0;
-  struct Pack {
-    bidi::CoopOp op;
-    void put(int v) { if (op.ni < 5) iv[op.ni++] = v; }
-    void put(float v) { if (op.nf < 2) op.f[op.nf++] = v; }
-    void put(long long v) { if (op.na < 3) op.a[op.na++] = v; }
-    void put(const LayerDev&) { has_layer = true; }
-    int iv[5] = {0, 0, 0, 0, 0};
-    bool has_layer = false;
-  };
-  template <class... Args> void add_op(const void* kernel, long long blocks, size_t smem, Args... args) {
-    static const std::pair<const void*, int> table[] = {
-        {(const void*)bidi::k_t_kw_activate, bidi::OP_KW_ACTIVATE}, {(const void*)bidi::k_t_kw_inhibit, bidi::OP_KW_INHIBIT},
-        {(const void*)bidi::k_t_reconstruct, bidi::OP_RECONSTRUCT}, {(const void*)bidi::k_t_kw_learn, bidi::OP_KW_LEARN},
-        {(const void*)bidi::k_t_ic_sweep, bidi::OP_IC_SWEEP},       {(const void*)bidi::k_t_ic_learn, bidi::OP_IC_LEARN},
-        {(const void*)bidi::k_t_predict, bidi::OP_PREDICT},         {(const void*)bidi::k_ic_finish, bidi::OP_IC_FINISH},
-        {(const void*)bidi::k_step_end, bidi::OP_STEP_END}};
-    int code = 0;
-    for (const auto& e : table) if (e.first == kernel) code = e.second;
-    if (!code) { collect_ok = false; return; }
-    Pack p;
-    memset(&p.op, 0, sizeof(p.op));
-    (p.put(args), ...);
-    p.op.code = code; p.op.blocks = (int)blocks;
-    // the first int after a layer descriptor is the layer index; the other ints follow
-    const int skip = p.has_layer ? 1 : 0;
-    p.op.l = p.has_layer ? p.iv[0] : 0;
-    for (int k = skip; k < p.op.ni; k++) p.op.i[k - skip] = p.iv[k];
-    p.op.ni -= skip;
-    collect->push_back(p.op);
-    collect_smem = std::max(collect_smem, smem);
-    collect_blocks = std::max(collect_blocks, (int)blocks);
-  }
   // bracket a launch with external event records when its kernel is the one being profiled
   bool profiled(const char* name) const { return !h->profile_name.empty() && h->profile_name == name; }
   void before(const char* name) {
@@ -584,7 +543,6 @@ struct Recorder {
     if (profiled(name)) cudaEventRecordWithFlags(h->profile_events.back().second, s(), cudaEventRecordExternal);
   }
   template <class K, class... Args> void launch(const char* name, K kernel, long long threads, Args... args) {
-    if (collect) { add_op((const void*)kernel, grid_for(threads, TILE_U * TILE_G), 0, args...); return; }
     before(name);
     const int block = kBlock;
     kernel<<<grid_for(threads, block), block, 0, s()>>>(h->P, args...);
@@ -606,7 +564,6 @@ int columns_pairs_per_warp(const ColumnsDev& C) {
 }
 template <class K, class... Args>
 void launch_tile(Recorder& R, const char* name, K kernel, long long tiles, size_t smem, Args... args) {
-  if (R.collect) { R.add_op((const void*)kernel, tiles, smem, args...); return; }
   R.before(name);
   kernel<<<(unsigned)tiles, TILE_U * TILE_G, smem, R.s()>>>(R.h->P, args...);
   R.after(name);
@@ -644,7 +601,6 @@ void record_columns(Recorder& R, int l) {
 template <class K, class... Args>
 void launch_grid(Recorder& R, const char* name, K kernel, long long blocks, size_t smem_floats, Args... args) {
   if (blocks <= 0) return;
-  if (R.collect) { R.collect_ok = false; return; }
   R.before(name);
   kernel<<<(unsigned)blocks, GRID_TX * GRID_TY, sizeof(float) * smem_floats, R.s()>>>(R.h->P, args...);
   R.after(name);
@@ -867,13 +823,13 @@ void record_step(Recorder& R, bool learn) {
   if (V == BIDI_KWINNERS) {
     // The reconstructions of a layer (sdr/RSDR.cpp:165-194) are read by nothing before the learning rule: where the
     // step is captured into a graph they form a second branch, beside the rest of the up pass and the down pass.
-    const bool fork_recon = R.capturing && !R.collect && h->side != nullptr && h->overlap_learn && h->profile_name.empty();
+    const bool fork_recon = R.capturing && h->side != nullptr && h->overlap_learn && h->profile_name.empty();
     bool forked = false;
     // sdr/PredictiveRSDR.cpp:102-112
     for (int l = 0; l < L; l++) {
       const LayerDev& Y = ly[l];
       const long long nxt = l < L - 1 ? ly[l + 1].vis_input : -1LL;
-      if (h->gridk[l].on && !R.collect) {
+      if (h->gridk[l].on) {
         const auto& G = h->gridk[l];
         const long long th = A * bidi::grid_tiles(Y.hw, Y.hh), tv = A * bidi::grid_tiles(Y.vw, Y.vh);
         R.before("kw_activate");
@@ -904,7 +860,7 @@ void record_step(Recorder& R, bool learn) {
     for (int l = L - 1; l >= 0; l--) {
       const LayerDev& Y = ly[l];
       const LayerDev& Up = ly[l < L - 1 ? l + 1 : l];
-      if (h->gridk[l].on && !R.collect) {
+      if (h->gridk[l].on) {
         const auto& G = h->gridk[l];
         const long long th = A * bidi::grid_tiles(Y.hw, Y.hh);
         launch_grid(R, "predict", bidi::k_g_kw_predict, th, 4 * (G.fb + G.pred), Y, l, (int)learn, Up.p_state, Up.p_state_prev, G.pred, G.fb);
@@ -925,7 +881,7 @@ void record_step(Recorder& R, bool learn) {
     // :173-185
     if (learn)
       for (int l = 0; l < L; l++) {
-        if (h->gridk[l].on && !R.collect) launch_grid(R, "kw_learn", bidi::k_g_kw_learn, A * bidi::grid_tiles(ly[l].hw, ly[l].hh), 0, ly[l], l);
+        if (h->gridk[l].on) launch_grid(R, "kw_learn", bidi::k_g_kw_learn, A * bidi::grid_tiles(ly[l].hw, ly[l].hh), 0, ly[l], l);
         else if (h->tiled[l]) launch_tile(R, "kw_learn", bidi::k_t_kw_learn, tiles_of(A, ly[l].nh), 0, ly[l], l);
         else R.launch("kw_learn", bidi::k_kw_learn, A * ly[l].nh, ly[l], l);
       }
@@ -943,7 +899,7 @@ void record_step(Recorder& R, bool learn) {
       return;
     }
     R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
-    if (h->gridk[0].on && !R.collect) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather, 0, 0.0f, 0);
+    if (h->gridk[0].on) launch_grid(R, "kw_predict_input", bidi::k_g_reconstruct, A * bidi::grid_tiles(ly[0].vw, ly[0].vh), 3 * h->gridk[0].gather, ly[0], 0, ly[0].p_state, 0, 1, h->gridk[0].gather, 0, 0.0f, 0);
     else if (h->tiled[0])
       launch_tile(R, "kw_predict_input", bidi::k_t_reconstruct, tiles_of(A, ly[0].nv), tile_bytes(ly[0].ff.max_cand), ly[0], 0, ly[0].p_state, 0,
                   0.0f, 0, 1);
@@ -965,12 +921,11 @@ void record_step(Recorder& R, bool learn) {
   };
   bool any_separate_learn = false;
   for (int l = 0; l < L; l++) any_separate_learn = any_separate_learn || !learns_in_coder(l);
-  const bool fork_learn = learn && any_separate_learn && h->overlap_learn && !R.collect && h->side != nullptr && R.capturing && !h->csrl;
-  if (h->csrl && R.collect) { R.collect_ok = false; return; }
+  const bool fork_learn = learn && any_separate_learn && h->overlap_learn && h->side != nullptr && R.capturing && !h->csrl;
   const int plearn = h->csrl ? 0 : (int)learn;  // deep::CSRL's prediction weights learn through traces after the SDRRL pass
   for (int l = 0; l < L; l++) {
     const long long nh = A * ly[l].nh, nvh = A * (ly[l].nv + ly[l].nh);
-    if (h->coder_cta[l] && !h->force_phase_kernels && !R.collect && (h->coder_cta[l] != 2 || h->dense_rows[l])) { // whole up pass of the layer in one launch
+    if (h->coder_cta[l] && !h->force_phase_kernels && (h->coder_cta[l] != 2 || h->dense_rows[l])) { // whole up pass of the layer in one launch
       const long long nxt = l < L - 1 ? ly[l + 1].vis_input : -1LL;
       R.before("coder");
       if (h->coder_cta[l] == 2) {  // windows span the grid: dense rows (bidi_coder_dense.cuh)
@@ -996,7 +951,7 @@ void record_step(Recorder& R, bool learn) {
       continue;
     }
     const LayerDev& Y = ly[l];
-    if (V == BIDI_ITERATIVE && h->persist[l].on && !h->force_phase_kernels && !R.collect && h->coop_mode == 0) {  // bidi_persist.cuh
+    if (V == BIDI_ITERATIVE && h->persist[l].on && !h->force_phase_kernels) {  // bidi_persist.cuh
       R.before("coder");
       launch_persist(h, R.s(), l);
       R.after("coder");
@@ -1008,7 +963,7 @@ void record_step(Recorder& R, bool learn) {
     const size_t sm_sweep = tile_bytes(nslots_of(Y.ff) + nslots_of(Y.rec) + nslots_of(Y.lat));
     const size_t sm_rec = tile_bytes(std::max(Y.ff.max_cand, Y.rec.max_cand));
     const long long t_sweep = tiles_of(A, Y.nh), t_rec = tiles_of(A, Y.nv) + tiles_of(A, Y.nh);
-    const bool gk = h->gridk[l].on && !R.collect;  // large layer: 2-D tiles with the source boxes in shared memory
+    const bool gk = h->gridk[l].on;  // large layer: 2-D tiles with the source boxes in shared memory
     const auto& G = h->gridk[l];
     const long long g_th = A * bidi::grid_tiles(Y.hw, Y.hh), g_tv = A * bidi::grid_tiles(Y.vw, Y.vh);
     int sweep_it = 0;
@@ -1085,8 +1040,7 @@ void record_step(Recorder& R, bool learn) {
   else if (learn) record_learn();
   R.launch("step_end", bidi::k_step_end, A * h->max_units, h->max_units);
   if (h->qnet) {  // sdr/QPRSDR.cpp:102-341, after _prsdr.simStep
-    if (R.collect) { R.collect_ok = false; return; }
-    R.before("qnet");
+      R.before("qnet");
     bidi::k_qnet<<<(unsigned)A, 256, 0, h->stream>>>(h->P, (int)learn);
     R.after("qnet");
     R.kernels++;
@@ -1094,11 +1048,11 @@ void record_step(Recorder& R, bool learn) {
 }
 
 // ---- layout of the layers the dense fused coder runs (bidi_coder_dense.cuh): rows while that kernel is the layer's
-// path, slot planes while any other kernel family is (the per-phase kernels, the general fused kernel, the cooperative
-// step -- all of which the tests select through bidi_set_option).  Switching converts every agent's region in place.
+// path, slot planes while any other kernel family is (the per-phase kernels, the general fused kernel -- which the
+// tests select through bidi_set_option).  Switching converts every agent's region in place.
 bool dense_wanted(const bidi_engine* h, int l) {
   // (a deep::CSRL's coder learns from rewards its SDRRL units produce in the down pass: not in the coder kernel's tail)
-  return h->coder_cta[l] == 2 && !h->force_phase_kernels && h->coop_mode == 0 && !h->csrl;
+  return h->coder_cta[l] == 2 && !h->force_phase_kernels && !h->csrl;
 }
 
 void convert_region(float* R, const LayerHost& H, int nh, bool to_rows) {
@@ -1206,57 +1160,11 @@ int strip_step_nccl(bidi_engine* h, bool learn);
 
 struct Recorder;
 void record_step(Recorder& R, bool learn);
-// every layer on the tile kernels, no columns, not a strip of a split layer
-bool coop_eligible(const bidi_engine* h) {
-  if (h->coop_mode == 0 || h->cfg.variant == BIDI_NEO_AGENT || h->strip_n > 1 || !h->profile_name.empty()) return false;
-  const int n = h->cfg.variant == BIDI_KWINNERS ? h->L : h->L + 1;
-  for (int l = 0; l < n; l++) if (!h->tiled[l]) return false;
-  return true;
-}
-void coop_release(bidi_engine* h) {
-  for (int k = 0; k < 2; k++) { cudaFree(h->d_coop_ops[k]); h->d_coop_ops[k] = nullptr; h->coop_n[k] = 0; }
-}
-// 1: the program for `learn` is ready; 0: this engine cannot run the step cooperatively
-int ensure_coop(bidi_engine* h, bool learn) {
-  if (h->d_coop_ops[learn]) return 1;
-  int coop = 0;
-  if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device) != cudaSuccess || !coop) { h->coop_mode = 0; return 0; }
-  std::vector<bidi::CoopOp> ops;
-  Recorder R{h};
-  R.collect = &ops;
-  record_step(R, learn);
-  if (!R.collect_ok || ops.empty()) { h->coop_mode = 0; return 0; }
-  const size_t smem = std::max(h->coop_smem, R.collect_smem);
-  if (smem > 48 * 1024 && cudaFuncSetAttribute(bidi::k_step_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    cudaGetLastError(); h->coop_mode = 0; return 0;
-  }
-  int per_sm = 0, sms = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bidi::k_step_coop, TILE_U * TILE_G, smem);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-  if (per_sm < 1 || sms < 1) { h->coop_mode = 0; return 0; }
-  h->coop_smem = smem;
-  h->coop_grid = std::max(1, std::min(per_sm * sms, std::max(R.collect_blocks, h->coop_grid)));
-  if (cudaMalloc(&h->d_coop_ops[learn], sizeof(bidi::CoopOp) * ops.size()) != cudaSuccess) { cudaGetLastError(); h->coop_mode = 0; return 0; }
-  if (cudaMemcpyAsync(h->d_coop_ops[learn], ops.data(), sizeof(bidi::CoopOp) * ops.size(), cudaMemcpyHostToDevice, h->stream) != cudaSuccess ||
-      cudaStreamSynchronize(h->stream) != cudaSuccess) { cudaGetLastError(); coop_release(h); h->coop_mode = 0; return 0; }
-  h->coop_n[learn] = (int)ops.size();
-  return 1;
-}
-
 int run_step(bidi_engine* h, bool learn, bool device_noise) {
   int rc = mirror_release(h);
   if (rc) return rc;
   h->state_touched = true;
   if (h->strip_n > 1) return strip_step_nccl(h, learn);
-  if (coop_eligible(h) && ensure_coop(h, learn)) {
-    const bidi::CoopOp* ops = h->d_coop_ops[learn];
-    int n = h->coop_n[learn];
-    void* args[] = {&h->P, &ops, &n};
-    CU(cudaLaunchCooperativeKernel((const void*)bidi::k_step_coop, dim3(h->coop_grid), dim3(TILE_U * TILE_G), args, h->coop_smem, h->stream));
-    h->launches += 1;
-    h->step_index++;
-    return BIDI_OK;
-  }
   if (h->qnet && device_noise) {
     bidi::k_noise_q<<<grid_for((long long)h->A * h->q_half, kBlock), kBlock, 0, h->stream>>>(h->P, h->d_noise_u, h->d_noise_v, h->noise_seed, h->step_index, h->first_agent);
     h->launches++;
@@ -1311,7 +1219,6 @@ void bidi_destroy(bidi_engine* h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_in) cudaEventDestroy(h->ev_in);
   strip_release(h);
-  coop_release(h);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->side) cudaStreamDestroy(h->side);
@@ -1859,7 +1766,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     }
   }
   h->dense_rows.assign(L, 0);
-  // node layers with few (agent, unit) threads use the cooperative tile kernels
+  // node layers with few (agent, unit) threads use the tile kernels
   h->tiled.assign(L + 1, 0);
   {
     size_t sm = 0;
@@ -2469,7 +2376,6 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     int rc = select_persist(h);
     if (rc) return rc;
   }
-  else if (std::string(name) == "coop_step") h->coop_mode = value != 0;
   else if (std::string(name) == "overlap_learn") h->overlap_learn = value != 0;
   else if (std::string(name) == "dense_coder") {  // 0: use the general fused coder kernel where the dense one was chosen
     if (!value) {
@@ -2487,7 +2393,6 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
   }
   else return fail(h, BIDI_EINVAL, "bidi_set_option: unknown option");
   for (auto& g : h->graphs) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
-  coop_release(h);
   return apply_layout(h);  // the dense coder's layers are rows exactly while that kernel is their path
 }
 

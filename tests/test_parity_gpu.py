@@ -43,27 +43,23 @@ def test_init_random_matches_oracle(case):
         assert diff_states(orc.state(), eng.state(agent=a)) == [], "agent %d" % a
 
 
-@pytest.mark.parametrize("path", ["default", "coop", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
+@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
 @pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
 def test_free_running_parity(case, path):
     """N steps from an identical state, no re-synchronisation: exact after every step.
     Every engine path is held to it: the default (a CUDA graph; fused per-agent coder kernel where the
     layer fits in shared memory -- its dense-row form where the windows span the grid --
     and cooperative tile kernels for small launches), the general fused coder kernel
-    everywhere, the whole step as ONE cooperative launch that interprets the phase list, one
+    everywhere, one
     kernel per phase with the tile kernels (large single agents), one kernel per
     phase with one thread per unit (large agent batches), and the 2-D grid-tile kernels
     (very large k-winners layers)."""
     name, cfg, ld, frame, reward = case
     orc = OracleHierarchy(cfg, ld, 1234)
     eng = Engine(cfg, ld, n_agents=1)
-    if path == "coop":  # the whole step as one cooperative launch interpreting the phase list
-        if cfg.variant in (cf.NEO_AGENT, cf.CSRL):
-            pytest.skip("no columns / SDRRL units in the cooperative step")
-        eng.set_option("coop_step", True)
     if path == "fused_general":
         eng.set_option("dense_coder", False)
-    elif path not in ("default", "coop"):
+    elif path != "default":
         eng.set_option("force_phase_kernels", True)
     if path == "per_phase_threads":
         eng.set_option("tile_kernels", False)
@@ -87,24 +83,19 @@ def test_free_running_parity(case, path):
         assert np.array_equal(orc.get_predictions(), eng.get_predictions()[0])
 
 
-@pytest.mark.parametrize("path", ["default", "coop", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
+@pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
 @pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
 def test_batched_free_running_parity(case, path):
     """Three agents in one engine, every variant on every engine path: each agent against its OWN oracle (own
     weights, own inputs, own reward) after every step -- the agent decomposition of the tile kernels (tiles_of),
-    the 2-D grid tiles, the Q network's one-CTA-per-agent launch, the cooperative interpreter and the pitched copy
-    of bidi_get_actions.  The cooperative path must really have been taken: one launch per step."""
+    the 2-D grid tiles, the Q network's one-CTA-per-agent launch and the pitched copy of bidi_get_actions."""
     name, cfg, ld, frame, reward = case
     A, steps = 3, 10
     eng = Engine(cfg, ld, n_agents=A, seed=1234)
     orcs = [OracleHierarchy(cfg, ld, 1234 + a) for a in range(A)]
-    if path == "coop":
-        if cfg.variant in (cf.NEO_AGENT, cf.CSRL):
-            pytest.skip("no columns / SDRRL units in the cooperative step")
-        eng.set_option("coop_step", True)
     if path == "fused_general":
         eng.set_option("dense_coder", False)
-    elif path not in ("default", "coop"):
+    elif path != "default":
         eng.set_option("force_phase_kernels", True)
     if path == "per_phase_threads":
         eng.set_option("tile_kernels", False)
@@ -126,11 +117,8 @@ def test_batched_free_running_parity(case, path):
         for a, o in enumerate(orcs):
             o.set_inputs(x[a])
             o.step(float(r[a]), learn)
-        before = eng.launch_count
         eng.set_inputs(x)
         eng.step(rewards=r, noise=noise, learn=learn)
-        if path == "coop" and cfg.variant != cf.QPRSDR:
-            assert eng.launch_count - before == 1, "the cooperative step was not taken"
         pred = eng.get_predictions()
         for a, o in enumerate(orcs):
             assert np.array_equal(o.get_predictions(), pred[a]), (t, a)

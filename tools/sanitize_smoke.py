@@ -2,7 +2,7 @@
 """Small invocation of every kernel family for compute-sanitizer (memcheck / racecheck):
   compute-sanitizer --tool memcheck python tools/sanitize_smoke.py
 C2 neo::Agent (column kernels, dense coder), C1 k-winners / iterative (tile kernels, fused coder,
-cooperative step), a QPRSDR, a split layer (grid kernels + same-process halo copies); 2 steps each."""
+per-phase kernels), a QPRSDR, a split layer (grid kernels + same-process halo copies); 2 steps each."""
 import os
 import sys
 
@@ -30,7 +30,7 @@ run(*cf.config_c2())
 run(*cf.config_c1(cf.KWINNERS), agents=1)
 run(*cf.config_c1(cf.KWINNERS), agents=1, opts=(("grid_kernels", 2),))
 run(*cf.config_c1(cf.ITERATIVE), agents=1)
-run(*cf.config_c1(cf.ITERATIVE), agents=1, opts=(("coop_step", 1),))
+run(*cf.config_c1(cf.ITERATIVE), agents=1, opts=(("persist_coder", 0),))
 run(*cf.config_c1(cf.NEO_HIERARCHY), agents=1, opts=(("force_phase_kernels", 1), ("tile_kernels", 0)))
 run(*cf.config_q_small())
 cfg, ld = cf.make_config(cf.KWINNERS, 24, 24, [dict(width=24, height=24, r_ff=3, r_rec=3, r_lat=3, r_pred=3, sparsity=0.15)])
