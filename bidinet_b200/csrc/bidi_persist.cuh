@@ -44,8 +44,8 @@ __device__ __forceinline__ void persist_sync(unsigned* ctr, unsigned& target, un
   __syncthreads();
   if (threadIdx.x == 0) {
     target += nblocks;
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    // arrival = a release at GPU scope: with the block barrier above it orders every thread's stores before it
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
     unsigned v;
     do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
   }
@@ -57,12 +57,31 @@ template <int DYN>
 __device__ __forceinline__ float persist_dot(const WinDev& w, const float* __restrict__ s0, int bw, const float* __restrict__ wsm, int ut, float sum) {
   if (w.r < 0) return sum;
   if (DYN > 0) {
-    for (int sx = 0; sx < w.dxn; sx++) {
+    // one window column (DYN slots) per trip, software-pipelined: the 2 x DYN shared-memory loads of the next column are
+    // issued before the DYN chained adds of the current one (a chain thread has its scheduler nearly to itself, so
+    // nothing else hides the load latency); the additions keep the list order
+    constexpr int DN = DYN > 0 ? DYN : 1;
+    float sa[DN], wa[DN], sb[DN], wb[DN];
+    const int n = w.dxn;
+    auto ld = [&](float* s, float* ww, int sx) {
       const float* sp = s0 + sx;
       const float* wp = wsm + (size_t)sx * DYN * ut;
 #pragma unroll
-      for (int sy = 0; sy < DYN; sy++) sum += sp[sy * bw] * wp[sy * ut];
+      for (int sy = 0; sy < DYN; sy++) { s[sy] = sp[sy * bw]; ww[sy] = wp[sy * ut]; }
+    };
+    auto eat = [&](const float* s, const float* ww) {
+#pragma unroll
+      for (int sy = 0; sy < DYN; sy++) sum += s[sy] * ww[sy];
+    };
+    if (n > 0) ld(sa, wa, 0);
+    int sx = 0;
+    for (; sx + 2 <= n; sx += 2) {
+      ld(sb, wb, sx + 1);
+      eat(sa, wa);
+      if (sx + 2 < n) ld(sa, wa, sx + 2);
+      eat(sb, wb);
     }
+    if (sx < n) eat(sa, wa);
   } else {
     for (int sx = 0; sx < w.dxn; sx++)
       for (int sy = 0; sy < w.dyn; sy++) sum += s0[sx + sy * bw] * wsm[(size_t)(sx * w.dyn + sy) * ut];
