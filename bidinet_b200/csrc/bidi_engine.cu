@@ -13,6 +13,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <random>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <vector>
@@ -1911,7 +1912,8 @@ int bidi_get_array(bidi_engine* h, int agent, int which, int layer, float* dst, 
 
 // The reference's createRandom draw order, replayed with the same
 // standard-library engine and distribution the reference uses.
-int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
+// `given`: draw from the caller's generator instead of std::mt19937(seed_base + agent) (one agent; bidi_init_random_generator)
+static int init_random_impl(bidi_engine* h, int first, int count, unsigned seed_base, std::mt19937* given) {
   if (!h || first < 0 || count < 0 || first + count > h->A) return fail(h, BIDI_EINVAL, "bidi_init_random: bad agent range");
   if (h->ipc_linked) return fail(h, BIDI_EINVAL, "bidi_init_random: not after bidi_strip_link_ipc (the neighbours store into this memory): initialise the state before bidi_strip_ipc_export");
   CU(cudaSetDevice(h->device));
@@ -1922,11 +1924,10 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
   const int L = h->L, V = h->cfg.variant;
   const bidi_config& g = h->cfg;
   const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-  const int nthreads = (int)std::min<unsigned>(hw, (unsigned)std::max(1, count));
+  const int nthreads = given ? 1 : (int)std::min<unsigned>(hw, (unsigned)std::max(1, count));
   std::vector<std::vector<float>> images(nthreads);
   std::vector<std::string> errors(nthreads);
-  auto fill_agent = [&](std::vector<float>& img, unsigned seed) {
-    std::mt19937 gen(seed);
+  auto fill_agent = [&](std::vector<float>& img, std::mt19937& gen) {
     std::uniform_real_distribution<float> weightDist(g.init_min_w, g.init_max_w);
     std::uniform_real_distribution<float> inhibitionDist(g.init_min_inh, g.init_max_inh);
     std::fill(img.begin(), img.end(), 0.0f);
@@ -2012,7 +2013,8 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
       if (e != cudaSuccess) { cuerr[t] = e; return; }
       images[t].resize((size_t)h->stride);
       for (int a = first + t; a < first + count; a += nthreads) {
-        fill_agent(images[t], seed_base + (unsigned)a);
+        std::mt19937 own(seed_base + (unsigned)a);
+        fill_agent(images[t], given ? *given : own);
         e = cudaMemcpyAsync(h->d_blob + (long long)a * h->stride, images[t].data(), sizeof(float) * h->stride, cudaMemcpyHostToDevice, up);
         if (e == cudaSuccess) e = cudaStreamSynchronize(up);
         if (e != cudaSuccess) { cuerr[t] = e; break; }
@@ -2021,6 +2023,26 @@ int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) {
     });
   for (auto& t : pool) t.join();
   for (auto e : cuerr) if (e != cudaSuccess) return fail(h, BIDI_ECUDA, std::string("bidi_init_random upload: ") + cudaGetErrorString(e));
+  return BIDI_OK;
+}
+
+int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base) { return init_random_impl(h, first, count, seed_base, nullptr); }
+
+int bidi_init_random_generator(bidi_engine* h, int agent, const char* state_in, char* state_out, int state_out_cap) {
+  if (!h || !state_in) return fail(h, BIDI_EINVAL, "bidi_init_random_generator: null argument");
+  std::mt19937 gen;
+  std::istringstream is(state_in);
+  is >> gen;
+  if (is.fail()) return fail(h, BIDI_EINVAL, "bidi_init_random_generator: state_in is not the text form of a std::mt19937");
+  const int rc = init_random_impl(h, agent, 1, 0u, &gen);
+  if (rc) return rc;
+  if (state_out) {
+    std::ostringstream os;
+    os << gen;
+    const std::string t = os.str();
+    if ((int)t.size() + 1 > state_out_cap) return fail(h, BIDI_EINVAL, "bidi_init_random_generator: state_out too small");
+    memcpy(state_out, t.c_str(), t.size() + 1);
+  }
   return BIDI_OK;
 }
 

@@ -23,6 +23,7 @@ ABI = {
     "bidi_create": (C.c_int, [C.POINTER(Config), C.POINTER(LayerDesc), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "bidi_destroy": (None, [C.c_void_p]),
     "bidi_init_random": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_uint]),
+    "bidi_init_random_generator": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int]),
     "bidi_num_agents": (C.c_int, [C.c_void_p]),
     "bidi_num_inputs": (C.c_int, [C.c_void_p]),
     "bidi_num_columns": (C.c_int, [C.c_void_p]),

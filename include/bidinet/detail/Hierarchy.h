@@ -6,8 +6,8 @@
 // (RunnerMain.cpp:139-154,239-249; Experiment_Prediction.cpp:124-148).  The facade
 // classes keep those names and signatures and forward to the extern "C" engine
 // (include/bidinet_b200.h).  Differences a caller can observe are listed in
-// INTEGRATION.md (getLayers() is replaced by per-array accessors; objects are
-// move-only because they own device memory).
+// INTEGRATION.md (getLayers() returns a read-only host snapshot of the state, the weight lists come
+// through per-array accessors; objects are move-only because they own device memory).
 #pragma once
 
 #include <random>
@@ -25,8 +25,69 @@ inline void check(int rc, bidi_engine* h, const char* what) {
   if (rc != BIDI_OK) throw std::runtime_error(std::string(what) + ": " + bidi_last_error(h));
 }
 
+// Host mirror of what the reference's callers read through getLayers() (sdr/IPredictiveRSDR.h:83-131,
+// sdr/PredictiveRSDR.h:63-104, neo/PredictiveHierarchy.h:82-132, neo/Agent.h:106-170; read by sdr/QPRSDR.cpp:123,
+// sdr/ICSRL.cpp:89, vis/CSRLVisualizer.cpp:58): per layer the coder's read accessors (`_sdr`) and the prediction nodes'
+// scalars.  The state lives in device memory; the mirror is downloaded on the first getLayers() after a step.
+struct CoderMirror {
+  int _visibleWidth = 0, _visibleHeight = 0, _hiddenWidth = 0, _hiddenHeight = 0;
+  std::vector<float> _visibleState, _visibleRecon, _hiddenState, _hiddenStatePrev;
+  float getVisibleRecon(int index) const { return _visibleRecon[(size_t)index]; }
+  float getVisibleRecon(int x, int y) const { return getVisibleRecon(x + y * _visibleWidth); }
+  float getVisibleState(int index) const { return _visibleState[(size_t)index]; }
+  float getVisibleState(int x, int y) const { return getVisibleState(x + y * _visibleWidth); }
+  float getHiddenState(int index) const { return _hiddenState[(size_t)index]; }
+  float getHiddenState(int x, int y) const { return getHiddenState(x + y * _hiddenWidth); }
+  float getHiddenStatePrev(int index) const { return _hiddenStatePrev[(size_t)index]; }
+  float getHiddenStatePrev(int x, int y) const { return getHiddenStatePrev(x + y * _hiddenWidth); }
+  int getNumVisible() const { return _visibleWidth * _visibleHeight; }
+  int getNumHidden() const { return _hiddenWidth * _hiddenHeight; }
+  int getVisibleWidth() const { return _visibleWidth; }
+  int getVisibleHeight() const { return _visibleHeight; }
+  int getHiddenWidth() const { return _hiddenWidth; }
+  int getHiddenHeight() const { return _hiddenHeight; }
+};
+struct PredictionNodeMirror {
+  float _state = 0.0f, _statePrev = 0.0f, _activation = 0.0f, _activationPrev = 0.0f, _baseline = 0.0f;
+};
+struct LayerMirror {
+  CoderMirror _sdr;
+  std::vector<PredictionNodeMirror> _predictionNodes;
+};
+
 class Hierarchy {
 public:
+  typedef LayerMirror Layer;
+  typedef PredictionNodeMirror PredictionNode;
+  // getLayers() of the reference classes: a read-only snapshot of the current state (see LayerMirror)
+  const std::vector<Layer>& getLayers() const {
+    if (!_layersFresh) {
+      const int L = _cfg.n_layers;
+      _layers.resize((size_t)L);
+      for (int l = 0; l < L; l++) {
+        Layer& y = _layers[(size_t)l];
+        y._sdr._visibleWidth = l == 0 ? _cfg.in_width : _descs[(size_t)l - 1].width;
+        y._sdr._visibleHeight = l == 0 ? _cfg.in_height : _descs[(size_t)l - 1].height;
+        y._sdr._hiddenWidth = _descs[(size_t)l].width; y._sdr._hiddenHeight = _descs[(size_t)l].height;
+        y._sdr._visibleState = optArray(BIDI_VIS_INPUT, l); y._sdr._visibleRecon = optArray(BIDI_VIS_RECON, l);
+        y._sdr._hiddenState = optArray(BIDI_HID_STATE, l); y._sdr._hiddenStatePrev = optArray(BIDI_HID_STATE_PREV, l);
+        const std::vector<float> s = optArray(BIDI_P_STATE, l), sp = optArray(BIDI_P_STATE_PREV, l), a = optArray(BIDI_P_ACTIVATION, l),
+                                 ap = optArray(BIDI_P_ACTIVATION_PREV, l), b = optArray(BIDI_P_BASELINE, l);
+        y._predictionNodes.assign(s.size(), PredictionNode());
+        for (size_t i = 0; i < s.size(); i++) {
+          PredictionNode& n = y._predictionNodes[i];
+          n._state = s[i];
+          if (i < sp.size()) n._statePrev = sp[i];
+          if (i < a.size()) n._activation = a[i];
+          if (i < ap.size()) n._activationPrev = ap[i];
+          if (i < b.size()) n._baseline = b[i];
+        }
+      }
+      _layersFresh = true;
+    }
+    return _layers;
+  }
+
   Hierarchy() = default;
   Hierarchy(const Hierarchy&) = delete;
   Hierarchy& operator=(const Hierarchy&) = delete;
@@ -34,8 +95,8 @@ public:
   Hierarchy& operator=(Hierarchy&& o) noexcept { swap(o); return *this; }
   ~Hierarchy() { if (_h) bidi_destroy(_h); }
 
-  // Serialised state in the reference's order (bidi_array in bidinet_b200.h); stands in
-  // for getLayers(), whose array-of-structs cannot be exposed from device memory.
+  // Serialised state in the reference's order (bidi_array in bidinet_b200.h): everything getLayers() does not
+  // mirror (the connection lists' weights and traces, thresholds, the columns' arrays).
   std::vector<float> getArray(int which, int layer) const {
     const long long n = bidi_array_len(_h, which, layer);
     std::vector<float> out(n > 0 ? (size_t)n : 0);
@@ -45,6 +106,14 @@ public:
   bidi_engine* engine() const { return _h; }
 
 protected:
+  mutable std::vector<Layer> _layers;
+  mutable bool _layersFresh = false;
+  std::vector<float> optArray(int which, int layer) const {  // empty when the variant does not have the array
+    const long long n = bidi_array_len(_h, which, layer);
+    std::vector<float> out(n > 0 ? (size_t)n : 0);
+    if (n > 0) check(bidi_get_array(_h, 0, which, layer, out.data(), n), _h, "bidi_get_array");
+    return out;
+  }
   bidi_engine* _h = nullptr;
   bidi_config _cfg{};
   std::vector<bidi_layer_desc> _descs;
@@ -55,6 +124,7 @@ protected:
   void swap(Hierarchy& o) {
     std::swap(_h, o._h); std::swap(_cfg, o._cfg); _descs.swap(o._descs); _inputs.swap(o._inputs);
     _predictions.swap(o._predictions); std::swap(_predictionsFresh, o._predictionsFresh);
+    _layers.swap(o._layers); std::swap(_layersFresh, o._layersFresh);
   }
 
   void create() {
@@ -67,6 +137,7 @@ protected:
     _inputs.assign((size_t)_cfg.in_width * _cfg.in_height, 0.0f);
     _predictions.assign(_inputs.size(), 0.0f);
     _predictionsFresh = true;
+    _layersFresh = false;
   }
 
   std::vector<int> counts(int which, int layer, int units) const {
@@ -134,6 +205,7 @@ protected:
     check(bidi_set_inputs(_h, _inputs.data()), _h, "bidi_set_inputs");
     check(bidi_step(_h, reward, u, v, learn ? 1 : 0), _h, "bidi_step");
     _predictionsFresh = false;
+    _layersFresh = false;
   }
   float prediction(int index) const {
     if (!_predictionsFresh) {

@@ -68,6 +68,7 @@ public:
     bidinet::detail::check(bidi_set_inputs(_h, _inputs.data()), _h, "bidi_set_inputs");
     bidinet::detail::check(bidi_step_generate(_h, normals.data(), noise), _h, "bidi_step_generate");
     _predictionsFresh = false;
+    _layersFresh = false;
   }
 
   void setInput(int index, float value) { _inputs[(size_t)index] = value; }

@@ -185,6 +185,13 @@ void bidi_destroy(bidi_engine* h);
  * neo/Column.cpp:22-43).
  */
 int bidi_init_random(bidi_engine* h, int first, int count, unsigned seed_base);
+/*
+ * The same replay for ONE agent, drawing from the CALLER's generator: `state_in` is the text form of a std::mt19937
+ * (operator<<: 624 words and the position), `state_out` (capacity state_out_cap, 8 KiB is enough; may be NULL) receives
+ * the generator's state after createRandom's draws, so that a caller-side std::mt19937 continues exactly where the
+ * reference's would (deep/CSRL.cpp:11-187 draws ~1e5 values per hierarchy in an order only the engine tabulates).
+ */
+int bidi_init_random_generator(bidi_engine* h, int agent, const char* state_in, char* state_out, int state_out_cap);
 
 /* Shape queries. */
 int bidi_num_agents(const bidi_engine* h);

@@ -11,6 +11,7 @@
 #include <sdr/QPRSDR.h>
 #include <neo/PredictiveHierarchy.h>
 #include <neo/Agent.h>
+#include <deep/CSRL.h>
 
 #include <algorithm>
 #include <cmath>
@@ -32,6 +33,21 @@ static void hashFloat(float v) {
 template <class H> static void report(const char* tag, int step, const H& h, int n) {
   for (int i = 0; i < n; i++) hashFloat(h.getPrediction(i));
   std::printf("%s %d %016llx\n", tag, step, g_hash);
+}
+
+// what the reference's own callers read through getLayers() (sdr/QPRSDR.cpp:123, sdr/ICSRL.cpp:89,
+// vis/CSRLVisualizer.cpp:58): the coder's geometry and hidden states, the prediction nodes' states
+template <class H> static void reportLayers(const char* tag, const H& h) {
+  for (size_t l = 0; l < h.getLayers().size(); l++) {
+    const auto& layer = h.getLayers()[l];
+    for (int i = 0; i < layer._sdr.getNumHidden(); i++) hashFloat(layer._sdr.getHiddenState(i));
+    for (size_t i = 0; i < layer._predictionNodes.size(); i++) {
+      hashFloat(layer._predictionNodes[i]._state);
+      hashFloat(layer._predictionNodes[i]._statePrev);
+    }
+    std::printf("%s layer %d: visible %dx%d hidden %dx%d, %d prediction nodes, %016llx\n", tag, (int)l, layer._sdr.getVisibleWidth(),
+                layer._sdr.getVisibleHeight(), layer._sdr.getHiddenWidth(), layer._sdr.getHiddenHeight(), (int)layer._predictionNodes.size(), g_hash);
+  }
 }
 
 int main() {
@@ -57,6 +73,7 @@ int main() {
         report("iprsdr", iter * 10 + i, prsdr, 4);
       }
     hashFloat(avgError);
+    reportLayers("iprsdr", prsdr);
     std::printf("iprsdr avgError %.9g generator %u\n", avgError, (unsigned)generator());
   }
   {  // sdr::PredictiveRSDR on a 16x16 moving pattern, setInput(x, y, v)
@@ -73,6 +90,7 @@ int main() {
       prsdr.simStep(t % 7 != 6);
       report("prsdr", t, prsdr, 256);
     }
+    reportLayers("prsdr", prsdr);
     std::printf("prsdr generator %u\n", (unsigned)generator());
   }
   {  // neo::PredictiveHierarchy, non-square input, prediction fed back when not learning
@@ -92,6 +110,7 @@ int main() {
       ph.simStepGenerate(generator, 0.2f);
       report("neoph-generate", t, ph, 63);
     }
+    reportLayers("neoph", ph);
     std::printf("neoph generator %u\n", (unsigned)generator());
   }
   {  // RunnerMain.cpp:139-154,235-251, headless: sine state vector instead of the Box2D runner
@@ -119,6 +138,7 @@ int main() {
       agent.simStep(reward / outputCount - 0.5f, generator);
       report("agent", steps, agent, 64);
     }
+    reportLayers("agent", agent);
     std::printf("agent generator %u\n", (unsigned)generator());
   }
   {  // sdr::QPRSDR: states in, actions fed back as inputs, reward, the way its createRandom/simStep/getAction are meant
@@ -147,6 +167,38 @@ int main() {
     std::printf("qprsdr generator %u\n", (unsigned)generator());
     agent->~QPRSDR();
     std::free(storage);
+  }
+  {  // deep::CSRL: state inputs set by the caller, inputs of type _action left to the hierarchy (it feeds its own exploratory
+     // outputs back, deep/CSRL.cpp:441-448), reward from the first action (deep/CSRL.h:245-267)
+    std::mt19937 generator(777);
+    std::vector<deep::CSRL::LayerDesc> layerDescs(2);
+    layerDescs[0]._width = 6; layerDescs[0]._height = 6;
+    layerDescs[1]._width = 3; layerDescs[1]._height = 3;
+    for (size_t l = 0; l < layerDescs.size(); l++) {
+      deep::CSRL::LayerDesc& d = layerDescs[l];
+      d._receptiveRadius = 2; d._recurrentRadius = 1; d._lateralRadius = 2; d._predictiveRadius = 1; d._feedBackRadius = 1;
+      d._numRecurrentInputs = 2 + (int)l; d._sdrIterSettle = 5; d._sdrIterMeasure = 2; d._cellsPerColumn = 4 + (int)l;
+      d._actionDeriveIterations = 5;
+    }
+    std::vector<deep::CSRL::InputType> inputTypes(30, deep::CSRL::_state);
+    for (int i = 20; i < 26; i++) inputTypes[i] = deep::CSRL::_action;
+    deep::CSRL csrl;
+    csrl._numRecurrentInputs = 2; csrl._cellsPerColumn = 3; csrl._actionDeriveIterations = 6; csrl._sdrIterSettle = 4; csrl._sdrIterMeasure = 2;
+    csrl.createRandom(6, 5, 2, inputTypes, layerDescs, -0.3f, 0.3f, 0.01f, 0.05f, 0.05f, generator);
+    std::printf("csrl created, generator %u\n", (unsigned)generator());
+    for (int t = 0; t < 30; t++) {
+      for (int i = 0; i < 30; i++)
+        if (inputTypes[i] == deep::CSRL::_state) csrl.setInput(i, 0.5f + 0.5f * std::sin(0.2f * t + 0.7f * i));
+      const float reward = csrl.getPrediction(20) - csrl.getPrediction(21);
+      csrl.simStep(reward, generator, t % 6 != 5);
+      if (std::getenv("DEMO_VERBOSE")) {
+        std::printf("  reward %.9g predictions", reward);
+        for (int i = 0; i < 30; i++) std::printf(" %.9g", csrl.getPrediction(i));
+        std::printf("\n");
+      }
+      report("csrl", t, csrl, 30);
+    }
+    std::printf("csrl generator %u\n", (unsigned)generator());
   }
   return 0;
 }
