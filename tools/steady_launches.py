@@ -42,8 +42,10 @@ def main():
     ls = list(launches.values())
     ls = ls[len(ls) // 2:]  # the second of the two captured steps
     T = sum(l["gpu__time_duration.sum"] for l in ls)
-    print("| # | kernel | us | warp instructions | DRAM read MB | DRAM written MB | TB/s | share |")
-    print("|---:|---|---:|---:|---:|---:|---:|---:|")
+    WF, BC = "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"
+    banks = all(WF in l and BC in l for l in ls)  # the shared-memory bank-conflict counters, when the capture has them
+    print("| # | kernel | us | warp instructions | DRAM read MB | DRAM written MB | TB/s | share |" + (" shared-memory wavefronts | of them bank-conflict replays |" if banks else ""))
+    print("|---:|---|---:|---:|---:|---:|---:|---:|" + ("---:|---:|" if banks else ""))
     tot_b = col_b = col_t = 0.0
     col_n = 0
     for k, l in enumerate(ls):
@@ -52,7 +54,8 @@ def main():
         if l["name"].startswith("k_columns"):
             col_b += rd + wr; col_t += t; col_n += 1
         print("| %d | %s | %.1f | %d | %.1f | %.1f | %.2f | %.1f%% |" % (k, l["name"], t, l["smsp__inst_executed.sum"], rd / 1e6, wr / 1e6,
-                                                                       (rd + wr) / t / 1e6, 100 * t / T))
+                                                                       (rd + wr) / t / 1e6, 100 * t / T)
+              + (" %d | %.1f%% |" % (l[WF], 100.0 * l[BC] / max(1.0, l[WF])) if banks else ""))
     print("| | **step** | %.1f | | | %.1f total | %.2f | 100%% |" % (T, tot_b / 1e6, tot_b / T / 1e6))
     print()
     print("k_columns*: %d launches per step, %.1f MB of DRAM traffic per step = %.3f MB per agent-step, %.1f%% of the step's time."
