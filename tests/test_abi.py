@@ -67,3 +67,23 @@ def test_product_does_not_touch_the_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(ROOT, "tools", f)).read()
             assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_facade_headers_build_and_link_against_the_abi():
+    """The drop-in C++ facade (include/bidinet/{sdr,neo,deep}/*.h) compiles and links against the C-ABI library on a box
+    without a GPU: one demo source drives every facade class (tests/facade/facade_demo.cpp; it is RUN by the gpu tests)."""
+    import subprocess
+    d = os.path.join(ROOT, "tests", "facade")
+    subprocess.check_call(["make", "-C", d, "facade_demo", "batch_demo"])
+    assert os.path.exists(os.path.join(d, "facade_demo"))
+
+
+def test_facade_golden_is_what_the_reference_prints():
+    """tests/golden/facade_demo.txt is the output of the same demo source built against the unmodified reference
+    (only where /root/reference exists: this container; the GPU box compares the facade build with the committed text)."""
+    import subprocess
+    if not os.path.isdir("/root/reference/BIDInet/source"):
+        pytest.skip("/root/reference absent")
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "facade"), "ref"])
+    out = subprocess.check_output([os.path.join(ROOT, "oracle", "_ref", "facade_demo_ref")]).decode()
+    assert out == open(os.path.join(ROOT, "tests", "golden", "facade_demo.txt")).read()
