@@ -314,18 +314,23 @@ def run_c5(args, rank, world, local_rank):
     ms = _max_over_ranks(ms, dist if world > 1 else None, "cuda")
     value = K / (ms * 1e-3)
 
-    # e2e: the whole frame goes to every part from host memory, the owned prediction rows come back
+    # e2e: the whole frame goes to every part from host memory, the owned prediction rows come back -- through the
+    # engine's page-locked staging buffers used in place (bidi_host_inputs / bidi_host_predictions), as in the other
+    # workloads: the host<->device copies are made every step, a second host-side copy of the 4 MB frame is not
+    x, pred = eng.host_inputs(), eng.host_predictions()
     for _ in range(W):
-        eng.set_inputs(frames[t % T])
+        np.copyto(x[0], frames[t % T])
+        eng.set_inputs(x)
         eng.step()
-        eng.get_predictions()
+        eng.get_predictions(out=pred)
         t += 1
     barrier()
     t0 = time.perf_counter()
     for _ in range(K):
-        eng.set_inputs(frames[t % T])
+        np.copyto(x[0], frames[t % T])
+        eng.set_inputs(x)
         eng.step()
-        pred = eng.get_predictions()
+        eng.get_predictions(out=pred)
         t += 1
     eng.sync()
     e2e_s = _max_over_ranks(time.perf_counter() - t0, dist if world > 1 else None, "cuda")
