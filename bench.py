@@ -579,7 +579,7 @@ def main():
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--variant", default="kwinners", choices=["kwinners", "iterative"], help="c1 / c4: which reference class")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0, help="c1 / c4: CPU time of the one-thread baseline sample")
-    ap.add_argument("--e2e-groups", type=int, default=2,
+    ap.add_argument("--e2e-groups", type=int, default=3,
                     help="c3: agent groups the end-to-end loop steps in turn (host I/O of one overlaps the GPU step of the other)")
     ap.add_argument("--single-process", action="store_true",
                     help="c3 over --gpus N devices from ONE process (bidi_create_sharded) instead of one torchrun rank per GPU")
