@@ -97,6 +97,50 @@ __device__ __forceinline__ void for_each_slot_batched(const WinDev& w, int ux, i
 struct WE { float w, e; };
 struct WTE { float w, tr, e; };
 
+// learn_dot (below) for windows that span the target grid (w.absx && w.absy: the RunnerMain hierarchy): slot (sx, sy) IS
+// target cell (sx, sy), so there are no clamps and no coordinate translation, and every address is a running pointer --
+// the generic body spends ~50 instructions per connection on index arithmetic, which made k_predict / k_predict_input
+// issue-bound at 1.9 TB/s.  Same loads, same operations, same order; prev / now are the source planes themselves.
+template <int NB, bool SKIP_ZERO>
+__device__ __forceinline__ float learn_dot_abs(const WinDev& w, int ux, int uy, float* __restrict__ plane, int U, int i, bool do_learn,
+                                               float k, float sum, const float* __restrict__ prev, const float* __restrict__ now) {
+  const SlotBox b = slot_box(w, ux, uy);
+  float* wc = plane + i;                       // slot (sx, 0) of this unit; a slot further down the column is U floats on
+  const int dyn = w.dyn, tw = w.tw;
+  for (int sx = 0; sx < w.dxn; sx++, wc += (size_t)dyn * U) {
+    const bool okx = do_learn && sx >= b.sx0 && sx <= b.sx1;
+    const bool xcl = w.excl && sx == b.cx;
+    const float* np = now + sx;                // target (sx, sy) = plane[sx + sy*tw]
+    const float* pp = prev + sx;
+    float* wq = wc;
+    for (int sy0 = 0; sy0 < dyn; sy0 += NB, wq += (size_t)NB * U, np += NB * tw, pp += NB * tw) {
+      float wv[NB], pv[NB], nv[NB];
+      if (sy0 + NB <= dyn) {
+#pragma unroll
+        for (int q = 0; q < NB; q++) { wv[q] = wq[(size_t)q * U]; nv[q] = np[q * tw]; pv[q] = do_learn ? pp[q * tw] : 0.0f; }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NB; q++) {
+          const int qq = min(q, dyn - 1 - sy0);
+          wv[q] = wq[(size_t)qq * U]; nv[q] = np[qq * tw]; pv[q] = do_learn ? pp[qq * tw] : 0.0f;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const int sy = sy0 + q;
+        if (sy < dyn) {
+          bool ok = okx && sy >= b.sy0 && sy <= b.sy1 && !(xcl && sy == b.cy);
+          if (SKIP_ZERO && pv[q] == 0.0f) ok = false;
+          float wn = wv[q];
+          if (ok) { wn = wv[q] + k * pv[q]; wq[(size_t)q * U] = wn; }
+          sum += nv[q] * wn;
+        }
+      }
+    }
+  }
+  return sum;
+}
+
 // The delta rule w += k*prev(target) and the product sum += now(target)*w that uses the updated weight, over
 // the whole slot box in ONE pass: every weight is read once, NB slots' loads in flight together.  The rule
 // touches only the unit's own connections (and, with SKIP_ZERO, only those whose source is not zero: k*0 = +-0
@@ -480,9 +524,14 @@ __global__ void k_predict(EngineDev P, LayerDev L, int l, int learn, long long u
     upd = err != 0.0f;
   }
   float activation = 0.0f;
-  if (!top)
-    activation = learn_dot<8, true>(L.fb, ux, uy, wfb, U, i, upd, kfb, activation, [&](int t) { return up_prev[t]; }, [&](int t) { return up_state[t]; });
-  activation = learn_dot<8, true>(L.pred, ux, uy, wpr, U, i, upd, kpr, activation, [&](int t) { return sprev[t]; }, [&](int t) { return state[t]; });
+  if (!top && L.fb.r >= 0) {
+    if (L.fb.absx && L.fb.absy) activation = learn_dot_abs<8, true>(L.fb, ux, uy, wfb, U, i, upd, kfb, activation, up_prev, up_state);
+    else activation = learn_dot<8, true>(L.fb, ux, uy, wfb, U, i, upd, kfb, activation, [&](int t) { return up_prev[t]; }, [&](int t) { return up_state[t]; });
+  }
+  if (L.pred.r >= 0) {
+    if (L.pred.absx && L.pred.absy) activation = learn_dot_abs<8, true>(L.pred, ux, uy, wpr, U, i, upd, kpr, activation, sprev, state);
+    else activation = learn_dot<8, true>(L.pred, ux, uy, wpr, U, i, upd, kpr, activation, [&](int t) { return sprev[t]; }, [&](int t) { return state[t]; });
+  }
   B[L.p_act + i] = activation;
   if (P.variant != BIDI_KWINNERS) B[L.p_state + i] = bidi_clamp01(activation);
 }
@@ -502,7 +551,8 @@ __global__ void k_predict_input(EngineDev P, LayerDev L, int learn, long long p0
     k = L.learn_fb * err; // learn_fb of the input layer = _learnInputFeedBack
   }
   float activation = 0.0f;
-  activation = learn_dot<8, false>(L.fb, ux, uy, wfb, U, i, learn != 0, k, activation, [&](int t) { return p0_prev[t]; }, [&](int t) { return p0[t]; });
+  if (L.fb.r >= 0 && L.fb.absx && L.fb.absy) activation = learn_dot_abs<8, false>(L.fb, ux, uy, wfb, U, i, learn != 0, k, activation, p0_prev, p0);
+  else activation = learn_dot<8, false>(L.fb, ux, uy, wfb, U, i, learn != 0, k, activation, [&](int t) { return p0_prev[t]; }, [&](int t) { return p0[t]; });
   B[L.p_act + i] = activation;
   P.pred_out[(long long)a * P.n_in + i] = activation;
 }
