@@ -165,6 +165,13 @@ class Engine:
         count = self.n_agents - first if count is None else count
         self._check(self.lib.bidi_init_random(self.h, first, count, seed_base), "bidi_init_random")
 
+    def init_random_generator(self, state_text, agent=0):
+        """createRandom's draws for ONE agent from the caller's generator: `state_text` is the text form of a std::mt19937
+        (operator<<: 624 words and the position); returns the generator's text form after the draws."""
+        out = C.create_string_buffer(16384)
+        self._check(self.lib.bidi_init_random_generator(self.h, agent, state_text.encode(), out, len(out)), "bidi_init_random_generator")
+        return out.value.decode()
+
     # ---- serialised state
     def array_len(self, which, layer):
         return int(self.lib.bidi_array_len(self.h, ARRAY[which] if isinstance(which, str) else which, layer))

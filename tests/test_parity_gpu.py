@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from bidinet_b200 import Engine
+from bidinet_b200.engine import BidiError
 from bidinet_b200 import config as cf
 from oracle.pyoracle import OracleHierarchy
 
@@ -41,6 +42,26 @@ def test_init_random_matches_oracle(case):
     for a in (0, 2):
         orc = OracleHierarchy(cfg, ld, 1234 + a)
         assert diff_states(orc.state(), eng.state(agent=a)) == [], "agent %d" % a
+
+
+@pytest.mark.parametrize("case", small_cases(), ids=lambda c: c[0])
+def test_init_random_from_the_callers_generator(case):
+    """bidi_init_random_generator: createRandom's draws taken from a caller-side std::mt19937 handed over as text (the
+    deep::CSRL facade's createRandom).  A generator seeded like bidi_init_random's gives the same weights; the state
+    that comes back is a valid generator that has moved on; a malformed state is refused."""
+    name, cfg, ld, _, _ = case
+    seeded = Engine(cfg, ld, n_agents=1, seed=1234)
+    eng = Engine(cfg, ld, n_agents=2)
+    key = np.random.RandomState(1234).get_state()[1]       # init_genrand(1234): the state of std::mt19937(1234)
+    text = " ".join(str(int(k)) for k in key) + " 624"
+    after = eng.init_random_generator(text, agent=1)
+    assert diff_states(seeded.state(agent=0), eng.state(agent=1)) == []
+    words = after.split()
+    assert len(words) == 625 and after != text
+    eng.init_random_generator(after, agent=0)               # the advanced state is accepted again
+    assert diff_states(eng.state(agent=0), eng.state(agent=1)) != []
+    with pytest.raises(BidiError):
+        eng.init_random_generator("1 2 3 not a generator")
 
 
 @pytest.mark.parametrize("path", ["default", "fused_general", "per_phase_tiles", "per_phase_threads", "per_phase_grid"])
