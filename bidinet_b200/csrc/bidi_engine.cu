@@ -212,8 +212,6 @@ struct bidi_engine {
   std::vector<int> q_act_index, q_a_input;
   float* d_qmask = nullptr; int* d_qtables = nullptr;
   bool use_tma_box = true;                         // option "tma_box": k_g_kw_activate's input box through a TMA tensor map
-  int dbg_act = 0;                                 // timing experiments on k_g_kw_activate (results are then wrong): 2 skip the dense sum, 4 skip the recurrent sum
-  int col_extra_smem = 0;                          // experiment: pad the column kernel's shared memory to lower its residency
   bool strip_use_graph = true;                     // record the split step (NCCL exchanges included) into a CUDA graph
   cudaEvent_t strip_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t strip_done = nullptr;
@@ -584,7 +582,7 @@ void record_columns(Recorder& R, int l) {
   const int ppw = columns_pairs_per_warp(C);
   const int n_pairs = (C.n + 1) / 2;
   const long long warps = (long long)h->A * ((n_pairs + ppw - 1) / ppw);
-  const size_t smem = columns_smem_bytes(C) + (size_t)h->col_extra_smem;
+  const size_t smem = columns_smem_bytes(C);
   R.before("columns");
   // x = pair (fastest: consecutive CTAs are one agent's pairs), (y, z) = agent
   const unsigned ay = (unsigned)std::min(h->A, 32768);
@@ -636,7 +634,7 @@ void launch_kw_activate(bidi_engine* h, cudaStream_t st, const bidi_engine::Grid
   if (blocks <= 0) return;
   const size_t smem = act_smem_bytes(G);
   const int dyn = (G.act_dense && Y.ff.dxn == Y.ff.dyn && !Y.ff.absx && !Y.ff.absy) ? Y.ff.dyn : 0;
-#define BIDI_ACT(D) bidi::k_g_kw_activate<D><<<(unsigned)blocks, 32, smem, st>>>(h->P, Y, l, G.act_dense | (G.act_dense ? h->dbg_act : 0), G.act_slab, G.act_box, G.act_cap, h->act_tmap, G.tm_bw, G.tm_bh)
+#define BIDI_ACT(D) bidi::k_g_kw_activate<D><<<(unsigned)blocks, 32, smem, st>>>(h->P, Y, l, G.act_dense, G.act_slab, G.act_box, G.act_cap, h->act_tmap, G.tm_bw, G.tm_bh)
   switch (dyn) {
     case 5: BIDI_ACT(5); break;
     case 7: BIDI_ACT(7); break;
@@ -2379,15 +2377,6 @@ int bidi_set_option(bidi_engine* h, const char* name, int value) {
     if (rc) return rc;
   }
   else if (std::string(name) == "strip_graph") h->strip_use_graph = value != 0;
-  else if (std::string(name) == "col_extra_smem") {
-    h->col_extra_smem = value;
-    size_t smem = 0;
-    for (auto& D : h->layers) if (D.col.n > 0) smem = std::max(smem, columns_smem_bytes(D.col));
-    CU(cudaFuncSetAttribute(bidi::k_columns16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
-    CU(cudaFuncSetAttribute(bidi::k_columns16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
-    CU(cudaFuncSetAttribute(bidi::k_columns16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem + value)));
-  }
-  else if (std::string(name) == "dbg_act") h->dbg_act = value;
   else if (std::string(name) == "tma_box") {
     h->use_tma_box = value != 0;
     int rc = select_grid_kernels(h);

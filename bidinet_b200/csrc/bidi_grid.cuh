@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, i
       const int k = 32 * t + lane, by = fast_div(k, inv_w), gx = bf.x0 + k - by * bf.w, gy = bf.y0 + by;
       xv[t] = (k < n && gx >= 0 && gx < wf.tw && gy >= 0 && gy < wf.th) ? x[gx + gy * wf.tw] : 0.0f;
     }
-    const int n_rec = (wr.r >= 0 && !(dense_ff & 4)) ? compact(sprev, br, wr.tw, wr.th) : 0;
+    const int n_rec = (wr.r >= 0) ? compact(sprev, br, wr.tw, wr.th) : 0;
 #pragma unroll
     for (int t = 0; t < NB; t++) { const int k = 32 * t + lane; if (k < n) xbox[k] = xv[t]; }
     for (int k0 = 32 * NB; k0 < n; k0 += 32 * NB) {  // (larger boxes: the rest, trip by trip)
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(32) k_g_kw_activate(EngineDev P, LayerDev L, i
     const float* rrow = B + wr.w_off + (long long)(T.ok ? T.unit : 0) * wr.row_pitch;
     const ListHits<8> H = (T.ok && wr.r >= 0) ? list_hits<8>(wr, ent, n_rec, T.ux, uy, rrow) : ListHits<8>{};
     mbar_wait(bar, 0);
-    if (T.ok && !(dense_ff & 2)) {
+    if (T.ok) {
       const float* s0 = xbox + (wf.absx ? 0 : wf.cx[T.ux] - wf.r - bf.x0) + (wf.absy ? 0 : wf.cy[uy] - wf.r - bf.y0) * bf.w;
       const float* wrow = slab + lane * wf.row_pitch;
       if (DYN > 0) {

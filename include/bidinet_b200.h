@@ -357,9 +357,17 @@ int bidi_save_snapshot(bidi_engine* h, const char* path);
 int bidi_load_snapshot(bidi_engine* h, const char* path);
 
 /*
- * Engine options.  "force_phase_kernels" = 1: run one kernel per phase even where
- * the fused per-agent coder kernel applies (both paths give identical results; the
- * tests compare them).
+ * Engine options: which of several kernel families, all with identical results, runs a layer (the parity tests hold
+ * every one to the oracle; the defaults are the fastest choice per layer shape).
+ *   "force_phase_kernels" 1: one kernel per phase even where a fused per-agent coder kernel applies
+ *   "dense_coder"         0: the general fused coder kernel where the dense-row one was chosen
+ *   "tile_kernels"        0: thread-per-unit kernels where the tile kernels (small launches) were chosen
+ *   "grid_kernels"        0 never / 1 wide, untiled k-winners layers (default) / 2 every k-winners layer
+ *   "persist_coder"       0: per-phase kernels for the large layers of a single iterative agent
+ *   "tma_box"             0: k_g_kw_activate stages its input box with plain loads instead of the tiled TMA load
+ *   "overlap_learn"       0: learning and reconstruction phases stay on the step's main graph branch
+ *   "strip_graph"         0: a split layer's step is issued launch by launch instead of as one graph
+ * Changing an option re-records the step graph and converts the affected layers' weight layout in place.
  */
 int bidi_set_option(bidi_engine* h, const char* name, int value);
 
