@@ -101,12 +101,14 @@ struct WTE { float w, tr, e; };
 // target cell (sx, sy), so there are no clamps and no coordinate translation, and every address is a running pointer --
 // the generic body spends ~50 instructions per connection on index arithmetic, which made k_predict / k_predict_input
 // issue-bound at 1.9 TB/s.  Same loads, same operations, same order; prev / now are the source planes themselves.
-template <int NB, bool SKIP_ZERO>
-__device__ __forceinline__ float learn_dot_abs(const WinDev& w, int ux, int uy, float* __restrict__ plane, int U, int i, bool do_learn,
-                                               float k, float sum, const float* __restrict__ prev, const float* __restrict__ now) {
+// DYN: the window height when it is 4 or 8 (the RunnerMain layers: every column of slots is then one full batch with no
+// remainder test), else 0
+template <int NB, bool SKIP_ZERO, int DYN>
+__device__ __forceinline__ float learn_dot_abs_n(const WinDev& w, int ux, int uy, float* __restrict__ plane, int U, int i, bool do_learn,
+                                                 float k, float sum, const float* __restrict__ prev, const float* __restrict__ now) {
   const SlotBox b = slot_box(w, ux, uy);
   float* wc = plane + i;                       // slot (sx, 0) of this unit; a slot further down the column is U floats on
-  const int dyn = w.dyn, tw = w.tw;
+  const int dyn = DYN ? DYN : w.dyn, tw = w.tw;
   for (int sx = 0; sx < w.dxn; sx++, wc += (size_t)dyn * U) {
     const bool okx = do_learn && sx >= b.sx0 && sx <= b.sx1;
     const bool xcl = w.excl && sx == b.cx;
@@ -139,6 +141,13 @@ __device__ __forceinline__ float learn_dot_abs(const WinDev& w, int ux, int uy, 
     }
   }
   return sum;
+}
+template <int NB, bool SKIP_ZERO>
+__device__ __forceinline__ float learn_dot_abs(const WinDev& w, int ux, int uy, float* __restrict__ plane, int U, int i, bool do_learn,
+                                               float k, float sum, const float* __restrict__ prev, const float* __restrict__ now) {
+  if (w.dyn == 8) return learn_dot_abs_n<8, SKIP_ZERO, 8>(w, ux, uy, plane, U, i, do_learn, k, sum, prev, now);
+  if (w.dyn == 4) return learn_dot_abs_n<4, SKIP_ZERO, 4>(w, ux, uy, plane, U, i, do_learn, k, sum, prev, now);
+  return learn_dot_abs_n<NB, SKIP_ZERO, 0>(w, ux, uy, plane, U, i, do_learn, k, sum, prev, now);
 }
 
 // The delta rule w += k*prev(target) and the product sum += now(target)*w that uses the updated weight, over
