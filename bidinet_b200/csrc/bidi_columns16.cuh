@@ -34,7 +34,9 @@ namespace bidi {
 __device__ __forceinline__ float lo32(u64 v) { float x, y; upk(v, x, y); return x; }
 __device__ __forceinline__ float hi32(u64 v) { float x, y; upk(v, x, y); return y; }
 
-template <int RH>
+// SMALL: every row of the layer is at most 32 inputs long (the top layer of the RunnerMain hierarchy: 16 + pad): the
+// gather and the reconstruction are unrolled for one trip instead of nine / five (their loops still cover any length).
+template <int RH, bool SMALL = false>
 __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l, ColPairTab T) {
   extern __shared__ __align__(128) float smem[];
   constexpr int CC = 16;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   if (lane == 0) mbar_init(bar, 1);
   const int in0 = !has ? 0 : (tab ? T.in_off[node] : C.in_off[node]);
   const int nin = !has ? 0 : (tab ? T.in_off[node + 1] : C.in_off[node + 1]) - in0;
-  constexpr int GT = 9;  // 144 inputs per trip
+  constexpr int GT = SMALL ? 2 : 9;  // inputs per lane of a gather trip: 144 (32) inputs per trip
   const bool staged = C.stage_n > 0;
   const int n0 = C.stage_len[0], n01 = n0 + C.stage_len[1], sn = C.stage_n;
   auto plane_off = [&](int k) -> long long {
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(32) k_columns16(EngineDev P, LayerDev L, int l
   const int n4 = SH >> 2, n2 = S >> 1;
   const u64* in2 = reinterpret_cast<const u64*>(in_s);
   u64* err2 = reinterpret_cast<u64*>(err);
-  constexpr int NP = 5;  // input pairs per lane per trip: 16*5*2 = 160 inputs
+  constexpr int NP = SMALL ? 1 : 5;  // input pairs per lane per trip: 16*5*2 = 160 (32) inputs
   for (int it = 0; it < C.iter; it++) {
     // inhibition += lat * spikePrev over the cells that spiked (the others add +-0; an absent entry adds +0,
     // which leaves a sum that started at +0 unchanged).  Done before the sweep, four loads in flight, so that

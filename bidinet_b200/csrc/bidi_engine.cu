@@ -590,6 +590,7 @@ void record_columns(Recorder& R, int l) {
   const ColPairTab& T = h->hl[l].col.tab;
   if (C.planar && C.rh == 64) bidi::k_columns16<64><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l, T);
   else if (C.planar && C.rh == 32) bidi::k_columns16<32><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l, T);
+  else if (C.planar && C.max_in <= 28) bidi::k_columns16<0, true><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l, T);
   else if (C.planar) bidi::k_columns16<0><<<pa, 32, smem, h->stream>>>(h->P, h->layers[l], l, T);
   else if (ppw == 2) bidi::k_columns<16><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
   else bidi::k_columns<32><<<grid_for(warps, BIDI_COL_WARPS), BIDI_COL_WARPS * 32, smem, h->stream>>>(h->P, h->layers[l], l);
@@ -1798,6 +1799,7 @@ int bidi_create(const bidi_config* cfg, const bidi_layer_desc* layers, int n_age
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_CREATE(cudaFuncSetAttribute(bidi::k_columns16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
